@@ -1,0 +1,89 @@
+"""Oracle pinning, layer 2: this repo's CPU restatement (oracle/orb_port.cpp) against
+(a) the committed outputs of the reference's own ORBextractor.cpp (tests/golden/orb_*.npz, always run) and
+(b) the reference compiled in place (oracle/_ref, when the prebuilt library or /root/reference is present)."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from vo_slam_test_b200 import synth
+
+from conftest import HAVE_REF_LIB
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "orb_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_port_matches_reference_golden(path):
+    g = np.load(path)
+    img = synth.make_frame(int(g["seed"]), int(g["H"]), int(g["W"]))
+    assert hashlib.sha256(img.tobytes()).hexdigest() == str(g["sha256"]), "synthetic generator drifted"
+    kps, desc = oracle.Port(int(g["nfeatures"])).extract(img)
+    assert len(kps) == len(g["kps"])
+    assert np.array_equal(kps, g["kps"])          # x, y, size, angle, response, octave, class_id: bit-exact
+    assert np.array_equal(desc, g["desc"])
+
+
+needs_ref = pytest.mark.skipif(not HAVE_REF_LIB, reason="oracle/_ref not built and /root/reference absent")
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,H,W,nf", [(21, 480, 640, 1000), (22, 480, 640, 1000), (23, 1080, 1920, 2000),
+                                         (24, 479, 641, 500), (25, 240, 320, 300), (26, 400, 420, 400)])
+def test_port_equals_compiled_reference(seed, H, W, nf):
+    img = synth.make_frame(seed, H, W)
+    kp, de = oracle.Port(nf).extract(img)
+    kr, dr = oracle.Ref(nf).extract(img)
+    assert np.array_equal(kp, kr) and np.array_equal(de, dr)
+
+
+@needs_ref
+def test_reference_parity_build_is_history_independent():
+    """With the monotonic allocator the unmodified reference is a pure function of its input."""
+    R = oracle.Ref()
+    imgs = [synth.make_frame(s) for s in (31, 32, 33)]
+    first = [R.extract(i) for i in imgs]
+    for i in (2, 0, 1, 0):
+        k, d = R.extract(imgs[i])
+        assert np.array_equal(k, first[i][0]) and np.array_equal(d, first[i][1])
+
+
+@needs_ref
+def test_octree_stage_vs_reference(port):
+    """DistributeOctTree alone (ORBextractor.cpp:545-769) on random candidate lists incl. 2-root shapes,
+    clustered points, N larger than the candidate count and tiny N."""
+    R = oracle.Ref()
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        rw = int(rng.integers(60, 900)); rh = int(rng.integers(60, 500))
+        if round(np.float32(rw) / np.float32(rh)) < 1:
+            continue
+        n = int(rng.integers(1, 3000))
+        if trial % 3 == 0:   # clustered
+            xs = np.clip(rng.normal(rw / 3, rw / 20, n), 3, rw - 4).astype(np.int32)
+            ys = np.clip(rng.normal(rh / 2, rh / 15, n), 3, rh - 4).astype(np.int32)
+        else:
+            xs = rng.integers(3, rw - 3, n).astype(np.int32); ys = rng.integers(3, rh - 3, n).astype(np.int32)
+        pts = np.unique(np.stack([ys, xs], 1), axis=0)       # distinct pixels, row-major like FAST output
+        cand = np.stack([pts[:, 1], pts[:, 0], rng.integers(7, 60, len(pts))], 1).astype(np.int32)
+        N = int(rng.choice([1, 5, 60, 217, 500, 5000]))
+        sel = port.octree(cand, rw, rh, N)
+        ref = R.octree(cand, rw, rh, N)
+        assert np.array_equal(cand[sel], ref), (trial, rw, rh, n, N)
+
+
+def test_flat_image_gives_no_keypoints(port):
+    kps, desc = port.extract(np.full((480, 640), 100, np.uint8))
+    assert len(kps) == 0 and desc.shape == (0, 32)
+
+
+def test_min_threshold_retry_fires(port):
+    """A low-contrast frame yields candidates only through the minThFAST retry (ORBextractor.cpp:820-824)."""
+    img = synth.make_frame(40)
+    low = (img.astype(np.int32) // 8 + 100).astype(np.uint8)  # contrast so low that th=20 finds almost nothing
+    n20 = len(port.fast(low, 20))
+    c = port.fast_cells(low)
+    assert n20 < 20 and len(c) > 5 * max(n20, 1)   # the candidates come from the threshold-7 retry
