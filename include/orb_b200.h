@@ -1,0 +1,182 @@
+/* orb_b200.h -- C ABI of the B200-native ORB front-end (libvoslam_b200.so).
+ *
+ * Drop-in boundary for the data-parallel front-end hot path of guisongchen/vo_slam_test:
+ *   - ORB feature extraction      reference: ORB_SLAM2::ORBextractor (include/myslam/ORBextractor.h:45-108,
+ *                                 src/ORBextractor.cpp:1051-1112 operator())
+ *   - binary-descriptor matching  reference: myslam::Matcher (include/myslam/matcher.h:16-37,
+ *                                 src/matcher.cpp) and the Frame grid index (src/frame.cpp:72-97,199-247)
+ *
+ * Plain C: pointers and sizes only, no C++/torch/OpenCV types.  Every function returns an int status
+ * (ORBX_OK == 0, negative == error) and never throws.  "host" entry points take host pointers and do
+ * the H2D/D2H copies themselves; "_device" entry points take device pointers that are already resident
+ * and run on the caller's CUDA stream (cudaStream_t passed as void*; NULL = default stream).
+ * A handle is not re-entrant (like the reference extractor: ORBextractor.h:85): one handle per thread.
+ * There is NO CPU fallback: without a CUDA device every compute entry point returns ORBX_ERR_CUDA.
+ */
+#ifndef ORB_B200_H
+#define ORB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  ORBX_OK = 0,
+  ORBX_ERR_ARG = -1,        /* null pointer / bad size / unsupported shape */
+  ORBX_ERR_CUDA = -2,       /* CUDA runtime error or no device */
+  ORBX_ERR_CAPACITY = -3,   /* caller buffer too small */
+  ORBX_ERR_SHAPE = -4       /* image too small / aspect ratio the reference cannot handle either */
+};
+
+/* Same five parameters as the reference constructor (ORBextractor.h:51-52), plus the device. */
+typedef struct orbx_params {
+  int nfeatures;
+  float scale_factor;
+  int nlevels;
+  int ini_th_fast;
+  int min_th_fast;
+  int device;               /* CUDA device ordinal */
+} orbx_params;
+
+/* Binary layout of cv::KeyPoint (28 bytes): what ORBextractor::operator() fills (ORBextractor.cpp:1081-1110). */
+typedef struct orbx_keypoint {
+  float x, y;               /* pt, already multiplied by the level scale factor (ORBextractor.cpp:1102-1108) */
+  float size;               /* (int)(31 * scale[level])                        (ORBextractor.cpp:845,854) */
+  float angle;              /* IC_Angle, degrees in [0,360)                    (ORBextractor.cpp:79-107)  */
+  float response;           /* FAST score                                                                  */
+  int32_t octave;           /* pyramid level                                                               */
+  int32_t class_id;         /* always -1                                                                   */
+} orbx_keypoint;
+
+typedef struct orbx_extractor* orbx_handle;
+
+const char* orbx_last_error(void);        /* thread-local message of the last failing call */
+int orbx_device_count(int* n);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Extractor  (replaces ORBextractor::ORBextractor / operator() / Get*ScaleFactors)
+ * ------------------------------------------------------------------------------------------------- */
+int orbx_create(const orbx_params* p, orbx_handle* out);
+int orbx_destroy(orbx_handle h);
+int orbx_get_levels(orbx_handle h, int* nlevels);                           /* ORBextractor.h:63 */
+int orbx_scale_factors(orbx_handle h, float* out, int n);                   /* ORBextractor.h:69 */
+int orbx_inv_scale_factors(orbx_handle h, float* out, int n);               /* ORBextractor.h:73 */
+int orbx_features_per_level(orbx_handle h, int* out, int n);                /* mnFeaturesPerLevel */
+/* Upper bound on keypoints per frame for this handle (sum over levels of N_l + 3). */
+int orbx_max_keypoints(orbx_handle h, int* cap);
+
+/* One frame, host buffers: ORBextractor::operator()(image, mask, keypoints, descriptors)
+ * (ORBextractor.cpp:1051).  `stride` = bytes between rows.  kps[cap], desc[cap*32].  *n = count.
+ * An empty image (w<=0 || h<=0 || !img) is a silent no-op with *n untouched, like the reference (:1054). */
+int orbx_extract(orbx_handle h, const uint8_t* img, int w, int height, size_t stride, orbx_keypoint* kps,
+                 uint8_t* desc, int cap, int* n);
+
+/* A batch of equally sized frames, host buffers.  Frame f starts at imgs + f*frame_stride.
+ * kps[nframes*cap], desc[nframes*cap*32], counts[nframes]. */
+int orbx_extract_batch(orbx_handle h, const uint8_t* imgs, int nframes, int w, int height, size_t row_stride,
+                       size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts);
+
+/* Same, everything already resident in device memory; asynchronous on `stream`. */
+int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes, int w, int height,
+                              size_t row_stride, size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc,
+                              int cap, int32_t* d_counts, void* stream);
+
+/* Number of kernels this library launched on this handle since creation (bench bookkeeping). */
+int orbx_launch_count(orbx_handle h, long long* n);
+
+/* Stage taps for stage-level parity tests (valid after an extract call; frame index within the last
+ * chunk processed).  Host output buffers. */
+int orbx_debug_level(orbx_handle h, int frame, int level, int blurred, uint8_t* out, int* w, int* height);
+int orbx_debug_candidates(orbx_handle h, int frame, int level, int32_t* xys /* n*3 */, int cap, int* n);
+int orbx_debug_selected(orbx_handle h, int frame, int level, int32_t* xys /* n*3 */, int cap, int* n);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Hamming matcher  (replaces Matcher::computeDistance matcher.cpp:1240-1256 and the best/second-best +
+ * ratio loop matcher.cpp:481-507, generalised to all pairs)
+ *
+ * For each query i: train rows scanned in ascending index, strict '<', first index wins:
+ *   idx[i], d1[i] = best; d2[i] = second best (256 if none); ok[i] = d1 <= th && (float)d1 < ratio*(float)d2.
+ * ------------------------------------------------------------------------------------------------- */
+int hamm_knn2(const uint8_t* q, int nq, const uint8_t* t, long long nt, int th, float ratio, int32_t* idx,
+              int32_t* d1, int32_t* d2, uint8_t* ok, int device);
+int hamm_knn2_device(const uint8_t* d_q, int nq, const uint8_t* d_t, long long nt, int th, float ratio,
+                     int32_t* d_idx, int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok, void* d_workspace,
+                     size_t workspace_bytes, void* stream);
+size_t hamm_knn2_workspace_bytes(int nq, long long nt);
+
+/* Frame-to-frame matching over a batch of extractor outputs (BASELINE config 2): pair p matches the
+ * descriptors of frame qf[p] (queries) against those of frame tf[p] (train); desc is [nframes][cap][32],
+ * counts[nframes]; outputs are [npairs][cap]. */
+int hamm_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_counts, int cap, const int32_t* d_qf,
+                           const int32_t* d_tf, int npairs, int th, float ratio, int32_t* d_idx, int32_t* d_d1,
+                           int32_t* d_d2, uint8_t* d_ok, void* stream);
+
+/* Merge of per-shard results of a train set split into `nshards` contiguous index ranges (BASELINE config 5):
+ * in_* are [nshards][nq] with idx already global; lowest index wins ties, second = 2nd smallest of the
+ * multiset {d1_s, d2_s}.  Used after the NCCL all-gather. */
+int hamm_knn2_merge_device(const int32_t* d_idx_in, const int32_t* d_d1_in, const int32_t* d_d2_in, int nshards,
+                           int nq, int th, float ratio, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2,
+                           uint8_t* d_ok, void* stream);
+
+long long hamm_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Grid index + projection searches
+ *   grid:  Frame::assignFeaturesToGrid / getFeaturesInArea   (frame.cpp:72-97,199-247; camera.h:8-9)
+ *   sbp_frame: Matcher::searchByProjection(Frame*,Frame*,radius,checkRot)        (matcher.cpp:18-148)
+ *   sbp_local: Matcher::searchByProjection(Frame*,vector<MapPoint*>&,thRadius)    (matcher.cpp:274-353)
+ * Map points are passed already projected (u, v, invz ...), so no Sophus/Eigen arithmetic is involved.
+ * ------------------------------------------------------------------------------------------------- */
+#define ORBX_GRID_COLS 64
+#define ORBX_GRID_ROWS 48
+
+typedef struct orbx_frame_view {      /* the "current frame" side; host or device pointers per entry point */
+  const orbx_keypoint* kps;           /* unKeypoints_ */
+  const uint8_t* desc;                /* descriptors_, n x 32 */
+  const float* uright;                /* uRight_ (<=0: no stereo check) */
+  int n;
+  float xmin, xmax, ymin, ymax;       /* image bounds (camera.cpp:42-45) */
+  const float* scale_factors;         /* scaleFactors_ */
+  int nlevels;
+  const uint8_t* occupied0;           /* 1 if mappoints_[i] already holds a point with observations */
+} orbx_frame_view;
+
+typedef struct orbx_sbp_frame_points { /* map points of the last frame, in index order */
+  int m;
+  const uint8_t* valid;               /* 0 models `!mp || outlier` (matcher.cpp:46) */
+  const float* u; const float* v; const float* invz;   /* projection into the current frame (:49-58) */
+  const int32_t* octave;              /* frame_last->unKeypoints_[i].octave */
+  const float* angle;                 /* frame_last->unKeypoints_[i].angle */
+  const uint8_t* desc;                /* mp->getDescriptor(), m x 32 */
+  const uint8_t* has_obs;             /* mp->observe_cnt_ > 0 */
+} orbx_sbp_frame_points;
+
+typedef struct orbx_sbp_local_points { /* local map points (matcher.cpp:278-298) */
+  int m;
+  const uint8_t* valid;               /* 0 models isBad() || !trackInLocalMap_ */
+  const float* u; const float* v; const float* ur;   /* trackProj_u_/v_/uR_ */
+  const int32_t* level;               /* trackScaleLevel_ */
+  const float* view_cos;              /* viewCos_ */
+  const uint8_t* desc;
+  const uint8_t* has_obs;             /* getObsCnt() > 0 */
+} orbx_sbp_local_points;
+
+/* CSR grid: cell_start[64*48+1], ids[n]; cell index = ix*48 + iy; ids ascending inside a cell. Host buffers. */
+int orbx_grid_build(const orbx_keypoint* kps, int n, float xmin, float xmax, float ymin, float ymax,
+                    int32_t* cell_start, int32_t* ids, int device);
+
+/* assign[i] (i < frame.n): index of the map point finally written to mappoints_[i]; -1 = never written;
+ * -2 = written, then cleared by the rotation-histogram check.  *match_cnt = the function's return value. */
+int orbx_search_by_projection_frame(const orbx_frame_view* frame, const orbx_sbp_frame_points* pts, float radius,
+                                    float bf, int forward, int backward, int check_rot, int32_t* assign,
+                                    int* match_cnt, int device);
+int orbx_search_by_projection_local(const orbx_frame_view* frame, const orbx_sbp_local_points* pts,
+                                    float th_radius, float ratio, int32_t* assign, int* match_cnt, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORB_B200_H */

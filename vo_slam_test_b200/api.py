@@ -1,0 +1,301 @@
+"""ctypes binding of include/orb_b200.h + the Python mirror of the reference operator API."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+TH_HIGH = 100   # matcher.cpp:11
+TH_LOW = 50     # matcher.cpp:12
+
+
+class OrbError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(HERE, "lib", "libvoslam_b200.so")
+
+
+_lib = None
+
+
+class _Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int), ("ini_th_fast", C.c_int),
+                ("min_th_fast", C.c_int), ("device", C.c_int)]
+
+
+class _FrameView(C.Structure):
+    _fields_ = [("kps", C.c_void_p), ("desc", C.c_void_p), ("uright", C.c_void_p), ("n", C.c_int),
+                ("xmin", C.c_float), ("xmax", C.c_float), ("ymin", C.c_float), ("ymax", C.c_float),
+                ("scale_factors", C.c_void_p), ("nlevels", C.c_int), ("occupied0", C.c_void_p)]
+
+
+class _SbpFramePoints(C.Structure):
+    _fields_ = [("m", C.c_int), ("valid", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("invz", C.c_void_p),
+                ("octave", C.c_void_p), ("angle", C.c_void_p), ("desc", C.c_void_p), ("has_obs", C.c_void_p)]
+
+
+class _SbpLocalPoints(C.Structure):
+    _fields_ = [("m", C.c_int), ("valid", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("ur", C.c_void_p),
+                ("level", C.c_void_p), ("view_cos", C.c_void_p), ("desc", C.c_void_p), ("has_obs", C.c_void_p)]
+
+
+def load_library():
+    """Load libvoslam_b200.so.  Raises OrbError if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise OrbError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(the CUDA library is the only implementation; there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    vp, i32, f32, sz, ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
+    L.orbx_last_error.restype = C.c_char_p
+    L.orbx_device_count.argtypes = [vp]
+    L.orbx_create.argtypes = [vp, vp]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_get_levels.argtypes = [vp, vp]
+    L.orbx_scale_factors.argtypes = [vp, vp, i32]
+    L.orbx_inv_scale_factors.argtypes = [vp, vp, i32]
+    L.orbx_features_per_level.argtypes = [vp, vp, i32]
+    L.orbx_max_keypoints.argtypes = [vp, vp]
+    L.orbx_extract.argtypes = [vp, vp, i32, i32, sz, vp, vp, i32, vp]
+    L.orbx_extract_batch.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp]
+    L.orbx_extract_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp, vp]
+    L.orbx_launch_count.argtypes = [vp, vp]
+    L.orbx_debug_level.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+    L.orbx_debug_candidates.argtypes = [vp, i32, i32, vp, i32, vp]
+    L.orbx_debug_selected.argtypes = [vp, i32, i32, vp, i32, vp]
+    L.hamm_knn2.argtypes = [vp, i32, vp, ll, i32, f32, vp, vp, vp, vp, i32]
+    L.hamm_knn2_device.argtypes = [vp, i32, vp, ll, i32, f32, vp, vp, vp, vp, vp, sz, vp]
+    L.hamm_knn2_workspace_bytes.restype = sz
+    L.hamm_knn2_workspace_bytes.argtypes = [i32, ll]
+    L.hamm_knn2_pairs_device.argtypes = [vp, vp, i32, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp]
+    L.hamm_knn2_merge_device.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]
+    L.hamm_launch_count.restype = ll
+    L.orbx_grid_build.argtypes = [vp, i32, f32, f32, f32, f32, vp, vp, i32]
+    L.orbx_search_by_projection_frame.argtypes = [vp, vp, f32, f32, i32, i32, i32, vp, vp, i32]
+    L.orbx_search_by_projection_local.argtypes = [vp, vp, f32, f32, vp, vp, i32]
+    _lib = L
+    return L
+
+
+def lib():
+    return load_library()
+
+
+def _check(rc):
+    if rc != 0:
+        raise OrbError("libvoslam_b200 error %d: %s" % (rc, load_library().orbx_last_error().decode()))
+
+
+def device_count():
+    n = C.c_int(0)
+    load_library().orbx_device_count(C.byref(n))
+    return n.value
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class ORBextractor:
+    """Mirror of ORB_SLAM2::ORBextractor (ORBextractor.h:45-108): same constructor arguments, call operator and getters."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, device=0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        p = _Params(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device)
+        _check(self._lib.orbx_create(C.byref(p), C.byref(self._h)))
+        self.nlevels = nlevels
+        self.device = device
+        cap = C.c_int()
+        _check(self._lib.orbx_max_keypoints(self._h, C.byref(cap)))
+        self.max_keypoints = cap.value
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.orbx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- getters (ORBextractor.h:63-75) ---------------------------------------------------------
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactors(self):
+        out = np.zeros(self.nlevels, np.float32)
+        _check(self._lib.orbx_scale_factors(self._h, _p(out), self.nlevels))
+        return out
+
+    def GetScaleFactor(self):
+        return float(self.GetScaleFactors()[1]) if self.nlevels > 1 else 1.0
+
+    def GetInverseScaleFactors(self):
+        out = np.zeros(self.nlevels, np.float32)
+        _check(self._lib.orbx_inv_scale_factors(self._h, _p(out), self.nlevels))
+        return out
+
+    def features_per_level(self):
+        out = np.zeros(self.nlevels, np.int32)
+        _check(self._lib.orbx_features_per_level(self._h, _p(out), self.nlevels))
+        return out
+
+    # -- operator() (ORBextractor.cpp:1051) ------------------------------------------------------
+    def __call__(self, image, mask=None):
+        """(keypoints[KP_DTYPE], descriptors[n,32] uint8); `mask` is ignored like in the reference (ORBextractor.h:58)."""
+        image = np.asarray(image)
+        if image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise OrbError("image must be 8-bit single channel (assert at ORBextractor.cpp:1058)")
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        H, W = image.shape
+        cap = self.max_keypoints
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        _check(self._lib.orbx_extract(self._h, C.c_void_p(image.ctypes.data), W, H, image.strides[0], _p(kps), _p(desc),
+                                      cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images):
+        """images: uint8 (B, H, W) host array -> (kps (B,cap), desc (B,cap,32), counts (B,))."""
+        images = np.ascontiguousarray(images, np.uint8)
+        B, H, W = images.shape
+        cap = self.max_keypoints
+        kps = np.zeros((B, cap), KP_DTYPE)
+        desc = np.zeros((B, cap, 32), np.uint8)
+        counts = np.zeros(B, np.int32)
+        _check(self._lib.orbx_extract_batch(self._h, _p(images), B, W, H, W, W * H, _p(kps), _p(desc), cap, _p(counts)))
+        return kps, desc, counts
+
+    def extract_batch_device(self, d_imgs, nframes, W, H, row_stride, frame_stride, d_kps, d_desc, cap, d_counts, stream=0):
+        """Raw device pointers (ints); asynchronous on `stream`."""
+        _check(self._lib.orbx_extract_batch_device(self._h, C.c_void_p(d_imgs), nframes, W, H, row_stride, frame_stride,
+                                                   C.c_void_p(d_kps), C.c_void_p(d_desc), cap, C.c_void_p(d_counts),
+                                                   C.c_void_p(stream)))
+
+    def launch_count(self):
+        n = C.c_longlong(0)
+        _check(self._lib.orbx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # -- stage taps ------------------------------------------------------------------------------
+    def debug_level(self, frame, level, blurred=False):
+        w = C.c_int(); h = C.c_int()
+        _check(self._lib.orbx_debug_level(self._h, frame, level, int(blurred), None, C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value), np.uint8)
+        _check(self._lib.orbx_debug_level(self._h, frame, level, int(blurred), _p(out), C.byref(w), C.byref(h)))
+        return out
+
+    def debug_candidates(self, frame, level, cap=1 << 20):
+        out = np.empty((cap, 3), np.int32); n = C.c_int()
+        _check(self._lib.orbx_debug_candidates(self._h, frame, level, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def debug_selected(self, frame, level, cap=1 << 16):
+        out = np.empty((cap, 3), np.int32); n = C.c_int()
+        _check(self._lib.orbx_debug_selected(self._h, frame, level, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+
+def knn2_device(d_q, nq, d_t, nt, th, ratio, d_idx, d_d1, d_d2, d_ok, d_ws=0, ws_bytes=0, stream=0):
+    _check(load_library().hamm_knn2_device(C.c_void_p(d_q), nq, C.c_void_p(d_t), nt, th, ratio, C.c_void_p(d_idx),
+                                           C.c_void_p(d_d1), C.c_void_p(d_d2), C.c_void_p(d_ok), C.c_void_p(d_ws),
+                                           ws_bytes, C.c_void_p(stream)))
+
+
+def grid_build(kps, bounds, device=0):
+    """Frame::assignFeaturesToGrid (frame.cpp:72-89) -> CSR (cell_start[64*48+1], ids); cell = ix*48+iy."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    start = np.zeros(64 * 48 + 1, np.int32)
+    ids = np.zeros(max(len(kps), 1), np.int32)
+    _check(load_library().orbx_grid_build(_p(kps), len(kps), bounds[0], bounds[1], bounds[2], bounds[3], _p(start), _p(ids),
+                                          device))
+    return start, ids[:start[-1]].copy()
+
+
+class Matcher:
+    """Mirror of myslam::Matcher (matcher.h:9-45) for the hot-path overloads; map points arrive already projected."""
+
+    def __init__(self, ratio=0.7, device=0):
+        self.ratio_ = float(ratio)
+        self.device = device
+        self._lib = load_library()
+
+    @staticmethod
+    def computeDistance(desp1, desp2, device=0):
+        """Matcher::computeDistance (matcher.cpp:1240-1256) of two 32-byte descriptors."""
+        a = np.ascontiguousarray(desp1, np.uint8).reshape(1, 32)
+        b = np.ascontiguousarray(desp2, np.uint8).reshape(1, 32)
+        idx, d1, d2, ok = Matcher(1.0, device).knn2(a, b, th=256)
+        return int(d1[0])
+
+    def knn2(self, queries, train, th=TH_LOW):
+        """Best/second-best + ratio loop of matcher.cpp:481-507 over all pairs -> (idx, d1, d2, ok)."""
+        q = np.ascontiguousarray(queries, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        nq = len(q)
+        idx = np.zeros(nq, np.int32); d1 = np.zeros(nq, np.int32); d2 = np.zeros(nq, np.int32); ok = np.zeros(nq, np.uint8)
+        _check(self._lib.hamm_knn2(_p(q), nq, _p(t), len(t), th, self.ratio_, _p(idx), _p(d1), _p(d2), _p(ok), self.device))
+        return idx, d1, d2, ok
+
+    @staticmethod
+    def _frame_view(frame, keep):
+        def a(x, dt):
+            y = np.ascontiguousarray(x, dt); keep.append(y); return y.ctypes.data
+        v = _FrameView()
+        v.kps = a(frame["kps"], KP_DTYPE); v.desc = a(frame["desc"], np.uint8); v.uright = a(frame["uright"], np.float32)
+        v.n = len(frame["kps"])
+        v.xmin, v.xmax, v.ymin, v.ymax = [float(b) for b in frame["bounds"]]
+        v.scale_factors = a(frame["scale_factors"], np.float32); v.nlevels = len(frame["scale_factors"])
+        v.occupied0 = a(frame["occupied0"], np.uint8)
+        return v
+
+    def searchByProjection(self, frame_curr, frame_last_points, radius, checkRot=True, bf=40.0, forward=False,
+                           backward=False):
+        """Matcher::searchByProjection(Frame*, Frame*, radius, checkRot) (matcher.cpp:18-148).
+        Returns (assign, match_cnt): assign[i] = map-point index written to frame_curr.mappoints_[i], -1 none,
+        -2 cleared by the rotation check."""
+        keep = []
+        def a(x, dt):
+            y = np.ascontiguousarray(x, dt); keep.append(y); return y.ctypes.data
+        fv = self._frame_view(frame_curr, keep)
+        p = frame_last_points
+        s = _SbpFramePoints()
+        s.m = len(p["u"]); s.valid = a(p["valid"], np.uint8); s.u = a(p["u"], np.float32); s.v = a(p["v"], np.float32)
+        s.invz = a(p["invz"], np.float32); s.octave = a(p["octave"], np.int32); s.angle = a(p["angle"], np.float32)
+        s.desc = a(p["desc"], np.uint8); s.has_obs = a(p["has_obs"], np.uint8)
+        assign = np.zeros(max(fv.n, 1), np.int32); cnt = C.c_int(0)
+        _check(self._lib.orbx_search_by_projection_frame(C.byref(fv), C.byref(s), radius, bf, int(forward), int(backward),
+                                                         int(checkRot), _p(assign), C.byref(cnt), self.device))
+        return assign[:fv.n].copy(), cnt.value
+
+    def searchByProjectionLocal(self, frame, mappoints, thRadius):
+        """Matcher::searchByProjection(Frame*, const vector<MapPoint*>&, thRadius) (matcher.cpp:274-353)."""
+        keep = []
+        def a(x, dt):
+            y = np.ascontiguousarray(x, dt); keep.append(y); return y.ctypes.data
+        fv = self._frame_view(frame, keep)
+        p = mappoints
+        s = _SbpLocalPoints()
+        s.m = len(p["u"]); s.valid = a(p["valid"], np.uint8); s.u = a(p["u"], np.float32); s.v = a(p["v"], np.float32)
+        s.ur = a(p["ur"], np.float32); s.level = a(p["level"], np.int32); s.view_cos = a(p["view_cos"], np.float32)
+        s.desc = a(p["desc"], np.uint8); s.has_obs = a(p["has_obs"], np.uint8)
+        assign = np.zeros(max(fv.n, 1), np.int32); cnt = C.c_int(0)
+        _check(self._lib.orbx_search_by_projection_local(C.byref(fv), C.byref(s), thRadius, self.ratio_, _p(assign),
+                                                         C.byref(cnt), self.device))
+        return assign[:fv.n].copy(), cnt.value

@@ -1,0 +1,74 @@
+// common.cuh -- shared helpers for the sm_100a kernels of libvoslam_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/orb_b200.h"
+
+namespace orbx {
+
+void set_error(const std::string& msg);
+
+#define ORBX_CUDA(call)                                                                              \
+  do {                                                                                               \
+    cudaError_t _e = (call);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      orbx::set_error(std::string(#call) + ": " + cudaGetErrorString(_e));                           \
+      return ORBX_ERR_CUDA;                                                                          \
+    }                                                                                                \
+  } while (0)
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+static inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Candidate / keypoint packing used between the stages: x:12 | y:12 | score:8 (region coordinates).
+__host__ __device__ static inline uint32_t pack_key(int x, int y, int s) {
+  return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
+}
+__host__ __device__ static inline int key_x(uint32_t k) { return (int)(k & 0xFFFu); }
+__host__ __device__ static inline int key_y(uint32_t k) { return (int)((k >> 12) & 0xFFFu); }
+__host__ __device__ static inline int key_s(uint32_t k) { return (int)(k >> 24); }
+
+// Exclusive scan of `n` ints held in shared memory, in place, by the whole block (blockDim.x threads,
+// a multiple of 32, at most 1024).  Returns the total.  `warp_sums` is a 33-int shared scratch.  Contains barriers.
+__device__ static inline int block_exclusive_scan(int* data, int n, int* warp_sums) {
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int per = (n + T - 1) / T;
+  const int lo = min(tid * per, n), hi = min(lo + per, n);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += data[i];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = (lane < (T >> 5)) ? warp_sums[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    warp_sums[lane] = wi - w;            // exclusive warp offsets
+    if (lane == 31) warp_sums[32] = wi;  // grand total
+  }
+  __syncthreads();
+  int run = warp_sums[wid] + incl - sum;
+  for (int i = lo; i < hi; ++i) {
+    int v = data[i];
+    data[i] = run;
+    run += v;
+  }
+  int total = warp_sums[32];
+  __syncthreads();
+  return total;
+}
+
+}  // namespace orbx

@@ -1,0 +1,248 @@
+// hamming.cu -- brute-force 256-bit Hamming top-2 ("kNN k=2 + ratio test") for sm_100a.
+//
+// Replaces Matcher::computeDistance (matcher.cpp:1240-1256) inside the best/second-best loop of
+// matcher.cpp:481-507, generalised to all pairs.  Pure integer work: XOR + POPC on eight
+// 32-bit words per pair, no tensor cores.  One thread owns one query (8 registers); train descriptors are
+// staged through shared memory and read as warp-wide broadcasts.
+//
+// Ordering contract (bit-exact with the sequential scan): train rows ascending, strict '<', first index wins.
+// Realised with packed keys  key = dist << 23 | local_index : min() over keys prefers the smaller distance and,
+// for equal distances, the smaller index; second best = min(best2, max(key, old best1)).
+#include <atomic>
+
+#include "common.cuh"
+
+namespace orbx {
+
+constexpr int kQT = 128;          // queries per CTA (threads)
+constexpr int kTT = 256;          // train descriptors per shared-memory tile (8 KB)
+constexpr uint32_t kKeyInit = (256u << 23) | 0x7FFFFFu;
+
+static std::atomic<long long> g_hamm_launches{0};
+
+__device__ __forceinline__ int hamming8(const uint32_t (&q)[8], const uint4 a, const uint4 b) {
+  return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
+         __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+}
+
+__device__ __forceinline__ void top2_update(uint32_t& k1, uint32_t& k2, uint32_t key) {
+  k2 = min(k2, max(key, k1));
+  k1 = min(k1, key);
+}
+
+// Scan train rows [t0, t0+nt) (nt < 2^23) for the CTA's queries; tiles go through `tile` (kTT*32 bytes).
+__device__ __forceinline__ void scan_train(const uint32_t (&q)[8], const uint8_t* __restrict__ train, int nt, uint4* tile,
+                                           uint32_t& k1, uint32_t& k2) {
+  const int tid = threadIdx.x;
+  for (int base = 0; base < nt; base += kTT) {
+    const int cnt = min(kTT, nt - base);
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(train + (size_t)base * 32);
+    for (int i = tid; i < cnt * 2; i += kQT) tile[i] = __ldg(src + i);
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+      const uint32_t d = (uint32_t)hamming8(q, a, b);
+      top2_update(k1, k2, (d << 23) | (uint32_t)(base + j));
+    }
+  }
+}
+
+__device__ __forceinline__ void load_query(uint32_t (&q)[8], const uint8_t* __restrict__ qs, int i, int nq) {
+  if (i < nq) {
+    const uint4* p = reinterpret_cast<const uint4*>(qs + (size_t)i * 32);
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = 0;
+  }
+}
+
+__device__ __forceinline__ uint8_t accept(int d1, int d2, int th, float ratio) {
+  return (d1 <= th && (float)d1 < __fmul_rn(ratio, (float)d2)) ? 1 : 0;   // matcher.cpp:504-506
+}
+
+// grid (ceil(nq/kQT), nsplit).  Split s scans train rows [s*per, min((s+1)*per, nt)).
+// nsplit == 1: final outputs are written directly; otherwise partial (idx, d1, d2) go to the workspace.
+__global__ void __launch_bounds__(kQT) knn2_kernel(const uint8_t* __restrict__ qs, int nq, const uint8_t* __restrict__ train,
+                                                   long long nt, long long per, int th, float ratio, int32_t* idx,
+                                                   int32_t* d1, int32_t* d2, uint8_t* ok, int32_t* part) {
+  __shared__ uint4 tile[kTT * 2];
+  const int i = blockIdx.x * kQT + threadIdx.x;
+  const int s = blockIdx.y;
+  const long long t0 = (long long)s * per;
+  const int cnt = (int)min(per, nt - t0);
+  uint32_t q[8];
+  load_query(q, qs, i, nq);
+  uint32_t k1 = kKeyInit, k2 = kKeyInit;
+  scan_train(q, train + (size_t)t0 * 32, cnt, tile, k1, k2);
+  if (i >= nq) return;
+  const int bd1 = (int)(k1 >> 23), bd2 = (int)(k2 >> 23);
+  const int bi = bd1 < 256 ? (int)(t0 + (long long)(k1 & 0x7FFFFFu)) : -1;
+  if (gridDim.y == 1) {
+    idx[i] = bi; d1[i] = bd1; d2[i] = bd2;
+    ok[i] = accept(bd1, bd2, th, ratio);
+  } else {
+    int32_t* p = part + ((size_t)s * nq + i) * 3;
+    p[0] = bi; p[1] = bd1; p[2] = bd2;
+  }
+}
+
+// Merge per-split / per-shard partial results (ascending train ranges): best = smallest d1, lowest range
+// wins ties (== lowest index); second = 2nd smallest of the multiset {d1_s, d2_s}.
+__global__ void knn2_merge_kernel(const int32_t* __restrict__ pidx, const int32_t* __restrict__ pd1,
+                                  const int32_t* __restrict__ pd2, int stride, int nparts, int nq, int th, float ratio,
+                                  int32_t* idx, int32_t* d1, int32_t* d2, uint8_t* ok) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  int b1 = 256, b2 = 256, bi = -1;
+  for (int s = 0; s < nparts; ++s) {
+    const size_t o = ((size_t)s * nq + i) * stride;
+    const int a1 = pd1[o], a2 = pd2[o], ai = pidx[o];
+    if (a1 < b1) { b2 = min(b1, a2); b1 = a1; bi = ai; }
+    else { b2 = min(b2, a1); }
+  }
+  idx[i] = bi; d1[i] = b1; d2[i] = b2;
+  ok[i] = accept(b1, b2, th, ratio);
+}
+
+// Frame-to-frame matching over extractor output: pair p = (query frame qf[p], train frame tf[p]).
+__global__ void __launch_bounds__(kQT) knn2_pairs_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ counts,
+                                                         int cap, const int32_t* __restrict__ qf, const int32_t* __restrict__ tf,
+                                                         int th, float ratio, int32_t* idx, int32_t* d1, int32_t* d2,
+                                                         uint8_t* ok) {
+  __shared__ uint4 tile[kTT * 2];
+  const int p = blockIdx.y;
+  const int fq = qf[p], ft = tf[p];
+  const int nq = min(counts[fq], cap), nt = min(counts[ft], cap);
+  if (blockIdx.x * kQT >= nq) return;
+  const int i = blockIdx.x * kQT + threadIdx.x;
+  uint32_t q[8];
+  load_query(q, desc + (size_t)fq * cap * 32, i, nq);
+  uint32_t k1 = kKeyInit, k2 = kKeyInit;
+  scan_train(q, desc + (size_t)ft * cap * 32, nt, tile, k1, k2);
+  if (i >= nq) return;
+  const int bd1 = (int)(k1 >> 23), bd2 = (int)(k2 >> 23);
+  const size_t o = (size_t)p * cap + i;
+  idx[o] = bd1 < 256 ? (int)(k1 & 0x7FFFFFu) : -1;
+  d1[o] = bd1; d2[o] = bd2;
+  ok[o] = accept(bd1, bd2, th, ratio);
+}
+
+static int pick_splits(int nq, long long nt, long long* per_out) {
+  const int qtiles = (nq + kQT - 1) / kQT;
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // aim at ~8 resident CTAs per SM, each split at least 4 tiles and below 2^23 rows
+  long long want = ((long long)sms * 8 + qtiles - 1) / qtiles;
+  long long maxSplits = (nt + 4LL * kTT - 1) / (4LL * kTT);
+  long long ns = std::max(1LL, std::min(want, maxSplits));
+  long long per = (nt + ns - 1) / ns;
+  per = (per + kTT - 1) / kTT * kTT;
+  const long long kMaxPer = (1LL << 23) - kTT;
+  if (per > kMaxPer) per = kMaxPer;
+  ns = (nt + per - 1) / per;
+  if (ns < 1) ns = 1;
+  *per_out = per;
+  return (int)ns;
+}
+
+}  // namespace orbx
+
+using namespace orbx;
+
+extern "C" {
+
+long long hamm_launch_count(void) { return g_hamm_launches.load(); }
+
+size_t hamm_knn2_workspace_bytes(int nq, long long nt) {
+  long long per;
+  const int ns = pick_splits(nq, nt, &per);
+  return ns > 1 ? (size_t)ns * nq * 3 * sizeof(int32_t) : 0;
+}
+
+int hamm_knn2_device(const uint8_t* d_q, int nq, const uint8_t* d_t, long long nt, int th, float ratio, int32_t* d_idx,
+                     int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (!d_q || !d_t || !d_idx || !d_d1 || !d_d2 || !d_ok || nq < 0 || nt < 0) { set_error("bad argument"); return ORBX_ERR_ARG; }
+  if (nq == 0) return ORBX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long per;
+  int ns = pick_splits(nq, nt, &per);
+  if (nt == 0) { ns = 1; per = kTT; }
+  if (ns > 1 && (!d_workspace || workspace_bytes < (size_t)ns * nq * 3 * sizeof(int32_t))) {
+    set_error("workspace too small (see hamm_knn2_workspace_bytes)");
+    return ORBX_ERR_CAPACITY;
+  }
+  dim3 grid((nq + kQT - 1) / kQT, ns);
+  knn2_kernel<<<grid, kQT, 0, st>>>(d_q, nq, d_t, nt, per, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace);
+  g_hamm_launches++;
+  if (ns > 1) {
+    const int32_t* part = (const int32_t*)d_workspace;
+    knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(part, part + 1, part + 2, 3, ns, nq, th, ratio, d_idx, d_d1, d_d2, d_ok);
+    g_hamm_launches++;
+  }
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+int hamm_knn2(const uint8_t* q, int nq, const uint8_t* t, long long nt, int th, float ratio, int32_t* idx, int32_t* d1,
+              int32_t* d2, uint8_t* ok, int device) {
+  if (!q || (!t && nt > 0) || !idx || !d1 || !d2 || !ok || nq < 0 || nt < 0) { set_error("bad argument"); return ORBX_ERR_ARG; }
+  if (nq == 0) return ORBX_OK;
+  ORBX_CUDA(cudaSetDevice(device));
+  uint8_t *dq = nullptr, *dt = nullptr, *dok = nullptr; int32_t *di = nullptr, *dd1 = nullptr, *dd2 = nullptr; void* ws = nullptr;
+  const size_t wsb = hamm_knn2_workspace_bytes(nq, nt);
+  int rc = ORBX_OK;
+  auto cleanup = [&]() { cudaFree(dq); cudaFree(dt); cudaFree(dok); cudaFree(di); cudaFree(dd1); cudaFree(dd2); cudaFree(ws); };
+#define HK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error(cudaGetErrorString(e_)); cleanup(); return ORBX_ERR_CUDA; } } while (0)
+  HK(cudaMalloc(&dq, (size_t)nq * 32)); HK(cudaMalloc(&dt, std::max<size_t>((size_t)nt * 32, 32)));
+  HK(cudaMalloc(&di, sizeof(int32_t) * nq)); HK(cudaMalloc(&dd1, sizeof(int32_t) * nq)); HK(cudaMalloc(&dd2, sizeof(int32_t) * nq));
+  HK(cudaMalloc(&dok, nq));
+  if (wsb) HK(cudaMalloc(&ws, wsb));
+  HK(cudaMemcpy(dq, q, (size_t)nq * 32, cudaMemcpyHostToDevice));
+  if (nt) HK(cudaMemcpy(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice));
+  rc = hamm_knn2_device(dq, nq, dt, nt, th, ratio, di, dd1, dd2, dok, ws, wsb, nullptr);
+  if (rc == ORBX_OK) {
+    HK(cudaMemcpy(idx, di, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost));
+    HK(cudaMemcpy(d1, dd1, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost));
+    HK(cudaMemcpy(d2, dd2, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost));
+    HK(cudaMemcpy(ok, dok, nq, cudaMemcpyDeviceToHost));
+  }
+#undef HK
+  cleanup();
+  return rc;
+}
+
+int hamm_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_counts, int cap, const int32_t* d_qf, const int32_t* d_tf,
+                           int npairs, int th, float ratio, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok,
+                           void* stream) {
+  if (!d_desc || !d_counts || !d_qf || !d_tf || !d_idx || !d_d1 || !d_d2 || !d_ok || cap <= 0 || npairs < 0) {
+    set_error("bad argument");
+    return ORBX_ERR_ARG;
+  }
+  if (npairs == 0) return ORBX_OK;
+  dim3 grid((cap + kQT - 1) / kQT, npairs);
+  knn2_pairs_kernel<<<grid, kQT, 0, (cudaStream_t)stream>>>(d_desc, d_counts, cap, d_qf, d_tf, th, ratio, d_idx, d_d1, d_d2, d_ok);
+  g_hamm_launches++;
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+int hamm_knn2_merge_device(const int32_t* d_idx_in, const int32_t* d_d1_in, const int32_t* d_d2_in, int nshards, int nq, int th,
+                           float ratio, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok, void* stream) {
+  if (!d_idx_in || !d_d1_in || !d_d2_in || !d_idx || !d_d1 || !d_d2 || !d_ok || nshards < 1 || nq < 0) {
+    set_error("bad argument");
+    return ORBX_ERR_ARG;
+  }
+  if (nq == 0) return ORBX_OK;
+  knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_idx_in, d_d1_in, d_d2_in, 1, nshards, nq, th, ratio,
+                                                                       d_idx, d_d1, d_d2, d_ok);
+  g_hamm_launches++;
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+}  // extern "C"

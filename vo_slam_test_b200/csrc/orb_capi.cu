@@ -1,0 +1,496 @@
+// orb_capi.cu -- C ABI of the extractor (include/orb_b200.h): host tables, geometry, workspaces, launch
+// sequencing.  Host-side tables mirror the reference constructor (ORBextractor.cpp:414-476) and
+// ComputePyramid's sizes (ORBextractor.cpp:1119-1120); everything per-pixel runs in orb_kernels.cu.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "orb_extract.cuh"
+#include "orb_pattern.h"
+
+namespace orbx {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+// kernels / launchers (orb_kernels.cu)
+void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe, uint8_t* dst, int dw, int dh,
+                   int dpitch, size_t dframe, const ResizeTaps& T, int nframes, cudaStream_t st);
+cudaError_t configure_kernels(const Geom& G);
+size_t fast_smem_bytes(const Geom& G);
+size_t octree_smem_bytes(const Geom& G);
+void launch_fast(const Geom& G, const Bufs& B, int nframes, cudaStream_t st);
+void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st);
+void launch_blur(const Geom& G, const Bufs& B, int nframes, cudaStream_t st);
+void launch_orient_desc(const Geom& G, const Bufs& B, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
+                        int frame0, int nframes, cudaStream_t st);
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+static inline int cv_round_d(double v) { return (int)lrint(v); }
+
+struct DevTaps {
+  ResizeTaps t{};
+  void* block = nullptr;
+};
+
+}  // namespace orbx
+
+using namespace orbx;
+
+struct orbx_extractor {
+  orbx_params p{};
+  // reference-constructor tables
+  std::vector<float> scale, invScale;
+  std::vector<int> nfeat;
+  int umax[16];
+  int maxKp = 0;
+  // geometry of the currently configured frame size
+  Geom G{};
+  bool haveGeom = false;
+  int chunk = 0;             // frames the workspace can hold
+  // device state
+  uint8_t* d_pyr = nullptr; uint8_t* d_blur = nullptr;
+  int* d_slotKeyBase = nullptr; int* d_slotCount = nullptr; uint32_t* d_slotKeys = nullptr;
+  uint32_t* d_flatKeys = nullptr; uint16_t* d_nodeOf = nullptr; int* d_candCount = nullptr;
+  uint32_t* d_sel = nullptr; int* d_selCount = nullptr;
+  float2* d_pattern = nullptr; int* d_umax = nullptr;
+  std::vector<DevTaps> taps;
+  // staging for the host entry points
+  uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
+  orbx_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int32_t* d_counts = nullptr;
+  size_t d_out_frames = 0; int d_out_cap = 0;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  // last chunk info for the debug taps
+  const uint8_t* last_img0 = nullptr; size_t last_rowStride = 0, last_frameStride = 0; int last_frames = 0;
+};
+
+namespace {
+
+int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+void free_workspace(orbx_extractor* h) {
+  cudaFree(h->d_pyr); cudaFree(h->d_blur); cudaFree(h->d_slotKeyBase); cudaFree(h->d_slotCount);
+  cudaFree(h->d_slotKeys); cudaFree(h->d_flatKeys); cudaFree(h->d_nodeOf); cudaFree(h->d_candCount);
+  cudaFree(h->d_sel); cudaFree(h->d_selCount);
+  h->d_pyr = h->d_blur = nullptr; h->d_slotKeyBase = nullptr; h->d_slotCount = nullptr; h->d_slotKeys = nullptr;
+  h->d_flatKeys = nullptr; h->d_nodeOf = nullptr; h->d_candCount = nullptr; h->d_sel = nullptr; h->d_selCount = nullptr;
+  for (auto& t : h->taps) cudaFree(t.block);
+  h->taps.clear();
+  h->haveGeom = false; h->chunk = 0;
+}
+
+// cv::resize tap tables for one axis
+void axis_taps(int ssize, int dsize, std::vector<int>& ofs, std::vector<short>& a0, std::vector<short>& a1) {
+  ofs.resize(dsize); a0.resize(dsize); a1.resize(dsize);
+  const double scale = 1.0 / ((double)dsize / ssize);
+  for (int d = 0; d < dsize; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+    ofs[d] = s;
+    a0[d] = (short)cv_round_f((1.f - f) * 2048.f);
+    a1[d] = (short)cv_round_f(f * 2048.f);
+  }
+}
+
+// Build the per-size geometry (cell grid, slots, capacities, workspace offsets) and allocate for `chunk` frames.
+int configure(orbx_extractor* h, int W, int H, int chunk) {
+  if (h->haveGeom && h->G.W == W && h->G.H == H && h->chunk >= chunk) return ORBX_OK;
+  free_workspace(h);
+  Geom& G = h->G;
+  memset(&G, 0, sizeof(G));
+  const int nl = h->p.nlevels;
+  G.nlevels = nl; G.W = W; G.H = H; G.iniTh = h->p.ini_th_fast; G.minTh = h->p.min_th_fast;
+  size_t pyrBytes = 0, blurBytes = 0;
+  int slot = 0, keyBase = 0, selBase = 0, blurTile = 0, slotKeys = 0;
+  std::vector<int> slotKeyBase;
+  G.nodeCap = 0; G.maxSlotsPerLevel = 0; G.fastTileW = 0; G.fastTileH = 0;
+  for (int l = 0; l < nl; ++l) {
+    LevelGeom& L = G.L[l];
+    const float s = h->invScale[l];
+    L.w = cv_round_f((float)W * s);                    // ORBextractor.cpp:1119-1120
+    L.h = cv_round_f((float)H * s);
+    L.regW = L.w - 2 * kMinBorder; L.regH = L.h - 2 * kMinBorder;
+    if (L.regW < 30 || L.regH < 30) { set_error("image too small for the pyramid: a level's FAST region is < 30 px"); return ORBX_ERR_SHAPE; }
+    if (L.regW > 4095 || L.regH > 4095) { set_error("image too large (level FAST region > 4095 px)"); return ORBX_ERR_SHAPE; }
+    L.nCols = L.regW / 30; L.nRows = L.regH / 30;      // :791-792 (float division then truncation == integer division here)
+    L.wCell = (L.regW + L.nCols - 1) / L.nCols;        // :793-794
+    L.hCell = (L.regH + L.nRows - 1) / L.nRows;
+    L.groups = (L.nCols + kCellsPerCta - 1) / kCellsPerCta;
+    L.slot0 = slot; L.nSlots = L.nRows * L.groups;
+    G.maxSlotsPerLevel = std::max(G.maxSlotsPerLevel, L.nSlots);
+    L.nFeat = h->nfeat[l];
+    L.nIni = (int)roundf((float)L.regW / (float)L.regH);   // :549
+    if (L.nIni < 1 || L.nIni > kMaxRoots) { set_error("unsupported aspect ratio (the reference's quadtree needs 1..16 root nodes)"); return ORBX_ERR_SHAPE; }
+    L.hX = (float)L.regW / L.nIni;                         // :551
+    for (int i = 0; i <= L.nIni; ++i) L.rootX[i] = (int)(L.hX * (float)i);   // :561-562
+    L.selCap = std::max(L.nFeat + 3, 4 * L.nIni);
+    L.selBase = selBase; selBase += L.selCap;
+    G.nodeCap = std::max(G.nodeCap, L.selCap + 1);
+    // slot capacities: NMS keeps no two 8-adjacent pixels inside a cell -> ceil(w/2)*ceil(h/2) per cell
+    int levelKeys = 0;
+    for (int ci = 0; ci < L.nRows; ++ci) {
+      const int ih = std::max(0, std::min(ci * L.hCell + L.hCell + 6, L.regH) - ci * L.hCell - 6);
+      for (int g = 0; g < L.groups; ++g) {
+        int capSlot = 0;
+        for (int j = g * kCellsPerCta; j < std::min((g + 1) * kCellsPerCta, L.nCols); ++j) {
+          const int iw = std::max(0, std::min(j * L.wCell + L.wCell + 6, L.regW) - j * L.wCell - 6);
+          capSlot += ((iw + 1) / 2) * ((ih + 1) / 2);
+        }
+        slotKeyBase.push_back(slotKeys);
+        slotKeys += capSlot; levelKeys += capSlot;
+      }
+    }
+    slot += L.nSlots;
+    L.keyBase = keyBase; L.keyCap = levelKeys; keyBase += levelKeys;
+    L.pitch = align_up(L.w, 64); L.bpitch = align_up(L.w, 64);
+    if (l > 0) { L.pyrOff = pyrBytes; pyrBytes += (size_t)chunk * L.h * L.pitch; }
+    L.blurOff = blurBytes; blurBytes += (size_t)chunk * L.h * L.bpitch;
+    L.blurTilesX = (L.w + 63) / 64; L.blurTilesY = (L.h + 31) / 32;
+    L.blurTile0 = blurTile; blurTile += L.blurTilesX * L.blurTilesY;
+    L.scale = h->scale[l];
+    L.kpSize = (float)(int)(31 * h->scale[l]);             // :845
+    G.fastTileW = std::max(G.fastTileW, align_up(std::min(kCellsPerCta, L.nCols) * L.wCell + 6, 4));
+    G.fastTileH = std::max(G.fastTileH, L.hCell + 6);
+  }
+  slotKeyBase.push_back(slotKeys);
+  G.totalSlots = slot; G.slotKeysPerFrame = slotKeys; G.keysPerFrame = keyBase; G.selPerFrame = selBase;
+  G.blurTiles = blurTile;
+  if (G.nodeCap > 60000) { set_error("nfeatures per level too large"); return ORBX_ERR_ARG; }
+  if (fast_smem_bytes(G) > 200 * 1024 || octree_smem_bytes(G) > 200 * 1024) { set_error("shape needs too much shared memory"); return ORBX_ERR_SHAPE; }
+
+  ORBX_CUDA(cudaSetDevice(h->p.device));
+  ORBX_CUDA(configure_kernels(G));
+  ORBX_CUDA(cudaMalloc(&h->d_pyr, std::max<size_t>(pyrBytes, 256)));
+  ORBX_CUDA(cudaMalloc(&h->d_blur, blurBytes));
+  ORBX_CUDA(cudaMalloc(&h->d_slotKeyBase, sizeof(int) * slotKeyBase.size()));
+  ORBX_CUDA(cudaMemcpy(h->d_slotKeyBase, slotKeyBase.data(), sizeof(int) * slotKeyBase.size(), cudaMemcpyHostToDevice));
+  ORBX_CUDA(cudaMalloc(&h->d_slotCount, sizeof(int) * (size_t)chunk * G.totalSlots));
+  ORBX_CUDA(cudaMalloc(&h->d_slotKeys, sizeof(uint32_t) * (size_t)chunk * G.slotKeysPerFrame));
+  ORBX_CUDA(cudaMalloc(&h->d_flatKeys, sizeof(uint32_t) * (size_t)chunk * G.keysPerFrame));
+  ORBX_CUDA(cudaMalloc(&h->d_nodeOf, sizeof(uint16_t) * (size_t)chunk * G.keysPerFrame));
+  ORBX_CUDA(cudaMalloc(&h->d_candCount, sizeof(int) * (size_t)chunk * nl));
+  ORBX_CUDA(cudaMalloc(&h->d_sel, sizeof(uint32_t) * (size_t)chunk * G.selPerFrame));
+  ORBX_CUDA(cudaMalloc(&h->d_selCount, sizeof(int) * (size_t)chunk * nl));
+  // resize tap tables per level >= 1
+  h->taps.resize(nl);
+  for (int l = 1; l < nl; ++l) {
+    const LevelGeom& S = G.L[l - 1];
+    const LevelGeom& D = G.L[l];
+    std::vector<int> xo, yo; std::vector<short> xa0, xa1, yb0, yb1;
+    axis_taps(S.w, D.w, xo, xa0, xa1);
+    axis_taps(S.h, D.h, yo, yb0, yb1);
+    const size_t bx = align_up_sz(sizeof(int) * D.w, 256), bs = align_up_sz(sizeof(short) * D.w, 256);
+    const size_t by = align_up_sz(sizeof(int) * D.h, 256), bt = align_up_sz(sizeof(short) * D.h, 256);
+    std::vector<uint8_t> blob(bx + 2 * bs + by + 2 * bt, 0);
+    memcpy(blob.data(), xo.data(), sizeof(int) * D.w);
+    memcpy(blob.data() + bx, xa0.data(), sizeof(short) * D.w);
+    memcpy(blob.data() + bx + bs, xa1.data(), sizeof(short) * D.w);
+    memcpy(blob.data() + bx + 2 * bs, yo.data(), sizeof(int) * D.h);
+    memcpy(blob.data() + bx + 2 * bs + by, yb0.data(), sizeof(short) * D.h);
+    memcpy(blob.data() + bx + 2 * bs + by + bt, yb1.data(), sizeof(short) * D.h);
+    DevTaps& T = h->taps[l];
+    ORBX_CUDA(cudaMalloc(&T.block, blob.size()));
+    ORBX_CUDA(cudaMemcpy(T.block, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    uint8_t* b = (uint8_t*)T.block;
+    T.t.xofs = (int*)b; T.t.xa0 = (short*)(b + bx); T.t.xa1 = (short*)(b + bx + bs);
+    T.t.yofs = (int*)(b + bx + 2 * bs); T.t.yb0 = (short*)(b + bx + 2 * bs + by); T.t.yb1 = (short*)(b + bx + 2 * bs + by + bt);
+  }
+  h->haveGeom = true;
+  h->chunk = chunk;
+  return ORBX_OK;
+}
+
+Bufs make_bufs(orbx_extractor* h, const uint8_t* img0, size_t rowStride, size_t frameStride) {
+  Bufs B{};
+  B.img0 = img0; B.rowStride0 = rowStride; B.frameStride0 = frameStride;
+  B.pyr = h->d_pyr; B.blur = h->d_blur; B.slotKeyBase = h->d_slotKeyBase; B.slotCount = h->d_slotCount;
+  B.slotKeys = h->d_slotKeys; B.flatKeys = h->d_flatKeys; B.nodeOf = h->d_nodeOf; B.candCount = h->d_candCount;
+  B.sel = h->d_sel; B.selCount = h->d_selCount; B.pattern = h->d_pattern; B.umax = h->d_umax;
+  return B;
+}
+
+// The whole extractor for frames [frame0, frame0+n) of a device-resident batch (n <= h->chunk).
+int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t frameStride, int frame0, int n,
+              orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t st) {
+  const Geom& G = h->G;
+  const uint8_t* img0 = d_imgs + (size_t)frame0 * frameStride;
+  Bufs B = make_bufs(h, img0, rowStride, frameStride);
+  for (int l = 1; l < G.nlevels; ++l) {        // ComputePyramid: level l from level l-1 (ORBextractor.cpp:1129)
+    const LevelGeom& S = G.L[l - 1];
+    const LevelGeom& D = G.L[l];
+    const uint8_t* src = (l == 1) ? img0 : h->d_pyr + S.pyrOff;
+    const int spitch = (l == 1) ? (int)rowStride : S.pitch;
+    const size_t sframe = (l == 1) ? frameStride : (size_t)S.h * S.pitch;
+    launch_resize(src, S.w, S.h, spitch, sframe, h->d_pyr + D.pyrOff, D.w, D.h, D.pitch, (size_t)D.h * D.pitch,
+                  h->taps[l].t, n, st);
+  }
+  launch_fast(G, B, n, st);
+  launch_octree(G, B, n, st);
+  launch_blur(G, B, n, st);
+  launch_orient_desc(G, B, d_kps, d_desc, cap, d_counts, frame0, n, st);
+  h->launches += (G.nlevels - 1) + 4;
+  h->last_img0 = img0; h->last_rowStride = rowStride; h->last_frameStride = frameStride; h->last_frames = n;
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+int check_handle(orbx_handle h) {
+  if (!h) { set_error("null handle"); return ORBX_ERR_ARG; }
+  return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* orbx_last_error(void) { return g_err.c_str(); }
+
+int orbx_device_count(int* n) {
+  if (!n) return ORBX_ERR_ARG;
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { *n = 0; set_error(cudaGetErrorString(e)); return ORBX_ERR_CUDA; }
+  *n = c;
+  return ORBX_OK;
+}
+
+int orbx_create(const orbx_params* p, orbx_handle* out) {
+  if (!p || !out) { set_error("null argument"); return ORBX_ERR_ARG; }
+  if (p->nlevels < 1 || p->nlevels > kMaxLevels || p->nfeatures < 1 || !(p->scale_factor > 1.0f) ||
+      p->ini_th_fast < 1 || p->min_th_fast < 1 || p->ini_th_fast > 254 || p->min_th_fast > 254) {
+    set_error("bad extractor parameters");
+    return ORBX_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || p->device < 0 || p->device >= ndev) {
+    set_error("no CUDA device (this library has no CPU fallback)");
+    return ORBX_ERR_CUDA;
+  }
+  orbx_extractor* h = new orbx_extractor();
+  h->p = *p;
+  const int nl = p->nlevels;
+  // ---- ORBextractor.cpp:419-451 (scaleFactor is stored as double, ORBextractor.h:98) ----------------
+  const double sf = (double)p->scale_factor;
+  h->scale.assign(nl, 1.f); h->invScale.assign(nl, 1.f);
+  for (int i = 1; i < nl; ++i) h->scale[i] = (float)(h->scale[i - 1] * sf);
+  for (int i = 0; i < nl; ++i) h->invScale[i] = 1.0f / h->scale[i];
+  h->nfeat.assign(nl, 0);
+  const float factor = (float)(1.0f / sf);
+  float want = (float)(p->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl)));
+  int sum = 0;
+  for (int l = 0; l < nl - 1; ++l) {
+    h->nfeat[l] = cv_round_f(want);
+    sum += h->nfeat[l];
+    want *= factor;
+  }
+  h->nfeat[nl - 1] = std::max(p->nfeatures - sum, 0);
+  // ---- ORBextractor.cpp:457-475: patch row extents ---------------------------------------------------
+  {
+    const int hp = 15;
+    const int vmax = (int)floor(hp * sqrt(2.f) / 2 + 1), vmin = (int)ceil(hp * sqrt(2.f) / 2);
+    const double hp2 = hp * hp;
+    for (int v = 0; v <= vmax; ++v) h->umax[v] = cv_round_d(sqrt(hp2 - v * v));
+    for (int v = hp, v0 = 0; v >= vmin; --v) {
+      while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+      h->umax[v] = v0;
+      ++v0;
+    }
+  }
+  h->maxKp = 0;
+  for (int l = 0; l < nl; ++l) h->maxKp += std::max(h->nfeat[l] + 3, 4 * kMaxRoots);
+  if (cudaSetDevice(p->device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaSetDevice/cudaStreamCreate failed");
+    delete h;
+    return ORBX_ERR_CUDA;
+  }
+  float2 pat[512];
+  for (int i = 0; i < 512; ++i) pat[i] = make_float2((float)orb_bit_pattern_31[2 * i], (float)orb_bit_pattern_31[2 * i + 1]);
+  if (cudaMalloc(&h->d_pattern, sizeof(pat)) != cudaSuccess || cudaMalloc(&h->d_umax, sizeof(int) * 16) != cudaSuccess ||
+      cudaMemcpy(h->d_pattern, pat, sizeof(pat), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->d_umax, h->umax, sizeof(int) * 16, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("device table upload failed");
+    delete h;
+    return ORBX_ERR_CUDA;
+  }
+  *out = h;
+  return ORBX_OK;
+}
+
+int orbx_destroy(orbx_handle h) {
+  if (!h) return ORBX_OK;
+  cudaSetDevice(h->p.device);
+  cudaDeviceSynchronize();
+  free_workspace(h);
+  cudaFree(h->d_pattern); cudaFree(h->d_umax); cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc);
+  cudaFree(h->d_counts);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return ORBX_OK;
+}
+
+int orbx_get_levels(orbx_handle h, int* nlevels) {
+  if (check_handle(h) || !nlevels) return ORBX_ERR_ARG;
+  *nlevels = h->p.nlevels;
+  return ORBX_OK;
+}
+int orbx_scale_factors(orbx_handle h, float* out, int n) {
+  if (check_handle(h) || !out || n < h->p.nlevels) return ORBX_ERR_ARG;
+  for (int i = 0; i < h->p.nlevels; ++i) out[i] = h->scale[i];
+  return ORBX_OK;
+}
+int orbx_inv_scale_factors(orbx_handle h, float* out, int n) {
+  if (check_handle(h) || !out || n < h->p.nlevels) return ORBX_ERR_ARG;
+  for (int i = 0; i < h->p.nlevels; ++i) out[i] = h->invScale[i];
+  return ORBX_OK;
+}
+int orbx_features_per_level(orbx_handle h, int* out, int n) {
+  if (check_handle(h) || !out || n < h->p.nlevels) return ORBX_ERR_ARG;
+  for (int i = 0; i < h->p.nlevels; ++i) out[i] = h->nfeat[i];
+  return ORBX_OK;
+}
+int orbx_max_keypoints(orbx_handle h, int* cap) {
+  if (check_handle(h) || !cap) return ORBX_ERR_ARG;
+  *cap = h->maxKp;
+  return ORBX_OK;
+}
+int orbx_launch_count(orbx_handle h, long long* n) {
+  if (check_handle(h) || !n) return ORBX_ERR_ARG;
+  *n = h->launches;
+  return ORBX_OK;
+}
+
+int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes, int w, int height, size_t row_stride,
+                              size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts,
+                              void* stream) {
+  if (check_handle(h)) return ORBX_ERR_ARG;
+  if (!d_imgs || !d_kps || !d_desc || !d_counts || nframes < 0 || w <= 0 || height <= 0 || cap <= 0 ||
+      row_stride < (size_t)w || frame_stride < row_stride * (size_t)(height - 1) + w) {
+    set_error("bad argument");
+    return ORBX_ERR_ARG;
+  }
+  if (nframes == 0) return ORBX_OK;
+  ORBX_CUDA(cudaSetDevice(h->p.device));
+  const int chunkMax = std::max(1, env_int("ORBX_CHUNK", 64));
+  const int chunk = std::min(nframes, chunkMax);
+  int rc = configure(h, w, height, chunk);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int f0 = 0; f0 < nframes; f0 += h->chunk) {
+    const int n = std::min(h->chunk, nframes - f0);
+    rc = run_chunk(h, d_imgs, row_stride, frame_stride, f0, n, d_kps, d_desc, cap, d_counts, st);
+    if (rc) return rc;
+  }
+  return ORBX_OK;
+}
+
+int orbx_extract_batch(orbx_handle h, const uint8_t* imgs, int nframes, int w, int height, size_t row_stride,
+                       size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts) {
+  if (check_handle(h)) return ORBX_ERR_ARG;
+  if (!imgs || !kps || !desc || !counts || nframes < 0 || w <= 0 || height <= 0 || cap <= 0 || row_stride < (size_t)w) {
+    set_error("bad argument");
+    return ORBX_ERR_ARG;
+  }
+  if (nframes == 0) return ORBX_OK;
+  ORBX_CUDA(cudaSetDevice(h->p.device));
+  const size_t pitch = align_up_sz((size_t)w, 64), fbytes = pitch * height;
+  if (h->d_in_bytes < fbytes * nframes) {
+    cudaFree(h->d_in);
+    h->d_in = nullptr; h->d_in_bytes = 0;
+    ORBX_CUDA(cudaMalloc(&h->d_in, fbytes * nframes));
+    h->d_in_bytes = fbytes * nframes;
+  }
+  if (h->d_out_frames < (size_t)nframes || h->d_out_cap < cap) {
+    cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
+    h->d_kps = nullptr; h->d_desc = nullptr; h->d_counts = nullptr; h->d_out_frames = 0;
+    ORBX_CUDA(cudaMalloc(&h->d_kps, sizeof(orbx_keypoint) * (size_t)nframes * cap));
+    ORBX_CUDA(cudaMalloc(&h->d_desc, (size_t)32 * nframes * cap));
+    ORBX_CUDA(cudaMalloc(&h->d_counts, sizeof(int32_t) * nframes));
+    h->d_out_frames = nframes; h->d_out_cap = cap;
+  }
+  cudaStream_t st = h->stream;
+  if (frame_stride == row_stride * (size_t)height) {
+    ORBX_CUDA(cudaMemcpy2DAsync(h->d_in, pitch, imgs, row_stride, w, (size_t)height * nframes, cudaMemcpyHostToDevice, st));
+  } else {
+    for (int f = 0; f < nframes; ++f)
+      ORBX_CUDA(cudaMemcpy2DAsync(h->d_in + f * fbytes, pitch, imgs + f * frame_stride, row_stride, w, height,
+                                  cudaMemcpyHostToDevice, st));
+  }
+  int rc = orbx_extract_batch_device(h, h->d_in, nframes, w, height, pitch, fbytes, h->d_kps, h->d_desc, cap, h->d_counts, st);
+  if (rc) return rc;
+  ORBX_CUDA(cudaMemcpyAsync(counts, h->d_counts, sizeof(int32_t) * nframes, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaMemcpyAsync(kps, h->d_kps, sizeof(orbx_keypoint) * (size_t)nframes * cap, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)32 * nframes * cap, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaStreamSynchronize(st));
+  return ORBX_OK;
+}
+
+int orbx_extract(orbx_handle h, const uint8_t* img, int w, int height, size_t stride, orbx_keypoint* kps, uint8_t* desc,
+                 int cap, int* n) {
+  if (check_handle(h)) return ORBX_ERR_ARG;
+  if (!img || w <= 0 || height <= 0) return ORBX_OK;   // `if(_image.empty()) return;` (ORBextractor.cpp:1054)
+  if (!n) { set_error("null count pointer"); return ORBX_ERR_ARG; }
+  int32_t c = 0;
+  int rc = orbx_extract_batch(h, img, 1, w, height, stride, stride * (size_t)height, kps, desc, cap, &c);
+  if (rc) return rc;
+  *n = c;
+  if (c > cap) { set_error("keypoint buffer too small"); return ORBX_ERR_CAPACITY; }
+  return ORBX_OK;
+}
+
+// ---- stage taps -------------------------------------------------------------------------------------------
+int orbx_debug_level(orbx_handle h, int frame, int level, int blurred, uint8_t* out, int* w, int* height) {
+  if (check_handle(h) || !h->haveGeom || level < 0 || level >= h->G.nlevels || frame < 0 || frame >= h->last_frames)
+    return ORBX_ERR_ARG;
+  const LevelGeom& L = h->G.L[level];
+  if (w) *w = L.w;
+  if (height) *height = L.h;
+  if (!out) return ORBX_OK;
+  ORBX_CUDA(cudaSetDevice(h->p.device));
+  ORBX_CUDA(cudaDeviceSynchronize());
+  const uint8_t* src; size_t pitch;
+  if (blurred) { src = h->d_blur + L.blurOff + (size_t)frame * L.h * L.bpitch; pitch = L.bpitch; }
+  else if (level == 0) { src = h->last_img0 + (size_t)frame * h->last_frameStride; pitch = h->last_rowStride; }
+  else { src = h->d_pyr + L.pyrOff + (size_t)frame * L.h * L.pitch; pitch = L.pitch; }
+  ORBX_CUDA(cudaMemcpy2D(out, L.w, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+  return ORBX_OK;
+}
+
+static int copy_keys(orbx_handle h, const uint32_t* d_src, int count, int32_t* xys, int cap, int* n) {
+  std::vector<uint32_t> k(std::max(count, 1));
+  if (count > 0) ORBX_CUDA(cudaMemcpy(k.data(), d_src, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < count && i < cap; ++i) { xys[3 * i] = key_x(k[i]); xys[3 * i + 1] = key_y(k[i]); xys[3 * i + 2] = key_s(k[i]); }
+  *n = count;
+  return ORBX_OK;
+}
+
+int orbx_debug_candidates(orbx_handle h, int frame, int level, int32_t* xys, int cap, int* n) {
+  if (check_handle(h) || !h->haveGeom || level < 0 || level >= h->G.nlevels || frame < 0 || frame >= h->last_frames || !n)
+    return ORBX_ERR_ARG;
+  ORBX_CUDA(cudaSetDevice(h->p.device));
+  ORBX_CUDA(cudaDeviceSynchronize());
+  int count = 0;
+  ORBX_CUDA(cudaMemcpy(&count, h->d_candCount + (size_t)frame * h->G.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  return copy_keys(h, h->d_flatKeys + (size_t)frame * h->G.keysPerFrame + h->G.L[level].keyBase, count, xys, cap, n);
+}
+
+int orbx_debug_selected(orbx_handle h, int frame, int level, int32_t* xys, int cap, int* n) {
+  if (check_handle(h) || !h->haveGeom || level < 0 || level >= h->G.nlevels || frame < 0 || frame >= h->last_frames || !n)
+    return ORBX_ERR_ARG;
+  ORBX_CUDA(cudaSetDevice(h->p.device));
+  ORBX_CUDA(cudaDeviceSynchronize());
+  int count = 0;
+  ORBX_CUDA(cudaMemcpy(&count, h->d_selCount + (size_t)frame * h->G.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  return copy_keys(h, h->d_sel + (size_t)frame * h->G.selPerFrame + h->G.L[level].selBase, count, xys, cap, n);
+}
+
+}  // extern "C"

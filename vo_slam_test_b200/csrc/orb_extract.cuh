@@ -1,0 +1,78 @@
+// orb_extract.cuh -- geometry/handle types shared by the extractor kernels and the C ABI.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace orbx {
+
+constexpr int kMaxLevels = 16;
+constexpr int kEdge = 19;            // EDGE_THRESHOLD        (ORBextractor.cpp:76)
+constexpr int kMinBorder = 16;       // EDGE_THRESHOLD - 3    (ORBextractor.cpp:780)
+constexpr int kCellsPerCta = 4;      // FAST cells handled by one CTA (one "slot")
+constexpr int kMaxRoots = 16;
+constexpr int kFastThreads = 256;
+constexpr int kOctThreads = 256;
+
+struct LevelGeom {
+  int w, h;                // level size
+  int regW, regH;          // FAST region (w-32) x (h-32)              (ORBextractor.cpp:780-789)
+  int nCols, nRows;        // cells                                    (:791-792)
+  int wCell, hCell;        //                                          (:793-794)
+  int groups;              // CTAs per cell row
+  int slot0, nSlots;       // slots of this level: nRows * groups, ordered (cell row, group)
+  int nFeat;               // mnFeaturesPerLevel                       (:439-451)
+  int nIni;                // quadtree roots                           (:549)
+  float hX;                //                                          (:551)
+  int rootX[kMaxRoots + 1];
+  int selBase, selCap;     // per-frame offset / capacity of the selected-keypoint array
+  int keyBase, keyCap;     // per-frame offset / capacity of the flat candidate array
+  int pitch;               // row pitch of this level in the pyramid workspace (levels >= 1)
+  int bpitch;              // row pitch in the blurred workspace
+  size_t pyrOff;           // byte offset of the [chunk][h][pitch] array of this level
+  size_t blurOff;
+  int blurTile0;           // first blur tile of this level in the fused blur launch
+  int blurTilesX, blurTilesY;
+  float scale;             // mvScaleFactor[level]
+  float kpSize;            // (int)(31*scale)                          (:845)
+};
+
+struct Geom {
+  int nlevels;
+  int W, H;
+  int iniTh, minTh;
+  int totalSlots;
+  int slotKeysPerFrame;    // sum of slot capacities
+  int keysPerFrame;        // sum of keyCap
+  int selPerFrame;         // sum of selCap
+  int nodeCap;             // max nodes of any level's quadtree
+  int maxSlotsPerLevel;
+  int blurTiles;
+  int fastTileW, fastTileH;  // smem tile extents of the FAST kernel
+  LevelGeom L[kMaxLevels];
+};
+
+// level-0 image set of the current chunk + workspaces
+struct Bufs {
+  const uint8_t* img0;     // level 0 = the caller's frames
+  size_t rowStride0, frameStride0;
+  uint8_t* pyr;            // levels >= 1
+  uint8_t* blur;           // blurred levels (all)
+  const int* slotKeyBase;  // [totalSlots+1]
+  int* slotCount;          // [chunk][totalSlots]
+  uint32_t* slotKeys;      // [chunk][slotKeysPerFrame]
+  uint32_t* flatKeys;      // [chunk][keysPerFrame]
+  uint16_t* nodeOf;        // [chunk][keysPerFrame]
+  int* candCount;          // [chunk][nlevels]
+  uint32_t* sel;           // [chunk][selPerFrame]
+  int* selCount;           // [chunk][nlevels]
+  const float2* pattern;   // 512 rBRIEF points
+  const int* umax;         // 16
+};
+
+struct ResizeTaps {        // device tables of one level
+  int* xofs; short* xa0; short* xa1;
+  int* yofs; short* yb0; short* yb1;
+};
+
+}  // namespace orbx
