@@ -1,0 +1,74 @@
+"""GPU parity, grid index + projection searches (frame.cpp:72-97,199-247; matcher.cpp:18-148,274-353) against the
+CPU oracle port: assignments and match counts bit-exact, including the greedy side effects."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle
+from vo_slam_test_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def vo():
+    import vo_slam_test_b200 as v
+    assert v.device_count() > 0
+    return v
+
+
+@pytest.fixture(scope="module")
+def frame_out():
+    P = oracle.Port()
+    kps, desc = P.extract(synth.make_frame(42))
+    return P, kps, desc, P.tables()[0]
+
+
+def test_grid_build(vo, frame_out):
+    P, kps, desc, sf = frame_out
+    for bounds in [(0.0, 640.0, 0.0, 480.0), (-12.5, 655.25, -7.0, 490.5)]:
+        ws, wi = P.grid_build(kps, *bounds)
+        gs, gi = vo.grid_build(kps, bounds)
+        assert np.array_equal(gs, ws) and np.array_equal(gi, wi)
+    # keypoints that fall in no bucket (round(x*0.1) == 64) must be dropped
+    assert ws[-1] <= len(kps)
+    e = vo.grid_build(kps[:0], (0.0, 640.0, 0.0, 480.0))
+    assert e[0][-1] == 0
+
+
+@pytest.mark.parametrize("m,stereo,mode,rot", [(10000, False, "none", True), (10000, True, "none", True),
+                                                (3000, False, "forward", True), (3000, True, "backward", False),
+                                                (1, False, "none", True), (500, False, "none", False)])
+def test_search_by_projection_frame(vo, frame_out, m, stereo, mode, rot):
+    P, kps, desc, sf = frame_out
+    frame, pts = synth.make_projection_case(kps, desc, sf, m, seed=m + int(stereo), stereo=stereo)
+    kw = dict(forward=(mode == "forward"), backward=(mode == "backward"))
+    want, wcnt = P.sbp_frame(frame, pts, 15.0, bf=40.0, check_rot=rot, **kw)
+    got, gcnt = vo.Matcher(0.9).searchByProjection(frame, pts, 15.0, checkRot=rot, bf=40.0, **kw)
+    assert gcnt == wcnt
+    assert np.array_equal(got, want)
+    if m >= 3000:
+        assert wcnt > 100 and (want >= 0).sum() > 100
+        if rot:
+            assert (want == -2).sum() > 0     # the rotation histogram did prune something
+
+
+@pytest.mark.parametrize("m,stereo,th", [(10000, False, 3.0), (4000, True, 5.0), (2, False, 3.0)])
+def test_search_by_projection_local(vo, frame_out, m, stereo, th):
+    P, kps, desc, sf = frame_out
+    frame, pts = synth.make_projection_case(kps, desc, sf, m, seed=7 * m, stereo=stereo, local=True)
+    want, wcnt = P.sbp_local(frame, pts, th, 0.8)
+    got, gcnt = vo.Matcher(0.8).searchByProjectionLocal(frame, pts, th)
+    assert gcnt == wcnt and np.array_equal(got, want)
+    if m >= 4000:
+        assert wcnt > 100
+
+
+def test_projection_empty_inputs(vo, frame_out):
+    P, kps, desc, sf = frame_out
+    frame, pts = synth.make_projection_case(kps, desc, sf, 50, seed=1)
+    empty = {k: v[:0] for k, v in pts.items()}
+    got, cnt = vo.Matcher(0.9).searchByProjection(frame, empty, 15.0)
+    assert cnt == 0 and (got == -1).all()
+    pts["valid"][:] = 0
+    got, cnt = vo.Matcher(0.9).searchByProjection(frame, pts, 15.0)
+    assert cnt == 0 and (got == -1).all()

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kQT) knn2_pairs_kernel(const uint8_t* __restri
 }
 
 static int pick_splits(int nq, long long nt, long long* per_out) {
+  if (nt <= 0 || nq <= 0) { *per_out = kTT; return 1; }
   const int qtiles = (nq + kQT - 1) / kQT;
   int sms = 148;
   int dev = 0;
@@ -170,8 +171,7 @@ int hamm_knn2_device(const uint8_t* d_q, int nq, const uint8_t* d_t, long long n
   if (nq == 0) return ORBX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   long long per;
-  int ns = pick_splits(nq, nt, &per);
-  if (nt == 0) { ns = 1; per = kTT; }
+  const int ns = pick_splits(nq, nt, &per);
   if (ns > 1 && (!d_workspace || workspace_bytes < (size_t)ns * nq * 3 * sizeof(int32_t))) {
     set_error("workspace too small (see hamm_knn2_workspace_bytes)");
     return ORBX_ERR_CAPACITY;

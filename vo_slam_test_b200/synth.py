@@ -74,3 +74,36 @@ def flip_bits(desc, nflips, rng):
             pos = rng.choice(256, size=k, replace=False)
             np.bitwise_xor.at(out[i], pos // 8, (1 << (pos % 8)).astype(np.uint8))
     return out
+
+
+def make_projection_case(kps, desc, scale_factors, m, seed=0, W=640, H=480, stereo=False, local=False):
+    """BASELINE config 4: `m` synthetic map points projected into a frame whose extractor output is (kps, desc).
+
+    Each point is a perturbed copy of a random frame feature: position jittered by a few pixels (some fall outside
+    the image), octave within +-1, descriptor with U[0,60] random bit flips, random observation flag.  Returns
+    (frame_dict, points_dict) in the layout the oracle and the product API share."""
+    rng = np.random.default_rng(seed)
+    n = len(kps)
+    nl = len(scale_factors)
+    src = rng.integers(0, n, m)
+    u = (kps["x"][src] + rng.normal(0, 4.0, m)).astype(np.float32)
+    v = (kps["y"][src] + rng.normal(0, 4.0, m)).astype(np.float32)
+    far = rng.random(m) < 0.05                       # 5 %: anywhere, including outside the image
+    u[far] = rng.uniform(-40, W + 40, far.sum()).astype(np.float32)
+    v[far] = rng.uniform(-40, H + 40, far.sum()).astype(np.float32)
+    octave = np.clip(kps["octave"][src] + rng.integers(-1, 2, m), 0, nl - 1).astype(np.int32)
+    mp_desc = flip_bits(desc[src], rng.integers(0, 61, m), rng)
+    frame = dict(kps=kps, desc=desc, bounds=(0.0, float(W), 0.0, float(H)), scale_factors=np.asarray(scale_factors, np.float32),
+                 uright=(kps["x"] - rng.uniform(5, 40, n)).astype(np.float32) if stereo else np.full(n, -1.0, np.float32),
+                 occupied0=(rng.random(n) < 0.03).astype(np.uint8))
+    z = rng.uniform(0.5, 8.0, m).astype(np.float32)
+    z[rng.random(m) < 0.02] *= -1                    # behind the camera
+    pts = dict(valid=(rng.random(m) > 0.03).astype(np.uint8), u=u, v=v, desc=mp_desc,
+               has_obs=(rng.random(m) < 0.6).astype(np.uint8))
+    if local:
+        pts.update(ur=(u - 40.0 / np.abs(z)).astype(np.float32), level=octave,
+                   view_cos=rng.uniform(0.99, 1.0, m).astype(np.float32))
+    else:
+        pts.update(invz=(1.0 / z).astype(np.float32), octave=octave,
+                   angle=((kps["angle"][src] + rng.normal(0, 6.0, m)) % 360.0).astype(np.float32))
+    return frame, pts
