@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native ORB front-end (BASELINE.json configs[1]).
+
+Workload (one "step"): a batch of synthetic 640x480 frames -> ORB extraction (1000 features, 8 levels, 1.2, FAST
+20/7) of every frame + frame-to-frame Hamming kNN (k=2, TH_LOW 50, ratio 0.7) between consecutive frames.
+Frames are independent units: with N GPUs every rank owns its own block of frames (no data-path collective,
+weak scaling: per-GPU work is fixed); `value` is whole-job frames/s.
+
+  python bench.py --gpus N --steps K --warmup W            # B200 arm (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's own CPU extractor
+                                                           # (oracle/_ref) + CPU matcher on all host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of value / e2e / roofline /
+cpu_baseline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_IMG, H_IMG = 640, 480
+NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 1000, 1.2, 8, 20, 7
+TH_LOW, RATIO = 50, 0.7
+METRIC = "ORB frames/s @640x480/1000kp (extract + frame-to-frame Hamming kNN k=2, ratio 0.7)"
+
+
+def level_sizes():
+    sc = [1.0]
+    for _ in range(1, NLEVELS):
+        sc.append(float(np.float32(sc[-1] * float(np.float32(SCALE)))))
+    out = []
+    for s in sc:
+        inv = np.float32(1.0) / np.float32(s)
+        out.append((int(np.rint(np.float32(W_IMG) * inv)), int(np.rint(np.float32(H_IMG) * inv))))
+    return out
+
+
+def algorithmic_bytes():
+    """SURVEY.md §8(d), stage-materialised convention, per frame."""
+    sz = level_sizes()
+    A = sum(w * h for w, h in sz); A0 = sz[0][0] * sz[0][1]; A7 = sz[-1][0] * sz[-1][1]
+    return {"pyramid": (A - A7) + (A - A0), "fast": A, "quadtree": 4 * 21000, "blur": 2 * A, "orient_desc": 60 * NFEAT,
+            "frame_total": 5 * A - A0 - A7 + 60 * NFEAT}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_step(imgs, cores, Ref, port):
+    """The reference's own extractor (oracle/_ref, one instance per core over disjoint frames, ORBextractor.h:85 is
+    stateful) + the reference's matcher loop (CPU port, threaded over queries) on `imgs`.  Returns seconds."""
+    t0 = time.perf_counter()
+    kps, desc, cnt = Ref.extract_batch(imgs, cores, keep_outputs=True)
+    for f in range(len(imgs) - 1):
+        port.knn2(desc[f, :cnt[f]], desc[f + 1, :cnt[f + 1]], TH_LOW, RATIO, nthreads=cores)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """--impl reference: CPU arm.  Rank 0 alone works; the other ranks exit 0."""
+    if rank != 0:
+        return
+    import oracle
+    from vo_slam_test_b200 import synth
+    cores = os.cpu_count() or 1
+    kind = "reference"
+    try:
+        Ref = oracle.Ref(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, parity=False)
+    except Exception:
+        Ref = None
+    port = oracle.Port(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    if Ref is None:      # no prebuilt oracle/_ref on this box: fall back to the CPU port of the same algorithm
+        kind = "port"
+
+        class _P:
+            def extract_batch(self, imgs, n, keep_outputs=True):
+                return port.extract_batch(imgs, n)
+        Ref = _P()
+    sample = max(cores * 8, 16)
+    imgs = synth.make_sequence(sample, seed=0)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_step(imgs[:max(cores, 2)], cores, Ref, port)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_reference_step(imgs, cores, Ref, port)
+    value = sample * args.steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "extract+match, bounded sample of %d synthetic 640x480 frames per step (of the 4096-frame "
+                                   "batch), 1000 features, 8 levels, 1.2, FAST 20/7, kNN k=2 TH_LOW 50 ratio 0.7" % sample,
+                       "frames_per_step": sample},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+                             "sample": "%d frames x %d steps, one extractor per core + threaded matcher" % (sample, args.steps)},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import vo_slam_test_b200 as vo
+    from vo_slam_test_b200 import api, synth, sharded
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    F = args.frames                                  # frames per GPU per step (weak scaling)
+    ex = vo.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank)
+    cap = ex.max_keypoints
+
+    # ---- synthetic input: pinned host batch + resident device copy -----------------------------------------
+    h_imgs = torch.empty((F, H_IMG, W_IMG), dtype=torch.uint8, pin_memory=True)
+    synth.make_sequence(F, seed=rank, out=h_imgs.numpy())
+    d_imgs = h_imgs.to(dev)
+    d_kps = torch.empty((F, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.empty((F, cap, 32), dtype=torch.uint8, device=dev)
+    d_counts = torch.zeros(F, dtype=torch.int32, device=dev)
+    npairs = F - 1
+    d_qf = torch.arange(0, npairs, dtype=torch.int32, device=dev)
+    d_tf = d_qf + 1
+    d_midx = torch.empty((max(npairs, 1), cap), dtype=torch.int32, device=dev)
+    d_md1 = torch.empty_like(d_midx); d_md2 = torch.empty_like(d_midx)
+    d_mok = torch.zeros((max(npairs, 1), cap), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_resident():
+        ex.extract_batch_device(d_imgs.data_ptr(), F, W_IMG, H_IMG, W_IMG, W_IMG * H_IMG, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                d_counts.data_ptr(), stream)
+        if npairs > 0:
+            api.knn2_pairs_device(d_desc.data_ptr(), d_counts.data_ptr(), cap, d_qf.data_ptr(), d_tf.data_ptr(), npairs, TH_LOW, RATIO,
+                                  d_midx.data_ptr(), d_md1.data_ptr(), d_md2.data_ptr(), d_mok.data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K resident steps, CUDA events on the launching stream, max over ranks ---------------
+    launches0 = ex.launch_count() + vo.lib().hamm_launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    launches = ex.launch_count() + vo.lib().hamm_launch_count() - launches0
+    value = world * F * args.steps / (ms_total / 1000.0)
+    counts = d_counts.cpu().numpy()
+    accepted = int(d_mok[:, :].sum().item()) if npairs > 0 else 0   # rows >= counts[f] are never written and stay 0
+
+    # ---- stage shares + Hamming rate (events inside the library / around the pairs kernel) ------------------
+    stage_ms = ex.profile_stages(d_imgs.data_ptr(), F, W_IMG, H_IMG, W_IMG, W_IMG * H_IMG, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                 d_counts.data_ptr(), stream)
+    names = ["pyramid", "fast", "quadtree", "blur", "orient_desc"]
+    ab = algorithmic_bytes()
+    hbm_peak, peak_src = 6650.0, "fallback"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, peak_src = float(mp["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(3):
+        api.knn2_pairs_device(d_desc.data_ptr(), d_counts.data_ptr(), cap, d_qf.data_ptr(), d_tf.data_ptr(), npairs, TH_LOW, RATIO,
+                              d_midx.data_ptr(), d_md1.data_ptr(), d_md2.data_ptr(), d_mok.data_ptr(), stream)
+    k1.record()
+    torch.cuda.synchronize()
+    pair_ms = k0.elapsed_time(k1) / 3
+    pair_matches = float((counts[:-1].astype(np.int64) * counts[1:].astype(np.int64)).sum())
+    stages = {n: {"ms_per_step": float(stage_ms[i]), "GBps": ab[n] * F / (float(stage_ms[i]) * 1e6) if stage_ms[i] > 0 else None}
+              for i, n in enumerate(names)}
+    stages["hamming_pairs"] = {"ms_per_step": pair_ms, "gmatch_per_s": pair_matches / (pair_ms * 1e6)}
+    dom = max(names, key=lambda n: stages[n]["ms_per_step"])
+    nchunks = (F + 63) // 64
+    dom_ms_launch = stages[dom]["ms_per_step"] / nchunks
+    achieved = ab[dom] * min(F, 64) / (dom_ms_launch * 1e6)
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src,
+                "note": "algorithmic bytes/launch = %d B/frame x %d frames/launch; whole-frame figure %.2f MB/frame -> %.1f GB/s (frac %.4f)"
+                        % (ab[dom], min(F, 64), ab["frame_total"] / 1e6, ab["frame_total"] * value / world / 1e9,
+                           ab["frame_total"] * value / world / 1e9 / hbm_peak)}
+
+    # ---- map-scale sharded Hamming top-2 (BASELINE config 5 shape: 1k queries vs 2M rows per GPU) ---------
+    hamming_map = None
+    if not args.skip_map:
+        Q, Ml = 1000, args.map_rows
+        g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+        d_t = torch.randint(0, 256, (Ml, 32), dtype=torch.uint8, device=dev, generator=g)
+        gq = torch.Generator(device=dev); gq.manual_seed(99)
+        d_q = torch.randint(0, 256, (Q, 32), dtype=torch.uint8, device=dev, generator=gq)
+        lo = rank * Ml
+        for _ in range(2):
+            sharded.sharded_knn2_cuda(d_q, d_t, lo, TH_LOW, RATIO, dist if world > 1 else None)
+        m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        m0.record()
+        reps = 5
+        for _ in range(reps):
+            sharded.sharded_knn2_cuda(d_q, d_t, lo, TH_LOW, RATIO, dist if world > 1 else None)
+        m1.record()
+        barrier()
+        mms = max_over_ranks(m0.elapsed_time(m1)) / reps
+        hamming_map = {"gmatch_per_s": world * Q * Ml / (mms * 1e6), "ms": mms, "queries": Q, "rows_per_gpu": Ml,
+                       "merge": "nccl all_gather + merge kernel" if world > 1 else "single shard"}
+        del d_t
+
+    # ---- end to end through the host C ABI: pinned host frames in, pinned host results out ------------------
+    h_kps = torch.empty((F, cap, 7), dtype=torch.float32, pin_memory=True)
+    h_desc = torch.empty((F, cap, 32), dtype=torch.uint8, pin_memory=True)
+    h_counts = torch.empty(F, dtype=torch.int32, pin_memory=True)
+    h_midx = torch.empty((max(npairs, 1), cap), dtype=torch.int32, pin_memory=True)
+    h_md1 = torch.empty_like(h_midx).pin_memory(); h_md2 = torch.empty_like(h_midx).pin_memory()
+    h_mok = torch.empty((max(npairs, 1), cap), dtype=torch.uint8, pin_memory=True)
+
+    def step_e2e():
+        ex.extract_match_batch(h_imgs.data_ptr(), F, W_IMG, H_IMG, h_kps.data_ptr(), h_desc.data_ptr(), cap, h_counts.data_ptr(),
+                               TH_LOW, RATIO, h_midx.data_ptr(), h_md1.data_ptr(), h_md2.data_ptr(), h_mok.data_ptr())
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    te = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * F * args.steps / te
+    h2d = F * W_IMG * H_IMG
+    d2h = F * 4 + F * cap * 28 + F * cap * 32 + npairs * cap * 13
+    assert np.array_equal(h_counts.numpy(), counts), "e2e and resident paths disagree"
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        import oracle
+        cores = os.cpu_count() or 1
+        port = oracle.Port(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+        try:
+            Ref = oracle.Ref(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, parity=False); kind = "reference"
+        except Exception:
+            Ref = None; kind = "port"
+        sample = min(F, max(cores * 64, 64))
+        imgs = h_imgs.numpy()[:sample]
+        if Ref is None:
+            class _P:
+                def extract_batch(self, im, n, keep_outputs=True):
+                    return port.extract_batch(im, n)
+            Ref = _P()
+        cpu_reference_step(imgs[:cores], cores, Ref, port)
+        t = cpu_reference_step(imgs, cores, Ref, port)
+        # parity spot check of the timed GPU outputs against the CPU arm on the same frames
+        # (against the canonical oracle: the timing build of the reference breaks quadtree ties by heap address, so
+        # its keypoint order depends on allocation history -- SURVEY App. B.1 -- and is not comparable bit for bit)
+        rk, rd, rc = port.extract_batch(imgs[:4], min(cores, 4))
+        for f in range(4):
+            assert rc[f] == counts[f] and np.array_equal(rd[f, :rc[f]], h_desc.numpy()[f, :rc[f]]), "GPU/CPU parity broke in bench"
+        cpu_baseline = {"value": sample / t, "unit": "frames/s", "cores": cores, "kind": kind,
+                        "sample": "first %d frames of the batch: reference ORBextractor.cpp (oracle/_ref, -O3) one instance per "
+                                  "core + CPU matcher threaded over queries; %.1f s of wall time" % (sample, t)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic",
+                "config": {"workload": "configs[1]: batch of %d synthetic 640x480 frames per GPU per step, ORB extract (1000 features, 8 "
+                                       "levels, 1.2, FAST 20/7) + frame-to-frame Hamming kNN (k=2, TH_LOW 50, ratio 0.7); frames sharded, "
+                                       "no collective" % F,
+                           "frames_per_gpu": F, "l2": "inputs (%.2f GB per GPU) larger than L2" % (F * W_IMG * H_IMG / 1e9),
+                           "chunk_frames": 64, "mean_keypoints": float(counts.mean()), "accepted_matches_per_pair": accepted / max(npairs, 1)},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "orbx_extract_match_batch (host C ABI, pinned host buffers, copies inside the timed region)"},
+                "gpu_launches": int(launches),
+                "roofline": roofline, "stages": stages, "hamming_gmatch_per_s": stages["hamming_pairs"]["gmatch_per_s"],
+                "hamming_map": hamming_map, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    ex.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=4096, help="frames per GPU per step")
+    ap.add_argument("--map-rows", type=int, default=2097152, help="map descriptors per GPU for the sharded kNN side metric")
+    ap.add_argument("--skip-map", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -84,6 +84,20 @@ int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes,
                               size_t row_stride, size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc,
                               int cap, int32_t* d_counts, void* stream);
 
+/* Host-buffer batch: extraction of every frame + frame-to-frame Hamming top-2 (BASELINE config 2; pair p: queries
+ * = descriptors of frame p, train = descriptors of frame p+1; the inner loop of matcher.cpp:481-507 with TH_LOW and
+ * ratio as arguments).  Host->device copies, kernels and device->host copies of successive chunks overlap on three
+ * streams; pass pinned memory for `imgs` and the outputs.  m_* are [(nframes-1) * cap]. */
+int orbx_extract_match_batch(orbx_handle h, const uint8_t* imgs, int nframes, int w, int height, size_t row_stride,
+                             size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts, int th,
+                             float ratio, int32_t* m_idx, int32_t* m_d1, int32_t* m_d2, uint8_t* m_ok);
+
+/* Per-stage device time of one resident batch, from CUDA events recorded on `stream` around every stage:
+ * ms[0..4] = pyramid, FAST, quadtree, blur, orientation+descriptors (summed over chunks), ms[5] = whole batch. */
+int orbx_profile_stages(orbx_handle h, const uint8_t* d_imgs, int nframes, int w, int height, size_t row_stride,
+                        size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts,
+                        void* stream, float* ms);
+
 /* Number of kernels this library launched on this handle since creation (bench bookkeeping). */
 int orbx_launch_count(orbx_handle h, long long* n);
 

@@ -69,6 +69,8 @@ def load_library():
     L.orbx_extract_batch.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp]
     L.orbx_extract_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp, vp]
     L.orbx_launch_count.argtypes = [vp, vp]
+    L.orbx_extract_match_batch.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp, i32, f32, vp, vp, vp, vp]
+    L.orbx_profile_stages.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp, vp, vp]
     L.orbx_debug_level.argtypes = [vp, i32, i32, i32, vp, vp, vp]
     L.orbx_debug_candidates.argtypes = [vp, i32, i32, vp, i32, vp]
     L.orbx_debug_selected.argtypes = [vp, i32, i32, vp, i32, vp]
@@ -188,6 +190,24 @@ class ORBextractor:
                                                    C.c_void_p(d_kps), C.c_void_p(d_desc), cap, C.c_void_p(d_counts),
                                                    C.c_void_p(stream)))
 
+    def extract_match_batch(self, imgs_ptr, nframes, W, H, kps_ptr, desc_ptr, cap, counts_ptr, th, ratio, midx_ptr,
+                            md1_ptr, md2_ptr, mok_ptr, row_stride=None, frame_stride=None):
+        """Host pointers (ints; pinned memory recommended): pipelined H2D -> extract -> frame-to-frame top-2 -> D2H."""
+        row_stride = W if row_stride is None else row_stride
+        frame_stride = row_stride * H if frame_stride is None else frame_stride
+        _check(self._lib.orbx_extract_match_batch(self._h, C.c_void_p(imgs_ptr), nframes, W, H, row_stride, frame_stride,
+                                                  C.c_void_p(kps_ptr), C.c_void_p(desc_ptr), cap, C.c_void_p(counts_ptr),
+                                                  th, ratio, C.c_void_p(midx_ptr), C.c_void_p(md1_ptr),
+                                                  C.c_void_p(md2_ptr), C.c_void_p(mok_ptr)))
+
+    def profile_stages(self, d_imgs, nframes, W, H, row_stride, frame_stride, d_kps, d_desc, cap, d_counts, stream=0):
+        """Per-stage device ms (pyramid, fast, quadtree, blur, orient+desc, total) of one resident batch."""
+        ms = np.zeros(6, np.float32)
+        _check(self._lib.orbx_profile_stages(self._h, C.c_void_p(d_imgs), nframes, W, H, row_stride, frame_stride,
+                                             C.c_void_p(d_kps), C.c_void_p(d_desc), cap, C.c_void_p(d_counts),
+                                             C.c_void_p(stream), _p(ms)))
+        return ms
+
     def launch_count(self):
         n = C.c_longlong(0)
         _check(self._lib.orbx_launch_count(self._h, C.byref(n)))
@@ -210,6 +230,22 @@ class ORBextractor:
         out = np.empty((cap, 3), np.int32); n = C.c_int()
         _check(self._lib.orbx_debug_selected(self._h, frame, level, _p(out), cap, C.byref(n)))
         return out[:n.value].copy()
+
+
+def knn2_pairs_device(d_desc, d_counts, cap, d_qf, d_tf, npairs, th, ratio, d_idx, d_d1, d_d2, d_ok, stream=0):
+    _check(load_library().hamm_knn2_pairs_device(C.c_void_p(d_desc), C.c_void_p(d_counts), cap, C.c_void_p(d_qf),
+                                                 C.c_void_p(d_tf), npairs, th, ratio, C.c_void_p(d_idx), C.c_void_p(d_d1),
+                                                 C.c_void_p(d_d2), C.c_void_p(d_ok), C.c_void_p(stream)))
+
+
+def knn2_merge_device(d_idx_in, d_d1_in, d_d2_in, nshards, nq, th, ratio, d_idx, d_d1, d_d2, d_ok, stream=0):
+    _check(load_library().hamm_knn2_merge_device(C.c_void_p(d_idx_in), C.c_void_p(d_d1_in), C.c_void_p(d_d2_in), nshards, nq,
+                                                 th, ratio, C.c_void_p(d_idx), C.c_void_p(d_d1), C.c_void_p(d_d2),
+                                                 C.c_void_p(d_ok), C.c_void_p(stream)))
+
+
+def knn2_workspace_bytes(nq, nt):
+    return int(load_library().hamm_knn2_workspace_bytes(nq, nt))
 
 
 def knn2_device(d_q, nq, d_t, nt, th, ratio, d_idx, d_d1, d_d2, d_ok, d_ws=0, ws_bytes=0, stream=0):

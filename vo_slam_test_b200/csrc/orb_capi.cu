@@ -62,7 +62,9 @@ struct orbx_extractor {
   uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
   orbx_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int32_t* d_counts = nullptr;
   size_t d_out_frames = 0; int d_out_cap = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copyStream = nullptr, backStream = nullptr;
+  int32_t *d_midx = nullptr, *d_md1 = nullptr, *d_md2 = nullptr, *d_qf = nullptr; uint8_t* d_mok = nullptr;
+  size_t m_frames = 0; int m_cap = 0;
   long long launches = 0;
   // last chunk info for the debug taps
   const uint8_t* last_img0 = nullptr; size_t last_rowStride = 0, last_frameStride = 0; int last_frames = 0;
@@ -221,10 +223,12 @@ Bufs make_bufs(orbx_extractor* h, const uint8_t* img0, size_t rowStride, size_t 
 
 // The whole extractor for frames [frame0, frame0+n) of a device-resident batch (n <= h->chunk).
 int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t frameStride, int frame0, int n,
-              orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t st) {
+              orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t st,
+              cudaEvent_t* ev = nullptr /* 6 events: before pyramid, fast, octree, blur, orient_desc, end */) {
   const Geom& G = h->G;
   const uint8_t* img0 = d_imgs + (size_t)frame0 * frameStride;
   Bufs B = make_bufs(h, img0, rowStride, frameStride);
+  if (ev) cudaEventRecord(ev[0], st);
   for (int l = 1; l < G.nlevels; ++l) {        // ComputePyramid: level l from level l-1 (ORBextractor.cpp:1129)
     const LevelGeom& S = G.L[l - 1];
     const LevelGeom& D = G.L[l];
@@ -234,10 +238,15 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
     launch_resize(src, S.w, S.h, spitch, sframe, h->d_pyr + D.pyrOff, D.w, D.h, D.pitch, (size_t)D.h * D.pitch,
                   h->taps[l].t, n, st);
   }
+  if (ev) cudaEventRecord(ev[1], st);
   launch_fast(G, B, n, st);
+  if (ev) cudaEventRecord(ev[2], st);
   launch_octree(G, B, n, st);
+  if (ev) cudaEventRecord(ev[3], st);
   launch_blur(G, B, n, st);
+  if (ev) cudaEventRecord(ev[4], st);
   launch_orient_desc(G, B, d_kps, d_desc, cap, d_counts, frame0, n, st);
+  if (ev) cudaEventRecord(ev[5], st);
   h->launches += (G.nlevels - 1) + 4;
   h->last_img0 = img0; h->last_rowStride = rowStride; h->last_frameStride = frameStride; h->last_frames = n;
   ORBX_CUDA(cudaGetLastError());
@@ -333,6 +342,9 @@ int orbx_destroy(orbx_handle h) {
   free_workspace(h);
   cudaFree(h->d_pattern); cudaFree(h->d_umax); cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc);
   cudaFree(h->d_counts);
+  cudaFree(h->d_midx); cudaFree(h->d_md1); cudaFree(h->d_md2); cudaFree(h->d_mok); cudaFree(h->d_qf);
+  if (h->copyStream) cudaStreamDestroy(h->copyStream);
+  if (h->backStream) cudaStreamDestroy(h->backStream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return ORBX_OK;
@@ -444,6 +456,148 @@ int orbx_extract(orbx_handle h, const uint8_t* img, int w, int height, size_t st
   if (rc) return rc;
   *n = c;
   if (c > cap) { set_error("keypoint buffer too small"); return ORBX_ERR_CAPACITY; }
+  return ORBX_OK;
+}
+
+
+// Per-stage device time of one batch (CUDA events on `stream` around every stage of every chunk; ms summed over
+// chunks).  ms[0..4] = pyramid, FAST, quadtree, blur, orientation+descriptors; ms[5] = whole batch.
+int orbx_profile_stages(orbx_handle h, const uint8_t* d_imgs, int nframes, int w, int height, size_t row_stride,
+                        size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts,
+                        void* stream, float* ms) {
+  if (check_handle(h)) return ORBX_ERR_ARG;
+  if (!d_imgs || !d_kps || !d_desc || !d_counts || !ms || nframes <= 0 || w <= 0 || height <= 0 || cap <= 0) {
+    set_error("bad argument");
+    return ORBX_ERR_ARG;
+  }
+  ORBX_CUDA(cudaSetDevice(h->p.device));
+  const int chunkMax = std::max(1, env_int("ORBX_CHUNK", 64));
+  int rc = configure(h, w, height, std::min(nframes, chunkMax));
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunks = (nframes + h->chunk - 1) / h->chunk;
+  std::vector<cudaEvent_t> ev((size_t)nchunks * 6);
+  for (auto& e : ev) ORBX_CUDA(cudaEventCreate(&e));
+  for (int c = 0; c < nchunks; ++c) {
+    const int f0 = c * h->chunk, n = std::min(h->chunk, nframes - f0);
+    rc = run_chunk(h, d_imgs, row_stride, frame_stride, f0, n, d_kps, d_desc, cap, d_counts, st, &ev[(size_t)c * 6]);
+    if (rc) break;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  for (int k = 0; k < 6; ++k) ms[k] = 0.f;
+  if (rc == ORBX_OK && e == cudaSuccess) {
+    for (int c = 0; c < nchunks; ++c)
+      for (int k = 0; k < 5; ++k) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ev[(size_t)c * 6 + k], ev[(size_t)c * 6 + k + 1]);
+        ms[k] += t;
+      }
+    cudaEventElapsedTime(&ms[5], ev[0], ev[(size_t)(nchunks - 1) * 6 + 5]);
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return ORBX_ERR_CUDA; }
+  return rc;
+}
+
+// Host-buffer batch: extraction of every frame + frame-to-frame Hamming top-2 (pair p: queries = frame p, train =
+// frame p+1), BASELINE config 2.  Host->device copies of chunk c+1 overlap the kernels of chunk c; results stream back
+// on a third stream.  imgs should be pinned for the copies to be asynchronous.  m_* are [(nframes-1) * cap].
+int orbx_extract_match_batch(orbx_handle h, const uint8_t* imgs, int nframes, int w, int height, size_t row_stride,
+                             size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts, int th,
+                             float ratio, int32_t* m_idx, int32_t* m_d1, int32_t* m_d2, uint8_t* m_ok) {
+  if (check_handle(h)) return ORBX_ERR_ARG;
+  if (!imgs || !kps || !desc || !counts || !m_idx || !m_d1 || !m_d2 || !m_ok || nframes <= 0 || w <= 0 || height <= 0 ||
+      cap <= 0 || row_stride < (size_t)w) {
+    set_error("bad argument");
+    return ORBX_ERR_ARG;
+  }
+  ORBX_CUDA(cudaSetDevice(h->p.device));
+  const int chunkMax = std::max(1, env_int("ORBX_CHUNK", 64));
+  int rc = configure(h, w, height, std::min(nframes, chunkMax));
+  if (rc) return rc;
+  const size_t pitch = align_up_sz((size_t)w, 64), fbytes = pitch * height;
+  const int npairs = nframes - 1;
+  if (h->d_in_bytes < fbytes * nframes) {
+    cudaFree(h->d_in); h->d_in = nullptr; h->d_in_bytes = 0;
+    ORBX_CUDA(cudaMalloc(&h->d_in, fbytes * nframes));
+    h->d_in_bytes = fbytes * nframes;
+  }
+  if (h->d_out_frames < (size_t)nframes || h->d_out_cap < cap) {
+    cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
+    h->d_kps = nullptr; h->d_desc = nullptr; h->d_counts = nullptr; h->d_out_frames = 0;
+    ORBX_CUDA(cudaMalloc(&h->d_kps, sizeof(orbx_keypoint) * (size_t)nframes * cap));
+    ORBX_CUDA(cudaMalloc(&h->d_desc, (size_t)32 * nframes * cap));
+    ORBX_CUDA(cudaMalloc(&h->d_counts, sizeof(int32_t) * nframes));
+    h->d_out_frames = nframes; h->d_out_cap = cap;
+  }
+  if (h->m_frames < (size_t)nframes || h->m_cap < cap) {
+    cudaFree(h->d_midx); cudaFree(h->d_md1); cudaFree(h->d_md2); cudaFree(h->d_mok); cudaFree(h->d_qf);
+    h->d_midx = h->d_md1 = h->d_md2 = nullptr; h->d_mok = nullptr; h->d_qf = nullptr; h->m_frames = 0;
+    const size_t np = std::max(npairs, 1);
+    ORBX_CUDA(cudaMalloc(&h->d_midx, sizeof(int32_t) * np * cap));
+    ORBX_CUDA(cudaMalloc(&h->d_md1, sizeof(int32_t) * np * cap));
+    ORBX_CUDA(cudaMalloc(&h->d_md2, sizeof(int32_t) * np * cap));
+    ORBX_CUDA(cudaMalloc(&h->d_mok, np * cap));
+    ORBX_CUDA(cudaMalloc(&h->d_qf, sizeof(int32_t) * (nframes + 1)));
+    std::vector<int32_t> iota(nframes + 1);
+    for (int i = 0; i <= nframes; ++i) iota[i] = i;
+    ORBX_CUDA(cudaMemcpy(h->d_qf, iota.data(), sizeof(int32_t) * (nframes + 1), cudaMemcpyHostToDevice));
+    h->m_frames = nframes; h->m_cap = cap;
+  }
+  if (!h->copyStream) {
+    ORBX_CUDA(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+    ORBX_CUDA(cudaStreamCreateWithFlags(&h->backStream, cudaStreamNonBlocking));
+  }
+  cudaStream_t sc = h->copyStream, sk = h->stream, sb = h->backStream;
+  const int nchunks = (nframes + h->chunk - 1) / h->chunk;
+  std::vector<cudaEvent_t> up(nchunks), done(nchunks);
+  for (int c = 0; c < nchunks; ++c) {
+    ORBX_CUDA(cudaEventCreateWithFlags(&up[c], cudaEventDisableTiming));
+    ORBX_CUDA(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+  }
+  const bool dense = frame_stride == row_stride * (size_t)height;
+  for (int c = 0; c < nchunks && rc == ORBX_OK; ++c) {
+    const int f0 = c * h->chunk, n = std::min(h->chunk, nframes - f0);
+    if (dense) {
+      cudaMemcpy2DAsync(h->d_in + f0 * fbytes, pitch, imgs + f0 * frame_stride, row_stride, w, (size_t)height * n,
+                        cudaMemcpyHostToDevice, sc);
+    } else {
+      for (int f = f0; f < f0 + n; ++f)
+        cudaMemcpy2DAsync(h->d_in + f * fbytes, pitch, imgs + f * frame_stride, row_stride, w, height, cudaMemcpyHostToDevice, sc);
+    }
+    cudaEventRecord(up[c], sc);
+    cudaStreamWaitEvent(sk, up[c], 0);
+    rc = run_chunk(h, h->d_in, pitch, fbytes, f0, n, h->d_kps, h->d_desc, cap, h->d_counts, sk);
+    if (rc) break;
+    // pairs whose second frame is now available: p in [max(f0-1,0), f0+n-1)
+    const int p0 = std::max(f0 - 1, 0), p1 = f0 + n - 1;
+    if (p1 > p0) {
+      rc = hamm_knn2_pairs_device(h->d_desc, h->d_counts, cap, h->d_qf + p0, h->d_qf + p0 + 1, p1 - p0, th, ratio,
+                                  h->d_midx + (size_t)p0 * cap, h->d_md1 + (size_t)p0 * cap, h->d_md2 + (size_t)p0 * cap,
+                                  h->d_mok + (size_t)p0 * cap, sk);
+      h->launches += 1;
+    }
+    cudaEventRecord(done[c], sk);
+    cudaStreamWaitEvent(sb, done[c], 0);
+    cudaMemcpyAsync(counts + f0, h->d_counts + f0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, sb);
+    cudaMemcpyAsync(kps + (size_t)f0 * cap, h->d_kps + (size_t)f0 * cap, sizeof(orbx_keypoint) * (size_t)n * cap, cudaMemcpyDeviceToHost, sb);
+    cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, h->d_desc + (size_t)f0 * cap * 32, (size_t)32 * n * cap, cudaMemcpyDeviceToHost, sb);
+    if (p1 > p0) {
+      const size_t o = (size_t)p0 * cap, cnt = (size_t)(p1 - p0) * cap;
+      cudaMemcpyAsync(m_idx + o, h->d_midx + o, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, sb);
+      cudaMemcpyAsync(m_d1 + o, h->d_md1 + o, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, sb);
+      cudaMemcpyAsync(m_d2 + o, h->d_md2 + o, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, sb);
+      cudaMemcpyAsync(m_ok + o, h->d_mok + o, cnt, cudaMemcpyDeviceToHost, sb);
+    }
+  }
+  cudaError_t e1 = cudaStreamSynchronize(sk), e2 = cudaStreamSynchronize(sb), e3 = cudaStreamSynchronize(sc);
+  for (int c = 0; c < nchunks; ++c) { cudaEventDestroy(up[c]); cudaEventDestroy(done[c]); }
+  if (rc) return rc;
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    set_error(cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    return ORBX_ERR_CUDA;
+  }
+  ORBX_CUDA(cudaGetLastError());
   return ORBX_OK;
 }
 

@@ -1,0 +1,83 @@
+"""Multi-GPU host logic: frame sharding (no collective) and map-scale sharded Hamming top-2 (one all-gather).
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch on the GPU box, gloo in CPU tests).
+
+* Frames (BASELINE config 2) are independent units: rank r owns a contiguous block; nothing is exchanged.
+* Map-scale brute-force kNN (BASELINE config 5): the train set is split into `world` contiguous index ranges
+  (rank r holds rows [r*per, min((r+1)*per, M))); queries are replicated.  Every rank computes its local top-2 with
+  global indices, the [Q,3] int32 records (idx, d1, d2) are all-gathered (12 B per query per rank) and every rank
+  runs the same merge: smallest d1 wins, lowest index wins ties (== the sequential scan of matcher.cpp:494-498),
+  second best = 2nd smallest of the multiset {d1_s, d2_s}.
+"""
+import numpy as np
+
+
+def frame_block(nframes, rank, world):
+    """Contiguous block [lo, hi) of `nframes` frames owned by `rank` (block sizes differ by at most one)."""
+    base, rem = divmod(nframes, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pair_block(nframes, rank, world):
+    """Frame-to-frame pairs (p, p+1) owned by `rank`: those whose FIRST frame is in the rank's block.  The block's
+    last pair needs frame hi, which belongs to the next rank: that boundary frame is replicated (returned as `halo`)."""
+    lo, hi = frame_block(nframes, rank, world)
+    p_hi = min(hi, nframes - 1)
+    halo = hi if (hi < nframes and hi > lo) else None
+    return lo, max(p_hi, lo), halo
+
+
+def train_shard(M, rank, world):
+    """Rows [lo, hi) of the train/map descriptor set held by `rank`."""
+    per = (M + world - 1) // world
+    lo = min(rank * per, M)
+    return lo, min(lo + per, M)
+
+
+def merge_top2_numpy(idx, d1, d2):
+    """Merge rule on host arrays [S, Q] (used by the CPU tests of the sharding logic; the GPU path runs
+    hamm_knn2_merge_device).  Shards must be in ascending train-index order."""
+    S, Q = d1.shape
+    b1 = np.full(Q, 256, np.int32); b2 = np.full(Q, 256, np.int32); bi = np.full(Q, -1, np.int32)
+    for s in range(S):
+        better = d1[s] < b1
+        b2 = np.where(better, np.minimum(b1, d2[s]), np.minimum(b2, d1[s]))
+        bi = np.where(better, idx[s], bi)
+        b1 = np.where(better, d1[s], b1)
+    return bi, b1, b2
+
+
+def allgather_records(rec, dist):
+    """All-gather a [Q,3] int32 tensor (idx, d1, d2) from every rank -> [world, Q, 3] (works for nccl and gloo)."""
+    import torch
+    world = dist.get_world_size()
+    out = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec.contiguous()) if rec.is_cuda else dist.all_gather(list(out.unbind(0)), rec.contiguous())
+    return out
+
+
+def sharded_knn2_cuda(d_q, d_t_local, shard_lo, th, ratio, dist, stream=None):
+    """Local shard top-2 on this rank's GPU, NCCL all-gather of the records, merge kernel.  torch CUDA tensors in,
+    (idx, d1, d2, ok) torch CUDA tensors out.  d_t_local holds train rows [shard_lo, shard_lo + len)."""
+    import torch
+    from . import api
+    Q, Ml = d_q.shape[0], d_t_local.shape[0]
+    dev = d_q.device
+    idx = torch.empty(Q, dtype=torch.int32, device=dev); d1 = torch.empty_like(idx); d2 = torch.empty_like(idx)
+    ok = torch.empty(Q, dtype=torch.uint8, device=dev)
+    wsb = api.knn2_workspace_bytes(Q, Ml)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    api.knn2_device(d_q.data_ptr(), Q, d_t_local.data_ptr(), Ml, th, ratio, idx.data_ptr(), d1.data_ptr(), d2.data_ptr(),
+                    ok.data_ptr(), ws.data_ptr(), wsb, st)
+    idx = torch.where(idx >= 0, idx + shard_lo, idx)          # local -> global row index
+    rec = torch.stack([idx, d1, d2], dim=1).contiguous()
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    if world == 1:
+        return idx, d1, d2, ok
+    allrec = allgather_records(rec, dist)                      # [world, Q, 3]
+    parts = allrec.permute(2, 0, 1).contiguous()               # [3, world, Q]
+    api.knn2_merge_device(parts[0].data_ptr(), parts[1].data_ptr(), parts[2].data_ptr(), world, Q, th, ratio,
+                          idx.data_ptr(), d1.data_ptr(), d2.data_ptr(), ok.data_ptr(), st)
+    return idx, d1, d2, ok
