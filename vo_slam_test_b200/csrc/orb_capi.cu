@@ -122,6 +122,7 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
     L.w = cv_round_f((float)W * s);                    // ORBextractor.cpp:1119-1120
     L.h = cv_round_f((float)H * s);
     L.regW = L.w - 2 * kMinBorder; L.regH = L.h - 2 * kMinBorder;
+    if (L.regW >= 30 && L.regH >= 30 && ((L.regW + L.regW / 30 - 1) / (L.regW / 30) > 63 || (L.regH + L.regH / 30 - 1) / (L.regH / 30) > 63)) { set_error("cell size out of range"); return ORBX_ERR_SHAPE; }
     if (L.regW < 30 || L.regH < 30) { set_error("image too small for the pyramid: a level's FAST region is < 30 px"); return ORBX_ERR_SHAPE; }
     if (L.regW > 4095 || L.regH > 4095) { set_error("image too large (level FAST region > 4095 px)"); return ORBX_ERR_SHAPE; }
     L.nCols = L.regW / 30; L.nRows = L.regH / 30;      // :791-792 (float division then truncation == integer division here)
@@ -150,6 +151,7 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
         }
         slotKeyBase.push_back(slotKeys);
         slotKeys += capSlot; levelKeys += capSlot;
+        G.fastSurvCap = std::max(G.fastSurvCap, capSlot);
       }
     }
     slot += L.nSlots;
@@ -161,7 +163,7 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
     L.blurTile0 = blurTile; blurTile += L.blurTilesX * L.blurTilesY;
     L.scale = h->scale[l];
     L.kpSize = (float)(int)(31 * h->scale[l]);             // :845
-    G.fastTileW = std::max(G.fastTileW, align_up(std::min(kCellsPerCta, L.nCols) * L.wCell + 6, 4));
+    G.fastTileW = std::max(G.fastTileW, align_up(std::min(kCellsPerCta, L.nCols) * L.wCell + 6 + 15, 16));
     G.fastTileH = std::max(G.fastTileH, L.hCell + 6);
   }
   slotKeyBase.push_back(slotKeys);

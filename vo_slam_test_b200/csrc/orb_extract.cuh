@@ -48,7 +48,8 @@ struct Geom {
   int nodeCap;             // max nodes of any level's quadtree
   int maxSlotsPerLevel;
   int blurTiles;
-  int fastTileW, fastTileH;  // smem tile extents of the FAST kernel
+  int fastTileW, fastTileH;  // smem tile extents of the FAST kernel (pitch is a multiple of 16)
+  int fastSurvCap;           // largest slot capacity (NMS survivors of one CTA)
   LevelGeom L[kMaxLevels];
 };
 

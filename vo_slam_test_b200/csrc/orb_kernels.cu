@@ -88,10 +88,13 @@ __device__ __forceinline__ int fast_best(const uint8_t* p, int pitch, int c) {
 }
 
 __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const Bufs B) {
+  // Work-efficient layout: (1) tile staged with 16-byte loads, (2) a cheap 16-pixel-ring rejection test over all
+  // pixels that pushes the few survivors into a shared-memory queue, (3) the full arc score and the per-cell NMS run
+  // densely over that queue only, (4) survivors are ranked by (cell, row, column) to emit them in the reference order.
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ int cnt20[kCellsPerCta];
-  __shared__ int scan_ws[40];
-  const int tid = threadIdx.x;
+  __shared__ int cellCnt[kCellsPerCta];
+  __shared__ int qn, sn, retryMask;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = blockIdx.x, f = blockIdx.y;
   int l = 0;
   while (l + 1 < G.nlevels && slot >= G.L[l + 1].slot0) ++l;
@@ -108,111 +111,130 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
     if (tid == 0) *out_count = 0;
     return;
   }
-  const int sp = G.fastTileW;                   // smem pitch
-  uint8_t* img = smem;                          // [fastTileH][sp]
-  uint8_t* sc = smem + G.fastTileH * sp;        // corner strength, same layout
-  uint8_t* fl = sc + G.fastTileH * sp;          // keep flags: bit0 = survives NMS at iniTh, bit1 = at minTh
+  const int sp = G.fastTileW;                                  // smem row pitch (multiple of 16)
+  uint8_t* img = smem;                                         // [fastTileH][sp]
+  uint8_t* sc = smem + G.fastTileH * sp;                       // corner strength (0 = not a corner at the pass threshold)
+  uint16_t* queue = (uint16_t*)(sc + G.fastTileH * sp);        // yi<<8 | xi of pixels passing the rejection test
+  uint32_t* surv = (uint32_t*)(queue + G.fastTileH * sp);      // cell<<24 | yi<<12 | cx of NMS survivors
 
   int pitch;
   const uint8_t* lvl = level_ptr(G, B, l, f, pitch);
-  const uint8_t* base = lvl + (size_t)(kMinBorder + ty0) * pitch + kMinBorder + tx0;
-  for (int i = tid; i < th * tw; i += kFastThreads) {
-    const int y = i / tw, x = i - y * tw;
-    img[y * sp + x] = __ldg(base + (size_t)y * pitch + x);
-    sc[y * sp + x] = 0;
-    fl[y * sp + x] = 0;
+  const int gx0 = kMinBorder + tx0;
+  int ox = 0;
+  if ((((uintptr_t)lvl | (uintptr_t)pitch) & 15) == 0) {
+    ox = gx0 & 15;
+    const int wpr = (ox + tw + 15) >> 4;                       // 16-byte words per tile row
+    const uint8_t* base = lvl + (size_t)(kMinBorder + ty0) * pitch + (gx0 - ox);
+    for (int i = tid; i < th * wpr; i += kFastThreads) {
+      const int y = i / wpr, w = i - y * wpr;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)y * pitch) + w);
+      *reinterpret_cast<uint4*>(img + y * sp + 16 * w) = v;
+    }
+  } else {
+    const uint8_t* base = lvl + (size_t)(kMinBorder + ty0) * pitch + gx0;
+    for (int y = warp; y < th; y += kFastThreads / 32)
+      for (int x = lane; x < tw; x += 32) img[y * sp + x] = __ldg(base + (size_t)y * pitch + x);
   }
-  if (tid < kCellsPerCta) cnt20[tid] = 0;
+  for (int i = tid; i < (th * sp) >> 4; i += kFastThreads) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < kCellsPerCta) cellCnt[tid] = 0;
+  if (tid == 0) { qn = 0; sn = 0; retryMask = 0; }
   __syncthreads();
 
-  const int tmin = min(G.iniTh, G.minTh);
-  for (int i = tid; i < ih * iw; i += kFastThreads) {
-    const int y = i / iw + 3, x = i - (y - 3) * iw + 3;
-    const uint8_t* p = img + y * sp + x;
-    const int c = p[0];
-    const int lo = c - tmin, hi = c + tmin;
+  const int w1 = L.wCell, w2 = 2 * L.wCell, w3 = 3 * L.wCell;
+  const uint8_t* img0 = img + 3 * sp + 3 + ox;                 // interior origin
+  uint8_t* sc0 = sc + 3 * sp + 3 + ox;
+
+  int t = G.iniTh;
+  int mask = 0xF;                                              // cells taking part in this pass
+  for (int pass = 0; pass < 2; ++pass) {
+    // ---- rejection test (necessary condition of a 9-arc: every opposite ring pair has a bright / a dark member)
+    for (int yi = warp; yi < ih; yi += kFastThreads / 32) {
+      for (int xi = lane; xi < iw; xi += 32) {
+        const int jj = (xi >= w1) + (xi >= w2) + (xi >= w3);
+        if (!((mask >> jj) & 1)) continue;
+        const uint8_t* p = img0 + yi * sp + xi;
+        const int c = p[0];
+        const int lo = c - t, hi = c + t;
 #define FCODE(v) ((int)((v) < lo) | ((int)((v) > hi) << 1))
-    int m = FCODE(p[3 * sp]) | FCODE(p[-3 * sp]);
-    if (!m) continue;
-    m &= FCODE(p[3]) | FCODE(p[-3]);
-    if (!m) continue;
-    m &= FCODE(p[2 * sp + 2]) | FCODE(p[-2 * sp - 2]);
-    m &= FCODE(p[-2 * sp + 2]) | FCODE(p[2 * sp - 2]);
-    if (!m) continue;
-    m &= FCODE(p[3 * sp + 1]) | FCODE(p[-3 * sp - 1]);
-    m &= FCODE(p[sp + 3]) | FCODE(p[-sp - 3]);
-    m &= FCODE(p[-sp + 3]) | FCODE(p[sp - 3]);
-    m &= FCODE(p[-3 * sp + 1]) | FCODE(p[3 * sp - 1]);
-    if (!m) continue;
+        int m = FCODE(p[3 * sp]) | FCODE(p[-3 * sp]);
+        if (!m) continue;
+        m &= FCODE(p[3]) | FCODE(p[-3]);
+        if (!m) continue;
+        m &= FCODE(p[2 * sp + 2]) | FCODE(p[-2 * sp - 2]);
+        m &= FCODE(p[-2 * sp + 2]) | FCODE(p[2 * sp - 2]);
+        if (!m) continue;
+        m &= FCODE(p[3 * sp + 1]) | FCODE(p[-3 * sp - 1]);
+        m &= FCODE(p[sp + 3]) | FCODE(p[-sp - 3]);
+        m &= FCODE(p[-sp + 3]) | FCODE(p[sp - 3]);
+        m &= FCODE(p[-3 * sp + 1]) | FCODE(p[3 * sp - 1]);
+        if (!m) continue;
 #undef FCODE
-    const int best = fast_best(p, sp, c);
-    if (best > tmin) sc[y * sp + x] = (uint8_t)best;
-  }
-  __syncthreads();
-
-  // NMS inside each cell's own candidate rectangle (pixels outside it count as score 0, like the zeroed
-  // border rows/columns of cv::FAST on the cell ROI)
-  for (int i = tid; i < ih * iw; i += kFastThreads) {
-    const int yi = i / iw, xi = i - yi * iw;
-    const int v = sc[(yi + 3) * sp + xi + 3];
-    if (v == 0) continue;
-    const int jj = xi / L.wCell, cx = xi - jj * L.wCell;
-    const int cw = min(L.wCell, iw - jj * L.wCell);
-    const bool hasL = cx > 0, hasR = cx + 1 < cw, hasU = yi > 0, hasD = yi + 1 < ih;
-    const uint8_t* s = sc + (yi + 3) * sp + xi + 3;
-    int nb[8];
-    nb[0] = (hasU && hasL) ? s[-sp - 1] : 0;  nb[1] = hasU ? s[-sp] : 0;  nb[2] = (hasU && hasR) ? s[-sp + 1] : 0;
-    nb[3] = hasL ? s[-1] : 0;                 nb[4] = hasR ? s[1] : 0;
-    nb[5] = (hasD && hasL) ? s[sp - 1] : 0;   nb[6] = hasD ? s[sp] : 0;   nb[7] = (hasD && hasR) ? s[sp + 1] : 0;
-    int flags = 0;
-    if (v > G.iniTh) {
-      bool keep = true;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) keep &= !(nb[k] > G.iniTh && nb[k] >= v);
-      if (keep) { flags |= 1; atomicAdd(&cnt20[jj], 1); }
+        queue[atomicAdd(&qn, 1)] = (uint16_t)((yi << 8) | xi);
+      }
     }
-    if (v > G.minTh) {
-      bool keep = true;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) keep &= !(nb[k] > G.minTh && nb[k] >= v);
-      if (keep) flags |= 2;
+    __syncthreads();
+    const int nq = qn;
+    // ---- full arc score, densely over the queue
+    for (int k = tid; k < nq; k += kFastThreads) {
+      const int e = queue[k], yi = e >> 8, xi = e & 255;
+      const uint8_t* p = img0 + yi * sp + xi;
+      const int best = fast_best(p, sp, p[0]);
+      sc0[yi * sp + xi] = (uint8_t)(best > t ? best : 0);
     }
-    fl[(yi + 3) * sp + xi + 3] = (uint8_t)flags;
+    __syncthreads();
+    // ---- 3x3 NMS inside each cell's own candidate rectangle (outside counts as score 0, like the zeroed border of
+    //      cv::FAST on the cell ROI); strict '>' against all eight neighbours
+    for (int k = tid; k < nq; k += kFastThreads) {
+      const int e = queue[k], yi = e >> 8, xi = e & 255;
+      const uint8_t* s = sc0 + yi * sp + xi;
+      const int v = s[0];
+      if (v == 0) continue;
+      const int jj = (xi >= w1) + (xi >= w2) + (xi >= w3);
+      const int cx = xi - jj * L.wCell;
+      const int cw = min(L.wCell, iw - jj * L.wCell);
+      const bool hasL = cx > 0, hasR = cx + 1 < cw, hasU = yi > 0, hasD = yi + 1 < ih;
+      bool keep = true;
+      keep &= !(hasU && hasL && s[-sp - 1] >= v);
+      keep &= !(hasU && s[-sp] >= v);
+      keep &= !(hasU && hasR && s[-sp + 1] >= v);
+      keep &= !(hasL && s[-1] >= v);
+      keep &= !(hasR && s[1] >= v);
+      keep &= !(hasD && hasL && s[sp - 1] >= v);
+      keep &= !(hasD && s[sp] >= v);
+      keep &= !(hasD && hasR && s[sp + 1] >= v);
+      if (keep) {
+        atomicAdd(&cellCnt[jj], 1);
+        surv[atomicAdd(&sn, 1)] = ((uint32_t)jj << 24) | ((uint32_t)yi << 12) | (uint32_t)cx;
+      }
+    }
+    __syncthreads();
+    // ---- cells that came back empty are retried at minThFAST (ORBextractor.cpp:820-824)
+    if (pass == 1 || G.minTh >= G.iniTh) break;
+    if (tid == 0) {
+      int r = 0;
+      for (int jj = 0; jj < j1 - j0; ++jj)
+        if (cellCnt[jj] == 0 && jj * L.wCell < iw) r |= 1 << jj;
+      retryMask = r;
+      qn = 0;
+    }
+    __syncthreads();
+    mask = retryMask;
+    if (mask == 0) break;
+    t = G.minTh;
   }
-  __syncthreads();
 
-  // ordered compaction: cells left to right, inside a cell row-major (the order cv::FAST emits and the
-  // reference appends, ORBextractor.cpp:826-834)
-  const int ncell = j1 - j0;
-  const int cellSeq = ih * L.wCell;
-  const int total = ncell * cellSeq;
-  const int per = (total + kFastThreads - 1) / kFastThreads;
-  const int s0 = min(tid * per, total), s1 = min(s0 + per, total);
-  auto kept = [&](int s, int& xi, int& yi) -> bool {
-    const int jj = s / cellSeq, r = s - jj * cellSeq;
-    yi = r / L.wCell;
-    const int cx = r - yi * L.wCell;
-    xi = jj * L.wCell + cx;
-    if (xi >= iw) return false;
-    const int need = (cnt20[jj] > 0) ? 1 : 2;
-    return (fl[(yi + 3) * sp + xi + 3] & need) != 0;
-  };
-  int mine = 0, xi, yi;
-  for (int s = s0; s < s1; ++s) mine += kept(s, xi, yi) ? 1 : 0;
-  // block exclusive scan of `mine`
-  __shared__ int offs[kFastThreads];
-  offs[tid] = mine;
-  __syncthreads();
-  const int totalKept = block_exclusive_scan(offs, kFastThreads, scan_ws);
-  int pos = offs[tid];
+  // ---- ordered emission: rank of a survivor = number of survivors with a smaller (cell, row, column) key
+  const int S = sn;
   uint32_t* out = B.slotKeys + (size_t)f * G.slotKeysPerFrame + __ldg(B.slotKeyBase + slot);
-  for (int s = s0; s < s1; ++s) {
-    if (kept(s, xi, yi)) {
-      const int best = sc[(yi + 3) * sp + xi + 3];
-      out[pos++] = pack_key(tx0 + xi + 3, ty0 + yi + 3, best - 1);
-    }
+  for (int k = tid; k < S; k += kFastThreads) {
+    const uint32_t key = surv[k];
+    int rank = 0;
+    for (int j = 0; j < S; ++j) rank += surv[j] < key ? 1 : 0;
+    const int jj = key >> 24, yi = (key >> 12) & 0xFFF, cx = key & 0xFFF;
+    const int xi = jj * L.wCell + cx;
+    out[rank] = pack_key(tx0 + xi + 3, ty0 + yi + 3, sc0[yi * sp + xi] - 1);
   }
-  if (tid == 0) *out_count = totalKept;
+  if (tid == 0) *out_count = S;
 }
 
 // ======================================================================================================
@@ -477,6 +499,7 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const Geom G, const
 // 64x32 output tile, horizontal pass into shared u16, vertical pass out of it.
 // ======================================================================================================
 constexpr int kBlurTW = 64, kBlurTH = 32;
+constexpr int kBlurInW = kBlurTW + 8;     // input tile columns: image x0-4 .. x0+TW+3 (whole 32-bit words)
 
 __device__ __forceinline__ int reflect101(int p, int len) {
   if (p < 0) p = -p;
@@ -485,8 +508,8 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 }
 
 __global__ void __launch_bounds__(256) blur_kernel(const Geom G, const Bufs B) {
-  __shared__ uint8_t tin[kBlurTH + 6][kBlurTW + 8];
-  __shared__ uint16_t hbuf[kBlurTH + 6][kBlurTW];
+  __shared__ __align__(16) uint8_t tin[kBlurTH + 6][kBlurInW];
+  __shared__ __align__(16) uint16_t hbuf[kBlurTH + 6][kBlurTW];
   const int tid = threadIdx.x, f = blockIdx.y;
   int l = 0;
   while (l + 1 < G.nlevels && (int)blockIdx.x >= G.L[l + 1].blurTile0) ++l;
@@ -496,27 +519,69 @@ __global__ void __launch_bounds__(256) blur_kernel(const Geom G, const Bufs B) {
   const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
   int pitch;
   const uint8_t* src = level_ptr(G, B, l, f, pitch);
-  for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256) {
-    const int r = i / (kBlurTW + 6), c = i - r * (kBlurTW + 6);
+  const bool aligned = (((uintptr_t)src | (uintptr_t)pitch) & 3) == 0;
+  // ---- stage (TH+6) x (TW+8) input bytes as 32-bit words; words touching the image border are assembled with
+  //      BORDER_REFLECT_101 addressing
+  constexpr int WPR = kBlurInW / 4;   // 18 words per row
+  for (int i = tid; i < (kBlurTH + 6) * WPR; i += 256) {
+    const int r = i / WPR, w = i - r * WPR;
     const int sy = reflect101(min(y0 + r - 3, L.h + 2), L.h);
-    const int sx = reflect101(min(x0 + c - 3, L.w + 2), L.w);
-    tin[r][c] = __ldg(src + (size_t)sy * pitch + sx);
+    const int gx = x0 - 4 + 4 * w;
+    const uint8_t* row = src + (size_t)sy * pitch;
+    uint32_t v;
+    if (aligned && gx >= 0 && gx + 3 < L.w) {
+      v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+    } else {
+      v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int sx = reflect101(min(max(gx + b, -3), L.w + 2), L.w);
+        v |= (uint32_t)__ldg(row + sx) << (8 * b);
+      }
+    }
+    *reinterpret_cast<uint32_t*>(&tin[r][4 * w]) = v;
   }
   __syncthreads();
-  for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
-    const int r = i / kBlurTW, c = i - r * kBlurTW;
-    const uint8_t* p = &tin[r][c];
-    hbuf[r][c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+  // ---- horizontal pass: one thread = 4 adjacent outputs of one row (8.8 fixed point, exact in u16)
+  for (int i = tid; i < (kBlurTH + 6) * (kBlurTW / 4); i += 256) {
+    const int r = i >> 4, q = i & 15;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(&tin[r][4 * q]);
+    const uint32_t a = wp[0], b = wp[1], c = wp[2];
+    // bytes p[0..11] = image x0-4+4q .. ; output xl = 4q+k uses p[k+1 .. k+7]
+    int p[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { p[k] = (a >> (8 * k)) & 255; p[4 + k] = (b >> (8 * k)) & 255; p[8 + k] = (c >> (8 * k)) & 255; }
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = 18 * (p[k + 1] + p[k + 7]) + 34 * (p[k + 2] + p[k + 6]) + 48 * (p[k + 3] + p[k + 5]) + 56 * p[k + 4];
+    *reinterpret_cast<uint2*>(&hbuf[r][4 * q]) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
   }
   __syncthreads();
+  // ---- vertical pass: one thread = 4 adjacent columns x 2 rows, one 32-bit store per row
   uint8_t* dst = B.blur + L.blurOff + (size_t)f * L.h * L.bpitch;
-  for (int i = tid; i < kBlurTH * kBlurTW; i += 256) {
-    const int r = i / kBlurTW, c = i - r * kBlurTW;
-    const int y = y0 + r, x = x0 + c;
-    if (y < L.h && x < L.w) {
-      const uint32_t acc = 18u * (hbuf[r][c] + hbuf[r + 6][c]) + 34u * (hbuf[r + 1][c] + hbuf[r + 5][c]) +
-                           48u * (hbuf[r + 2][c] + hbuf[r + 4][c]) + 56u * hbuf[r + 3][c] + 32768u;
-      dst[(size_t)y * L.bpitch + x] = (uint8_t)(acc >> 16);
+  {
+    const int q = tid & 15, g = tid >> 4;          // g: 0..15 -> output rows 2g, 2g+1
+    uint32_t h[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint2 v = *reinterpret_cast<const uint2*>(&hbuf[2 * g + r][4 * q]);
+      h[r][0] = v.x & 0xFFFF; h[r][1] = v.x >> 16; h[r][2] = v.y & 0xFFFF; h[r][3] = v.y >> 16;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int y = y0 + 2 * g + rr, x = x0 + 4 * q;
+      if (y >= L.h || x >= L.w) continue;
+      uint32_t packed = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t acc = 18u * (h[rr][k] + h[rr + 6][k]) + 34u * (h[rr + 1][k] + h[rr + 5][k]) +
+                             48u * (h[rr + 2][k] + h[rr + 4][k]) + 56u * h[rr + 3][k] + 32768u;
+        packed |= (acc >> 16) << (8 * k);
+      }
+      uint8_t* d = dst + (size_t)y * L.bpitch + x;
+      if (x + 3 < L.w) *reinterpret_cast<uint32_t*>(d) = packed;     // bpitch is a multiple of 64, x of 4
+      else for (int k = 0; x + k < L.w; ++k) d[k] = (uint8_t)(packed >> (8 * k));
     }
   }
 }
@@ -582,11 +647,39 @@ __device__ __forceinline__ void glibc_sincosf(float y, float& s_out, float& c_ou
   if (n & 1) { s_out = cosv; c_out = sinv; } else { s_out = sinv; c_out = cosv; }
 }
 
+constexpr int kPatchRowsU = 31, kPatchPitchU = 44;   // unblurred 31x31 patch rows, 44-byte pitch (11 words: conflict-free rows)
+constexpr int kPatchRowsB = 37, kPatchPitchB = 52;   // blurred 37x37 patch (+-18), 52-byte pitch (13 words)
+constexpr int kPatchBytes = kPatchRowsU * kPatchPitchU + kPatchRowsB * kPatchPitchB;   // 3288 B per warp
+
+// Stage rows [y-R, y+R] x columns [x-R, x+R] of an image into shared memory (one warp), as aligned 32-bit words when the
+// image allows it.  Returns the column offset `ox` such that patch(r, c) = dst[r*P + ox + c], c = 0 <-> image column x-R.
+template <int R, int P>
+__device__ __forceinline__ int stage_patch(uint8_t* dst, const uint8_t* img, int pitch, int x, int y, int lane) {
+  constexpr int ROWS = 2 * R + 1;
+  const uint8_t* base = img + (size_t)(y - R) * pitch + (x - R);
+  if ((((uintptr_t)img | (uintptr_t)pitch) & 3) == 0) {
+    const int ox = (int)((uintptr_t)base & 3);
+    constexpr int WPR = (ROWS + 3 + 3) / 4;          // words per row covering ox + ROWS bytes
+    const uint8_t* abase = base - ox;
+    for (int i = lane; i < ROWS * WPR; i += 32) {
+      const int r = i / WPR, w = i - r * WPR;
+      *reinterpret_cast<uint32_t*>(dst + r * P + 4 * w) = __ldg(reinterpret_cast<const uint32_t*>(abase + (size_t)r * pitch) + w);
+    }
+    return ox;
+  }
+  for (int i = lane; i < ROWS * ROWS; i += 32) {
+    const int r = i / ROWS, c = i - r * ROWS;
+    dst[r * P + c] = __ldg(base + (size_t)r * pitch + c);
+  }
+  return 0;
+}
+
 __global__ void __launch_bounds__(256) orient_desc_kernel(const Geom G, const Bufs B, orbx_keypoint* __restrict__ kps_out,
                                                           uint8_t* __restrict__ desc_out, int cap,
                                                           int32_t* __restrict__ counts_out, int frame0) {
-  const int lane = threadIdx.x & 31;
-  const int slotIdx = blockIdx.x * 8 + (threadIdx.x >> 5);   // index into the per-frame selected array
+  __shared__ __align__(16) uint8_t patches[8][kPatchBytes + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slotIdx = blockIdx.x * 8 + warp;   // index into the per-frame selected array
   const int f = blockIdx.y;
   if (slotIdx >= G.selPerFrame) return;
   int l = 0;
@@ -603,22 +696,27 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(const Geom G, const Bu
   if (slotIdx == 0 && lane == 0) counts_out[frame0 + f] = total;
   if (i >= selCount[l]) return;
   const int o = before + i;
-  if (o >= cap) return;   // caller buffer smaller than the keypoint count: count is still reported
+  if (o >= cap) return;   // caller buffer smaller than the keypoint count: the count is still reported
 
   const uint32_t key = B.sel[(size_t)f * G.selPerFrame + slotIdx];
   const int x = key_x(key) + kMinBorder, y = key_y(key) + kMinBorder;   // (ORBextractor.cpp:851-852)
   int pitch;
   const uint8_t* img = level_ptr(G, B, l, f, pitch);
+  uint8_t* pu = patches[warp];
+  uint8_t* pb = pu + kPatchRowsU * kPatchPitchU;
+  const int oxu = stage_patch<15, kPatchPitchU>(pu, img, pitch, x, y, lane);
+  const int oxb = stage_patch<18, kPatchPitchB>(pb, B.blur + L.blurOff + (size_t)f * L.h * L.bpitch, L.bpitch, x, y, lane);
+  __syncwarp();
 
   // ---- moments over the radius-15 disc: lane <-> row v = lane-15 --------------------------------------
   int m10 = 0, m01 = 0;
   if (lane < 31) {
     const int v = lane - 15;
     const int d = __ldg(B.umax + abs(v));
-    const uint8_t* row = img + (size_t)(y + v) * pitch + x;
+    const uint8_t* row = pu + lane * kPatchPitchU + oxu + 15;
     int sum = 0;
     for (int u = -d; u <= d; ++u) {
-      const int p = __ldg(row + u);
+      const int p = row[u];
       m10 += u * p;
       sum += p;
     }
@@ -628,11 +726,11 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(const Geom G, const Bu
   m01 = __reduce_add_sync(0xffffffffu, m01);
   const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-  // ---- rBRIEF on the blurred level ---------------------------------------------------------------------
+  // ---- rBRIEF on the blurred patch ---------------------------------------------------------------------
   const float factorPI = (float)(3.1415926535897932384626433832795 / (double)180.f);
   float a, b;
   glibc_sincosf(__fmul_rn(angle, factorPI), b, a);
-  const uint8_t* bl = B.blur + L.blurOff + (size_t)f * L.h * L.bpitch + (size_t)y * L.bpitch + x;
+  const uint8_t* bl = pb + 18 * kPatchPitchB + oxb + 18;
   const float2* pat = B.pattern + lane * 16;
   int val = 0;
 #pragma unroll
@@ -642,7 +740,7 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(const Geom G, const Bu
     const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(p0.x, a), __fmul_rn(p0.y, b)));
     const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(p1.x, b), __fmul_rn(p1.y, a)));
     const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(p1.x, a), __fmul_rn(p1.y, b)));
-    const int t0 = __ldg(bl + r0 * L.bpitch + c0), t1 = __ldg(bl + r1 * L.bpitch + c1);
+    const int t0 = bl[r0 * kPatchPitchB + c0], t1 = bl[r1 * kPatchPitchB + c1];
     val |= (t0 < t1) << j;
   }
   desc_out[((size_t)(frame0 + f) * cap + o) * 32 + lane] = (uint8_t)val;
@@ -662,7 +760,7 @@ void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe
   resize_kernel<<<grid, block, 0, st>>>(src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
 }
 
-size_t fast_smem_bytes(const Geom& G) { return (size_t)3 * G.fastTileW * G.fastTileH; }
+size_t fast_smem_bytes(const Geom& G) { return (size_t)4 * G.fastTileW * G.fastTileH + 4 * (size_t)G.fastSurvCap + 64; }
 
 size_t octree_smem_bytes(const Geom& G) {
   const size_t cap = G.nodeCap;
