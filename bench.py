@@ -241,13 +241,14 @@ def run_b200(args, rank, world, local_rank):
               for i, n in enumerate(names)}
     stages["hamming_pairs"] = {"ms_per_step": pair_ms, "gmatch_per_s": pair_matches / (pair_ms * 1e6)}
     dom = max(names, key=lambda n: stages[n]["ms_per_step"])
-    nchunks = (F + 63) // 64
+    chunk = int(os.environ.get("ORBX_CHUNK", "256"))
+    nchunks = (F + chunk - 1) // chunk
     dom_ms_launch = stages[dom]["ms_per_step"] / nchunks
-    achieved = ab[dom] * min(F, 64) / (dom_ms_launch * 1e6)
+    achieved = ab[dom] * min(F, chunk) / (dom_ms_launch * 1e6)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": None, "peak_source": peak_src,
                 "note": "algorithmic bytes/launch = %d B/frame x %d frames/launch; whole-frame figure %.2f MB/frame -> %.1f GB/s (frac %.4f)"
-                        % (ab[dom], min(F, 64), ab["frame_total"] / 1e6, ab["frame_total"] * value / world / 1e9,
+                        % (ab[dom], min(F, chunk), ab["frame_total"] / 1e6, ab["frame_total"] * value / world / 1e9,
                            ab["frame_total"] * value / world / 1e9 / hbm_peak)}
 
     # ---- map-scale sharded Hamming top-2 (BASELINE config 5 shape: 1k queries vs 2M rows per GPU) ---------
@@ -335,7 +336,7 @@ def run_b200(args, rank, world, local_rank):
                                        "levels, 1.2, FAST 20/7) + frame-to-frame Hamming kNN (k=2, TH_LOW 50, ratio 0.7); frames sharded, "
                                        "no collective" % F,
                            "frames_per_gpu": F, "l2": "inputs (%.2f GB per GPU) larger than L2" % (F * W_IMG * H_IMG / 1e9),
-                           "chunk_frames": 64, "mean_keypoints": float(counts.mean()), "accepted_matches_per_pair": accepted / max(npairs, 1)},
+                           "chunk_frames": int(os.environ.get("ORBX_CHUNK", "256")), "mean_keypoints": float(counts.mean()), "accepted_matches_per_pair": accepted / max(npairs, 1)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "orbx_extract_match_batch (host C ABI, pinned host buffers, copies inside the timed region)"},

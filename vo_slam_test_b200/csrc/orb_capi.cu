@@ -72,6 +72,8 @@ struct orbx_extractor {
 
 namespace {
 
+constexpr int kDefaultChunk = 256;
+
 int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
@@ -325,7 +327,12 @@ int orbx_create(const orbx_params* p, orbx_handle* out) {
     return ORBX_ERR_CUDA;
   }
   float2 pat[512];
-  for (int i = 0; i < 512; ++i) pat[i] = make_float2((float)orb_bit_pattern_31[2 * i], (float)orb_bit_pattern_31[2 * i + 1]);
+  // transposed for coalesced warp reads: entry [k][lane] = point k (0..15) of descriptor byte `lane`
+  for (int lane = 0; lane < 32; ++lane)
+    for (int k = 0; k < 16; ++k) {
+      const int i = lane * 16 + k;
+      pat[k * 32 + lane] = make_float2((float)orb_bit_pattern_31[2 * i], (float)orb_bit_pattern_31[2 * i + 1]);
+    }
   if (cudaMalloc(&h->d_pattern, sizeof(pat)) != cudaSuccess || cudaMalloc(&h->d_umax, sizeof(int) * 16) != cudaSuccess ||
       cudaMemcpy(h->d_pattern, pat, sizeof(pat), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(h->d_umax, h->umax, sizeof(int) * 16, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -394,7 +401,7 @@ int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes,
   }
   if (nframes == 0) return ORBX_OK;
   ORBX_CUDA(cudaSetDevice(h->p.device));
-  const int chunkMax = std::max(1, env_int("ORBX_CHUNK", 64));
+  const int chunkMax = std::max(1, env_int("ORBX_CHUNK", kDefaultChunk));
   const int chunk = std::min(nframes, chunkMax);
   int rc = configure(h, w, height, chunk);
   if (rc) return rc;
@@ -473,7 +480,7 @@ int orbx_profile_stages(orbx_handle h, const uint8_t* d_imgs, int nframes, int w
     return ORBX_ERR_ARG;
   }
   ORBX_CUDA(cudaSetDevice(h->p.device));
-  const int chunkMax = std::max(1, env_int("ORBX_CHUNK", 64));
+  const int chunkMax = std::max(1, env_int("ORBX_CHUNK", kDefaultChunk));
   int rc = configure(h, w, height, std::min(nframes, chunkMax));
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -514,7 +521,7 @@ int orbx_extract_match_batch(orbx_handle h, const uint8_t* imgs, int nframes, in
     return ORBX_ERR_ARG;
   }
   ORBX_CUDA(cudaSetDevice(h->p.device));
-  const int chunkMax = std::max(1, env_int("ORBX_CHUNK", 64));
+  const int chunkMax = std::max(1, env_int("ORBX_CHUNK", kDefaultChunk));
   int rc = configure(h, w, height, std::min(nframes, chunkMax));
   if (rc) return rc;
   const size_t pitch = align_up_sz((size_t)w, 64), fbytes = pitch * height;

@@ -731,11 +731,12 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(const Geom G, const Bu
   float a, b;
   glibc_sincosf(__fmul_rn(angle, factorPI), b, a);
   const uint8_t* bl = pb + 18 * kPatchPitchB + oxb + 18;
-  const float2* pat = B.pattern + lane * 16;
+  // pattern is stored transposed, [point-in-byte 0..15][byte/lane 0..31], so a warp reads 256 contiguous bytes
+  const float2* pat = B.pattern + lane;
   int val = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float2 p0 = __ldg(pat + 2 * j), p1 = __ldg(pat + 2 * j + 1);
+    const float2 p0 = __ldg(pat + 32 * (2 * j)), p1 = __ldg(pat + 32 * (2 * j + 1));
     const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(p0.x, b), __fmul_rn(p0.y, a)));
     const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(p0.x, a), __fmul_rn(p0.y, b)));
     const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(p1.x, b), __fmul_rn(p1.y, a)));
