@@ -145,7 +145,7 @@ def run_reference(args, rank, world):
                              "sample": "%d frames x %d steps, one extractor per core + threaded matcher" % (sample, args.steps)},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args, rank, world, local_rank):
@@ -343,11 +343,28 @@ def run_b200(args, rank, world, local_rank):
                 "gpu_launches": int(launches),
                 "roofline": roofline, "stages": stages, "hamming_gmatch_per_s": stages["hamming_pairs"]["gmatch_per_s"],
                 "hamming_map": hamming_map, "cpu_baseline": cpu_baseline}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ex.close()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else any library prints (e.g. NCCL's version banner)
+    was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -87,6 +87,80 @@ __device__ __forceinline__ int fast_best(const uint8_t* p, int pitch, int c) {
   return max(a, -b);
 }
 
+// ---- packed-byte helpers for the rejection test: one thread tests 4 horizontally adjacent centres at once ----------
+// W[0..3] = 16 bytes of one tile row starting at the 4-byte-aligned address at or below (xi-3); SH = misalignment.
+template <int SH, int DX>
+__device__ __forceinline__ uint32_t pick4(const uint32_t (&W)[4]) {
+  constexpr int off = SH + 3 + DX, wi = off >> 2, sft = (off & 3) * 8;
+  if (sft == 0) return W[wi];
+  return __funnelshift_r(W[wi], W[wi + 1], sft);
+}
+__device__ __forceinline__ void load_window(uint32_t (&W)[4], const uint8_t* p) {
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+  W[0] = q[0]; W[1] = q[1]; W[2] = q[2]; W[3] = q[3];
+}
+// per-byte |s - c| > t  ->  bit 7 of each byte.  kc = 0x7F7F7F7F - (t & 0x7F) * 0x01010101; hiT = (t >= 128).
+__device__ __forceinline__ uint32_t far4(uint32_t s, uint32_t c, uint32_t kc, bool hiT) {
+  const uint32_t a = __vabsdiffu4(s, c);
+  const uint32_t low = (a & 0x7F7F7F7Fu) + kc;          // bit 7 set iff (a & 0x7F) > (t & 0x7F)
+  return (hiT ? (a & low) : (a | low)) & 0x80808080u;
+}
+
+// Necessary condition of a FAST-9 corner (same shape as OpenCV's quick test, sign-agnostic): every opposite ring pair
+// has a member that differs from the centre by more than t.  Returns per-byte flags (bit 7) for the 4 centres.
+template <int SH>
+__device__ __forceinline__ uint32_t reject4(const uint8_t* rowm3, int sp, uint32_t kc, bool hiT) {
+  uint32_t Wp3[4], Wm3[4], W0[4];
+  load_window(Wm3, rowm3);
+  load_window(W0, rowm3 + 3 * sp);
+  load_window(Wp3, rowm3 + 6 * sp);
+  const uint32_t c = pick4<SH, 0>(W0);
+  uint32_t m = far4(pick4<SH, 0>(Wp3), c, kc, hiT) | far4(pick4<SH, 0>(Wm3), c, kc, hiT);     // ring 0 | 8
+  m &= far4(pick4<SH, 3>(W0), c, kc, hiT) | far4(pick4<SH, -3>(W0), c, kc, hiT);               // ring 4 | 12
+  if (m == 0) return 0;
+  m &= far4(pick4<SH, 1>(Wp3), c, kc, hiT) | far4(pick4<SH, -1>(Wm3), c, kc, hiT);             // ring 1 | 9
+  m &= far4(pick4<SH, 1>(Wm3), c, kc, hiT) | far4(pick4<SH, -1>(Wp3), c, kc, hiT);             // ring 7 | 15
+  if (m == 0) return 0;
+  uint32_t Wa[4], Wb[4];
+  load_window(Wa, rowm3 + 5 * sp);   // row +2
+  load_window(Wb, rowm3 + 1 * sp);   // row -2
+  m &= far4(pick4<SH, 2>(Wa), c, kc, hiT) | far4(pick4<SH, -2>(Wb), c, kc, hiT);               // ring 2 | 10
+  m &= far4(pick4<SH, 2>(Wb), c, kc, hiT) | far4(pick4<SH, -2>(Wa), c, kc, hiT);               // ring 6 | 14
+  if (m == 0) return 0;
+  load_window(Wa, rowm3 + 4 * sp);   // row +1
+  load_window(Wb, rowm3 + 2 * sp);   // row -1
+  m &= far4(pick4<SH, 3>(Wa), c, kc, hiT) | far4(pick4<SH, -3>(Wb), c, kc, hiT);               // ring 3 | 11
+  m &= far4(pick4<SH, 3>(Wb), c, kc, hiT) | far4(pick4<SH, -3>(Wa), c, kc, hiT);               // ring 5 | 13
+  return m;
+}
+
+// Corner strength of TWO pixels at once in packed signed 16-bit lanes (VIMNMX.S16x2).
+__device__ __forceinline__ void fast_best2(const uint8_t* pa, const uint8_t* pb, int sp, int& bestA, int& bestB) {
+  const int ca = pa[0], cb = pb[0];
+  uint32_t d[16];
+#define D2(k, off) d[k] = __byte_perm((uint32_t)(ca - pa[off]), (uint32_t)(cb - pb[off]), 0x5410)
+  D2(0, 3 * sp);       D2(1, 3 * sp + 1);   D2(2, 2 * sp + 2);    D2(3, sp + 3);
+  D2(4, 3);            D2(5, -sp + 3);      D2(6, -2 * sp + 2);   D2(7, -3 * sp + 1);
+  D2(8, -3 * sp);      D2(9, -3 * sp - 1);  D2(10, -2 * sp - 2);  D2(11, -sp - 3);
+  D2(12, -3);          D2(13, sp - 3);      D2(14, 2 * sp - 2);   D2(15, 3 * sp - 1);
+#undef D2
+  uint32_t mn2[16], mx2[16], mn4[16], mx4[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { mn2[k] = __vmins2(d[k], d[(k + 1) & 15]); mx2[k] = __vmaxs2(d[k], d[(k + 1) & 15]); }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { mn4[k] = __vmins2(mn2[k], mn2[(k + 2) & 15]); mx4[k] = __vmaxs2(mx2[k], mx2[(k + 2) & 15]); }
+  uint32_t a = 0x80008000u, b = 0x7FFF7FFFu;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t mn9 = __vmins2(__vmins2(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+    const uint32_t mx9 = __vmaxs2(__vmaxs2(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+    a = __vmaxs2(a, mn9);
+    b = __vmins2(b, mx9);
+  }
+  bestA = max((int)(short)(a & 0xFFFF), -(int)(short)(b & 0xFFFF));
+  bestB = max((int)(short)(a >> 16), -(int)(short)(b >> 16));
+}
+
 __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const Bufs B) {
   // Work-efficient layout: (1) tile staged with 16-byte loads, (2) a cheap 16-pixel-ring rejection test over all
   // pixels that pushes the few survivors into a shared-memory queue, (3) the full arc score and the per-cell NMS run
@@ -147,39 +221,45 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
   int t = G.iniTh;
   int mask = 0xF;                                              // cells taking part in this pass
   for (int pass = 0; pass < 2; ++pass) {
-    // ---- rejection test (necessary condition of a 9-arc: every opposite ring pair has a bright / a dark member)
-    for (int yi = warp; yi < ih; yi += kFastThreads / 32) {
-      for (int xi = lane; xi < iw; xi += 32) {
-        const int jj = (xi >= w1) + (xi >= w2) + (xi >= w3);
-        if (!((mask >> jj) & 1)) continue;
-        const uint8_t* p = img0 + yi * sp + xi;
-        const int c = p[0];
-        const int lo = c - t, hi = c + t;
-#define FCODE(v) ((int)((v) < lo) | ((int)((v) > hi) << 1))
-        int m = FCODE(p[3 * sp]) | FCODE(p[-3 * sp]);
-        if (!m) continue;
-        m &= FCODE(p[3]) | FCODE(p[-3]);
-        if (!m) continue;
-        m &= FCODE(p[2 * sp + 2]) | FCODE(p[-2 * sp - 2]);
-        m &= FCODE(p[-2 * sp + 2]) | FCODE(p[2 * sp - 2]);
-        if (!m) continue;
-        m &= FCODE(p[3 * sp + 1]) | FCODE(p[-3 * sp - 1]);
-        m &= FCODE(p[sp + 3]) | FCODE(p[-sp - 3]);
-        m &= FCODE(p[-sp + 3]) | FCODE(p[sp - 3]);
-        m &= FCODE(p[-3 * sp + 1]) | FCODE(p[3 * sp - 1]);
-        if (!m) continue;
-#undef FCODE
-        queue[atomicAdd(&qn, 1)] = (uint16_t)((yi << 8) | xi);
+    // ---- rejection test, 4 adjacent centres per thread in packed bytes (see reject4); survivors go to the queue
+    {
+      const uint32_t kc = 0x7F7F7F7Fu - (uint32_t)(t & 0x7F) * 0x01010101u;
+      const bool hiT = t >= 128;
+      const int nq4 = (iw + 3) >> 2;
+      const int sh = ox & 3;
+      for (int item = tid; item < ih * nq4; item += kFastThreads) {
+        const int yi = item / nq4, q4 = item - yi * nq4;
+        const int xi = 4 * q4;
+        // cells of the 4 pixels (a quad can straddle a cell boundary)
+        const uint8_t* rowm3 = img + yi * sp + ((ox + xi) & ~3);      // tile row yi (= interior row yi - 3), aligned window
+        uint32_t m;
+        switch (sh) {
+          case 0: m = reject4<0>(rowm3, sp, kc, hiT); break;
+          case 1: m = reject4<1>(rowm3, sp, kc, hiT); break;
+          case 2: m = reject4<2>(rowm3, sp, kc, hiT); break;
+          default: m = reject4<3>(rowm3, sp, kc, hiT); break;
+        }
+        if (m == 0) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int x = xi + k;
+          if (!((m >> (8 * k + 7)) & 1) || x >= iw) continue;
+          const int jj = (x >= w1) + (x >= w2) + (x >= w3);
+          if (!((mask >> jj) & 1)) continue;
+          queue[atomicAdd(&qn, 1)] = (uint16_t)((yi << 8) | x);
+        }
       }
     }
     __syncthreads();
     const int nq = qn;
-    // ---- full arc score, densely over the queue
-    for (int k = tid; k < nq; k += kFastThreads) {
-      const int e = queue[k], yi = e >> 8, xi = e & 255;
-      const uint8_t* p = img0 + yi * sp + xi;
-      const int best = fast_best(p, sp, p[0]);
-      sc0[yi * sp + xi] = (uint8_t)(best > t ? best : 0);
+    // ---- full arc score, densely over the queue, two entries per thread (packed 16-bit min/max network)
+    for (int k = tid; 2 * k < nq; k += kFastThreads) {
+      const int e0 = queue[2 * k], e1 = queue[min(2 * k + 1, nq - 1)];
+      const int y0 = e0 >> 8, x0 = e0 & 255, y1 = e1 >> 8, x1 = e1 & 255;
+      int b0, b1;
+      fast_best2(img0 + y0 * sp + x0, img0 + y1 * sp + x1, sp, b0, b1);
+      sc0[y0 * sp + x0] = (uint8_t)(b0 > t ? b0 : 0);
+      sc0[y1 * sp + x1] = (uint8_t)(b1 > t ? b1 : 0);
     }
     __syncthreads();
     // ---- 3x3 NMS inside each cell's own candidate rectangle (outside counts as score 0, like the zeroed border of
