@@ -161,7 +161,7 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
     L.pitch = align_up(L.w, 64); L.bpitch = align_up(L.w, 64);
     if (l > 0) { L.pyrOff = pyrBytes; pyrBytes += (size_t)chunk * L.h * L.pitch; }
     L.blurOff = blurBytes; blurBytes += (size_t)chunk * L.h * L.bpitch;
-    L.blurTilesX = (L.w + 63) / 64; L.blurTilesY = (L.h + 31) / 32;
+    L.blurTilesX = (L.w + 63) / 64; L.blurTilesY = (L.h + 25) / 26;   // kBlurTW x kBlurTH of orb_kernels.cu
     L.blurTile0 = blurTile; blurTile += L.blurTilesX * L.blurTilesY;
     L.scale = h->scale[l];
     L.kpSize = (float)(int)(31 * h->scale[l]);             // :845

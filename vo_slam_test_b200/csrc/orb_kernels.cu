@@ -107,9 +107,10 @@ __device__ __forceinline__ uint32_t far4(uint32_t s, uint32_t c, uint32_t kc, bo
 }
 
 // Necessary condition of a FAST-9 corner (same shape as OpenCV's quick test, sign-agnostic): every opposite ring pair
-// has a member that differs from the centre by more than t.  Returns per-byte flags (bit 7) for the 4 centres.
+// has a member that differs from the centre by more than t.  Per-byte flags (bit 7) for the 4 centres, in two stages so
+// that the second one can run densely over the items that survived the first.
 template <int SH>
-__device__ __forceinline__ uint32_t reject4(const uint8_t* rowm3, int sp, uint32_t kc, bool hiT) {
+__device__ __forceinline__ uint32_t reject4_a(const uint8_t* rowm3, int sp, uint32_t kc, bool hiT) {   // rows -3, 0, +3
   uint32_t Wp3[4], Wm3[4], W0[4];
   load_window(Wm3, rowm3);
   load_window(W0, rowm3 + 3 * sp);
@@ -117,16 +118,19 @@ __device__ __forceinline__ uint32_t reject4(const uint8_t* rowm3, int sp, uint32
   const uint32_t c = pick4<SH, 0>(W0);
   uint32_t m = far4(pick4<SH, 0>(Wp3), c, kc, hiT) | far4(pick4<SH, 0>(Wm3), c, kc, hiT);     // ring 0 | 8
   m &= far4(pick4<SH, 3>(W0), c, kc, hiT) | far4(pick4<SH, -3>(W0), c, kc, hiT);               // ring 4 | 12
-  if (m == 0) return 0;
   m &= far4(pick4<SH, 1>(Wp3), c, kc, hiT) | far4(pick4<SH, -1>(Wm3), c, kc, hiT);             // ring 1 | 9
   m &= far4(pick4<SH, 1>(Wm3), c, kc, hiT) | far4(pick4<SH, -1>(Wp3), c, kc, hiT);             // ring 7 | 15
-  if (m == 0) return 0;
-  uint32_t Wa[4], Wb[4];
+  return m;
+}
+template <int SH>
+__device__ __forceinline__ uint32_t reject4_b(const uint8_t* rowm3, int sp, uint32_t kc, bool hiT, uint32_t m) {   // rows +-1, +-2
+  uint32_t W0[4], Wa[4], Wb[4];
+  load_window(W0, rowm3 + 3 * sp);
+  const uint32_t c = pick4<SH, 0>(W0);
   load_window(Wa, rowm3 + 5 * sp);   // row +2
   load_window(Wb, rowm3 + 1 * sp);   // row -2
   m &= far4(pick4<SH, 2>(Wa), c, kc, hiT) | far4(pick4<SH, -2>(Wb), c, kc, hiT);               // ring 2 | 10
   m &= far4(pick4<SH, 2>(Wb), c, kc, hiT) | far4(pick4<SH, -2>(Wa), c, kc, hiT);               // ring 6 | 14
-  if (m == 0) return 0;
   load_window(Wa, rowm3 + 4 * sp);   // row +1
   load_window(Wb, rowm3 + 2 * sp);   // row -1
   m &= far4(pick4<SH, 3>(Wa), c, kc, hiT) | far4(pick4<SH, -3>(Wb), c, kc, hiT);               // ring 3 | 11
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
   // densely over that queue only, (4) survivors are ranked by (cell, row, column) to emit them in the reference order.
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int cellCnt[kCellsPerCta];
-  __shared__ int qn, sn, retryMask;
+  __shared__ int qn, sn, in, retryMask;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = blockIdx.x, f = blockIdx.y;
   int l = 0;
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
   uint8_t* sc = smem + G.fastTileH * sp;                       // corner strength (0 = not a corner at the pass threshold)
   uint16_t* queue = (uint16_t*)(sc + G.fastTileH * sp);        // yi<<8 | xi of pixels passing the rejection test
   uint32_t* surv = (uint32_t*)(queue + G.fastTileH * sp);      // cell<<24 | yi<<12 | cx of NMS survivors
+  uint16_t* itemq = (uint16_t*)(surv + G.fastSurvCap);         // quads surviving rejection stage a: item | flags<<12
 
   int pitch;
   const uint8_t* lvl = level_ptr(G, B, l, f, pitch);
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
   }
   for (int i = tid; i < (th * sp) >> 4; i += kFastThreads) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
   if (tid < kCellsPerCta) cellCnt[tid] = 0;
-  if (tid == 0) { qn = 0; sn = 0; retryMask = 0; }
+  if (tid == 0) { qn = 0; sn = 0; in = 0; retryMask = 0; }
   __syncthreads();
 
   const int w1 = L.wCell, w2 = 2 * L.wCell, w3 = 3 * L.wCell;
@@ -221,32 +226,59 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
   int t = G.iniTh;
   int mask = 0xF;                                              // cells taking part in this pass
   for (int pass = 0; pass < 2; ++pass) {
-    // ---- rejection test, 4 adjacent centres per thread in packed bytes (see reject4); survivors go to the queue
+    // ---- rejection test, 4 adjacent centres per thread in packed bytes.  Stage a (rows -3,0,+3) runs over every
+    //      quad; quads with a surviving centre are queued and stage b (rows +-1,+-2) runs densely over that queue;
+    //      surviving centres go to the pixel queue.
     {
       const uint32_t kc = 0x7F7F7F7Fu - (uint32_t)(t & 0x7F) * 0x01010101u;
       const bool hiT = t >= 128;
       const int nq4 = (iw + 3) >> 2;
+      const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nq4 + 1;            // item / nq4 == umulhi(item, magic) for item < 2^16
       const int sh = ox & 3;
+      const int aox = ox & ~3;
       for (int item = tid; item < ih * nq4; item += kFastThreads) {
-        const int yi = item / nq4, q4 = item - yi * nq4;
-        const int xi = 4 * q4;
-        // cells of the 4 pixels (a quad can straddle a cell boundary)
-        const uint8_t* rowm3 = img + yi * sp + ((ox + xi) & ~3);      // tile row yi (= interior row yi - 3), aligned window
+        const int yi = nq4 == 1 ? item : (int)__umulhi((uint32_t)item, magic), xi = 4 * (item - yi * nq4);
+        const uint8_t* rowm3 = img + yi * sp + aox + xi;                // tile row yi (= interior row yi - 3), aligned window
         uint32_t m;
         switch (sh) {
-          case 0: m = reject4<0>(rowm3, sp, kc, hiT); break;
-          case 1: m = reject4<1>(rowm3, sp, kc, hiT); break;
-          case 2: m = reject4<2>(rowm3, sp, kc, hiT); break;
-          default: m = reject4<3>(rowm3, sp, kc, hiT); break;
+          case 0: m = reject4_a<0>(rowm3, sp, kc, hiT); break;
+          case 1: m = reject4_a<1>(rowm3, sp, kc, hiT); break;
+          case 2: m = reject4_a<2>(rowm3, sp, kc, hiT); break;
+          default: m = reject4_a<3>(rowm3, sp, kc, hiT); break;
         }
-        if (m == 0) continue;
+        m &= 0x80808080u;
+        if (m) {
+          const uint32_t bits = ((m >> 7) & 1) | ((m >> 14) & 2) | ((m >> 21) & 4) | ((m >> 28) & 8);
+          itemq[atomicAdd(&in, 1)] = (uint16_t)(item | (bits << 12));
+        }
+      }
+      __syncthreads();
+      const int ni = in;
+      for (int k = tid; k < ni; k += kFastThreads) {
+        const int e = itemq[k], item = e & 0xFFF;
+        const uint32_t bits = e >> 12;
+        const int yi = nq4 == 1 ? item : (int)__umulhi((uint32_t)item, magic), xi = 4 * (item - yi * nq4);
+        const uint8_t* rowm3 = img + yi * sp + aox + xi;
+        uint32_t m = ((bits & 1) << 7) | ((bits & 2) << 14) | ((bits & 4) << 21) | ((bits & 8) << 28);
+        switch (sh) {
+          case 0: m = reject4_b<0>(rowm3, sp, kc, hiT, m); break;
+          case 1: m = reject4_b<1>(rowm3, sp, kc, hiT, m); break;
+          case 2: m = reject4_b<2>(rowm3, sp, kc, hiT, m); break;
+          default: m = reject4_b<3>(rowm3, sp, kc, hiT, m); break;
+        }
+        // keep centres that exist (x < iw) and whose cell takes part in this pass
+        uint32_t keep = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int x = xi + k;
-          if (!((m >> (8 * k + 7)) & 1) || x >= iw) continue;
+        for (int j = 0; j < 4; ++j) {
+          const int x = xi + j;
           const int jj = (x >= w1) + (x >= w2) + (x >= w3);
-          if (!((mask >> jj) & 1)) continue;
-          queue[atomicAdd(&qn, 1)] = (uint16_t)((yi << 8) | x);
+          if (((m >> (8 * j + 7)) & 1) && x < iw && ((mask >> jj) & 1)) keep |= 1u << j;
+        }
+        if (keep) {
+          int pos = atomicAdd(&qn, __popc(keep));
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if ((keep >> j) & 1) queue[pos++] = (uint16_t)((yi << 8) | (xi + j));
         }
       }
     }
@@ -296,6 +328,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
         if (cellCnt[jj] == 0 && jj * L.wCell < iw) r |= 1 << jj;
       retryMask = r;
       qn = 0;
+      in = 0;
     }
     __syncthreads();
     mask = retryMask;
@@ -578,8 +611,8 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const Geom G, const
 // arithmetic: SURVEY App. A.3).  All levels of all frames of the chunk in one launch; one CTA = one
 // 64x32 output tile, horizontal pass into shared u16, vertical pass out of it.
 // ======================================================================================================
-constexpr int kBlurTW = 64, kBlurTH = 32;
-constexpr int kBlurInW = kBlurTW + 8;     // input tile columns: image x0-4 .. x0+TW+3 (whole 32-bit words)
+constexpr int kBlurTW = 64, kBlurTH = 26;        // output tile; TH+6 = 32 input rows = 16 row pairs x 16 column quads = 256 threads
+constexpr int kBlurInW = kBlurTW + 8;            // input tile columns: image x0-4 .. x0+TW+3 (whole 32-bit words)
 
 __device__ __forceinline__ int reflect101(int p, int len) {
   if (p < 0) p = -p;
@@ -587,9 +620,17 @@ __device__ __forceinline__ int reflect101(int p, int len) {
   return p;
 }
 
+// 8.8 fixed-point kernel {18,34,48,56,48,34,18} packed for the integer dot-product instructions
+constexpr uint32_t kBlurK0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);   // taps 0..3 (dp4a)
+constexpr uint32_t kBlurK1 = 48u | (34u << 8) | (18u << 16);                 // taps 4..6 (dp4a)
+
+__device__ __forceinline__ uint32_t blur_h(uint32_t w0, uint32_t w1) {       // w0 = p[x-3..x], w1 = p[x+1..x+4]
+  return __dp4a(w1, kBlurK1, __dp4a(w0, kBlurK0, 0u));
+}
+
 __global__ void __launch_bounds__(256) blur_kernel(const Geom G, const Bufs B) {
   __shared__ __align__(16) uint8_t tin[kBlurTH + 6][kBlurInW];
-  __shared__ __align__(16) uint16_t hbuf[kBlurTH + 6][kBlurTW];
+  __shared__ __align__(16) uint32_t hpair[(kBlurTH + 6) / 2][kBlurTW];      // rows 2p (low half) and 2p+1 (high half) of the horizontal pass
   const int tid = threadIdx.x, f = blockIdx.y;
   int l = 0;
   while (l + 1 < G.nlevels && (int)blockIdx.x >= G.L[l + 1].blurTile0) ++l;
@@ -600,8 +641,7 @@ __global__ void __launch_bounds__(256) blur_kernel(const Geom G, const Bufs B) {
   int pitch;
   const uint8_t* src = level_ptr(G, B, l, f, pitch);
   const bool aligned = (((uintptr_t)src | (uintptr_t)pitch) & 3) == 0;
-  // ---- stage (TH+6) x (TW+8) input bytes as 32-bit words; words touching the image border are assembled with
-  //      BORDER_REFLECT_101 addressing
+  // ---- stage 32 x 72 input bytes as 32-bit words; words touching the image border use BORDER_REFLECT_101 addressing
   constexpr int WPR = kBlurInW / 4;   // 18 words per row
   for (int i = tid; i < (kBlurTH + 6) * WPR; i += 256) {
     const int r = i / WPR, w = i - r * WPR;
@@ -622,43 +662,53 @@ __global__ void __launch_bounds__(256) blur_kernel(const Geom G, const Bufs B) {
     *reinterpret_cast<uint32_t*>(&tin[r][4 * w]) = v;
   }
   __syncthreads();
-  // ---- horizontal pass: one thread = 4 adjacent outputs of one row (8.8 fixed point, exact in u16)
-  for (int i = tid; i < (kBlurTH + 6) * (kBlurTW / 4); i += 256) {
-    const int r = i >> 4, q = i & 15;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(&tin[r][4 * q]);
-    const uint32_t a = wp[0], b = wp[1], c = wp[2];
-    // bytes p[0..11] = image x0-4+4q .. ; output xl = 4q+k uses p[k+1 .. k+7]
-    int p[12];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { p[k] = (a >> (8 * k)) & 255; p[4 + k] = (b >> (8 * k)) & 255; p[8 + k] = (c >> (8 * k)) & 255; }
-    uint32_t o[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      o[k] = 18 * (p[k + 1] + p[k + 7]) + 34 * (p[k + 2] + p[k + 6]) + 48 * (p[k + 3] + p[k + 5]) + 56 * p[k + 4];
-    *reinterpret_cast<uint2*>(&hbuf[r][4 * q]) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
-  }
-  __syncthreads();
-  // ---- vertical pass: one thread = 4 adjacent columns x 2 rows, one 32-bit store per row
-  uint8_t* dst = B.blur + L.blurOff + (size_t)f * L.h * L.bpitch;
+  // ---- horizontal pass: one thread = 4 adjacent columns of 2 adjacent rows; exact in u16 (max 255*256)
   {
-    const int q = tid & 15, g = tid >> 4;          // g: 0..15 -> output rows 2g, 2g+1
-    uint32_t h[8][4];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const uint2 v = *reinterpret_cast<const uint2*>(&hbuf[2 * g + r][4 * q]);
-      h[r][0] = v.x & 0xFFFF; h[r][1] = v.x >> 16; h[r][2] = v.y & 0xFFFF; h[r][3] = v.y >> 16;
-    }
+    const int q = tid & 15, rp = tid >> 4;            // rp: row pair 0..15
+    uint32_t o[2][4];
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-      const int y = y0 + 2 * g + rr, x = x0 + 4 * q;
-      if (y >= L.h || x >= L.w) continue;
-      uint32_t packed = 0;
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(&tin[2 * rp + rr][4 * q]);
+      const uint32_t a = wp[0], b = wp[1], c = wp[2];   // bytes j = 0..11 <-> image x0-4+4q+j; output k uses bytes k+1..k+7
+      o[rr][0] = blur_h(__funnelshift_r(a, b, 8), __funnelshift_r(b, c, 8));
+      o[rr][1] = blur_h(__funnelshift_r(a, b, 16), __funnelshift_r(b, c, 16));
+      o[rr][2] = blur_h(__funnelshift_r(a, b, 24), __funnelshift_r(b, c, 24));
+      o[rr][3] = blur_h(b, c);
+    }
+    *reinterpret_cast<uint4*>(&hpair[rp][4 * q]) = make_uint4(o[0][0] | (o[1][0] << 16), o[0][1] | (o[1][1] << 16),
+                                                             o[0][2] | (o[1][2] << 16), o[0][3] | (o[1][3] << 16));
+  }
+  __syncthreads();
+  // ---- vertical pass: one thread = 4 columns x 2 rows (2g, 2g+1); both rows read the same four row pairs
+  if (tid < (kBlurTH / 2) * 16) {
+    const int q = tid & 15, g = tid >> 4;             // g: 0..12
+    uint4 P[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t acc = 18u * (h[rr][k] + h[rr + 6][k]) + 34u * (h[rr + 1][k] + h[rr + 5][k]) +
-                             48u * (h[rr + 2][k] + h[rr + 4][k]) + 56u * h[rr + 3][k] + 32768u;
-        packed |= (acc >> 16) << (8 * k);
-      }
+    for (int p = 0; p < 4; ++p) P[p] = *reinterpret_cast<const uint4*>(&hpair[g + p][4 * q]);
+    // even output row 2g: taps on rows 2g..2g+6 -> pairs (k0,k1)(k2,k3)(k4,k5)(k6,-); odd row 2g+1: (-,k0)(k1,k2)(k3,k4)(k5,k6)
+    constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;
+    constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);
+    uint32_t ev = 0, od = 0;
+    const uint32_t* c0 = reinterpret_cast<const uint32_t*>(&P[0]);
+    const uint32_t* c1 = reinterpret_cast<const uint32_t*>(&P[1]);
+    const uint32_t* c2 = reinterpret_cast<const uint32_t*>(&P[2]);
+    const uint32_t* c3 = reinterpret_cast<const uint32_t*>(&P[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t e = __dp2a_lo(c0[k], E0, 32768u);
+      e = __dp2a_lo(c1[k], E1, e); e = __dp2a_lo(c2[k], E2, e); e = __dp2a_lo(c3[k], E3, e);
+      uint32_t o = __dp2a_lo(c0[k], O0, 32768u);
+      o = __dp2a_lo(c1[k], O1, o); o = __dp2a_lo(c2[k], O2, o); o = __dp2a_lo(c3[k], O3, o);
+      ev |= (e >> 16) << (8 * k);
+      od |= (o >> 16) << (8 * k);
+    }
+    uint8_t* dst = B.blur + L.blurOff + (size_t)f * L.h * L.bpitch;
+    const int x = x0 + 4 * q;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int y = y0 + 2 * g + rr;
+      const uint32_t packed = rr ? od : ev;
+      if (y >= L.h || x >= L.w) continue;
       uint8_t* d = dst + (size_t)y * L.bpitch + x;
       if (x + 3 < L.w) *reinterpret_cast<uint32_t*>(d) = packed;     // bpitch is a multiple of 64, x of 4
       else for (int k = 0; x + k < L.w; ++k) d[k] = (uint8_t)(packed >> (8 * k));
@@ -841,7 +891,9 @@ void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe
   resize_kernel<<<grid, block, 0, st>>>(src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
 }
 
-size_t fast_smem_bytes(const Geom& G) { return (size_t)4 * G.fastTileW * G.fastTileH + 4 * (size_t)G.fastSurvCap + 64; }
+size_t fast_smem_bytes(const Geom& G) {
+  return (size_t)4 * G.fastTileW * G.fastTileH + 4 * (size_t)G.fastSurvCap + (size_t)G.fastTileW * G.fastTileH / 2 + 64;
+}
 
 size_t octree_smem_bytes(const Geom& G) {
   const size_t cap = G.nodeCap;
