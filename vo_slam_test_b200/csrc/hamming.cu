@@ -16,13 +16,44 @@ namespace orbx {
 
 constexpr int kQT = 128;          // queries per CTA (threads)
 constexpr int kTT = 256;          // train descriptors per shared-memory tile (8 KB)
+constexpr int kStages = 3;        // tiles in flight (TMA bulk copies, mbarrier-tracked)
 constexpr uint32_t kKeyInit = (256u << 23) | 0x7FFFFFu;
 
 static std::atomic<long long> g_hamm_launches{0};
 
+// ---- mbarrier + 1-D bulk copy (TMA engine: cp.async.bulk -> UBLKCP) ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// 256-bit Hamming distance with a carry-save adder tree: 7 of the 8 XOR words are compressed 3:2 (LOP3 0x96 / 0xE8)
+// so that only 5 POPC are needed instead of 8 -- POPC is the scarce pipe (16/clk/SM), see DESIGN.md.
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); }
 __device__ __forceinline__ int hamming8(const uint32_t (&q)[8], const uint4 a, const uint4 b) {
-  return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
-         __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+  const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+  const uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+  const uint32_t s1 = x0 ^ x1 ^ x2, c1 = maj3(x0, x1, x2);
+  const uint32_t s2 = x3 ^ x4 ^ x5, c2 = maj3(x3, x4, x5);
+  const uint32_t s3 = s1 ^ s2 ^ x6, c3 = maj3(s1, s2, x6);
+  return (__popc(s3) + __popc(x7)) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
 }
 
 __device__ __forceinline__ void top2_update(uint32_t& k1, uint32_t& k2, uint32_t key) {
@@ -30,21 +61,46 @@ __device__ __forceinline__ void top2_update(uint32_t& k1, uint32_t& k2, uint32_t
   k1 = min(k1, key);
 }
 
-// Scan train rows [t0, t0+nt) (nt < 2^23) for the CTA's queries; tiles go through `tile` (kTT*32 bytes).
-__device__ __forceinline__ void scan_train(const uint32_t (&q)[8], const uint8_t* __restrict__ train, int nt, uint4* tile,
+struct TileRing {
+  uint4* tile;        // kStages * kTT * 2 uint4
+  uint64_t* full;     // kStages barriers
+};
+
+// Scan train rows [0, nt) (nt < 2^23) for the CTA's queries.  Tiles of kTT rows are fetched by the TMA engine
+// (one elected thread issues cp.async.bulk, completion is tracked by an mbarrier per stage), kStages deep.
+__device__ __forceinline__ void scan_train(const uint32_t (&q)[8], const uint8_t* __restrict__ train, int nt, const TileRing& R,
                                            uint32_t& k1, uint32_t& k2) {
   const int tid = threadIdx.x;
-  for (int base = 0; base < nt; base += kTT) {
-    const int cnt = min(kTT, nt - base);
-    __syncthreads();
-    const uint4* src = reinterpret_cast<const uint4*>(train + (size_t)base * 32);
-    for (int i = tid; i < cnt * 2; i += kQT) tile[i] = __ldg(src + i);
-    __syncthreads();
+  const int ntiles = (nt + kTT - 1) / kTT;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&R.full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int t) {
+    const int s = t % kStages;
+    const uint32_t bytes = (uint32_t)min(kTT, nt - t * kTT) * 32u;
+    mbar_expect_tx(&R.full[s], bytes);
+    bulk_g2s(R.tile + (size_t)s * kTT * 2, train + (size_t)t * kTT * 32, bytes, &R.full[s]);
+  };
+  if (tid == 0)
+    for (int t = 0; t < min(kStages, ntiles); ++t) issue(t);
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % kStages;
+    mbar_wait(&R.full[s], (uint32_t)((t / kStages) & 1));
+    const uint4* tile = R.tile + (size_t)s * kTT * 2;
+    const int cnt = min(kTT, nt - t * kTT);
+    const int base = t * kTT;
 #pragma unroll 4
     for (int j = 0; j < cnt; ++j) {
       const uint4 a = tile[2 * j], b = tile[2 * j + 1];
       const uint32_t d = (uint32_t)hamming8(q, a, b);
       top2_update(k1, k2, (d << 23) | (uint32_t)(base + j));
+    }
+    __syncthreads();                                   // everyone is done reading stage s
+    if (tid == 0 && t + kStages < ntiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before async-proxy writes
+      issue(t + kStages);
     }
   }
 }
@@ -69,7 +125,9 @@ __device__ __forceinline__ uint8_t accept(int d1, int d2, int th, float ratio) {
 __global__ void __launch_bounds__(kQT) knn2_kernel(const uint8_t* __restrict__ qs, int nq, const uint8_t* __restrict__ train,
                                                    long long nt, long long per, int th, float ratio, int32_t* idx,
                                                    int32_t* d1, int32_t* d2, uint8_t* ok, int32_t* part) {
-  __shared__ uint4 tile[kTT * 2];
+  __shared__ __align__(128) uint4 tile[kStages * kTT * 2];
+  __shared__ __align__(8) uint64_t full[kStages];
+  const TileRing ring{tile, full};
   const int i = blockIdx.x * kQT + threadIdx.x;
   const int s = blockIdx.y;
   const long long t0 = (long long)s * per;
@@ -77,7 +135,7 @@ __global__ void __launch_bounds__(kQT) knn2_kernel(const uint8_t* __restrict__ q
   uint32_t q[8];
   load_query(q, qs, i, nq);
   uint32_t k1 = kKeyInit, k2 = kKeyInit;
-  scan_train(q, train + (size_t)t0 * 32, cnt, tile, k1, k2);
+  scan_train(q, train + (size_t)t0 * 32, cnt, ring, k1, k2);
   if (i >= nq) return;
   const int bd1 = (int)(k1 >> 23), bd2 = (int)(k2 >> 23);
   const int bi = bd1 < 256 ? (int)(t0 + (long long)(k1 & 0x7FFFFFu)) : -1;
@@ -113,7 +171,9 @@ __global__ void __launch_bounds__(kQT) knn2_pairs_kernel(const uint8_t* __restri
                                                          int cap, const int32_t* __restrict__ qf, const int32_t* __restrict__ tf,
                                                          int th, float ratio, int32_t* idx, int32_t* d1, int32_t* d2,
                                                          uint8_t* ok) {
-  __shared__ uint4 tile[kTT * 2];
+  __shared__ __align__(128) uint4 tile[kStages * kTT * 2];
+  __shared__ __align__(8) uint64_t full[kStages];
+  const TileRing ring{tile, full};
   const int p = blockIdx.y;
   const int fq = qf[p], ft = tf[p];
   const int nq = min(counts[fq], cap), nt = min(counts[ft], cap);
@@ -122,7 +182,7 @@ __global__ void __launch_bounds__(kQT) knn2_pairs_kernel(const uint8_t* __restri
   uint32_t q[8];
   load_query(q, desc + (size_t)fq * cap * 32, i, nq);
   uint32_t k1 = kKeyInit, k2 = kKeyInit;
-  scan_train(q, desc + (size_t)ft * cap * 32, nt, tile, k1, k2);
+  scan_train(q, desc + (size_t)ft * cap * 32, nt, ring, k1, k2);
   if (i >= nq) return;
   const int bd1 = (int)(k1 >> 23), bd2 = (int)(k2 >> 23);
   const size_t o = (size_t)p * cap + i;

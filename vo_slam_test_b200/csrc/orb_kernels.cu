@@ -641,25 +641,30 @@ __global__ void __launch_bounds__(256) blur_kernel(const Geom G, const Bufs B) {
   int pitch;
   const uint8_t* src = level_ptr(G, B, l, f, pitch);
   const bool aligned = (((uintptr_t)src | (uintptr_t)pitch) & 3) == 0;
-  // ---- stage 32 x 72 input bytes as 32-bit words; words touching the image border use BORDER_REFLECT_101 addressing
-  constexpr int WPR = kBlurInW / 4;   // 18 words per row
-  for (int i = tid; i < (kBlurTH + 6) * WPR; i += 256) {
-    const int r = i / WPR, w = i - r * WPR;
+  // ---- stage 32 x 72 input bytes as 32-bit words: thread = (row, 8 lanes x up to 3 words); the row's REFLECT_101
+  //      source line is resolved once per thread, only words touching the left/right image border take the slow path
+  {
+    constexpr int WPR = kBlurInW / 4;   // 18 words per row
+    const int r = tid >> 3, wb = tid & 7;
     const int sy = reflect101(min(y0 + r - 3, L.h + 2), L.h);
-    const int gx = x0 - 4 + 4 * w;
     const uint8_t* row = src + (size_t)sy * pitch;
-    uint32_t v;
-    if (aligned && gx >= 0 && gx + 3 < L.w) {
-      v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-    } else {
-      v = 0;
+    uint32_t* trow = reinterpret_cast<uint32_t*>(&tin[r][0]);
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int sx = reflect101(min(max(gx + b, -3), L.w + 2), L.w);
-        v |= (uint32_t)__ldg(row + sx) << (8 * b);
+    for (int w = wb; w < WPR; w += 8) {
+      const int gx = x0 - 4 + 4 * w;
+      uint32_t v;
+      if (aligned && gx >= 0 && gx + 3 < L.w) {
+        v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+      } else {
+        v = 0;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const int sx = reflect101(min(max(gx + bb, -3), L.w + 2), L.w);
+          v |= (uint32_t)__ldg(row + sx) << (8 * bb);
+        }
       }
+      trow[w] = v;
     }
-    *reinterpret_cast<uint32_t*>(&tin[r][4 * w]) = v;
   }
   __syncthreads();
   // ---- horizontal pass: one thread = 4 adjacent columns of 2 adjacent rows; exact in u16 (max 255*256)
