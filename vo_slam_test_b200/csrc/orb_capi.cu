@@ -197,19 +197,41 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
     axis_taps(S.h, D.h, yo, yb0, yb1);
     const size_t bx = align_up_sz(sizeof(int) * D.w, 256), bs = align_up_sz(sizeof(short) * D.w, 256);
     const size_t by = align_up_sz(sizeof(int) * D.h, 256), bt = align_up_sz(sizeof(short) * D.h, 256);
-    std::vector<uint8_t> blob(bx + 2 * bs + by + 2 * bt, 0);
+    const int nquad = (D.w + 3) / 4;
+    const size_t bq = align_up_sz(sizeof(int4) * nquad, 256), bw = align_up_sz(sizeof(uint4) * nquad, 256);
+    std::vector<int4> quad(nquad);
+    std::vector<uint4> xw(nquad);
+    int quadOk = 1;
+    for (int q = 0; q < nquad; ++q) {
+      const int s0 = xo[4 * q];
+      uint32_t sels = 0, wv[4];
+      for (int i = 0; i < 4; ++i) {
+        const int dx = std::min(4 * q + i, D.w - 1);
+        const int o = xo[dx] - s0;
+        if (o < 0 || o + 1 > 7) quadOk = 0;
+        sels |= (uint32_t)((o & 7) | (((o + 1) & 7) << 4)) << (8 * i);
+        wv[i] = (uint32_t)(uint16_t)xa0[dx] | ((uint32_t)(uint16_t)xa1[dx] << 16);
+      }
+      quad[q] = make_int4(s0 & ~3, (s0 & 3) * 8, (int)sels, 0);
+      xw[q] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
+    std::vector<uint8_t> blob(bx + 2 * bs + by + 2 * bt + bq + bw, 0);
     memcpy(blob.data(), xo.data(), sizeof(int) * D.w);
     memcpy(blob.data() + bx, xa0.data(), sizeof(short) * D.w);
     memcpy(blob.data() + bx + bs, xa1.data(), sizeof(short) * D.w);
     memcpy(blob.data() + bx + 2 * bs, yo.data(), sizeof(int) * D.h);
     memcpy(blob.data() + bx + 2 * bs + by, yb0.data(), sizeof(short) * D.h);
     memcpy(blob.data() + bx + 2 * bs + by + bt, yb1.data(), sizeof(short) * D.h);
+    memcpy(blob.data() + bx + 2 * bs + by + 2 * bt, quad.data(), sizeof(int4) * nquad);
+    memcpy(blob.data() + bx + 2 * bs + by + 2 * bt + bq, xw.data(), sizeof(uint4) * nquad);
     DevTaps& T = h->taps[l];
     ORBX_CUDA(cudaMalloc(&T.block, blob.size()));
     ORBX_CUDA(cudaMemcpy(T.block, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     uint8_t* b = (uint8_t*)T.block;
     T.t.xofs = (int*)b; T.t.xa0 = (short*)(b + bx); T.t.xa1 = (short*)(b + bx + bs);
     T.t.yofs = (int*)(b + bx + 2 * bs); T.t.yb0 = (short*)(b + bx + 2 * bs + by); T.t.yb1 = (short*)(b + bx + 2 * bs + by + bt);
+    T.t.quad = (int4*)(b + bx + 2 * bs + by + 2 * bt); T.t.xw = (uint4*)(b + bx + 2 * bs + by + 2 * bt + bq);
+    T.t.quadOk = quadOk;
   }
   h->haveGeom = true;
   h->chunk = chunk;

@@ -74,6 +74,9 @@ struct Bufs {
 struct ResizeTaps {        // device tables of one level
   int* xofs; short* xa0; short* xa1;
   int* yofs; short* yb0; short* yb1;
+  // per destination quad (4 px): {aligned source byte offset, funnel shift, 4 byte-pair selectors, -} and the four
+  // packed weight pairs a0 | a1 << 16; quadOk = every quad's taps fit an 8-byte window (scale factor <= 2)
+  int4* quad; uint4* xw; int quadOk;
 };
 
 }  // namespace orbx

@@ -52,6 +52,50 @@ __global__ void __launch_bounds__(256) resize_kernel(const uint8_t* __restrict__
   }
 }
 
+// Word-granular variant (the one normally used): one thread = 4 destination pixels; per source row three aligned
+// 32-bit loads + two funnel shifts give the 8 bytes starting at the quad's first tap, PRMT picks each pixel's byte
+// pair and one IDP (dp2a) applies the two 11-bit weights.  Needs 4-byte aligned source rows and scale <= 2.
+__global__ void __launch_bounds__(256) resize4_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
+                                                      size_t sframe, uint8_t* __restrict__ dst, int dw, int dh,
+                                                      int dpitch, size_t dframe, ResizeTaps T) {
+  const int q = blockIdx.x * 32 + threadIdx.x;
+  const int dy = blockIdx.y * 8 + threadIdx.y;
+  const int dx0 = q * 4;
+  if (dx0 >= dw || dy >= dh) return;
+  const int f = blockIdx.z;
+  const int4 Q = __ldg(T.quad + q);
+  const uint4 Wt = __ldg(T.xw + q);
+  const int sy0 = __ldg(T.yofs + dy);
+  const int sy1 = min(sy0 + 1, sh - 1);
+  const int b0 = __ldg(T.yb0 + dy), b1 = __ldg(T.yb1 + dy);
+  const int lastw = (sw - 1) & ~3;                      // words past it hold no tap with a non-zero weight
+  const int o0 = min(Q.x, lastw), o1 = min(Q.x + 4, lastw), o2 = min(Q.x + 8, lastw);
+  const uint8_t* r0 = src + f * sframe + (size_t)sy0 * spitch;
+  const uint8_t* r1 = src + f * sframe + (size_t)sy1 * spitch;
+  const uint32_t a0 = __ldg(reinterpret_cast<const uint32_t*>(r0 + o0)), a1 = __ldg(reinterpret_cast<const uint32_t*>(r0 + o1)),
+                 a2 = __ldg(reinterpret_cast<const uint32_t*>(r0 + o2));
+  const uint32_t c0 = __ldg(reinterpret_cast<const uint32_t*>(r1 + o0)), c1 = __ldg(reinterpret_cast<const uint32_t*>(r1 + o1)),
+                 c2 = __ldg(reinterpret_cast<const uint32_t*>(r1 + o2));
+  const uint32_t lo0 = __funnelshift_r(a0, a1, Q.y), hi0 = __funnelshift_r(a1, a2, Q.y);
+  const uint32_t lo1 = __funnelshift_r(c0, c1, Q.y), hi1 = __funnelshift_r(c1, c2, Q.y);
+  const uint32_t wts[4] = {Wt.x, Wt.y, Wt.z, Wt.w};
+  uint32_t out = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t sel = ((uint32_t)Q.z >> (8 * i)) & 0xFFu;
+    const int h0 = (int)__dp2a_lo(wts[i], __byte_perm(lo0, hi0, sel), 0u);
+    const int h1 = (int)__dp2a_lo(wts[i], __byte_perm(lo1, hi1, sel), 0u);
+    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    out |= (uint32_t)v << (8 * i);
+  }
+  uint8_t* d = dst + f * dframe + (size_t)dy * dpitch + dx0;
+  if (dx0 + 3 < dw) {
+    *reinterpret_cast<uint32_t*>(d) = out;
+  } else {
+    for (int i = 0; dx0 + i < dw; ++i) d[i] = (uint8_t)(out >> (8 * i));
+  }
+}
+
 // ======================================================================================================
 // K2  per-cell FAST-9/16 + per-cell 3x3 NMS + iniTh/minTh retry + ordered compaction
 // (ORBextractor.cpp:796-836 around cv::FAST; arithmetic: SURVEY App. A.2).
@@ -171,7 +215,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
   // densely over that queue only, (4) survivors are ranked by (cell, row, column) to emit them in the reference order.
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int cellCnt[kCellsPerCta];
-  __shared__ int qn, sn, in, retryMask;
+  __shared__ int qn, sn, in, cn, retryMask;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = blockIdx.x, f = blockIdx.y;
   int l = 0;
@@ -195,6 +239,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
   uint16_t* queue = (uint16_t*)(sc + G.fastTileH * sp);        // yi<<8 | xi of pixels passing the rejection test
   uint32_t* surv = (uint32_t*)(queue + G.fastTileH * sp);      // cell<<24 | yi<<12 | cx of NMS survivors
   uint16_t* itemq = (uint16_t*)(surv + G.fastSurvCap);         // quads surviving rejection stage a: item | flags<<12
+  uint16_t* cornerq = itemq + ((G.fastTileH * sp) >> 2);        // pixels whose strength exceeds the pass threshold
 
   int pitch;
   const uint8_t* lvl = level_ptr(G, B, l, f, pitch);
@@ -202,21 +247,25 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
   int ox = 0;
   if ((((uintptr_t)lvl | (uintptr_t)pitch) & 15) == 0) {
     ox = gx0 & 15;
-    const int wpr = (ox + tw + 15) >> 4;                       // 16-byte words per tile row
+    const int wpr = (ox + tw + 15) >> 4;                       // 16-byte words per tile row (<= 32)
     const uint8_t* base = lvl + (size_t)(kMinBorder + ty0) * pitch + (gx0 - ox);
-    for (int i = tid; i < th * wpr; i += kFastThreads) {
-      const int y = i / wpr, w = i - y * wpr;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)y * pitch) + w);
-      *reinterpret_cast<uint4*>(img + y * sp + 16 * w) = v;
-    }
+    const int lg = wpr <= 16 ? 4 : 5;                          // slots per row = 1 << lg
+    const int w = tid & ((1 << lg) - 1);
+    if (w < wpr)
+      for (int y = tid >> lg; y < th; y += kFastThreads >> lg)
+        *reinterpret_cast<uint4*>(img + y * sp + 16 * w) = __ldg(reinterpret_cast<const uint4*>(base + (size_t)y * pitch) + w);
   } else {
     const uint8_t* base = lvl + (size_t)(kMinBorder + ty0) * pitch + gx0;
     for (int y = warp; y < th; y += kFastThreads / 32)
       for (int x = lane; x < tw; x += 32) img[y * sp + x] = __ldg(base + (size_t)y * pitch + x);
   }
-  for (int i = tid; i < (th * sp) >> 4; i += kFastThreads) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
+  {
+    uint4* z = reinterpret_cast<uint4*>(sc);
+    const int nz = (th * sp) >> 4;
+    for (int i = tid; i < nz; i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
   if (tid < kCellsPerCta) cellCnt[tid] = 0;
-  if (tid == 0) { qn = 0; sn = 0; in = 0; retryMask = 0; }
+  if (tid == 0) { qn = 0; sn = 0; in = 0; cn = 0; retryMask = 0; }
   __syncthreads();
 
   const int w1 = L.wCell, w2 = 2 * L.wCell, w3 = 3 * L.wCell;
@@ -290,17 +339,23 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
       const int y0 = e0 >> 8, x0 = e0 & 255, y1 = e1 >> 8, x1 = e1 & 255;
       int b0, b1;
       fast_best2(img0 + y0 * sp + x0, img0 + y1 * sp + x1, sp, b0, b1);
-      sc0[y0 * sp + x0] = (uint8_t)(b0 > t ? b0 : 0);
-      sc0[y1 * sp + x1] = (uint8_t)(b1 > t ? b1 : 0);
+      const bool c0 = b0 > t, c1 = b1 > t && (2 * k + 1 < nq);
+      sc0[y0 * sp + x0] = (uint8_t)(c0 ? b0 : 0);
+      if (2 * k + 1 < nq) sc0[y1 * sp + x1] = (uint8_t)(b1 > t ? b1 : 0);
+      if (c0 | c1) {
+        int pos = atomicAdd(&cn, (int)c0 + (int)c1);
+        if (c0) cornerq[pos++] = (uint16_t)e0;
+        if (c1) cornerq[pos] = (uint16_t)e1;
+      }
     }
     __syncthreads();
     // ---- 3x3 NMS inside each cell's own candidate rectangle (outside counts as score 0, like the zeroed border of
     //      cv::FAST on the cell ROI); strict '>' against all eight neighbours
-    for (int k = tid; k < nq; k += kFastThreads) {
-      const int e = queue[k], yi = e >> 8, xi = e & 255;
+    const int nc = cn;
+    for (int k = tid; k < nc; k += kFastThreads) {
+      const int e = cornerq[k], yi = e >> 8, xi = e & 255;
       const uint8_t* s = sc0 + yi * sp + xi;
       const int v = s[0];
-      if (v == 0) continue;
       const int jj = (xi >= w1) + (xi >= w2) + (xi >= w3);
       const int cx = xi - jj * L.wCell;
       const int cw = min(L.wCell, iw - jj * L.wCell);
@@ -329,6 +384,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
       retryMask = r;
       qn = 0;
       in = 0;
+      cn = 0;
     }
     __syncthreads();
     mask = retryMask;
@@ -893,11 +949,16 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(const Geom G, const Bu
 void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe, uint8_t* dst, int dw, int dh,
                    int dpitch, size_t dframe, const ResizeTaps& T, int nframes, cudaStream_t st) {
   dim3 block(32, 8), grid((dw + 127) / 128, (dh + 7) / 8, nframes);
-  resize_kernel<<<grid, block, 0, st>>>(src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
+  const bool aligned = ((((uintptr_t)src) | (uintptr_t)spitch | (uintptr_t)sframe) & 3) == 0;
+  if (T.quadOk && aligned)
+    resize4_kernel<<<grid, block, 0, st>>>(src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
+  else
+    resize_kernel<<<grid, block, 0, st>>>(src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
 }
 
 size_t fast_smem_bytes(const Geom& G) {
-  return (size_t)4 * G.fastTileW * G.fastTileH + 4 * (size_t)G.fastSurvCap + (size_t)G.fastTileW * G.fastTileH / 2 + 64;
+  return (size_t)4 * G.fastTileW * G.fastTileH + 4 * (size_t)G.fastSurvCap + (size_t)G.fastTileW * G.fastTileH / 2 +
+         (size_t)2 * G.fastTileW * G.fastTileH + 64;
 }
 
 size_t octree_smem_bytes(const Geom& G) {
