@@ -1,0 +1,121 @@
+"""GPU parity of the batch / device / pipelined entry points and size-independent properties at BASELINE scale."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle
+from vo_slam_test_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def vo():
+    import vo_slam_test_b200 as v
+    assert v.device_count() > 0
+    return v
+
+
+def test_extract_match_batch_equals_oracle(vo):
+    """orbx_extract_match_batch (host ABI, three-stream pipeline, chunked) == oracle extractor + oracle top-2."""
+    import os
+    os.environ["ORBX_CHUNK"] = "5"          # force several chunks and pairs that straddle chunk boundaries
+    try:
+        B = 13
+        imgs = synth.make_sequence(B, seed=11)
+        ex = vo.ORBextractor()
+        cap = ex.max_keypoints
+        kps = np.zeros((B, cap), vo.KP_DTYPE); desc = np.zeros((B, cap, 32), np.uint8); cnt = np.zeros(B, np.int32)
+        midx = np.full((B - 1, cap), -7, np.int32); md1 = np.zeros((B - 1, cap), np.int32); md2 = np.zeros((B - 1, cap), np.int32)
+        mok = np.zeros((B - 1, cap), np.uint8)
+        ex.extract_match_batch(imgs.ctypes.data, B, 640, 480, kps.ctypes.data, desc.ctypes.data, cap, cnt.ctypes.data, 50, 0.7,
+                               midx.ctypes.data, md1.ctypes.data, md2.ctypes.data, mok.ctypes.data)
+        P = oracle.Port()
+        ref = [P.extract(imgs[f]) for f in range(B)]
+        for f in range(B):
+            assert cnt[f] == len(ref[f][0])
+            assert np.array_equal(kps[f, :cnt[f]], ref[f][0]) and np.array_equal(desc[f, :cnt[f]], ref[f][1])
+        for p in range(B - 1):
+            want = P.knn2(ref[p][1], ref[p + 1][1], 50, 0.7)
+            n = cnt[p]
+            assert np.array_equal(midx[p, :n], want[0]) and np.array_equal(md1[p, :n], want[1])
+            assert np.array_equal(md2[p, :n], want[2]) and np.array_equal(mok[p, :n], want[3])
+            assert want[3].sum() > 100          # consecutive frames of the panning sequence really match
+        ex.close()
+    finally:
+        del os.environ["ORBX_CHUNK"]
+
+
+def test_device_api_with_unaligned_strides(vo):
+    """Resident frames whose row stride is not a multiple of 4/16: the byte-granular fallback paths of the pyramid, FAST,
+    blur and patch staging must give the same bits as the aligned paths."""
+    torch = pytest.importorskip("torch")
+    B, H, W = 3, 480, 640
+    imgs = synth.make_sequence(B, seed=5)
+    P = oracle.Port()
+    ex = vo.ORBextractor()
+    cap = ex.max_keypoints
+    for pad, off in [(0, 0), (3, 1), (7, 2), (16, 0)]:
+        big = torch.zeros((B, H, W + pad), dtype=torch.uint8, device="cuda")
+        big[:, :, off:off + W] = torch.from_numpy(imgs).cuda() if pad else torch.from_numpy(imgs).cuda()[:, :, :W]
+        d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda")
+        d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+        ex.extract_batch_device(big.data_ptr() + off, B, W, H, W + pad, (W + pad) * H, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                d_cnt.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        cnt = d_cnt.cpu().numpy(); kp = d_kps.cpu().numpy().view(np.uint8).reshape(B, cap, 28); de = d_desc.cpu().numpy()
+        for f in range(B):
+            rk, rd = P.extract(imgs[f])
+            assert cnt[f] == len(rk), (pad, off)
+            assert np.array_equal(kp[f, :cnt[f]].reshape(-1).view(vo.KP_DTYPE), rk), (pad, off)
+            assert np.array_equal(de[f, :cnt[f]], rd), (pad, off)
+    ex.close()
+
+
+def test_properties_at_baseline_scale(vo):
+    """Size-independent properties on a 1024-frame resident batch (too big for the CPU oracle in a test):
+    determinism across runs and chunkings, duplicate frames give identical output, self-matching is the identity,
+    keypoint counts respect the quadtree's N .. N+3 per level bound, spot frames equal the oracle."""
+    torch = pytest.importorskip("torch")
+    import os
+    B = 1024
+    imgs = synth.make_sequence(B, seed=21)
+    imgs[700] = imgs[100]                                  # planted duplicate
+    ex = vo.ORBextractor()
+    cap = ex.max_keypoints
+    d_imgs = torch.from_numpy(imgs).cuda()
+    outs = []
+    for chunk in ("256", "37"):
+        os.environ["ORBX_CHUNK"] = chunk
+        ex2 = vo.ORBextractor()
+        d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda")
+        d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+        ex2.extract_batch_device(d_imgs.data_ptr(), B, 640, 480, 640, 640 * 480, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                 d_cnt.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs.append((d_kps.cpu().numpy(), d_desc.cpu().numpy(), d_cnt.cpu().numpy()))
+        ex2.close()
+    del os.environ["ORBX_CHUNK"]
+    (k0, d0, c0), (k1, d1, c1) = outs
+    assert np.array_equal(c0, c1)
+    nf = ex.features_per_level()
+    assert c0.min() > 900 and c0.max() <= int(nf.sum()) + 3 * len(nf)
+    for f in range(B):
+        n = c0[f]
+        assert np.array_equal(k0[f, :n].view(np.uint32), k1[f, :n].view(np.uint32)) and np.array_equal(d0[f, :n], d1[f, :n])
+    n = c0[100]
+    assert c0[700] == n and np.array_equal(d0[700, :n], d0[100, :n]) and np.array_equal(k0[700, :n].view(np.uint32), k0[100, :n].view(np.uint32))
+    P = oracle.Port()
+    for f in (0, 511, 1023):
+        rk, rd = P.extract(imgs[f])
+        assert c0[f] == len(rk) and np.array_equal(d0[f, :c0[f]], rd)
+    # self-matching: every descriptor's nearest neighbour in its own frame is the first identical row (itself unless duplicated)
+    M = vo.Matcher(0.7)
+    idx, dd1, dd2, ok = M.knn2(d0[5, :c0[5]], d0[5, :c0[5]])
+    assert (dd1 == 0).all()
+    first = np.array([np.flatnonzero((d0[5, :c0[5]] == row).all(1))[0] for row in d0[5, :c0[5]]])
+    assert np.array_equal(idx, first)
+    ex.close()
