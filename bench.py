@@ -311,6 +311,25 @@ def run_b200(args, rank, world, local_rank):
     d2h = F * 4 + F * cap * 28 + F * cap * 32 + npairs * cap * 13
     assert np.array_equal(h_counts.numpy(), counts), "e2e and resident paths disagree"
 
+    # ---- single-frame latency through orbx_extract (the reference's actual call pattern: one frame per call) ------
+    single = None
+    if rank == 0:
+        import ctypes as C
+        one = np.ascontiguousarray(h_imgs.numpy()[0])
+        skp = np.zeros(cap, api.KP_DTYPE); sde = np.zeros((cap, 32), np.uint8); n1 = C.c_int(0)
+        L = vo.lib()
+        def call():
+            rc = L.orbx_extract(ex._h, C.c_void_p(one.ctypes.data), W_IMG, H_IMG, W_IMG, C.c_void_p(skp.ctypes.data),
+                                C.c_void_p(sde.ctypes.data), cap, C.byref(n1))
+            assert rc == 0
+        for _ in range(5):
+            call()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            call()
+        single = {"ms_per_frame": (time.perf_counter() - t0) / 50 * 1e3, "api": "orbx_extract (host in, host out, synchronous)",
+                  "keypoints": int(n1.value)}
+
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -354,7 +373,7 @@ def run_b200(args, rank, world, local_rank):
                         "api": "orbx_extract_match_batch (host C ABI, pinned host buffers, copies inside the timed region)"},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "stages": stages, "hamming_gmatch_per_s": stages["hamming_pairs"]["gmatch_per_s"],
-                "hamming_roofline": hamming_roofline, "hamming_map": hamming_map, "cpu_baseline": cpu_baseline}
+                "hamming_roofline": hamming_roofline, "hamming_map": hamming_map, "single_frame": single, "cpu_baseline": cpu_baseline}
         emit(line)
     ex.close()
 

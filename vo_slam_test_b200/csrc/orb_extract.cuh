@@ -9,9 +9,9 @@ namespace orbx {
 constexpr int kMaxLevels = 16;
 constexpr int kEdge = 19;            // EDGE_THRESHOLD        (ORBextractor.cpp:76)
 constexpr int kMinBorder = 16;       // EDGE_THRESHOLD - 3    (ORBextractor.cpp:780)
-constexpr int kCellsPerCta = 4;      // FAST cells handled by one CTA (one "slot")
+constexpr int kCellsPerCta = 2;      // FAST cells handled by one CTA (one "slot")
 constexpr int kMaxRoots = 16;
-constexpr int kFastThreads = 256;
+constexpr int kFastThreads = 128;
 constexpr int kOctThreads = 256;
 
 struct LevelGeom {
