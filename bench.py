@@ -257,8 +257,16 @@ def run_b200(args, rank, world, local_rank):
     nchunks = (F + chunk - 1) // chunk
     dom_ms_launch = stages[dom]["ms_per_step"] / nchunks
     achieved = ab[dom] * min(F, chunk) / (dom_ms_launch * 1e6)
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture, per launch
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        kname = {"fast": "fast_kernel", "blur": "blur_kernel", "orient_desc": "orient_desc_kernel", "quadtree": "octree_kernel",
+                 "pyramid": "resize4_kernel"}[dom]
+        traffic = tr["kernels"][kname]["dram_bytes_per_frame"] * min(F, chunk)
+    except Exception:
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "note": "algorithmic bytes/launch = %d B/frame x %d frames/launch; whole-frame figure %.2f MB/frame -> %.1f GB/s (frac %.4f)"
                         % (ab[dom], min(F, chunk), ab["frame_total"] / 1e6, ab["frame_total"] * value / world / 1e9,
                            ab["frame_total"] * value / world / 1e9 / hbm_peak)}
@@ -313,7 +321,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- single-frame latency through orbx_extract (the reference's actual call pattern: one frame per call) ------
     single = None
-    if rank == 0:
+    if rank == 0 and not args.skip_single:
         import ctypes as C
         one = np.ascontiguousarray(h_imgs.numpy()[0])
         skp = np.zeros(cap, api.KP_DTYPE); sde = np.zeros((cap, 32), np.uint8); n1 = C.c_int(0)
@@ -405,6 +413,7 @@ def main():
     ap.add_argument("--map-rows", type=int, default=2097152, help="map descriptors per GPU for the sharded kNN side metric")
     ap.add_argument("--skip-map", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-single", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -162,7 +162,7 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
     if (l > 0) { L.pyrOff = pyrBytes; pyrBytes += (size_t)chunk * L.h * L.pitch; }
     L.blurOff = blurBytes; blurBytes += (size_t)chunk * L.h * L.bpitch;
     L.blurTilesX = (L.w + 63) / 64; L.blurTilesY = (L.h + 25) / 26;   // kBlurTW x kBlurTH of orb_kernels.cu
-    L.blurTile0 = blurTile; blurTile += L.blurTilesX * L.blurTilesY;
+    L.blurTile0 = blurTile; blurTile += L.blurTilesX;      // one CTA per 64-px column strip
     L.scale = h->scale[l];
     L.kpSize = (float)(int)(31 * h->scale[l]);             // :845
     G.fastTileW = std::max(G.fastTileW, align_up(std::min(kCellsPerCta, L.nCols) * L.wCell + 6 + 15, 16));

@@ -685,95 +685,110 @@ __device__ __forceinline__ uint32_t blur_h(uint32_t w0, uint32_t w1) {       // 
 }
 
 __global__ void __launch_bounds__(256) blur_kernel(const Geom G, const Bufs B) {
+  // One CTA = one 64-pixel-wide column strip of one level of one frame; it walks down the strip in 26-row tiles so that
+  // the level lookup, pointers and alignment checks are paid once per strip instead of once per tile.
   __shared__ __align__(16) uint8_t tin[kBlurTH + 6][kBlurInW];
   __shared__ __align__(16) uint32_t hpair[(kBlurTH + 6) / 2][kBlurTW];      // rows 2p (low half) and 2p+1 (high half) of the horizontal pass
   const int tid = threadIdx.x, f = blockIdx.y;
   int l = 0;
   while (l + 1 < G.nlevels && (int)blockIdx.x >= G.L[l + 1].blurTile0) ++l;
   const LevelGeom& L = G.L[l];
-  const int t = blockIdx.x - L.blurTile0;
-  const int ty = t / L.blurTilesX, tx = t - ty * L.blurTilesX;
-  const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
+  const int tx = blockIdx.x - L.blurTile0;
+  const int x0 = tx * kBlurTW;
+  const int W = L.w, H = L.h, bpitch = L.bpitch, tilesY = L.blurTilesY;
   int pitch;
   const uint8_t* src = level_ptr(G, B, l, f, pitch);
   const bool aligned = (((uintptr_t)src | (uintptr_t)pitch) & 3) == 0;
-  // ---- stage 32 x 72 input bytes as 32-bit words: thread = (row, 8 lanes x up to 3 words); the row's REFLECT_101
-  //      source line is resolved once per thread, only words touching the left/right image border take the slow path
-  {
-    constexpr int WPR = kBlurInW / 4;   // 18 words per row
-    const int r = tid >> 3, wb = tid & 7;
-    const int sy = reflect101(min(y0 + r - 3, L.h + 2), L.h);
-    const uint8_t* row = src + (size_t)sy * pitch;
-    uint32_t* trow = reinterpret_cast<uint32_t*>(&tin[r][0]);
+  uint8_t* dst = B.blur + L.blurOff + (size_t)f * H * bpitch;
+  constexpr int WPR = kBlurInW / 4;   // 18 words per row
+  const int lr = tid >> 3, wb = tid & 7;                    // load role: row, first word
+  const int hq = tid & 15, hrp = tid >> 4;                  // horizontal/vertical role: column quad, row pair
+  // per-thread column classification for the load (fixed for the whole strip)
+  int gxw[3]; bool fastw[3];
 #pragma unroll
-    for (int w = wb; w < WPR; w += 8) {
-      const int gx = x0 - 4 + 4 * w;
-      uint32_t v;
-      if (aligned && gx >= 0 && gx + 3 < L.w) {
-        v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-      } else {
-        v = 0;
+  for (int k = 0; k < 3; ++k) {
+    const int w = wb + 8 * k;
+    gxw[k] = x0 - 4 + 4 * w;
+    fastw[k] = aligned && w < WPR && gxw[k] >= 0 && gxw[k] + 3 < W;
+  }
+  for (int ty = 0; ty < tilesY; ++ty) {
+    const int y0 = ty * kBlurTH;
+    // ---- stage 32 x 72 input bytes as 32-bit words (rows resolved with BORDER_REFLECT_101 once per thread)
+    {
+      const int sy = reflect101(min(y0 + lr - 3, H + 2), H);
+      const uint8_t* row = src + (size_t)sy * pitch;
+      uint32_t* trow = reinterpret_cast<uint32_t*>(&tin[lr][0]);
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const int sx = reflect101(min(max(gx + bb, -3), L.w + 2), L.w);
-          v |= (uint32_t)__ldg(row + sx) << (8 * bb);
+      for (int k = 0; k < 3; ++k) {
+        const int w = wb + 8 * k;
+        if (w >= WPR) continue;
+        uint32_t v;
+        if (fastw[k]) {
+          v = __ldg(reinterpret_cast<const uint32_t*>(row + gxw[k]));
+        } else {
+          v = 0;
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            const int sx = reflect101(min(max(gxw[k] + bb, -3), W + 2), W);
+            v |= (uint32_t)__ldg(row + sx) << (8 * bb);
+          }
         }
+        trow[w] = v;
       }
-      trow[w] = v;
     }
-  }
-  __syncthreads();
-  // ---- horizontal pass: one thread = 4 adjacent columns of 2 adjacent rows; exact in u16 (max 255*256)
-  {
-    const int q = tid & 15, rp = tid >> 4;            // rp: row pair 0..15
-    uint32_t o[2][4];
+    __syncthreads();
+    // ---- horizontal pass: one thread = 4 adjacent columns of 2 adjacent rows; exact in u16 (max 255*256)
+    {
+      uint32_t o[2][4];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(&tin[2 * rp + rr][4 * q]);
-      const uint32_t a = wp[0], b = wp[1], c = wp[2];   // bytes j = 0..11 <-> image x0-4+4q+j; output k uses bytes k+1..k+7
-      o[rr][0] = blur_h(__funnelshift_r(a, b, 8), __funnelshift_r(b, c, 8));
-      o[rr][1] = blur_h(__funnelshift_r(a, b, 16), __funnelshift_r(b, c, 16));
-      o[rr][2] = blur_h(__funnelshift_r(a, b, 24), __funnelshift_r(b, c, 24));
-      o[rr][3] = blur_h(b, c);
+      for (int rr = 0; rr < 2; ++rr) {
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(&tin[2 * hrp + rr][4 * hq]);
+        const uint32_t a = wp[0], b = wp[1], c = wp[2];   // bytes j = 0..11 <-> image x0-4+4q+j; output k uses bytes k+1..k+7
+        o[rr][0] = blur_h(__funnelshift_r(a, b, 8), __funnelshift_r(b, c, 8));
+        o[rr][1] = blur_h(__funnelshift_r(a, b, 16), __funnelshift_r(b, c, 16));
+        o[rr][2] = blur_h(__funnelshift_r(a, b, 24), __funnelshift_r(b, c, 24));
+        o[rr][3] = blur_h(b, c);
+      }
+      *reinterpret_cast<uint4*>(&hpair[hrp][4 * hq]) = make_uint4(o[0][0] | (o[1][0] << 16), o[0][1] | (o[1][1] << 16),
+                                                                 o[0][2] | (o[1][2] << 16), o[0][3] | (o[1][3] << 16));
     }
-    *reinterpret_cast<uint4*>(&hpair[rp][4 * q]) = make_uint4(o[0][0] | (o[1][0] << 16), o[0][1] | (o[1][1] << 16),
-                                                             o[0][2] | (o[1][2] << 16), o[0][3] | (o[1][3] << 16));
-  }
-  __syncthreads();
-  // ---- vertical pass: one thread = 4 columns x 2 rows (2g, 2g+1); both rows read the same four row pairs
-  if (tid < (kBlurTH / 2) * 16) {
-    const int q = tid & 15, g = tid >> 4;             // g: 0..12
-    uint4 P[4];
+    __syncthreads();
+    // ---- vertical pass: one thread = 4 columns x 2 rows (2g, 2g+1); both rows read the same four row pairs
+    if (hrp < kBlurTH / 2) {
+      const int g = hrp;
+      uint4 P[4];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) P[p] = *reinterpret_cast<const uint4*>(&hpair[g + p][4 * q]);
-    // even output row 2g: taps on rows 2g..2g+6 -> pairs (k0,k1)(k2,k3)(k4,k5)(k6,-); odd row 2g+1: (-,k0)(k1,k2)(k3,k4)(k5,k6)
-    constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;
-    constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);
-    uint32_t ev = 0, od = 0;
-    const uint32_t* c0 = reinterpret_cast<const uint32_t*>(&P[0]);
-    const uint32_t* c1 = reinterpret_cast<const uint32_t*>(&P[1]);
-    const uint32_t* c2 = reinterpret_cast<const uint32_t*>(&P[2]);
-    const uint32_t* c3 = reinterpret_cast<const uint32_t*>(&P[3]);
+      for (int p = 0; p < 4; ++p) P[p] = *reinterpret_cast<const uint4*>(&hpair[g + p][4 * hq]);
+      // even output row 2g: taps on rows 2g..2g+6 -> pairs (k0,k1)(k2,k3)(k4,k5)(k6,-); odd row 2g+1: (-,k0)(k1,k2)(k3,k4)(k5,k6)
+      constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;
+      constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);
+      uint32_t ev = 0, od = 0;
+      const uint32_t* c0 = reinterpret_cast<const uint32_t*>(&P[0]);
+      const uint32_t* c1 = reinterpret_cast<const uint32_t*>(&P[1]);
+      const uint32_t* c2 = reinterpret_cast<const uint32_t*>(&P[2]);
+      const uint32_t* c3 = reinterpret_cast<const uint32_t*>(&P[3]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint32_t e = __dp2a_lo(c0[k], E0, 32768u);
-      e = __dp2a_lo(c1[k], E1, e); e = __dp2a_lo(c2[k], E2, e); e = __dp2a_lo(c3[k], E3, e);
-      uint32_t o = __dp2a_lo(c0[k], O0, 32768u);
-      o = __dp2a_lo(c1[k], O1, o); o = __dp2a_lo(c2[k], O2, o); o = __dp2a_lo(c3[k], O3, o);
-      ev |= (e >> 16) << (8 * k);
-      od |= (o >> 16) << (8 * k);
+      for (int k = 0; k < 4; ++k) {
+        uint32_t e = __dp2a_lo(c0[k], E0, 32768u);
+        e = __dp2a_lo(c1[k], E1, e); e = __dp2a_lo(c2[k], E2, e); e = __dp2a_lo(c3[k], E3, e);
+        uint32_t o = __dp2a_lo(c0[k], O0, 32768u);
+        o = __dp2a_lo(c1[k], O1, o); o = __dp2a_lo(c2[k], O2, o); o = __dp2a_lo(c3[k], O3, o);
+        ev |= (e >> 16) << (8 * k);
+        od |= (o >> 16) << (8 * k);
+      }
+      const int x = x0 + 4 * hq;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int y = y0 + 2 * g + rr;
+        const uint32_t packed = rr ? od : ev;
+        if (y >= H || x >= W) continue;
+        uint8_t* d = dst + (size_t)y * bpitch + x;
+        if (x + 3 < W) *reinterpret_cast<uint32_t*>(d) = packed;     // bpitch is a multiple of 64, x of 4
+        else for (int k = 0; x + k < W; ++k) d[k] = (uint8_t)(packed >> (8 * k));
+      }
     }
-    uint8_t* dst = B.blur + L.blurOff + (size_t)f * L.h * L.bpitch;
-    const int x = x0 + 4 * q;
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int y = y0 + 2 * g + rr;
-      const uint32_t packed = rr ? od : ev;
-      if (y >= L.h || x >= L.w) continue;
-      uint8_t* d = dst + (size_t)y * L.bpitch + x;
-      if (x + 3 < L.w) *reinterpret_cast<uint32_t*>(d) = packed;     // bpitch is a multiple of 64, x of 4
-      else for (int k = 0; x + k < L.w; ++k) d[k] = (uint8_t)(packed >> (8 * k));
-    }
+    // the next tile's staging writes tin (last read before the second barrier) and its horizontal pass writes hpair
+    // only after the next barrier, which every thread reaches after finishing this vertical pass
   }
 }
 
