@@ -9,11 +9,17 @@
 // skipped by later points (matcher.cpp:87,314), later points overwrite earlier claims (:110,:347).  Once a
 // feature is claimed by a point with observations nobody can claim it again, so "blocked" is monotone and
 //   blocked(feature c, seen by point i)  <=>  occupied0[c]  or  exists j < i with choice[j] == c and has_obs[j].
-// That turns the sequential loop into a fixed point: every round recomputes all choices in parallel from the
-// previous round's block times; point i is final after at most i+1 rounds and in practice after a handful.
-// Candidates are produced once (parallel over points, window walked ix-outer / iy-inner like frame.cpp:223-243
-// so distance ties resolve identically) and only the cheap selection is iterated.
+// That turns the sequential loop into a fixed point.  Points are resolved in index order in chunks of one CTA
+// (1024 points): inside a chunk all choices are recomputed in parallel from the previous round's block times until
+// nothing changes (a point only depends on earlier points, so the fixed point is unique and equals the sequential
+// result); the chunk's block times are then frozen for the following chunks.
+//
+// Candidates are produced once by one warp per map point.  The grid is a CSR with cell index ix*48+iy, so for a fixed
+// ix the cells iy0..iy1 of a window are ONE contiguous CSR range: the warp strides over it with coalesced loads and
+// compacts the survivors in order with ballots, which is exactly the ix-outer / iy-inner / in-cell order of
+// frame.cpp:223-243 (so distance ties resolve identically).
 #include <limits.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -25,12 +31,14 @@ namespace orbx {
 constexpr int GC = ORBX_GRID_COLS, GR = ORBX_GRID_ROWS, NCELL = GC * GR;
 constexpr int TH_HIGH = 100;      // matcher.cpp:11
 constexpr int HISTO = 30;         // matcher.cpp:13
+constexpr int kResolveThreads = 1024;
 
 struct FrameDev {
-  const orbx_keypoint* kps; const uint8_t* desc; const float* uright; int n;
+  const orbx_keypoint* kps; const uint8_t* desc; int n;
   float xmin, xmax, ymin, ymax, gw, gh;
   const float* scale; int nlevels; const uint8_t* occupied0;
   const int* cellStart; const int* ids;
+  const float4* feat;               // per feature: x, y, octave (as float bits), uRight
 };
 
 struct PointsDev {   // union of the two variants' per-point inputs
@@ -73,61 +81,59 @@ __device__ __forceinline__ Window make_window(const FrameDev& F, const PointsDev
   return w;
 }
 
-// Walk the window exactly like Frame::getFeaturesInArea and apply the per-candidate gates of the matcher loop
-// that do not depend on earlier assignments (stereo consistency).  fn(idx) is called in traversal order.
-template <bool LOCAL, typename Fn>
-__device__ __forceinline__ void walk_window(const FrameDev& F, const SearchParams& S, const Window& w, Fn fn) {
+// cell range of a window (frame.cpp:205-221): floor for both ends
+__device__ __forceinline__ bool window_cells(const FrameDev& F, const Window& w, int& x0, int& x1, int& y0, int& y1) {
   const float du = __fsub_rn(w.u, F.xmin), dv = __fsub_rn(w.v, F.ymin);
-  const int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(du, w.r), F.gw)));          // frame.cpp:205-221
-  if (x0 >= GC) return;
-  const int x1 = min(GC - 1, (int)floorf(__fmul_rn(__fadd_rn(du, w.r), F.gw)));
-  if (x1 < 0) return;
-  const int y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(dv, w.r), F.gh)));
-  if (y0 >= GR) return;
-  const int y1 = min(GR - 1, (int)floorf(__fmul_rn(__fadd_rn(dv, w.r), F.gh)));
-  if (y1 < 0) return;
-  for (int ix = x0; ix <= x1; ++ix)
-    for (int iy = y0; iy <= y1; ++iy) {
-      const int c = ix * GR + iy;
-      for (int e = F.cellStart[c]; e < F.cellStart[c + 1]; ++e) {
-        const int idx = F.ids[e];
-        const orbx_keypoint k = F.kps[idx];
-        if (k.octave < w.minL || k.octave > w.maxL) continue;
-        if (!(fabsf(__fsub_rn(k.x, w.u)) < w.r && fabsf(__fsub_rn(k.y, w.v)) < w.r)) continue;
-        const float urt = F.uright[idx];
-        if (urt > 0) {
-          float err;
-          if (LOCAL) err = fabsf(__fsub_rn(w.aux, urt));                                        // matcher.cpp:317-322
-          else err = fabsf(__fsub_rn(__fsub_rn(w.u, __fmul_rn(S.bf, w.aux)), urt));             // :90-96
-          if (err > w.r) continue;
-        }
-        fn(idx);
-      }
-    }
+  x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(du, w.r), F.gw)));
+  if (x0 >= GC) return false;
+  x1 = min(GC - 1, (int)floorf(__fmul_rn(__fadd_rn(du, w.r), F.gw)));
+  if (x1 < 0) return false;
+  y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(dv, w.r), F.gh)));
+  if (y0 >= GR) return false;
+  y1 = min(GR - 1, (int)floorf(__fmul_rn(__fadd_rn(dv, w.r), F.gh)));
+  if (y1 < 0) return false;
+  return true;
 }
 
-__device__ __forceinline__ int hamming256(const uint8_t* a, const uint8_t* b) {
-  const uint4* p = reinterpret_cast<const uint4*>(a);
+// level / distance / stereo gates of one candidate (frame.cpp:234-241, matcher.cpp:90-96 / :317-322)
+template <bool LOCAL>
+__device__ __forceinline__ bool gate(const SearchParams& S, const Window& w, const float4 ft) {
+  const int oct = __float_as_int(ft.z);
+  if (oct < w.minL || oct > w.maxL) return false;
+  if (!(fabsf(__fsub_rn(ft.x, w.u)) < w.r && fabsf(__fsub_rn(ft.y, w.v)) < w.r)) return false;
+  if (ft.w > 0) {
+    float err;
+    if (LOCAL) err = fabsf(__fsub_rn(w.aux, ft.w));
+    else err = fabsf(__fsub_rn(__fsub_rn(w.u, __fmul_rn(S.bf, w.aux)), ft.w));
+    if (err > w.r) return false;
+  }
+  return true;
+}
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint8_t* b) {
   const uint4* q = reinterpret_cast<const uint4*>(b);
-  const uint4 a0 = p[0], a1 = p[1], b0 = q[0], b1 = q[1];
+  const uint4 b0 = __ldg(q), b1 = __ldg(q + 1);
   return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
          __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
 // ---- grid build (one CTA) ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) grid_build_kernel(const orbx_keypoint* __restrict__ kps, int n, float xmin, float ymin,
-                                                          float gw, float gh, int* cellOf, int* cellStart, int* ids) {
+__global__ void __launch_bounds__(1024) grid_build_kernel(const orbx_keypoint* __restrict__ kps, const float* __restrict__ uright,
+                                                          int n, float xmin, float ymin, float gw, float gh, int* cellOf,
+                                                          int* cellStart, int* ids, float4* feat) {
   __shared__ int cnt[NCELL];
   __shared__ int ws[40];
   const int tid = threadIdx.x, T = blockDim.x;
   for (int c = tid; c < NCELL; c += T) cnt[c] = 0;
   __syncthreads();
   for (int i = tid; i < n; i += T) {
-    const int gx = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, xmin), gw));      // frame.cpp:83-84
-    const int gy = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, ymin), gh));
+    const orbx_keypoint k = kps[i];
+    const int gx = (int)roundf(__fmul_rn(__fsub_rn(k.x, xmin), gw));      // frame.cpp:83-84
+    const int gy = (int)roundf(__fmul_rn(__fsub_rn(k.y, ymin), gh));
     int c = -1;
     if (gx >= 0 && gx < GC && gy >= 0 && gy < GR) { c = gx * GR + gy; atomicAdd(&cnt[c], 1); }   // :91-97
     cellOf[i] = c;
+    if (feat) feat[i] = make_float4(k.x, k.y, __int_as_float(k.octave), uright ? uright[i] : -1.f);
   }
   __syncthreads();
   const int total = block_exclusive_scan(cnt, NCELL, ws);
@@ -144,50 +150,53 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const orbx_keypoint* _
   }
 }
 
-// ---- candidate generation ---------------------------------------------------------------------------------
+// ---- candidate generation: one warp per map point ---------------------------------------------------------
+// misc[0] = running total of candidates (atomic allocation), misc[3] = overflow flag
 template <bool LOCAL>
-__global__ void sbp_count_kernel(FrameDev F, PointsDev P, SearchParams S, int* counts) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) sbp_walk_kernel(FrameDev F, PointsDev P, SearchParams S, int* offs, int* cnts, uint32_t* cand,
+                                                       int cap, int* misc) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= P.m) return;
-  int c = 0;
   const Window w = make_window<LOCAL>(F, P, S, i);
-  if (w.ok) walk_window<LOCAL>(F, S, w, [&](int) { ++c; });
-  counts[i] = c;
-}
-
-__global__ void __launch_bounds__(1024) sbp_scan_kernel(int* counts, int m, int* total) {
-  // in-place exclusive scan of counts[0..m) by one CTA, chunked through shared memory
-  __shared__ int buf[4096];
-  __shared__ int ws[40];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < m; base += 4096) {
-    const int len = min(4096, m - base);
-    for (int i = threadIdx.x; i < len; i += blockDim.x) buf[i] = counts[base + i];
-    __syncthreads();
-    const int t = block_exclusive_scan(buf, len, ws);
-    const int c = carry;
-    for (int i = threadIdx.x; i < len; i += blockDim.x) counts[base + i] = buf[i] + c;
-    __syncthreads();
-    if (threadIdx.x == 0) carry = c + t;
-    __syncthreads();
+  int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+  const bool any = w.ok && window_cells(F, w, x0, x1, y0, y1);
+  int cnt = 0;
+  if (any) {
+    for (int ix = x0; ix <= x1; ++ix) {
+      const int lo = __ldg(F.cellStart + ix * GR + y0), hi = __ldg(F.cellStart + ix * GR + y1 + 1);
+      for (int e = lo + lane; e < ((hi - lo + 31) & ~31) + lo; e += 32) {
+        bool pass = false;
+        if (e < hi) pass = gate<LOCAL>(S, w, __ldg(F.feat + __ldg(F.ids + e)));
+        cnt += __popc(__ballot_sync(0xffffffffu, pass));
+      }
+    }
   }
-  if (threadIdx.x == 0) { counts[m] = carry; *total = carry; }
-}
-
-template <bool LOCAL>
-__global__ void sbp_fill_kernel(FrameDev F, PointsDev P, SearchParams S, const int* offs, uint32_t* cand) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.m) return;
-  const Window w = make_window<LOCAL>(F, P, S, i);
-  if (!w.ok) return;
-  int o = offs[i];
-  const uint8_t* d = P.desc + (size_t)i * 32;
-  walk_window<LOCAL>(F, S, w, [&](int idx) {
-    const int dist = hamming256(d, F.desc + (size_t)idx * 32);
-    cand[o++] = (uint32_t)idx | ((uint32_t)dist << 20);
-  });
+  int base = 0;
+  if (lane == 0) {
+    if (cnt > 0) base = atomicAdd(&misc[0], cnt);
+    offs[i] = base; cnts[i] = cnt;
+    if (base + cnt > cap) { misc[3] = 1; cnts[i] = 0; }
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (cnt == 0 || base + cnt > cap) return;
+  const uint4* dq = reinterpret_cast<const uint4*>(P.desc + (size_t)i * 32);
+  const uint4 d0 = __ldg(dq), d1 = __ldg(dq + 1);
+  int run = base;
+  for (int ix = x0; ix <= x1; ++ix) {
+    const int lo = __ldg(F.cellStart + ix * GR + y0), hi = __ldg(F.cellStart + ix * GR + y1 + 1);
+    for (int e = lo + lane; e < ((hi - lo + 31) & ~31) + lo; e += 32) {
+      bool pass = false;
+      int idx = 0;
+      if (e < hi) { idx = __ldg(F.ids + e); pass = gate<LOCAL>(S, w, __ldg(F.feat + idx)); }
+      const unsigned b = __ballot_sync(0xffffffffu, pass);
+      if (pass) {
+        const int dist = hamming256(d0, d1, F.desc + (size_t)idx * 32);
+        cand[run + __popc(b & ((1u << lane) - 1))] = (uint32_t)idx | ((uint32_t)dist << 20);
+      }
+      run += __popc(b);
+    }
+  }
 }
 
 // ---- ordered resolution (one CTA) -------------------------------------------------------------------------
@@ -211,33 +220,41 @@ __device__ __forceinline__ int select_choice(const FrameDev& F, const SearchPara
   return bestI;
 }
 
+// blockF / blockT: block times (global scratch, or shared memory when n fits)
 template <bool LOCAL>
-__global__ void __launch_bounds__(1024) sbp_resolve_kernel(FrameDev F, PointsDev P, SearchParams S, const int* offs,
-                                                           const uint32_t* cand, int* choice, int* blockTime, int32_t* assign,
-                                                           int* match_cnt, int* rounds_out) {
-  __shared__ int changed, cnt, hist[HISTO], keepBin[3];
+__global__ void __launch_bounds__(kResolveThreads) sbp_resolve_kernel(FrameDev F, PointsDev P, SearchParams S, const int* offs,
+                                                                     const int* cnts, const uint32_t* cand, int* choice,
+                                                                     int* gBlockF, int* gBlockT, int smemN, int32_t* assign,
+                                                                     int* misc) {
+  extern __shared__ int sblock[];
+  __shared__ int cnt, hist[HISTO], keepBin[3];
   const int tid = threadIdx.x, T = blockDim.x, m = P.m, n = F.n;
-  for (int i = tid; i < m; i += T) choice[i] = -1;
+  int* blockF = (n <= smemN) ? sblock : gBlockF;
+  int* blockT = (n <= smemN) ? sblock + smemN : gBlockT;
+  for (int c = tid; c < n; c += T) blockF[c] = F.occupied0[c] ? -1 : INT_MAX;
+  __syncthreads();
   int rounds = 0;
-  while (true) {
-    if (tid == 0) changed = 0;
-    for (int c = tid; c < n; c += T) blockTime[c] = F.occupied0[c] ? -1 : INT_MAX;
-    __syncthreads();
-    for (int i = tid; i < m; i += T) {
-      const int c = choice[i];
-      if (c >= 0 && P.has_obs[i]) atomicMin(&blockTime[c], i);
+  for (int c0 = 0; c0 < m; c0 += T) {
+    const int i = c0 + tid;
+    const bool valid = i < m;
+    const int b = valid ? offs[i] : 0, e = valid ? b + cnts[i] : 0;
+    const bool obs = valid && P.has_obs[i];
+    int ch = -1;
+    while (true) {
+      for (int c = tid; c < n; c += T) blockT[c] = blockF[c];
+      __syncthreads();
+      if (obs && ch >= 0) atomicMin(&blockT[ch], i);
+      __syncthreads();
+      const int nc = (e > b) ? select_choice<LOCAL>(F, S, cand, b, e, i, blockT) : -1;
+      const int changed = nc != ch;
+      ch = nc;
+      ++rounds;
+      if (!__syncthreads_or(changed)) break;
     }
+    // blockT holds the block times implied by the (now stable) choices of this chunk: freeze them
+    for (int c = tid; c < n; c += T) blockF[c] = blockT[c];
+    if (valid) choice[i] = ch;
     __syncthreads();
-    for (int i = tid; i < m; i += T) {
-      const int b = offs[i], e = offs[i + 1];
-      const int nc = (e > b) ? select_choice<LOCAL>(F, S, cand, b, e, i, blockTime) : -1;
-      if (nc != choice[i]) { choice[i] = nc; changed = 1; }
-    }
-    __syncthreads();
-    ++rounds;
-    const bool again = changed != 0;
-    __syncthreads();
-    if (!again || rounds > m + 2) break;
   }
   // final holders: the last accepted writer of each feature (matcher.cpp:110 / :347)
   if (tid == 0) cnt = 0;
@@ -287,7 +304,7 @@ __global__ void __launch_bounds__(1024) sbp_resolve_kernel(FrameDev F, PointsDev
     if (dropped) atomicSub(&cnt, dropped);
     __syncthreads();
   }
-  if (tid == 0) { *match_cnt = cnt; *rounds_out = rounds; }
+  if (tid == 0) { misc[1] = cnt; misc[2] = rounds; }
 }
 
 // ---- host orchestration -----------------------------------------------------------------------------------
@@ -297,9 +314,11 @@ struct DevArena {      // grow-only per-thread device scratch so repeated search
     if (dev != device || bytes > cap) {
       if (base) { cudaSetDevice(device < 0 ? dev : device); cudaFree(base); base = nullptr; cap = 0; }
       if (cudaSetDevice(dev) != cudaSuccess) return ORBX_ERR_CUDA;
-      size_t want = std::max(bytes, (size_t)8 << 20);
+      size_t want = std::max(bytes + bytes / 2, (size_t)8 << 20);
       if (cudaMalloc(&base, want) != cudaSuccess) { base = nullptr; return ORBX_ERR_CUDA; }
       cap = want; device = dev;
+    } else if (cudaSetDevice(dev) != cudaSuccess) {
+      return ORBX_ERR_CUDA;
     }
     used = 0;
     return ORBX_OK;
@@ -311,41 +330,27 @@ struct DevArena {      // grow-only per-thread device scratch so repeated search
     return p;
   }
 };
-static thread_local DevArena g_arena, g_cand_arena;
-
-template <typename T> static size_t padded(size_t count) { return align_up_sz(sizeof(T) * count, 256) + 256; }
-
-struct FrameUpload { FrameDev F; int* cellOf; int* cellStart; int* ids; };
-
-static size_t frame_bytes(const orbx_frame_view* f) {
-  const size_t n = std::max(f->n, 1);
-  return padded<orbx_keypoint>(n) + padded<uint8_t>(n * 32) + padded<float>(n) + padded<float>(f->nlevels + 1) + padded<uint8_t>(n) +
-         padded<int>(n) + padded<int>(NCELL + 1) + padded<int>(n);
-}
-
-static int upload_frame(DevArena& A, const orbx_frame_view* f, FrameUpload& U, cudaStream_t st) {
-  const int n = f->n;
-  orbx_keypoint* kps = A.take<orbx_keypoint>(std::max(n, 1));
-  uint8_t* desc = A.take<uint8_t>((size_t)std::max(n, 1) * 32);
-  float* ur = A.take<float>(std::max(n, 1));
-  float* sc = A.take<float>(f->nlevels + 1);
-  uint8_t* occ = A.take<uint8_t>(std::max(n, 1));
-  U.cellOf = A.take<int>(std::max(n, 1)); U.cellStart = A.take<int>(NCELL + 1); U.ids = A.take<int>(std::max(n, 1));
-  if (n > 0) {
-    ORBX_CUDA(cudaMemcpyAsync(kps, f->kps, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice, st));
-    ORBX_CUDA(cudaMemcpyAsync(desc, f->desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
-    ORBX_CUDA(cudaMemcpyAsync(ur, f->uright, sizeof(float) * n, cudaMemcpyHostToDevice, st));
-    ORBX_CUDA(cudaMemcpyAsync(occ, f->occupied0, n, cudaMemcpyHostToDevice, st));
+struct HostArena {     // pinned staging so that all inputs of one search go up in a single copy
+  uint8_t* base = nullptr; size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes > cap) {
+      if (base) cudaFreeHost(base);
+      base = nullptr; cap = 0;
+      size_t want = std::max(bytes + bytes / 2, (size_t)4 << 20);
+      if (cudaMallocHost(&base, want) != cudaSuccess) { base = nullptr; return ORBX_ERR_CUDA; }
+      cap = want;
+    }
+    return ORBX_OK;
   }
-  ORBX_CUDA(cudaMemcpyAsync(sc, f->scale_factors, sizeof(float) * f->nlevels, cudaMemcpyHostToDevice, st));
-  FrameDev& F = U.F;
-  F.kps = kps; F.desc = desc; F.uright = ur; F.n = n; F.xmin = f->xmin; F.xmax = f->xmax; F.ymin = f->ymin; F.ymax = f->ymax;
-  F.gw = (float)GC / (f->xmax - f->xmin);           // camera.cpp:47-48
-  F.gh = (float)GR / (f->ymax - f->ymin);
-  F.scale = sc; F.nlevels = f->nlevels; F.occupied0 = occ; F.cellStart = U.cellStart; F.ids = U.ids;
-  grid_build_kernel<<<1, 1024, 0, st>>>(kps, n, F.xmin, F.ymin, F.gw, F.gh, U.cellOf, U.cellStart, U.ids);
-  return ORBX_OK;
-}
+};
+static thread_local DevArena g_arena, g_cand_arena;
+static thread_local HostArena g_host;
+
+// one packed upload: the same layout on the host staging buffer and on the device
+struct Packer {
+  size_t used = 0;
+  size_t add(size_t bytes) { used = align_up_sz(used, 256); size_t o = used; used += bytes; return o; }
+};
 
 static int check_frame(const orbx_frame_view* f) {
   if (!f || f->n < 0 || f->n >= (1 << 20) || f->nlevels < 1 || !f->scale_factors || !(f->xmax > f->xmin) || !(f->ymax > f->ymin) ||
@@ -371,47 +376,73 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
     *match_cnt = 0;
     return ORBX_OK;
   }
-  const size_t bytes = frame_bytes(frame) + padded<uint8_t>(m) * 2 + padded<float>(m) * 4 + padded<int32_t>(m) + padded<uint8_t>((size_t)m * 32) +
-                       padded<int>(m + 1) + padded<int>(m) + padded<int>(n) + padded<int32_t>(n) + padded<int>(4);
-  if (g_arena.reserve(bytes, device)) { set_error("device scratch allocation failed"); return ORBX_ERR_CUDA; }
+  // ---- pack every input into one pinned staging block ------------------------------------------------------
+  Packer pk;
+  const size_t o_kps = pk.add(sizeof(orbx_keypoint) * n), o_desc = pk.add((size_t)n * 32), o_ur = pk.add(sizeof(float) * n);
+  const size_t o_sc = pk.add(sizeof(float) * frame->nlevels), o_occ = pk.add(n);
+  const size_t o_valid = pk.add(m), o_obs = pk.add(m), o_u = pk.add(sizeof(float) * m), o_v = pk.add(sizeof(float) * m);
+  const size_t o_aux = pk.add(sizeof(float) * m), o_ac = pk.add(sizeof(float) * m), o_lvl = pk.add(sizeof(int32_t) * m);
+  const size_t o_pd = pk.add((size_t)m * 32);
+  const size_t inBytes = align_up_sz(pk.used, 256);
+  // device-only scratch behind the inputs
+  const size_t o_cellOf = pk.add(sizeof(int) * n), o_cellStart = pk.add(sizeof(int) * (NCELL + 1)), o_ids = pk.add(sizeof(int) * n);
+  const size_t o_feat = pk.add(sizeof(float4) * n), o_offs = pk.add(sizeof(int) * m), o_cnts = pk.add(sizeof(int) * m);
+  const size_t o_choice = pk.add(sizeof(int) * m), o_bF = pk.add(sizeof(int) * n), o_bT = pk.add(sizeof(int) * n);
+  const size_t o_assign = pk.add(sizeof(int32_t) * n), o_misc = pk.add(sizeof(int) * 8);
+  if (g_host.reserve(inBytes) || g_arena.reserve(pk.used + 256, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
+  uint8_t* hb = g_host.base;
+  memcpy(hb + o_kps, frame->kps, sizeof(orbx_keypoint) * n); memcpy(hb + o_desc, frame->desc, (size_t)n * 32);
+  memcpy(hb + o_ur, frame->uright, sizeof(float) * n); memcpy(hb + o_sc, frame->scale_factors, sizeof(float) * frame->nlevels);
+  memcpy(hb + o_occ, frame->occupied0, n);
+  memcpy(hb + o_valid, valid, m); memcpy(hb + o_obs, has_obs, m); memcpy(hb + o_u, u, sizeof(float) * m);
+  memcpy(hb + o_v, v, sizeof(float) * m); memcpy(hb + o_aux, aux, sizeof(float) * m); memcpy(hb + o_ac, angle_or_cos, sizeof(float) * m);
+  memcpy(hb + o_lvl, level, sizeof(int32_t) * m); memcpy(hb + o_pd, desc, (size_t)m * 32);
   cudaStream_t st = nullptr;
-  DevArena& A = g_arena;
-  FrameUpload U;
-  int rc = upload_frame(A, frame, U, st);
-  if (rc) return rc;
+  uint8_t* db = g_arena.take<uint8_t>(pk.used);
+  ORBX_CUDA(cudaMemcpyAsync(db, hb, inBytes, cudaMemcpyHostToDevice, st));
+  int* d_misc = (int*)(db + o_misc);
+  ORBX_CUDA(cudaMemsetAsync(d_misc, 0, sizeof(int) * 8, st));
+
+  FrameDev F;
+  F.kps = (const orbx_keypoint*)(db + o_kps); F.desc = db + o_desc; F.n = n;
+  F.xmin = frame->xmin; F.xmax = frame->xmax; F.ymin = frame->ymin; F.ymax = frame->ymax;
+  F.gw = (float)GC / (frame->xmax - frame->xmin);           // camera.cpp:47-48
+  F.gh = (float)GR / (frame->ymax - frame->ymin);
+  F.scale = (const float*)(db + o_sc); F.nlevels = frame->nlevels; F.occupied0 = db + o_occ;
+  F.cellStart = (const int*)(db + o_cellStart); F.ids = (const int*)(db + o_ids); F.feat = (const float4*)(db + o_feat);
   PointsDev P;
-  P.m = m;
-  uint8_t* d_valid = A.take<uint8_t>(m); uint8_t* d_obs = A.take<uint8_t>(m);
-  float* d_u = A.take<float>(m); float* d_v = A.take<float>(m); float* d_aux = A.take<float>(m); float* d_ac = A.take<float>(m);
-  int32_t* d_level = A.take<int32_t>(m); uint8_t* d_desc = A.take<uint8_t>((size_t)m * 32);
-  int* d_offs = A.take<int>(m + 1); int* d_choice = A.take<int>(m); int* d_block = A.take<int>(n);
-  int32_t* d_assign = A.take<int32_t>(n); int* d_misc = A.take<int>(4);
-  ORBX_CUDA(cudaMemcpyAsync(d_valid, valid, m, cudaMemcpyHostToDevice, st));
-  ORBX_CUDA(cudaMemcpyAsync(d_obs, has_obs, m, cudaMemcpyHostToDevice, st));
-  ORBX_CUDA(cudaMemcpyAsync(d_u, u, sizeof(float) * m, cudaMemcpyHostToDevice, st));
-  ORBX_CUDA(cudaMemcpyAsync(d_v, v, sizeof(float) * m, cudaMemcpyHostToDevice, st));
-  ORBX_CUDA(cudaMemcpyAsync(d_aux, aux, sizeof(float) * m, cudaMemcpyHostToDevice, st));
-  ORBX_CUDA(cudaMemcpyAsync(d_ac, angle_or_cos, sizeof(float) * m, cudaMemcpyHostToDevice, st));
-  ORBX_CUDA(cudaMemcpyAsync(d_level, level, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
-  ORBX_CUDA(cudaMemcpyAsync(d_desc, desc, (size_t)m * 32, cudaMemcpyHostToDevice, st));
-  P.valid = d_valid; P.u = d_u; P.v = d_v; P.aux = d_aux; P.level = d_level; P.angle_or_cos = d_ac; P.desc = d_desc; P.has_obs = d_obs;
-  const int blocks = (m + 127) / 128;
-  sbp_count_kernel<LOCAL><<<blocks, 128, 0, st>>>(U.F, P, S, d_offs);
-  sbp_scan_kernel<<<1, 1024, 0, st>>>(d_offs, m, d_misc);
-  int total = 0;
-  ORBX_CUDA(cudaMemcpyAsync(&total, d_misc, sizeof(int), cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaStreamSynchronize(st));
-  if (g_cand_arena.reserve(padded<uint32_t>(std::max(total, 1)), device)) { set_error("device scratch allocation failed"); return ORBX_ERR_CUDA; }
-  uint32_t* d_cand = g_cand_arena.take<uint32_t>(std::max(total, 1));
-  sbp_fill_kernel<LOCAL><<<blocks, 128, 0, st>>>(U.F, P, S, d_offs, d_cand);
-  sbp_resolve_kernel<LOCAL><<<1, 1024, 0, st>>>(U.F, P, S, d_offs, d_cand, d_choice, d_block, d_assign, d_misc + 1, d_misc + 2);
-  int res[2] = {0, 0};
-  ORBX_CUDA(cudaMemcpyAsync(assign, d_assign, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(res, d_misc + 1, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaStreamSynchronize(st));
-  ORBX_CUDA(cudaGetLastError());
-  *match_cnt = res[0];
-  return ORBX_OK;
+  P.m = m; P.valid = db + o_valid; P.has_obs = db + o_obs; P.u = (const float*)(db + o_u); P.v = (const float*)(db + o_v);
+  P.aux = (const float*)(db + o_aux); P.angle_or_cos = (const float*)(db + o_ac); P.level = (const int32_t*)(db + o_lvl);
+  P.desc = db + o_pd;
+
+  grid_build_kernel<<<1, 1024, 0, st>>>(F.kps, (const float*)(db + o_ur), n, F.xmin, F.ymin, F.gw, F.gh, (int*)(db + o_cellOf),
+                                        (int*)(db + o_cellStart), (int*)(db + o_ids), (float4*)(db + o_feat));
+  // candidate buffer: start with 48 per point; on overflow the search is re-run with the exact size (known afterwards)
+  size_t capCand = std::max<size_t>((size_t)m * 48, 4096);
+  const int smemN = 8192;
+  static thread_local bool attrSet = false;
+  if (!attrSet) {
+    ORBX_CUDA(cudaFuncSetAttribute(sbp_resolve_kernel<LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * 2 * smemN)));
+    attrSet = true;
+  }
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (g_cand_arena.reserve(sizeof(uint32_t) * capCand + 256, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
+    uint32_t* d_cand = g_cand_arena.take<uint32_t>(capCand);
+    if (attempt) ORBX_CUDA(cudaMemsetAsync(d_misc, 0, sizeof(int) * 8, st));
+    sbp_walk_kernel<LOCAL><<<(m + 7) / 8, 256, 0, st>>>(F, P, S, (int*)(db + o_offs), (int*)(db + o_cnts), d_cand, (int)std::min<size_t>(capCand, INT_MAX), d_misc);
+    sbp_resolve_kernel<LOCAL><<<1, kResolveThreads, sizeof(int) * 2 * smemN, st>>>(F, P, S, (const int*)(db + o_offs), (const int*)(db + o_cnts), d_cand,
+                                                                              (int*)(db + o_choice), (int*)(db + o_bF), (int*)(db + o_bT), smemN,
+                                                                              (int32_t*)(db + o_assign), d_misc);
+    int res[4] = {0, 0, 0, 0};
+    ORBX_CUDA(cudaMemcpyAsync(res, d_misc, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(assign, db + o_assign, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaStreamSynchronize(st));
+    ORBX_CUDA(cudaGetLastError());
+    if (!res[3]) { *match_cnt = res[1]; return ORBX_OK; }
+    capCand = (size_t)res[0] + 1024;      // exact need (the allocation counter keeps counting past the capacity)
+  }
+  set_error("candidate buffer overflow");
+  return ORBX_ERR_CAPACITY;
 }
 
 }  // namespace orbx
@@ -424,14 +455,15 @@ int orbx_grid_build(const orbx_keypoint* kps, int n, float xmin, float xmax, flo
                     int32_t* ids, int device) {
   if (n < 0 || (n > 0 && !kps) || !cell_start || !ids || !(xmax > xmin) || !(ymax > ymin)) { set_error("bad argument"); return ORBX_ERR_ARG; }
   const size_t nn = std::max(n, 1);
-  if (g_arena.reserve(padded<orbx_keypoint>(nn) + padded<int>(nn) * 2 + padded<int>(NCELL + 1), device)) {
+  if (g_arena.reserve(sizeof(orbx_keypoint) * nn + sizeof(int) * (2 * nn + NCELL + 1) + 2048, device)) {
     set_error("device scratch allocation failed");
     return ORBX_ERR_CUDA;
   }
   orbx_keypoint* d_k = g_arena.take<orbx_keypoint>(nn);
   int* d_cellOf = g_arena.take<int>(nn); int* d_start = g_arena.take<int>(NCELL + 1); int* d_ids = g_arena.take<int>(nn);
   if (n) ORBX_CUDA(cudaMemcpy(d_k, kps, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice));
-  grid_build_kernel<<<1, 1024>>>(d_k, n, xmin, ymin, (float)GC / (xmax - xmin), (float)GR / (ymax - ymin), d_cellOf, d_start, d_ids);
+  grid_build_kernel<<<1, 1024>>>(d_k, nullptr, n, xmin, ymin, (float)GC / (xmax - xmin), (float)GR / (ymax - ymin), d_cellOf, d_start, d_ids,
+                                 nullptr);
   ORBX_CUDA(cudaMemcpy(cell_start, d_start, sizeof(int) * (NCELL + 1), cudaMemcpyDeviceToHost));
   if (cell_start[NCELL] > 0) ORBX_CUDA(cudaMemcpy(ids, d_ids, sizeof(int) * cell_start[NCELL], cudaMemcpyDeviceToHost));
   ORBX_CUDA(cudaGetLastError());
