@@ -190,6 +190,31 @@ int orbx_search_by_projection_frame(const orbx_frame_view* frame, const orbx_sbp
 int orbx_search_by_projection_local(const orbx_frame_view* frame, const orbx_sbp_local_points* pts,
                                     float th_radius, float ratio, int32_t* assign, int* match_cnt, int device);
 
+/* ---------------------------------------------------------------------------------------------------
+ * BoW-guided matching
+ *   mode 0: Matcher::searchByBoW(KeyFrame*, Frame*, matches, checkRot)       (matcher.cpp:449-559)
+ *           match[i] (i < b.n, frame feature) = index of the keyframe feature whose map point was assigned
+ *   mode 1: Matcher::searchByBoW(KeyFrame*, KeyFrame*, matches, checkRot)    (matcher.cpp:561-677)
+ *           match[i] (i < a.n, kf1 feature)   = index of the matched kf2 feature
+ * -1 = no match, -2 = matched, then cleared by the rotation-histogram check.  Each side passes its DBoW3
+ * FeatureVector as a CSR sorted by node id (std::map order): node_ids[ngroups], group_start[ngroups+1],
+ * feat_idx[group_start[ngroups]] (feature indices in their vector order).  valid[i] = the feature's map point exists
+ * and is not bad (side b in mode 0: all ones).  Host pointers.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct orbx_bow_side {
+  int n;                       /* features */
+  const uint8_t* desc;         /* n x 32 */
+  const float* angle;          /* unKeypoints_[i].angle */
+  const uint8_t* valid;
+  int ngroups;
+  const uint32_t* node_ids;
+  const int32_t* group_start;
+  const int32_t* feat_idx;
+} orbx_bow_side;
+
+int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b, int mode, float ratio, int th_low, int check_rot,
+                       int32_t* match, int* match_cnt, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,21 @@ class _SbpLocalIn(C.Structure):
                 ("th_radius", C.c_float), ("ratio", C.c_float)]
 
 
+class _BowSide(C.Structure):
+    _fields_ = [("n", C.c_int), ("desc", C.c_void_p), ("angle", C.c_void_p), ("valid", C.c_void_p), ("ngroups", C.c_int),
+                ("node_ids", C.c_void_p), ("group_start", C.c_void_p), ("feat_idx", C.c_void_p)]
+
+
+def _bow_side(side, keep, struct=_BowSide):
+    def a(x, dt):
+        y = np.ascontiguousarray(x, dt); keep.append(y); return y.ctypes.data
+    s = struct()
+    s.n = len(side["desc"]); s.desc = a(side["desc"], np.uint8); s.angle = a(side["angle"], np.float32)
+    s.valid = a(side["valid"], np.uint8); s.ngroups = len(side["node_ids"]); s.node_ids = a(side["node_ids"], np.uint32)
+    s.group_start = a(side["group_start"], np.int32); s.feat_idx = a(side["feat_idx"], np.int32)
+    return s
+
+
 class Port:
     """ctypes view of oracle/liborbport.so (this repo's CPU restatement)."""
 
@@ -240,6 +255,17 @@ class Port:
         self.lib.port_sbp_frame.restype = C.c_int
         cnt = self.lib.port_sbp_frame(C.byref(s), _ptr(assign))
         return assign[:s.n].copy(), cnt
+
+    def search_by_bow(self, a, b, mode, ratio=0.7, th_low=50, check_rot=True):
+        """a, b: dict(desc, angle, valid, node_ids, group_start, feat_idx); mode 0 KF->Frame, 1 KF->KF."""
+        keep = []
+        sa = _bow_side(a, keep); sb = _bow_side(b, keep)
+        n_out = sb.n if mode == 0 else sa.n
+        match = np.empty(max(n_out, 1), np.int32)
+        self.lib.port_search_by_bow.restype = C.c_int
+        self.lib.port_search_by_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]
+        cnt = self.lib.port_search_by_bow(C.byref(sa), C.byref(sb), mode, ratio, th_low, int(check_rot), _ptr(match))
+        return match[:n_out].copy(), cnt
 
     def sbp_local(self, frame, pts, th_radius, ratio):
         """pts: dict(valid,u,v,ur,level,view_cos,desc,has_obs)."""

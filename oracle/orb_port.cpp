@@ -24,6 +24,7 @@
 //   searchByProjection(F,F)      matcher.cpp:18-148          -> port_sbp_frame()
 //   searchByProjection(F,local)  matcher.cpp:274-353         -> port_sbp_local()
 //   computeThreeMax        matcher.cpp:1258-1304             -> three_max()
+//   searchByBoW (both)     matcher.cpp:449-559, 561-677      -> port_search_by_bow()
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -646,6 +647,68 @@ int port_sbp_local(const port_sbp_local_in* in, int32_t* assign) {
       blocked[bestI] = in->has_obs[i];
       ++cnt;
     }
+  }
+  return cnt;
+}
+
+
+struct port_bow_side {
+  int n; const uint8_t* desc; const float* angle; const uint8_t* valid;
+  int ngroups; const uint32_t* node_ids; const int32_t* group_start; const int32_t* feat_idx;
+};
+
+// matcher.cpp:449-559 (mode 0, KeyFrame -> Frame) and :561-677 (mode 1, KeyFrame -> KeyFrame).
+// The FeatureVectors arrive as CSR sorted by node id; the merge walk (:465-535) visits the nodes both sides share.
+int port_search_by_bow(const port_bow_side* a, const port_bow_side* b, int mode, float ratio, int th_low, int check_rot,
+                       int32_t* match) {
+  const int nOut = mode == 0 ? b->n : a->n;
+  for (int i = 0; i < nOut; ++i) match[i] = -1;
+  std::vector<uint8_t> taken(b->n, 0);
+  std::vector<std::vector<int>> hist(30);
+  const float pdf = 30 / 360.0f;
+  int cnt = 0;
+  int ga = 0, gb = 0;
+  while (ga < a->ngroups && gb < b->ngroups) {
+    if (a->node_ids[ga] == b->node_ids[gb]) {
+      for (int ia = a->group_start[ga]; ia < a->group_start[ga + 1]; ++ia) {
+        const int idx1 = a->feat_idx[ia];
+        if (!a->valid[idx1]) continue;
+        int best1 = 256, best2 = 256, bestIdx = -1;
+        for (int ib = b->group_start[gb]; ib < b->group_start[gb + 1]; ++ib) {
+          const int idx2 = b->feat_idx[ib];
+          if (taken[idx2] || !b->valid[idx2]) continue;
+          const int d = hamming256(a->desc + (size_t)idx1 * 32, b->desc + (size_t)idx2 * 32);
+          if (d < best1) { best2 = best1; best1 = d; bestIdx = idx2; }
+          else if (d < best2) best2 = d;
+        }
+        if (best1 <= th_low && (float)best1 < ratio * (float)best2) {
+          taken[bestIdx] = 1;
+          const int outIdx = mode == 0 ? bestIdx : idx1;
+          match[outIdx] = mode == 0 ? idx1 : bestIdx;
+          if (check_rot) {
+            float rot = a->angle[idx1] - b->angle[bestIdx];
+            if (rot < 0) rot += 360.0f;
+            int bin = mode == 0 ? cvp::cv_round(rot * pdf) : (int)roundf(rot * pdf);
+            if (bin == 30) bin = 0;
+            hist[bin].push_back(outIdx);
+          }
+          ++cnt;
+        }
+      }
+      ++ga; ++gb;
+    } else if (a->node_ids[ga] < b->node_ids[gb]) {
+      while (ga < a->ngroups && a->node_ids[ga] < b->node_ids[gb]) ++ga;      // lower_bound
+    } else {
+      while (gb < b->ngroups && b->node_ids[gb] < a->node_ids[ga]) ++gb;
+    }
+  }
+  if (check_rot) {
+    int sizes[30], i1, i2, i3;
+    for (int k = 0; k < 30; ++k) sizes[k] = (int)hist[k].size();
+    three_max(sizes, 30, i1, i2, i3);
+    for (int k = 0; k < 30; ++k)
+      if (k != i1 && k != i2 && k != i3)
+        for (int idx : hist[k]) { match[idx] = -2; --cnt; }
   }
   return cnt;
 }

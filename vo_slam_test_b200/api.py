@@ -45,6 +45,11 @@ class _SbpLocalPoints(C.Structure):
                 ("level", C.c_void_p), ("view_cos", C.c_void_p), ("desc", C.c_void_p), ("has_obs", C.c_void_p)]
 
 
+class _BowSide(C.Structure):
+    _fields_ = [("n", C.c_int), ("desc", C.c_void_p), ("angle", C.c_void_p), ("valid", C.c_void_p), ("ngroups", C.c_int),
+                ("node_ids", C.c_void_p), ("group_start", C.c_void_p), ("feat_idx", C.c_void_p)]
+
+
 def load_library():
     """Load libvoslam_b200.so.  Raises OrbError if it has not been built (no fallback)."""
     global _lib
@@ -84,6 +89,7 @@ def load_library():
     L.orbx_grid_build.argtypes = [vp, i32, f32, f32, f32, f32, vp, vp, i32]
     L.orbx_search_by_projection_frame.argtypes = [vp, vp, f32, f32, i32, i32, i32, vp, vp, i32]
     L.orbx_search_by_projection_local.argtypes = [vp, vp, f32, f32, vp, vp, i32]
+    L.orbx_search_by_bow.argtypes = [vp, vp, i32, f32, i32, i32, vp, vp, i32]
     _lib = L
     return L
 
@@ -319,6 +325,26 @@ class Matcher:
         _check(self._lib.orbx_search_by_projection_frame(C.byref(fv), C.byref(s), radius, bf, int(forward), int(backward),
                                                          int(checkRot), _p(assign), C.byref(cnt), self.device))
         return assign[:fv.n].copy(), cnt.value
+
+    def searchByBoW(self, side_a, side_b, mode=0, checkRot=True, th_low=TH_LOW):
+        """Matcher::searchByBoW: mode 0 = (KeyFrame*, Frame*) (matcher.cpp:449-559), mode 1 = (KeyFrame*, KeyFrame*)
+        (matcher.cpp:561-677).  Each side: dict(desc, angle, valid, node_ids, group_start, feat_idx) with the DBoW3
+        FeatureVector as a CSR sorted by node id.  Returns (match, match_cnt); see include/orb_b200.h."""
+        keep = []
+        def side(d):
+            def a(x, dt):
+                y = np.ascontiguousarray(x, dt); keep.append(y); return y.ctypes.data
+            s = _BowSide()
+            s.n = len(d["desc"]); s.desc = a(d["desc"], np.uint8); s.angle = a(d["angle"], np.float32)
+            s.valid = a(d["valid"], np.uint8); s.ngroups = len(d["node_ids"]); s.node_ids = a(d["node_ids"], np.uint32)
+            s.group_start = a(d["group_start"], np.int32); s.feat_idx = a(d["feat_idx"], np.int32)
+            return s
+        sa, sb = side(side_a), side(side_b)
+        n_out = sb.n if mode == 0 else sa.n
+        match = np.zeros(max(n_out, 1), np.int32); cnt = C.c_int(0)
+        _check(self._lib.orbx_search_by_bow(C.byref(sa), C.byref(sb), mode, self.ratio_, th_low, int(checkRot), _p(match),
+                                            C.byref(cnt), self.device))
+        return match[:n_out].copy(), cnt.value
 
     def searchByProjectionLocal(self, frame, mappoints, thRadius):
         """Matcher::searchByProjection(Frame*, const vector<MapPoint*>&, thRadius) (matcher.cpp:274-353)."""

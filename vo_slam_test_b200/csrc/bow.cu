@@ -1,0 +1,215 @@
+// bow.cu -- BoW-guided matching: Matcher::searchByBoW(KeyFrame*, Frame*, ...) (matcher.cpp:449-559) and
+// Matcher::searchByBoW(KeyFrame*, KeyFrame*, ...) (matcher.cpp:561-677) for sm_100a.
+//
+// Both overloads merge-walk two DBoW3 FeatureVectors (vocabulary node -> feature indices) and, inside every node the
+// two sides share, run the greedy best/second-best + ratio loop: side-A features in order, each scanning the side-B
+// features of the node that are not yet taken (matcher.cpp:488 / :606).  A feature belongs to exactly one node, so
+// the greedy dependency never crosses nodes: one warp owns one shared node and replays the loop exactly (A features
+// sequentially, B features across the lanes, lexicographic (distance, position) top-2 by shuffles = strict '<' in
+// scan order), nodes run in parallel.  The rotation-histogram check (computeThreeMax, :537-556 / :655-671) runs in a
+// second one-CTA kernel.
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace orbx {
+
+constexpr int HISTO_B = 30;
+
+struct BowSideDev {
+  int n; const uint8_t* desc; const float* angle; const uint8_t* valid;
+  int ngroups; const uint32_t* node_ids; const int32_t* group_start; const int32_t* feat_idx;
+};
+
+__device__ __forceinline__ int hamm(const uint4 a0, const uint4 a1, const uint8_t* b) {
+  const uint4* q = reinterpret_cast<const uint4*>(b);
+  const uint4 b0 = __ldg(q), b1 = __ldg(q + 1);
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// mode 0: KeyFrame -> Frame   : match[b_idx] = a_idx   (mappointMatches is indexed by the frame feature, :508)
+// mode 1: KeyFrame -> KeyFrame: match[a_idx] = b_idx   (mappointMatches is indexed by the kf1 feature, :629)
+__global__ void __launch_bounds__(256) bow_match_kernel(BowSideDev A, BowSideDev B, int mode, float ratio, int th_low, int check_rot,
+                                                        int* takenB, int32_t* match, int8_t* binOf, int* hist) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= A.ngroups) return;
+  const uint32_t node = __ldg(A.node_ids + g);
+  int lo = 0, hi = B.ngroups;                       // lower_bound of `node` in B's sorted node ids (:531-534)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(B.node_ids + mid) < node) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= B.ngroups || __ldg(B.node_ids + lo) != node) return;
+  const int as = __ldg(A.group_start + g), ae = __ldg(A.group_start + g + 1);
+  const int bs = __ldg(B.group_start + lo), be = __ldg(B.group_start + lo + 1);
+  const uint32_t kInit = (256u << 20) | 0xFFFFFu;
+  for (int ia = as; ia < ae; ++ia) {
+    const int idx1 = __ldg(A.feat_idx + ia);
+    if (!A.valid[idx1]) continue;                   // `!mpk || mpk->isBad()` (:476 / :594)
+    const uint4* dq = reinterpret_cast<const uint4*>(A.desc + (size_t)idx1 * 32);
+    const uint4 d0 = __ldg(dq), d1 = __ldg(dq + 1);
+    uint32_t k1 = kInit, k2 = kInit;
+    for (int ib = bs + lane; ib < be; ib += 32) {
+      const int idx2 = __ldg(B.feat_idx + ib);
+      if (*((volatile int*)takenB + idx2) || !B.valid[idx2]) continue;    // (:488 / :606-609)
+      const uint32_t key = ((uint32_t)hamm(d0, d1, B.desc + (size_t)idx2 * 32) << 20) | (uint32_t)(ib - bs);
+      k2 = min(k2, max(key, k1));
+      k1 = min(k1, key);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+      const uint32_t n1 = min(k1, o1);
+      k2 = min(max(k1, o1), min(k2, o2));
+      k1 = n1;
+    }
+    const int best1 = (int)(k1 >> 20), best2 = (int)(k2 >> 20);
+    if (best1 <= th_low && (float)best1 < __fmul_rn(ratio, (float)best2)) {          // (:504-506 / :625-627)
+      const int idx2 = __ldg(B.feat_idx + bs + (int)(k1 & 0xFFFFFu));
+      if (lane == 0) {
+        takenB[idx2] = 1;
+        const int outIdx = mode == 0 ? idx2 : idx1;
+        match[outIdx] = mode == 0 ? idx1 : idx2;
+        if (check_rot) {
+          float rot = __fsub_rn(A.angle[idx1], B.angle[idx2]);                       // (:513-521 / :634-642)
+          if (rot < 0) rot = __fadd_rn(rot, 360.0f);
+          const float v = __fmul_rn(rot, (float)HISTO_B / 360.0f);
+          int bin = mode == 0 ? __float2int_rn(v) : (int)roundf(v);                  // cvRound (:517) vs round (:637)
+          if (bin == HISTO_B) bin = 0;
+          binOf[outIdx] = (int8_t)bin;
+          if (bin >= 0 && bin < HISTO_B) atomicAdd(&hist[bin], 1);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(1024) bow_finish_kernel(int nOut, int check_rot, int32_t* match, const int8_t* binOf, const int* hist,
+                                                          int* result) {
+  __shared__ int keep[3], cnt;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    cnt = 0;
+    int m1 = 0, m2 = 0, m3 = 0, i1 = -1, i2 = -1, i3 = -1;          // computeThreeMax, matcher.cpp:1258-1304
+    for (int i = 0; i < HISTO_B; ++i) {
+      const int s = hist[i];
+      if (s > m1) { m3 = m2; i3 = i2; m2 = m1; i2 = i1; m1 = s; i1 = i; }
+      else if (s > m2) { m3 = m2; i3 = i2; m2 = s; i2 = i; }
+      else if (s > m3) { m3 = s; i3 = i; }
+    }
+    if ((float)m2 < __fmul_rn(0.1f, (float)m1)) { i2 = -1; i3 = -1; }
+    else if ((float)m3 < __fmul_rn(0.1f, (float)m1)) { i3 = -1; }
+    keep[0] = i1; keep[1] = i2; keep[2] = i3;
+  }
+  __syncthreads();
+  int mine = 0;
+  for (int i = tid; i < nOut; i += blockDim.x) {
+    if (match[i] < 0) continue;
+    if (check_rot) {
+      const int b = binOf[i];
+      if (b != keep[0] && b != keep[1] && b != keep[2]) { match[i] = -2; continue; }   // cleared by the rotation check
+    }
+    ++mine;
+  }
+  if (mine) atomicAdd(&cnt, mine);
+  __syncthreads();
+  if (tid == 0) *result = cnt;
+}
+
+struct Arena {
+  uint8_t* d = nullptr; uint8_t* h = nullptr; size_t dcap = 0, hcap = 0; int device = -1;
+  int reserve(size_t dbytes, size_t hbytes, int dev) {
+    if (cudaSetDevice(dev) != cudaSuccess) return ORBX_ERR_CUDA;
+    if (dev != device || dbytes > dcap) {
+      if (d) cudaFree(d);
+      d = nullptr; dcap = 0;
+      const size_t want = std::max(dbytes + dbytes / 2, (size_t)4 << 20);
+      if (cudaMalloc(&d, want) != cudaSuccess) { d = nullptr; return ORBX_ERR_CUDA; }
+      dcap = want; device = dev;
+    }
+    if (hbytes > hcap) {
+      if (h) cudaFreeHost(h);
+      h = nullptr; hcap = 0;
+      const size_t want = std::max(hbytes + hbytes / 2, (size_t)4 << 20);
+      if (cudaMallocHost(&h, want) != cudaSuccess) { h = nullptr; return ORBX_ERR_CUDA; }
+      hcap = want;
+    }
+    return ORBX_OK;
+  }
+};
+static thread_local Arena g_bow;
+
+static int check_side(const orbx_bow_side* s) {
+  if (!s || s->n < 0 || s->ngroups < 0 || (s->n > 0 && (!s->desc || !s->angle || !s->valid)) ||
+      (s->ngroups > 0 && (!s->node_ids || !s->group_start || !s->feat_idx))) {
+    set_error("bad BoW side");
+    return ORBX_ERR_ARG;
+  }
+  return ORBX_OK;
+}
+
+}  // namespace orbx
+
+using namespace orbx;
+
+extern "C" int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b, int mode, float ratio, int th_low, int check_rot,
+                                  int32_t* match, int* match_cnt, int device) {
+  if (check_side(a) || check_side(b)) return ORBX_ERR_ARG;
+  if (!match || !match_cnt || (mode != 0 && mode != 1)) { set_error("bad argument"); return ORBX_ERR_ARG; }
+  const int nOut = mode == 0 ? b->n : a->n;
+  if (a->ngroups == 0 || b->ngroups == 0 || a->n == 0 || b->n == 0) {
+    for (int i = 0; i < nOut; ++i) match[i] = -1;
+    *match_cnt = 0;
+    return ORBX_OK;
+  }
+  size_t used = 0;
+  auto add = [&](size_t bytes) { used = align_up_sz(used, 256); size_t o = used; used += bytes; return o; };
+  size_t oa[6], ob[6];
+  const orbx_bow_side* sides[2] = {a, b};
+  size_t* offs[2] = {oa, ob};
+  for (int s = 0; s < 2; ++s) {
+    const orbx_bow_side* S = sides[s];
+    const int nfi = S->group_start[S->ngroups];
+    offs[s][0] = add((size_t)S->n * 32); offs[s][1] = add(sizeof(float) * S->n); offs[s][2] = add(S->n);
+    offs[s][3] = add(sizeof(uint32_t) * S->ngroups); offs[s][4] = add(sizeof(int32_t) * (S->ngroups + 1)); offs[s][5] = add(sizeof(int32_t) * nfi);
+  }
+  const size_t inBytes = align_up_sz(used, 256);
+  const size_t o_taken = add(sizeof(int) * b->n), o_match = add(sizeof(int32_t) * nOut), o_bin = add(nOut), o_hist = add(sizeof(int) * 32),
+               o_res = add(sizeof(int) * 4);
+  if (g_bow.reserve(used + 256, inBytes, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
+  for (int s = 0; s < 2; ++s) {
+    const orbx_bow_side* S = sides[s];
+    const int nfi = S->group_start[S->ngroups];
+    memcpy(g_bow.h + offs[s][0], S->desc, (size_t)S->n * 32); memcpy(g_bow.h + offs[s][1], S->angle, sizeof(float) * S->n);
+    memcpy(g_bow.h + offs[s][2], S->valid, S->n); memcpy(g_bow.h + offs[s][3], S->node_ids, sizeof(uint32_t) * S->ngroups);
+    memcpy(g_bow.h + offs[s][4], S->group_start, sizeof(int32_t) * (S->ngroups + 1)); memcpy(g_bow.h + offs[s][5], S->feat_idx, sizeof(int32_t) * nfi);
+  }
+  cudaStream_t st = nullptr;
+  uint8_t* db = g_bow.d;
+  ORBX_CUDA(cudaMemcpyAsync(db, g_bow.h, inBytes, cudaMemcpyHostToDevice, st));
+  ORBX_CUDA(cudaMemsetAsync(db + o_taken, 0, sizeof(int) * b->n, st));
+  ORBX_CUDA(cudaMemsetAsync(db + o_match, 0xFF, sizeof(int32_t) * nOut, st));      // -1
+  ORBX_CUDA(cudaMemsetAsync(db + o_hist, 0, sizeof(int) * 32 + 256, st));
+  BowSideDev D[2];
+  for (int s = 0; s < 2; ++s) {
+    D[s].n = sides[s]->n; D[s].desc = db + offs[s][0]; D[s].angle = (const float*)(db + offs[s][1]); D[s].valid = db + offs[s][2];
+    D[s].ngroups = sides[s]->ngroups; D[s].node_ids = (const uint32_t*)(db + offs[s][3]);
+    D[s].group_start = (const int32_t*)(db + offs[s][4]); D[s].feat_idx = (const int32_t*)(db + offs[s][5]);
+  }
+  bow_match_kernel<<<(a->ngroups + 7) / 8, 256, 0, st>>>(D[0], D[1], mode, ratio, th_low, check_rot, (int*)(db + o_taken),
+                                                         (int32_t*)(db + o_match), (int8_t*)(db + o_bin), (int*)(db + o_hist));
+  bow_finish_kernel<<<1, 1024, 0, st>>>(nOut, check_rot, (int32_t*)(db + o_match), (const int8_t*)(db + o_bin), (const int*)(db + o_hist),
+                                        (int*)(db + o_res));
+  int res = 0;
+  ORBX_CUDA(cudaMemcpyAsync(match, db + o_match, sizeof(int32_t) * nOut, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaMemcpyAsync(&res, db + o_res, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaStreamSynchronize(st));
+  ORBX_CUDA(cudaGetLastError());
+  *match_cnt = res;
+  return ORBX_OK;
+}

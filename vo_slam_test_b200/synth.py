@@ -107,3 +107,24 @@ def make_projection_case(kps, desc, scale_factors, m, seed=0, W=640, H=480, ster
         pts.update(invz=(1.0 / z).astype(np.float32), octave=octave,
                    angle=((kps["angle"][src] + rng.normal(0, 6.0, m)) % 360.0).astype(np.float32))
     return frame, pts
+
+
+def make_bow_side(desc, angle, valid=None, node_bits=9, seed=0, shuffle=True):
+    """A synthetic DBoW3 FeatureVector for a descriptor set: vocabulary node = the first `node_bits` bits of the
+    descriptor (so near-duplicate descriptors mostly share a node, like words of a real vocabulary), returned as the
+    CSR the C ABI takes: node ids ascending (std::map order), feature indices in insertion order (ascending index,
+    optionally shuffled to prove that the in-node order is honoured)."""
+    rng = np.random.default_rng(seed)
+    n = len(desc)
+    bits = np.unpackbits(desc[:, :4], axis=1)[:, :node_bits].astype(np.uint32)
+    node = (bits << np.arange(node_bits - 1, -1, -1, dtype=np.uint32)).sum(1).astype(np.uint32)
+    ids = np.unique(node)
+    start = [0]; feat = []
+    for v in ids:
+        f = np.flatnonzero(node == v)
+        if shuffle and len(f) > 1 and rng.random() < 0.3:
+            f = rng.permutation(f)
+        feat.append(f); start.append(start[-1] + len(f))
+    return dict(desc=desc, angle=np.asarray(angle, np.float32), valid=np.ones(n, np.uint8) if valid is None else valid,
+                node_ids=ids, group_start=np.asarray(start, np.int32),
+                feat_idx=np.concatenate(feat).astype(np.int32) if feat else np.zeros(0, np.int32))
