@@ -22,7 +22,7 @@ void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe
 cudaError_t configure_kernels(const Geom& G);
 size_t fast_smem_bytes(const Geom& G);
 size_t octree_smem_bytes(const Geom& G);
-void launch_fast(const Geom& G, const Bufs& B, int nframes, cudaStream_t st);
+void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st);
 void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st);
 void launch_blur(const Geom& G, const Bufs& B, int nframes, cudaStream_t st);
 void launch_orient_desc(const Geom& G, const Bufs& B, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
@@ -30,6 +30,10 @@ void launch_orient_desc(const Geom& G, const Bufs& B, orbx_keypoint* kps, uint8_
 
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
 static inline int cv_round_d(double v) { return (int)lrint(v); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct DevTaps {
   ResizeTaps t{};
@@ -58,6 +62,10 @@ struct orbx_extractor {
   uint32_t* d_sel = nullptr; int* d_selCount = nullptr;
   float2* d_pattern = nullptr; int* d_umax = nullptr;
   std::vector<DevTaps> taps;
+  TmaSet tma{};              // FAST tile descriptors (levels >= 1 fixed after configure, level 0 per call)
+  CUtensorMap hostMaps[kMaxLevels];   // host copies; d_maps mirrors them in device memory
+  CUtensorMap* d_maps = nullptr;
+  EncodeTiledFn encode = nullptr;
   // staging for the host entry points
   uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
   orbx_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int32_t* d_counts = nullptr;
@@ -66,6 +74,7 @@ struct orbx_extractor {
   int32_t *d_midx = nullptr, *d_md1 = nullptr, *d_md2 = nullptr, *d_qf = nullptr; uint8_t* d_mok = nullptr;
   size_t m_frames = 0; int m_cap = 0;
   long long launches = 0;
+  const uint8_t* map0_base = nullptr; size_t map0_row = 0, map0_frame = 0; int map0_n = 0, map0_want = 0;
   // last chunk info for the debug taps
   const uint8_t* last_img0 = nullptr; size_t last_rowStride = 0, last_frameStride = 0; int last_frames = 0;
 };
@@ -88,6 +97,8 @@ void free_workspace(orbx_extractor* h) {
   for (auto& t : h->taps) cudaFree(t.block);
   h->taps.clear();
   h->haveGeom = false; h->chunk = 0;
+  h->map0_base = nullptr; h->map0_n = 0;
+  for (int l = 0; l < kMaxLevels; ++l) h->tma.use[l] = 0;
 }
 
 // cv::resize tap tables for one axis
@@ -104,6 +115,27 @@ void axis_taps(int ssize, int dsize, std::vector<int>& ofs, std::vector<short>& 
     a0[d] = (short)cv_round_f((1.f - f) * 2048.f);
     a1[d] = (short)cv_round_f(f * 2048.f);
   }
+}
+
+// One rank-3 (x bytes, y rows, frame) tiled tensor map over a level; box = the FAST kernel's shared-memory tile.
+bool encode_level_map(orbx_extractor* h, int l, const uint8_t* base, size_t pitch, size_t frameStride, int nframes) {
+  h->tma.use[l] = 0;
+  if (!h->encode || !h->d_maps || env_int("ORBX_NO_TMA", 0)) return false;
+  if ((((uintptr_t)base) | pitch | frameStride) & 15) return false;      // TMA needs 16-byte aligned base and strides
+  const LevelGeom& L = h->G.L[l];
+  if (h->G.fastTileW > 256 || h->G.fastTileH > 256) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)std::max(nframes, 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frameStride};
+  cuuint32_t box[3] = {(cuuint32_t)h->G.fastTileW, (cuuint32_t)h->G.fastTileH, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = h->encode(&h->hostMaps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  // stream-ordered upload on the legacy default stream would serialise; a synchronous copy is fine (rare event)
+  if (cudaMemcpy(h->d_maps + l, &h->hostMaps[l], sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  h->tma.use[l] = 1;
+  return true;
 }
 
 // Build the per-size geometry (cell grid, slots, capacities, workspace offsets) and allocate for `chunk` frames.
@@ -235,6 +267,8 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
   }
   h->haveGeom = true;
   h->chunk = chunk;
+  for (int l = 1; l < nl; ++l)
+    encode_level_map(h, l, h->d_pyr + G.L[l].pyrOff, (size_t)G.L[l].pitch, (size_t)G.L[l].h * G.L[l].pitch, chunk);
   return ORBX_OK;
 }
 
@@ -252,6 +286,11 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
               orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t st,
               cudaEvent_t* ev = nullptr /* 6 events: before pyramid, fast, octree, blur, orient_desc, end */) {
   const Geom& G = h->G;
+  if (h->map0_base != d_imgs || h->map0_row != rowStride || h->map0_frame != frameStride || h->map0_n < frame0 + n) {
+    // level 0 is the caller's buffer: (re)describe it; the map covers frames [0, frame0+n) at least
+    encode_level_map(h, 0, d_imgs, rowStride, frameStride, std::max(frame0 + n, h->map0_want));
+    h->map0_base = d_imgs; h->map0_row = rowStride; h->map0_frame = frameStride; h->map0_n = std::max(frame0 + n, h->map0_want);
+  }
   const uint8_t* img0 = d_imgs + (size_t)frame0 * frameStride;
   Bufs B = make_bufs(h, img0, rowStride, frameStride);
   if (ev) cudaEventRecord(ev[0], st);
@@ -265,7 +304,8 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
                   h->taps[l].t, n, st);
   }
   if (ev) cudaEventRecord(ev[1], st);
-  launch_fast(G, B, n, st);
+  h->tma.frame0 = frame0;
+  launch_fast(G, B, h->tma, n, st);
   if (ev) cudaEventRecord(ev[2], st);
   launch_octree(G, B, n, st);
   if (ev) cudaEventRecord(ev[3], st);
@@ -348,6 +388,14 @@ int orbx_create(const orbx_params* p, orbx_handle* out) {
     delete h;
     return ORBX_ERR_CUDA;
   }
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      h->encode = (EncodeTiledFn)fn;
+    if (cudaMalloc(&h->d_maps, sizeof(CUtensorMap) * kMaxLevels) != cudaSuccess) h->d_maps = nullptr;
+    h->tma.map = h->d_maps;
+  }
   float2 pat[512];
   // transposed for coalesced warp reads: entry [k][lane] = point k (0..15) of descriptor byte `lane`
   for (int lane = 0; lane < 32; ++lane)
@@ -371,6 +419,7 @@ int orbx_destroy(orbx_handle h) {
   cudaSetDevice(h->p.device);
   cudaDeviceSynchronize();
   free_workspace(h);
+  cudaFree(h->d_maps);
   cudaFree(h->d_pattern); cudaFree(h->d_umax); cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc);
   cudaFree(h->d_counts);
   cudaFree(h->d_midx); cudaFree(h->d_md1); cudaFree(h->d_md2); cudaFree(h->d_mok); cudaFree(h->d_qf);
@@ -428,6 +477,7 @@ int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes,
   int rc = configure(h, w, height, chunk);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  h->map0_want = nframes;
   for (int f0 = 0; f0 < nframes; f0 += h->chunk) {
     const int n = std::min(h->chunk, nframes - f0);
     rc = run_chunk(h, d_imgs, row_stride, frame_stride, f0, n, d_kps, d_desc, cap, d_counts, st);
@@ -506,6 +556,7 @@ int orbx_profile_stages(orbx_handle h, const uint8_t* d_imgs, int nframes, int w
   int rc = configure(h, w, height, std::min(nframes, chunkMax));
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  h->map0_want = nframes;
   const int nchunks = (nframes + h->chunk - 1) / h->chunk;
   std::vector<cudaEvent_t> ev((size_t)nchunks * 6);
   for (auto& e : ev) ORBX_CUDA(cudaEventCreate(&e));
@@ -580,6 +631,7 @@ int orbx_extract_match_batch(orbx_handle h, const uint8_t* imgs, int nframes, in
     ORBX_CUDA(cudaStreamCreateWithFlags(&h->backStream, cudaStreamNonBlocking));
   }
   cudaStream_t sc = h->copyStream, sk = h->stream, sb = h->backStream;
+  h->map0_want = nframes;
   const int nchunks = (nframes + h->chunk - 1) / h->chunk;
   std::vector<cudaEvent_t> up(nchunks), done(nchunks);
   for (int c = 0; c < nchunks; ++c) {

@@ -2,6 +2,8 @@
 #pragma once
 #include <vector>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace orbx {
@@ -69,6 +71,15 @@ struct Bufs {
   int* selCount;           // [chunk][nlevels]
   const float2* pattern;   // 512 rBRIEF points
   const int* umax;         // 16
+};
+
+// TMA descriptors (cuTensorMapEncodeTiled, rank 3: x bytes, y rows, frame) of every pyramid level, used by the FAST
+// kernel to fetch its tile with one cp.async.bulk.tensor instead of a load/store loop.  use[l] == 0: the level cannot be
+// described (base or pitch not 16-byte aligned) and the kernel falls back to vector/byte loads.
+struct TmaSet {
+  const CUtensorMap* map;  // kMaxLevels descriptors in GLOBAL memory (64-byte aligned), written by the host before launch
+  int use[kMaxLevels];
+  int frame0;              // z coordinate of the chunk's first frame in the level-0 map (levels >= 1 are chunk-local)
 };
 
 struct ResizeTaps {        // device tables of one level

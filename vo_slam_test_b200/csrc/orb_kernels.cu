@@ -209,13 +209,14 @@ __device__ __forceinline__ void fast_best2(const uint8_t* pa, const uint8_t* pb,
   bestB = max((int)(short)(a >> 16), -(int)(short)(b >> 16));
 }
 
-__global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const Bufs B) {
+__global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const Bufs B, const TmaSet TM) {
   // Work-efficient layout: (1) tile staged with 16-byte loads, (2) a cheap 16-pixel-ring rejection test over all
   // pixels that pushes the few survivors into a shared-memory queue, (3) the full arc score and the per-cell NMS run
   // densely over that queue only, (4) survivors are ranked by (cell, row, column) to emit them in the reference order.
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int cellCnt[kCellsPerCta];
   __shared__ int qn, sn, in, cn, retryMask;
+  __shared__ __align__(8) uint64_t tmaBar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = blockIdx.x, f = blockIdx.y;
   int l = 0;
@@ -245,7 +246,26 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
   const uint8_t* lvl = level_ptr(G, B, l, f, pitch);
   const int gx0 = kMinBorder + tx0;
   int ox = 0;
-  if ((((uintptr_t)lvl | (uintptr_t)pitch) & 15) == 0) {
+  const bool viaTma = TM.use[l] != 0;
+  if (viaTma) {
+    // ---- one TMA tile load (UTMALDG): box = fastTileW x fastTileH bytes at (gx0 & ~15, 16+ty0, frame); rows land with
+    //      pitch sp, out-of-image parts are zero-filled and never read.  Completion is tracked by an mbarrier.
+    //      The innermost TMA coordinate must be 16-byte aligned (an unaligned one raises "illegal instruction" on
+    //      B200, measured with tools/scratch/tma_test*.cu), hence the same `ox` shift as the vector-load path.
+    ox = gx0 & 15;
+    if (tid == 0) {
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tmaBar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(sp * G.fastTileH)) : "memory");
+      const int z = (l == 0 ? TM.frame0 : 0) + f;
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+              (uint32_t)__cvta_generic_to_shared(img)),
+          "l"(reinterpret_cast<uint64_t>(TM.map + l)), "r"(gx0 - ox), "r"(kMinBorder + ty0), "r"(z), "r"(bar)
+          : "memory");
+    }
+  } else if ((((uintptr_t)lvl | (uintptr_t)pitch) & 15) == 0) {
     ox = gx0 & 15;
     const int wpr = (ox + tw + 15) >> 4;                       // 16-byte words per tile row (<= 32)
     const uint8_t* base = lvl + (size_t)(kMinBorder + ty0) * pitch + (gx0 - ox);
@@ -267,6 +287,16 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const 
   if (tid < kCellsPerCta) cellCnt[tid] = 0;
   if (tid == 0) { qn = 0; sn = 0; in = 0; cn = 0; retryMask = 0; }
   __syncthreads();
+  if (viaTma) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tmaBar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "TW_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra TD_%=;\n\t"
+        "bra TW_%=;\n\t"
+        "TD_%=:\n\t}" ::"r"(bar) : "memory");
+  }
 
   const int w1 = L.wCell, w2 = 2 * L.wCell, w3 = 3 * L.wCell;
   const uint8_t* img0 = img + 3 * sp + 3 + ox;                 // interior origin
@@ -988,8 +1018,8 @@ cudaError_t configure_kernels(const Geom& G) {
   return cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_smem_bytes(G));
 }
 
-void launch_fast(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
-  fast_kernel<<<dim3(G.totalSlots, nframes), kFastThreads, fast_smem_bytes(G), st>>>(G, B);
+void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st) {
+  fast_kernel<<<dim3(G.totalSlots, nframes), kFastThreads, fast_smem_bytes(G), st>>>(G, B, TM);
 }
 void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
   octree_kernel<<<dim3(G.nlevels, nframes), kOctThreads, octree_smem_bytes(G), st>>>(G, B);
