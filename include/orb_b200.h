@@ -190,6 +190,20 @@ int orbx_search_by_projection_frame(const orbx_frame_view* frame, const orbx_sbp
 int orbx_search_by_projection_local(const orbx_frame_view* frame, const orbx_sbp_local_points* pts,
                                     float th_radius, float ratio, int32_t* assign, int* match_cnt, int device);
 
+/* SURVEY section 8f, rank 2 (same kernels, different gates).  Both take orbx_sbp_frame_points with
+ *   valid[i]  = every host-side gate of the reference loop passed (null / bad / found set, depth sign, image bounds,
+ *               distance range, viewing angle),  octave[i] = mp->predictScale(...),  invz / has_obs unused (pass zeros).
+ * reloc: Matcher::searchByProjection(Frame*, KeyFrame*, radius, distThreshold, found, checkRot)   (matcher.cpp:150-272)
+ *        frame->occupied0[i] = frame_curr->mappoints_[i] != nullptr;  angle[i] = keyframe->unKeypoints_[i].angle.
+ * sim3 : Matcher::searchByProjection(KeyFrame*, Sim3&, loopMapPoints, matchMapPoints, th)         (matcher.cpp:356-447)
+ *        `keyframe` describes the keyframe's features; occupied0[i] = matchMapPoints[i] != nullptr on entry.  The
+ *        reference tests matchMapPoints[j] with the window position j instead of the feature index (:422); that is
+ *        reproduced bit for bit. */
+int orbx_search_by_projection_reloc(const orbx_frame_view* frame, const orbx_sbp_frame_points* pts, float radius,
+                                    float dist_threshold, int check_rot, int32_t* assign, int* match_cnt, int device);
+int orbx_search_by_projection_sim3(const orbx_frame_view* keyframe, const orbx_sbp_frame_points* pts, int th, int32_t* assign,
+                                   int* match_cnt, int device);
+
 /* ---------------------------------------------------------------------------------------------------
  * BoW-guided matching
  *   mode 0: Matcher::searchByBoW(KeyFrame*, Frame*, matches, checkRot)       (matcher.cpp:449-559)

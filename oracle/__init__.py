@@ -267,6 +267,39 @@ class Port:
         cnt = self.lib.port_search_by_bow(C.byref(sa), C.byref(sb), mode, ratio, th_low, int(check_rot), _ptr(match))
         return match[:n_out].copy(), cnt
 
+    def _sbp_frame_struct(self, frame, pts, radius, check_rot, keep):
+        def a(x, dt):
+            y = np.ascontiguousarray(x, dt); keep.append(y); return y.ctypes.data
+        s = _SbpFrameIn()
+        s.kps = a(frame["kps"], KP_DTYPE); s.desc = a(frame["desc"], np.uint8); s.uright = a(frame["uright"], np.float32)
+        s.n = len(frame["kps"])
+        s.xmin, s.xmax, s.ymin, s.ymax = [float(b) for b in frame["bounds"]]
+        s.scale_factors = a(frame["scale_factors"], np.float32); s.nlevels = len(frame["scale_factors"])
+        s.occupied0 = a(frame["occupied0"], np.uint8)
+        s.m = len(pts["u"]); s.valid = a(pts["valid"], np.uint8); s.u = a(pts["u"], np.float32)
+        s.v = a(pts["v"], np.float32); s.invz = a(pts["invz"], np.float32); s.octave = a(pts["octave"], np.int32)
+        s.angle = a(pts["angle"], np.float32); s.mp_desc = a(pts["desc"], np.uint8); s.has_obs = a(pts["has_obs"], np.uint8)
+        s.radius = radius; s.bf = 0.0; s.forward = 0; s.backward = 0; s.check_rot = int(check_rot)
+        return s
+
+    def sbp_reloc(self, frame, pts, radius, dist_threshold, check_rot=True):
+        keep = []
+        s = self._sbp_frame_struct(frame, pts, radius, check_rot, keep)
+        assign = np.empty(max(s.n, 1), np.int32)
+        self.lib.port_sbp_reloc.restype = C.c_int
+        self.lib.port_sbp_reloc.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+        cnt = self.lib.port_sbp_reloc(C.byref(s), dist_threshold, _ptr(assign))
+        return assign[:s.n].copy(), cnt
+
+    def sbp_sim3(self, keyframe, pts, th):
+        keep = []
+        s = self._sbp_frame_struct(keyframe, pts, 0.0, False, keep)
+        assign = np.empty(max(s.n, 1), np.int32)
+        self.lib.port_sbp_sim3.restype = C.c_int
+        self.lib.port_sbp_sim3.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        cnt = self.lib.port_sbp_sim3(C.byref(s), int(th), _ptr(assign))
+        return assign[:s.n].copy(), cnt
+
     def sbp_local(self, frame, pts, th_radius, ratio):
         """pts: dict(valid,u,v,ur,level,view_cos,desc,has_obs)."""
         keep = []

@@ -24,6 +24,8 @@
 //   searchByProjection(F,F)      matcher.cpp:18-148          -> port_sbp_frame()
 //   searchByProjection(F,local)  matcher.cpp:274-353         -> port_sbp_local()
 //   computeThreeMax        matcher.cpp:1258-1304             -> three_max()
+//   searchByProjection(F,KF)     matcher.cpp:150-272         -> port_sbp_reloc()
+//   searchByProjection(KF,Sim3)  matcher.cpp:356-447         -> port_sbp_sim3()
 //   searchByBoW (both)     matcher.cpp:449-559, 561-677      -> port_search_by_bow()
 #include <cmath>
 #include <cstdint>
@@ -709,6 +711,93 @@ int port_search_by_bow(const port_bow_side* a, const port_bow_side* b, int mode,
     for (int k = 0; k < 30; ++k)
       if (k != i1 && k != i2 && k != i3)
         for (int idx : hist[k]) { match[idx] = -2; --cnt; }
+  }
+  return cnt;
+}
+
+
+// KeyFrame::getFeaturesInArea (keyframe.cpp:268-312): the Frame version without the level filter.
+static void area_nolevel(const Grid& g, const PortKp* kps, float u, float v, float r, std::vector<int>& out) {
+  g.area(kps, u, v, r, -1000000, 1000000, out);
+}
+
+// matcher.cpp:150-272.  Reuses port_sbp_frame_in: valid[i] = all host-side gates passed, octave[i] = predicted level,
+// occupied0[i] = frame_curr->mappoints_[i] != nullptr; invz / has_obs / uright unused.
+int port_sbp_reloc(const port_sbp_frame_in* in, float dist_threshold, int32_t* assign) {
+  const PortKp* kps = (const PortKp*)in->kps;
+  Grid g;
+  g.build(kps, in->n, in->xmin, in->xmax, in->ymin, in->ymax);
+  std::vector<uint8_t> taken(in->occupied0, in->occupied0 + in->n);
+  for (int i = 0; i < in->n; ++i) assign[i] = -1;
+  std::vector<std::vector<int>> hist(30);
+  const float pdf = 30 / 360.0f;
+  int cnt = 0;
+  std::vector<int> win;
+  for (int i = 0; i < in->m; ++i) {
+    if (!in->valid[i]) continue;
+    const int lp = in->octave[i];
+    const float rs = in->radius * in->scale_factors[lp];
+    g.area(kps, in->u[i], in->v[i], rs, lp - 1, lp + 1, win);
+    if (win.empty()) continue;
+    int bestD = 256, bestI = -1;
+    for (int idx : win) {
+      if (taken[idx]) continue;                                            // :218
+      int d = hamming256(in->mp_desc + (size_t)i * 32, in->desc + (size_t)idx * 32);
+      if (d < bestD) { bestD = d; bestI = idx; }
+    }
+    if (bestD <= dist_threshold) {                                         // :231
+      assign[bestI] = i;
+      taken[bestI] = 1;
+      ++cnt;
+      if (in->check_rot) {
+        float rot = in->angle[i] - kps[bestI].angle;
+        if (rot < 0) rot += 360.0f;
+        int bin = cvp::cv_round(rot * pdf);
+        if (bin == 30) bin = 0;
+        hist[bin].push_back(bestI);
+      }
+    }
+  }
+  if (in->check_rot) {
+    int sizes[30], i1, i2, i3;
+    for (int b = 0; b < 30; ++b) sizes[b] = (int)hist[b].size();
+    three_max(sizes, 30, i1, i2, i3);
+    for (int b = 0; b < 30; ++b)
+      if (b != i1 && b != i2 && b != i3)
+        for (int idx : hist[b]) { assign[idx] = -2; --cnt; }
+  }
+  return cnt;
+}
+
+// matcher.cpp:356-447, including the `matchMapPoints[j]` indexing by window position (:422).
+int port_sbp_sim3(const port_sbp_frame_in* in, int th, int32_t* assign) {
+  const PortKp* kps = (const PortKp*)in->kps;
+  Grid g;
+  g.build(kps, in->n, in->xmin, in->xmax, in->ymin, in->ymax);
+  std::vector<uint8_t> matched(in->occupied0, in->occupied0 + in->n);       // matchMapPoints[i] != nullptr
+  for (int i = 0; i < in->n; ++i) assign[i] = -1;
+  int cnt = 0;
+  std::vector<int> win;
+  for (int i = 0; i < in->m; ++i) {
+    if (!in->valid[i]) continue;
+    const int lp = in->octave[i];
+    const float radius = th * in->scale_factors[lp];
+    area_nolevel(g, kps, in->u[i], in->v[i], radius, win);
+    if (win.empty()) continue;
+    int bestD = 256, bestI = -1;
+    for (int j = 0; j < (int)win.size(); ++j) {
+      const int idx = win[j];
+      if (matched[j]) continue;                                            // sic: [j], not [idx]
+      const int level = kps[idx].octave;
+      if (level < lp - 1 || level > lp) continue;
+      int d = hamming256(in->mp_desc + (size_t)i * 32, in->desc + (size_t)idx * 32);
+      if (d < bestD) { bestD = d; bestI = idx; }
+    }
+    if (bestD <= 50) {                                                     // TH_LOW
+      assign[bestI] = i;
+      matched[bestI] = 1;
+      ++cnt;
+    }
   }
   return cnt;
 }

@@ -72,3 +72,34 @@ def test_projection_empty_inputs(vo, frame_out):
     pts["valid"][:] = 0
     got, cnt = vo.Matcher(0.9).searchByProjection(frame, pts, 15.0)
     assert cnt == 0 and (got == -1).all()
+
+
+@pytest.mark.parametrize("m,rot,th", [(10000, True, 100.0), (4000, False, 64.0), (3, True, 100.0)])
+def test_search_by_projection_reloc(vo, frame_out, m, rot, th):
+    """Matcher::searchByProjection(Frame*, KeyFrame*, ...) (matcher.cpp:150-272): any held feature blocks."""
+    P, kps, desc, sf = frame_out
+    frame, pts = synth.make_projection_case(kps, desc, sf, m, seed=3 * m + 1)
+    frame["occupied0"] = (np.random.default_rng(m).random(len(kps)) < 0.1).astype(np.uint8)
+    want, wcnt = P.sbp_reloc(frame, pts, 15.0, th, rot)
+    got, gcnt = vo.Matcher(0.9).searchByProjectionKeyFrame(frame, pts, 15.0, th, checkRot=rot)
+    assert gcnt == wcnt and np.array_equal(got, want)
+    if m >= 4000:
+        assert wcnt > 100
+        held = np.flatnonzero(frame["occupied0"])
+        assert (want[held] == -1).all()              # features that already hold a map point are never claimed
+
+
+@pytest.mark.parametrize("m,th", [(10000, 10), (2500, 4), (2, 10)])
+def test_search_by_projection_sim3(vo, frame_out, m, th):
+    """Matcher::searchByProjection(KeyFrame*, Sim3&, ...) (matcher.cpp:356-447) with the matchMapPoints[j] quirk."""
+    P, kps, desc, sf = frame_out
+    frame, pts = synth.make_projection_case(kps, desc, sf, m, seed=5 * m + 2)
+    frame["occupied0"] = (np.random.default_rng(m + 1).random(len(kps)) < 0.2).astype(np.uint8)
+    want, wcnt = P.sbp_sim3(frame, pts, th)
+    got, gcnt = vo.Matcher(0.9).searchByProjectionSim3(frame, pts, th)
+    assert gcnt == wcnt and np.array_equal(got, want)
+    if m >= 2500:
+        assert wcnt > 100
+        # the quirk matters: indexing the taken test by feature instead of by position gives a different answer
+        frame2 = dict(frame); frame2["occupied0"] = np.zeros(len(kps), np.uint8)
+        assert not np.array_equal(P.sbp_sim3(frame2, pts, th)[0], want)

@@ -90,6 +90,8 @@ def load_library():
     L.orbx_search_by_projection_frame.argtypes = [vp, vp, f32, f32, i32, i32, i32, vp, vp, i32]
     L.orbx_search_by_projection_local.argtypes = [vp, vp, f32, f32, vp, vp, i32]
     L.orbx_search_by_bow.argtypes = [vp, vp, i32, f32, i32, i32, vp, vp, i32]
+    L.orbx_search_by_projection_reloc.argtypes = [vp, vp, f32, f32, i32, vp, vp, i32]
+    L.orbx_search_by_projection_sim3.argtypes = [vp, vp, i32, vp, vp, i32]
     _lib = L
     return L
 
@@ -324,6 +326,32 @@ class Matcher:
         assign = np.zeros(max(fv.n, 1), np.int32); cnt = C.c_int(0)
         _check(self._lib.orbx_search_by_projection_frame(C.byref(fv), C.byref(s), radius, bf, int(forward), int(backward),
                                                          int(checkRot), _p(assign), C.byref(cnt), self.device))
+        return assign[:fv.n].copy(), cnt.value
+
+    def _frame_points(self, p, keep):
+        def a(x, dt):
+            y = np.ascontiguousarray(x, dt); keep.append(y); return y.ctypes.data
+        s = _SbpFramePoints()
+        s.m = len(p["u"]); s.valid = a(p["valid"], np.uint8); s.u = a(p["u"], np.float32); s.v = a(p["v"], np.float32)
+        s.invz = a(p["invz"], np.float32); s.octave = a(p["octave"], np.int32); s.angle = a(p["angle"], np.float32)
+        s.desc = a(p["desc"], np.uint8); s.has_obs = a(p["has_obs"], np.uint8)
+        return s
+
+    def searchByProjectionKeyFrame(self, frame_curr, keyframe_points, radius, distThreshold, checkRot=True):
+        """Matcher::searchByProjection(Frame*, KeyFrame*, radius, distThreshold, found, checkRot) (matcher.cpp:150-272)."""
+        keep = []
+        fv = self._frame_view(frame_curr, keep); s = self._frame_points(keyframe_points, keep)
+        assign = np.zeros(max(fv.n, 1), np.int32); cnt = C.c_int(0)
+        _check(self._lib.orbx_search_by_projection_reloc(C.byref(fv), C.byref(s), radius, distThreshold, int(checkRot), _p(assign),
+                                                         C.byref(cnt), self.device))
+        return assign[:fv.n].copy(), cnt.value
+
+    def searchByProjectionSim3(self, keyframe, loop_points, th):
+        """Matcher::searchByProjection(KeyFrame*, Sim3&, loopMapPoints, matchMapPoints, th) (matcher.cpp:356-447)."""
+        keep = []
+        fv = self._frame_view(keyframe, keep); s = self._frame_points(loop_points, keep)
+        assign = np.zeros(max(fv.n, 1), np.int32); cnt = C.c_int(0)
+        _check(self._lib.orbx_search_by_projection_sim3(C.byref(fv), C.byref(s), int(th), _p(assign), C.byref(cnt), self.device))
         return assign[:fv.n].copy(), cnt.value
 
     def searchByBoW(self, side_a, side_b, mode=0, checkRot=True, th_low=TH_LOW):

@@ -51,6 +51,13 @@ struct SearchParams {
   float radius;      // frame: radius; local: thRadius
   float bf; int forward, backward, check_rot;
   float ratio;
+  float th;          // accept iff (float)bestDist <= th   (TH_HIGH, distThreshold or TH_LOW depending on the overload)
+  int block_all;     // every accepted claim blocks the feature (overloads that test `mappoints_[idx]` without the obs count)
+  int pos_block;     // the "already matched" test is indexed by the candidate's POSITION in the window list instead of its
+                     // feature index: the reference bug `matchMapPoints[j]` at matcher.cpp:422, reproduced for parity
+  int level_at_select;   // window query has no level filter (KeyFrame::getFeaturesInArea); levels gate at selection (:425-427)
+  int host_gates;    // depth-sign and image-bounds gates were already applied by the caller (folded into valid[])
+  int level_span_lo, level_span_hi;   // non-LOCAL level window = [lvl + lo, lvl + hi] when neither forward nor backward
 };
 
 struct Window { bool ok; float u, v, r, aux; int minL, maxL; };
@@ -68,14 +75,16 @@ __device__ __forceinline__ Window make_window(const FrameDev& F, const PointsDev
     w.r = __fmul_rn(radius, F.scale[lvl]);                               // :296
     w.minL = lvl - 1; w.maxL = lvl;                                      // :297-298
   } else {
-    if (w.aux < 0.0f) return w;                                          // z < 0 (:51)
-    const int xMin = (int)F.xmin, xMax = (int)F.xmax, yMin = (int)F.ymin, yMax = (int)F.ymax;   // :27-30
-    if (w.u < xMin || w.u > xMax) return w;                              // :60-63
-    if (w.v < yMin || w.v > yMax) return w;
+    if (!S.host_gates) {
+      if (w.aux < 0.0f) return w;                                        // z < 0 (:51)
+      const int xMin = (int)F.xmin, xMax = (int)F.xmax, yMin = (int)F.ymin, yMax = (int)F.ymax;   // :27-30
+      if (w.u < xMin || w.u > xMax) return w;                            // :60-63
+      if (w.v < yMin || w.v > yMax) return w;
+    }
     w.r = __fmul_rn(S.radius, F.scale[lvl]);                             // :67
     if (S.forward) { w.minL = lvl; w.maxL = F.nlevels; }                 // :70-75
     else if (S.backward) { w.minL = 0; w.maxL = lvl; }
-    else { w.minL = lvl - 1; w.maxL = lvl + 1; }
+    else { w.minL = lvl + S.level_span_lo; w.maxL = lvl + S.level_span_hi; }
   }
   w.ok = true;
   return w;
@@ -99,7 +108,7 @@ __device__ __forceinline__ bool window_cells(const FrameDev& F, const Window& w,
 template <bool LOCAL>
 __device__ __forceinline__ bool gate(const SearchParams& S, const Window& w, const float4 ft) {
   const int oct = __float_as_int(ft.z);
-  if (oct < w.minL || oct > w.maxL) return false;
+  if (!S.level_at_select && (oct < w.minL || oct > w.maxL)) return false;
   if (!(fabsf(__fsub_rn(ft.x, w.u)) < w.r && fabsf(__fsub_rn(ft.y, w.v)) < w.r)) return false;
   if (ft.w > 0) {
     float err;
@@ -191,7 +200,11 @@ __global__ void __launch_bounds__(256) sbp_walk_kernel(FrameDev F, PointsDev P, 
       if (e < hi) { idx = __ldg(F.ids + e); pass = gate<LOCAL>(S, w, __ldg(F.feat + idx)); }
       const unsigned b = __ballot_sync(0xffffffffu, pass);
       if (pass) {
-        const int dist = hamming256(d0, d1, F.desc + (size_t)idx * 32);
+        int dist = hamming256(d0, d1, F.desc + (size_t)idx * 32);
+        if (S.level_at_select) {               // keeps its position in the list but can never be selected
+          const int oct = __float_as_int(__ldg(F.feat + idx).z);
+          if (oct < w.minL || oct > w.maxL) dist = 511;
+        }
         cand[run + __popc(b & ((1u << lane) - 1))] = (uint32_t)idx | ((uint32_t)dist << 20);
       }
       run += __popc(b);
@@ -207,7 +220,8 @@ __device__ __forceinline__ int select_choice(const FrameDev& F, const SearchPara
   for (int k = b; k < e; ++k) {
     const uint32_t c = cand[k];
     const int idx = (int)(c & 0xFFFFFu), d = (int)(c >> 20);
-    if (blockTime[idx] < i) continue;                                  // matcher.cpp:87 / :314
+    if (blockTime[S.pos_block ? (k - b) : idx] < i) continue;          // matcher.cpp:87 / :314 / :218 / :422
+    if (d == 511) continue;                                            // level gate applied at selection (:425-427)
     if (LOCAL) {
       if (d < bestD) { bestD2 = bestD; bestD = d; bestL2 = bestL; bestL = F.kps[idx].octave; bestI = idx; }   // :327-339
       else if (d < bestD2) { bestL2 = F.kps[idx].octave; bestD2 = d; }
@@ -215,7 +229,7 @@ __device__ __forceinline__ int select_choice(const FrameDev& F, const SearchPara
       if (d < bestD) { bestD = d; bestI = idx; }                       // :101-105
     }
   }
-  if (bestD > TH_HIGH) return -1;                                      // :108 / :342
+  if (!((float)bestD <= S.th)) return -1;                              // :108 / :342 / :233 / :439
   if (LOCAL && bestL == bestL2 && (float)bestD > __fmul_rn(S.ratio, (float)bestD2)) return -1;   // :344
   return bestI;
 }
@@ -238,7 +252,7 @@ __global__ void __launch_bounds__(kResolveThreads) sbp_resolve_kernel(FrameDev F
     const int i = c0 + tid;
     const bool valid = i < m;
     const int b = valid ? offs[i] : 0, e = valid ? b + cnts[i] : 0;
-    const bool obs = valid && P.has_obs[i];
+    const bool obs = valid && (S.block_all || P.has_obs[i]);
     int ch = -1;
     while (true) {
       for (int c = tid; c < n; c += T) blockT[c] = blockF[c];
@@ -475,6 +489,7 @@ int orbx_search_by_projection_frame(const orbx_frame_view* frame, const orbx_sbp
   if (!pts) { set_error("null points"); return ORBX_ERR_ARG; }
   SearchParams S{};
   S.radius = radius; S.bf = bf; S.forward = forward; S.backward = backward; S.check_rot = check_rot; S.ratio = 0.f;
+  S.th = (float)TH_HIGH; S.level_span_lo = -1; S.level_span_hi = 1;
   return run_search<false>(frame, pts->m, pts->valid, pts->u, pts->v, pts->invz, pts->octave, pts->angle, pts->desc, pts->has_obs, S,
                            assign, match_cnt, device);
 }
@@ -483,9 +498,36 @@ int orbx_search_by_projection_local(const orbx_frame_view* frame, const orbx_sbp
                                     int32_t* assign, int* match_cnt, int device) {
   if (!pts) { set_error("null points"); return ORBX_ERR_ARG; }
   SearchParams S{};
-  S.radius = th_radius; S.ratio = ratio;
+  S.radius = th_radius; S.ratio = ratio; S.th = (float)TH_HIGH;
   return run_search<true>(frame, pts->m, pts->valid, pts->u, pts->v, pts->ur, pts->level, pts->view_cos, pts->desc, pts->has_obs, S,
                           assign, match_cnt, device);
+}
+
+
+// Matcher::searchByProjection(Frame*, KeyFrame*, radius, distThreshold, found, checkRot)  (matcher.cpp:150-272).
+// pts->valid folds the host-side gates (:173-200: null/bad/found, z <= 0, image bounds, distance range); pts->octave is
+// mp->predictScale(); any feature that already holds a map point is skipped (:218), every accepted claim blocks.
+int orbx_search_by_projection_reloc(const orbx_frame_view* frame, const orbx_sbp_frame_points* pts, float radius, float dist_threshold,
+                                    int check_rot, int32_t* assign, int* match_cnt, int device) {
+  if (!pts) { set_error("null points"); return ORBX_ERR_ARG; }
+  SearchParams S{};
+  S.radius = radius; S.check_rot = check_rot; S.th = dist_threshold; S.block_all = 1; S.host_gates = 1; S.level_span_lo = -1; S.level_span_hi = 1;
+  return run_search<false>(frame, pts->m, pts->valid, pts->u, pts->v, pts->invz, pts->octave, pts->angle, pts->desc, pts->has_obs, S,
+                           assign, match_cnt, device);
+}
+
+// Matcher::searchByProjection(KeyFrame*, Sim3&, loopMapPoints, matchMapPoints, th)  (matcher.cpp:356-447).
+// The window comes from KeyFrame::getFeaturesInArea (no level filter, keyframe.cpp:268-312); levels [l-1, l] gate at
+// selection (:425-427); accept at TH_LOW (:439); the "already matched" test reads matchMapPoints[j] with the window
+// POSITION j (:422) -- reproduced as is.  frame->occupied0 = matchMapPoints[i] != nullptr on entry.
+int orbx_search_by_projection_sim3(const orbx_frame_view* keyframe, const orbx_sbp_frame_points* pts, int th, int32_t* assign,
+                                   int* match_cnt, int device) {
+  if (!pts) { set_error("null points"); return ORBX_ERR_ARG; }
+  SearchParams S{};
+  S.radius = (float)th; S.check_rot = 0; S.th = 50.0f; S.block_all = 1; S.host_gates = 1; S.pos_block = 1; S.level_at_select = 1;
+  S.level_span_lo = -1; S.level_span_hi = 0;
+  return run_search<false>(keyframe, pts->m, pts->valid, pts->u, pts->v, pts->invz, pts->octave, pts->angle, pts->desc, pts->has_obs, S,
+                           assign, match_cnt, device);
 }
 
 }  // extern "C"
