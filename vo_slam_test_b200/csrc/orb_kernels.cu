@@ -209,7 +209,7 @@ __device__ __forceinline__ void fast_best2(const uint8_t* pa, const uint8_t* pb,
   bestB = max((int)(short)(a >> 16), -(int)(short)(b >> 16));
 }
 
-__global__ void __launch_bounds__(kFastThreads) fast_kernel(const Geom G, const Bufs B, const TmaSet TM) {
+__global__ void __launch_bounds__(kFastThreads) fast_kernel(const __grid_constant__ Geom G, const Bufs B, const TmaSet TM) {
   // Work-efficient layout: (1) tile staged with 16-byte loads, (2) a cheap 16-pixel-ring rejection test over all
   // pixels that pushes the few survivors into a shared-memory queue, (3) the full arc score and the per-cell NMS run
   // densely over that queue only, (4) survivors are ranked by (cell, row, column) to emit them in the reference order.
@@ -465,7 +465,7 @@ __device__ __forceinline__ int quadrant_of(const short4 b, int x, int y) {
   return (x < mx ? 0 : 1) | (y < my ? 0 : 2);     // 0:n1 1:n2 2:n3 3:n4   (:521-531)
 }
 
-__global__ void __launch_bounds__(kOctThreads) octree_kernel(const Geom G, const Bufs B) {
+__global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_constant__ Geom G, const Bufs B) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, T = kOctThreads;
   const int l = blockIdx.x, f = blockIdx.y;
@@ -714,7 +714,7 @@ __device__ __forceinline__ uint32_t blur_h(uint32_t w0, uint32_t w1) {       // 
   return __dp4a(w1, kBlurK1, __dp4a(w0, kBlurK0, 0u));
 }
 
-__global__ void __launch_bounds__(256) blur_kernel(const Geom G, const Bufs B) {
+__global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geom G, const Bufs B) {
   // One CTA = one 64-pixel-wide column strip of one level of one frame; it walks down the strip in 26-row tiles so that
   // the level lookup, pointers and alignment checks are paid once per strip instead of once per tile.
   __shared__ __align__(16) uint8_t tin[kBlurTH + 6][kBlurInW];
@@ -910,7 +910,7 @@ __device__ __forceinline__ int stage_patch(uint8_t* dst, const uint8_t* img, int
   return 0;
 }
 
-__global__ void __launch_bounds__(256) orient_desc_kernel(const Geom G, const Bufs B, orbx_keypoint* __restrict__ kps_out,
+__global__ void __launch_bounds__(256) orient_desc_kernel(const __grid_constant__ Geom G, const Bufs B, orbx_keypoint* __restrict__ kps_out,
                                                           uint8_t* __restrict__ desc_out, int cap,
                                                           int32_t* __restrict__ counts_out, int frame0) {
   __shared__ __align__(16) uint8_t patches[8][kPatchBytes + 8];
