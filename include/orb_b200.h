@@ -229,6 +229,13 @@ typedef struct orbx_bow_side {
 int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b, int mode, float ratio, int th_low, int check_rot,
                        int32_t* match, int* match_cnt, int device);
 
+/* MapPoint::computeDescriptor (mappoint.cpp:118-179) for `npoints` map points at once.
+ * desc: all observed descriptors back to back (32 B each); start[npoints+1]: CSR (observations of point p are rows
+ * start[p] .. start[p+1]-1, in the order the reference's std::map<KeyFrame*,size_t> iteration pushes them, bad key frames
+ * already removed).  best[p] = row (relative to start[p]) whose median distance to the others is smallest, first row
+ * wins ties; -1 for a point without observations (the reference keeps its old descriptor).  Host pointers. */
+int orbx_medoid_descriptors(const uint8_t* desc, const int32_t* start, int npoints, int32_t* best, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -256,6 +256,13 @@ class Port:
         cnt = self.lib.port_sbp_frame(C.byref(s), _ptr(assign))
         return assign[:s.n].copy(), cnt
 
+    def medoid(self, desc, start):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); start = np.ascontiguousarray(start, np.int32)
+        best = np.empty(max(len(start) - 1, 1), np.int32)
+        self.lib.port_medoid.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        self.lib.port_medoid(_ptr(desc), _ptr(start), len(start) - 1, _ptr(best))
+        return best[:len(start) - 1].copy()
+
     def search_by_bow(self, a, b, mode, ratio=0.7, th_low=50, check_rot=True):
         """a, b: dict(desc, angle, valid, node_ids, group_start, feat_idx); mode 0 KF->Frame, 1 KF->KF."""
         keep = []

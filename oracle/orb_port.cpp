@@ -26,6 +26,7 @@
 //   computeThreeMax        matcher.cpp:1258-1304             -> three_max()
 //   searchByProjection(F,KF)     matcher.cpp:150-272         -> port_sbp_reloc()
 //   searchByProjection(KF,Sim3)  matcher.cpp:356-447         -> port_sbp_sim3()
+//   MapPoint::computeDescriptor  mappoint.cpp:118-179        -> port_medoid()
 //   searchByBoW (both)     matcher.cpp:449-559, 561-677      -> port_search_by_bow()
 #include <cmath>
 #include <cstdint>
@@ -800,6 +801,31 @@ int port_sbp_sim3(const port_sbp_frame_in* in, int th, int32_t* assign) {
     }
   }
   return cnt;
+}
+
+
+// mappoint.cpp:118-179 for many map points (CSR of their observed descriptors).
+void port_medoid(const uint8_t* desc, const int32_t* start, int npoints, int32_t* best) {
+  for (int p = 0; p < npoints; ++p) {
+    const int N = start[p + 1] - start[p];
+    if (N <= 0) { best[p] = -1; continue; }
+    const uint8_t* D = desc + (size_t)start[p] * 32;
+    std::vector<std::vector<float>> distances(N, std::vector<float>(N, 0));
+    for (int i = 0; i < N; ++i)
+      for (int j = i + 1; j < N; ++j) {
+        const int dij = hamming256(D + (size_t)i * 32, D + (size_t)j * 32);
+        distances[i][j] = (float)dij;
+        distances[j][i] = (float)dij;
+      }
+    int bestMid = 256, bestIdx = 0;
+    for (int i = 0; i < N; ++i) {
+      std::vector<int> dist(distances[i].begin(), distances[i].end());
+      std::sort(dist.begin(), dist.end());
+      const int mid = dist[int(0.5 * (N - 1))];
+      if (mid < bestMid) { bestMid = mid; bestIdx = i; }
+    }
+    best[p] = bestIdx;
+  }
 }
 
 }  // extern "C"

@@ -13,7 +13,7 @@ Everything computes in hand-written CUDA behind the C ABI of ``include/orb_b200.
 any compute call without the built library or without a CUDA device raises.
 """
 from .api import (KP_DTYPE, Matcher, ORBextractor, OrbError, device_count, grid_build, knn2_device, knn2_merge_device,
-                  knn2_pairs_device, knn2_workspace_bytes, lib, lib_path, load_library)
+                  knn2_pairs_device, knn2_workspace_bytes, lib, lib_path, load_library, medoid_descriptors)
 
 __all__ = ["ORBextractor", "Matcher", "grid_build", "knn2_device", "KP_DTYPE", "OrbError", "device_count", "lib",
-           "lib_path", "load_library"]
+           "lib_path", "load_library", "medoid_descriptors"]

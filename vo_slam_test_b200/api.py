@@ -90,6 +90,7 @@ def load_library():
     L.orbx_search_by_projection_frame.argtypes = [vp, vp, f32, f32, i32, i32, i32, vp, vp, i32]
     L.orbx_search_by_projection_local.argtypes = [vp, vp, f32, f32, vp, vp, i32]
     L.orbx_search_by_bow.argtypes = [vp, vp, i32, f32, i32, i32, vp, vp, i32]
+    L.orbx_medoid_descriptors.argtypes = [vp, vp, i32, vp, i32]
     L.orbx_search_by_projection_reloc.argtypes = [vp, vp, f32, f32, i32, vp, vp, i32]
     L.orbx_search_by_projection_sim3.argtypes = [vp, vp, i32, vp, vp, i32]
     _lib = L
@@ -260,6 +261,16 @@ def knn2_device(d_q, nq, d_t, nt, th, ratio, d_idx, d_d1, d_d2, d_ok, d_ws=0, ws
     _check(load_library().hamm_knn2_device(C.c_void_p(d_q), nq, C.c_void_p(d_t), nt, th, ratio, C.c_void_p(d_idx),
                                            C.c_void_p(d_d1), C.c_void_p(d_d2), C.c_void_p(d_ok), C.c_void_p(d_ws),
                                            ws_bytes, C.c_void_p(stream)))
+
+
+def medoid_descriptors(desc, start, device=0):
+    """MapPoint::computeDescriptor (mappoint.cpp:118-179) for many map points: desc (total,32) uint8, start CSR (P+1)."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    start = np.ascontiguousarray(start, np.int32)
+    P = len(start) - 1
+    best = np.zeros(max(P, 1), np.int32)
+    _check(load_library().orbx_medoid_descriptors(_p(desc), _p(start), P, _p(best), device))
+    return best[:P].copy()
 
 
 def grid_build(kps, bounds, device=0):
