@@ -204,6 +204,20 @@ int orbx_search_by_projection_reloc(const orbx_frame_view* frame, const orbx_sbp
 int orbx_search_by_projection_sim3(const orbx_frame_view* keyframe, const orbx_sbp_frame_points* pts, int th, int32_t* assign,
                                    int* match_cnt, int device);
 
+/* Independent windowed best match per projected point -- the data-parallel core shared by Matcher::searchBySim3
+ * (matcher.cpp:717-775,777-836), fuseMapPoints (:1026-1100) and fuseByPose (:1157-1224): window from
+ * KeyFrame::getFeaturesInArea (keyframe.cpp:268-312), levels [level_predict-1, level_predict], strict '<' argmin in
+ * window order.  best_idx[i] (i < pts->m) = keyframe feature, or -1 when the best distance exceeds dist_threshold.
+ * chi2_gate != 0 adds fuseMapPoints' reprojection test (:1073-1095); pts->invz then carries ur = u - bf/z and the
+ * keyframe's uright uses the reference's `>= 0` convention.  The pointer-graph surgery that follows in the fuse
+ * functions (replaceMapPoint / addObservation) stays on the host and replays best_idx in order. */
+int orbx_window_argmin(const orbx_frame_view* keyframe, const orbx_sbp_frame_points* pts, float th_radius, float dist_threshold,
+                       int chi2_gate, int32_t* best_idx, int device);
+/* Matcher::searchBySim3 (matcher.cpp:679-865): both directed searches (TH_HIGH) and the mutual-consistency check.
+ * pts12 / pts21 hold one projected point per feature of kf1 / kf2 (valid = 0 for features without a usable map point). */
+int orbx_search_by_sim3(const orbx_frame_view* kf1, const orbx_sbp_frame_points* pts12, const orbx_frame_view* kf2,
+                        const orbx_sbp_frame_points* pts21, float th, int32_t* match12, int* found, int device);
+
 /* ---------------------------------------------------------------------------------------------------
  * BoW-guided matching
  *   mode 0: Matcher::searchByBoW(KeyFrame*, Frame*, matches, checkRot)       (matcher.cpp:449-559)

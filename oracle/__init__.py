@@ -307,6 +307,24 @@ class Port:
         cnt = self.lib.port_sbp_sim3(C.byref(s), int(th), _ptr(assign))
         return assign[:s.n].copy(), cnt
 
+    def window_argmin(self, keyframe, pts, th_radius, dist_threshold, chi2=False):
+        keep = []
+        s = self._sbp_frame_struct(keyframe, pts, 0.0, False, keep)
+        best = np.empty(max(s.m, 1), np.int32)
+        self.lib.port_window_argmin.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]
+        self.lib.port_window_argmin(C.byref(s), th_radius, dist_threshold, int(chi2), _ptr(best))
+        return best[:s.m].copy()
+
+    def search_by_sim3(self, kf1, pts12, kf2, pts21, th):
+        keep = []
+        s12 = self._sbp_frame_struct(kf2, pts12, 0.0, False, keep)
+        s21 = self._sbp_frame_struct(kf1, pts21, 0.0, False, keep)
+        match = np.empty(max(s12.m, 1), np.int32)
+        self.lib.port_search_by_sim3.restype = C.c_int
+        self.lib.port_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        found = self.lib.port_search_by_sim3(C.byref(s12), C.byref(s21), th, _ptr(match))
+        return match[:s12.m].copy(), found
+
     def sbp_local(self, frame, pts, th_radius, ratio):
         """pts: dict(valid,u,v,ur,level,view_cos,desc,has_obs)."""
         keep = []

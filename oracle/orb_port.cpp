@@ -26,6 +26,7 @@
 //   computeThreeMax        matcher.cpp:1258-1304             -> three_max()
 //   searchByProjection(F,KF)     matcher.cpp:150-272         -> port_sbp_reloc()
 //   searchByProjection(KF,Sim3)  matcher.cpp:356-447         -> port_sbp_sim3()
+//   searchBySim3 / fuse cores    matcher.cpp:679-865,1012-1238 -> port_window_argmin(), port_search_by_sim3()
 //   MapPoint::computeDescriptor  mappoint.cpp:118-179        -> port_medoid()
 //   searchByBoW (both)     matcher.cpp:449-559, 561-677      -> port_search_by_bow()
 #include <cmath>
@@ -826,6 +827,60 @@ void port_medoid(const uint8_t* desc, const int32_t* start, int npoints, int32_t
     }
     best[p] = bestIdx;
   }
+}
+
+
+// Common search core of searchBySim3 (matcher.cpp:745-775 / :806-836), fuseMapPoints (:1057-1100, chi2 != 0) and
+// fuseByPose (:1190-1224).  in->invz carries ur when chi2 != 0; in->uright uses the `>= 0` convention of :1077.
+void port_window_argmin(const port_sbp_frame_in* in, float th_radius, float dist_threshold, int chi2, int32_t* best) {
+  const PortKp* kps = (const PortKp*)in->kps;
+  Grid g;
+  g.build(kps, in->n, in->xmin, in->xmax, in->ymin, in->ymax);
+  std::vector<int> win;
+  for (int i = 0; i < in->m; ++i) {
+    best[i] = -1;
+    if (!in->valid[i]) continue;
+    const int lp = in->octave[i];
+    const float u = in->u[i], v = in->v[i];
+    const float radius = th_radius * in->scale_factors[lp];
+    area_nolevel(g, kps, u, v, radius, win);
+    if (win.empty()) continue;
+    int bestD = 256, bestI = -1;
+    for (int idx : win) {
+      const PortKp& kp = kps[idx];
+      if (kp.octave < lp - 1 || kp.octave > lp) continue;
+      if (chi2) {
+        const float ex = u - kp.x, ey = v - kp.y;
+        const float invSigma = 1.0f / in->scale_factors[kp.octave];
+        if (in->uright[idx] >= 0) {
+          const float er = in->invz[i] - in->uright[idx];
+          const float e2 = ex * ex + ey * ey + er * er;
+          if (e2 * invSigma * invSigma > 7.815f) continue;
+        } else {
+          const float e2 = ex * ex + ey * ey;
+          if (e2 * invSigma * invSigma > 5.991f) continue;
+        }
+      }
+      const int d = hamming256(in->mp_desc + (size_t)i * 32, in->desc + (size_t)idx * 32);
+      if (d < bestD) { bestD = d; bestI = idx; }
+    }
+    if (bestD <= dist_threshold) best[i] = bestI;
+  }
+}
+
+// matcher.cpp:679-865
+int port_search_by_sim3(const port_sbp_frame_in* in12 /* frame = kf2, points = kf1's */, const port_sbp_frame_in* in21, float th,
+                        int32_t* match12) {
+  std::vector<int32_t> m1(std::max(in12->m, 1)), m2(std::max(in21->m, 1));
+  port_window_argmin(in12, th, 100.f, 0, m1.data());
+  port_window_argmin(in21, th, 100.f, 0, m2.data());
+  int found = 0;
+  for (int i = 0; i < in12->m; ++i) {
+    match12[i] = -1;
+    const int idx2 = m1[i];
+    if (idx2 >= 0 && m2[idx2] == i) { match12[i] = idx2; ++found; }
+  }
+  return found;
 }
 
 }  // extern "C"

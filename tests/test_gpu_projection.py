@@ -103,3 +103,44 @@ def test_search_by_projection_sim3(vo, frame_out, m, th):
         # the quirk matters: indexing the taken test by feature instead of by position gives a different answer
         frame2 = dict(frame); frame2["occupied0"] = np.zeros(len(kps), np.uint8)
         assert not np.array_equal(P.sbp_sim3(frame2, pts, th)[0], want)
+
+
+@pytest.mark.parametrize("chi2,stereo,th", [(False, False, 50.0), (True, False, 50.0), (True, True, 50.0), (False, True, 100.0)])
+def test_window_argmin_fuse_cores(vo, frame_out, chi2, stereo, th):
+    """fuseByPose (:1157-1224) / fuseMapPoints with its chi-square gate (:1073-1095) / searchBySim3 directed search."""
+    P, kps, desc, sf = frame_out
+    frame, pts = synth.make_projection_case(kps, desc, sf, 6000, seed=77 + int(chi2) + 2 * int(stereo), stereo=stereo)
+    if stereo:
+        frame["uright"][::5] = -1.0                          # mixed stereo / mono features (>= 0 convention)
+        frame["uright"][1::7] = 0.0
+    pts["invz"] = (pts["u"] - np.random.default_rng(1).uniform(0, 30, len(pts["u"]))).astype(np.float32)   # carries ur
+    want = P.window_argmin(frame, pts, 3.0, th, chi2)
+    got = vo.Matcher(0.9).windowArgmin(frame, pts, 3.0, th, chi2)
+    assert np.array_equal(got, want)
+    assert (want >= 0).sum() > 200
+    if chi2:
+        loose = P.window_argmin(frame, pts, 3.0, th, False)
+        assert (loose >= 0).sum() > (want >= 0).sum()       # the gate really rejects some candidates
+
+
+def test_search_by_sim3(vo, frame_out):
+    """Matcher::searchBySim3 (matcher.cpp:679-865) between two frames of the panning sequence."""
+    P, kps1, desc1, sf = frame_out
+    seq = synth.make_sequence(2, seed=9)
+    kps1, desc1 = P.extract(seq[0]); kps2, desc2 = P.extract(seq[1])
+    rng = np.random.default_rng(4)
+    def view(k, d):
+        return dict(kps=k, desc=d, bounds=(0.0, 640.0, 0.0, 480.0), scale_factors=sf, uright=np.full(len(k), -1, np.float32),
+                    occupied0=np.zeros(len(k), np.uint8))
+    def proj(k, d, shift):
+        n = len(k)
+        return dict(valid=(rng.random(n) > 0.15).astype(np.uint8), u=(k["x"] + shift + rng.normal(0, 1.5, n)).astype(np.float32),
+                    v=(k["y"] + rng.normal(0, 1.5, n)).astype(np.float32), invz=np.zeros(n, np.float32),
+                    octave=np.clip(k["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32), angle=k["angle"], desc=d,
+                    has_obs=np.zeros(n, np.uint8))
+    kf1, kf2 = view(kps1, desc1), view(kps2, desc2)
+    p12, p21 = proj(kps1, desc1, -2.0), proj(kps2, desc2, 2.0)      # the sequence pans 2 px per frame
+    want, wf = P.search_by_sim3(kf1, p12, kf2, p21, 7.5)
+    got, gf = vo.Matcher(0.9).searchBySim3(kf1, p12, kf2, p21, 7.5)
+    assert gf == wf and np.array_equal(got, want)
+    assert wf > 100

@@ -90,6 +90,8 @@ def load_library():
     L.orbx_search_by_projection_frame.argtypes = [vp, vp, f32, f32, i32, i32, i32, vp, vp, i32]
     L.orbx_search_by_projection_local.argtypes = [vp, vp, f32, f32, vp, vp, i32]
     L.orbx_search_by_bow.argtypes = [vp, vp, i32, f32, i32, i32, vp, vp, i32]
+    L.orbx_window_argmin.argtypes = [vp, vp, f32, f32, i32, vp, i32]
+    L.orbx_search_by_sim3.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32]
     L.orbx_medoid_descriptors.argtypes = [vp, vp, i32, vp, i32]
     L.orbx_search_by_projection_reloc.argtypes = [vp, vp, f32, f32, i32, vp, vp, i32]
     L.orbx_search_by_projection_sim3.argtypes = [vp, vp, i32, vp, vp, i32]
@@ -364,6 +366,25 @@ class Matcher:
         assign = np.zeros(max(fv.n, 1), np.int32); cnt = C.c_int(0)
         _check(self._lib.orbx_search_by_projection_sim3(C.byref(fv), C.byref(s), int(th), _p(assign), C.byref(cnt), self.device))
         return assign[:fv.n].copy(), cnt.value
+
+    def windowArgmin(self, keyframe, points, thRadius, distThreshold, chi2=False):
+        """Search core of searchBySim3 / fuseMapPoints (chi2=True) / fuseByPose: best keyframe feature per projected point
+        (levels [l-1, l], strict '<' in window order), -1 when the best distance exceeds distThreshold."""
+        keep = []
+        fv = self._frame_view(keyframe, keep); s = self._frame_points(points, keep)
+        best = np.zeros(max(s.m, 1), np.int32)
+        _check(self._lib.orbx_window_argmin(C.byref(fv), C.byref(s), thRadius, distThreshold, int(chi2), _p(best), self.device))
+        return best[:s.m].copy()
+
+    def searchBySim3(self, kf1, pts12, kf2, pts21, th):
+        """Matcher::searchBySim3 (matcher.cpp:679-865): (match12, found)."""
+        keep = []
+        v1 = self._frame_view(kf1, keep); v2 = self._frame_view(kf2, keep)
+        s12 = self._frame_points(pts12, keep); s21 = self._frame_points(pts21, keep)
+        match = np.zeros(max(s12.m, 1), np.int32); found = C.c_int(0)
+        _check(self._lib.orbx_search_by_sim3(C.byref(v1), C.byref(s12), C.byref(v2), C.byref(s21), th, _p(match), C.byref(found),
+                                             self.device))
+        return match[:s12.m].copy(), found.value
 
     def searchByBoW(self, side_a, side_b, mode=0, checkRot=True, th_low=TH_LOW):
         """Matcher::searchByBoW: mode 0 = (KeyFrame*, Frame*) (matcher.cpp:449-559), mode 1 = (KeyFrame*, KeyFrame*)

@@ -56,6 +56,8 @@ struct SearchParams {
   int pos_block;     // the "already matched" test is indexed by the candidate's POSITION in the window list instead of its
                      // feature index: the reference bug `matchMapPoints[j]` at matcher.cpp:422, reproduced for parity
   int level_at_select;   // window query has no level filter (KeyFrame::getFeaturesInArea); levels gate at selection (:425-427)
+  int no_block;      // points are independent (no claimed-feature test at all): searchBySim3 / fuse overloads
+  int chi2;          // fuseMapPoints' reprojection gate (matcher.cpp:1077-1095); per-point aux carries ur = u - bf/z
   int host_gates;    // depth-sign and image-bounds gates were already applied by the caller (folded into valid[])
   int level_span_lo, level_span_hi;   // non-LOCAL level window = [lvl + lo, lvl + hi] when neither forward nor backward
 };
@@ -106,11 +108,23 @@ __device__ __forceinline__ bool window_cells(const FrameDev& F, const Window& w,
 
 // level / distance / stereo gates of one candidate (frame.cpp:234-241, matcher.cpp:90-96 / :317-322)
 template <bool LOCAL>
-__device__ __forceinline__ bool gate(const SearchParams& S, const Window& w, const float4 ft) {
+__device__ __forceinline__ bool gate(const FrameDev& F, const SearchParams& S, const Window& w, const float4 ft) {
   const int oct = __float_as_int(ft.z);
   if (!S.level_at_select && (oct < w.minL || oct > w.maxL)) return false;
   if (!(fabsf(__fsub_rn(ft.x, w.u)) < w.r && fabsf(__fsub_rn(ft.y, w.v)) < w.r)) return false;
-  if (ft.w > 0) {
+  if (S.chi2) {                                                          // matcher.cpp:1073-1095
+    const float ex = __fsub_rn(w.u, ft.x), ey = __fsub_rn(w.v, ft.y);
+    const float invSigma = __fdiv_rn(1.0f, F.scale[oct]);
+    float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+    float lim = 5.991f;
+    if (ft.w >= 0) {
+      const float er = __fsub_rn(w.aux, ft.w);
+      e2 = __fadd_rn(e2, __fmul_rn(er, er));
+      lim = 7.815f;
+    }
+    return !(__fmul_rn(__fmul_rn(e2, invSigma), invSigma) > lim);
+  }
+  if (ft.w > 0 && (LOCAL || !S.host_gates)) {      // stereo consistency exists only in the two tracking overloads
     float err;
     if (LOCAL) err = fabsf(__fsub_rn(w.aux, ft.w));
     else err = fabsf(__fsub_rn(__fsub_rn(w.u, __fmul_rn(S.bf, w.aux)), ft.w));
@@ -176,7 +190,7 @@ __global__ void __launch_bounds__(256) sbp_walk_kernel(FrameDev F, PointsDev P, 
       const int lo = __ldg(F.cellStart + ix * GR + y0), hi = __ldg(F.cellStart + ix * GR + y1 + 1);
       for (int e = lo + lane; e < ((hi - lo + 31) & ~31) + lo; e += 32) {
         bool pass = false;
-        if (e < hi) pass = gate<LOCAL>(S, w, __ldg(F.feat + __ldg(F.ids + e)));
+        if (e < hi) pass = gate<LOCAL>(F, S, w, __ldg(F.feat + __ldg(F.ids + e)));
         cnt += __popc(__ballot_sync(0xffffffffu, pass));
       }
     }
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(256) sbp_walk_kernel(FrameDev F, PointsDev P, 
     for (int e = lo + lane; e < ((hi - lo + 31) & ~31) + lo; e += 32) {
       bool pass = false;
       int idx = 0;
-      if (e < hi) { idx = __ldg(F.ids + e); pass = gate<LOCAL>(S, w, __ldg(F.feat + idx)); }
+      if (e < hi) { idx = __ldg(F.ids + e); pass = gate<LOCAL>(F, S, w, __ldg(F.feat + idx)); }
       const unsigned b = __ballot_sync(0xffffffffu, pass);
       if (pass) {
         int dist = hamming256(d0, d1, F.desc + (size_t)idx * 32);
@@ -245,14 +259,14 @@ __global__ void __launch_bounds__(kResolveThreads) sbp_resolve_kernel(FrameDev F
   const int tid = threadIdx.x, T = blockDim.x, m = P.m, n = F.n;
   int* blockF = (n <= smemN) ? sblock : gBlockF;
   int* blockT = (n <= smemN) ? sblock + smemN : gBlockT;
-  for (int c = tid; c < n; c += T) blockF[c] = F.occupied0[c] ? -1 : INT_MAX;
+  for (int c = tid; c < n; c += T) blockF[c] = (!S.no_block && F.occupied0[c]) ? -1 : INT_MAX;
   __syncthreads();
   int rounds = 0;
   for (int c0 = 0; c0 < m; c0 += T) {
     const int i = c0 + tid;
     const bool valid = i < m;
     const int b = valid ? offs[i] : 0, e = valid ? b + cnts[i] : 0;
-    const bool obs = valid && (S.block_all || P.has_obs[i]);
+    const bool obs = valid && !S.no_block && (S.block_all || P.has_obs[i]);
     int ch = -1;
     while (true) {
       for (int c = tid; c < n; c += T) blockT[c] = blockF[c];
@@ -378,7 +392,7 @@ static int check_frame(const orbx_frame_view* f) {
 template <bool LOCAL>
 static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid, const float* u, const float* v, const float* aux,
                       const int32_t* level, const float* angle_or_cos, const uint8_t* desc, const uint8_t* has_obs,
-                      const SearchParams& S, int32_t* assign, int* match_cnt, int device) {
+                      const SearchParams& S, int32_t* assign, int* match_cnt, int device, int32_t* choice_out = nullptr) {
   if (check_frame(frame)) return ORBX_ERR_ARG;
   if (!assign || !match_cnt || m < 0 || (m > 0 && (!valid || !u || !v || !aux || !level || !angle_or_cos || !desc || !has_obs))) {
     set_error("bad argument");
@@ -387,6 +401,7 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
   const int n = frame->n;
   if (m == 0 || n == 0) {
     for (int i = 0; i < n; ++i) assign[i] = -1;
+    if (choice_out) for (int i = 0; i < m; ++i) choice_out[i] = -1;
     *match_cnt = 0;
     return ORBX_OK;
   }
@@ -450,6 +465,7 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
     int res[4] = {0, 0, 0, 0};
     ORBX_CUDA(cudaMemcpyAsync(res, d_misc, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
     ORBX_CUDA(cudaMemcpyAsync(assign, db + o_assign, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (choice_out) ORBX_CUDA(cudaMemcpyAsync(choice_out, db + o_choice, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
     ORBX_CUDA(cudaStreamSynchronize(st));
     ORBX_CUDA(cudaGetLastError());
     if (!res[3]) { *match_cnt = res[1]; return ORBX_OK; }
@@ -528,6 +544,44 @@ int orbx_search_by_projection_sim3(const orbx_frame_view* keyframe, const orbx_s
   S.level_span_lo = -1; S.level_span_hi = 0;
   return run_search<false>(keyframe, pts->m, pts->valid, pts->u, pts->v, pts->invz, pts->octave, pts->angle, pts->desc, pts->has_obs, S,
                            assign, match_cnt, device);
+}
+
+
+// Independent windowed best match per point: the common core of searchBySim3 (matcher.cpp:717-775, 777-836),
+// fuseMapPoints (:1026-1100) and fuseByPose (:1157-1224): window from KeyFrame::getFeaturesInArea, levels
+// [level_predict-1, level_predict], strict '<' argmin in window order, accepted iff bestDist <= dist_threshold.
+// chi2_gate != 0 adds fuseMapPoints' reprojection test (pts->invz then carries ur = u - bf/z).  Points do not interact.
+int orbx_window_argmin(const orbx_frame_view* keyframe, const orbx_sbp_frame_points* pts, float th_radius, float dist_threshold,
+                       int chi2_gate, int32_t* best_idx, int device) {
+  if (!pts || !best_idx) { set_error("null argument"); return ORBX_ERR_ARG; }
+  SearchParams S{};
+  S.radius = th_radius; S.th = dist_threshold; S.no_block = 1; S.host_gates = 1; S.chi2 = chi2_gate; S.level_span_lo = -1; S.level_span_hi = 0;
+  std::vector<int32_t> assign(std::max(keyframe ? keyframe->n : 0, 1));
+  int cnt = 0;
+  return run_search<false>(keyframe, pts->m, pts->valid, pts->u, pts->v, pts->invz, pts->octave, pts->angle, pts->desc, pts->has_obs, S,
+                           assign.data(), &cnt, device, best_idx);
+}
+
+// Matcher::searchBySim3 (matcher.cpp:679-865): both directed searches + the mutual-consistency check (:848-861).
+// pts12: kf1's map points projected into kf2 (m = kf1 features); pts21: kf2's projected into kf1.  match12[i] = matched
+// kf2 feature of kf1 feature i, or -1.
+int orbx_search_by_sim3(const orbx_frame_view* kf1, const orbx_sbp_frame_points* pts12, const orbx_frame_view* kf2,
+                        const orbx_sbp_frame_points* pts21, float th, int32_t* match12, int* found, int device) {
+  if (!kf1 || !kf2 || !pts12 || !pts21 || !match12 || !found) { set_error("null argument"); return ORBX_ERR_ARG; }
+  if (pts12->m != kf1->n || pts21->m != kf2->n) { set_error("one projected point per key-frame feature expected"); return ORBX_ERR_ARG; }
+  std::vector<int32_t> m1(std::max(pts12->m, 1)), m2(std::max(pts21->m, 1));
+  int rc = orbx_window_argmin(kf2, pts12, th, (float)TH_HIGH, 0, m1.data(), device);
+  if (rc) return rc;
+  rc = orbx_window_argmin(kf1, pts21, th, (float)TH_HIGH, 0, m2.data(), device);
+  if (rc) return rc;
+  int f = 0;
+  for (int i = 0; i < pts12->m; ++i) {
+    const int idx2 = m1[i];
+    match12[i] = -1;
+    if (idx2 >= 0 && m2[idx2] == i) { match12[i] = idx2; ++f; }
+  }
+  *found = f;
+  return ORBX_OK;
 }
 
 }  // extern "C"
