@@ -243,6 +243,20 @@ typedef struct orbx_bow_side {
 int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b, int mode, float ratio, int th_low, int check_rot,
                        int32_t* match, int* match_cnt, int device);
 
+/* Matcher::searchForTriangulation(KeyFrame*, KeyFrame*, matchIdxs, F12, checkRot)   (matcher.cpp:867-1010; rank 4).
+ * side.valid[i] = the feature has NO map point (:902, :921).  F12: row-major 3x3 doubles; (ex, ey): epipole of camera 1 in
+ * image 2 (:886-890); scale_factors2: keyframe2->scaleFactors_.  match[i] (i < a->side.n) = matched kf2 feature, -1 none,
+ * -2 cleared by the rotation check.  The epipolar test (:1306-1324) is evaluated in double without FMA, left to right. */
+typedef struct orbx_tri_side {
+  orbx_bow_side side;
+  const orbx_keypoint* kps;    /* unKeypoints_ */
+  const float* uright;         /* uRight_ (>= 0: stereo) */
+} orbx_tri_side;
+
+int orbx_search_for_triangulation(const orbx_tri_side* a, const orbx_tri_side* b, const double* F12, float ex, float ey,
+                                  const float* scale_factors2, int nlevels, int th_low, int check_rot, int32_t* match,
+                                  int* match_cnt, int device);
+
 /* MapPoint::computeDescriptor (mappoint.cpp:118-179) for `npoints` map points at once.
  * desc: all observed descriptors back to back (32 B each); start[npoints+1]: CSR (observations of point p are rows
  * start[p] .. start[p+1]-1, in the order the reference's std::map<KeyFrame*,size_t> iteration pushes them, bad key frames

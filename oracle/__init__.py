@@ -76,6 +76,10 @@ def _bow_side(side, keep, struct=_BowSide):
     return s
 
 
+class _TriSide(C.Structure):
+    _fields_ = [("side", _BowSide), ("kps", C.c_void_p), ("uright", C.c_void_p)]
+
+
 class Port:
     """ctypes view of oracle/liborbport.so (this repo's CPU restatement)."""
 
@@ -255,6 +259,24 @@ class Port:
         self.lib.port_sbp_frame.restype = C.c_int
         cnt = self.lib.port_sbp_frame(C.byref(s), _ptr(assign))
         return assign[:s.n].copy(), cnt
+
+    def search_for_triangulation(self, a, b, F12, epipole, scale2, th_low=50, check_rot=True):
+        """a, b: BoW side dicts + 'kps' (KP_DTYPE) + 'uright'."""
+        keep = []
+        def tri(d):
+            t = _TriSide(); t.side = _bow_side(d, keep)
+            k = np.ascontiguousarray(d["kps"], KP_DTYPE); u = np.ascontiguousarray(d["uright"], np.float32); keep.extend([k, u])
+            t.kps = k.ctypes.data; t.uright = u.ctypes.data
+            return t
+        ta, tb = tri(a), tri(b)
+        F = np.ascontiguousarray(F12, np.float64).reshape(9); sc = np.ascontiguousarray(scale2, np.float32)
+        match = np.empty(max(ta.side.n, 1), np.int32)
+        self.lib.port_search_for_triangulation.restype = C.c_int
+        self.lib.port_search_for_triangulation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
+                                                           C.c_int, C.c_int, C.c_void_p]
+        cnt = self.lib.port_search_for_triangulation(C.byref(ta), C.byref(tb), _ptr(F), epipole[0], epipole[1], _ptr(sc), th_low,
+                                                     int(check_rot), _ptr(match))
+        return match[:ta.side.n].copy(), cnt
 
     def medoid(self, desc, start):
         desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); start = np.ascontiguousarray(start, np.int32)

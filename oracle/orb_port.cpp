@@ -27,6 +27,7 @@
 //   searchByProjection(F,KF)     matcher.cpp:150-272         -> port_sbp_reloc()
 //   searchByProjection(KF,Sim3)  matcher.cpp:356-447         -> port_sbp_sim3()
 //   searchBySim3 / fuse cores    matcher.cpp:679-865,1012-1238 -> port_window_argmin(), port_search_by_sim3()
+//   searchForTriangulation       matcher.cpp:867-1010,1306-1324 -> port_search_for_triangulation()
 //   MapPoint::computeDescriptor  mappoint.cpp:118-179        -> port_medoid()
 //   searchByBoW (both)     matcher.cpp:449-559, 561-677      -> port_search_by_bow()
 #include <cmath>
@@ -881,6 +882,83 @@ int port_search_by_sim3(const port_sbp_frame_in* in12 /* frame = kf2, points = k
     if (idx2 >= 0 && m2[idx2] == i) { match12[i] = idx2; ++found; }
   }
   return found;
+}
+
+
+struct port_tri_side { port_bow_side side; const void* kps; const float* uright; };
+
+// matcher.cpp:1306-1324 (Eigen 3-term products evaluated left to right in double, then the two casts to float)
+static bool epipolar_ok(const double* F, const PortKp& k1, const PortKp& k2, const float* scale2) {
+  const double p1[3] = {(double)k1.x, (double)k1.y, 1.0};
+  double l[3];
+  for (int j = 0; j < 3; ++j) l[j] = p1[0] * F[j] + p1[1] * F[3 + j] + p1[2] * F[6 + j];
+  const float numerator = (float)(l[0] * (double)k2.x + l[1] * (double)k2.y + l[2] * 1.0);
+  const float denominator = (float)(l[0] * l[0] + l[1] * l[1]);
+  if (denominator == 0) return false;
+  const float d_square = numerator * numerator / denominator;
+  const float sigma = scale2[k2.octave];
+  return d_square < 3.84f * sigma * sigma;
+}
+
+// matcher.cpp:867-1010
+int port_search_for_triangulation(const port_tri_side* a, const port_tri_side* b, const double* F12, float ex, float ey,
+                                  const float* scale2, int th_low, int check_rot, int32_t* match) {
+  const PortKp* k1s = (const PortKp*)a->kps;
+  const PortKp* k2s = (const PortKp*)b->kps;
+  for (int i = 0; i < a->side.n; ++i) match[i] = -1;
+  std::vector<uint8_t> matched2(b->side.n, 0);
+  std::vector<std::vector<int>> hist(30);
+  const float pdf = 30 / 360.0f;
+  int cnt = 0, ga = 0, gb = 0;
+  while (ga < a->side.ngroups && gb < b->side.ngroups) {
+    if (a->side.node_ids[ga] == b->side.node_ids[gb]) {
+      for (int ia = a->side.group_start[ga]; ia < a->side.group_start[ga + 1]; ++ia) {
+        const int idx1 = a->side.feat_idx[ia];
+        if (!a->side.valid[idx1]) continue;                      // `if (mpk) continue;`
+        const bool stereo1 = a->uright[idx1] >= 0;
+        int bestDist = th_low, bestIdx2 = -1;
+        for (int ib = b->side.group_start[gb]; ib < b->side.group_start[gb + 1]; ++ib) {
+          const int idx2 = b->side.feat_idx[ib];
+          if (matched2[idx2] || !b->side.valid[idx2]) continue;
+          const bool stereo2 = b->uright[idx2] >= 0;
+          const int dist = hamming256(a->side.desc + (size_t)idx1 * 32, b->side.desc + (size_t)idx2 * 32);
+          if (dist > th_low || dist > bestDist) continue;
+          const PortKp& kpt2 = k2s[idx2];
+          if (!stereo1 && !stereo2) {
+            const float distex = ex - kpt2.x, distey = ey - kpt2.y;
+            if (distex * distex + distey * distey < 100 * scale2[kpt2.octave]) continue;
+          }
+          if (epipolar_ok(F12, k1s[idx1], kpt2, scale2)) { bestDist = dist; bestIdx2 = idx2; }
+        }
+        if (bestIdx2 >= 0) {
+          match[idx1] = bestIdx2;
+          matched2[bestIdx2] = 1;
+          if (check_rot) {
+            float rot = k1s[idx1].angle - k2s[bestIdx2].angle;
+            if (rot < 0) rot += 360.0f;
+            int bin = (int)roundf(rot * pdf);
+            if (bin == 30) bin = 0;
+            hist[bin].push_back(idx1);
+          }
+          ++cnt;
+        }
+      }
+      ++ga; ++gb;
+    } else if (a->side.node_ids[ga] < b->side.node_ids[gb]) {
+      while (ga < a->side.ngroups && a->side.node_ids[ga] < b->side.node_ids[gb]) ++ga;
+    } else {
+      while (gb < b->side.ngroups && b->side.node_ids[gb] < a->side.node_ids[ga]) ++gb;
+    }
+  }
+  if (check_rot) {
+    int sizes[30], i1, i2, i3;
+    for (int k = 0; k < 30; ++k) sizes[k] = (int)hist[k].size();
+    three_max(sizes, 30, i1, i2, i3);
+    for (int k = 0; k < 30; ++k)
+      if (k != i1 && k != i2 && k != i3)
+        for (int idx : hist[k]) { match[idx] = -2; --cnt; }
+  }
+  return cnt;
 }
 
 }  // extern "C"

@@ -119,3 +119,27 @@ def test_search_by_bow_empty():
     assert c == 0 and (m == -1).all() and len(m) == 20
     m, c = vo.Matcher(0.7).searchByBoW(A, E, mode=1)
     assert c == 0 and (m == -1).all() and len(m) == 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rot,stereo", [(True, False), (False, True), (True, True)])
+def test_search_for_triangulation_gpu(rot, stereo):
+    """Matcher::searchForTriangulation (matcher.cpp:867-1010) on two frames of the panning sequence; the fundamental
+    matrix of a pure x-translation makes the epipolar test select same-row pairs."""
+    import vo_slam_test_b200 as vo
+    P = oracle.Port()
+    seq = synth.make_sequence(2, seed=31)
+    k1, d1 = P.extract(seq[0]); k2, d2 = P.extract(seq[1])
+    sf = P.tables()[0]
+    rng = np.random.default_rng(8)
+    def side(k, d, seed):
+        s = synth.make_bow_side(d, k["angle"], (rng.random(len(k)) > 0.3).astype(np.uint8), 6, seed)   # valid = no map point yet
+        s["kps"] = k
+        s["uright"] = np.where(rng.random(len(k)) < 0.5, k["x"] - 10.0, -1.0).astype(np.float32) if stereo else np.full(len(k), -1.0, np.float32)
+        return s
+    A, B = side(k1, d1, 1), side(k2, d2, 2)
+    F12 = np.array([[0, 0, 0], [0, 0, -1.0], [0, 1.0, 0]])          # p1^T F p2 = y2 - y1  (epipolar lines are image rows)
+    want, wc = P.search_for_triangulation(A, B, F12, (600.0, 240.0), sf, 50, rot)
+    got, gc = vo.Matcher(0.6).searchForTriangulation(A, B, F12, (600.0, 240.0), sf, checkRot=rot)
+    assert gc == wc and np.array_equal(got, want)
+    assert wc > 30

@@ -50,6 +50,10 @@ class _BowSide(C.Structure):
                 ("node_ids", C.c_void_p), ("group_start", C.c_void_p), ("feat_idx", C.c_void_p)]
 
 
+class _TriSide(C.Structure):
+    _fields_ = [("side", _BowSide), ("kps", C.c_void_p), ("uright", C.c_void_p)]
+
+
 def load_library():
     """Load libvoslam_b200.so.  Raises OrbError if it has not been built (no fallback)."""
     global _lib
@@ -90,6 +94,7 @@ def load_library():
     L.orbx_search_by_projection_frame.argtypes = [vp, vp, f32, f32, i32, i32, i32, vp, vp, i32]
     L.orbx_search_by_projection_local.argtypes = [vp, vp, f32, f32, vp, vp, i32]
     L.orbx_search_by_bow.argtypes = [vp, vp, i32, f32, i32, i32, vp, vp, i32]
+    L.orbx_search_for_triangulation.argtypes = [vp, vp, vp, f32, f32, vp, i32, i32, i32, vp, vp, i32]
     L.orbx_window_argmin.argtypes = [vp, vp, f32, f32, i32, vp, i32]
     L.orbx_search_by_sim3.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32]
     L.orbx_medoid_descriptors.argtypes = [vp, vp, i32, vp, i32]
@@ -385,6 +390,26 @@ class Matcher:
         _check(self._lib.orbx_search_by_sim3(C.byref(v1), C.byref(s12), C.byref(v2), C.byref(s21), th, _p(match), C.byref(found),
                                              self.device))
         return match[:s12.m].copy(), found.value
+
+    def searchForTriangulation(self, side1, side2, F12, epipole, scale_factors2, checkRot=True, th_low=TH_LOW):
+        """Matcher::searchForTriangulation (matcher.cpp:867-1010).  side dicts = BoW side + 'kps' + 'uright'; returns
+        (match12, match_cnt) with match12[i] = kf2 feature of kf1 feature i (-1 none, -2 cleared by the rotation check)."""
+        keep = []
+        def tri(d):
+            def a(x, dt):
+                y = np.ascontiguousarray(x, dt); keep.append(y); return y.ctypes.data
+            t = _TriSide()
+            t.side.n = len(d["desc"]); t.side.desc = a(d["desc"], np.uint8); t.side.angle = a(d["angle"], np.float32)
+            t.side.valid = a(d["valid"], np.uint8); t.side.ngroups = len(d["node_ids"]); t.side.node_ids = a(d["node_ids"], np.uint32)
+            t.side.group_start = a(d["group_start"], np.int32); t.side.feat_idx = a(d["feat_idx"], np.int32)
+            t.kps = a(d["kps"], KP_DTYPE); t.uright = a(d["uright"], np.float32)
+            return t
+        ta, tb = tri(side1), tri(side2)
+        F = np.ascontiguousarray(F12, np.float64).reshape(9); sc = np.ascontiguousarray(scale_factors2, np.float32)
+        match = np.zeros(max(ta.side.n, 1), np.int32); cnt = C.c_int(0)
+        _check(self._lib.orbx_search_for_triangulation(C.byref(ta), C.byref(tb), _p(F), epipole[0], epipole[1], _p(sc), len(sc),
+                                                       th_low, int(checkRot), _p(match), C.byref(cnt), self.device))
+        return match[:ta.side.n].copy(), cnt.value
 
     def searchByBoW(self, side_a, side_b, mode=0, checkRot=True, th_low=TH_LOW):
         """Matcher::searchByBoW: mode 0 = (KeyFrame*, Frame*) (matcher.cpp:449-559), mode 1 = (KeyFrame*, KeyFrame*)

@@ -89,6 +89,93 @@ __global__ void __launch_bounds__(256) bow_match_kernel(BowSideDev A, BowSideDev
   }
 }
 
+// ---- searchForTriangulation (matcher.cpp:867-1010) -----------------------------------------------------------
+struct TriSideDev {
+  BowSideDev s;                 // valid[i] = the feature has NO map point yet (:902, :921)
+  const orbx_keypoint* kps;     // unKeypoints_
+  const float* uright;          // uRight_ (>= 0: stereo)
+};
+struct TriParams {
+  double F[9];                  // F12, row major
+  float ex, ey;                 // epipole of camera 1 in image 2 (:886-890)
+  const float* scale2;          // keyframe2->scaleFactors_
+  int check_rot;
+};
+
+// Matcher::checkEpipolarConstrain (matcher.cpp:1306-1324): doubles up to the two casts to float, no FMA.
+__device__ __forceinline__ bool epipolar_ok(const TriParams& T, const orbx_keypoint& k1, const orbx_keypoint& k2) {
+  const double x1 = (double)k1.x, y1 = (double)k1.y, x2 = (double)k2.x, y2 = (double)k2.y;
+  double l[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) l[j] = __dadd_rn(__dadd_rn(__dmul_rn(x1, T.F[j]), __dmul_rn(y1, T.F[3 + j])), T.F[6 + j]);
+  const float num = (float)__dadd_rn(__dadd_rn(__dmul_rn(l[0], x2), __dmul_rn(l[1], y2)), l[2]);
+  const float den = (float)__dadd_rn(__dmul_rn(l[0], l[0]), __dmul_rn(l[1], l[1]));
+  if (den == 0) return false;
+  const float d2 = __fdiv_rn(__fmul_rn(num, num), den);
+  const float sigma = T.scale2[k2.octave];
+  return d2 < __fmul_rn(__fmul_rn(3.84f, sigma), sigma);
+}
+
+// One warp per shared vocabulary node, like bow_match_kernel, but with the triangulation rules: candidates need
+// dist <= TH_LOW and dist <= running best (so among equal distances the LAST one in scan order wins, :925-926,:941-945),
+// mono-mono pairs close to the epipole are dropped (:930-938) and the epipolar test must pass.  match[idx1] = idx2.
+__global__ void __launch_bounds__(256) tri_match_kernel(TriSideDev A, TriSideDev B, TriParams T, int th_low, int* takenB, int32_t* match,
+                                                        int8_t* binOf, int* hist) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= A.s.ngroups) return;
+  const uint32_t node = __ldg(A.s.node_ids + g);
+  int lo = 0, hi = B.s.ngroups;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(B.s.node_ids + mid) < node) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= B.s.ngroups || __ldg(B.s.node_ids + lo) != node) return;
+  const int as = __ldg(A.s.group_start + g), ae = __ldg(A.s.group_start + g + 1);
+  const int bs = __ldg(B.s.group_start + lo), be = __ldg(B.s.group_start + lo + 1);
+  const uint32_t kNone = 0xFFFFFFFFu;
+  for (int ia = as; ia < ae; ++ia) {
+    const int idx1 = __ldg(A.s.feat_idx + ia);
+    if (!A.s.valid[idx1]) continue;
+    const bool stereo1 = A.uright[idx1] >= 0;
+    const orbx_keypoint k1 = A.kps[idx1];
+    const uint4* dq = reinterpret_cast<const uint4*>(A.s.desc + (size_t)idx1 * 32);
+    const uint4 d0 = __ldg(dq), d1 = __ldg(dq + 1);
+    uint32_t best = kNone;                            // dist << 20 | (0xFFFFF - position): min = smallest dist, then LAST position
+    for (int ib = bs + lane; ib < be; ib += 32) {
+      const int idx2 = __ldg(B.s.feat_idx + ib);
+      if (*((volatile int*)takenB + idx2) || !B.s.valid[idx2]) continue;
+      const int dist = hamm(d0, d1, B.s.desc + (size_t)idx2 * 32);
+      if (dist > th_low) continue;
+      const orbx_keypoint k2 = B.kps[idx2];
+      if (!stereo1 && !(B.uright[idx2] >= 0)) {
+        const float dx = __fsub_rn(T.ex, k2.x), dy = __fsub_rn(T.ey, k2.y);
+        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, T.scale2[k2.octave])) continue;
+      }
+      if (!epipolar_ok(T, k1, k2)) continue;
+      best = min(best, ((uint32_t)dist << 20) | (0xFFFFFu - (uint32_t)(ib - bs)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (best != kNone) {
+      const int idx2 = __ldg(B.s.feat_idx + bs + (int)(0xFFFFFu - (best & 0xFFFFFu)));
+      if (lane == 0) {
+        takenB[idx2] = 1;
+        match[idx1] = idx2;
+        if (T.check_rot) {
+          float rot = __fsub_rn(k1.angle, B.kps[idx2].angle);
+          if (rot < 0) rot = __fadd_rn(rot, 360.0f);
+          int bin = (int)roundf(__fmul_rn(rot, (float)HISTO_B / 360.0f));      // round(), :961
+          if (bin == HISTO_B) bin = 0;
+          binOf[idx1] = (int8_t)bin;
+          if (bin >= 0 && bin < HISTO_B) atomicAdd(&hist[bin], 1);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(1024) bow_finish_kernel(int nOut, int check_rot, int32_t* match, const int8_t* binOf, const int* hist,
                                                           int* result) {
   __shared__ int keep[3], cnt;
@@ -203,6 +290,80 @@ extern "C" int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b
   }
   bow_match_kernel<<<(a->ngroups + 7) / 8, 256, 0, st>>>(D[0], D[1], mode, ratio, th_low, check_rot, (int*)(db + o_taken),
                                                          (int32_t*)(db + o_match), (int8_t*)(db + o_bin), (int*)(db + o_hist));
+  bow_finish_kernel<<<1, 1024, 0, st>>>(nOut, check_rot, (int32_t*)(db + o_match), (const int8_t*)(db + o_bin), (const int*)(db + o_hist),
+                                        (int*)(db + o_res));
+  int res = 0;
+  ORBX_CUDA(cudaMemcpyAsync(match, db + o_match, sizeof(int32_t) * nOut, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaMemcpyAsync(&res, db + o_res, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaStreamSynchronize(st));
+  ORBX_CUDA(cudaGetLastError());
+  *match_cnt = res;
+  return ORBX_OK;
+}
+
+// Matcher::searchForTriangulation(KeyFrame*, KeyFrame*, matchIdxs, F12, checkRot)  (matcher.cpp:867-1010).
+// match[i] (i < a->side.n) = matched keyframe-2 feature, -1 none, -2 cleared by the rotation check; the caller builds
+// matchIdxs from the entries >= 0 in ascending i (:1000-1007).
+extern "C" int orbx_search_for_triangulation(const orbx_tri_side* a, const orbx_tri_side* b, const double* F12, float ex, float ey,
+                                             const float* scale_factors2, int nlevels, int th_low, int check_rot, int32_t* match,
+                                             int* match_cnt, int device) {
+  if (!a || !b || !F12 || !scale_factors2 || nlevels < 1) { set_error("null argument"); return ORBX_ERR_ARG; }
+  if (check_side(&a->side) || check_side(&b->side)) return ORBX_ERR_ARG;
+  if (!match || !match_cnt || (a->side.n > 0 && (!a->kps || !a->uright)) || (b->side.n > 0 && (!b->kps || !b->uright))) {
+    set_error("bad argument");
+    return ORBX_ERR_ARG;
+  }
+  const int nOut = a->side.n;
+  if (a->side.ngroups == 0 || b->side.ngroups == 0 || a->side.n == 0 || b->side.n == 0) {
+    for (int i = 0; i < nOut; ++i) match[i] = -1;
+    *match_cnt = 0;
+    return ORBX_OK;
+  }
+  size_t used = 0;
+  auto add = [&](size_t bytes) { used = align_up_sz(used, 256); size_t o = used; used += bytes; return o; };
+  size_t off[2][8];
+  const orbx_tri_side* sides[2] = {a, b};
+  for (int s = 0; s < 2; ++s) {
+    const orbx_bow_side* S = &sides[s]->side;
+    const int nfi = S->group_start[S->ngroups];
+    off[s][0] = add((size_t)S->n * 32); off[s][1] = add(sizeof(float) * S->n); off[s][2] = add(S->n);
+    off[s][3] = add(sizeof(uint32_t) * S->ngroups); off[s][4] = add(sizeof(int32_t) * (S->ngroups + 1)); off[s][5] = add(sizeof(int32_t) * nfi);
+    off[s][6] = add(sizeof(orbx_keypoint) * S->n); off[s][7] = add(sizeof(float) * S->n);
+  }
+  const size_t o_scale = add(sizeof(float) * nlevels);
+  const size_t inBytes = align_up_sz(used, 256);
+  const size_t o_taken = add(sizeof(int) * b->side.n), o_match = add(sizeof(int32_t) * nOut), o_bin = add(nOut), o_hist = add(sizeof(int) * 32),
+               o_res = add(sizeof(int) * 4);
+  if (g_bow.reserve(used + 256, inBytes, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
+  uint8_t* hb = g_bow.h;
+  for (int s = 0; s < 2; ++s) {
+    const orbx_bow_side* S = &sides[s]->side;
+    const int nfi = S->group_start[S->ngroups];
+    memcpy(hb + off[s][0], S->desc, (size_t)S->n * 32); memcpy(hb + off[s][1], S->angle, sizeof(float) * S->n);
+    memcpy(hb + off[s][2], S->valid, S->n); memcpy(hb + off[s][3], S->node_ids, sizeof(uint32_t) * S->ngroups);
+    memcpy(hb + off[s][4], S->group_start, sizeof(int32_t) * (S->ngroups + 1)); memcpy(hb + off[s][5], S->feat_idx, sizeof(int32_t) * nfi);
+    memcpy(hb + off[s][6], sides[s]->kps, sizeof(orbx_keypoint) * S->n); memcpy(hb + off[s][7], sides[s]->uright, sizeof(float) * S->n);
+  }
+  memcpy(hb + o_scale, scale_factors2, sizeof(float) * nlevels);
+  cudaStream_t st = nullptr;
+  uint8_t* db = g_bow.d;
+  ORBX_CUDA(cudaMemcpyAsync(db, hb, inBytes, cudaMemcpyHostToDevice, st));
+  ORBX_CUDA(cudaMemsetAsync(db + o_taken, 0, sizeof(int) * b->side.n, st));
+  ORBX_CUDA(cudaMemsetAsync(db + o_match, 0xFF, sizeof(int32_t) * nOut, st));
+  ORBX_CUDA(cudaMemsetAsync(db + o_hist, 0, sizeof(int) * 32 + 256, st));
+  TriSideDev D[2];
+  for (int s = 0; s < 2; ++s) {
+    const orbx_bow_side* S = &sides[s]->side;
+    D[s].s.n = S->n; D[s].s.desc = db + off[s][0]; D[s].s.angle = (const float*)(db + off[s][1]); D[s].s.valid = db + off[s][2];
+    D[s].s.ngroups = S->ngroups; D[s].s.node_ids = (const uint32_t*)(db + off[s][3]);
+    D[s].s.group_start = (const int32_t*)(db + off[s][4]); D[s].s.feat_idx = (const int32_t*)(db + off[s][5]);
+    D[s].kps = (const orbx_keypoint*)(db + off[s][6]); D[s].uright = (const float*)(db + off[s][7]);
+  }
+  TriParams T;
+  for (int i = 0; i < 9; ++i) T.F[i] = F12[i];
+  T.ex = ex; T.ey = ey; T.scale2 = (const float*)(db + o_scale); T.check_rot = check_rot;
+  tri_match_kernel<<<(a->side.ngroups + 7) / 8, 256, 0, st>>>(D[0], D[1], T, th_low, (int*)(db + o_taken), (int32_t*)(db + o_match),
+                                                              (int8_t*)(db + o_bin), (int*)(db + o_hist));
   bow_finish_kernel<<<1, 1024, 0, st>>>(nOut, check_rot, (int32_t*)(db + o_match), (const int8_t*)(db + o_bin), (const int*)(db + o_hist),
                                         (int*)(db + o_res));
   int res = 0;
