@@ -97,6 +97,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so that the pinned staging buffers of the
+    end-to-end path are allocated (first touch) on the NUMA node the GPU hangs off.  Best effort, silent on failure."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1 and 64 * i + b < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def cpu_reference_step(imgs, cores, Ref, port):
     """The reference's own extractor (oracle/_ref, one instance per core over disjoint frames, ORBextractor.h:85 is
     stateful) + the reference's matcher loop (CPU port, threaded over queries) on `imgs`.  Returns seconds."""
@@ -156,6 +172,8 @@ def run_b200(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)            # before any pinned allocation: first touch on the GPU's NUMA node
     F = args.frames                                  # frames per GPU per step (weak scaling)
     ex = vo.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank)
     cap = ex.max_keypoints
