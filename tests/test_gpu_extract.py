@@ -115,3 +115,29 @@ def test_other_parameters(vo):
         rk, rd = P.extract(img)
         assert np.array_equal(k, rk) and np.array_equal(d, rd), (nf, sf, nl)
         ex.close()
+
+
+def test_error_convention(vo):
+    """The C ABI never throws: bad arguments, too small buffers and unsupported shapes come back as status codes."""
+    import ctypes as C
+    L = vo.lib()
+    ex = vo.ORBextractor()
+    img = synth.make_frame(3)
+    kps = np.zeros(10, vo.KP_DTYPE); desc = np.zeros((10, 32), np.uint8); n = C.c_int(-1)
+    rc = L.orbx_extract(ex._h, C.c_void_p(img.ctypes.data), 640, 480, 640, C.c_void_p(kps.ctypes.data), C.c_void_p(desc.ctypes.data), 10,
+                        C.byref(n))
+    assert rc == -3 and n.value > 900                      # ORBX_ERR_CAPACITY, the needed count is still reported
+    rk, rd = oracle.Port().extract(img)
+    assert np.array_equal(kps, rk[:10]) and np.array_equal(desc, rd[:10])     # the part that fits is correct
+    assert L.orbx_extract(None, C.c_void_p(img.ctypes.data), 640, 480, 640, None, None, 10, C.byref(n)) == -1
+    assert L.orbx_extract(ex._h, C.c_void_p(img.ctypes.data), 640, 480, 100, C.c_void_p(kps.ctypes.data), C.c_void_p(desc.ctypes.data), 10,
+                          C.byref(n)) == -1               # stride < width
+    wide = np.zeros((300, 4300), np.uint8)
+    with pytest.raises(vo.OrbError, match="too large|aspect"):
+        ex(wide)
+    assert b"" != L.orbx_last_error()
+    p = vo.api._Params(1000, 0.9, 8, 20, 7, 0); h = C.c_void_p()
+    assert L.orbx_create(C.byref(p), C.byref(h)) == -1     # scale factor <= 1
+    p = vo.api._Params(1000, 1.2, 8, 20, 7, 99)
+    assert L.orbx_create(C.byref(p), C.byref(h)) == -2     # no such device
+    ex.close()
