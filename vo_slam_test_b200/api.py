@@ -18,7 +18,8 @@ class OrbError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(HERE, "lib", "libvoslam_b200.so")
+    """In-tree build of the C-ABI library; ORBX_LIB overrides it (A/B experiments with alternative builds)."""
+    return os.environ.get("ORBX_LIB") or os.path.join(HERE, "lib", "libvoslam_b200.so")
 
 
 _lib = None

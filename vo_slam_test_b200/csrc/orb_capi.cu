@@ -199,6 +199,9 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
     L.kpSize = (float)(int)(31 * h->scale[l]);             // :845
     G.fastTileW = std::max(G.fastTileW, align_up(std::min(kCellsPerCta, L.nCols) * L.wCell + 6 + 15, 16));
     G.fastTileH = std::max(G.fastTileH, L.hCell + 6);
+    G.fastCellPix = std::max(G.fastCellPix, align_up(L.wCell * L.hCell, 8));
+    G.fastCellQuads = std::max(G.fastCellQuads, align_up(((L.wCell + 3) / 4) * L.hCell, 8));
+    G.fastCellSurv = std::max(G.fastCellSurv, align_up(((L.wCell + 1) / 2) * ((L.hCell + 1) / 2), 4));
   }
   slotKeyBase.push_back(slotKeys);
   G.totalSlots = slot; G.slotKeysPerFrame = slotKeys; G.keysPerFrame = keyBase; G.selPerFrame = selBase;

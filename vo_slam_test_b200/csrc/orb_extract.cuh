@@ -52,6 +52,7 @@ struct Geom {
   int blurTiles;
   int fastTileW, fastTileH;  // smem tile extents of the FAST kernel (pitch is a multiple of 16)
   int fastSurvCap;           // largest slot capacity (NMS survivors of one CTA)
+  int fastCellPix, fastCellQuads, fastCellSurv;   // per-cell maxima (pixels, 4-pixel quads, NMS survivors), 16-byte rounded
   LevelGeom L[kMaxLevels];
 };
 

@@ -2,6 +2,8 @@
 //
 // Built with -fmad=false: the reference binary has no FMA contraction (CMakeLists.txt:4-5), and the float
 // paths below (fastAtan2, descriptor rotation, keypoint scaling) must round exactly like it.
+#include <stdlib.h>
+
 #include "orb_extract.cuh"
 
 namespace orbx {
@@ -434,6 +436,237 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const __grid_constan
     out[rank] = pack_key(tx0 + xi + 3, ty0 + yi + 3, sc0[yi * sp + xi] - 1);
   }
   if (tid == 0) *out_count = S;
+}
+
+// ---- warp-synchronous variant (the default): one warp owns one cell end to end, so the phases are separated by
+// __syncwarp instead of CTA barriers (barrier stalls were the top stall reason of fast_kernel) and queue appends use
+// ballots / warp scans instead of shared-memory atomics.  Same arithmetic and the same output order as fast_kernel.
+constexpr int kWarpCells = 2;                     // cells (= warps) per CTA of the warp-synchronous variant
+
+template <int SH>
+__device__ __forceinline__ uint32_t fw_stage_a(const uint8_t* rowm3, int sp, uint32_t kc, bool hiT) { return reject4_a<SH>(rowm3, sp, kc, hiT); }
+
+__global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid_constant__ Geom G, const Bufs B, const TmaSet TM) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ int cellOut[kWarpCells];
+  __shared__ __align__(8) uint64_t tmaBar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = blockIdx.x, f = blockIdx.y;
+  int l = 0;
+  while (l + 1 < G.nlevels && slot >= G.L[l + 1].slot0) ++l;
+  const LevelGeom& L = G.L[l];
+  const int ls = slot - L.slot0;
+  const int ci = ls / L.groups, grp = ls - ci * L.groups;
+  const int j0 = grp * kCellsPerCta, j1 = min(j0 + kCellsPerCta, L.nCols);
+  const int tx0 = j0 * L.wCell, tx1 = min(j1 * L.wCell + 6, L.regW);
+  const int ty0 = ci * L.hCell, ty1 = min(ty0 + L.hCell + 6, L.regH);
+  const int tw = tx1 - tx0, th = ty1 - ty0;
+  const int iw = tw - 6, ih = th - 6;
+  int* out_count = B.slotCount + (size_t)f * G.totalSlots + slot;
+  if (iw <= 0 || ih <= 0) {
+    if (tid == 0) *out_count = 0;
+    return;
+  }
+  const int sp = G.fastTileW;
+  const int tileBytes = G.fastTileH * sp;
+  uint8_t* img = smem;
+  uint8_t* sc = smem + tileBytes;
+  // per-warp scratch: queue (u16 per cell pixel), itemq (u16 per quad), surv (u32 per NMS survivor)
+  const int cellPix = G.fastCellPix, cellQuads = G.fastCellQuads, cellSurv = G.fastCellSurv;
+  uint8_t* wbase = sc + tileBytes + (size_t)warp * (2 * cellPix + 2 * cellQuads + 4 * cellSurv);
+  uint16_t* queue = (uint16_t*)wbase;
+  uint16_t* itemq = queue + cellPix;
+  uint32_t* surv = (uint32_t*)(itemq + cellQuads);
+
+  int pitch;
+  const uint8_t* lvl = level_ptr(G, B, l, f, pitch);
+  const int gx0 = kMinBorder + tx0;
+  int ox = 0;
+  const bool viaTma = TM.use[l] != 0;
+  if (viaTma) {
+    ox = gx0 & 15;
+    if (tid == 0) {
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tmaBar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)tileBytes) : "memory");
+      const int z = (l == 0 ? TM.frame0 : 0) + f;
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+              (uint32_t)__cvta_generic_to_shared(img)),
+          "l"(reinterpret_cast<uint64_t>(TM.map + l)), "r"(gx0 - ox), "r"(kMinBorder + ty0), "r"(z), "r"(bar)
+          : "memory");
+    }
+  } else if ((((uintptr_t)lvl | (uintptr_t)pitch) & 15) == 0) {
+    ox = gx0 & 15;
+    const int wpr = (ox + tw + 15) >> 4;
+    const uint8_t* base = lvl + (size_t)(kMinBorder + ty0) * pitch + (gx0 - ox);
+    for (int i = tid; i < th * wpr; i += 32 * kWarpCells) {
+      const int y = i / wpr, w = i - y * wpr;
+      *reinterpret_cast<uint4*>(img + y * sp + 16 * w) = __ldg(reinterpret_cast<const uint4*>(base + (size_t)y * pitch) + w);
+    }
+  } else {
+    const uint8_t* base = lvl + (size_t)(kMinBorder + ty0) * pitch + gx0;
+    for (int y = warp; y < th; y += kWarpCells)
+      for (int x = lane; x < tw; x += 32) img[y * sp + x] = __ldg(base + (size_t)y * pitch + x);
+  }
+  {
+    uint4* z = reinterpret_cast<uint4*>(sc);
+    for (int i = tid; i < (th * sp) >> 4; i += 32 * kWarpCells) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  if (viaTma) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tmaBar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "TW_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra TD_%=;\n\t"
+        "bra TW_%=;\n\t"
+        "TD_%=:\n\t}" ::"r"(bar) : "memory");
+  }
+
+  // ---- this warp's cell -----------------------------------------------------------------------------------------
+  const int jj = warp;
+  const int cx0 = jj * L.wCell;                           // first interior column of the cell (tile-interior coordinates)
+  const int cw = min(L.wCell, iw - cx0);                  // cell width (<= 0: the cell does not exist in this slot)
+  int S = 0;
+  const uint8_t* img0 = img + 3 * sp + 3 + ox;
+  uint8_t* sc0 = sc + 3 * sp + 3 + ox;
+  if (jj < j1 - j0 && cw > 0) {
+    const int nq4 = (cw + 3) >> 2;
+    const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nq4 + 1;
+    const int sh = (ox + cx0) & 3, aox = (ox + cx0) & ~3;  // quads start at the cell's first pixel
+    int t = G.iniTh;
+    for (int pass = 0; pass < 2; ++pass) {
+      const uint32_t kc = 0x7F7F7F7Fu - (uint32_t)(t & 0x7F) * 0x01010101u;
+      const bool hiT = t >= 128;
+      // stage a over every quad of the cell
+      int ni = 0;
+      for (int base = 0; base < ih * nq4; base += 32) {
+        const int item = base + lane;
+        uint32_t m = 0;
+        if (item < ih * nq4) {
+          const int yi = nq4 == 1 ? item : (int)__umulhi((uint32_t)item, magic), xq = 4 * (item - yi * nq4);
+          const uint8_t* rowm3 = img + yi * sp + aox + xq;
+          switch (sh) {
+            case 0: m = reject4_a<0>(rowm3, sp, kc, hiT); break;
+            case 1: m = reject4_a<1>(rowm3, sp, kc, hiT); break;
+            case 2: m = reject4_a<2>(rowm3, sp, kc, hiT); break;
+            default: m = reject4_a<3>(rowm3, sp, kc, hiT); break;
+          }
+          m &= 0x80808080u;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
+        if (m) {
+          const uint32_t bits = ((m >> 7) & 1) | ((m >> 14) & 2) | ((m >> 21) & 4) | ((m >> 28) & 8);
+          itemq[ni + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(item | (bits << 12));
+        }
+        ni += __popc(bal);
+      }
+      __syncwarp();
+      // stage b densely over the surviving quads -> pixel queue
+      int nq = 0;
+      for (int base = 0; base < ni; base += 32) {
+        const int k = base + lane;
+        uint32_t keep = 0;
+        int yi = 0, xq = 0;
+        if (k < ni) {
+          const int e = itemq[k], item = e & 0xFFF;
+          const uint32_t bits = e >> 12;
+          yi = nq4 == 1 ? item : (int)__umulhi((uint32_t)item, magic); xq = 4 * (item - yi * nq4);
+          const uint8_t* rowm3 = img + yi * sp + aox + xq;
+          uint32_t m = ((bits & 1) << 7) | ((bits & 2) << 14) | ((bits & 4) << 21) | ((bits & 8) << 28);
+          switch (sh) {
+            case 0: m = reject4_b<0>(rowm3, sp, kc, hiT, m); break;
+            case 1: m = reject4_b<1>(rowm3, sp, kc, hiT, m); break;
+            case 2: m = reject4_b<2>(rowm3, sp, kc, hiT, m); break;
+            default: m = reject4_b<3>(rowm3, sp, kc, hiT, m); break;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (((m >> (8 * j + 7)) & 1) && xq + j < cw) keep |= 1u << j;
+        }
+        // warp-ordered append of up to 4 pixels per lane
+        const int cnt = __popc(keep);
+        int pre = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+        int pos = nq + pre - cnt;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((keep >> j) & 1) queue[pos++] = (uint16_t)((yi << 8) | (xq + j));
+        nq += __shfl_sync(0xffffffffu, pre, 31);
+      }
+      __syncwarp();
+      // score two queue entries per lane; corners are compacted in place at the front of the same queue
+      int nc = 0;
+      for (int base = 0; base < nq; base += 64) {
+        const int k0 = base + 2 * lane, k1 = k0 + 1;
+        int e0 = 0, e1 = 0, b0 = 0, b1 = 0;
+        if (k0 < nq) {
+          e0 = queue[k0]; e1 = queue[min(k1, nq - 1)];
+          const int y0 = e0 >> 8, x0 = e0 & 255, y1 = e1 >> 8, x1 = e1 & 255;
+          fast_best2(img0 + y0 * sp + cx0 + x0, img0 + y1 * sp + cx0 + x1, sp, b0, b1);
+          sc0[y0 * sp + cx0 + x0] = (uint8_t)(b0 > t ? b0 : 0);
+          if (k1 < nq) sc0[y1 * sp + cx0 + x1] = (uint8_t)(b1 > t ? b1 : 0);
+        }
+        const bool c0 = k0 < nq && b0 > t, c1 = k1 < nq && b1 > t;
+        const int cnt = (int)c0 + (int)c1;
+        int pre = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+        __syncwarp();                                  // every lane has read its entries before anyone overwrites the front
+        int pos = nc + pre - cnt;
+        if (c0) queue[pos++] = (uint16_t)e0;
+        if (c1) queue[pos] = (uint16_t)e1;
+        nc += __shfl_sync(0xffffffffu, pre, 31);
+        __syncwarp();
+      }
+      // NMS inside the cell (outside the cell counts as 0); survivors appended in any order, ranked later
+      for (int base = 0; base < nc; base += 32) {
+        const int k = base + lane;
+        bool keep = false;
+        int e = 0;
+        if (k < nc) {
+          e = queue[k];
+          const int yi = e >> 8, cx = e & 255;
+          const uint8_t* s = sc0 + yi * sp + cx0 + cx;
+          const int v = s[0];
+          const bool hasL = cx > 0, hasR = cx + 1 < cw, hasU = yi > 0, hasD = yi + 1 < ih;
+          keep = true;
+          keep &= !(hasU && hasL && s[-sp - 1] >= v);
+          keep &= !(hasU && s[-sp] >= v);
+          keep &= !(hasU && hasR && s[-sp + 1] >= v);
+          keep &= !(hasL && s[-1] >= v);
+          keep &= !(hasR && s[1] >= v);
+          keep &= !(hasD && hasL && s[sp - 1] >= v);
+          keep &= !(hasD && s[sp] >= v);
+          keep &= !(hasD && hasR && s[sp + 1] >= v);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) surv[S + __popc(bal & ((1u << lane) - 1))] = (uint32_t)e;      // yi<<8 | cx : already the (row, col) order key
+        S += __popc(bal);
+      }
+      __syncwarp();
+      if (S > 0 || pass == 1 || G.minTh >= G.iniTh) break;     // empty cell: retry at minThFAST (ORBextractor.cpp:820-824)
+      t = G.minTh;
+    }
+  }
+  // ---- ordered emission: cells left to right, inside a cell by (row, column) ----------------------------------------
+  if (lane == 0) cellOut[warp] = S;
+  __syncthreads();
+  int off = 0, total = 0;
+  for (int w = 0; w < kWarpCells; ++w) { const int c = cellOut[w]; if (w < warp) off += c; total += c; }
+  uint32_t* out = B.slotKeys + (size_t)f * G.slotKeysPerFrame + __ldg(B.slotKeyBase + slot);
+  for (int k = lane; k < S; k += 32) {
+    const uint32_t key = surv[k];
+    int rank = 0;
+    for (int j = 0; j < S; ++j) rank += surv[j] < key ? 1 : 0;
+    const int yi = key >> 8, cx = key & 255;
+    out[off + rank] = pack_key(tx0 + cx0 + cx + 3, ty0 + yi + 3, sc0[yi * sp + cx0 + cx] - 1);
+  }
+  if (tid == 0) *out_count = total;
 }
 
 // ======================================================================================================
@@ -1001,6 +1234,8 @@ void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe
     resize_kernel<<<grid, block, 0, st>>>(src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
 }
 
+size_t fast_warp_smem_bytes(const Geom& G);
+
 size_t fast_smem_bytes(const Geom& G) {
   return (size_t)4 * G.fastTileW * G.fastTileH + 4 * (size_t)G.fastSurvCap + (size_t)G.fastTileW * G.fastTileH / 2 +
          (size_t)2 * G.fastTileW * G.fastTileH + 64;
@@ -1015,10 +1250,26 @@ size_t octree_smem_bytes(const Geom& G) {
 cudaError_t configure_kernels(const Geom& G) {
   cudaError_t e = cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(G));
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(fast_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_warp_smem_bytes(G));
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_smem_bytes(G));
 }
 
+size_t fast_warp_smem_bytes(const Geom& G) {
+  return (size_t)2 * G.fastTileW * G.fastTileH + (size_t)kWarpCells * (2 * G.fastCellPix + 2 * G.fastCellQuads + 4 * G.fastCellSurv) + 64;
+}
+
+static bool use_fast_warp() {
+  // default: the warp-synchronous kernel (measured 9 % faster); ORBX_FAST_WARP=0 selects the CTA-wide one for A/B runs
+  static const bool v = !(getenv("ORBX_FAST_WARP") && atoi(getenv("ORBX_FAST_WARP")) == 0) && kCellsPerCta == kWarpCells;
+  return v;
+}
+
 void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st) {
+  if (use_fast_warp()) {
+    fast_warp_kernel<<<dim3(G.totalSlots, nframes), 32 * kWarpCells, fast_warp_smem_bytes(G), st>>>(G, B, TM);
+    return;
+  }
   fast_kernel<<<dim3(G.totalSlots, nframes), kFastThreads, fast_smem_bytes(G), st>>>(G, B, TM);
 }
 void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
