@@ -264,6 +264,35 @@ int orbx_search_for_triangulation(const orbx_tri_side* a, const orbx_tri_side* b
  * wins ties; -1 for a point without observations (the reference keeps its old descriptor).  Host pointers. */
 int orbx_medoid_descriptors(const uint8_t* desc, const int32_t* start, int npoints, int32_t* best, int device);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Frame post-processing between extraction and matching: what Frame::Frame does after
+ * the extractor call (frame.cpp:22-32) -- undistortKeyPoints (frame.cpp:36-70, cv::undistortPoints(pts, pts, K, D,
+ * noArray(), K): 5 iterations in double, bit-exact to OpenCV 4.13), findDepth (frame.cpp:108-133) and
+ * assignFeaturesToGrid (frame.cpp:72-97) -- for a batch of frames laid out like the output of orbx_extract_batch.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct orbx_camera {
+  float fx, fy, cx, cy;               /* camera.cpp:10-13 (K_ is CV_32F, camera.cpp:19-21) */
+  float dist[8];                      /* k1 k2 p1 p2 [k3 [k4 k5 k6]]; camera.cpp:27-38 builds 4 or 5 of them */
+  int ndist;                          /* 0..8; dist[0] == 0 copies the keypoints unchanged (frame.cpp:41-45) */
+  float bf;                           /* camera_bf (frame.cpp:116,129) */
+  float xmin, xmax, ymin, ymax;       /* image bounds of the grid (camera.cpp:42-45) */
+} orbx_camera;
+
+/* kps[nframes*cap] + counts[nframes]: extractor output.  depth: nframes float32 images (height x w, strides in BYTES),
+ * sampled at the ORIGINAL keypoint with float->int truncation (frame.cpp:121-123); NULL = no depth (all -1).
+ * Outputs per frame f (entries at or beyond counts[f] are unspecified):
+ *   unkps[f*cap + i]     unKeypoints_[i]            uright[f*cap + i]  uRight_[i]  (-1 where depth <= 0)
+ *   depth_out[f*cap + i] depth_[i]                  cell_start[f*(64*48+1) + c], ids[f*cap + ..]  CSR grid as orbx_grid_build
+ * Device variant: everything resident, asynchronous on `stream`. */
+int orbx_frame_finish(const orbx_camera* cam, const orbx_keypoint* kps, const int32_t* counts, int nframes, int cap,
+                      const float* depth, int w, int height, size_t depth_row_stride, size_t depth_frame_stride,
+                      orbx_keypoint* unkps, float* uright, float* depth_out, int32_t* cell_start, int32_t* ids,
+                      int device);
+int orbx_frame_finish_device(const orbx_camera* cam, const orbx_keypoint* d_kps, const int32_t* d_counts, int nframes,
+                             int cap, const float* d_depth, int w, int height, size_t depth_row_stride,
+                             size_t depth_frame_stride, orbx_keypoint* d_unkps, float* d_uright, float* d_depth_out,
+                             int32_t* d_cell_start, int32_t* d_ids, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

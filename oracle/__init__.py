@@ -233,6 +233,26 @@ class Port:
         n = self.lib.port_grid_build(_ptr(kps), len(kps), xmin, xmax, ymin, ymax, _ptr(start), _ptr(ids))
         return start, ids[:n].copy()
 
+    def frame_finish(self, kps, cam, depth=None):
+        """frame.cpp:36-133 + :72-97 on one frame.  cam: dict(fx, fy, cx, cy, dist, bf, bounds=(xmin, xmax, ymin, ymax))."""
+        kps = np.ascontiguousarray(kps)
+        if kps.dtype != KP_DTYPE:
+            kps = np.ascontiguousarray(kps, np.float32).view(KP_DTYPE).reshape(-1)
+        n = len(kps)
+        cs = camera_struct(cam)
+        un = np.empty_like(kps); ur = np.empty(n, np.float32); dp = np.empty(n, np.float32)
+        start = np.empty(64 * 48 + 1, np.int32); ids = np.empty(max(n, 1), np.int32)
+        H, W, step = (0, 0, 0)
+        if depth is not None:
+            assert depth.dtype == np.float32 and depth.strides[1] == 4
+            H, W = depth.shape; step = depth.strides[0]
+        self.lib.port_frame_finish.restype = C.c_int
+        self.lib.port_frame_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        m = self.lib.port_frame_finish(C.addressof(cs), _ptr(kps), n, depth.ctypes.data if depth is not None else None, W, H,
+                                       step, _ptr(un), _ptr(ur), _ptr(dp), _ptr(start), _ptr(ids))
+        return un, ur, dp, start, ids[:m].copy()
+
     def features_in_area(self, kps, bounds, u, v, r, min_level, max_level):
         kps = np.ascontiguousarray(kps)
         out = np.empty(max(len(kps), 1), np.int32)
@@ -447,3 +467,21 @@ class Ref:
             return kps, desc, cnt
         self.lib.orbref_extract_batch(*self.args, _ptr(imgs), B, W, H, None, None, cap, _ptr(cnt), nthreads)
         return None, None, cnt
+
+
+class CameraStruct(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("dist", C.c_float * 8),
+                ("ndist", C.c_int), ("bf", C.c_float), ("xmin", C.c_float), ("xmax", C.c_float), ("ymin", C.c_float),
+                ("ymax", C.c_float)]
+
+
+def camera_struct(cam):
+    cs = CameraStruct()
+    cs.fx, cs.fy, cs.cx, cs.cy, cs.bf = cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam.get("bf", 0.0)
+    d = list(cam.get("dist", []))
+    assert len(d) <= 8
+    for i in range(8):
+        cs.dist[i] = d[i] if i < len(d) else 0.0
+    cs.ndist = len(d)
+    cs.xmin, cs.xmax, cs.ymin, cs.ymax = cam["bounds"]
+    return cs

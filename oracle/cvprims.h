@@ -247,4 +247,34 @@ static inline void fast9_16(const uint8_t* img, int w, int h, size_t step, int t
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// cv::undistortPoints(src, dst, K, D, noArray(), P = K), CV_32FC2 (call site frame.cpp:58).  OpenCV >= 3.x runs the
+// fixed-point inversion of the distortion model for exactly 5 iterations (TermCriteria(MAX_ITER, 5, 0.01): the
+// epsilon is unused because the type has no EPS bit), everything in double without FMA contraction, then applies
+// P * R (R = I) and narrows to float.  k = {k1,k2,p1,p2,k3,k4,k5,k6} widened from float; the thin-prism and tilt
+// terms the reference never passes (camera.cpp:27-38 builds 4 or 5 coefficients) are zero and drop out exactly.
+// Pinned bit-exact against cv2 4.13.0 (tests/golden/cv2_undistort.npz).
+static inline void undistort_point_k(float u_in, float v_in, double fx, double fy, double cx, double cy, const double* k,
+                                     float* u_out, float* v_out) {
+  const double ifx = 1. / fx, ify = 1. / fy;
+  const double u = u_in, v = v_in;
+  double x = (u - cx) * ifx, y = (v - cy) * ify;
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = x * x + y * y;
+    const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+    if (icdist < 0) {          // OpenCV regression test 14583: give up and return the linear back-projection
+      x = (u - cx) * ifx;
+      y = (v - cy) * ify;
+      break;
+    }
+    const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x);
+    const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y;
+    x = (x0 - deltaX) * icdist;
+    y = (y0 - deltaY) * icdist;
+  }
+  *u_out = (float)(fx * x + cx);
+  *v_out = (float)(fy * y + cy);
+}
+
 }  // namespace cvp

@@ -526,6 +526,31 @@ int port_grid_build(const void* kps, int n, float xmin, float xmax, float ymin, 
   return o;
 }
 
+// Frame post-processing after extraction (frame.cpp:22-32): undistortKeyPoints (:36-70), findDepth (:108-133),
+// assignFeaturesToGrid (:72-97).  Camera constants as floats like camera.cpp:10-48; dist = k1 k2 p1 p2 [k3 [k4 k5 k6]].
+struct port_camera { float fx, fy, cx, cy; float dist[8]; int ndist; float bf; float xmin, xmax, ymin, ymax; };
+
+int port_frame_finish(const port_camera* cam, const void* kps_in, int n, const float* depth, int W, int H, size_t depth_step,
+                      void* unkps_out, float* uright, float* depth_out, int* cell_start, int* ids) {
+  const PortKp* kps = (const PortKp*)kps_in;
+  PortKp* un = (PortKp*)unkps_out;
+  double k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < cam->ndist && i < 8; ++i) k[i] = (double)cam->dist[i];
+  for (int i = 0; i < n; ++i) {
+    un[i] = kps[i];
+    if (cam->dist[0] != 0.0f)                                                        // frame.cpp:41-45
+      cvp::undistort_point_k(kps[i].x, kps[i].y, cam->fx, cam->fy, cam->cx, cam->cy, k, &un[i].x, &un[i].y);
+    uright[i] = -1.f; depth_out[i] = -1.f;                                           // :113-114
+    if (depth) {
+      const int c = (int)kps[i].x, r = (int)kps[i].y;                                // at<float>(v,u): float -> int truncation (:123)
+      (void)W; (void)H;
+      const float d = *(const float*)((const char*)depth + (size_t)r * depth_step + (size_t)c * sizeof(float));
+      if (d > 0) { depth_out[i] = d; uright[i] = un[i].x - cam->bf / d; }            // :126-130
+    }
+  }
+  return port_grid_build(un, n, cam->xmin, cam->xmax, cam->ymin, cam->ymax, cell_start, ids);
+}
+
 int port_features_in_area(const void* kps, int n, float xmin, float xmax, float ymin, float ymax, float u, float v,
                           float r, int minL, int maxL, int* out, int cap) {
   Grid g;

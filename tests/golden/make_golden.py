@@ -32,7 +32,27 @@ def fast_cv2(img, th):
     return np.array([[int(p.pt[0]), int(p.pt[1]), int(p.response)] for p in k], np.int32).reshape(-1, 3)
 
 
+def undistort_golden():
+    """cv2.undistortPoints(pts, K, D, None, K) -- the call of frame.cpp:58 -- on keypoint-like coordinates."""
+    rng = np.random.default_rng(77)
+    N = 6000
+    pts = np.stack([rng.uniform(0, 640, N), rng.uniform(0, 480, N)], 1).astype(np.float32)
+    pts[: N // 2] = np.floor(pts[: N // 2])                       # level-0 keypoints are integer valued
+    pts[:4] = [[0, 0], [639, 479], [318.6, 255.3], [320, 240]]
+    K = np.array([[517.3, 0, 318.6], [0, 516.5, 255.3], [0, 0, 1]], np.float32)     # TUM fr1 (config/example.yaml)
+    sets = {"tum1": [0.2624, -0.9531, -0.0054, 0.0026, 1.1633], "four": [-0.28, 0.07, 0.0002, 0.00002],
+            "rational": [0.1, -0.2, 0.001, 0.002, 0.05, 0.01, 0.02, 0.003],
+            "strong": [-6.0, 2.0, 0.01, -0.02, 0.5]}              # drives icdist < 0 for points far from the centre
+    d = {"pts": pts, "K": K}
+    for name, D in sets.items():
+        D = np.array(D, np.float32)
+        d["D_" + name] = D
+        d["out_" + name] = cv2.undistortPoints(pts.reshape(-1, 1, 2).copy(), K, D, None, K).reshape(-1, 2)
+    np.savez_compressed(os.path.join(OUT, "cv2_undistort.npz"), cv2_version=cv2.__version__, **d)
+
+
 def main():
+    undistort_golden()
     rng = np.random.default_rng(1234)
     d = {}
     # resize: noise image and a structured one, odd sizes

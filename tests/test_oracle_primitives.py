@@ -99,3 +99,51 @@ def test_fast_tiny_rois(port):
     for (h, w) in [(6, 40), (40, 6), (7, 7), (3, 3), (8, 9)]:
         roi = img[100:100 + h, 100:100 + w]
         assert np.array_equal(port.fast(roi, 7), _fast_cv2(roi, 7))
+
+
+def _cam(K, D, bf=40.0, bounds=(0.0, 640.0, 0.0, 480.0)):
+    return dict(fx=float(K[0, 0]), fy=float(K[1, 1]), cx=float(K[0, 2]), cy=float(K[1, 2]), dist=[float(x) for x in D], bf=bf,
+                bounds=bounds)
+
+
+@pytest.mark.parametrize("name", ["tum1", "four", "rational", "strong"])
+def test_undistort_golden(port, golden_dir, name):
+    """cv::undistortPoints(.., K, D, noArray(), K) of frame.cpp:58, pinned to cv2 4.13.0 (bit-exact, NaNs alike)."""
+    g = np.load(os.path.join(golden_dir, "cv2_undistort.npz"))
+    kps = np.zeros((len(g["pts"]), 7), np.float32); kps[:, :2] = g["pts"]
+    un = port.frame_finish(kps, _cam(g["K"], g["D_" + name]))[0]
+    assert np.array_equal(np.stack([un["x"], un["y"]], 1), g["out_" + name], equal_nan=True)
+    assert np.array_equal(un["size"], kps[:, 2]) and np.array_equal(un["octave"].view(np.float32), kps[:, 5])
+
+
+def test_undistort_live_cv2(port):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    pts = np.stack([rng.uniform(-20, 1300, 50000), rng.uniform(-20, 740, 50000)], 1).astype(np.float32)
+    K = np.array([[718.856, 0, 607.1928], [0, 718.2, 185.2157], [0, 0, 1]], np.float32)
+    D = np.array([-0.3, 0.12, 0.0007, -0.0003, -0.02], np.float32)
+    kps = np.zeros((len(pts), 7), np.float32); kps[:, :2] = pts
+    un = port.frame_finish(kps, _cam(K, D, bounds=(0.0, 1280.0, 0.0, 720.0)))[0]
+    ref = cv2.undistortPoints(pts.reshape(-1, 1, 2).copy(), K, D, None, K).reshape(-1, 2)
+    assert np.array_equal(np.stack([un["x"], un["y"]], 1), ref, equal_nan=True)
+
+
+def test_frame_finish_depth_and_grid(port):
+    """findDepth (frame.cpp:108-133) and the grid on the UNDISTORTED points (frame.cpp:72-89), restated in numpy."""
+    rng = np.random.default_rng(9)
+    kps, _ = port.extract(synth.make_frame(11))
+    depth = rng.uniform(0.3, 8.0, (480, 640)).astype(np.float32)
+    depth[rng.random((480, 640)) < 0.2] = 0.0
+    K = np.array([[517.3, 0, 318.6], [0, 516.5, 255.3], [0, 0, 1]], np.float32)
+    for D in ([0.2624, -0.9531, -0.0054, 0.0026, 1.1633], [0.0, 0.0, 0.0, 0.0]):
+        cam = _cam(K, np.array(D, np.float32))
+        un, ur, dp, start, ids = port.frame_finish(kps, cam, depth[:, :])
+        if D[0] == 0.0:
+            assert np.array_equal(un, kps)                                          # frame.cpp:41-45
+        d = depth[kps["y"].astype(np.int32), kps["x"].astype(np.int32)]
+        pos = d > 0
+        assert np.array_equal(dp, np.where(pos, d, np.float32(-1)))
+        exp_ur = np.where(pos, un["x"] - np.float32(cam["bf"]) / np.where(pos, d, np.float32(1)), np.float32(-1)).astype(np.float32)
+        assert np.array_equal(ur, exp_ur)
+        s2, i2 = port.grid_build(un, *cam["bounds"])
+        assert np.array_equal(start, s2) and np.array_equal(ids, i2)

@@ -55,6 +55,12 @@ class _TriSide(C.Structure):
     _fields_ = [("side", _BowSide), ("kps", C.c_void_p), ("uright", C.c_void_p)]
 
 
+class _Camera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("dist", C.c_float * 8),
+                ("ndist", C.c_int), ("bf", C.c_float), ("xmin", C.c_float), ("xmax", C.c_float), ("ymin", C.c_float),
+                ("ymax", C.c_float)]
+
+
 def load_library():
     """Load libvoslam_b200.so.  Raises OrbError if it has not been built (no fallback)."""
     global _lib
@@ -101,6 +107,8 @@ def load_library():
     L.orbx_medoid_descriptors.argtypes = [vp, vp, i32, vp, i32]
     L.orbx_search_by_projection_reloc.argtypes = [vp, vp, f32, f32, i32, vp, vp, i32]
     L.orbx_search_by_projection_sim3.argtypes = [vp, vp, i32, vp, vp, i32]
+    L.orbx_frame_finish.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, sz, sz, vp, vp, vp, vp, vp, i32]
+    L.orbx_frame_finish_device.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, sz, sz, vp, vp, vp, vp, vp, i32, vp]
     _lib = L
     return L
 
@@ -289,6 +297,41 @@ def grid_build(kps, bounds, device=0):
     _check(load_library().orbx_grid_build(_p(kps), len(kps), bounds[0], bounds[1], bounds[2], bounds[3], _p(start), _p(ids),
                                           device))
     return start, ids[:start[-1]].copy()
+
+
+def camera(fx, fy, cx, cy, dist=(), bf=0.0, bounds=(0.0, 640.0, 0.0, 480.0)):
+    """Camera constants of camera.cpp:10-48 as the C struct orbx_camera."""
+    c = _Camera()
+    c.fx, c.fy, c.cx, c.cy, c.bf = fx, fy, cx, cy, bf
+    dist = list(dist)
+    if len(dist) > 8:
+        raise OrbError("at most 8 distortion coefficients (k1 k2 p1 p2 k3 k4 k5 k6)")
+    for i, v in enumerate(dist):
+        c.dist[i] = v
+    c.ndist = len(dist)
+    c.xmin, c.xmax, c.ymin, c.ymax = bounds
+    return c
+
+
+def frame_finish(kps, counts, cam, depth=None, device=0):
+    """Frame::undistortKeyPoints + findDepth + assignFeaturesToGrid (frame.cpp:36-133) for a batch of frames.
+
+    kps [F, cap] (KP_DTYPE) and counts [F] as returned by the batch extractor; depth [F, H, W] float32 or None.
+    Returns (unkps [F, cap], uright [F, cap], depth [F, cap], cell_start [F, 64*48+1], ids [F, cap])."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    if kps.ndim == 1:
+        kps = kps[None]
+    F, cap = kps.shape
+    counts = np.ascontiguousarray(counts, np.int32).reshape(F)
+    un = np.zeros((F, cap), KP_DTYPE); ur = np.zeros((F, cap), np.float32); dp = np.zeros((F, cap), np.float32)
+    start = np.zeros((F, 64 * 48 + 1), np.int32); ids = np.zeros((F, cap), np.int32)
+    W = H = 0; rs = fs = 0; dptr = None
+    if depth is not None:
+        depth = np.ascontiguousarray(depth, np.float32).reshape(F, *depth.shape[-2:])
+        H, W = depth.shape[1:]; rs, fs = depth.strides[1], depth.strides[0]; dptr = _p(depth)
+    _check(load_library().orbx_frame_finish(C.byref(cam), _p(kps), _p(counts), F, cap, dptr, W, H, rs, fs, _p(un), _p(ur), _p(dp),
+                                            _p(start), _p(ids), device))
+    return un, ur, dp, start, ids
 
 
 class Matcher:
