@@ -452,6 +452,7 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
   __shared__ __align__(8) uint64_t tmaBar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = blockIdx.x, f = blockIdx.y;
+  const int keyBase = __ldg(B.slotKeyBase + slot);        // needed only by the emission: fetched now, off the critical path
   int l = 0;
   while (l + 1 < G.nlevels && slot >= G.L[l + 1].slot0) ++l;
   const LevelGeom& L = G.L[l];
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
   __syncthreads();
   int off = 0, total = 0;
   for (int w = 0; w < kWarpCells; ++w) { const int c = cellOut[w]; if (w < warp) off += c; total += c; }
-  uint32_t* out = B.slotKeys + (size_t)f * G.slotKeysPerFrame + __ldg(B.slotKeyBase + slot);
+  uint32_t* out = B.slotKeys + (size_t)f * G.slotKeysPerFrame + keyBase;
   for (int k = lane; k < S; k += 32) {
     const uint32_t key = surv[k];
     int rank = 0;
@@ -950,7 +951,7 @@ __device__ __forceinline__ uint32_t blur_h(uint32_t w0, uint32_t w1) {       // 
 __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geom G, const Bufs B) {
   // One CTA = one 64-pixel-wide column strip of one level of one frame; it walks down the strip in 26-row tiles so that
   // the level lookup, pointers and alignment checks are paid once per strip instead of once per tile.
-  __shared__ __align__(16) uint8_t tin[kBlurTH + 6][kBlurInW];
+  __shared__ __align__(16) uint8_t tin[2][kBlurTH + 6][kBlurInW];           // double buffered: tile ty+1 streams in (cp.async) under tile ty's math
   __shared__ __align__(16) uint32_t hpair[(kBlurTH + 6) / 2][kBlurTW];      // rows 2p (low half) and 2p+1 (high half) of the horizontal pass
   const int tid = threadIdx.x, f = blockIdx.y;
   int l = 0;
@@ -974,30 +975,38 @@ __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geom 
     gxw[k] = x0 - 4 + 4 * w;
     fastw[k] = aligned && w < WPR && gxw[k] >= 0 && gxw[k] + 3 < W;
   }
-  for (int ty = 0; ty < tilesY; ++ty) {
-    const int y0 = ty * kBlurTH;
-    // ---- stage 32 x 72 input bytes as 32-bit words (rows resolved with BORDER_REFLECT_101 once per thread)
-    {
-      const int sy = reflect101(min(y0 + lr - 3, H + 2), H);
-      const uint8_t* row = src + (size_t)sy * pitch;
-      uint32_t* trow = reinterpret_cast<uint32_t*>(&tin[lr][0]);
+  // stage 32 x 72 input bytes of tile ty as 32-bit words (rows resolved with BORDER_REFLECT_101 once per thread): interior
+  // words by cp.async straight into shared memory, words that touch the left/right border assembled from reflected bytes
+  auto stage = [&](int buf, int ty) {
+    const int sy = reflect101(min(ty * kBlurTH + lr - 3, H + 2), H);
+    const uint8_t* row = src + (size_t)sy * pitch;
+    uint32_t* trow = reinterpret_cast<uint32_t*>(&tin[buf][lr][0]);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int w = wb + 8 * k;
-        if (w >= WPR) continue;
-        uint32_t v;
-        if (fastw[k]) {
-          v = __ldg(reinterpret_cast<const uint32_t*>(row + gxw[k]));
-        } else {
-          v = 0;
+    for (int k = 0; k < 3; ++k) {
+      const int w = wb + 8 * k;
+      if (w >= WPR) continue;
+      if (fastw[k]) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(trow + w)), "l"(row + gxw[k]) : "memory");
+      } else {
+        uint32_t v = 0;
 #pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            const int sx = reflect101(min(max(gxw[k] + bb, -3), W + 2), W);
-            v |= (uint32_t)__ldg(row + sx) << (8 * bb);
-          }
+        for (int bb = 0; bb < 4; ++bb) {
+          const int sx = reflect101(min(max(gxw[k] + bb, -3), W + 2), W);
+          v |= (uint32_t)__ldg(row + sx) << (8 * bb);
         }
         trow[w] = v;
       }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0, 0);
+  for (int ty = 0; ty < tilesY; ++ty) {
+    const int y0 = ty * kBlurTH, buf = ty & 1;
+    if (ty + 1 < tilesY) {
+      stage(buf ^ 1, ty + 1);     // its previous contents were last read before the second barrier of iteration ty-1
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     // ---- horizontal pass: one thread = 4 adjacent columns of 2 adjacent rows; exact in u16 (max 255*256)
@@ -1005,7 +1014,7 @@ __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geom 
       uint32_t o[2][4];
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(&tin[2 * hrp + rr][4 * hq]);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(&tin[buf][2 * hrp + rr][4 * hq]);
         const uint32_t a = wp[0], b = wp[1], c = wp[2];   // bytes j = 0..11 <-> image x0-4+4q+j; output k uses bytes k+1..k+7
         o[rr][0] = blur_h(__funnelshift_r(a, b, 8), __funnelshift_r(b, c, 8));
         o[rr][1] = blur_h(__funnelshift_r(a, b, 16), __funnelshift_r(b, c, 16));
@@ -1050,8 +1059,8 @@ __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geom 
         else for (int k = 0; x + k < W; ++k) d[k] = (uint8_t)(packed >> (8 * k));
       }
     }
-    // the next tile's staging writes tin (last read before the second barrier) and its horizontal pass writes hpair
-    // only after the next barrier, which every thread reaches after finishing this vertical pass
+    // the next iteration's horizontal pass writes hpair only after its first barrier, which every thread reaches after
+    // finishing this vertical pass
   }
 }
 
@@ -1117,22 +1126,35 @@ __device__ __forceinline__ void glibc_sincosf(float y, float& s_out, float& c_ou
 }
 
 constexpr int kPatchRowsU = 31, kPatchPitchU = 44;   // unblurred 31x31 patch rows, 44-byte pitch (11 words: conflict-free rows)
-constexpr int kPatchRowsB = 37, kPatchPitchB = 52;   // blurred 37x37 patch (+-18), 52-byte pitch (13 words)
-constexpr int kPatchBytes = kPatchRowsU * kPatchPitchU + kPatchRowsB * kPatchPitchB;   // 3288 B per warp
+constexpr int kPatchRowsB = 37, kPatchPitchB = 56;   // blurred 37x37 patch (+-18), 56-byte pitch (14 words, 8-byte aligned rows)
+constexpr int kPatchBytes = kPatchRowsU * kPatchPitchU + kPatchRowsB * kPatchPitchB;   // 3436 B per warp
 
-// Stage rows [y-R, y+R] x columns [x-R, x+R] of an image into shared memory (one warp), as aligned 32-bit words when the
-// image allows it.  Returns the column offset `ox` such that patch(r, c) = dst[r*P + ox + c], c = 0 <-> image column x-R.
-template <int R, int P>
+// Stage rows [y-R, y+R] x columns [x-R, x+R] of an image into shared memory (one warp).  Returns the column offset `ox`
+// such that patch(r, c) = dst[r*P + ox + c], c = 0 <-> image column x-R.  When the image is CW-byte aligned (CW = 4 or
+// 8) the rows are fetched as aligned CW-byte pieces with cp.async (LDGSTS): no register round trip, so all copies of
+// both patches are in flight at once and the warp waits once (cp_async_wait_all) instead of once per load.  Lanes
+// map to (row-in-group, piece) and step down by whole row groups: no per-copy index arithmetic.
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int R, int P, int CW>
 __device__ __forceinline__ int stage_patch(uint8_t* dst, const uint8_t* img, int pitch, int x, int y, int lane) {
   constexpr int ROWS = 2 * R + 1;
   const uint8_t* base = img + (size_t)(y - R) * pitch + (x - R);
-  if ((((uintptr_t)img | (uintptr_t)pitch) & 3) == 0) {
-    const int ox = (int)((uintptr_t)base & 3);
-    constexpr int WPR = (ROWS + 3 + 3) / 4;          // words per row covering ox + ROWS bytes
-    const uint8_t* abase = base - ox;
-    for (int i = lane; i < ROWS * WPR; i += 32) {
-      const int r = i / WPR, w = i - r * WPR;
-      *reinterpret_cast<uint32_t*>(dst + r * P + 4 * w) = __ldg(reinterpret_cast<const uint32_t*>(abase + (size_t)r * pitch) + w);
+  if ((((uintptr_t)img | (uintptr_t)pitch) & (CW - 1)) == 0) {
+    const int ox = (int)((uintptr_t)base & (CW - 1));
+    constexpr int PPR = (ROWS + CW - 1 + CW - 1) / CW;          // pieces per row covering ox + ROWS bytes
+    constexpr int RPG = 32 / PPR;                               // rows per group of lanes
+    static_assert(PPR * CW <= P && P % CW == 0, "patch pitch");
+    const int rs = lane / PPR, w = lane - rs * PPR;
+    if (rs < RPG) {
+      const uint8_t* src = base - ox + (size_t)rs * pitch + CW * w;
+      uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + rs * P + CW * w);
+#pragma unroll
+      for (int r = rs; r < ROWS + RPG - 1; r += RPG) {
+        if (r < ROWS) asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src), "n"(CW) : "memory");
+        src += (size_t)RPG * pitch;
+        d += RPG * P;
+      }
     }
     return ox;
   }
@@ -1146,7 +1168,8 @@ __device__ __forceinline__ int stage_patch(uint8_t* dst, const uint8_t* img, int
 __global__ void __launch_bounds__(256) orient_desc_kernel(const __grid_constant__ Geom G, const Bufs B, orbx_keypoint* __restrict__ kps_out,
                                                           uint8_t* __restrict__ desc_out, int cap,
                                                           int32_t* __restrict__ counts_out, int frame0) {
-  __shared__ __align__(16) uint8_t patches[8][kPatchBytes + 8];
+  __shared__ __align__(16) uint8_t patches[8][kPatchBytes + 4];   // per warp: blurred patch (8-byte aligned rows) then the unblurred one
+  static_assert((kPatchBytes + 4) % 8 == 0 && (kPatchRowsB * kPatchPitchB) % 8 == 0, "patch alignment");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slotIdx = blockIdx.x * 8 + warp;   // index into the per-frame selected array
   const int f = blockIdx.y;
@@ -1171,10 +1194,11 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(const __grid_constant_
   const int x = key_x(key) + kMinBorder, y = key_y(key) + kMinBorder;   // (ORBextractor.cpp:851-852)
   int pitch;
   const uint8_t* img = level_ptr(G, B, l, f, pitch);
-  uint8_t* pu = patches[warp];
-  uint8_t* pb = pu + kPatchRowsU * kPatchPitchU;
-  const int oxu = stage_patch<15, kPatchPitchU>(pu, img, pitch, x, y, lane);
-  const int oxb = stage_patch<18, kPatchPitchB>(pb, B.blur + L.blurOff + (size_t)f * L.h * L.bpitch, L.bpitch, x, y, lane);
+  uint8_t* pb = patches[warp];
+  uint8_t* pu = pb + kPatchRowsB * kPatchPitchB;
+  const int oxu = stage_patch<15, kPatchPitchU, 4>(pu, img, pitch, x, y, lane);
+  const int oxb = stage_patch<18, kPatchPitchB, 8>(pb, B.blur + L.blurOff + (size_t)f * L.h * L.bpitch, L.bpitch, x, y, lane);
+  cp_async_wait_all();
   __syncwarp();
 
   // ---- moments over the radius-15 disc: lane <-> row v = lane-15 --------------------------------------
