@@ -147,7 +147,7 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
   const int nl = h->p.nlevels;
   G.nlevels = nl; G.W = W; G.H = H; G.iniTh = h->p.ini_th_fast; G.minTh = h->p.min_th_fast;
   size_t pyrBytes = 0, blurBytes = 0;
-  int slot = 0, keyBase = 0, selBase = 0, blurTile = 0, slotKeys = 0;
+  int slot = 0, keyBase = 0, selBase = 0, blurTile = 0, bwTile = 0, slotKeys = 0;
   std::vector<int> slotKeyBase;
   G.nodeCap = 0; G.maxSlotsPerLevel = 0; G.fastTileW = 0; G.fastTileH = 0;
   for (int l = 0; l < nl; ++l) {
@@ -195,6 +195,8 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
     L.blurOff = blurBytes; blurBytes += (size_t)chunk * L.h * L.bpitch;
     L.blurTilesX = (L.w + 63) / 64; L.blurTilesY = (L.h + 25) / 26;   // kBlurTW x kBlurTH of orb_kernels.cu
     L.blurTile0 = blurTile; blurTile += L.blurTilesX;      // one CTA per 64-px column strip
+    L.bwTilesX = (L.w + 63) / 64; L.bwTilesY = (L.h + 207) / 208;     // kBwTileH of orb_kernels.cu
+    L.bwTile0 = bwTile; bwTile += L.bwTilesX * L.bwTilesY;
     L.scale = h->scale[l];
     L.kpSize = (float)(int)(31 * h->scale[l]);             // :845
     G.fastTileW = std::max(G.fastTileW, align_up(std::min(kCellsPerCta, L.nCols) * L.wCell + 6 + 15, 16));
@@ -206,6 +208,7 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
   slotKeyBase.push_back(slotKeys);
   G.totalSlots = slot; G.slotKeysPerFrame = slotKeys; G.keysPerFrame = keyBase; G.selPerFrame = selBase;
   G.blurTiles = blurTile;
+  G.bwTiles = bwTile;
   if (G.nodeCap > 60000) { set_error("nfeatures per level too large"); return ORBX_ERR_ARG; }
   if (fast_smem_bytes(G) > 200 * 1024 || octree_smem_bytes(G) > 200 * 1024) { set_error("shape needs too much shared memory"); return ORBX_ERR_SHAPE; }
 

@@ -35,6 +35,7 @@ struct LevelGeom {
   size_t blurOff;
   int blurTile0;           // first blur tile of this level in the fused blur launch
   int blurTilesX, blurTilesY;
+  int bwTile0, bwTilesX, bwTilesY;   // register-blocked blur: CTAs of 64 columns x 208 rows
   float scale;             // mvScaleFactor[level]
   float kpSize;            // (int)(31*scale)                          (:845)
 };
@@ -50,6 +51,7 @@ struct Geom {
   int nodeCap;             // max nodes of any level's quadtree
   int maxSlotsPerLevel;
   int blurTiles;
+  int bwTiles;
   int fastTileW, fastTileH;  // smem tile extents of the FAST kernel (pitch is a multiple of 16)
   int fastSurvCap;           // largest slot capacity (NMS survivors of one CTA)
   int fastCellPix, fastCellQuads, fastCellSurv;   // per-cell maxima (pixels, 4-pixel quads, NMS survivors), 16-byte rounded

@@ -1064,6 +1064,142 @@ __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geom 
   }
 }
 
+// ---- register-blocked variant (the default): no shared memory, no barriers.  One thread owns 4 adjacent columns and
+// walks down kBwRows output rows: per input row pair it does the horizontal pass once (3 aligned words -> 4 pixels x 2
+// rows, dp4a) and keeps the last four pair results (u16x2 per column) in registers; every step then emits two output
+// rows with dp2a.  All index arithmetic, table lookups and barriers of the tiled kernel are paid once per 26 rows
+// instead of once per row pair (31 -> ~12 thread instructions per pixel).  Same arithmetic, bit for bit.
+constexpr int kBwRows = 26;                        // output rows per thread (+6 halo rows = 16 input row pairs)
+constexpr int kBwPairs = (kBwRows + 6) / 2;
+constexpr int kBwSegs = 8;                         // vertical segments per CTA: 4 warps x 2 half-warps
+constexpr int kBwTileH = kBwRows * kBwSegs;        // 208 output rows per CTA, 64 columns
+
+// Row fetch of the register-blocked blur: the 12 bytes x = 4q-4 .. 4q+7 of one (already row-reflected) image row as three
+// words.  MODE 0: interior quads, three aligned loads.  MODE 1: quads whose window crosses the left/right image border:
+// three loads at clamped word indices + PRMT gathers with per-thread selectors (computed once per thread, the border
+// pattern is the same for every row) that apply BORDER_REFLECT_101.  MODE 2: rows that are not 4-byte aligned (a caller
+// image with an odd stride): reflected byte loads, out of line.
+struct BlurEdge { uint32_t s1[3], s2[3], m[3]; int w0, w2; };
+
+__device__ __forceinline__ BlurEdge blur_edge_selectors(int q, int W) {
+  BlurEdge E;
+  const int lastw = (W - 1) >> 2;
+  E.w0 = max(q - 1, 0); E.w2 = min(q + 1, lastw);
+  const int wk[3] = {E.w0, q, E.w2};
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    uint32_t s1 = 0, s2 = 0, m = 0;
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      const int x = reflect101(min(max(4 * q - 4 + 4 * v + bb, -3), W + 2), W);
+      int idx = 0;                                   // position in the 12-byte pool (words w0, q, w2); 0 if never needed
+      if ((x >> 2) == wk[0]) idx = (x & 3);
+      else if ((x >> 2) == wk[1]) idx = 4 + (x & 3);
+      else if ((x >> 2) == wk[2]) idx = 8 + (x & 3);
+      if (idx < 8) { s1 |= (uint32_t)idx << (4 * bb); m |= 0xFFu << (8 * bb); }
+      else s2 |= (uint32_t)(idx - 4) << (4 * bb);
+    }
+    E.s1[v] = s1; E.s2[v] = s2; E.m[v] = m;
+  }
+  return E;
+}
+
+__device__ __noinline__ void blur_fetch_bytes(const uint8_t* __restrict__ row, int q, int W, uint32_t& a, uint32_t& b, uint32_t& c) {
+  uint32_t v[3] = {0u, 0u, 0u};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      const int sx = reflect101(min(max(4 * q - 4 + 4 * k + bb, -3), W + 2), W);
+      v[k] |= (uint32_t)__ldg(row + sx) << (8 * bb);
+    }
+  a = v[0]; b = v[1]; c = v[2];
+}
+
+template <int MODE>
+__device__ __forceinline__ void blur_fetch(const uint8_t* __restrict__ row, int q, int W, const BlurEdge& E, uint32_t& a, uint32_t& b, uint32_t& c) {
+  if (MODE == 0) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(row) + q;
+    a = __ldg(w - 1); b = __ldg(w); c = __ldg(w + 1);
+  } else if (MODE == 1) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(row);
+    const uint32_t p0 = __ldg(w + E.w0), p1 = __ldg(w + q), p2 = __ldg(w + E.w2);
+    a = (__byte_perm(p0, p1, E.s1[0]) & E.m[0]) | (__byte_perm(p1, p2, E.s2[0]) & ~E.m[0]);
+    b = (__byte_perm(p0, p1, E.s1[1]) & E.m[1]) | (__byte_perm(p1, p2, E.s2[1]) & ~E.m[1]);
+    c = (__byte_perm(p0, p1, E.s1[2]) & E.m[2]) | (__byte_perm(p1, p2, E.s2[2]) & ~E.m[2]);
+  } else {
+    blur_fetch_bytes(row, q, W, a, b, c);
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void blur_walk_body(const uint8_t* __restrict__ src, int pitch, int W, int H, int q, int y0,
+                                               uint8_t* __restrict__ dst, int bpitch) {
+  constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;
+  constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);
+  BlurEdge E;
+  if (MODE == 1) E = blur_edge_selectors(q, W);
+  uint32_t ring[4][4];                                             // [pair & 3][column]: row 2p low half, row 2p+1 high half
+  static_assert(kBwPairs % 4 == 0, "ring period");
+#pragma unroll 1
+  for (int pg = 0; pg < kBwPairs / 4; ++pg)
+#pragma unroll
+  for (int pi = 0; pi < 4; ++pi) {
+    const int p = pg * 4 + pi;
+    uint32_t o[2][4];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int sy = reflect101(min(y0 - 3 + 2 * p + rr, H + 2), H);
+      uint32_t a, b, c;
+      blur_fetch<MODE>(src + (size_t)sy * pitch, q, W, E, a, b, c);
+      o[rr][0] = blur_h(__funnelshift_r(a, b, 8), __funnelshift_r(b, c, 8));
+      o[rr][1] = blur_h(__funnelshift_r(a, b, 16), __funnelshift_r(b, c, 16));
+      o[rr][2] = blur_h(__funnelshift_r(a, b, 24), __funnelshift_r(b, c, 24));
+      o[rr][3] = blur_h(b, c);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ring[pi][k] = o[0][k] | (o[1][k] << 16);
+    if (pg > 0 || pi == 3) {
+      const int g = p - 3;                                         // output rows y0+2g (even taps) and y0+2g+1 (odd taps)
+      uint32_t e[4], d[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t c0 = ring[(pi + 1) & 3][k], c1 = ring[(pi + 2) & 3][k], c2 = ring[(pi + 3) & 3][k], c3 = ring[pi][k];
+        e[k] = __dp2a_lo(c3, E3, __dp2a_lo(c2, E2, __dp2a_lo(c1, E1, __dp2a_lo(c0, E0, 32768u))));
+        d[k] = __dp2a_lo(c3, O3, __dp2a_lo(c2, O2, __dp2a_lo(c1, O1, __dp2a_lo(c0, O0, 32768u))));
+      }
+      // result = bits 16..23 of each accumulator (<= 255): gather byte 2 of four registers into one word
+      const uint32_t ev = __byte_perm(__byte_perm(e[0], e[1], 0x0062), __byte_perm(e[2], e[3], 0x0062), 0x5410);
+      const uint32_t od = __byte_perm(__byte_perm(d[0], d[1], 0x0062), __byte_perm(d[2], d[3], 0x0062), 0x5410);
+      const int y = y0 + 2 * g;
+      if (y < H) *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * g) * bpitch) = ev;          // bpitch is a multiple of 64: the
+      if (y + 1 < H) *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * g + 1) * bpitch) = od;  // columns >= W are padding
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, 8) blur_walk_kernel(const __grid_constant__ Geom G, const Bufs B) {
+  const int tid = threadIdx.x, f = blockIdx.y;
+  int l = 0;
+  while (l + 1 < G.nlevels && (int)blockIdx.x >= G.L[l + 1].bwTile0) ++l;
+  const LevelGeom& L = G.L[l];
+  const int t = blockIdx.x - L.bwTile0;
+  const int ty = t / L.bwTilesX, tx = t - ty * L.bwTilesX;
+  const int W = L.w, H = L.h, bpitch = L.bpitch;
+  const int q = tx * 16 + (tid & 15);                              // column quad
+  const int y0 = ty * kBwTileH + (tid >> 4) * kBwRows;             // first output row of this thread
+  const bool live = 4 * q < W && y0 < H;
+  int pitch;
+  const uint8_t* src = level_ptr(G, B, l, f, pitch);
+  uint8_t* dst = B.blur + L.blurOff + (size_t)f * H * bpitch + (size_t)y0 * bpitch + 4 * q;
+  const bool unaligned = (((uintptr_t)src | (uintptr_t)pitch) & 3) != 0;                 // uniform per level
+  const bool edge = __any_sync(0xffffffffu, live && (q == 0 || 4 * q + 7 >= W));          // uniform per warp
+  if (!live) return;
+  if (unaligned) blur_walk_body<2>(src, pitch, W, H, q, y0, dst, bpitch);
+  else if (edge) blur_walk_body<1>(src, pitch, W, H, q, y0, dst, bpitch);
+  else blur_walk_body<0>(src, pitch, W, H, q, y0, dst, bpitch);
+}
+
 // ======================================================================================================
 // K4+K6  IC_Angle (ORBextractor.cpp:79-107) + rotated BRIEF (ORBextractor.cpp:110-151) + output assembly
 // (ORBextractor.cpp:845-855, 1085-1111).  One warp per selected keypoint: lanes = patch rows for the
@@ -1300,7 +1436,10 @@ void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
   octree_kernel<<<dim3(G.nlevels, nframes), kOctThreads, octree_smem_bytes(G), st>>>(G, B);
 }
 void launch_blur(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
-  blur_kernel<<<dim3(G.blurTiles, nframes), 256, 0, st>>>(G, B);
+  // default: the register-blocked kernel; ORBX_BLUR_WALK=0 selects the shared-memory tile kernel for A/B runs
+  static const bool walk = !(getenv("ORBX_BLUR_WALK") && atoi(getenv("ORBX_BLUR_WALK")) == 0);
+  if (walk) blur_walk_kernel<<<dim3(G.bwTiles, nframes), 128, 0, st>>>(G, B);
+  else blur_kernel<<<dim3(G.blurTiles, nframes), 256, 0, st>>>(G, B);
 }
 void launch_orient_desc(const Geom& G, const Bufs& B, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
                         int frame0, int nframes, cudaStream_t st) {
