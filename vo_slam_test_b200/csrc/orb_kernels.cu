@@ -1132,49 +1132,64 @@ __device__ __forceinline__ void blur_fetch(const uint8_t* __restrict__ row, int 
   }
 }
 
-template <int MODE>
+// VEDGE = false: every input row y0-3 .. y0+kBwRows+2 of the thread lies inside the image, rows are reached by pointer
+// increments; VEDGE = true: rows are resolved with BORDER_REFLECT_101 one by one (top/bottom segments).
+template <int MODE, bool VEDGE>
 __device__ __forceinline__ void blur_walk_body(const uint8_t* __restrict__ src, int pitch, int W, int H, int q, int y0,
                                                uint8_t* __restrict__ dst, int bpitch) {
   constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;
   constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);
   BlurEdge E;
   if (MODE == 1) E = blur_edge_selectors(q, W);
+  const uint8_t* rowp = src + (ptrdiff_t)(y0 - 3) * pitch;          // VEDGE == false only
+  const int rowsLeft = H - y0;                                      // output row y0 + k exists iff k < rowsLeft
   uint32_t ring[4][4];                                             // [pair & 3][column]: row 2p low half, row 2p+1 high half
   static_assert(kBwPairs % 4 == 0, "ring period");
 #pragma unroll 1
-  for (int pg = 0; pg < kBwPairs / 4; ++pg)
+  for (int pg = 0; pg < kBwPairs / 4; ++pg) {
 #pragma unroll
-  for (int pi = 0; pi < 4; ++pi) {
-    const int p = pg * 4 + pi;
-    uint32_t o[2][4];
+    for (int pi = 0; pi < 4; ++pi) {
+      const int p = pg * 4 + pi;
+      uint32_t o[2][4];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int sy = reflect101(min(y0 - 3 + 2 * p + rr, H + 2), H);
-      uint32_t a, b, c;
-      blur_fetch<MODE>(src + (size_t)sy * pitch, q, W, E, a, b, c);
-      o[rr][0] = blur_h(__funnelshift_r(a, b, 8), __funnelshift_r(b, c, 8));
-      o[rr][1] = blur_h(__funnelshift_r(a, b, 16), __funnelshift_r(b, c, 16));
-      o[rr][2] = blur_h(__funnelshift_r(a, b, 24), __funnelshift_r(b, c, 24));
-      o[rr][3] = blur_h(b, c);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) ring[pi][k] = o[0][k] | (o[1][k] << 16);
-    if (pg > 0 || pi == 3) {
-      const int g = p - 3;                                         // output rows y0+2g (even taps) and y0+2g+1 (odd taps)
-      uint32_t e[4], d[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t c0 = ring[(pi + 1) & 3][k], c1 = ring[(pi + 2) & 3][k], c2 = ring[(pi + 3) & 3][k], c3 = ring[pi][k];
-        e[k] = __dp2a_lo(c3, E3, __dp2a_lo(c2, E2, __dp2a_lo(c1, E1, __dp2a_lo(c0, E0, 32768u))));
-        d[k] = __dp2a_lo(c3, O3, __dp2a_lo(c2, O2, __dp2a_lo(c1, O1, __dp2a_lo(c0, O0, 32768u))));
+      for (int rr = 0; rr < 2; ++rr) {
+        const uint8_t* row;
+        if (VEDGE) row = src + (size_t)reflect101(min(y0 - 3 + 2 * p + rr, H + 2), H) * pitch;
+        else row = rowp + (2 * pi + rr) * pitch;
+        uint32_t a, b, c;
+        blur_fetch<MODE>(row, q, W, E, a, b, c);
+        o[rr][0] = blur_h(__funnelshift_r(a, b, 8), __funnelshift_r(b, c, 8));
+        o[rr][1] = blur_h(__funnelshift_r(a, b, 16), __funnelshift_r(b, c, 16));
+        o[rr][2] = blur_h(__funnelshift_r(a, b, 24), __funnelshift_r(b, c, 24));
+        o[rr][3] = blur_h(b, c);
       }
-      // result = bits 16..23 of each accumulator (<= 255): gather byte 2 of four registers into one word
-      const uint32_t ev = __byte_perm(__byte_perm(e[0], e[1], 0x0062), __byte_perm(e[2], e[3], 0x0062), 0x5410);
-      const uint32_t od = __byte_perm(__byte_perm(d[0], d[1], 0x0062), __byte_perm(d[2], d[3], 0x0062), 0x5410);
-      const int y = y0 + 2 * g;
-      if (y < H) *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * g) * bpitch) = ev;          // bpitch is a multiple of 64: the
-      if (y + 1 < H) *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * g + 1) * bpitch) = od;  // columns >= W are padding
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ring[pi][k] = __byte_perm(o[0][k], o[1][k], 0x5410);   // both fit 16 bits
+      if (pg > 0 || pi == 3) {
+        // output rows 2g (even taps) and 2g+1 (odd taps) of the thread, g = p - 3; dst already points at row 2*(4*pg - 3)
+        uint32_t e[4], d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t c0 = ring[(pi + 1) & 3][k], c1 = ring[(pi + 2) & 3][k], c2 = ring[(pi + 3) & 3][k], c3 = ring[pi][k];
+          e[k] = __dp2a_lo(c3, E3, __dp2a_lo(c2, E2, __dp2a_lo(c1, E1, __dp2a_lo(c0, E0, 32768u))));
+          d[k] = __dp2a_lo(c3, O3, __dp2a_lo(c2, O2, __dp2a_lo(c1, O1, __dp2a_lo(c0, O0, 32768u))));
+        }
+        // result = bits 16..23 of each accumulator (<= 255): gather byte 2 of four registers into one word
+        const uint32_t ev = __byte_perm(__byte_perm(e[0], e[1], 0x0062), __byte_perm(e[2], e[3], 0x0062), 0x5410);
+        const uint32_t od = __byte_perm(__byte_perm(d[0], d[1], 0x0062), __byte_perm(d[2], d[3], 0x0062), 0x5410);
+        const int k0 = 2 * (p - 3);
+        uint8_t* d0 = dst + (ptrdiff_t)(2 * pi) * bpitch;           // bpitch is a multiple of 64: columns >= W are padding
+        if (VEDGE) {
+          if (k0 < rowsLeft) *reinterpret_cast<uint32_t*>(d0) = ev;
+          if (k0 + 1 < rowsLeft) *reinterpret_cast<uint32_t*>(d0 + bpitch) = od;
+        } else {
+          *reinterpret_cast<uint32_t*>(d0) = ev;
+          *reinterpret_cast<uint32_t*>(d0 + bpitch) = od;
+        }
+      }
     }
+    rowp += 8 * pitch;
+    dst += (ptrdiff_t)8 * bpitch;
   }
 }
 
@@ -1191,13 +1206,15 @@ __global__ void __launch_bounds__(128, 8) blur_walk_kernel(const __grid_constant
   const bool live = 4 * q < W && y0 < H;
   int pitch;
   const uint8_t* src = level_ptr(G, B, l, f, pitch);
-  uint8_t* dst = B.blur + L.blurOff + (size_t)f * H * bpitch + (size_t)y0 * bpitch + 4 * q;
+  // dst points at output row y0 - 6: the walk advances it by 8 rows per group of 4 pairs and the first group only emits pair 3
+  uint8_t* dst = B.blur + L.blurOff + (size_t)f * H * bpitch + (ptrdiff_t)(y0 - 6) * bpitch + 4 * q;
   const bool unaligned = (((uintptr_t)src | (uintptr_t)pitch) & 3) != 0;                 // uniform per level
   const bool edge = __any_sync(0xffffffffu, live && (q == 0 || 4 * q + 7 >= W));          // uniform per warp
+  const bool vedge = __any_sync(0xffffffffu, live && (y0 < 3 || y0 + kBwRows + 3 > H));   // uniform per warp
   if (!live) return;
-  if (unaligned) blur_walk_body<2>(src, pitch, W, H, q, y0, dst, bpitch);
-  else if (edge) blur_walk_body<1>(src, pitch, W, H, q, y0, dst, bpitch);
-  else blur_walk_body<0>(src, pitch, W, H, q, y0, dst, bpitch);
+  if (unaligned) blur_walk_body<2, true>(src, pitch, W, H, q, y0, dst, bpitch);
+  else if (edge) { if (vedge) blur_walk_body<1, true>(src, pitch, W, H, q, y0, dst, bpitch); else blur_walk_body<1, false>(src, pitch, W, H, q, y0, dst, bpitch); }
+  else { if (vedge) blur_walk_body<0, true>(src, pitch, W, H, q, y0, dst, bpitch); else blur_walk_body<0, false>(src, pitch, W, H, q, y0, dst, bpitch); }
 }
 
 // ======================================================================================================
