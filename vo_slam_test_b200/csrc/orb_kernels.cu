@@ -766,7 +766,7 @@ __device__ __forceinline__ int quadrant_of(const short4 b, int x, int y) {
   return (x < mx ? 0 : 1) | (y < my ? 0 : 2);     // 0:n1 1:n2 2:n3 3:n4   (:521-531)
 }
 
-__global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_constant__ Geom G, const Bufs B) {
+__global__ void __launch_bounds__(kOctThreads, 5) octree_kernel(const __grid_constant__ Geom G, const Bufs B) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, T = kOctThreads;
   const int l = blockIdx.x, f = blockIdx.y;
@@ -1398,19 +1398,18 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(const __grid_constant_
   while (l + 1 < G.nlevels && slotIdx >= G.L[l + 1].selBase) ++l;
   const LevelGeom& L = G.L[l];
   const int i = slotIdx - L.selBase;
-  const int* selCount = B.selCount + (size_t)f * G.nlevels;
-  int before = 0, total = 0;
-  for (int q = 0; q < G.nlevels; ++q) {
-    const int c = selCount[q];
-    if (q < l) before += c;
-    total += c;
-  }
+  // lane q fetches the count of level q while the (possibly unused) key of this slot is already on its way: one global
+  // round trip instead of three dependent ones before the patches can be requested
+  const int cl = lane < G.nlevels ? __ldg(B.selCount + (size_t)f * G.nlevels + lane) : 0;
+  const uint32_t key = __ldg(B.sel + (size_t)f * G.selPerFrame + slotIdx);
+  const int total = __reduce_add_sync(0xffffffffu, cl);
+  const int before = __reduce_add_sync(0xffffffffu, lane < l ? cl : 0);
+  const int cntL = __shfl_sync(0xffffffffu, cl, l);
   if (slotIdx == 0 && lane == 0) counts_out[frame0 + f] = total;
-  if (i >= selCount[l]) return;
+  if (i >= cntL) return;
   const int o = before + i;
   if (o >= cap) return;   // caller buffer smaller than the keypoint count: the count is still reported
 
-  const uint32_t key = B.sel[(size_t)f * G.selPerFrame + slotIdx];
   const int x = key_x(key) + kMinBorder, y = key_y(key) + kMinBorder;   // (ORBextractor.cpp:851-852)
   int pitch;
   const uint8_t* img = level_ptr(G, B, l, f, pitch);
