@@ -44,6 +44,13 @@ struct DevTaps {
 
 using namespace orbx;
 
+namespace orbx {
+int pdl_enabled() {
+  static const int v = getenv("ORBX_PDL") ? atoi(getenv("ORBX_PDL")) : 1;
+  return v;
+}
+}  // namespace orbx
+
 struct orbx_extractor {
   orbx_params p{};
   // reference-constructor tables

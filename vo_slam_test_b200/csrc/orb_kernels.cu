@@ -25,6 +25,7 @@ __device__ __forceinline__ const uint8_t* level_ptr(const Geom& G, const Bufs& B
 __global__ void __launch_bounds__(256) resize_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                                                      size_t sframe, uint8_t* __restrict__ dst, int dw, int dh,
                                                      int dpitch, size_t dframe, ResizeTaps T) {
+  pdl_prologue();
   const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int dy = blockIdx.y * 8 + threadIdx.y;
   if (dx0 >= dw || dy >= dh) return;
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256) resize_kernel(const uint8_t* __restrict__
 __global__ void __launch_bounds__(256) resize4_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                                                       size_t sframe, uint8_t* __restrict__ dst, int dw, int dh,
                                                       int dpitch, size_t dframe, ResizeTaps T) {
+  pdl_prologue();
   const int q = blockIdx.x * 32 + threadIdx.x;
   const int dy = blockIdx.y * 8 + threadIdx.y;
   const int dx0 = q * 4;
@@ -108,6 +110,7 @@ constexpr int kRwRows = 16;
 __global__ void __launch_bounds__(128) resize_walk_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                                                           size_t sframe, uint8_t* __restrict__ dst, int dw, int dh,
                                                           int dpitch, size_t dframe, ResizeTaps T) {
+  pdl_prologue();
   const int q = blockIdx.x * 32 + threadIdx.x;
   const int dy0 = (blockIdx.y * 4 + threadIdx.y) * kRwRows;
   const int dx0 = q * 4;
@@ -279,6 +282,7 @@ __device__ __forceinline__ void fast_best2(const uint8_t* pa, const uint8_t* pb,
 }
 
 __global__ void __launch_bounds__(kFastThreads) fast_kernel(const __grid_constant__ Geom G, const Bufs B, const TmaSet TM) {
+  pdl_prologue();
   // Work-efficient layout: (1) tile staged with 16-byte loads, (2) a cheap 16-pixel-ring rejection test over all
   // pixels that pushes the few survivors into a shared-memory queue, (3) the full arc score and the per-cell NMS run
   // densely over that queue only, (4) survivors are ranked by (cell, row, column) to emit them in the reference order.
@@ -514,6 +518,7 @@ template <int SH>
 __device__ __forceinline__ uint32_t fw_stage_a(const uint8_t* rowm3, int sp, uint32_t kc, bool hiT) { return reject4_a<SH>(rowm3, sp, kc, hiT); }
 
 __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid_constant__ Geom G, const Bufs B, const TmaSet TM) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int cellOut[kWarpCells];
   __shared__ __align__(8) uint64_t tmaBar;
@@ -767,6 +772,7 @@ __device__ __forceinline__ int quadrant_of(const short4 b, int x, int y) {
 }
 
 __global__ void __launch_bounds__(kOctThreads, 5) octree_kernel(const __grid_constant__ Geom G, const Bufs B) {
+  pdl_prologue();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, T = kOctThreads;
   const int l = blockIdx.x, f = blockIdx.y;
@@ -1016,6 +1022,7 @@ __device__ __forceinline__ uint32_t blur_h(uint32_t w0, uint32_t w1) {       // 
 }
 
 __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geom G, const Bufs B) {
+  pdl_prologue();
   // One CTA = one 64-pixel-wide column strip of one level of one frame; it walks down the strip in 26-row tiles so that
   // the level lookup, pointers and alignment checks are paid once per strip instead of once per tile.
   __shared__ __align__(16) uint8_t tin[2][kBlurTH + 6][kBlurInW];           // double buffered: tile ty+1 streams in (cp.async) under tile ty's math
@@ -1261,6 +1268,7 @@ __device__ __forceinline__ void blur_walk_body(const uint8_t* __restrict__ src, 
 }
 
 __global__ void __launch_bounds__(128, 8) blur_walk_kernel(const __grid_constant__ Geom G, const Bufs B) {
+  pdl_prologue();
   const int tid = threadIdx.x, f = blockIdx.y;
   int l = 0;
   while (l + 1 < G.nlevels && (int)blockIdx.x >= G.L[l + 1].bwTile0) ++l;
@@ -1388,6 +1396,7 @@ __device__ __forceinline__ int stage_patch(uint8_t* dst, const uint8_t* img, int
 __global__ void __launch_bounds__(256) orient_desc_kernel(const __grid_constant__ Geom G, const Bufs B, orbx_keypoint* __restrict__ kps_out,
                                                           uint8_t* __restrict__ desc_out, int cap,
                                                           int32_t* __restrict__ counts_out, int frame0) {
+  pdl_prologue();
   __shared__ __align__(16) uint8_t patches[8][kPatchBytes + 4];   // per warp: blurred patch (8-byte aligned rows) then the unblurred one
   static_assert((kPatchBytes + 4) % 8 == 0 && (kPatchRowsB * kPatchPitchB) % 8 == 0, "patch alignment");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1475,11 +1484,11 @@ void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe
   static const bool walk = !(getenv("ORBX_RESIZE_WALK") && atoi(getenv("ORBX_RESIZE_WALK")) == 0);
   if (T.quadOk && aligned && walk) {
     const dim3 wblock(32, 4), wgrid((dw + 127) / 128, (dh + 4 * kRwRows - 1) / (4 * kRwRows), nframes);
-    resize_walk_kernel<<<wgrid, wblock, 0, st>>>(src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
+    launch_chain(pdl_enabled() >= 1, resize_walk_kernel, wgrid, wblock, 0, st, src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
   } else if (T.quadOk && aligned)
-    resize4_kernel<<<grid, block, 0, st>>>(src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
+    launch_chain(pdl_enabled() >= 1, resize4_kernel, grid, block, 0, st, src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
   else
-    resize_kernel<<<grid, block, 0, st>>>(src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
+    launch_chain(pdl_enabled() >= 1, resize_kernel, grid, block, 0, st, src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
 }
 
 size_t fast_warp_smem_bytes(const Geom& G);
@@ -1515,23 +1524,23 @@ static bool use_fast_warp() {
 
 void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st) {
   if (use_fast_warp()) {
-    fast_warp_kernel<<<dim3(G.totalSlots, nframes), 32 * kWarpCells, fast_warp_smem_bytes(G), st>>>(G, B, TM);
+    launch_chain(pdl_enabled() >= 2, fast_warp_kernel, dim3(G.totalSlots, nframes), dim3(32 * kWarpCells), fast_warp_smem_bytes(G), st, G, B, TM);
     return;
   }
-  fast_kernel<<<dim3(G.totalSlots, nframes), kFastThreads, fast_smem_bytes(G), st>>>(G, B, TM);
+  launch_chain(pdl_enabled() >= 2, fast_kernel, dim3(G.totalSlots, nframes), dim3(kFastThreads), fast_smem_bytes(G), st, G, B, TM);
 }
 void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
-  octree_kernel<<<dim3(G.nlevels, nframes), kOctThreads, octree_smem_bytes(G), st>>>(G, B);
+  launch_chain(pdl_enabled() >= 2, octree_kernel, dim3(G.nlevels, nframes), dim3(kOctThreads), octree_smem_bytes(G), st, G, B);
 }
 void launch_blur(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
   // default: the register-blocked kernel; ORBX_BLUR_WALK=0 selects the shared-memory tile kernel for A/B runs
   static const bool walk = !(getenv("ORBX_BLUR_WALK") && atoi(getenv("ORBX_BLUR_WALK")) == 0);
-  if (walk) blur_walk_kernel<<<dim3(G.bwTiles, nframes), 128, 0, st>>>(G, B);
-  else blur_kernel<<<dim3(G.blurTiles, nframes), 256, 0, st>>>(G, B);
+  if (walk) launch_chain(pdl_enabled() >= 2, blur_walk_kernel, dim3(G.bwTiles, nframes), dim3(128), 0, st, G, B);
+  else launch_chain(pdl_enabled() >= 2, blur_kernel, dim3(G.blurTiles, nframes), dim3(256), 0, st, G, B);
 }
 void launch_orient_desc(const Geom& G, const Bufs& B, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
                         int frame0, int nframes, cudaStream_t st) {
-  orient_desc_kernel<<<dim3((G.selPerFrame + 7) / 8, nframes), 256, 0, st>>>(G, B, kps, desc, cap, counts, frame0);
+  launch_chain(pdl_enabled() >= 2, orient_desc_kernel, dim3((G.selPerFrame + 7) / 8, nframes), dim3(256), 0, st, G, B, kps, desc, cap, counts, frame0);
 }
 
 }  // namespace orbx
