@@ -54,6 +54,7 @@ struct Geom {
   int bwTiles;
   int fastTileW, fastTileH;  // smem tile extents of the FAST kernel (pitch is a multiple of 16)
   int fastSurvCap;           // largest slot capacity (NMS survivors of one CTA)
+  int fastScW, fastScH;      // score map of the warp-synchronous FAST kernel: cell interiors only (pitch multiple of 16)
   int fastCellPix, fastCellQuads, fastCellSurv;   // per-cell maxima (pixels, 4-pixel quads, NMS survivors), 16-byte rounded
   LevelGeom L[kMaxLevels];
 };

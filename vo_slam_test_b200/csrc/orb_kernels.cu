@@ -543,13 +543,16 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
   const int sp = G.fastTileW;
   const int tileBytes = G.fastTileH * sp;
   uint8_t* img = smem;
-  uint8_t* sc = smem + tileBytes;
-  // per-warp scratch: queue (u16 per cell pixel), itemq (u16 per quad), surv (u32 per NMS survivor)
-  const int cellPix = G.fastCellPix, cellQuads = G.fastCellQuads, cellSurv = G.fastCellSurv;
-  uint8_t* wbase = sc + tileBytes + (size_t)warp * (2 * cellPix + 2 * cellQuads + 4 * cellSurv);
+  uint8_t* sc = smem + tileBytes;                        // corner strengths of the cell interiors only, pitch scp
+  const int scp = G.fastScW, scBytes = G.fastScW * G.fastScH;
+  // per-warp scratch: queue (u16 per cell pixel) and one region shared by itemq (u16 per quad, dead after stage b) and
+  // surv (u32 per NMS survivor, written after stage b; a retry pass only happens when no survivor was written)
+  const int cellPix = G.fastCellPix;
+  const int shared2 = max(2 * G.fastCellQuads, 4 * G.fastCellSurv);
+  uint8_t* wbase = sc + scBytes + (size_t)warp * (2 * cellPix + shared2);
   uint16_t* queue = (uint16_t*)wbase;
   uint16_t* itemq = queue + cellPix;
-  uint32_t* surv = (uint32_t*)(itemq + cellQuads);
+  uint32_t* surv = (uint32_t*)itemq;
 
   int pitch;
   const uint8_t* lvl = level_ptr(G, B, l, f, pitch);
@@ -585,7 +588,7 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
   }
   {
     uint4* z = reinterpret_cast<uint4*>(sc);
-    for (int i = tid; i < (th * sp) >> 4; i += 32 * kWarpCells) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (ih * scp) >> 4; i += 32 * kWarpCells) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   if (viaTma) {
@@ -605,7 +608,7 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
   const int cw = min(L.wCell, iw - cx0);                  // cell width (<= 0: the cell does not exist in this slot)
   int S = 0;
   const uint8_t* img0 = img + 3 * sp + 3 + ox;
-  uint8_t* sc0 = sc + 3 * sp + 3 + ox;
+  uint8_t* sc0 = sc;                                       // sc0[yi * scp + cx0 + cx]
   if (jj < j1 - j0 && cw > 0) {
     const int nq4 = (cw + 3) >> 2;
     const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nq4 + 1;
@@ -681,8 +684,8 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
           e0 = queue[k0]; e1 = queue[min(k1, nq - 1)];
           const int y0 = e0 >> 8, x0 = e0 & 255, y1 = e1 >> 8, x1 = e1 & 255;
           fast_best2(img0 + y0 * sp + cx0 + x0, img0 + y1 * sp + cx0 + x1, sp, b0, b1);
-          sc0[y0 * sp + cx0 + x0] = (uint8_t)(b0 > t ? b0 : 0);
-          if (k1 < nq) sc0[y1 * sp + cx0 + x1] = (uint8_t)(b1 > t ? b1 : 0);
+          sc0[y0 * scp + cx0 + x0] = (uint8_t)(b0 > t ? b0 : 0);
+          if (k1 < nq) sc0[y1 * scp + cx0 + x1] = (uint8_t)(b1 > t ? b1 : 0);
         }
         const bool c0 = k0 < nq && b0 > t, c1 = k1 < nq && b1 > t;
         const int cnt = (int)c0 + (int)c1;
@@ -704,18 +707,18 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
         if (k < nc) {
           e = queue[k];
           const int yi = e >> 8, cx = e & 255;
-          const uint8_t* s = sc0 + yi * sp + cx0 + cx;
+          const uint8_t* s = sc0 + yi * scp + cx0 + cx;
           const int v = s[0];
           const bool hasL = cx > 0, hasR = cx + 1 < cw, hasU = yi > 0, hasD = yi + 1 < ih;
           keep = true;
-          keep &= !(hasU && hasL && s[-sp - 1] >= v);
-          keep &= !(hasU && s[-sp] >= v);
-          keep &= !(hasU && hasR && s[-sp + 1] >= v);
+          keep &= !(hasU && hasL && s[-scp - 1] >= v);
+          keep &= !(hasU && s[-scp] >= v);
+          keep &= !(hasU && hasR && s[-scp + 1] >= v);
           keep &= !(hasL && s[-1] >= v);
           keep &= !(hasR && s[1] >= v);
-          keep &= !(hasD && hasL && s[sp - 1] >= v);
-          keep &= !(hasD && s[sp] >= v);
-          keep &= !(hasD && hasR && s[sp + 1] >= v);
+          keep &= !(hasD && hasL && s[scp - 1] >= v);
+          keep &= !(hasD && s[scp] >= v);
+          keep &= !(hasD && hasR && s[scp + 1] >= v);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (keep) surv[S + __popc(bal & ((1u << lane) - 1))] = (uint32_t)e;      // yi<<8 | cx : already the (row, col) order key
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
     int rank = 0;
     for (int j = 0; j < S; ++j) rank += surv[j] < key ? 1 : 0;
     const int yi = key >> 8, cx = key & 255;
-    out[off + rank] = pack_key(tx0 + cx0 + cx + 3, ty0 + yi + 3, sc0[yi * sp + cx0 + cx] - 1);
+    out[off + rank] = pack_key(tx0 + cx0 + cx + 3, ty0 + yi + 3, sc0[yi * scp + cx0 + cx] - 1);
   }
   if (tid == 0) *out_count = total;
 }
@@ -1513,7 +1516,8 @@ cudaError_t configure_kernels(const Geom& G) {
 }
 
 size_t fast_warp_smem_bytes(const Geom& G) {
-  return (size_t)2 * G.fastTileW * G.fastTileH + (size_t)kWarpCells * (2 * G.fastCellPix + 2 * G.fastCellQuads + 4 * G.fastCellSurv) + 64;
+  return (size_t)G.fastTileW * G.fastTileH + (size_t)G.fastScW * G.fastScH +
+         (size_t)kWarpCells * (2 * G.fastCellPix + std::max(2 * G.fastCellQuads, 4 * G.fastCellSurv)) + 64;
 }
 
 static bool use_fast_warp() {
