@@ -25,7 +25,7 @@ size_t octree_smem_bytes(const Geom& G);
 void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st);
 void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st);
 void launch_blur(const Geom& G, const Bufs& B, int nframes, cudaStream_t st);
-void launch_orient_desc(const Geom& G, const Bufs& B, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
+void launch_orient_desc(const Geom& G, const Bufs& B, const TmaSet& TM, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
                         int frame0, int nframes, cudaStream_t st);
 
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
@@ -70,7 +70,8 @@ struct orbx_extractor {
   float2* d_pattern = nullptr; int* d_umax = nullptr;
   std::vector<DevTaps> taps;
   TmaSet tma{};              // FAST tile descriptors (levels >= 1 fixed after configure, level 0 per call)
-  CUtensorMap hostMaps[kMaxLevels];   // host copies; d_maps mirrors them in device memory
+  CUtensorMap hostMaps[3 * kMaxLevels];   // host copies; d_maps mirrors them in device memory (layout: TmaSet::map)
+  bool patchU[kMaxLevels] = {}, patchB[kMaxLevels] = {};   // which orientation / descriptor patch maps are valid
   CUtensorMap* d_maps = nullptr;
   EncodeTiledFn encode = nullptr;
   // staging for the host entry points
@@ -105,7 +106,8 @@ void free_workspace(orbx_extractor* h) {
   h->taps.clear();
   h->haveGeom = false; h->chunk = 0;
   h->map0_base = nullptr; h->map0_n = 0;
-  for (int l = 0; l < kMaxLevels; ++l) h->tma.use[l] = 0;
+  for (int l = 0; l < kMaxLevels; ++l) { h->tma.use[l] = 0; h->patchU[l] = h->patchB[l] = false; }
+  h->tma.usePatch = 0;
 }
 
 // cv::resize tap tables for one axis
@@ -124,25 +126,37 @@ void axis_taps(int ssize, int dsize, std::vector<int>& ofs, std::vector<short>& 
   }
 }
 
-// One rank-3 (x bytes, y rows, frame) tiled tensor map over a level; box = the FAST kernel's shared-memory tile.
-bool encode_level_map(orbx_extractor* h, int l, const uint8_t* base, size_t pitch, size_t frameStride, int nframes) {
-  h->tma.use[l] = 0;
+// One rank-3 (x bytes, y rows, frame) tiled tensor map over a w x h x nframes byte image into slot `idx` of d_maps.
+bool encode_map(orbx_extractor* h, int idx, const uint8_t* base, int w, int hgt, size_t pitch, size_t frameStride, int nframes,
+                int boxW, int boxH) {
   if (!h->encode || !h->d_maps || env_int("ORBX_NO_TMA", 0)) return false;
   if ((((uintptr_t)base) | pitch | frameStride) & 15) return false;      // TMA needs 16-byte aligned base and strides
-  const LevelGeom& L = h->G.L[l];
-  if (h->G.fastTileW > 256 || h->G.fastTileH > 256) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)std::max(nframes, 1)};
+  if (boxW > 256 || boxH > 256) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)hgt, (cuuint64_t)std::max(nframes, 1)};
   cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frameStride};
-  cuuint32_t box[3] = {(cuuint32_t)h->G.fastTileW, (cuuint32_t)h->G.fastTileH, 1};
+  cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = h->encode(&h->hostMaps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
+  CUresult r = h->encode(&h->hostMaps[idx], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   // stream-ordered upload on the legacy default stream would serialise; a synchronous copy is fine (rare event)
-  if (cudaMemcpy(h->d_maps + l, &h->hostMaps[l], sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess) return false;
-  h->tma.use[l] = 1;
-  return true;
+  return cudaMemcpy(h->d_maps + idx, &h->hostMaps[idx], sizeof(CUtensorMap), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+void refresh_use_patch(orbx_extractor* h) {
+  int ok = 1;
+  for (int l = 0; l < h->G.nlevels; ++l) ok &= (h->patchU[l] && h->patchB[l]) ? 1 : 0;
+  h->tma.usePatch = ok;
+}
+
+// Descriptors of an UNBLURRED level: the FAST kernel's shared-memory tile and the 48x31 orientation patch.
+bool encode_level_map(orbx_extractor* h, int l, const uint8_t* base, size_t pitch, size_t frameStride, int nframes) {
+  const LevelGeom& L = h->G.L[l];
+  h->tma.use[l] = encode_map(h, l, base, L.w, L.h, pitch, frameStride, nframes, h->G.fastTileW, h->G.fastTileH) ? 1 : 0;
+  h->patchU[l] = encode_map(h, kMaxLevels + l, base, L.w, L.h, pitch, frameStride, nframes, kOdUW, kOdUH);
+  refresh_use_patch(h);
+  return h->tma.use[l] != 0;
 }
 
 // Build the per-size geometry (cell grid, slots, capacities, workspace offsets) and allocate for `chunk` frames.
@@ -284,6 +298,10 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
   h->chunk = chunk;
   for (int l = 1; l < nl; ++l)
     encode_level_map(h, l, h->d_pyr + G.L[l].pyrOff, (size_t)G.L[l].pitch, (size_t)G.L[l].h * G.L[l].pitch, chunk);
+  for (int l = 0; l < nl; ++l)                 // blurred levels: the 64x37 descriptor patch
+    h->patchB[l] = encode_map(h, 2 * kMaxLevels + l, h->d_blur + G.L[l].blurOff, G.L[l].w, G.L[l].h, (size_t)G.L[l].bpitch,
+                              (size_t)G.L[l].h * G.L[l].bpitch, chunk, kOdBW, kOdBH);
+  refresh_use_patch(h);
   return ORBX_OK;
 }
 
@@ -326,7 +344,7 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
   if (ev) cudaEventRecord(ev[3], st);
   launch_blur(G, B, n, st);
   if (ev) cudaEventRecord(ev[4], st);
-  launch_orient_desc(G, B, d_kps, d_desc, cap, d_counts, frame0, n, st);
+  launch_orient_desc(G, B, h->tma, d_kps, d_desc, cap, d_counts, frame0, n, st);
   if (ev) cudaEventRecord(ev[5], st);
   h->launches += (G.nlevels - 1) + 4;
   h->last_img0 = img0; h->last_rowStride = rowStride; h->last_frameStride = frameStride; h->last_frames = n;
@@ -408,7 +426,7 @@ int orbx_create(const orbx_params* p, orbx_handle* out) {
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
       h->encode = (EncodeTiledFn)fn;
-    if (cudaMalloc(&h->d_maps, sizeof(CUtensorMap) * kMaxLevels) != cudaSuccess) h->d_maps = nullptr;
+    if (cudaMalloc(&h->d_maps, sizeof(CUtensorMap) * 3 * kMaxLevels) != cudaSuccess) h->d_maps = nullptr;
     h->tma.map = h->d_maps;
   }
   float2 pat[512];

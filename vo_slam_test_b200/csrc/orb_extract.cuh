@@ -11,7 +11,10 @@ namespace orbx {
 constexpr int kMaxLevels = 16;
 constexpr int kEdge = 19;            // EDGE_THRESHOLD        (ORBextractor.cpp:76)
 constexpr int kMinBorder = 16;       // EDGE_THRESHOLD - 3    (ORBextractor.cpp:780)
-constexpr int kCellsPerCta = 2;      // FAST cells handled by one CTA (one "slot")
+#ifndef ORBX_CELLS_PER_CTA
+#define ORBX_CELLS_PER_CTA 2           // -DORBX_CELLS_PER_CTA=1|2|4 builds A/B variants (tools/build_variants.sh)
+#endif
+constexpr int kCellsPerCta = ORBX_CELLS_PER_CTA;      // FAST cells handled by one CTA (one "slot")
 constexpr int kMaxRoots = 16;
 constexpr int kFastThreads = 128;
 constexpr int kOctThreads = 256;
@@ -81,10 +84,15 @@ struct Bufs {
 // kernel to fetch its tile with one cp.async.bulk.tensor instead of a load/store loop.  use[l] == 0: the level cannot be
 // described (base or pitch not 16-byte aligned) and the kernel falls back to vector/byte loads.
 struct TmaSet {
-  const CUtensorMap* map;  // kMaxLevels descriptors in GLOBAL memory (64-byte aligned), written by the host before launch
+  const CUtensorMap* map;  // 3*kMaxLevels descriptors in GLOBAL memory (64-byte aligned), written by the host before launch:
+                           // [l] FAST tile of level l, [kMaxLevels + l] 48x31 orientation patch of level l,
+                           // [2*kMaxLevels + l] 64x37 descriptor patch of BLURRED level l
   int use[kMaxLevels];
-  int frame0;              // z coordinate of the chunk's first frame in the level-0 map (levels >= 1 are chunk-local)
+  int usePatch;            // every level has both patch descriptors -> orient_desc_tma_kernel
+  int frame0;              // z coordinate of the chunk's first frame in the level-0 maps (levels >= 1 are chunk-local)
 };
+constexpr int kOdUW = 48, kOdUH = 31;    // orientation patch box: 31 rows of (15 + 31 + pad) bytes, x origin 16-byte aligned
+constexpr int kOdBW = 64, kOdBH = 37;    // descriptor patch box: 37 rows of (15 + 37 + pad) bytes
 
 struct ResizeTaps {        // device tables of one level
   int* xofs; short* xa0; short* xa1;

@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const __grid_constan
 // ---- warp-synchronous variant (the default): one warp owns one cell end to end, so the phases are separated by
 // __syncwarp instead of CTA barriers (barrier stalls were the top stall reason of fast_kernel) and queue appends use
 // ballots / warp scans instead of shared-memory atomics.  Same arithmetic and the same output order as fast_kernel.
-constexpr int kWarpCells = 2;                     // cells (= warps) per CTA of the warp-synchronous variant
+constexpr int kWarpCells = kCellsPerCta;          // cells (= warps) per CTA of the warp-synchronous variant
 
 template <int SH>
 __device__ __forceinline__ uint32_t fw_stage_a(const uint8_t* rowm3, int sp, uint32_t kc, bool hiT) { return reject4_a<SH>(rowm3, sp, kc, hiT); }
@@ -1478,6 +1478,199 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(const __grid_constant_
   }
 }
 
+// ---- TMA-fed, software-pipelined variant (the default when every level has patch descriptors) -----------------------
+// The kernel above is bound by the LSU data pipe (77 % of peak: byte-wise smem reads for the moments, LDGSTS staging,
+// pattern loads) with the DRAM latency of the patches exposed behind two dependent global loads.  Here
+//  * both patches of a keypoint arrive by ONE cp.async.bulk.tensor each (UTMALDG; no LSU wavefronts, no register
+//    traffic) into a two-stage per-warp ring guarded by mbarriers, and a warp walks kOdK consecutive slots so the
+//    patches of keypoint k+1 are in flight while keypoint k is computed;
+//  * the moments read a row as three 16-byte words per lane and use IDP (dp4a, u8 x s8) against the column weights
+//    after masking the bytes outside the radius-15 disc: 12 LDS wavefronts + 16 IDP instead of 31 LDS.U8 + 62 IMAD/IADD;
+//  * the 16 pattern points of a lane stay in registers across the warp's keypoints;
+//  * cvRound = add-magic-number rounding on the FMA pipe (exact round-half-even for |v| < 2^22) instead of F2I.
+// Arithmetic and output are identical to orient_desc_kernel.
+constexpr int kOdK = 4;                 // consecutive selected-keypoint slots per warp
+constexpr int kOdWarps = 4;             // warps per CTA
+constexpr int kOdStage = 3968;          // bytes per ring stage: 48x31 patch at 0, 64x37 patch at 1536 (both 128-byte aligned)
+constexpr int kOdBOff = 1536;
+constexpr uint32_t kOdTx = kOdUW * kOdUH + kOdBW * kOdBH;
+
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // sum of (unsigned byte of a) * (signed byte of b) + c
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__host__ __device__ constexpr uint32_t od_wu(int j) {   // column weights u = -15 + 4j + b of aligned patch word j as packed s8
+  return (uint32_t)((-15 + 4 * j) & 0xFF) | ((uint32_t)((-14 + 4 * j) & 0xFF) << 8) | ((uint32_t)((-13 + 4 * j) & 0xFF) << 16) |
+         ((uint32_t)((-12 + 4 * j) & 0xFF) << 24);
+}
+template <int WS>
+__device__ __forceinline__ void od_row_moments(const uint4* row, int bsh, const uint32_t* mk, int& m10, int& sum) {
+  const uint4 q0 = row[0], q1 = row[1], q2 = row[2];
+  const uint32_t W[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t a = __funnelshift_r(W[WS + j], W[WS + j + 1], bsh) & mk[j];
+    sum = dp4a_us(a, 0x01010101u, sum);
+    m10 = dp4a_us(a, od_wu(j), m10);
+  }
+}
+__device__ __forceinline__ int od_round(float v) {                        // cvRound(v) + 0x4B400000
+  return __float_as_int(__fadd_rn(v, 12582912.f));
+}
+
+__global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __grid_constant__ Geom G, const Bufs B, const TmaSet TM,
+                                                                        orbx_keypoint* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
+                                                                        int cap, int32_t* __restrict__ counts_out, int frame0) {
+  pdl_prologue();
+  __shared__ __align__(128) uint8_t ring[kOdWarps][2][kOdStage];
+  __shared__ __align__(8) uint64_t bars[kOdWarps][2];
+  __shared__ uint32_t momMask[16 * 9];       // [|v|][word j] byte mask of |u| <= umax[|v|]; row stride 9: conflict-free across lanes
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f = blockIdx.y;
+  for (int i = tid; i < 16 * 9; i += 32 * kOdWarps) {
+    const int av = i / 9, j = i - av * 9, d = __ldg(B.umax + av);
+    uint32_t m = 0;
+    for (int b = 0; b < 4; ++b) {
+      const int u = -15 + 4 * j + b;
+      if (j < 8 && u >= -d && u <= d) m |= 0xFFu << (8 * b);
+    }
+    momMask[i] = m;
+  }
+  if (tid < 2 * kOdWarps) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bars[tid >> 1][tid & 1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();                            // the only CTA-wide barrier: the warps are independent from here on
+
+  const int slot0 = (blockIdx.x * kOdWarps + warp) * kOdK;
+  if (slot0 >= G.selPerFrame) return;
+  // lane q < nlevels: count of level q; lane k < kOdK: key / level / output position of slot slot0 + k (one global round trip)
+  const int cl = lane < G.nlevels ? __ldg(B.selCount + (size_t)f * G.nlevels + lane) : 0;
+  const int myslot = min(slot0 + lane, G.selPerFrame - 1);
+  const uint32_t mykey = lane < kOdK ? __ldg(B.sel + (size_t)f * G.selPerFrame + myslot) : 0u;
+  int myl = 0;
+  while (myl + 1 < G.nlevels && myslot >= G.L[myl + 1].selBase) ++myl;
+  int before = 0, cntL = 0, total = 0;
+  for (int q = 0; q < G.nlevels; ++q) {
+    const int c = __shfl_sync(0xffffffffu, cl, q);
+    total += c;
+    if (q < myl) before += c;
+    if (q == myl) cntL = c;
+  }
+  if (blockIdx.x == 0 && tid == 0) counts_out[frame0 + f] = total;
+  const int myi = myslot - G.L[myl].selBase, myo = before + myi;
+  // caller buffer smaller than the keypoint count: the count is still reported
+  unsigned todo = __ballot_sync(0xffffffffu, lane < kOdK && slot0 + lane < G.selPerFrame && myi < cntL && myo < cap);
+  if (todo == 0) return;
+
+  float2 pat[16];                             // pattern stored transposed [point-in-byte][lane]: coalesced, loaded once per warp
+#pragma unroll
+  for (int k = 0; k < 16; ++k) pat[k] = __ldg(B.pattern + 32 * k + lane);
+
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(&ring[warp][0][0]);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[warp][0]);
+  auto issue = [&](int k, int stage) {        // lane 0 only: request both patches of slot slot0 + k into `stage`
+    const uint32_t key = __shfl_sync(0xffffffffu, mykey, k);
+    const int l = __shfl_sync(0xffffffffu, myl, k);
+    if (lane == 0) {
+      const int x = key_x(key) + kMinBorder, y = key_y(key) + kMinBorder;
+      const int xu = x - 15, xb = x - 18;
+      const uint32_t bar = bar0 + 8 * stage, dst = ring0 + kOdStage * stage;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kOdTx) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+          "l"(reinterpret_cast<uint64_t>(TM.map + kMaxLevels + l)), "r"(xu & ~15), "r"(y - 15), "r"((l == 0 ? TM.frame0 : 0) + f), "r"(bar)
+          : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst + kOdBOff),
+          "l"(reinterpret_cast<uint64_t>(TM.map + 2 * kMaxLevels + l)), "r"(xb & ~15), "r"(y - 18), "r"(f), "r"(bar)
+          : "memory");
+    }
+  };
+
+  int cur = __ffs(todo) - 1;
+  todo &= todo - 1;
+  issue(cur, 0);
+  unsigned n = 0;                             // keypoints done by this warp: stage = n & 1, barrier parity = (n >> 1) & 1
+  while (cur >= 0) {
+    const int nxt = todo ? __ffs(todo) - 1 : -1;
+    todo &= todo - 1;
+    const int stage = n & 1;
+    if (nxt >= 0) issue(nxt, stage ^ 1);      // the other stage was released by the __syncwarp that ended the previous iteration
+    {
+      const uint32_t bar = bar0 + 8 * stage, par = (n >> 1) & 1;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "OW_%=:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+          "@p bra OD_%=;\n\t"
+          "bra OW_%=;\n\t"
+          "OD_%=:\n\t}" ::"r"(bar), "r"(par) : "memory");
+    }
+    const uint32_t key = __shfl_sync(0xffffffffu, mykey, cur);
+    const int l = __shfl_sync(0xffffffffu, myl, cur);
+    const int o = __shfl_sync(0xffffffffu, myo, cur);
+    const LevelGeom& L = G.L[l];
+    const int x = key_x(key) + kMinBorder, y = key_y(key) + kMinBorder;   // (ORBextractor.cpp:851-852)
+    const uint8_t* pu = &ring[warp][stage][0];
+    const uint8_t* pb = pu + kOdBOff;
+    const int oxu = (x - 15) & 15, oxb = (x - 18) & 15;
+
+    // ---- moments over the radius-15 disc: lane <-> row v = lane-15 (ORBextractor.cpp:79-107) --------------
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+      const int v = lane - 15;
+      const uint4* row = reinterpret_cast<const uint4*>(pu + lane * kOdUW);
+      const uint32_t* mk = momMask + abs(v) * 9;
+      const int bsh = 8 * (oxu & 3);
+      int sum = 0;
+      switch (oxu >> 2) {
+        case 0: od_row_moments<0>(row, bsh, mk, m10, sum); break;
+        case 1: od_row_moments<1>(row, bsh, mk, m10, sum); break;
+        case 2: od_row_moments<2>(row, bsh, mk, m10, sum); break;
+        default: od_row_moments<3>(row, bsh, mk, m10, sum); break;
+      }
+      m01 = v * sum;
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- rBRIEF on the blurred patch (ORBextractor.cpp:110-151) ---------------------------------------------
+    const float factorPI = (float)(3.1415926535897932384626433832795 / (double)180.f);
+    float a, b;
+    glibc_sincosf(__fmul_rn(angle, factorPI), b, a);
+    // sample address = centre + row * 64 + col with row, col carrying the rounding bias 0x4B400000 each
+    const uint32_t bl = (uint32_t)__cvta_generic_to_shared(pb) + 18 * kOdBW + oxb + 18 - 65u * 0x4B400000u;
+    int val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 p0 = pat[2 * j], p1 = pat[2 * j + 1];
+      const uint32_t r0 = (uint32_t)od_round(__fadd_rn(__fmul_rn(p0.x, b), __fmul_rn(p0.y, a)));
+      const uint32_t c0 = (uint32_t)od_round(__fsub_rn(__fmul_rn(p0.x, a), __fmul_rn(p0.y, b)));
+      const uint32_t r1 = (uint32_t)od_round(__fadd_rn(__fmul_rn(p1.x, b), __fmul_rn(p1.y, a)));
+      const uint32_t c1 = (uint32_t)od_round(__fsub_rn(__fmul_rn(p1.x, a), __fmul_rn(p1.y, b)));
+      uint32_t t0, t1;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"(bl + r0 * kOdBW + c0));
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"(bl + r1 * kOdBW + c1));
+      val |= (t0 < t1) << j;
+    }
+    desc_out[((size_t)(frame0 + f) * cap + o) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+      orbx_keypoint k;
+      k.x = (float)x; k.y = (float)y;
+      if (l != 0) { k.x = __fmul_rn(k.x, L.scale); k.y = __fmul_rn(k.y, L.scale); }   // (:1102-1108)
+      k.size = L.kpSize; k.angle = angle; k.response = (float)key_s(key); k.octave = l; k.class_id = -1;
+      kps_out[(size_t)(frame0 + f) * cap + o] = k;
+    }
+    __syncwarp();                             // every lane is done with this stage before it is requested again
+    cur = nxt;
+    ++n;
+  }
+}
+
 // ---- launch wrappers (called from the C ABI in orb_capi.cu) ---------------------------------------------
 void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe, uint8_t* dst, int dw, int dh,
                    int dpitch, size_t dframe, const ResizeTaps& T, int nframes, cudaStream_t st) {
@@ -1542,8 +1735,16 @@ void launch_blur(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
   if (walk) launch_chain(pdl_enabled() >= 2, blur_walk_kernel, dim3(G.bwTiles, nframes), dim3(128), 0, st, G, B);
   else launch_chain(pdl_enabled() >= 2, blur_kernel, dim3(G.blurTiles, nframes), dim3(256), 0, st, G, B);
 }
-void launch_orient_desc(const Geom& G, const Bufs& B, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
+void launch_orient_desc(const Geom& G, const Bufs& B, const TmaSet& TM, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
                         int frame0, int nframes, cudaStream_t st) {
+  // default: the TMA-fed pipelined kernel; ORBX_OD_TMA=0 (or a level that TMA cannot describe) selects the LDGSTS one
+  static const bool tma = !(getenv("ORBX_OD_TMA") && atoi(getenv("ORBX_OD_TMA")) == 0);
+  if (tma && TM.usePatch) {
+    const int per = kOdWarps * kOdK;
+    launch_chain(pdl_enabled() >= 2, orient_desc_tma_kernel, dim3((G.selPerFrame + per - 1) / per, nframes), dim3(32 * kOdWarps), 0, st,
+                 G, B, TM, kps, desc, cap, counts, frame0);
+    return;
+  }
   launch_chain(pdl_enabled() >= 2, orient_desc_kernel, dim3((G.selPerFrame + 7) / 8, nframes), dim3(256), 0, st, G, B, kps, desc, cap, counts, frame0);
 }
 
