@@ -1272,11 +1272,13 @@ __device__ __forceinline__ void blur_walk_body(const uint8_t* __restrict__ src, 
 
 __global__ void __launch_bounds__(128, 8) blur_walk_kernel(const __grid_constant__ Geom G, const Bufs B) {
   pdl_prologue();
-  const int tid = threadIdx.x, f = blockIdx.y;
+  // frames are the FAST grid dimension: CTAs that are resident together work on the same tile of different frames, i.e. run
+  // the same specialisation of the walk (interior / border variants), which keeps the instruction cache warm
+  const int tid = threadIdx.x, f = blockIdx.x;
   int l = 0;
-  while (l + 1 < G.nlevels && (int)blockIdx.x >= G.L[l + 1].bwTile0) ++l;
+  while (l + 1 < G.nlevels && (int)blockIdx.y >= G.L[l + 1].bwTile0) ++l;
   const LevelGeom& L = G.L[l];
-  const int t = blockIdx.x - L.bwTile0;
+  const int t = blockIdx.y - L.bwTile0;
   const int ty = t / L.bwTilesX, tx = t - ty * L.bwTilesX;
   const int W = L.w, H = L.h, bpitch = L.bpitch;
   const int q = tx * 16 + (tid & 15);                              // column quad
@@ -1732,7 +1734,7 @@ void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
 void launch_blur(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
   // default: the register-blocked kernel; ORBX_BLUR_WALK=0 selects the shared-memory tile kernel for A/B runs
   static const bool walk = !(getenv("ORBX_BLUR_WALK") && atoi(getenv("ORBX_BLUR_WALK")) == 0);
-  if (walk) launch_chain(pdl_enabled() >= 2, blur_walk_kernel, dim3(G.bwTiles, nframes), dim3(128), 0, st, G, B);
+  if (walk) launch_chain(pdl_enabled() >= 2, blur_walk_kernel, dim3(nframes, G.bwTiles), dim3(128), 0, st, G, B);
   else launch_chain(pdl_enabled() >= 2, blur_kernel, dim3(G.blurTiles, nframes), dim3(256), 0, st, G, B);
 }
 void launch_orient_desc(const Geom& G, const Bufs& B, const TmaSet& TM, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
