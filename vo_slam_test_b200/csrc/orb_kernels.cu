@@ -6,6 +6,17 @@
 
 #include "orb_extract.cuh"
 
+// grid order switches (A/B builds): 1 = frames are the fast grid dimension
+#ifndef ORBX_FAST_FF
+#define ORBX_FAST_FF 1
+#endif
+#ifndef ORBX_OCT_FF
+#define ORBX_OCT_FF 1
+#endif
+#ifndef ORBX_OD_FF
+#define ORBX_OD_FF 0
+#endif
+
 namespace orbx {
 
 __device__ __forceinline__ const uint8_t* level_ptr(const Geom& G, const Bufs& B, int l, int f, int& pitch) {
@@ -523,7 +534,11 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
   __shared__ int cellOut[kWarpCells];
   __shared__ __align__(8) uint64_t tmaBar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if ORBX_FAST_FF
+  const int slot = blockIdx.y, f = blockIdx.x;
+#else
   const int slot = blockIdx.x, f = blockIdx.y;
+#endif
   const int keyBase = __ldg(B.slotKeyBase + slot);        // needed only by the emission: fetched now, off the critical path
   int l = 0;
   while (l + 1 < G.nlevels && slot >= G.L[l + 1].slot0) ++l;
@@ -778,7 +793,11 @@ __global__ void __launch_bounds__(kOctThreads, 5) octree_kernel(const __grid_con
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, T = kOctThreads;
+#if ORBX_OCT_FF
+  const int l = blockIdx.y, f = blockIdx.x;
+#else
   const int l = blockIdx.x, f = blockIdx.y;
+#endif
   const LevelGeom& L = G.L[l];
   const int cap = G.nodeCap;
   OctSmem S;
@@ -1529,7 +1548,11 @@ __global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __
   __shared__ __align__(8) uint64_t bars[kOdWarps][2];
   __shared__ uint32_t momMask[16 * 9];       // [|v|][word j] byte mask of |u| <= umax[|v|]; row stride 9: conflict-free across lanes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int f = blockIdx.y;
+#if ORBX_OD_FF
+  const int f = blockIdx.x, bx = blockIdx.y;
+#else
+  const int f = blockIdx.y, bx = blockIdx.x;
+#endif
   for (int i = tid; i < 16 * 9; i += 32 * kOdWarps) {
     const int av = i / 9, j = i - av * 9, d = __ldg(B.umax + av);
     uint32_t m = 0;
@@ -1545,7 +1568,7 @@ __global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __
   }
   __syncthreads();                            // the only CTA-wide barrier: the warps are independent from here on
 
-  const int slot0 = (blockIdx.x * kOdWarps + warp) * kOdK;
+  const int slot0 = (bx * kOdWarps + warp) * kOdK;
   if (slot0 >= G.selPerFrame) return;
   // lane q < nlevels: count of level q; lane k < kOdK: key / level / output position of slot slot0 + k (one global round trip)
   const int cl = lane < G.nlevels ? __ldg(B.selCount + (size_t)f * G.nlevels + lane) : 0;
@@ -1560,7 +1583,7 @@ __global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __
     if (q < myl) before += c;
     if (q == myl) cntL = c;
   }
-  if (blockIdx.x == 0 && tid == 0) counts_out[frame0 + f] = total;
+  if (bx == 0 && tid == 0) counts_out[frame0 + f] = total;
   const int myi = myslot - G.L[myl].selBase, myo = before + myi;
   // caller buffer smaller than the keypoint count: the count is still reported
   unsigned todo = __ballot_sync(0xffffffffu, lane < kOdK && slot0 + lane < G.selPerFrame && myi < cntL && myo < cap);
@@ -1723,13 +1746,13 @@ static bool use_fast_warp() {
 
 void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st) {
   if (use_fast_warp()) {
-    launch_chain(pdl_enabled() >= 2, fast_warp_kernel, dim3(G.totalSlots, nframes), dim3(32 * kWarpCells), fast_warp_smem_bytes(G), st, G, B, TM);
+    launch_chain(pdl_enabled() >= 2, fast_warp_kernel, ORBX_FAST_FF ? dim3(nframes, G.totalSlots) : dim3(G.totalSlots, nframes), dim3(32 * kWarpCells), fast_warp_smem_bytes(G), st, G, B, TM);
     return;
   }
   launch_chain(pdl_enabled() >= 2, fast_kernel, dim3(G.totalSlots, nframes), dim3(kFastThreads), fast_smem_bytes(G), st, G, B, TM);
 }
 void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
-  launch_chain(pdl_enabled() >= 2, octree_kernel, dim3(G.nlevels, nframes), dim3(kOctThreads), octree_smem_bytes(G), st, G, B);
+  launch_chain(pdl_enabled() >= 2, octree_kernel, ORBX_OCT_FF ? dim3(nframes, G.nlevels) : dim3(G.nlevels, nframes), dim3(kOctThreads), octree_smem_bytes(G), st, G, B);
 }
 void launch_blur(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
   // default: the register-blocked kernel; ORBX_BLUR_WALK=0 selects the shared-memory tile kernel for A/B runs
@@ -1743,7 +1766,7 @@ void launch_orient_desc(const Geom& G, const Bufs& B, const TmaSet& TM, orbx_key
   static const bool tma = !(getenv("ORBX_OD_TMA") && atoi(getenv("ORBX_OD_TMA")) == 0);
   if (tma && TM.usePatch) {
     const int per = kOdWarps * kOdK;
-    launch_chain(pdl_enabled() >= 2, orient_desc_tma_kernel, dim3((G.selPerFrame + per - 1) / per, nframes), dim3(32 * kOdWarps), 0, st,
+    launch_chain(pdl_enabled() >= 2, orient_desc_tma_kernel, ORBX_OD_FF ? dim3(nframes, (G.selPerFrame + per - 1) / per) : dim3((G.selPerFrame + per - 1) / per, nframes), dim3(32 * kOdWarps), 0, st,
                  G, B, TM, kps, desc, cap, counts, frame0);
     return;
   }
