@@ -18,7 +18,8 @@ void set_error(const std::string& msg) { g_err = msg; }
 
 // kernels / launchers (orb_kernels.cu)
 void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe, uint8_t* dst, int dw, int dh,
-                   int dpitch, size_t dframe, const ResizeTaps& T, int nframes, cudaStream_t st);
+                   int dpitch, size_t dframe, const ResizeTaps& T, const ResizeTma& R, const CUtensorMap* map, int z0, int nframes,
+                   cudaStream_t st);
 cudaError_t configure_kernels(const Geom& G);
 size_t fast_smem_bytes(const Geom& G);
 size_t octree_smem_bytes(const Geom& G);
@@ -37,6 +38,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct DevTaps {
   ResizeTaps t{};
+  ResizeTma rt{};          // box geometry of the TMA-staged resize; rt.use is set when the source map could be encoded
+  bool rtFits = false;     // tile origins / box fit the limits (independent of the descriptor)
   void* block = nullptr;
 };
 
@@ -70,7 +73,7 @@ struct orbx_extractor {
   float2* d_pattern = nullptr; int* d_umax = nullptr;
   std::vector<DevTaps> taps;
   TmaSet tma{};              // FAST tile descriptors (levels >= 1 fixed after configure, level 0 per call)
-  CUtensorMap hostMaps[3 * kMaxLevels];   // host copies; d_maps mirrors them in device memory (layout: TmaSet::map)
+  CUtensorMap hostMaps[4 * kMaxLevels];   // host copies; d_maps mirrors them in device memory (layout: TmaSet::map)
   bool patchU[kMaxLevels] = {}, patchB[kMaxLevels] = {};   // which orientation / descriptor patch maps are valid
   CUtensorMap* d_maps = nullptr;
   EncodeTiledFn encode = nullptr;
@@ -155,6 +158,10 @@ bool encode_level_map(orbx_extractor* h, int l, const uint8_t* base, size_t pitc
   const LevelGeom& L = h->G.L[l];
   h->tma.use[l] = encode_map(h, l, base, L.w, L.h, pitch, frameStride, nframes, h->G.fastTileW, h->G.fastTileH) ? 1 : 0;
   h->patchU[l] = encode_map(h, kMaxLevels + l, base, L.w, L.h, pitch, frameStride, nframes, kOdUW, kOdUH);
+  if (l + 1 < h->G.nlevels && l + 1 < (int)h->taps.size()) {       // this level is the resize source of level l + 1
+    DevTaps& T = h->taps[l + 1];
+    T.rt.use = T.rtFits && encode_map(h, 3 * kMaxLevels + l + 1, base, L.w, L.h, pitch, frameStride, nframes, T.rt.boxW, T.rt.boxH) ? 1 : 0;
+  }
   refresh_use_patch(h);
   return h->tma.use[l] != 0;
 }
@@ -276,6 +283,29 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
       quad[q] = make_int4(s0 & ~3, (s0 & 3) * 8, (int)sels, 0);
       xw[q] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
     }
+    {   // TMA-staged resize: source box origin of every 128-column / 64-row destination tile, and the box that covers all
+      DevTaps& T = h->taps[l];
+      T.rt = ResizeTma{};
+      const int ntx = (D.w + kRzTileW - 1) / kRzTileW, nty = (D.h + kRzTileH - 1) / kRzTileH;
+      bool fits = quadOk && ntx <= kRzMaxTX && nty <= kRzMaxTY;
+      int boxW = 16, boxH = 1;
+      for (int tx = 0; fits && tx < ntx; ++tx) {
+        const int q0 = tx * (kRzTileW / 4), q1 = std::min(q0 + kRzTileW / 4, nquad) - 1;
+        const int x0 = quad[q0].x & ~15, x1 = quad[q1].x + 12;
+        if (x0 > 32767) fits = false;
+        T.rt.x0[tx] = (short)x0;
+        boxW = std::max(boxW, align_up(x1 - x0, 16));
+      }
+      for (int ty = 0; fits && ty < nty; ++ty) {
+        const int d0 = ty * kRzTileH, d1 = std::min(d0 + kRzTileH, D.h) - 1;
+        const int y0 = yo[d0], y1 = std::min(yo[d1] + 1, S.h - 1);
+        if (y0 > 32767) fits = false;
+        T.rt.y0[ty] = (short)y0;
+        boxH = std::max(boxH, y1 - y0 + 1);
+      }
+      T.rt.boxW = boxW; T.rt.boxH = boxH;
+      T.rtFits = fits && boxW <= 256 && boxH <= 256 && (size_t)boxW * boxH <= 48 * 1024;
+    }
     std::vector<uint8_t> blob(bx + 2 * bs + by + 2 * bt + bq + bw, 0);
     memcpy(blob.data(), xo.data(), sizeof(int) * D.w);
     memcpy(blob.data() + bx, xa0.data(), sizeof(short) * D.w);
@@ -334,7 +364,7 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
     const int spitch = (l == 1) ? (int)rowStride : S.pitch;
     const size_t sframe = (l == 1) ? frameStride : (size_t)S.h * S.pitch;
     launch_resize(src, S.w, S.h, spitch, sframe, h->d_pyr + D.pyrOff, D.w, D.h, D.pitch, (size_t)D.h * D.pitch,
-                  h->taps[l].t, n, st);
+                  h->taps[l].t, h->taps[l].rt, h->d_maps ? h->d_maps + 3 * kMaxLevels + l : nullptr, l == 1 ? frame0 : 0, n, st);
   }
   if (ev) cudaEventRecord(ev[1], st);
   h->tma.frame0 = frame0;
@@ -426,7 +456,7 @@ int orbx_create(const orbx_params* p, orbx_handle* out) {
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
       h->encode = (EncodeTiledFn)fn;
-    if (cudaMalloc(&h->d_maps, sizeof(CUtensorMap) * 3 * kMaxLevels) != cudaSuccess) h->d_maps = nullptr;
+    if (cudaMalloc(&h->d_maps, sizeof(CUtensorMap) * 4 * kMaxLevels) != cudaSuccess) h->d_maps = nullptr;
     h->tma.map = h->d_maps;
   }
   float2 pat[512];

@@ -84,9 +84,10 @@ struct Bufs {
 // kernel to fetch its tile with one cp.async.bulk.tensor instead of a load/store loop.  use[l] == 0: the level cannot be
 // described (base or pitch not 16-byte aligned) and the kernel falls back to vector/byte loads.
 struct TmaSet {
-  const CUtensorMap* map;  // 3*kMaxLevels descriptors in GLOBAL memory (64-byte aligned), written by the host before launch:
+  const CUtensorMap* map;  // 4*kMaxLevels descriptors in GLOBAL memory (64-byte aligned), written by the host before launch:
                            // [l] FAST tile of level l, [kMaxLevels + l] 48x31 orientation patch of level l,
-                           // [2*kMaxLevels + l] 64x37 descriptor patch of BLURRED level l
+                           // [2*kMaxLevels + l] 64x37 descriptor patch of BLURRED level l,
+                           // [3*kMaxLevels + l] resize source box of destination level l (a box over level l-1)
   int use[kMaxLevels];
   int usePatch;            // every level has both patch descriptors -> orient_desc_tma_kernel
   int frame0;              // z coordinate of the chunk's first frame in the level-0 maps (levels >= 1 are chunk-local)
@@ -100,6 +101,16 @@ struct ResizeTaps {        // device tables of one level
   // per destination quad (4 px): {aligned source byte offset, funnel shift, 4 byte-pair selectors, -} and the four
   // packed weight pairs a0 | a1 << 16; quadOk = every quad's taps fit an 8-byte window (scale factor <= 2)
   int4* quad; uint4* xw; int quadOk;
+};
+
+// TMA staging of the resize source (resize_tma_kernel): a CTA produces a 128 x 64 destination tile from ONE
+// cp.async.bulk.tensor box of the source level; the box origin of every tile column / tile row comes from the tap tables.
+constexpr int kRzTileW = 128, kRzTileH = 64, kRzMaxTX = 32, kRzMaxTY = 48;
+struct ResizeTma {
+  int use;                 // descriptor valid and the boxes fit (else: resize_walk_kernel)
+  int boxW, boxH;          // bytes x rows, boxW a multiple of 16, both <= 256
+  short x0[kRzMaxTX];      // 16-byte aligned source byte offset of tile column tx
+  short y0[kRzMaxTY];      // first source row of tile row ty
 };
 
 }  // namespace orbx

@@ -179,6 +179,104 @@ __global__ void __launch_bounds__(128) resize_walk_kernel(const uint8_t* __restr
   }
 }
 
+// TMA-staged variant (the default when the source level can be described): the 128 x 64 destination tile of a CTA needs
+// a source box of about 170 x 80 bytes, fetched by ONE cp.async.bulk.tensor (UTMALDG) into shared memory while the
+// threads load their tap tables; the walk then reads its three words per source row with LDS, so the dependent
+// global-load latency that bounded resize_walk_kernel (long-scoreboard stalls 9 per issue) is paid once per CTA and
+// overlapped by the other resident CTAs.  Row taps of the 16 rows of a warp live in lanes 0..15 and are broadcast by
+// shuffles.  Same integer arithmetic as resize_walk_kernel.
+__global__ void __launch_bounds__(128) resize_tma_kernel(const CUtensorMap* __restrict__ map, int z0, int sh, uint8_t* __restrict__ dst,
+                                                         int dw, int dh, int dpitch, size_t dframe, ResizeTaps T,
+                                                         const __grid_constant__ ResizeTma R) {
+  pdl_prologue();
+  extern __shared__ __align__(128) uint8_t rz_tile[];
+  __shared__ __align__(8) uint64_t bar;
+  const int lane = threadIdx.x, wy = threadIdx.y, f = blockIdx.z;
+  const int tx0 = R.x0[blockIdx.x], ty0 = R.y0[blockIdx.y];
+  const uint32_t barA = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (lane == 0 && wy == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barA), "r"((uint32_t)(R.boxW * R.boxH)) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            (uint32_t)__cvta_generic_to_shared(rz_tile)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(tx0), "r"(ty0), "r"(z0 + f), "r"(barA)
+        : "memory");
+  }
+  const int q = blockIdx.x * (kRzTileW / 4) + lane;
+  const int dy0 = blockIdx.y * kRzTileH + wy * kRwRows;
+  const int dx0 = q * 4;
+  const bool live = dx0 < dw && dy0 < dh;
+  int4 Q = make_int4(0, 0, 0, 0);
+  uint4 Wt = make_uint4(0, 0, 0, 0);
+  if (live) { Q = __ldg(T.quad + q); Wt = __ldg(T.xw + q); }
+  // lane i < 16 holds the taps of destination row dy0 + i
+  int tsy = 0, tb = 0;
+  if (lane < kRwRows && dy0 + lane < dh) {
+    tsy = __ldg(T.yofs + dy0 + lane);
+    tb = (int)(uint16_t)__ldg(T.yb0 + dy0 + lane) | ((int)(uint16_t)__ldg(T.yb1 + dy0 + lane) << 16);
+  }
+  __syncthreads();                               // barrier initialised before anyone polls it
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "RW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+      "@p bra RD_%=;\n\t"
+      "bra RW_%=;\n\t"
+      "RD_%=:\n\t}" ::"r"(barA) : "memory");
+  if (dy0 >= dh) return;                         // warp-uniform
+  const uint32_t sel0 = (uint32_t)Q.z & 0xFFu, sel1 = ((uint32_t)Q.z >> 8) & 0xFFu, sel2 = ((uint32_t)Q.z >> 16) & 0xFFu,
+                 sel3 = ((uint32_t)Q.z >> 24) & 0xFFu;
+  const uint8_t* p0 = rz_tile + (live ? Q.x - tx0 : 0);
+  const int bw = R.boxW;
+  auto hrow = [&](int sy, int (&h)[4]) {         // (a0*p[sx] + a1*p[sx+1]) >> 4 for the four columns
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(p0 + (sy - ty0) * bw);
+    const uint32_t a0 = r[0], a1 = r[1], a2 = r[2];
+    const uint32_t lo = __funnelshift_r(a0, a1, Q.y), hi = __funnelshift_r(a1, a2, Q.y);
+    h[0] = (int)(__dp2a_lo(Wt.x, __byte_perm(lo, hi, sel0), 0u) >> 4);
+    h[1] = (int)(__dp2a_lo(Wt.y, __byte_perm(lo, hi, sel1), 0u) >> 4);
+    h[2] = (int)(__dp2a_lo(Wt.z, __byte_perm(lo, hi, sel2), 0u) >> 4);
+    h[3] = (int)(__dp2a_lo(Wt.w, __byte_perm(lo, hi, sel3), 0u) >> 4);
+  };
+  uint8_t* d = dst + f * dframe + (size_t)dy0 * dpitch + dx0;
+  const bool whole = dx0 + 3 < dw;
+  const int rows = min(kRwRows, dh - dy0);
+  int h0[4], h1[4];
+  int r1 = -1;                                   // source row held in h1
+  for (int i = 0; i < rows; ++i) {
+    const int sy0 = __shfl_sync(0xffffffffu, tsy, i);
+    const int bb = __shfl_sync(0xffffffffu, tb, i);
+    const int b0 = (int)(short)(bb & 0xFFFF), b1 = bb >> 16;
+    const int sy1 = min(sy0 + 1, sh - 1);
+    if (sy0 == r1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h0[k] = h1[k];
+    } else {
+      hrow(sy0, h0);
+    }
+    if (sy1 != sy0) {
+      hrow(sy1, h1);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h1[k] = h0[k];
+    }
+    r1 = sy1;
+    if (live) {
+      uint32_t v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (uint32_t)((((b0 * h0[k]) >> 16) + ((b1 * h1[k]) >> 16) + 2) >> 2);
+      const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+      if (whole) {
+        *reinterpret_cast<uint32_t*>(d) = out;
+      } else {
+        for (int k = 0; dx0 + k < dw; ++k) d[k] = (uint8_t)(out >> (8 * k));
+      }
+    }
+    d += dpitch;
+  }
+}
+
 // ======================================================================================================
 // K2  per-cell FAST-9/16 + per-cell 3x3 NMS + iniTh/minTh retry + ordered compaction
 // (ORBextractor.cpp:796-836 around cv::FAST; arithmetic: SURVEY App. A.2).
@@ -1698,12 +1796,18 @@ __global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __
 
 // ---- launch wrappers (called from the C ABI in orb_capi.cu) ---------------------------------------------
 void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe, uint8_t* dst, int dw, int dh,
-                   int dpitch, size_t dframe, const ResizeTaps& T, int nframes, cudaStream_t st) {
+                   int dpitch, size_t dframe, const ResizeTaps& T, const ResizeTma& R, const CUtensorMap* map, int z0, int nframes,
+                   cudaStream_t st) {
   dim3 block(32, 8), grid((dw + 127) / 128, (dh + 7) / 8, nframes);
   const bool aligned = ((((uintptr_t)src) | (uintptr_t)spitch | (uintptr_t)sframe) & 3) == 0;
-  // default: the register-blocked kernel; ORBX_RESIZE_WALK=0 selects the one-quad-per-thread kernel for A/B runs
+  // default: TMA-staged tiles; ORBX_RESIZE_TMA=0 selects the register-blocked global-load walk, ORBX_RESIZE_WALK=0 the
+  // one-quad-per-thread kernel (A/B runs)
+  static const bool tma = !(getenv("ORBX_RESIZE_TMA") && atoi(getenv("ORBX_RESIZE_TMA")) == 0);
   static const bool walk = !(getenv("ORBX_RESIZE_WALK") && atoi(getenv("ORBX_RESIZE_WALK")) == 0);
-  if (T.quadOk && aligned && walk) {
+  if (T.quadOk && R.use && tma && map) {
+    const dim3 tblock(32, 4), tgrid((dw + kRzTileW - 1) / kRzTileW, (dh + kRzTileH - 1) / kRzTileH, nframes);
+    launch_chain(pdl_enabled() >= 1, resize_tma_kernel, tgrid, tblock, (size_t)R.boxW * R.boxH, st, map, z0, sh, dst, dw, dh, dpitch, dframe, T, R);
+  } else if (T.quadOk && aligned && walk) {
     const dim3 wblock(32, 4), wgrid((dw + 127) / 128, (dh + 4 * kRwRows - 1) / (4 * kRwRows), nframes);
     launch_chain(pdl_enabled() >= 1, resize_walk_kernel, wgrid, wblock, 0, st, src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
   } else if (T.quadOk && aligned)
