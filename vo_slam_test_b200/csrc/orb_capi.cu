@@ -25,7 +25,7 @@ size_t fast_smem_bytes(const Geom& G);
 size_t octree_smem_bytes(const Geom& G);
 void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st);
 void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st);
-void launch_blur(const Geom& G, const Bufs& B, int nframes, cudaStream_t st);
+void launch_blur(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st);
 void launch_orient_desc(const Geom& G, const Bufs& B, const TmaSet& TM, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
                         int frame0, int nframes, cudaStream_t st);
 
@@ -73,8 +73,8 @@ struct orbx_extractor {
   float2* d_pattern = nullptr; int* d_umax = nullptr;
   std::vector<DevTaps> taps;
   TmaSet tma{};              // FAST tile descriptors (levels >= 1 fixed after configure, level 0 per call)
-  CUtensorMap hostMaps[4 * kMaxLevels];   // host copies; d_maps mirrors them in device memory (layout: TmaSet::map)
-  bool patchU[kMaxLevels] = {}, patchB[kMaxLevels] = {};   // which orientation / descriptor patch maps are valid
+  CUtensorMap hostMaps[5 * kMaxLevels];   // host copies; d_maps mirrors them in device memory (layout: TmaSet::map)
+  bool patchU[kMaxLevels] = {}, patchB[kMaxLevels] = {}, blurSrc[kMaxLevels] = {};   // which orientation / descriptor patch maps are valid
   CUtensorMap* d_maps = nullptr;
   EncodeTiledFn encode = nullptr;
   // staging for the host entry points
@@ -109,8 +109,8 @@ void free_workspace(orbx_extractor* h) {
   h->taps.clear();
   h->haveGeom = false; h->chunk = 0;
   h->map0_base = nullptr; h->map0_n = 0;
-  for (int l = 0; l < kMaxLevels; ++l) { h->tma.use[l] = 0; h->patchU[l] = h->patchB[l] = false; }
-  h->tma.usePatch = 0;
+  for (int l = 0; l < kMaxLevels; ++l) { h->tma.use[l] = 0; h->patchU[l] = h->patchB[l] = h->blurSrc[l] = false; }
+  h->tma.usePatch = 0; h->tma.useBlur = 0;
 }
 
 // cv::resize tap tables for one axis
@@ -149,8 +149,10 @@ bool encode_map(orbx_extractor* h, int idx, const uint8_t* base, int w, int hgt,
 
 void refresh_use_patch(orbx_extractor* h) {
   int ok = 1;
-  for (int l = 0; l < h->G.nlevels; ++l) ok &= (h->patchU[l] && h->patchB[l]) ? 1 : 0;
+  int okb = 1;
+  for (int l = 0; l < h->G.nlevels; ++l) { ok &= (h->patchU[l] && h->patchB[l]) ? 1 : 0; okb &= h->blurSrc[l] ? 1 : 0; }
   h->tma.usePatch = ok;
+  h->tma.useBlur = okb;
 }
 
 // Descriptors of an UNBLURRED level: the FAST kernel's shared-memory tile and the 48x31 orientation patch.
@@ -158,6 +160,7 @@ bool encode_level_map(orbx_extractor* h, int l, const uint8_t* base, size_t pitc
   const LevelGeom& L = h->G.L[l];
   h->tma.use[l] = encode_map(h, l, base, L.w, L.h, pitch, frameStride, nframes, h->G.fastTileW, h->G.fastTileH) ? 1 : 0;
   h->patchU[l] = encode_map(h, kMaxLevels + l, base, L.w, L.h, pitch, frameStride, nframes, kOdUW, kOdUH);
+  h->blurSrc[l] = encode_map(h, 4 * kMaxLevels + l, base, L.w, L.h, pitch, frameStride, nframes, kBtBoxW, kBtBoxH);
   if (l + 1 < h->G.nlevels && l + 1 < (int)h->taps.size()) {       // this level is the resize source of level l + 1
     DevTaps& T = h->taps[l + 1];
     T.rt.use = T.rtFits && encode_map(h, 3 * kMaxLevels + l + 1, base, L.w, L.h, pitch, frameStride, nframes, T.rt.boxW, T.rt.boxH) ? 1 : 0;
@@ -372,7 +375,7 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
   if (ev) cudaEventRecord(ev[2], st);
   launch_octree(G, B, n, st);
   if (ev) cudaEventRecord(ev[3], st);
-  launch_blur(G, B, n, st);
+  launch_blur(G, B, h->tma, n, st);
   if (ev) cudaEventRecord(ev[4], st);
   launch_orient_desc(G, B, h->tma, d_kps, d_desc, cap, d_counts, frame0, n, st);
   if (ev) cudaEventRecord(ev[5], st);
@@ -456,7 +459,7 @@ int orbx_create(const orbx_params* p, orbx_handle* out) {
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
       h->encode = (EncodeTiledFn)fn;
-    if (cudaMalloc(&h->d_maps, sizeof(CUtensorMap) * 4 * kMaxLevels) != cudaSuccess) h->d_maps = nullptr;
+    if (cudaMalloc(&h->d_maps, sizeof(CUtensorMap) * 5 * kMaxLevels) != cudaSuccess) h->d_maps = nullptr;
     h->tma.map = h->d_maps;
   }
   float2 pat[512];

@@ -84,15 +84,18 @@ struct Bufs {
 // kernel to fetch its tile with one cp.async.bulk.tensor instead of a load/store loop.  use[l] == 0: the level cannot be
 // described (base or pitch not 16-byte aligned) and the kernel falls back to vector/byte loads.
 struct TmaSet {
-  const CUtensorMap* map;  // 4*kMaxLevels descriptors in GLOBAL memory (64-byte aligned), written by the host before launch:
+  const CUtensorMap* map;  // 5*kMaxLevels descriptors in GLOBAL memory (64-byte aligned), written by the host before launch:
                            // [l] FAST tile of level l, [kMaxLevels + l] 48x31 orientation patch of level l,
                            // [2*kMaxLevels + l] 64x37 descriptor patch of BLURRED level l,
-                           // [3*kMaxLevels + l] resize source box of destination level l (a box over level l-1)
+                           // [3*kMaxLevels + l] resize source box of destination level l (a box over level l-1),
+                           // [4*kMaxLevels + l] 96x214 blur source box of level l
   int use[kMaxLevels];
   int usePatch;            // every level has both patch descriptors -> orient_desc_tma_kernel
+  int useBlur;             // every level has a blur source descriptor -> blur_tma_kernel
   int frame0;              // z coordinate of the chunk's first frame in the level-0 maps (levels >= 1 are chunk-local)
 };
 constexpr int kOdUW = 48, kOdUH = 31;    // orientation patch box: 31 rows of (15 + 31 + pad) bytes, x origin 16-byte aligned
+constexpr int kBtBoxW = 96, kBtBoxH = 214; // blur source box: 64 columns + 16-byte aligned halos, 208 rows + 3 + 3
 constexpr int kOdBW = 64, kOdBH = 37;    // descriptor patch box: 37 rows of (15 + 37 + pad) bytes
 
 struct ResizeTaps {        // device tables of one level

@@ -1414,6 +1414,122 @@ __global__ void __launch_bounds__(128, 8) blur_walk_kernel(const __grid_constant
   else { if (vedge) blur_walk_body<0, true>(src, pitch, W, H, q, y0, dst, bpitch); else blur_walk_body<0, false>(src, pitch, W, H, q, y0, dst, bpitch); }
 }
 
+// ---- TMA-staged variant (the default when every level can be described) ------------------------------------------
+// Same register-blocked walk, but the 64 x 208 tile of a CTA (+3 halo rows/columns, box 96 x 214 bytes) arrives by ONE
+// cp.async.bulk.tensor.  TMA zero-fills outside the image, so BORDER_REFLECT_101 is applied IN shared memory afterwards
+// (3 halo rows, then 3 halo columns per row: a few hundred byte copies, border tiles only).  Every thread then runs the
+// interior code path on LDS: one specialisation instead of five (instruction-cache misses were the top stall of
+// blur_walk_kernel) and no dependent global-load latency in the walk.
+static_assert(kBtBoxH == kBwTileH + 6 && kBtBoxW == 64 + 32, "blur box");
+__global__ void __launch_bounds__(128, 8) blur_tma_kernel(const __grid_constant__ Geom G, const Bufs B, const TmaSet TM) {
+  pdl_prologue();
+  __shared__ __align__(128) uint8_t tile[kBtBoxH * kBtBoxW];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, f = blockIdx.x;
+  int l = 0;
+  while (l + 1 < G.nlevels && (int)blockIdx.y >= G.L[l + 1].bwTile0) ++l;
+  const LevelGeom& L = G.L[l];
+  const int t = blockIdx.y - L.bwTile0;
+  const int ty = t / L.bwTilesX, tx = t - ty * L.bwTilesX;
+  const int W = L.w, H = L.h, bpitch = L.bpitch;
+  const int bx0 = tx * 64 - 16, by0 = ty * kBwTileH - 3;           // image coordinates of tile[0][0]
+  const uint32_t barA = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barA), "r"((uint32_t)(kBtBoxW * kBtBoxH)) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            (uint32_t)__cvta_generic_to_shared(tile)),
+        "l"(reinterpret_cast<uint64_t>(TM.map + 4 * kMaxLevels + l)), "r"(bx0), "r"(by0), "r"((l == 0 ? TM.frame0 : 0) + f), "r"(barA)
+        : "memory");
+  }
+  __syncthreads();
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "BW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+      "@p bra BD_%=;\n\t"
+      "bra BW_%=;\n\t"
+      "BD_%=:\n\t}" ::"r"(barA) : "memory");
+  // ---- BORDER_REFLECT_101 inside the tile (CTA-uniform conditions) ----------------------------------------------
+  const bool top = by0 < 0, bottom = by0 + kBtBoxH > H, left = bx0 < 0, right = bx0 + kBtBoxW > W;
+  if (top | bottom) {
+    if (top)                                                       // image rows -3..-1 <- rows 3..1
+      for (int i = tid; i < 3 * kBtBoxW; i += 128) {
+        const int k = i / kBtBoxW + 1, x = i - (k - 1) * kBtBoxW;
+        tile[(-k - by0) * kBtBoxW + x] = tile[(k - by0) * kBtBoxW + x];
+      }
+    if (bottom)                                                    // image rows H..H+2 <- rows H-2..H-4
+      for (int i = tid; i < 3 * kBtBoxW; i += 128) {
+        const int k = i / kBtBoxW, x = i - k * kBtBoxW;
+        const int r = H + k - by0;
+        if (r < kBtBoxH) tile[r * kBtBoxW + x] = tile[(H - 2 - k - by0) * kBtBoxW + x];
+      }
+    __syncthreads();
+  }
+  if (left | right) {
+    for (int r = tid; r < kBtBoxH; r += 128) {
+      uint8_t* row = tile + r * kBtBoxW;
+      if (left) { row[-1 - bx0] = row[1 - bx0]; row[-2 - bx0] = row[2 - bx0]; row[-3 - bx0] = row[3 - bx0]; }
+      if (right) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (W + k - bx0 < kBtBoxW) row[W + k - bx0] = row[W - 2 - k - bx0];
+      }
+    }
+    __syncthreads();
+  }
+
+  const int q = tx * 16 + (tid & 15);                              // column quad
+  const int seg = tid >> 4;
+  const int y0 = ty * kBwTileH + seg * kBwRows;                    // first output row of this thread
+  if (!(4 * q < W && y0 < H)) return;
+  constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;
+  constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);
+  // tile row of image row y0-3 is seg*kBwRows; word (tid&15) + 4 of a tile row holds image bytes 4q..4q+3
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(tile + seg * kBwRows * kBtBoxW) + 4 + (tid & 15);
+  uint8_t* dst = B.blur + L.blurOff + (size_t)f * H * bpitch + (ptrdiff_t)(y0 - 6) * bpitch + 4 * q;
+  const int rowsLeft = H - y0;                                     // output row y0 + k exists iff k < rowsLeft
+  uint32_t ring[4][4];                                             // [pair & 3][column]: row 2p low half, row 2p+1 high half
+#pragma unroll 1
+  for (int pg = 0; pg < kBwPairs / 4; ++pg) {
+#pragma unroll
+    for (int pi = 0; pi < 4; ++pi) {
+      const int p = pg * 4 + pi;
+      uint32_t o[2][4];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const uint32_t* w = wp + (2 * pi + rr) * (kBtBoxW / 4);
+        const uint32_t a = w[-1], b = w[0], c = w[1];
+        o[rr][0] = blur_h(__funnelshift_r(a, b, 8), __funnelshift_r(b, c, 8));
+        o[rr][1] = blur_h(__funnelshift_r(a, b, 16), __funnelshift_r(b, c, 16));
+        o[rr][2] = blur_h(__funnelshift_r(a, b, 24), __funnelshift_r(b, c, 24));
+        o[rr][3] = blur_h(b, c);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ring[pi][k] = __byte_perm(o[0][k], o[1][k], 0x5410);   // both fit 16 bits
+      if (pg > 0 || pi == 3) {
+        uint32_t e[4], d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t c0 = ring[(pi + 1) & 3][k], c1 = ring[(pi + 2) & 3][k], c2 = ring[(pi + 3) & 3][k], c3 = ring[pi][k];
+          e[k] = __dp2a_lo(c3, E3, __dp2a_lo(c2, E2, __dp2a_lo(c1, E1, __dp2a_lo(c0, E0, 32768u))));
+          d[k] = __dp2a_lo(c3, O3, __dp2a_lo(c2, O2, __dp2a_lo(c1, O1, __dp2a_lo(c0, O0, 32768u))));
+        }
+        const uint32_t ev = __byte_perm(__byte_perm(e[0], e[1], 0x0062), __byte_perm(e[2], e[3], 0x0062), 0x5410);
+        const uint32_t od = __byte_perm(__byte_perm(d[0], d[1], 0x0062), __byte_perm(d[2], d[3], 0x0062), 0x5410);
+        const int k0 = 2 * (p - 3);
+        uint8_t* d0 = dst + (ptrdiff_t)(2 * pi) * bpitch;           // bpitch is a multiple of 64: columns >= W are padding
+        if (k0 < rowsLeft) *reinterpret_cast<uint32_t*>(d0) = ev;
+        if (k0 + 1 < rowsLeft) *reinterpret_cast<uint32_t*>(d0 + bpitch) = od;
+      }
+    }
+    wp += 8 * (kBtBoxW / 4);
+    dst += (ptrdiff_t)8 * bpitch;
+  }
+}
+
 // ======================================================================================================
 // K4+K6  IC_Angle (ORBextractor.cpp:79-107) + rotated BRIEF (ORBextractor.cpp:110-151) + output assembly
 // (ORBextractor.cpp:845-855, 1085-1111).  One warp per selected keypoint: lanes = patch rows for the
@@ -1858,7 +1974,13 @@ void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cu
 void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
   launch_chain(pdl_enabled() >= 2, octree_kernel, ORBX_OCT_FF ? dim3(nframes, G.nlevels) : dim3(G.nlevels, nframes), dim3(kOctThreads), octree_smem_bytes(G), st, G, B);
 }
-void launch_blur(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
+void launch_blur(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st) {
+  // default: TMA-staged tiles; ORBX_BLUR_TMA=0 selects the global-load walk for A/B runs
+  static const bool tma = !(getenv("ORBX_BLUR_TMA") && atoi(getenv("ORBX_BLUR_TMA")) == 0);
+  if (tma && TM.useBlur) {
+    launch_chain(pdl_enabled() >= 2, blur_tma_kernel, dim3(nframes, G.bwTiles), dim3(128), 0, st, G, B, TM);
+    return;
+  }
   // default: the register-blocked kernel; ORBX_BLUR_WALK=0 selects the shared-memory tile kernel for A/B runs
   static const bool walk = !(getenv("ORBX_BLUR_WALK") && atoi(getenv("ORBX_BLUR_WALK")) == 0);
   if (walk) launch_chain(pdl_enabled() >= 2, blur_walk_kernel, dim3(nframes, G.bwTiles), dim3(128), 0, st, G, B);
