@@ -325,11 +325,18 @@ __device__ __forceinline__ void load_window(uint32_t (&W)[4], const uint8_t* p) 
   W[0] = q[0]; W[1] = q[1]; W[2] = q[2]; W[3] = q[3];
 }
 // per-byte |s - c| > t  ->  bit 7 of each byte.  kc = 0x7F7F7F7F - (t & 0x7F) * 0x01010101; hiT = (t >= 128).
+// The flags only feed a REJECTION filter (every survivor is re-decided by the exact arc score), so for t < 128 the
+// bytes are added without masking bit 7 first: a byte's own flag stays exact (a carry out of it means a >= 129 + t,
+// whose bit 7 is set anyway) and a carry INTO a byte can only turn its "a > t" into "a >= t" -- a superset.
 __device__ __forceinline__ uint32_t far4(uint32_t s, uint32_t c, uint32_t kc, bool hiT) {
   const uint32_t a = __vabsdiffu4(s, c);
+  if (!hiT) return (a | (a + kc)) & 0x80808080u;
   const uint32_t low = (a & 0x7F7F7F7Fu) + kc;          // bit 7 set iff (a & 0x7F) > (t & 0x7F)
-  return (hiT ? (a & low) : (a | low)) & 0x80808080u;
+  return (a & low) & 0x80808080u;
 }
+// bit 7 of the four bytes of m -> bits 0..3, and back (one IMAD on the otherwise idle FMA pipe instead of shift/mask chains)
+__device__ __forceinline__ uint32_t gather_flags(uint32_t m) { return (((m >> 7) & 0x01010101u) * 0x00204081u) >> 21 & 0xFu; }
+__device__ __forceinline__ uint32_t scatter_flags(uint32_t bits) { return (bits * 0x10204080u) & 0x80808080u; }
 
 // Necessary condition of a FAST-9 corner (same shape as OpenCV's quick test, sign-agnostic): every opposite ring pair
 // has a member that differs from the centre by more than t.  Per-byte flags (bit 7) for the 4 centres, in two stages so
@@ -390,7 +397,7 @@ __device__ __forceinline__ void fast_best2(const uint8_t* pa, const uint8_t* pb,
   bestB = max((int)(short)(a >> 16), -(int)(short)(b >> 16));
 }
 
-__global__ void __launch_bounds__(kFastThreads) fast_kernel(const __grid_constant__ Geom G, const Bufs B, const TmaSet TM) {
+__global__ void __launch_bounds__(kFastThreads) fast_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM) {
   pdl_prologue();
   // Work-efficient layout: (1) tile staged with 16-byte loads, (2) a cheap 16-pixel-ring rejection test over all
   // pixels that pushes the few survivors into a shared-memory queue, (3) the full arc score and the per-cell NMS run
@@ -626,7 +633,7 @@ constexpr int kWarpCells = kCellsPerCta;          // cells (= warps) per CTA of 
 template <int SH>
 __device__ __forceinline__ uint32_t fw_stage_a(const uint8_t* rowm3, int sp, uint32_t kc, bool hiT) { return reject4_a<SH>(rowm3, sp, kc, hiT); }
 
-__global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid_constant__ Geom G, const Bufs B, const TmaSet TM) {
+__global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM) {
   pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int cellOut[kWarpCells];
@@ -747,10 +754,7 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
           m &= 0x80808080u;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
-        if (m) {
-          const uint32_t bits = ((m >> 7) & 1) | ((m >> 14) & 2) | ((m >> 21) & 4) | ((m >> 28) & 8);
-          itemq[ni + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(item | (bits << 12));
-        }
+        if (m) itemq[ni + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(item | (gather_flags(m) << 12));
         ni += __popc(bal);
       }
       __syncwarp();
@@ -765,16 +769,15 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
           const uint32_t bits = e >> 12;
           yi = nq4 == 1 ? item : (int)__umulhi((uint32_t)item, magic); xq = 4 * (item - yi * nq4);
           const uint8_t* rowm3 = img + yi * sp + aox + xq;
-          uint32_t m = ((bits & 1) << 7) | ((bits & 2) << 14) | ((bits & 4) << 21) | ((bits & 8) << 28);
+          uint32_t m = scatter_flags(bits);
           switch (sh) {
             case 0: m = reject4_b<0>(rowm3, sp, kc, hiT, m); break;
             case 1: m = reject4_b<1>(rowm3, sp, kc, hiT, m); break;
             case 2: m = reject4_b<2>(rowm3, sp, kc, hiT, m); break;
             default: m = reject4_b<3>(rowm3, sp, kc, hiT, m); break;
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (((m >> (8 * j + 7)) & 1) && xq + j < cw) keep |= 1u << j;
+          // centres xq + j >= cw lie outside the cell: keep the flags of the first cw - xq bytes only
+          keep = gather_flags(m & (0x80808080u >> (8 * max(0, 4 - (cw - xq)))));
         }
         // warp-ordered append of up to 4 pixels per lane
         const int cnt = __popc(keep);
@@ -848,12 +851,12 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
   int off = 0, total = 0;
   for (int w = 0; w < kWarpCells; ++w) { const int c = cellOut[w]; if (w < warp) off += c; total += c; }
   uint32_t* out = B.slotKeys + (size_t)f * G.slotKeysPerFrame + keyBase;
+  // Every queue of this warp is filled in increasing (row, column) order and every compaction (ballot / warp scan) keeps
+  // that order, so surv[] is already sorted by its key: position = rank, no ranking pass.
   for (int k = lane; k < S; k += 32) {
     const uint32_t key = surv[k];
-    int rank = 0;
-    for (int j = 0; j < S; ++j) rank += surv[j] < key ? 1 : 0;
     const int yi = key >> 8, cx = key & 255;
-    out[off + rank] = pack_key(tx0 + cx0 + cx + 3, ty0 + yi + 3, sc0[yi * scp + cx0 + cx] - 1);
+    out[off + k] = pack_key(tx0 + cx0 + cx + 3, ty0 + yi + 3, sc0[yi * scp + cx0 + cx] - 1);
   }
   if (tid == 0) *out_count = total;
 }
@@ -1421,7 +1424,7 @@ __global__ void __launch_bounds__(128, 8) blur_walk_kernel(const __grid_constant
 // interior code path on LDS: one specialisation instead of five (instruction-cache misses were the top stall of
 // blur_walk_kernel) and no dependent global-load latency in the walk.
 static_assert(kBtBoxH == kBwTileH + 6 && kBtBoxW == 64 + 32, "blur box");
-__global__ void __launch_bounds__(128, 8) blur_tma_kernel(const __grid_constant__ Geom G, const Bufs B, const TmaSet TM) {
+__global__ void __launch_bounds__(128, 8) blur_tma_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM) {
   pdl_prologue();
   __shared__ __align__(128) uint8_t tile[kBtBoxH * kBtBoxW];
   __shared__ __align__(8) uint64_t bar;
@@ -1754,7 +1757,7 @@ __device__ __forceinline__ int od_round(float v) {                        // cvR
   return __float_as_int(__fadd_rn(v, 12582912.f));
 }
 
-__global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __grid_constant__ Geom G, const Bufs B, const TmaSet TM,
+__global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM,
                                                                         orbx_keypoint* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
                                                                         int cap, int32_t* __restrict__ counts_out, int frame0) {
   pdl_prologue();
