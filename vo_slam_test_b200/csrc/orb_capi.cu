@@ -232,8 +232,8 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
     L.kpSize = (float)(int)(31 * h->scale[l]);             // :845
     G.fastTileW = std::max(G.fastTileW, align_up(std::min(kCellsPerCta, L.nCols) * L.wCell + 6 + 15, 16));
     G.fastTileH = std::max(G.fastTileH, L.hCell + 6);
-    G.fastScW = std::max(G.fastScW, align_up(std::min(kCellsPerCta, L.nCols) * L.wCell, 16));
-    G.fastScH = std::max(G.fastScH, L.hCell);
+    G.fastScW = std::max(G.fastScW, align_up(std::min(kCellsPerCta, L.nCols) * (L.wCell + 2), 16));   // every cell framed by zeros
+    G.fastScH = std::max(G.fastScH, L.hCell + 2);
     G.fastCellPix = std::max(G.fastCellPix, align_up(L.wCell * L.hCell, 8));
     G.fastCellQuads = std::max(G.fastCellQuads, align_up(((L.wCell + 3) / 4) * L.hCell, 8));
     G.fastCellSurv = std::max(G.fastCellSurv, align_up(((L.wCell + 1) / 2) * ((L.hCell + 1) / 2), 4));

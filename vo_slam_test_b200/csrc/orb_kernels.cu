@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
   const int sp = G.fastTileW;
   const int tileBytes = G.fastTileH * sp;
   uint8_t* img = smem;
-  uint8_t* sc = smem + tileBytes;                        // corner strengths of the cell interiors only, pitch scp
+  uint8_t* sc = smem + tileBytes;                        // corner strengths of the cell interiors, each cell framed by a zero border
   const int scp = G.fastScW, scBytes = G.fastScW * G.fastScH;
   // per-warp scratch: queue (u16 per cell pixel) and one region shared by itemq (u16 per quad, dead after stage b) and
   // surv (u32 per NMS survivor, written after stage b; a retry pass only happens when no survivor was written)
@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
   }
   {
     uint4* z = reinterpret_cast<uint4*>(sc);
-    for (int i = tid; i < (ih * scp) >> 4; i += 32 * kWarpCells) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < ((ih + 2) * scp) >> 4; i += 32 * kWarpCells) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   if (viaTma) {
@@ -728,7 +728,9 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
   const int cw = min(L.wCell, iw - cx0);                  // cell width (<= 0: the cell does not exist in this slot)
   int S = 0;
   const uint8_t* img0 = img + 3 * sp + 3 + ox;
-  uint8_t* sc0 = sc;                                       // sc0[yi * scp + cx0 + cx]
+  // this cell's score map: sc0[yi * scp + cx], yi in [-1, ih], cx in [-1, cw]; the frame stays 0 = "outside the cell counts
+  // as 0" (the zeroed border of cv::FAST on the cell ROI), so the NMS needs no edge flags
+  uint8_t* sc0 = sc + scp + jj * (L.wCell + 2) + 1;
   if (jj < j1 - j0 && cw > 0) {
     const int nq4 = (cw + 3) >> 2;
     const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nq4 + 1;
@@ -800,8 +802,8 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
           e0 = queue[k0]; e1 = queue[min(k1, nq - 1)];
           const int y0 = e0 >> 8, x0 = e0 & 255, y1 = e1 >> 8, x1 = e1 & 255;
           fast_best2(img0 + y0 * sp + cx0 + x0, img0 + y1 * sp + cx0 + x1, sp, b0, b1);
-          sc0[y0 * scp + cx0 + x0] = (uint8_t)(b0 > t ? b0 : 0);
-          if (k1 < nq) sc0[y1 * scp + cx0 + x1] = (uint8_t)(b1 > t ? b1 : 0);
+          sc0[y0 * scp + x0] = (uint8_t)(b0 > t ? b0 : 0);
+          if (k1 < nq) sc0[y1 * scp + x1] = (uint8_t)(b1 > t ? b1 : 0);
         }
         const bool c0 = k0 < nq && b0 > t, c1 = k1 < nq && b1 > t;
         const int cnt = (int)c0 + (int)c1;
@@ -823,18 +825,9 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
         if (k < nc) {
           e = queue[k];
           const int yi = e >> 8, cx = e & 255;
-          const uint8_t* s = sc0 + yi * scp + cx0 + cx;
+          const uint8_t* s = sc0 + yi * scp + cx;
           const int v = s[0];
-          const bool hasL = cx > 0, hasR = cx + 1 < cw, hasU = yi > 0, hasD = yi + 1 < ih;
-          keep = true;
-          keep &= !(hasU && hasL && s[-scp - 1] >= v);
-          keep &= !(hasU && s[-scp] >= v);
-          keep &= !(hasU && hasR && s[-scp + 1] >= v);
-          keep &= !(hasL && s[-1] >= v);
-          keep &= !(hasR && s[1] >= v);
-          keep &= !(hasD && hasL && s[scp - 1] >= v);
-          keep &= !(hasD && s[scp] >= v);
-          keep &= !(hasD && hasR && s[scp + 1] >= v);
+          keep = (v > s[-scp - 1]) & (v > s[-scp]) & (v > s[-scp + 1]) & (v > s[-1]) & (v > s[1]) & (v > s[scp - 1]) & (v > s[scp]) & (v > s[scp + 1]);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (keep) surv[S + __popc(bal & ((1u << lane) - 1))] = (uint32_t)e;      // yi<<8 | cx : already the (row, col) order key
@@ -856,7 +849,7 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
   for (int k = lane; k < S; k += 32) {
     const uint32_t key = surv[k];
     const int yi = key >> 8, cx = key & 255;
-    out[off + k] = pack_key(tx0 + cx0 + cx + 3, ty0 + yi + 3, sc0[yi * scp + cx0 + cx] - 1);
+    out[off + k] = pack_key(tx0 + cx0 + cx + 3, ty0 + yi + 3, sc0[yi * scp + cx] - 1);
   }
   if (tid == 0) *out_count = total;
 }
