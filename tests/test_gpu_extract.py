@@ -57,6 +57,23 @@ def test_extract_matches_oracle(vo, seed, H, W, nf):
 KP_FIELDS = ["x", "y", "size", "angle", "response", "octave", "class_id"]
 
 
+@pytest.mark.parametrize("ini,mn", [(130, 128), (140, 20), (20, 20), (200, 150), (40, 3)])
+def test_unusual_fast_thresholds(vo, ini, mn):
+    """Thresholds >= 128 take the unfiltered path of the FAST kernel (the packed-byte rejection test covers t < 128 only);
+    minTh >= iniTh disables the retry.  Same bit-exact contract."""
+    img = synth.make_frame(21, 240, 320)
+    img[60:120, 40:200] = np.where((np.indices((60, 160)).sum(0) // 9) % 2 == 0, 0, 255).astype(np.uint8)   # contrast > 128
+    P = oracle.Port(300, 1.2, 8, ini, mn)
+    ex = vo.ORBextractor(300, 1.2, 8, ini, mn)
+    kps, desc = ex(img)
+    rk, rd = P.extract(img)
+    assert len(kps) == len(rk) and len(rk) > 0
+    for name in KP_FIELDS:
+        assert np.array_equal(kps[name].view(np.uint32), rk[name].view(np.uint32)), name
+    assert np.array_equal(desc, rd)
+    ex.close()
+
+
 def test_extract_matches_reference_fixtures(vo):
     """Committed outputs of the reference's own ORBextractor.cpp (tests/golden/orb_*.npz)."""
     for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "orb_*.npz"))):

@@ -633,7 +633,76 @@ constexpr int kWarpCells = kCellsPerCta;          // cells (= warps) per CTA of 
 template <int SH>
 __device__ __forceinline__ uint32_t fw_stage_a(const uint8_t* rowm3, int sp, uint32_t kc, bool hiT) { return reject4_a<SH>(rowm3, sp, kc, hiT); }
 
-__global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM) {
+// The two rejection stages of one cell as functions of the window misalignment SH (a warp-uniform runtime value) for
+// t < 128: dispatching ONCE per stage keeps the per-item code free of the 4-way switch and, more importantly, of the
+// predicated double implementation of far4 (ptxas issued both threshold forms of every test, predicated on hiT: 6 issue
+// slots per ring pixel instead of 3).  FILTER = false: pass everything (see FW_DISPATCH).
+template <int SH, bool FILTER>
+__device__ __forceinline__ int fw_stage_a(const uint8_t* img, int sp, int aox, int nq4, uint32_t magic, int nItems, uint32_t kc,
+                                          uint16_t* itemq, int lane) {
+  int ni = 0;
+#pragma unroll 1
+  for (int base = 0; base < nItems; base += 32) {
+    const int item = base + lane;
+    uint32_t m = 0;
+    if (item < nItems) {
+      const int yi = nq4 == 1 ? item : (int)__umulhi((uint32_t)item, magic), xq = 4 * (item - yi * nq4);
+      m = FILTER ? reject4_a<SH>(img + yi * sp + aox + xq, sp, kc, false) & 0x80808080u : 0x80808080u;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
+    if (m) itemq[ni + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(item | (gather_flags(m) << 12));
+    ni += __popc(bal);
+  }
+  return ni;
+}
+template <int SH, bool FILTER>
+__device__ __forceinline__ int fw_stage_b(const uint8_t* img, int sp, int aox, int nq4, uint32_t magic, int cw, uint32_t kc,
+                                          const uint16_t* itemq, int ni, uint16_t* queue, int lane) {
+  int nq = 0;
+#pragma unroll 1
+  for (int base = 0; base < ni; base += 32) {
+    const int k = base + lane;
+    uint32_t keep = 0;
+    int yi = 0, xq = 0;
+    if (k < ni) {
+      const int e = itemq[k], item = e & 0xFFF;
+      yi = nq4 == 1 ? item : (int)__umulhi((uint32_t)item, magic); xq = 4 * (item - yi * nq4);
+      const uint32_t m0 = scatter_flags((uint32_t)e >> 12);
+      const uint32_t m = FILTER ? reject4_b<SH>(img + yi * sp + aox + xq, sp, kc, false, m0) : m0;
+      // centres xq + j >= cw lie outside the cell: keep the flags of the first cw - xq bytes only
+      keep = gather_flags(m & (0x80808080u >> (8 * max(0, 4 - (cw - xq)))));
+    }
+    // warp-ordered append of up to 4 pixels per lane
+    const int cnt = __popc(keep);
+    int pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+    int pos = nq + pre - cnt;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((keep >> j) & 1) queue[pos++] = (uint16_t)((yi << 8) | (xq + j));
+    nq += __shfl_sync(0xffffffffu, pre, 31);
+  }
+  return nq;
+}
+// t >= 128 is legal but meaningless in practice.  The rejection stages are only filters in front of the exact arc score,
+// so that case simply runs without them (every pixel of the cell is scored): correct, slow, and no second set of four
+// variants in the kernel (with all eight inlined, instruction-fetch stalls ate the whole gain of the dispatch).
+#define FW_DISPATCH(RES, FN, ...)                                                                   \
+  do {                                                                                              \
+    if (hiT) RES = FN<0, false>(__VA_ARGS__);                                                       \
+    else switch (sh) {                                                                              \
+        case 0: RES = FN<0, true>(__VA_ARGS__); break;                                              \
+        case 1: RES = FN<1, true>(__VA_ARGS__); break;                                              \
+        case 2: RES = FN<2, true>(__VA_ARGS__); break;                                              \
+        default: RES = FN<3, true>(__VA_ARGS__); break;                                             \
+      }                                                                                             \
+  } while (0)
+
+#ifndef ORBX_FAST_MINB
+#define ORBX_FAST_MINB 16
+#endif
+__global__ void __launch_bounds__(32 * kWarpCells, ORBX_FAST_MINB) fast_warp_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM) {
   pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int cellOut[kWarpCells];
@@ -739,59 +808,13 @@ __global__ void __launch_bounds__(32 * kWarpCells) fast_warp_kernel(const __grid
     for (int pass = 0; pass < 2; ++pass) {
       const uint32_t kc = 0x7F7F7F7Fu - (uint32_t)(t & 0x7F) * 0x01010101u;
       const bool hiT = t >= 128;
-      // stage a over every quad of the cell
+      // stage a over every quad of the cell -> quads with a surviving centre
       int ni = 0;
-      for (int base = 0; base < ih * nq4; base += 32) {
-        const int item = base + lane;
-        uint32_t m = 0;
-        if (item < ih * nq4) {
-          const int yi = nq4 == 1 ? item : (int)__umulhi((uint32_t)item, magic), xq = 4 * (item - yi * nq4);
-          const uint8_t* rowm3 = img + yi * sp + aox + xq;
-          switch (sh) {
-            case 0: m = reject4_a<0>(rowm3, sp, kc, hiT); break;
-            case 1: m = reject4_a<1>(rowm3, sp, kc, hiT); break;
-            case 2: m = reject4_a<2>(rowm3, sp, kc, hiT); break;
-            default: m = reject4_a<3>(rowm3, sp, kc, hiT); break;
-          }
-          m &= 0x80808080u;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
-        if (m) itemq[ni + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(item | (gather_flags(m) << 12));
-        ni += __popc(bal);
-      }
+      FW_DISPATCH(ni, fw_stage_a, img, sp, aox, nq4, magic, ih * nq4, kc, itemq, lane);
       __syncwarp();
       // stage b densely over the surviving quads -> pixel queue
       int nq = 0;
-      for (int base = 0; base < ni; base += 32) {
-        const int k = base + lane;
-        uint32_t keep = 0;
-        int yi = 0, xq = 0;
-        if (k < ni) {
-          const int e = itemq[k], item = e & 0xFFF;
-          const uint32_t bits = e >> 12;
-          yi = nq4 == 1 ? item : (int)__umulhi((uint32_t)item, magic); xq = 4 * (item - yi * nq4);
-          const uint8_t* rowm3 = img + yi * sp + aox + xq;
-          uint32_t m = scatter_flags(bits);
-          switch (sh) {
-            case 0: m = reject4_b<0>(rowm3, sp, kc, hiT, m); break;
-            case 1: m = reject4_b<1>(rowm3, sp, kc, hiT, m); break;
-            case 2: m = reject4_b<2>(rowm3, sp, kc, hiT, m); break;
-            default: m = reject4_b<3>(rowm3, sp, kc, hiT, m); break;
-          }
-          // centres xq + j >= cw lie outside the cell: keep the flags of the first cw - xq bytes only
-          keep = gather_flags(m & (0x80808080u >> (8 * max(0, 4 - (cw - xq)))));
-        }
-        // warp-ordered append of up to 4 pixels per lane
-        const int cnt = __popc(keep);
-        int pre = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
-        int pos = nq + pre - cnt;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if ((keep >> j) & 1) queue[pos++] = (uint16_t)((yi << 8) | (xq + j));
-        nq += __shfl_sync(0xffffffffu, pre, 31);
-      }
+      FW_DISPATCH(nq, fw_stage_b, img, sp, aox, nq4, magic, cw, kc, itemq, ni, queue, lane);
       __syncwarp();
       // score two queue entries per lane; corners are compacted in place at the front of the same queue
       int nc = 0;
@@ -883,7 +906,7 @@ __device__ __forceinline__ int quadrant_of(const short4 b, int x, int y) {
   return (x < mx ? 0 : 1) | (y < my ? 0 : 2);     // 0:n1 1:n2 2:n3 3:n4   (:521-531)
 }
 
-__global__ void __launch_bounds__(kOctThreads, 5) octree_kernel(const __grid_constant__ Geom G, const Bufs B) {
+__global__ void __launch_bounds__(kOctThreads, ORBX_OCT_MINB) octree_kernel(const __grid_constant__ Geom G, const Bufs B) {
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, T = kOctThreads;
