@@ -672,16 +672,16 @@ __device__ __forceinline__ int fw_stage_b(const uint8_t* img, int sp, int aox, i
       // centres xq + j >= cw lie outside the cell: keep the flags of the first cw - xq bytes only
       keep = gather_flags(m & (0x80808080u >> (8 * max(0, 4 - (cw - xq)))));
     }
-    // warp-ordered append of up to 4 pixels per lane
-    const int cnt = __popc(keep);
-    int pre = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
-    int pos = nq + pre - cnt;
+    // warp-ordered append of up to 4 pixels per lane: position = pixels kept by lower lanes (four independent ballots
+    // instead of a five-step shuffle scan) + pixels kept by this lane before j
+    const unsigned lt = (1u << lane) - 1;
+    const unsigned b0 = __ballot_sync(0xffffffffu, keep & 1), b1 = __ballot_sync(0xffffffffu, keep & 2),
+                   b2 = __ballot_sync(0xffffffffu, keep & 4), b3 = __ballot_sync(0xffffffffu, keep & 8);
+    int pos = nq + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if ((keep >> j) & 1) queue[pos++] = (uint16_t)((yi << 8) | (xq + j));
-    nq += __shfl_sync(0xffffffffu, pre, 31);
+    nq += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
   }
   return nq;
 }
@@ -829,15 +829,13 @@ __global__ void __launch_bounds__(32 * kWarpCells, ORBX_FAST_MINB) fast_warp_ker
           if (k1 < nq) sc0[y1 * scp + x1] = (uint8_t)(b1 > t ? b1 : 0);
         }
         const bool c0 = k0 < nq && b0 > t, c1 = k1 < nq && b1 > t;
-        const int cnt = (int)c0 + (int)c1;
-        int pre = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
-        __syncwarp();                                  // every lane has read its entries before anyone overwrites the front
-        int pos = nc + pre - cnt;
+        // the ballots also order the queue reads above before the overwrites of its front below
+        const unsigned lt = (1u << lane) - 1;
+        const unsigned bal0 = __ballot_sync(0xffffffffu, c0), bal1 = __ballot_sync(0xffffffffu, c1);
+        int pos = nc + __popc(bal0 & lt) + __popc(bal1 & lt);
         if (c0) queue[pos++] = (uint16_t)e0;
         if (c1) queue[pos] = (uint16_t)e1;
-        nc += __shfl_sync(0xffffffffu, pre, 31);
+        nc += __popc(bal0) + __popc(bal1);
         __syncwarp();
       }
       // NMS inside the cell (outside the cell counts as 0); survivors appended in any order, ranked later
