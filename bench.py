@@ -278,8 +278,9 @@ def run_b200(args, rank, world, local_rank):
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture, per launch
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        knames = {"fast": ("fast_warp_kernel", "fast_kernel"), "blur": ("blur_kernel",), "orient_desc": ("orient_desc_kernel",),
-                  "quadtree": ("octree_kernel",), "pyramid": ("resize4_kernel",)}[dom]
+        knames = {"fast": ("fast_warp_kernel", "fast_kernel"), "blur": ("blur_tma_kernel", "blur_walk_kernel", "blur_kernel"),
+                  "orient_desc": ("orient_desc_tma_kernel", "orient_desc_kernel"), "quadtree": ("octree_kernel",),
+                  "pyramid": ("resize_tma_kernel", "resize_walk_kernel", "resize4_kernel")}[dom]
         kname = [k for k in knames if k in tr["kernels"]][0]
         traffic = tr["kernels"][kname]["dram_bytes_per_frame"] * min(F, chunk)
     except Exception:

@@ -372,29 +372,40 @@ __device__ __forceinline__ uint32_t reject4_b(const uint8_t* rowm3, int sp, uint
 
 // Corner strength of TWO pixels at once in packed signed 16-bit lanes (VIMNMX.S16x2).
 __device__ __forceinline__ void fast_best2(const uint8_t* pa, const uint8_t* pb, int sp, int& bestA, int& bestB) {
-  const int ca = pa[0], cb = pb[0];
+  // d = centre - ring pixel, both pixels' differences in one register.  The centres carry a bias of 256 per lane so that ONE
+  // 32-bit subtraction serves both lanes (the low lane never borrows); min/max commute with the bias, removed at the end.
+  const uint32_t cc = ((uint32_t)pa[0] + 256u) | (((uint32_t)pb[0] + 256u) << 16);
   uint32_t d[16];
-#define D2(k, off) d[k] = __byte_perm((uint32_t)(ca - pa[off]), (uint32_t)(cb - pb[off]), 0x5410)
+#define D2(k, off) d[k] = cc - __byte_perm((uint32_t)pa[off], (uint32_t)pb[off], 0x5410)
   D2(0, 3 * sp);       D2(1, 3 * sp + 1);   D2(2, 2 * sp + 2);    D2(3, sp + 3);
   D2(4, 3);            D2(5, -sp + 3);      D2(6, -2 * sp + 2);   D2(7, -3 * sp + 1);
   D2(8, -3 * sp);      D2(9, -3 * sp - 1);  D2(10, -2 * sp - 2);  D2(11, -sp - 3);
   D2(12, -3);          D2(13, sp - 3);      D2(14, 2 * sp - 2);   D2(15, 3 * sp - 1);
 #undef D2
-  uint32_t mn2[16], mx2[16], mn4[16], mx4[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) { mn2[k] = __vmins2(d[k], d[(k + 1) & 15]); mx2[k] = __vmaxs2(d[k], d[(k + 1) & 15]); }
-#pragma unroll
-  for (int k = 0; k < 16; ++k) { mn4[k] = __vmins2(mn2[k], mn2[(k + 2) & 15]); mx4[k] = __vmaxs2(mx2[k], mx2[(k + 2) & 15]); }
-  uint32_t a = 0x80008000u, b = 0x7FFF7FFFu;
+  // min / max over every arc of 9 consecutive ring positions as 3 x 3 windows of three-input packed min/max (VIMNMX3):
+  // 32 + 32 instructions for the 16 arcs, then a three-input reduction tree over the arcs
+  uint32_t mn3[16], mx3[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const uint32_t mn9 = __vmins2(__vmins2(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-    const uint32_t mx9 = __vmaxs2(__vmaxs2(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-    a = __vmaxs2(a, mn9);
-    b = __vmins2(b, mx9);
+    mn3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    mx3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
   }
-  bestA = max((int)(short)(a & 0xFFFF), -(int)(short)(b & 0xFFFF));
-  bestB = max((int)(short)(a >> 16), -(int)(short)(b >> 16));
+  uint32_t mn9[16], mx9[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    mn9[k] = __vimin3_s16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);   // min over ring k..k+8
+    mx9[k] = __vimax3_s16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
+  }
+  uint32_t a5[5], b5[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    a5[k] = __vimax3_s16x2(mn9[3 * k], mn9[3 * k + 1], mn9[3 * k + 2]);
+    b5[k] = __vimin3_s16x2(mx9[3 * k], mx9[3 * k + 1], mx9[3 * k + 2]);
+  }
+  const uint32_t a = __vimax3_s16x2(__vimax3_s16x2(a5[0], a5[1], a5[2]), a5[3], __vmaxs2(a5[4], mn9[15]));
+  const uint32_t b = __vimin3_s16x2(__vimin3_s16x2(b5[0], b5[1], b5[2]), b5[3], __vmins2(b5[4], mx9[15]));
+  bestA = max((int)(a & 0xFFFF) - 256, 256 - (int)(b & 0xFFFF));
+  bestB = max((int)(a >> 16) - 256, 256 - (int)(b >> 16));
 }
 
 __global__ void __launch_bounds__(kFastThreads) fast_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM) {
