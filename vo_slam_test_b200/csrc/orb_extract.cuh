@@ -17,13 +17,7 @@ constexpr int kMinBorder = 16;       // EDGE_THRESHOLD - 3    (ORBextractor.cpp:
 constexpr int kCellsPerCta = ORBX_CELLS_PER_CTA;      // FAST cells handled by one CTA (one "slot")
 constexpr int kMaxRoots = 16;
 constexpr int kFastThreads = 128;
-#ifndef ORBX_OCT_THREADS
-#define ORBX_OCT_THREADS 128
-#endif
-#ifndef ORBX_OCT_MINB
-#define ORBX_OCT_MINB 7
-#endif
-constexpr int kOctThreads = ORBX_OCT_THREADS;
+constexpr int kOctMaxThreads = 1024; // quadtree CTA size is chosen per launch (launch_octree): 128 ... 1024
 
 struct LevelGeom {
   int w, h;                // level size

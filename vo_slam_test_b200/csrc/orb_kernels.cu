@@ -915,10 +915,10 @@ __device__ __forceinline__ int quadrant_of(const short4 b, int x, int y) {
   return (x < mx ? 0 : 1) | (y < my ? 0 : 2);     // 0:n1 1:n2 2:n3 3:n4   (:521-531)
 }
 
-__global__ void __launch_bounds__(kOctThreads, ORBX_OCT_MINB) octree_kernel(const __grid_constant__ Geom G, const Bufs B) {
+__global__ void __launch_bounds__(kOctMaxThreads) octree_kernel(const __grid_constant__ Geom G, const Bufs B) {
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int tid = threadIdx.x, T = kOctThreads;
+  const int tid = threadIdx.x, T = blockDim.x;            // 128 ... 1024 threads, chosen by the host from the frame size
 #if ORBX_OCT_FF
   const int l = blockIdx.y, f = blockIdx.x;
 #else
@@ -1010,10 +1010,11 @@ __global__ void __launch_bounds__(kOctThreads, ORBX_OCT_MINB) octree_kernel(cons
   int phase = 1;
   bool finish = false;
   while (!finish) {
-    const short4* box = S.box[cur];
-    const int* cnt = S.cnt[cur];
-    short4* nbox = S.box[cur ^ 1];
-    int* ncnt = S.cnt[cur ^ 1];
+    // selects instead of S.box[cur]: a runtime index would put the pointer struct into local memory
+    const short4* box = cur ? S.box[1] : S.box[0];
+    const int* cnt = cur ? S.cnt[1] : S.cnt[0];
+    short4* nbox = cur ? S.box[0] : S.box[1];
+    int* ncnt = cur ? S.cnt[0] : S.cnt[1];
     const int Sn = Scount;
 
     for (int i = tid; i < Sn * 4; i += T) S.cnt4[i] = 0;
@@ -2000,7 +2001,13 @@ void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cu
   launch_chain(pdl_enabled() >= 2, fast_kernel, dim3(G.totalSlots, nframes), dim3(kFastThreads), fast_smem_bytes(G), st, G, B, TM);
 }
 void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
-  launch_chain(pdl_enabled() >= 2, octree_kernel, ORBX_OCT_FF ? dim3(nframes, G.nlevels) : dim3(G.nlevels, nframes), dim3(kOctThreads), octree_smem_bytes(G), st, G, B);
+  // CTA size: barriers dominate small levels (128 threads: 1.74 ms vs 1.96 at 256 for 640x480), the quadratic ranking pass
+  // and the key loops dominate large ones (4K level 0: ~150 k candidates, ~1100 nodes); ORBX_OCT_THREADS overrides
+  static const int forced = getenv("ORBX_OCT_THREADS") ? atoi(getenv("ORBX_OCT_THREADS")) : 0;
+  const long long area = (long long)G.W * G.H;
+  int threads = area < 600000 ? 128 : area < 3000000 ? 512 : 1024;    // measured: 1080p 0.67 / 0.42 / 0.35 ms per 128 frames at 128 / 256 / 512
+  if (forced == 128 || forced == 256 || forced == 512 || forced == 1024) threads = forced;
+  launch_chain(pdl_enabled() >= 2, octree_kernel, ORBX_OCT_FF ? dim3(nframes, G.nlevels) : dim3(G.nlevels, nframes), dim3(threads), octree_smem_bytes(G), st, G, B);
 }
 void launch_blur(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st) {
   // default: TMA-staged tiles; ORBX_BLUR_TMA=0 selects the global-load walk for A/B runs
