@@ -4,7 +4,7 @@
 TAG=${1:-rX}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_$TAG.log
-SMALL="python bench.py --frames 256 --steps 1 --warmup 1 --skip-map --skip-cpu --skip-single"
+SMALL="python bench.py --frames 512 --steps 1 --warmup 1 --skip-map --skip-cpu --skip-single"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $SMALL > /dev/null 2> gpurun_out/ncu_launch_$TAG.err
 ncu --set full --clock-control none --import-source on -k regex:'resize|fast|octree|blur|orient|knn2' -s 12 -c 12 -f -o gpurun_out/prof_$TAG $SMALL > /dev/null 2> gpurun_out/ncu_full_$TAG.err
 tail -2 gpurun_out/ncu_full_$TAG.err
