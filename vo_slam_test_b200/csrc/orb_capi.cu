@@ -217,6 +217,7 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
     L.wCell = (L.regW + L.nCols - 1) / L.nCols;        // :793-794
     L.hCell = (L.regH + L.nRows - 1) / L.nRows;
     L.groups = (L.nCols + kCellsPerCta - 1) / kCellsPerCta;
+    L.groupsMagic = 0xFFFFFFFFu / (uint32_t)L.groups + 1;
     L.slot0 = slot; L.nSlots = L.nRows * L.groups;
     G.maxSlotsPerLevel = std::max(G.maxSlotsPerLevel, L.nSlots);
     L.nFeat = h->nfeat[l];

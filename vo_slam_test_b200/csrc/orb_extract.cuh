@@ -25,6 +25,7 @@ struct LevelGeom {
   int nCols, nRows;        // cells                                    (:791-792)
   int wCell, hCell;        //                                          (:793-794)
   int groups;              // CTAs per cell row
+  uint32_t groupsMagic;    // 0xFFFFFFFF / groups + 1: slot / groups == umulhi(slot, groupsMagic) for slot < 2^16
   int slot0, nSlots;       // slots of this level: nRows * groups, ordered (cell row, group)
   int nFeat;               // mnFeaturesPerLevel                       (:439-451)
   int nIni;                // quadtree roots                           (:549)

@@ -713,6 +713,13 @@ __device__ __forceinline__ int fw_stage_b(const uint8_t* img, int sp, int aox, i
 #ifndef ORBX_FAST_MINB
 #define ORBX_FAST_MINB 16
 #endif
+// kDivMagic[n] = 0xFFFFFFFF / n + 1 (n = 1..32; cells are at most 63 px = 16 quads wide): division by a warp-uniform small
+// divisor without the ~20-instruction integer division sequence
+__constant__ uint32_t kDivMagic[33] = {0u, 0u /* n == 1 is special-cased by the callers */, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u,
+    0x2AAAAAABu, 0x24924925u, 0x20000000u, 0x1C71C71Du, 0x1999999Au, 0x1745D175u, 0x15555556u, 0x13B13B14u, 0x12492493u, 0x11111112u,
+    0x10000000u, 0x0F0F0F10u, 0x0E38E38Fu, 0x0D79435Fu, 0x0CCCCCCDu, 0x0C30C30Du, 0x0BA2E8BBu, 0x0B21642Du, 0x0AAAAAABu, 0x0A3D70A4u,
+    0x09D89D8Au, 0x097B425Fu, 0x0924924Au, 0x08D3DCB1u, 0x08888889u, 0x08421085u, 0x08000000u};
+
 __global__ void __launch_bounds__(32 * kWarpCells, ORBX_FAST_MINB) fast_warp_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM) {
   pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
@@ -729,7 +736,7 @@ __global__ void __launch_bounds__(32 * kWarpCells, ORBX_FAST_MINB) fast_warp_ker
   while (l + 1 < G.nlevels && slot >= G.L[l + 1].slot0) ++l;
   const LevelGeom& L = G.L[l];
   const int ls = slot - L.slot0;
-  const int ci = ls / L.groups, grp = ls - ci * L.groups;
+  const int ci = L.groups == 1 ? ls : (int)__umulhi((uint32_t)ls, L.groupsMagic), grp = ls - ci * L.groups;   // no integer division
   const int j0 = grp * kCellsPerCta, j1 = min(j0 + kCellsPerCta, L.nCols);
   const int tx0 = j0 * L.wCell, tx1 = min(j1 * L.wCell + 6, L.regW);
   const int ty0 = ci * L.hCell, ty1 = min(ty0 + L.hCell + 6, L.regH);
@@ -813,7 +820,7 @@ __global__ void __launch_bounds__(32 * kWarpCells, ORBX_FAST_MINB) fast_warp_ker
   uint8_t* sc0 = sc + scp + jj * (L.wCell + 2) + 1;
   if (jj < j1 - j0 && cw > 0) {
     const int nq4 = (cw + 3) >> 2;
-    const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nq4 + 1;
+    const uint32_t magic = kDivMagic[min(nq4, 32)];       // item / nq4 == umulhi(item, magic) for item < 2^16
     const int sh = (ox + cx0) & 3, aox = (ox + cx0) & ~3;  // quads start at the cell's first pixel
     int t = G.iniTh;
     for (int pass = 0; pass < 2; ++pass) {
