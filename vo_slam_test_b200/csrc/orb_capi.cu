@@ -377,7 +377,10 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
               cudaEvent_t* ev = nullptr /* 6 events: before pyramid, fast, octree, blur, orient_desc, end */) {
   const Geom& G = h->G;
   if (h->map0_base != d_imgs || h->map0_row != rowStride || h->map0_frame != frameStride || h->map0_n < frame0 + n) {
-    // level 0 is the caller's buffer: (re)describe it; the map covers frames [0, frame0+n) at least
+    // level 0 is the caller's buffer: (re)describe it; the map covers frames [0, frame0+n) at least.  The descriptors live
+    // in device memory and are rewritten in place, so earlier launches of this handle (any stream) that may still read
+    // the old ones are drained first; this only happens when the caller switches input buffers.
+    if (h->map0_base) cudaDeviceSynchronize();
     encode_level_map(h, 0, d_imgs, rowStride, frameStride, std::max(frame0 + n, h->map0_want));
     h->map0_base = d_imgs; h->map0_row = rowStride; h->map0_frame = frameStride; h->map0_n = std::max(frame0 + n, h->map0_want);
   }
