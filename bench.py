@@ -300,19 +300,51 @@ def run_b200(args, rank, world, local_rank):
         gq = torch.Generator(device=dev); gq.manual_seed(99)
         d_q = torch.randint(0, 256, (Q, 32), dtype=torch.uint8, device=dev, generator=gq)
         lo = rank * Ml
-        for _ in range(2):
-            sharded.sharded_knn2_cuda(d_q, d_t, lo, TH_LOW, RATIO, dist if world > 1 else None)
-        m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True)
-        barrier()
-        m0.record()
-        reps = 5
-        for _ in range(reps):
-            sharded.sharded_knn2_cuda(d_q, d_t, lo, TH_LOW, RATIO, dist if world > 1 else None)
-        m1.record()
-        barrier()
-        mms = max_over_ranks(m0.elapsed_time(m1)) / reps
-        hamming_map = {"gmatch_per_s": world * Q * Ml / (mms * 1e6), "ms": mms, "queries": Q, "rows_per_gpu": Ml,
-                       "merge": "nccl all_gather + merge kernel" if world > 1 else "single shard"}
+        # N > 1: the exchange is fused into the kernels (P2P stores into peers' HBM over NVLink + flags); the NCCL
+        # all-gather path is the fallback (ORBX_PEER_MERGE=0, or CUDA IPC not available) and is timed beside it
+        xchg, merge_kind = None, "single shard"
+        if world > 1:
+            merge_kind = "nccl all_gather + merge kernel"
+            if os.environ.get("ORBX_PEER_MERGE", "1") != "0":
+                try:
+                    xchg = sharded.PeerExchange(dist, local_rank, Q)
+                    merge_kind = "fused: P2P stores into peers' exchange buffers (CUDA IPC over NVLink) + flag wait"
+                except Exception as e:      # noqa: BLE001
+                    sys.stderr.write("peer exchange unavailable, using NCCL all-gather: %r\n" % (e,))
+                    xchg = None
+            flags = [1 if xchg is not None else 0]
+            agree = torch.tensor(flags, device=dev, dtype=torch.int32)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            if int(agree.item()) == 0 and xchg is not None:       # every rank must take the same path
+                xchg.close(); xchg = None
+                merge_kind = "nccl all_gather + merge kernel"
+
+        def run_map(use_peer):
+            if use_peer:
+                return sharded.sharded_knn2_peer(d_q, d_t, lo, TH_LOW, RATIO, xchg, check=False)
+            return sharded.sharded_knn2_cuda(d_q, d_t, lo, TH_LOW, RATIO, dist if world > 1 else None)
+
+        def time_map(use_peer):
+            for _ in range(2):
+                run_map(use_peer)
+            m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True)
+            barrier()
+            m0.record()
+            reps = 5
+            for _ in range(reps):
+                out = run_map(use_peer)
+            m1.record()
+            barrier()
+            return max_over_ranks(m0.elapsed_time(m1)) / reps, out
+
+        mms, out = time_map(xchg is not None)
+        hamming_map = {"gmatch_per_s": world * Q * Ml / (mms * 1e6), "ms": mms, "queries": Q, "rows_per_gpu": Ml, "merge": merge_kind}
+        if xchg is not None:
+            nms, ref = time_map(False)
+            same = all(bool(torch.equal(a, b)) for a, b in zip(out, ref))
+            hamming_map["nccl_all_gather_ms"] = nms
+            hamming_map["fused_equals_nccl_path"] = same
+            xchg.close()
         del d_t
 
     # ---- end to end through the host C ABI: pinned host frames in, pinned host results out ------------------

@@ -135,6 +135,25 @@ int hamm_knn2_merge_device(const int32_t* d_idx_in, const int32_t* d_d1_in, cons
                            int nq, int th, float ratio, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2,
                            uint8_t* d_ok, void* stream);
 
+/* Sharded top-2 with the exchange fused into the kernels (BASELINE config 5): instead of an NCCL all-gather, the
+ * merge kernel of every rank STORES its per-shard records straight into exchange buffers in all peers' HBM (CUDA IPC
+ * mappings over NVLink / NVSwitch) and releases a per-source flag; the final merge acquires the flags in its own buffer.
+ *   hamm_exchange_alloc   this rank's buffer + its 64-byte IPC handle (exchange the handles with any host-side all-gather)
+ *   hamm_exchange_open    map a peer's buffer from its handle;  hamm_exchange_close / hamm_exchange_free at shutdown
+ *   hamm_knn2_sharded_device  bufs[world] = every rank's buffer as seen from this process (bufs[rank] = own);
+ *                         epoch = 1, 2, 3, ... identical on all ranks per call; d_status (int32, zero-initialised) becomes
+ *                         1 if a peer's flag did not arrive within ~1 s (the kernel never hangs).
+ * Results are identical to hamm_knn2 over the concatenated train set. */
+size_t hamm_exchange_bytes(int world, int max_queries);
+int hamm_exchange_alloc(int device, int world, int max_queries, void** buf, unsigned char ipc_handle[64]);
+int hamm_exchange_open(int device, const unsigned char ipc_handle[64], void** peer_buf);
+int hamm_exchange_close(void* peer_buf);
+int hamm_exchange_free(void* buf);
+int hamm_knn2_sharded_device(const uint8_t* d_q, int nq, const uint8_t* d_t_local, long long nt_local, long long shard_lo, int th,
+                             float ratio, int rank, int world, void* const* bufs, int max_queries, int epoch, int32_t* d_idx,
+                             int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok, int32_t* d_status, void* d_workspace,
+                             size_t workspace_bytes, void* stream);
+
 long long hamm_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------

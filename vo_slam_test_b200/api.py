@@ -97,6 +97,13 @@ def load_library():
     L.hamm_knn2_pairs_device.argtypes = [vp, vp, i32, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp]
     L.hamm_knn2_merge_device.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]
     L.hamm_launch_count.restype = ll
+    L.hamm_exchange_bytes.restype = sz
+    L.hamm_exchange_bytes.argtypes = [i32, i32]
+    L.hamm_exchange_alloc.argtypes = [i32, i32, i32, vp, vp]
+    L.hamm_exchange_open.argtypes = [i32, vp, vp]
+    L.hamm_exchange_close.argtypes = [vp]
+    L.hamm_exchange_free.argtypes = [vp]
+    L.hamm_knn2_sharded_device.argtypes = [vp, i32, vp, ll, ll, i32, f32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     L.orbx_grid_build.argtypes = [vp, i32, f32, f32, f32, f32, vp, vp, i32]
     L.orbx_search_by_projection_frame.argtypes = [vp, vp, f32, f32, i32, i32, i32, vp, vp, i32]
     L.orbx_search_by_projection_local.argtypes = [vp, vp, f32, f32, vp, vp, i32]
@@ -267,6 +274,40 @@ def knn2_merge_device(d_idx_in, d_d1_in, d_d2_in, nshards, nq, th, ratio, d_idx,
     _check(load_library().hamm_knn2_merge_device(C.c_void_p(d_idx_in), C.c_void_p(d_d1_in), C.c_void_p(d_d2_in), nshards, nq,
                                                  th, ratio, C.c_void_p(d_idx), C.c_void_p(d_d1), C.c_void_p(d_d2),
                                                  C.c_void_p(d_ok), C.c_void_p(stream)))
+
+
+def exchange_alloc(device, world, max_queries):
+    """This rank's exchange buffer for the fused sharded top-2 -> (device pointer, 64-byte CUDA IPC handle)."""
+    buf = C.c_void_p()
+    hdl = (C.c_ubyte * 64)()
+    _check(load_library().hamm_exchange_alloc(device, world, max_queries, C.byref(buf), hdl))
+    return buf.value, bytes(hdl)
+
+
+def exchange_open(device, handle):
+    """Map a peer's exchange buffer from its IPC handle -> device pointer valid in this process."""
+    buf = C.c_void_p()
+    hdl = (C.c_ubyte * 64).from_buffer_copy(handle)
+    _check(load_library().hamm_exchange_open(device, hdl, C.byref(buf)))
+    return buf.value
+
+
+def exchange_close(ptr):
+    _check(load_library().hamm_exchange_close(C.c_void_p(ptr)))
+
+
+def exchange_free(ptr):
+    _check(load_library().hamm_exchange_free(C.c_void_p(ptr)))
+
+
+def knn2_sharded_device(d_q, nq, d_t, nt, shard_lo, th, ratio, rank, world, bufs, max_queries, epoch, d_idx, d_d1, d_d2, d_ok,
+                        d_status, d_ws=0, ws_bytes=0, stream=0):
+    """Local shard top-2 + peer-memory scatter + merge (hamm_knn2_sharded_device); bufs = list of `world` device pointers."""
+    arr = (C.c_void_p * world)(*bufs)
+    _check(load_library().hamm_knn2_sharded_device(C.c_void_p(d_q), nq, C.c_void_p(d_t), nt, shard_lo, th, ratio, rank, world, arr,
+                                                   max_queries, epoch, C.c_void_p(d_idx), C.c_void_p(d_d1), C.c_void_p(d_d2),
+                                                   C.c_void_p(d_ok), C.c_void_p(d_status), C.c_void_p(d_ws), ws_bytes,
+                                                   C.c_void_p(stream)))
 
 
 def knn2_workspace_bytes(nq, nt):

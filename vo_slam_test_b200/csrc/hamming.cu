@@ -9,6 +9,7 @@
 // Realised with packed keys  key = dist << 23 | local_index : min() over keys prefers the smaller distance and,
 // for equal distances, the smaller index; second best = min(best2, max(key, old best1)).
 #include <atomic>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -191,6 +192,84 @@ __global__ void __launch_bounds__(kQT) knn2_pairs_kernel(const uint8_t* __restri
   ok[o] = accept(bd1, bd2, th, ratio);
 }
 
+// ---- sharded top-2 with the exchange fused into the kernels (no NCCL on the data path) -------------------------------
+// Every rank owns an exchange buffer in its HBM that all peers have mapped (CUDA IPC over NVLink / NVSwitch):
+//   int32 [0, 2*kMaxPeers)   flags[parity][source rank] = epoch of the last completed scatter of that source
+//   int32 [32]               CTA counter of the local scatter kernel
+//   int32 [kXchgHdr ...)     records[parity][source rank][max_queries][3] = (global idx, d1, d2)
+// knn2_merge_scatter_kernel merges the per-split partials of the local shard and STORES each record straight into all
+// peers' buffers (P2P stores), fences at system scope; the last CTA then releases flags[parity][rank] = epoch on every peer.
+// knn2_gather_merge_kernel acquires the flags of all sources in its own buffer (bounded spin) and merges the records.
+// Two parities alternate per call: a rank that is one call ahead writes the other half, and it cannot get two calls
+// ahead because its gather of call n+1 waits for every peer's scatter of call n+1.
+constexpr int kMaxPeers = 16;
+constexpr int kXchgHdr = 64;
+struct PeerSet { int32_t* p[kMaxPeers]; };
+__host__ __device__ inline size_t xchg_rec_off(int parity, int src, int world, int maxq) {
+  return (size_t)kXchgHdr + ((size_t)(parity * world + src) * maxq) * 3;
+}
+__device__ __forceinline__ void st_release_sys(int32_t* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void knn2_merge_scatter_kernel(const int32_t* __restrict__ pidx, const int32_t* __restrict__ pd1,
+                                          const int32_t* __restrict__ pd2, int stride, int nparts, int nq, long long shard_lo,
+                                          PeerSet peers, int rank, int world, int maxq, int parity, int epoch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) {
+    int b1 = 256, b2 = 256, bi = -1;
+    for (int s = 0; s < nparts; ++s) {
+      const size_t o = ((size_t)s * nq + i) * stride;
+      const int a1 = pd1[o], a2 = pd2[o], ai = pidx[o];
+      if (a1 < b1) { b2 = min(b1, a2); b1 = a1; bi = ai; }
+      else { b2 = min(b2, a1); }
+    }
+    const int gi = bi >= 0 ? (int)(shard_lo + bi) : -1;       // local -> global row index
+    const size_t o = xchg_rec_off(parity, rank, world, maxq) + (size_t)3 * i;
+    for (int p = 0; p < world; ++p) {
+      int32_t* r = peers.p[p] + o;
+      r[0] = gi; r[1] = b1; r[2] = b2;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t* done = peers.p[rank] + 32;
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1) {           // last CTA: every record of this rank is written and fenced
+      atomicExch(done, 0);
+      __threadfence_system();
+      for (int p = 0; p < world; ++p) st_release_sys(peers.p[p] + parity * kMaxPeers + rank, epoch);
+    }
+  }
+}
+
+__global__ void knn2_gather_merge_kernel(const int32_t* __restrict__ own, int world, int nq, int maxq, int parity, int epoch, int th,
+                                         float ratio, int32_t* idx, int32_t* d1, int32_t* d2, uint8_t* ok, int32_t* status) {
+  if ((int)threadIdx.x < world) {                            // one thread per source rank; ~1 s bound instead of a hang
+    const int32_t* flag = own + parity * kMaxPeers + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) != epoch) {
+      if (clock64() - t0 > 2000000000LL) { atomicExch(status, 1); break; }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  int b1 = 256, b2 = 256, bi = -1;
+  for (int s = 0; s < world; ++s) {                           // sources in ascending train-index order
+    const int32_t* r = own + xchg_rec_off(parity, s, world, maxq) + (size_t)3 * i;
+    const int ai = __ldcg(r), a1 = __ldcg(r + 1), a2 = __ldcg(r + 2);   // L2 only: peers wrote these lines
+    if (a1 < b1) { b2 = min(b1, a2); b1 = a1; bi = ai; }
+    else { b2 = min(b2, a1); }
+  }
+  idx[i] = bi; d1[i] = b1; d2[i] = b2;
+  ok[i] = accept(b1, b2, th, ratio);
+}
+
 static int pick_splits(int nq, long long nt, long long* per_out) {
   if (nt <= 0 || nq <= 0) { *per_out = kTT; return 1; }
   const int qtiles = (nq + kQT - 1) / kQT;
@@ -301,6 +380,87 @@ int hamm_knn2_merge_device(const int32_t* d_idx_in, const int32_t* d_d1_in, cons
   knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_idx_in, d_d1_in, d_d2_in, 1, nshards, nq, th, ratio,
                                                                        d_idx, d_d1, d_d2, d_ok);
   g_hamm_launches++;
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+size_t hamm_exchange_bytes(int world, int max_queries) {
+  if (world < 1 || world > kMaxPeers || max_queries < 1) return 0;
+  return sizeof(int32_t) * (xchg_rec_off(2, 0, world, max_queries));
+}
+
+int hamm_exchange_alloc(int device, int world, int max_queries, void** buf, unsigned char ipc_handle[64]) {
+  const size_t bytes = hamm_exchange_bytes(world, max_queries);
+  if (!buf || !ipc_handle || bytes == 0) { set_error("bad argument"); return ORBX_ERR_ARG; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  ORBX_CUDA(cudaSetDevice(device));
+  void* p = nullptr;
+  ORBX_CUDA(cudaMalloc(&p, bytes));
+  ORBX_CUDA(cudaMemset(p, 0, bytes));
+  ORBX_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t hdl;
+  cudaError_t e = cudaIpcGetMemHandle(&hdl, p);
+  if (e != cudaSuccess) { cudaFree(p); set_error(cudaGetErrorString(e)); return ORBX_ERR_CUDA; }
+  memcpy(ipc_handle, &hdl, 64);
+  *buf = p;
+  return ORBX_OK;
+}
+
+int hamm_exchange_open(int device, const unsigned char ipc_handle[64], void** peer_buf) {
+  if (!ipc_handle || !peer_buf) { set_error("bad argument"); return ORBX_ERR_ARG; }
+  ORBX_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t hdl;
+  memcpy(&hdl, ipc_handle, 64);
+  ORBX_CUDA(cudaIpcOpenMemHandle(peer_buf, hdl, cudaIpcMemLazyEnablePeerAccess));
+  return ORBX_OK;
+}
+
+int hamm_exchange_close(void* peer_buf) {
+  if (peer_buf) ORBX_CUDA(cudaIpcCloseMemHandle(peer_buf));
+  return ORBX_OK;
+}
+
+int hamm_exchange_free(void* buf) {
+  if (buf) ORBX_CUDA(cudaFree(buf));
+  return ORBX_OK;
+}
+
+int hamm_knn2_sharded_device(const uint8_t* d_q, int nq, const uint8_t* d_t, long long nt, long long shard_lo, int th, float ratio,
+                             int rank, int world, void* const* bufs, int max_queries, int epoch, int32_t* d_idx, int32_t* d_d1,
+                             int32_t* d_d2, uint8_t* d_ok, int32_t* d_status, void* d_workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (!d_q || (!d_t && nt > 0) || !d_idx || !d_d1 || !d_d2 || !d_ok || !d_status || !bufs || nq < 0 || nt < 0 || world < 1 ||
+      world > kMaxPeers || rank < 0 || rank >= world || nq > max_queries || epoch < 1) {
+    set_error("bad argument");
+    return ORBX_ERR_ARG;
+  }
+  if (nq == 0) return ORBX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  PeerSet peers{};
+  for (int p = 0; p < world; ++p) {
+    if (!bufs[p]) { set_error("null exchange buffer"); return ORBX_ERR_ARG; }
+    peers.p[p] = (int32_t*)bufs[p];
+  }
+  long long per;
+  const int ns = pick_splits(nq, nt, &per);
+  if (ns > 1 && (!d_workspace || workspace_bytes < (size_t)ns * nq * 3 * sizeof(int32_t))) {
+    set_error("workspace too small (see hamm_knn2_workspace_bytes)");
+    return ORBX_ERR_CAPACITY;
+  }
+  // local shard: per-split partials (ns > 1) or the shard result in the output arrays (ns == 1), local row indices
+  dim3 grid((nq + kQT - 1) / kQT, ns);
+  knn2_kernel<<<grid, kQT, 0, st>>>(d_q, nq, d_t, nt, per, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace);
+  const int parity = epoch & 1;
+  const int32_t* part = (const int32_t*)d_workspace;
+  if (ns > 1)
+    knn2_merge_scatter_kernel<<<(nq + 127) / 128, 128, 0, st>>>(part, part + 1, part + 2, 3, ns, nq, shard_lo, peers, rank, world,
+                                                               max_queries, parity, epoch);
+  else
+    knn2_merge_scatter_kernel<<<(nq + 127) / 128, 128, 0, st>>>(d_idx, d_d1, d_d2, 1, 1, nq, shard_lo, peers, rank, world,
+                                                               max_queries, parity, epoch);
+  knn2_gather_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(peers.p[rank], world, nq, max_queries, parity, epoch, th, ratio, d_idx,
+                                                            d_d1, d_d2, d_ok, d_status);
+  g_hamm_launches += 3;
   ORBX_CUDA(cudaGetLastError());
   return ORBX_OK;
 }

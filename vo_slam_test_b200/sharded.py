@@ -81,3 +81,54 @@ def sharded_knn2_cuda(d_q, d_t_local, shard_lo, th, ratio, dist, stream=None):
     api.knn2_merge_device(parts[0].data_ptr(), parts[1].data_ptr(), parts[2].data_ptr(), world, Q, th, ratio,
                           idx.data_ptr(), d1.data_ptr(), d2.data_ptr(), ok.data_ptr(), st)
     return idx, d1, d2, ok
+
+
+class PeerExchange:
+    """Exchange buffers of the fused sharded top-2 (hamm_knn2_sharded_device): every rank allocates one buffer in its HBM,
+    the 64-byte CUDA IPC handles are all-gathered once on the host side, and every rank maps all peers' buffers.  After
+    that the per-call data path has no collective: the merge kernel stores its records into the peers' buffers over
+    NVLink and the final merge waits on per-source flags in its own buffer."""
+
+    def __init__(self, dist, device, max_queries):
+        from . import api
+        self.dist, self.device, self.max_queries = dist, int(device), int(max_queries)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.own, handle = api.exchange_alloc(self.device, self.world, self.max_queries)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle)
+        self.bufs = [self.own if r == self.rank else api.exchange_open(self.device, handles[r]) for r in range(self.world)]
+        self.epoch = 0
+        dist.barrier()                       # nobody scatters before every rank has mapped every buffer
+
+    def close(self):
+        from . import api
+        if self.bufs is None:
+            return
+        self.dist.barrier()                  # nobody unmaps while a peer may still store into it
+        for r, b in enumerate(self.bufs):
+            if r != self.rank:
+                api.exchange_close(b)
+        self.dist.barrier()
+        api.exchange_free(self.own)
+        self.bufs = None
+
+
+def sharded_knn2_peer(d_q, d_t_local, shard_lo, th, ratio, xchg, check=True):
+    """Same contract as sharded_knn2_cuda, but the exchange is fused into the kernels (xchg = PeerExchange).  `check`
+    reads the status word back (one sync) and raises if a peer's records did not arrive."""
+    import torch
+    from . import api
+    Q, Ml = d_q.shape[0], d_t_local.shape[0]
+    dev = d_q.device
+    idx = torch.empty(Q, dtype=torch.int32, device=dev); d1 = torch.empty_like(idx); d2 = torch.empty_like(idx)
+    ok = torch.empty(Q, dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    wsb = api.knn2_workspace_bytes(Q, Ml)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+    xchg.epoch += 1
+    api.knn2_sharded_device(d_q.data_ptr(), Q, d_t_local.data_ptr(), Ml, int(shard_lo), th, ratio, xchg.rank, xchg.world, xchg.bufs,
+                            xchg.max_queries, xchg.epoch, idx.data_ptr(), d1.data_ptr(), d2.data_ptr(), ok.data_ptr(),
+                            status.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
+    if check and int(status.item()) != 0:
+        raise RuntimeError("sharded top-2: a peer's records did not arrive (exchange timed out)")
+    return idx, d1, d2, ok
