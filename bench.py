@@ -312,11 +312,8 @@ def run_b200(args, rank, world, local_rank):
                 except Exception as e:      # noqa: BLE001
                     sys.stderr.write("peer exchange unavailable, using NCCL all-gather: %r\n" % (e,))
                     xchg = None
-            flags = [1 if xchg is not None else 0]
-            agree = torch.tensor(flags, device=dev, dtype=torch.int32)
-            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
-            if int(agree.item()) == 0 and xchg is not None:       # every rank must take the same path
-                xchg.close(); xchg = None
+            # PeerExchange agrees on success across ranks itself (every rank raises or none does)
+            if xchg is None:
                 merge_kind = "nccl all_gather + merge kernel"
 
         def run_map(use_peer):

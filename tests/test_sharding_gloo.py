@@ -100,3 +100,45 @@ def test_sharded_knn_and_frame_blocks_gloo(world):
     for rank, mi, m1, m2, cnt in res:
         assert np.array_equal(mi, want[0]) and np.array_equal(m1, want[1]) and np.array_equal(m2, want[2])
         assert np.array_equal(cnt, wantcnt)       # every frame extracted exactly once across ranks
+
+
+def _peer_setup_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        try:
+            sharded.PeerExchange(dist, 0, 16)
+            out.put((rank, "constructed"))
+        except RuntimeError as e:
+            out.put((rank, "raised: %s" % e))
+        t = __import__("torch").ones(1)
+        dist.all_reduce(t)                    # the ranks are still in step after the failed set-up
+        out.put((rank, "in step %d" % int(t.item())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_setup_fails_on_every_rank_together():
+    """Without a CUDA device the exchange buffers cannot be allocated.  The set-up must then fail on EVERY rank (no rank may
+    be left waiting in a collective) and leave the process group usable -- the property bench.py's fallback to the NCCL
+    all-gather relies on."""
+    import torch.multiprocessing as mp
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without CUDA: with a GPU the set-up succeeds (covered by the -m gpu tests / bench --gpus 2)")
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_setup_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in range(2 * world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in range(world):
+        msgs = [m for r, m in res if r == rank]
+        assert any(m.startswith("raised: peer exchange set-up failed") for m in msgs), msgs
+        assert "in step 2" in msgs

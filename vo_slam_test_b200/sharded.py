@@ -93,12 +93,36 @@ class PeerExchange:
         from . import api
         self.dist, self.device, self.max_queries = dist, int(device), int(max_queries)
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.own, handle = api.exchange_alloc(self.device, self.world, self.max_queries)
+        self.bufs, self.own, self.epoch = None, None, 0
+        # Every rank runs the SAME sequence of collectives whatever fails locally (a rank that raised early would leave
+        # its peers waiting in a collective): local failures are recorded and agreed on afterwards.
+        handle, err = None, None
+        try:
+            self.own, handle = api.exchange_alloc(self.device, self.world, self.max_queries)
+        except Exception as e:      # noqa: BLE001
+            err = repr(e)
         handles = [None] * self.world
         dist.all_gather_object(handles, handle)
-        self.bufs = [self.own if r == self.rank else api.exchange_open(self.device, handles[r]) for r in range(self.world)]
-        self.epoch = 0
-        dist.barrier()                       # nobody scatters before every rank has mapped every buffer
+        bufs = [None] * self.world
+        if err is None and all(h is not None for h in handles):
+            try:
+                for r in range(self.world):
+                    bufs[r] = self.own if r == self.rank else api.exchange_open(self.device, handles[r])
+            except Exception as e:  # noqa: BLE001
+                err = repr(e)
+        elif err is None:
+            err = "a peer could not allocate its exchange buffer"
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err)          # also the barrier: nobody scatters before every rank has mapped every buffer
+        if any(e is not None for e in errs):
+            for r, b in enumerate(bufs):
+                if b is not None and r != self.rank:
+                    api.exchange_close(b)
+            if self.own is not None:
+                api.exchange_free(self.own)
+            self.own = None
+            raise RuntimeError("peer exchange set-up failed: %s" % next(e for e in errs if e is not None))
+        self.bufs = bufs
 
     def close(self):
         from . import api
