@@ -1946,6 +1946,16 @@ __global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __
   }
 }
 
+// Latency mode: with a handful of frames per launch (orbx_extract: one) the chunk chain is bound by launch + CTA start-up
+// latency, so every kernel is launched as a programmatic dependent launch; with full chunks that costs 2 % (ORBX_PDL).
+// (measured, one frame per call: VGA 0.242 -> 0.208 ms; at 1080p the early-resident CTAs of the next kernel take slots
+// from the running one and it gets slower, hence the pixel bound)
+constexpr int kLatencyFrames = 8;
+constexpr long long kLatencyPixels = 1000000;
+static inline bool pdl_long(const Geom& G, int nframes) {
+  return pdl_enabled() >= 2 || (pdl_enabled() >= 1 && (long long)nframes * G.W * G.H <= kLatencyPixels);
+}
+
 // ---- launch wrappers (called from the C ABI in orb_capi.cu) ---------------------------------------------
 void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe, uint8_t* dst, int dw, int dh,
                    int dpitch, size_t dframe, const ResizeTaps& T, const ResizeTma& R, const CUtensorMap* map, int z0, int nframes,
@@ -2002,31 +2012,32 @@ static bool use_fast_warp() {
 
 void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st) {
   if (use_fast_warp()) {
-    launch_chain(pdl_enabled() >= 2, fast_warp_kernel, ORBX_FAST_FF ? dim3(nframes, G.totalSlots) : dim3(G.totalSlots, nframes), dim3(32 * kWarpCells), fast_warp_smem_bytes(G), st, G, B, TM);
+    launch_chain(pdl_long(G, nframes), fast_warp_kernel, ORBX_FAST_FF ? dim3(nframes, G.totalSlots) : dim3(G.totalSlots, nframes), dim3(32 * kWarpCells), fast_warp_smem_bytes(G), st, G, B, TM);
     return;
   }
-  launch_chain(pdl_enabled() >= 2, fast_kernel, dim3(G.totalSlots, nframes), dim3(kFastThreads), fast_smem_bytes(G), st, G, B, TM);
+  launch_chain(pdl_long(G, nframes), fast_kernel, dim3(G.totalSlots, nframes), dim3(kFastThreads), fast_smem_bytes(G), st, G, B, TM);
 }
 void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
   // CTA size: barriers dominate small levels (128 threads: 1.74 ms vs 1.96 at 256 for 640x480), the quadratic ranking pass
   // and the key loops dominate large ones (4K level 0: ~150 k candidates, ~1100 nodes); ORBX_OCT_THREADS overrides
   static const int forced = getenv("ORBX_OCT_THREADS") ? atoi(getenv("ORBX_OCT_THREADS")) : 0;
   const long long area = (long long)G.W * G.H;
-  int threads = area < 600000 ? 128 : area < 3000000 ? 512 : 1024;    // measured: 1080p 0.67 / 0.42 / 0.35 ms per 128 frames at 128 / 256 / 512
+  int threads = area < 600000 ? 128 : area < 3000000 ? 512 : 1024;
+  if (nframes <= kLatencyFrames) threads = std::max(threads, 512);   // a handful of CTAs: the level-0 CTA is the critical path    // measured: 1080p 0.67 / 0.42 / 0.35 ms per 128 frames at 128 / 256 / 512
   if (forced == 128 || forced == 256 || forced == 512 || forced == 1024) threads = forced;
-  launch_chain(pdl_enabled() >= 2, octree_kernel, ORBX_OCT_FF ? dim3(nframes, G.nlevels) : dim3(G.nlevels, nframes), dim3(threads), octree_smem_bytes(G), st, G, B);
+  launch_chain(pdl_long(G, nframes), octree_kernel, ORBX_OCT_FF ? dim3(nframes, G.nlevels) : dim3(G.nlevels, nframes), dim3(threads), octree_smem_bytes(G), st, G, B);
 }
 void launch_blur(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st) {
   // default: TMA-staged tiles; ORBX_BLUR_TMA=0 selects the global-load walk for A/B runs
   static const bool tma = !(getenv("ORBX_BLUR_TMA") && atoi(getenv("ORBX_BLUR_TMA")) == 0);
   if (tma && TM.useBlur) {
-    launch_chain(pdl_enabled() >= 2, blur_tma_kernel, dim3(nframes, G.bwTiles), dim3(128), 0, st, G, B, TM);
+    launch_chain(pdl_long(G, nframes), blur_tma_kernel, dim3(nframes, G.bwTiles), dim3(128), 0, st, G, B, TM);
     return;
   }
   // default: the register-blocked kernel; ORBX_BLUR_WALK=0 selects the shared-memory tile kernel for A/B runs
   static const bool walk = !(getenv("ORBX_BLUR_WALK") && atoi(getenv("ORBX_BLUR_WALK")) == 0);
-  if (walk) launch_chain(pdl_enabled() >= 2, blur_walk_kernel, dim3(nframes, G.bwTiles), dim3(128), 0, st, G, B);
-  else launch_chain(pdl_enabled() >= 2, blur_kernel, dim3(G.blurTiles, nframes), dim3(256), 0, st, G, B);
+  if (walk) launch_chain(pdl_long(G, nframes), blur_walk_kernel, dim3(nframes, G.bwTiles), dim3(128), 0, st, G, B);
+  else launch_chain(pdl_long(G, nframes), blur_kernel, dim3(G.blurTiles, nframes), dim3(256), 0, st, G, B);
 }
 void launch_orient_desc(const Geom& G, const Bufs& B, const TmaSet& TM, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
                         int frame0, int nframes, cudaStream_t st) {
@@ -2034,11 +2045,11 @@ void launch_orient_desc(const Geom& G, const Bufs& B, const TmaSet& TM, orbx_key
   static const bool tma = !(getenv("ORBX_OD_TMA") && atoi(getenv("ORBX_OD_TMA")) == 0);
   if (tma && TM.usePatch) {
     const int per = kOdWarps * kOdK;
-    launch_chain(pdl_enabled() >= 2, orient_desc_tma_kernel, ORBX_OD_FF ? dim3(nframes, (G.selPerFrame + per - 1) / per) : dim3((G.selPerFrame + per - 1) / per, nframes), dim3(32 * kOdWarps), 0, st,
+    launch_chain(pdl_long(G, nframes), orient_desc_tma_kernel, ORBX_OD_FF ? dim3(nframes, (G.selPerFrame + per - 1) / per) : dim3((G.selPerFrame + per - 1) / per, nframes), dim3(32 * kOdWarps), 0, st,
                  G, B, TM, kps, desc, cap, counts, frame0);
     return;
   }
-  launch_chain(pdl_enabled() >= 2, orient_desc_kernel, dim3((G.selPerFrame + 7) / 8, nframes), dim3(256), 0, st, G, B, kps, desc, cap, counts, frame0);
+  launch_chain(pdl_long(G, nframes), orient_desc_kernel, dim3((G.selPerFrame + 7) / 8, nframes), dim3(256), 0, st, G, B, kps, desc, cap, counts, frame0);
 }
 
 }  // namespace orbx
