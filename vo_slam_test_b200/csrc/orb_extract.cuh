@@ -109,7 +109,11 @@ struct ResizeTaps {        // device tables of one level
 
 // TMA staging of the resize source (resize_tma_kernel): a CTA produces a 128 x 64 destination tile from ONE
 // cp.async.bulk.tensor box of the source level; the box origin of every tile column / tile row comes from the tap tables.
-constexpr int kRzTileW = 128, kRzTileH = 64, kRzMaxTX = 32, kRzMaxTY = 48;
+#ifndef ORBX_RW_ROWS
+#define ORBX_RW_ROWS 16                // destination rows per thread of the resize walks (A/B builds: 8, 32)
+#endif
+constexpr int kRwRows = ORBX_RW_ROWS;
+constexpr int kRzTileW = 128, kRzTileH = 4 * kRwRows, kRzMaxTX = 32, kRzMaxTY = 3072 / kRzTileH;
 struct ResizeTma {
   int use;                 // descriptor valid and the boxes fit (else: resize_walk_kernel)
   int boxW, boxH;          // bytes x rows, boxW a multiple of 16, both <= 256

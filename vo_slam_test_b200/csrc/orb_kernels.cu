@@ -116,7 +116,6 @@ __global__ void __launch_bounds__(256) resize4_kernel(const uint8_t* __restrict_
 // horizontal interpolation of a source row is reused by the next destination row whenever its first tap row is the
 // previous row's second one (4 rows out of 5 at scale 1.2): 1.25 instead of 2 horizontal passes per destination row.
 // A warp = 32 quads of one row segment, so the reuse test is warp-uniform.  Same integer arithmetic.
-constexpr int kRwRows = 16;
 
 __global__ void __launch_bounds__(128) resize_walk_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                                                           size_t sframe, uint8_t* __restrict__ dst, int dw, int dh,
@@ -1760,8 +1759,14 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(const __grid_constant_
 //  * the 16 pattern points of a lane stay in registers across the warp's keypoints;
 //  * cvRound = add-magic-number rounding on the FMA pipe (exact round-half-even for |v| < 2^22) instead of F2I.
 // Arithmetic and output are identical to orient_desc_kernel.
-constexpr int kOdK = 4;                 // consecutive selected-keypoint slots per warp
-constexpr int kOdWarps = 4;             // warps per CTA
+#ifndef ORBX_OD_K
+#define ORBX_OD_K 8
+#endif
+#ifndef ORBX_OD_WARPS
+#define ORBX_OD_WARPS 4
+#endif
+constexpr int kOdK = ORBX_OD_K;         // consecutive selected-keypoint slots per warp
+constexpr int kOdWarps = ORBX_OD_WARPS; // warps per CTA
 constexpr int kOdStage = 3968;          // bytes per ring stage: 48x31 patch at 0, 64x37 patch at 1536 (both 128-byte aligned)
 constexpr int kOdBOff = 1536;
 constexpr uint32_t kOdTx = kOdUW * kOdUH + kOdBW * kOdBH;
