@@ -102,8 +102,24 @@ int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
-int resident_chunk() { return std::max(1, env_int("ORBX_CHUNK", kDefaultChunk)); }
-int host_chunk() { return std::max(1, env_int("ORBX_CHUNK_HOST", env_int("ORBX_CHUNK", kDefaultHostChunk))); }
+// The workspace (pyramid, blurred pyramid, candidate lists) is about 8 bytes per input pixel per frame of the chunk; the
+// default chunk is capped so that it stays below ~4 GiB (VGA: 512 frames = 1 GB, 1080p: 256, 4K: 64).  An explicit
+// ORBX_CHUNK / ORBX_CHUNK_HOST is taken as given.
+int capped_chunk(int dflt, int w, int hgt) {
+  const long long per_frame = 8LL * w * hgt;
+  const long long cap = std::max(16LL, (4LL << 30) / std::max(per_frame, 1LL));
+  int c = (int)std::min<long long>(dflt, cap);
+  if (c >= 64) c &= ~31;
+  return std::max(1, c);
+}
+int resident_chunk(int w, int hgt) {
+  const int e = env_int("ORBX_CHUNK", 0);
+  return e > 0 ? e : capped_chunk(kDefaultChunk, w, hgt);
+}
+int host_chunk(int w, int hgt) {
+  const int e = env_int("ORBX_CHUNK_HOST", env_int("ORBX_CHUNK", 0));
+  return e > 0 ? e : capped_chunk(kDefaultHostChunk, w, hgt);
+}
 
 // Chunk schedule of the host-pipelined path: a short first chunk (kernels start after a quarter-chunk upload) and a short
 // last one (only a quarter chunk of kernels + download is left when the last upload ends), full chunks in between.
@@ -565,7 +581,7 @@ int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes,
   }
   if (nframes == 0) return ORBX_OK;
   ORBX_CUDA(cudaSetDevice(h->p.device));
-  const int chunk = std::min(nframes, resident_chunk());
+  const int chunk = std::min(nframes, resident_chunk(w, height));
   int rc = configure(h, w, height, chunk);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -646,7 +662,7 @@ int orbx_profile_stages(orbx_handle h, const uint8_t* d_imgs, int nframes, int w
     return ORBX_ERR_ARG;
   }
   ORBX_CUDA(cudaSetDevice(h->p.device));
-  const int chunk = std::min(nframes, resident_chunk());
+  const int chunk = std::min(nframes, resident_chunk(w, height));
   int rc = configure(h, w, height, chunk);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -688,8 +704,8 @@ int orbx_extract_match_batch(orbx_handle h, const uint8_t* imgs, int nframes, in
     return ORBX_ERR_ARG;
   }
   ORBX_CUDA(cudaSetDevice(h->p.device));
-  const std::vector<std::pair<int, int>> sched = host_schedule(nframes, std::min(nframes, host_chunk()));
-  int rc = configure(h, w, height, std::min(nframes, host_chunk()));
+  const std::vector<std::pair<int, int>> sched = host_schedule(nframes, std::min(nframes, host_chunk(w, height)));
+  int rc = configure(h, w, height, std::min(nframes, host_chunk(w, height)));
   if (rc) return rc;
   const size_t pitch = align_up_sz((size_t)w, 64), fbytes = pitch * height;
   const int npairs = nframes - 1;

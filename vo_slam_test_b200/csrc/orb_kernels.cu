@@ -855,7 +855,8 @@ __global__ void __launch_bounds__(32 * kWarpCells, ORBX_FAST_MINB) fast_warp_ker
         nc += __popc(bal0) + __popc(bal1);
         __syncwarp();
       }
-      // NMS inside the cell (outside the cell counts as 0); survivors appended in any order, ranked later
+      // NMS inside the cell (the zero frame of the score map = "outside the cell counts as 0"); the ballot compaction keeps
+      // the queue's (row, column) order, which is the emission order
       for (int base = 0; base < nc; base += 32) {
         const int k = base + lane;
         bool keep = false;
