@@ -123,6 +123,33 @@ def test_edge_cases(vo):
     ex.close()
 
 
+@pytest.mark.parametrize("kind", ["noise", "checker3", "checker2", "saltpepper", "stripes", "blocks_equal_scores"])
+@pytest.mark.parametrize("H,W,nf", [(240, 320, 500), (480, 640, 1000)])
+def test_adversarial_images(vo, kind, H, W, nf):
+    """Corner-dense inputs: every queue of the FAST kernel near its worst case, thousands of equal scores for the NMS and the
+    quadtree's strongest-key ties, cells with no corner at all next to saturated ones."""
+    rng = np.random.default_rng(H + len(kind))
+    yy, xx = np.indices((H, W))
+    img = {
+        "noise": lambda: rng.integers(0, 256, (H, W), dtype=np.uint8),
+        "checker3": lambda: (((yy // 3 + xx // 3) % 2) * 255).astype(np.uint8),
+        "checker2": lambda: (((yy // 2 + xx // 2) % 2) * 200 + 20).astype(np.uint8),
+        "saltpepper": lambda: np.where(rng.random((H, W)) < 0.1, 255, 0).astype(np.uint8),
+        "stripes": lambda: ((xx % 4 < 2) * 255).astype(np.uint8),
+        "blocks_equal_scores": lambda: (((yy // 9 + xx // 11) % 2) * 90 + 60).astype(np.uint8),
+    }[kind]()
+    P = oracle.Port(nf)
+    ex = vo.ORBextractor(nf, 1.2, 8, 20, 7)
+    kps, desc = ex(img)
+    _stage_check(ex, P, img, P.tables()[2])
+    rk, rd = P.extract(img)
+    assert len(kps) == len(rk)
+    for name in KP_FIELDS:
+        assert np.array_equal(kps[name].view(np.uint32), rk[name].view(np.uint32)), name
+    assert np.array_equal(desc, rd)
+    ex.close()
+
+
 def test_other_parameters(vo):
     img = synth.make_frame(77, 600, 800)
     for (nf, sf, nl, ini, mn) in [(500, 1.2, 4, 20, 7), (1500, 1.1, 8, 30, 10), (800, 1.5, 5, 12, 5)]:
