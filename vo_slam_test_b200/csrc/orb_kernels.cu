@@ -369,13 +369,19 @@ __device__ __forceinline__ uint32_t reject4_b(const uint8_t* rowm3, int sp, uint
   return m;
 }
 
+__device__ __forceinline__ uint32_t pack_lo_hi(uint32_t lo, uint32_t hi) {   // lo | hi << 16 for lo, hi < 2^16, as one IMAD
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+  return r;
+}
 // Corner strength of TWO pixels at once in packed signed 16-bit lanes (VIMNMX.S16x2).
 __device__ __forceinline__ void fast_best2(const uint8_t* pa, const uint8_t* pb, int sp, int& bestA, int& bestB) {
   // d = centre - ring pixel, both pixels' differences in one register.  The centres carry a bias of 256 per lane so that ONE
   // 32-bit subtraction serves both lanes (the low lane never borrows); min/max commute with the bias, removed at the end.
   const uint32_t cc = ((uint32_t)pa[0] + 256u) | (((uint32_t)pb[0] + 256u) << 16);
   uint32_t d[16];
-#define D2(k, off) d[k] = cc - __byte_perm((uint32_t)pa[off], (uint32_t)pb[off], 0x5410)
+  // the two ring bytes are packed by a multiply-add (FMA pipe) instead of PRMT: the ALU pipe is the bound of this kernel
+#define D2(k, off) d[k] = cc - pack_lo_hi((uint32_t)pa[off], (uint32_t)pb[off])
   D2(0, 3 * sp);       D2(1, 3 * sp + 1);   D2(2, 2 * sp + 2);    D2(3, sp + 3);
   D2(4, 3);            D2(5, -sp + 3);      D2(6, -2 * sp + 2);   D2(7, -3 * sp + 1);
   D2(8, -3 * sp);      D2(9, -3 * sp - 1);  D2(10, -2 * sp - 2);  D2(11, -sp - 3);
