@@ -19,6 +19,12 @@
 
 namespace orbx {
 
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {   // a * b + c as one IMAD (FMA pipe), never LEA/SHF
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
 __device__ __forceinline__ const uint8_t* level_ptr(const Geom& G, const Bufs& B, int l, int f, int& pitch) {
   if (l == 0) {
     pitch = (int)B.rowStride0;
@@ -264,8 +270,10 @@ __global__ void __launch_bounds__(128) resize_tma_kernel(const CUtensorMap* __re
     if (live) {
       uint32_t v[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = (uint32_t)((((b0 * h0[k]) >> 16) + ((b1 * h1[k]) >> 16) + 2) >> 2);
-      const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+      // "+ 2" rides on the second product (a multiple of 2^16 added before the floor shift) and the four results (<= 255)
+      // are packed by multiply-adds: both moves take work off the ALU pipe, the bound of this kernel, onto the FMA pipe
+      for (int k = 0; k < 4; ++k) v[k] = (uint32_t)((((b0 * h0[k]) >> 16) + ((b1 * h1[k] + 0x20000) >> 16)) >> 2);
+      const uint32_t out = mad_u32(mad_u32(mad_u32(v[3], 256u, v[2]), 256u, v[1]), 256u, v[0]);
       if (whole) {
         *reinterpret_cast<uint32_t*>(d) = out;
       } else {
