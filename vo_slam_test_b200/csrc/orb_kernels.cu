@@ -766,13 +766,13 @@ __global__ void __launch_bounds__(32 * kWarpCells, ORBX_FAST_MINB) fast_warp_ker
   uint8_t* sc = smem + tileBytes;                        // corner strengths of the cell interiors, each cell framed by a zero border
   const int scp = G.fastScW, scBytes = G.fastScW * G.fastScH;
   // per-warp scratch: queue (u16 per cell pixel) and one region shared by itemq (u16 per quad, dead after stage b) and
-  // surv (u32 per NMS survivor, written after stage b; a retry pass only happens when no survivor was written)
+  // surv (u16 per NMS survivor, written after stage b; a retry pass only happens when no survivor was written)
   const int cellPix = G.fastCellPix;
-  const int shared2 = max(2 * G.fastCellQuads, 4 * G.fastCellSurv);
+  const int shared2 = (max(2 * G.fastCellQuads, 2 * G.fastCellSurv) + 15) & ~15;
   uint8_t* wbase = sc + scBytes + (size_t)warp * (2 * cellPix + shared2);
   uint16_t* queue = (uint16_t*)wbase;
   uint16_t* itemq = queue + cellPix;
-  uint32_t* surv = (uint32_t*)itemq;
+  uint16_t* surv = itemq;
 
   int pitch;
   const uint8_t* lvl = level_ptr(G, B, l, f, pitch);
@@ -883,7 +883,7 @@ __global__ void __launch_bounds__(32 * kWarpCells, ORBX_FAST_MINB) fast_warp_ker
           keep = (v > s[-scp - 1]) & (v > s[-scp]) & (v > s[-scp + 1]) & (v > s[-1]) & (v > s[1]) & (v > s[scp - 1]) & (v > s[scp]) & (v > s[scp + 1]);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) surv[S + __popc(bal & ((1u << lane) - 1))] = (uint32_t)e;      // yi<<8 | cx : already the (row, col) order key
+        if (keep) surv[S + __popc(bal & ((1u << lane) - 1))] = (uint16_t)e;      // yi<<8 | cx : already the (row, col) order key
         S += __popc(bal);
       }
       __syncwarp();
@@ -2021,7 +2021,7 @@ cudaError_t configure_kernels(const Geom& G) {
 
 size_t fast_warp_smem_bytes(const Geom& G) {
   return (size_t)G.fastTileW * G.fastTileH + (size_t)G.fastScW * G.fastScH +
-         (size_t)kWarpCells * (2 * G.fastCellPix + std::max(2 * G.fastCellQuads, 4 * G.fastCellSurv)) + 64;
+         (size_t)kWarpCells * (2 * G.fastCellPix + ((std::max(2 * G.fastCellQuads, 2 * G.fastCellSurv) + 15) & ~15)) + 64;
 }
 
 static bool use_fast_warp() {
