@@ -860,9 +860,9 @@ __global__ void __launch_bounds__(32 * kWarpCells, ORBX_FAST_MINB) fast_warp_ker
           if (k1 < nq) sc0[y1 * scp + x1] = (uint8_t)(b1 > t ? b1 : 0);
         }
         const bool c0 = k0 < nq && b0 > t, c1 = k1 < nq && b1 > t;
-        // the ballots also order the queue reads above before the overwrites of its front below
         const unsigned lt = (1u << lane) - 1;
         const unsigned bal0 = __ballot_sync(0xffffffffu, c0), bal1 = __ballot_sync(0xffffffffu, c1);
+        __syncwarp();                                  // every lane has read its entries before anyone overwrites the front
         int pos = nc + __popc(bal0 & lt) + __popc(bal1 & lt);
         if (c0) queue[pos++] = (uint16_t)e0;
         if (c1) queue[pos] = (uint16_t)e1;
