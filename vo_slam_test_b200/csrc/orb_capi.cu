@@ -329,7 +329,14 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
     {   // TMA-staged resize: source box origin of every 128-column / 64-row destination tile, and the box that covers all
       DevTaps& T = h->taps[l];
       T.rt = ResizeTma{};
-      const int ntx = (D.w + kRzTileW - 1) / kRzTileW, nty = (D.h + kRzTileH - 1) / kRzTileH;
+      // small levels: half-height tiles, so that a chunk still makes a few waves of CTAs (levels 6-7 of a VGA pyramid were
+      // single partial waves: issue 65 % against 85-90 % on the large levels)
+      const int ntx = (D.w + kRzTileW - 1) / kRzTileW;
+      const long long ctasFull = (long long)ntx * ((D.h + kRzTileH - 1) / kRzTileH) * chunk;
+      T.rt.rows = (ctasFull < 6000 && env_int("ORBX_RESIZE_SMALL_TILES", 1)) ? kRwRows / 2 : kRwRows;
+      if ((D.h + 4 * T.rt.rows - 1) / (4 * T.rt.rows) > kRzMaxTY) T.rt.rows = kRwRows;      // tall level: keep the origin table in range
+      const int tileH = 4 * T.rt.rows;
+      const int nty = (D.h + tileH - 1) / tileH;
       bool fits = quadOk && ntx <= kRzMaxTX && nty <= kRzMaxTY;
       int boxW = 16, boxH = 1;
       for (int tx = 0; fits && tx < ntx; ++tx) {
@@ -340,7 +347,7 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
         boxW = std::max(boxW, align_up(x1 - x0, 16));
       }
       for (int ty = 0; fits && ty < nty; ++ty) {
-        const int d0 = ty * kRzTileH, d1 = std::min(d0 + kRzTileH, D.h) - 1;
+        const int d0 = ty * tileH, d1 = std::min(d0 + tileH, D.h) - 1;
         const int y0 = yo[d0], y1 = std::min(yo[d1] + 1, S.h - 1);
         if (y0 > 32767) fits = false;
         T.rt.y0[ty] = (short)y0;

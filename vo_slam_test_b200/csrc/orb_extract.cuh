@@ -116,6 +116,7 @@ constexpr int kRwRows = ORBX_RW_ROWS;
 constexpr int kRzTileW = 128, kRzTileH = 4 * kRwRows, kRzMaxTX = 32, kRzMaxTY = 3072 / kRzTileH;
 struct ResizeTma {
   int use;                 // descriptor valid and the boxes fit (else: resize_walk_kernel)
+  int rows;                // destination rows per warp: kRwRows, or half of it for small levels (more, shorter CTAs)
   int boxW, boxH;          // bytes x rows, boxW a multiple of 16, both <= 256
   short x0[kRzMaxTX];      // 16-byte aligned source byte offset of tile column tx
   short y0[kRzMaxTY];      // first source row of tile row ty

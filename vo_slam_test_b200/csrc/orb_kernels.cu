@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128) resize_tma_kernel(const CUtensorMap* __re
         : "memory");
   }
   const int q = blockIdx.x * (kRzTileW / 4) + lane;
-  const int dy0 = blockIdx.y * kRzTileH + wy * kRwRows;
+  const int dy0 = (blockIdx.y * 4 + wy) * R.rows;
   const int dx0 = q * 4;
   const bool live = dx0 < dw && dy0 < dh;
   int4 Q = make_int4(0, 0, 0, 0);
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(128) resize_tma_kernel(const CUtensorMap* __re
   if (live) { Q = __ldg(T.quad + q); Wt = __ldg(T.xw + q); }
   // lane i < 16 holds the taps of destination row dy0 + i
   int tsy = 0, tb = 0;
-  if (lane < kRwRows && dy0 + lane < dh) {
+  if (lane < R.rows && dy0 + lane < dh) {
     tsy = __ldg(T.yofs + dy0 + lane);
     tb = (int)(uint16_t)__ldg(T.yb0 + dy0 + lane) | ((int)(uint16_t)__ldg(T.yb1 + dy0 + lane) << 16);
   }
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(128) resize_tma_kernel(const CUtensorMap* __re
   };
   uint8_t* d = dst + f * dframe + (size_t)dy0 * dpitch + dx0;
   const bool whole = dx0 + 3 < dw;
-  const int rows = min(kRwRows, dh - dy0);
+  const int rows = min(R.rows, dh - dy0);
   int h0[4], h1[4];
   int r1 = -1;                                   // source row held in h1
   for (int i = 0; i < rows; ++i) {
@@ -1987,7 +1987,7 @@ void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe
   static const bool tma = !(getenv("ORBX_RESIZE_TMA") && atoi(getenv("ORBX_RESIZE_TMA")) == 0);
   static const bool walk = !(getenv("ORBX_RESIZE_WALK") && atoi(getenv("ORBX_RESIZE_WALK")) == 0);
   if (T.quadOk && R.use && tma && map) {
-    const dim3 tblock(32, 4), tgrid((dw + kRzTileW - 1) / kRzTileW, (dh + kRzTileH - 1) / kRzTileH, nframes);
+    const dim3 tblock(32, 4), tgrid((dw + kRzTileW - 1) / kRzTileW, (dh + 4 * R.rows - 1) / (4 * R.rows), nframes);
     launch_chain(pdl_enabled() >= 1, resize_tma_kernel, tgrid, tblock, (size_t)R.boxW * R.boxH, st, map, z0, sh, dst, dw, dh, dpitch, dframe, T, R);
   } else if (T.quadOk && aligned && walk) {
     const dim3 wblock(32, 4), wgrid((dw + 127) / 128, (dh + 4 * kRwRows - 1) / (4 * kRwRows), nframes);
