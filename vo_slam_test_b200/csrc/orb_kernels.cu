@@ -1812,7 +1812,7 @@ __device__ __forceinline__ int od_round(float v) {                        // cvR
 
 __global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM,
                                                                         orbx_keypoint* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
-                                                                        int cap, int32_t* __restrict__ counts_out, int frame0) {
+                                                                        int cap, int32_t* __restrict__ counts_out, int frame0, int K) {
   pdl_prologue();
   __shared__ __align__(128) uint8_t ring[kOdWarps][2][kOdStage];
   __shared__ __align__(8) uint64_t bars[kOdWarps][2];
@@ -1838,12 +1838,12 @@ __global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __
   }
   __syncthreads();                            // the only CTA-wide barrier: the warps are independent from here on
 
-  const int slot0 = (bx * kOdWarps + warp) * kOdK;
+  const int slot0 = (bx * kOdWarps + warp) * K;             // K consecutive slots per warp (kOdK; 2 for latency-bound launches)
   if (slot0 >= G.selPerFrame) return;
   // lane q < nlevels: count of level q; lane k < kOdK: key / level / output position of slot slot0 + k (one global round trip)
   const int cl = lane < G.nlevels ? __ldg(B.selCount + (size_t)f * G.nlevels + lane) : 0;
   const int myslot = min(slot0 + lane, G.selPerFrame - 1);
-  const uint32_t mykey = lane < kOdK ? __ldg(B.sel + (size_t)f * G.selPerFrame + myslot) : 0u;
+  const uint32_t mykey = lane < K ? __ldg(B.sel + (size_t)f * G.selPerFrame + myslot) : 0u;
   int myl = 0;
   while (myl + 1 < G.nlevels && myslot >= G.L[myl + 1].selBase) ++myl;
   int before = 0, cntL = 0, total = 0;
@@ -1856,7 +1856,7 @@ __global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __
   if (bx == 0 && tid == 0) counts_out[frame0 + f] = total;
   const int myi = myslot - G.L[myl].selBase, myo = before + myi;
   // caller buffer smaller than the keypoint count: the count is still reported
-  unsigned todo = __ballot_sync(0xffffffffu, lane < kOdK && slot0 + lane < G.selPerFrame && myi < cntL && myo < cap);
+  unsigned todo = __ballot_sync(0xffffffffu, lane < K && slot0 + lane < G.selPerFrame && myi < cntL && myo < cap);
   if (todo == 0) return;
 
   float2 pat[16];                             // pattern stored transposed [point-in-byte][lane]: coalesced, loaded once per warp
@@ -2064,9 +2064,10 @@ void launch_orient_desc(const Geom& G, const Bufs& B, const TmaSet& TM, orbx_key
   // default: the TMA-fed pipelined kernel; ORBX_OD_TMA=0 (or a level that TMA cannot describe) selects the LDGSTS one
   static const bool tma = !(getenv("ORBX_OD_TMA") && atoi(getenv("ORBX_OD_TMA")) == 0);
   if (tma && TM.usePatch) {
-    const int per = kOdWarps * kOdK;
+    const int K = nframes <= kLatencyFrames ? 2 : kOdK;      // few frames: more, shorter warps (12.4 -> ~5 us for one VGA frame)
+    const int per = kOdWarps * K;
     launch_chain(pdl_long(G, nframes), orient_desc_tma_kernel, ORBX_OD_FF ? dim3(nframes, (G.selPerFrame + per - 1) / per) : dim3((G.selPerFrame + per - 1) / per, nframes), dim3(32 * kOdWarps), 0, st,
-                 G, B, TM, kps, desc, cap, counts, frame0);
+                 G, B, TM, kps, desc, cap, counts, frame0, K);
     return;
   }
   launch_chain(pdl_long(G, nframes), orient_desc_kernel, dim3((G.selPerFrame + 7) / 8, nframes), dim3(256), 0, st, G, B, kps, desc, cap, counts, frame0);
