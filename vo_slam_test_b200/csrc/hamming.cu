@@ -15,9 +15,18 @@
 
 namespace orbx {
 
-constexpr int kQT = 128;          // queries per CTA (threads)
-constexpr int kTT = 256;          // train descriptors per shared-memory tile (8 KB)
-constexpr int kStages = 3;        // tiles in flight (TMA bulk copies, mbarrier-tracked)
+#ifndef ORBX_HAMM_QT
+#define ORBX_HAMM_QT 128
+#endif
+#ifndef ORBX_HAMM_TT
+#define ORBX_HAMM_TT 256
+#endif
+#ifndef ORBX_HAMM_STAGES
+#define ORBX_HAMM_STAGES 3
+#endif
+constexpr int kQT = ORBX_HAMM_QT;          // queries per CTA (threads)
+constexpr int kTT = ORBX_HAMM_TT;          // train descriptors per shared-memory tile (8 KB at 256)
+constexpr int kStages = ORBX_HAMM_STAGES;  // tiles in flight (TMA bulk copies, mbarrier-tracked)
 constexpr uint32_t kKeyInit = (256u << 23) | 0x7FFFFFu;
 
 static std::atomic<long long> g_hamm_launches{0};
