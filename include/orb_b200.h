@@ -154,6 +154,13 @@ int hamm_knn2_sharded_device(const uint8_t* d_q, int nq, const uint8_t* d_t_loca
                              int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok, int32_t* d_status, void* d_workspace,
                              size_t workspace_bytes, void* stream);
 
+/* Same call split in two: phases bit 0 = local shard scan + scatter into the peers, bit 1 = flag wait + merge (3 = both).
+ * Lets a single process that plays several ranks on one device enqueue every scatter before any merge (tests). */
+int hamm_knn2_sharded_phases_device(const uint8_t* d_q, int nq, const uint8_t* d_t_local, long long nt_local, long long shard_lo,
+                                    int th, float ratio, int rank, int world, void* const* bufs, int max_queries, int epoch,
+                                    int32_t* d_idx, int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok, int32_t* d_status,
+                                    void* d_workspace, size_t workspace_bytes, void* stream, int phases);
+
 long long hamm_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -55,10 +55,11 @@ def test_compute_distance(vo):
 
 
 def test_fused_peer_exchange_two_virtual_ranks(vo):
-    """hamm_knn2_sharded_device with two 'ranks' living on one GPU in one process: both exchange buffers are plain
-    device allocations, the scatters of both ranks are enqueued before the gathers (one stream), so the flag protocol,
-    the parity switch between calls and the merge rule are exercised without CUDA IPC.  Result == one kNN over the whole
-    train set == the CPU oracle."""
+    """hamm_knn2_sharded_device with two 'ranks' living on one GPU in one process: both exchange buffers are plain device
+    allocations, and the phase-split entry point lets the single stream enqueue the scan + scatter of BOTH ranks before
+    either merge (in a real job every rank has its own GPU and the merge's flag wait overlaps the peers' scatters).
+    Exercises the record layout, the flag protocol, the parity switch between calls and the merge rule without CUDA IPC.
+    Result == one kNN over the whole train set == the CPU oracle."""
     import torch
     from vo_slam_test_b200 import api
     rng = np.random.default_rng(5)
@@ -77,29 +78,25 @@ def test_fused_peer_exchange_two_virtual_ranks(vo):
     try:
         for epoch in (1, 2, 3):                                        # three calls: both parities, buffer reuse
             outs = []
-            # per rank: kNN + scatter; the gather kernels follow in stream order only after BOTH scatters were enqueued,
-            # which the library cannot do for us here -- so rank 1 runs first up to its gather, whose flags need rank 0:
-            # enqueue rank 0's whole call, then rank 1's; rank 0's gather would spin for rank 1's scatter, which is behind it
-            # in the same stream.  Therefore each virtual rank gets its own stream.
-            streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
             for r in range(world):
-                with torch.cuda.stream(streams[r]):
-                    idx = torch.empty(Q, dtype=torch.int32, device=dev); d1 = torch.empty_like(idx); d2 = torch.empty_like(idx)
-                    ok = torch.empty(Q, dtype=torch.uint8, device=dev)
-                    status = torch.zeros(1, dtype=torch.int32, device=dev)
-                    wsb = api.knn2_workspace_bytes(Q, shards[r].shape[0])
-                    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+                idx = torch.empty(Q, dtype=torch.int32, device=dev); d1 = torch.empty_like(idx); d2 = torch.empty_like(idx)
+                ok = torch.empty(Q, dtype=torch.uint8, device=dev)
+                status = torch.zeros(1, dtype=torch.int32, device=dev)
+                wsb = api.knn2_workspace_bytes(Q, shards[r].shape[0])
+                ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+                outs.append((idx, d1, d2, ok, status, ws, wsb))
+            for phases in (1, 2):
+                for r in range(world):
+                    idx, d1, d2, ok, status, ws, wsb = outs[r]
                     api.knn2_sharded_device(d_q.data_ptr(), Q, shards[r].data_ptr(), shards[r].shape[0], los[r], 50, 0.7, r, world,
                                             bufs, 1024, epoch, idx.data_ptr(), d1.data_ptr(), d2.data_ptr(), ok.data_ptr(),
-                                            status.data_ptr(), ws.data_ptr(), wsb, streams[r].cuda_stream)
-                    outs.append((idx, d1, d2, ok, status, ws))
+                                            status.data_ptr(), ws.data_ptr(), wsb, st, phases=phases)
             torch.cuda.synchronize()
             for r in range(world):
-                idx, d1, d2, ok, status, _ = outs[r]
+                idx, d1, d2, ok, status = outs[r][:5]
                 assert int(status.item()) == 0, "exchange timed out"
                 got = (idx.cpu().numpy(), d1.cpu().numpy(), d2.cpu().numpy(), ok.cpu().numpy())
                 assert all(np.array_equal(a, b) for a, b in zip(got, want)), "rank %d epoch %d" % (r, epoch)
     finally:
         for b in bufs:
             api.exchange_free(b)
-    del st

@@ -104,6 +104,7 @@ def load_library():
     L.hamm_exchange_close.argtypes = [vp]
     L.hamm_exchange_free.argtypes = [vp]
     L.hamm_knn2_sharded_device.argtypes = [vp, i32, vp, ll, ll, i32, f32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.hamm_knn2_sharded_phases_device.argtypes = [vp, i32, vp, ll, ll, i32, f32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp, i32]
     L.orbx_grid_build.argtypes = [vp, i32, f32, f32, f32, f32, vp, vp, i32]
     L.orbx_search_by_projection_frame.argtypes = [vp, vp, f32, f32, i32, i32, i32, vp, vp, i32]
     L.orbx_search_by_projection_local.argtypes = [vp, vp, f32, f32, vp, vp, i32]
@@ -301,13 +302,14 @@ def exchange_free(ptr):
 
 
 def knn2_sharded_device(d_q, nq, d_t, nt, shard_lo, th, ratio, rank, world, bufs, max_queries, epoch, d_idx, d_d1, d_d2, d_ok,
-                        d_status, d_ws=0, ws_bytes=0, stream=0):
-    """Local shard top-2 + peer-memory scatter + merge (hamm_knn2_sharded_device); bufs = list of `world` device pointers."""
+                        d_status, d_ws=0, ws_bytes=0, stream=0, phases=3):
+    """Local shard top-2 + peer-memory scatter + merge (hamm_knn2_sharded[_phases]_device); bufs = list of `world` device
+    pointers; phases: 1 = scan + scatter only, 2 = flag wait + merge only, 3 = both."""
     arr = (C.c_void_p * world)(*bufs)
-    _check(load_library().hamm_knn2_sharded_device(C.c_void_p(d_q), nq, C.c_void_p(d_t), nt, shard_lo, th, ratio, rank, world, arr,
-                                                   max_queries, epoch, C.c_void_p(d_idx), C.c_void_p(d_d1), C.c_void_p(d_d2),
-                                                   C.c_void_p(d_ok), C.c_void_p(d_status), C.c_void_p(d_ws), ws_bytes,
-                                                   C.c_void_p(stream)))
+    _check(load_library().hamm_knn2_sharded_phases_device(C.c_void_p(d_q), nq, C.c_void_p(d_t), nt, shard_lo, th, ratio, rank, world,
+                                                          arr, max_queries, epoch, C.c_void_p(d_idx), C.c_void_p(d_d1),
+                                                          C.c_void_p(d_d2), C.c_void_p(d_ok), C.c_void_p(d_status), C.c_void_p(d_ws),
+                                                          ws_bytes, C.c_void_p(stream), phases))
 
 
 def knn2_workspace_bytes(nq, nt):

@@ -438,6 +438,14 @@ int hamm_knn2_sharded_device(const uint8_t* d_q, int nq, const uint8_t* d_t, lon
                              int rank, int world, void* const* bufs, int max_queries, int epoch, int32_t* d_idx, int32_t* d_d1,
                              int32_t* d_d2, uint8_t* d_ok, int32_t* d_status, void* d_workspace, size_t workspace_bytes,
                              void* stream) {
+  return hamm_knn2_sharded_phases_device(d_q, nq, d_t, nt, shard_lo, th, ratio, rank, world, bufs, max_queries, epoch, d_idx, d_d1,
+                                         d_d2, d_ok, d_status, d_workspace, workspace_bytes, stream, 3);
+}
+
+int hamm_knn2_sharded_phases_device(const uint8_t* d_q, int nq, const uint8_t* d_t, long long nt, long long shard_lo, int th,
+                                    float ratio, int rank, int world, void* const* bufs, int max_queries, int epoch, int32_t* d_idx,
+                                    int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok, int32_t* d_status, void* d_workspace,
+                                    size_t workspace_bytes, void* stream, int phases) {
   if (!d_q || (!d_t && nt > 0) || !d_idx || !d_d1 || !d_d2 || !d_ok || !d_status || !bufs || nq < 0 || nt < 0 || world < 1 ||
       world > kMaxPeers || rank < 0 || rank >= world || nq > max_queries || epoch < 1) {
     set_error("bad argument");
@@ -456,20 +464,25 @@ int hamm_knn2_sharded_device(const uint8_t* d_q, int nq, const uint8_t* d_t, lon
     set_error("workspace too small (see hamm_knn2_workspace_bytes)");
     return ORBX_ERR_CAPACITY;
   }
-  // local shard: per-split partials (ns > 1) or the shard result in the output arrays (ns == 1), local row indices
-  dim3 grid((nq + kQT - 1) / kQT, ns);
-  knn2_kernel<<<grid, kQT, 0, st>>>(d_q, nq, d_t, nt, per, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace);
   const int parity = epoch & 1;
-  const int32_t* part = (const int32_t*)d_workspace;
-  if (ns > 1)
-    knn2_merge_scatter_kernel<<<(nq + 127) / 128, 128, 0, st>>>(part, part + 1, part + 2, 3, ns, nq, shard_lo, peers, rank, world,
-                                                               max_queries, parity, epoch);
-  else
-    knn2_merge_scatter_kernel<<<(nq + 127) / 128, 128, 0, st>>>(d_idx, d_d1, d_d2, 1, 1, nq, shard_lo, peers, rank, world,
-                                                               max_queries, parity, epoch);
-  knn2_gather_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(peers.p[rank], world, nq, max_queries, parity, epoch, th, ratio, d_idx,
-                                                            d_d1, d_d2, d_ok, d_status);
-  g_hamm_launches += 3;
+  if (phases & 1) {
+    // local shard: per-split partials (ns > 1) or the shard result in the output arrays (ns == 1), local row indices
+    dim3 grid((nq + kQT - 1) / kQT, ns);
+    knn2_kernel<<<grid, kQT, 0, st>>>(d_q, nq, d_t, nt, per, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace);
+    const int32_t* part = (const int32_t*)d_workspace;
+    if (ns > 1)
+      knn2_merge_scatter_kernel<<<(nq + 127) / 128, 128, 0, st>>>(part, part + 1, part + 2, 3, ns, nq, shard_lo, peers, rank, world,
+                                                                 max_queries, parity, epoch);
+    else
+      knn2_merge_scatter_kernel<<<(nq + 127) / 128, 128, 0, st>>>(d_idx, d_d1, d_d2, 1, 1, nq, shard_lo, peers, rank, world,
+                                                                 max_queries, parity, epoch);
+    g_hamm_launches += 2;
+  }
+  if (phases & 2) {
+    knn2_gather_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(peers.p[rank], world, nq, max_queries, parity, epoch, th, ratio, d_idx,
+                                                              d_d1, d_d2, d_ok, d_status);
+    g_hamm_launches += 1;
+  }
   ORBX_CUDA(cudaGetLastError());
   return ORBX_OK;
 }
