@@ -80,6 +80,7 @@ struct orbx_extractor {
   // staging for the host entry points
   uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
   orbx_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int32_t* d_counts = nullptr;
+  uint8_t* d_one = nullptr; uint8_t* h_one = nullptr; int one_cap = 0;   // single-frame path: packed [count | kps | desc], pinned mirror
   size_t d_out_frames = 0; int d_out_cap = 0;
   cudaStream_t stream = nullptr, copyStream = nullptr, backStream = nullptr;
   int32_t *d_midx = nullptr, *d_md1 = nullptr, *d_md2 = nullptr, *d_qf = nullptr; uint8_t* d_mok = nullptr;
@@ -538,6 +539,7 @@ int orbx_destroy(orbx_handle h) {
   cudaFree(h->d_maps);
   cudaFree(h->d_pattern); cudaFree(h->d_umax); cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc);
   cudaFree(h->d_counts);
+  cudaFree(h->d_one); if (h->h_one) cudaFreeHost(h->h_one);
   cudaFree(h->d_midx); cudaFree(h->d_md1); cudaFree(h->d_md2); cudaFree(h->d_mok); cudaFree(h->d_qf);
   if (h->copyStream) cudaStreamDestroy(h->copyStream);
   if (h->backStream) cudaStreamDestroy(h->backStream);
@@ -616,6 +618,33 @@ int orbx_extract_batch(orbx_handle h, const uint8_t* imgs, int nframes, int w, i
     h->d_in = nullptr; h->d_in_bytes = 0;
     ORBX_CUDA(cudaMalloc(&h->d_in, fbytes * nframes));
     h->d_in_bytes = fbytes * nframes;
+  }
+  if (nframes == 1) {
+    // The drop-in operator() case: results are packed as [count | keypoints | descriptors] in one device block and come
+    // back in ONE copy into a pinned mirror (three copies into the caller's pageable arrays cost ~3x the latency); only
+    // the valid entries are then copied out on the host.
+    const size_t offK = 64, offD = offK + sizeof(orbx_keypoint) * (size_t)cap, total = offD + (size_t)32 * cap;
+    if (h->one_cap < cap) {
+      cudaFree(h->d_one); if (h->h_one) cudaFreeHost(h->h_one);
+      h->d_one = nullptr; h->h_one = nullptr; h->one_cap = 0;
+      ORBX_CUDA(cudaMalloc(&h->d_one, total));
+      ORBX_CUDA(cudaHostAlloc(&h->h_one, total, cudaHostAllocDefault));
+      h->one_cap = cap;
+    }
+    cudaStream_t st1 = h->stream;
+    if (pitch == row_stride) ORBX_CUDA(cudaMemcpyAsync(h->d_in, imgs, fbytes, cudaMemcpyHostToDevice, st1));
+    else ORBX_CUDA(cudaMemcpy2DAsync(h->d_in, pitch, imgs, row_stride, w, height, cudaMemcpyHostToDevice, st1));
+    int rc1 = orbx_extract_batch_device(h, h->d_in, 1, w, height, pitch, fbytes, (orbx_keypoint*)(h->d_one + offK), h->d_one + offD, cap,
+                                        (int32_t*)h->d_one, st1);
+    if (rc1) return rc1;
+    ORBX_CUDA(cudaMemcpyAsync(h->h_one, h->d_one, total, cudaMemcpyDeviceToHost, st1));
+    ORBX_CUDA(cudaStreamSynchronize(st1));
+    const int32_t c = *(const int32_t*)h->h_one;
+    const int ncopy = std::max(0, std::min((int)c, cap));
+    counts[0] = c;
+    memcpy(kps, h->h_one + offK, sizeof(orbx_keypoint) * (size_t)ncopy);
+    memcpy(desc, h->h_one + offD, (size_t)32 * ncopy);
+    return ORBX_OK;
   }
   if (h->d_out_frames < (size_t)nframes || h->d_out_cap < cap) {
     cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
