@@ -1,0 +1,338 @@
+// orb_b200_matcher.hpp -- header-only C++ adapter: the reference's Matcher search signatures on top of the C ABI.
+//
+// The reference's `myslam::Matcher` (include/myslam/matcher.h:16-37) walks Frame / KeyFrame / MapPoint objects through
+// raw pointers.  The object walk (null / bad / outlier gates, the Sophus projection, the writes into `mappoints_`) stays
+// on the host, verbatim in meaning; the data-parallel inner loops (grid window, Hamming distances, best / second best,
+// greedy exclusion, rotation histogram) run in libvoslam_b200.so.  A maintainer keeps matcher.h and replaces the bodies
+// in src/matcher.cpp by one-liners:
+//
+//     #include "orb_b200_matcher.hpp"
+//     int Matcher::searchByProjection(Frame* c, Frame* l, const float radius, bool checkRot)
+//     { return myslam_b200::searchByProjection(c, l, radius, checkRot); }
+//     int Matcher::searchByProjection(Frame* f, const vector<MapPoint*>& mps, const float th)
+//     { return myslam_b200::searchByProjection(f, mps, th, ratio_); }
+//     int Matcher::searchByBoW(KeyFrame* kf, Frame* f, vector<MapPoint*>& m, bool checkRot)
+//     { return myslam_b200::searchByBoW(kf, f, m, checkRot, ratio_); }
+//     int Matcher::searchByBoW(KeyFrame* k1, KeyFrame* k2, vector<MapPoint*>& m, bool checkRot)
+//     { return myslam_b200::searchByBoWKeyFrames(k1, k2, m, checkRot, ratio_); }
+//
+// or uses `myslam_b200::MatcherT<Frame, KeyFrame, MapPoint>` as the class itself.  Everything is a template over the
+// reference's own types and touches only members the reference's loops touch (named at each use), so the header needs
+// neither Sophus, Eigen nor DBoW3 itself.  In this repo it is compiled and run against stand-in types
+// (tests/tools/myslam_stub.hpp, tests/tools/matcher_adapter_check.cpp), next to a loop-for-loop CPU statement of the
+// reference functions over the same objects.
+//
+// Error convention: the reference returns match counts and cannot fail; the adapter throws std::runtime_error with
+// orbx_last_error() when the CUDA path fails (there is no CPU fallback to fall back to).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "orb_b200.h"
+
+namespace myslam_b200 {
+
+namespace detail {
+
+inline void check(int rc) {
+  if (rc != ORBX_OK) throw std::runtime_error(std::string("libvoslam_b200: ") + orbx_last_error());
+}
+
+static_assert(sizeof(orbx_keypoint) == 28, "orbx_keypoint mirrors cv::KeyPoint");
+
+// Flat view of the feature side of a Frame / KeyFrame: unKeypoints_, descriptors_ (n x 32 CV_8U), uRight_, scaleFactors_
+// and the image bounds (frame.h:24-43).  cv::KeyPoint is layout-compatible with orbx_keypoint (28 bytes).
+template <class FrameT>
+struct FrameArrays {
+  std::vector<uint8_t> desc, occupied;
+  orbx_frame_view view;
+  explicit FrameArrays(FrameT* f) {
+    const int n = (int)f->unKeypoints_.size();
+    desc.resize((size_t)n * 32);
+    for (int i = 0; i < n; ++i) std::memcpy(&desc[(size_t)i * 32], f->descriptors_.ptr(i), 32);
+    occupied.assign(n > 0 ? n : 1, 0);
+    view.kps = reinterpret_cast<const orbx_keypoint*>(f->unKeypoints_.data());
+    view.desc = desc.data();
+    view.uright = f->uRight_.data();
+    view.n = n;
+    view.xmin = f->xMin_; view.xmax = f->xMax_; view.ymin = f->yMin_; view.ymax = f->yMax_;
+    view.scale_factors = f->scaleFactors_.data();
+    view.nlevels = (int)f->scaleFactors_.size();
+    view.occupied0 = occupied.data();
+  }
+};
+
+// A DBoW3::FeatureVector (std::map<NodeId, std::vector<unsigned>>, iterated in node-id order) as the CSR of orbx_bow_side.
+template <class FeatVecT>
+struct FeatCsr {
+  std::vector<uint32_t> node_ids;
+  std::vector<int32_t> group_start, feat_idx;
+  explicit FeatCsr(const FeatVecT& fv) {
+    group_start.push_back(0);
+    for (typename FeatVecT::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+      node_ids.push_back((uint32_t)it->first);
+      for (size_t k = 0; k < it->second.size(); ++k) feat_idx.push_back((int32_t)it->second[k]);
+      group_start.push_back((int32_t)feat_idx.size());
+    }
+    if (feat_idx.empty()) feat_idx.push_back(0);      // keep data() non-null
+    if (node_ids.empty()) node_ids.push_back(0);
+  }
+  int ngroups() const { return (int)group_start.size() - 1; }
+};
+
+template <class FrameLike>
+struct BowSide {
+  std::vector<uint8_t> desc, valid;
+  std::vector<float> angle;
+  orbx_bow_side side;
+  template <class Csr>
+  BowSide(FrameLike* f, const Csr& csr) {
+    const int n = (int)f->unKeypoints_.size();
+    desc.resize((size_t)(n > 0 ? n : 1) * 32);
+    angle.resize(n > 0 ? n : 1);
+    valid.assign(n > 0 ? n : 1, 1);
+    for (int i = 0; i < n; ++i) {
+      std::memcpy(&desc[(size_t)i * 32], f->descriptors_.ptr(i), 32);
+      angle[i] = f->unKeypoints_[i].angle;
+    }
+    side.n = n; side.desc = desc.data(); side.angle = angle.data(); side.valid = valid.data();
+    side.ngroups = csr.ngroups(); side.node_ids = csr.node_ids.data(); side.group_start = csr.group_start.data();
+    side.feat_idx = csr.feat_idx.data();
+  }
+};
+
+}  // namespace detail
+
+// Matcher::searchByProjection(Frame* frame_curr, Frame* frame_last, radius, checkRot)          matcher.cpp:18-148
+// Host: the per-point gates and the projection of :33-66 (same types, same float casts); device: the window search, the
+// "already holds an observed point" exclusion (:90), the stereo gate (:93-99), the strict-< argmin (:104-108), TH_HIGH
+// and the rotation histogram (:111-145).  The writes of :113 and :141 are replayed from `assign`.
+template <class FrameT>
+int searchByProjection(FrameT* frame_curr, FrameT* frame_last, const float radius, bool checkRot = true, int device = 0) {
+  const int xMax = frame_curr->xMax_, xMin = frame_curr->xMin_;     // int on purpose: the reference truncates (:28-31)
+  const int yMax = frame_curr->yMax_, yMin = frame_curr->yMin_;
+  const float b = frame_curr->camera_->b_, bf = frame_curr->camera_->bf_;
+
+  auto Tcw = frame_curr->Tcw_;
+  auto Tlc = frame_last->Tcw_ * Tcw.inverse();
+  auto tlc = Tlc.translation();
+  const bool forward = static_cast<float>(tlc[2]) > b;
+  const bool backward = -static_cast<float>(tlc[2]) > b;
+
+  const int M = (int)frame_last->mappoints_.size();
+  const int M1 = M > 0 ? M : 1;
+  std::vector<uint8_t> valid(M1, 0), has_obs(M1, 0), desc((size_t)M1 * 32, 0);
+  std::vector<float> u(M1, 0.f), v(M1, 0.f), invz(M1, 0.f), angle(M1, 0.f);
+  std::vector<int32_t> octave(M1, 0);
+  for (int i = 0; i < M; ++i) {
+    auto* mp = frame_last->mappoints_[i];
+    if (!mp || frame_last->outliers_[i]) continue;
+    auto p_camera = Tcw * mp->getPose();
+    const float z = static_cast<float>(p_camera[2]);
+    if (z < 0.0f) continue;
+    auto pixel = frame_curr->camera_->camera2pixel(p_camera);
+    const float pu = pixel[0], pv = pixel[1];
+    if (pu < xMin || pu > xMax) continue;
+    if (pv < yMin || pv > yMax) continue;
+    valid[i] = 1;
+    u[i] = pu; v[i] = pv; invz[i] = 1.0f / z;
+    octave[i] = frame_last->unKeypoints_[i].octave;
+    angle[i] = frame_last->unKeypoints_[i].angle;
+    has_obs[i] = mp->observe_cnt_ > 0;
+    std::memcpy(&desc[(size_t)i * 32], mp->getDescriptor().data, 32);
+  }
+
+  detail::FrameArrays<FrameT> cur(frame_curr);
+  for (int i = 0; i < cur.view.n; ++i)
+    cur.occupied[i] = frame_curr->mappoints_[i] && frame_curr->mappoints_[i]->observe_cnt_ > 0;
+  orbx_sbp_frame_points pts = {M, valid.data(), u.data(), v.data(), invz.data(), octave.data(), angle.data(), desc.data(),
+                               has_obs.data()};
+  std::vector<int32_t> assign(cur.view.n > 0 ? cur.view.n : 1, -1);
+  int match_cnt = 0;
+  detail::check(orbx_search_by_projection_frame(&cur.view, &pts, radius, bf, forward, backward, checkRot, assign.data(),
+                                                &match_cnt, device));
+  for (int i = 0; i < cur.view.n; ++i) {
+    if (assign[i] >= 0) frame_curr->mappoints_[i] = frame_last->mappoints_[assign[i]];
+    else if (assign[i] == -2) frame_curr->mappoints_[i] = nullptr;
+  }
+  return match_cnt;
+}
+
+// Matcher::searchByProjection(Frame* frame, const vector<MapPoint*>& mappoints, thRadius)        matcher.cpp:274-353
+// `ratio` is the Matcher's ratio_ member (:344).
+template <class FrameT, class MapPointT>
+int searchByProjection(FrameT* frame, const std::vector<MapPointT*>& mappoints, const float thRadius, float ratio,
+                       int device = 0) {
+  const int M = (int)mappoints.size();
+  const int M1 = M > 0 ? M : 1;
+  std::vector<uint8_t> valid(M1, 0), has_obs(M1, 0), desc((size_t)M1 * 32, 0);
+  std::vector<float> u(M1, 0.f), v(M1, 0.f), ur(M1, 0.f), view_cos(M1, 0.f);
+  std::vector<int32_t> level(M1, 0);
+  for (int i = 0; i < M; ++i) {
+    MapPointT* mp = mappoints[i];
+    if (mp->isBad() || !mp->trackInLocalMap_) continue;
+    valid[i] = 1;
+    u[i] = mp->trackProj_u_; v[i] = mp->trackProj_v_; ur[i] = mp->trackProj_uR_;
+    level[i] = mp->trackScaleLevel_;
+    view_cos[i] = mp->viewCos_;
+    has_obs[i] = mp->getObsCnt() > 0;
+    std::memcpy(&desc[(size_t)i * 32], mp->getDescriptor().data, 32);
+  }
+  detail::FrameArrays<FrameT> cur(frame);
+  for (int i = 0; i < cur.view.n; ++i) cur.occupied[i] = frame->mappoints_[i] && frame->mappoints_[i]->getObsCnt() > 0;
+  orbx_sbp_local_points pts = {M, valid.data(), u.data(), v.data(), ur.data(), level.data(), view_cos.data(), desc.data(),
+                               has_obs.data()};
+  std::vector<int32_t> assign(cur.view.n > 0 ? cur.view.n : 1, -1);
+  int match_cnt = 0;
+  detail::check(orbx_search_by_projection_local(&cur.view, &pts, thRadius, ratio, assign.data(), &match_cnt, device));
+  for (int i = 0; i < cur.view.n; ++i)
+    if (assign[i] >= 0) frame->mappoints_[i] = mappoints[assign[i]];
+  return match_cnt;
+}
+
+// Matcher::searchByProjection(Frame* frame_curr, KeyFrame* keyframe, radius, distThreshold, found, checkRot)
+//                                                                                                matcher.cpp:150-272
+// Host: null / bad / `found` gates, projection, depth sign, image bounds, distance range, predictScale (:170-202);
+// device: window over [level_predict-1, level_predict+1], "feature already holds a point" exclusion (:218), argmin,
+// distThreshold, rotation histogram.  The window radius uses the KEY FRAME's scale factors (:203), like the reference.
+template <class FrameT, class KeyFrameT, class FoundSetT>
+int searchByProjection(FrameT* frame_curr, KeyFrameT* keyframe, const float radius, const float distThreshold,
+                       const FoundSetT& found, bool checkRot = true, int device = 0) {
+  const int xMax = frame_curr->xMax_, xMin = frame_curr->xMin_;
+  const int yMax = frame_curr->yMax_, yMin = frame_curr->yMin_;
+  const auto Tcw = frame_curr->Tcw_;
+  auto Ow = Tcw.inverse().translation();
+  const auto mappoints = keyframe->getMapPoints();
+  const int M = (int)mappoints.size();
+  const int M1 = M > 0 ? M : 1;
+  std::vector<uint8_t> valid(M1, 0), zeros8(M1, 0), desc((size_t)M1 * 32, 0);
+  std::vector<float> u(M1, 0.f), v(M1, 0.f), zerosf(M1, 0.f), angle(M1, 0.f);
+  std::vector<int32_t> octave(M1, 0);
+  for (int i = 0; i < M; ++i) {
+    auto* mp = mappoints[i];
+    if (!mp) continue;
+    if (mp->isBad() || found.count(mp)) continue;
+    auto p_camera = Tcw * mp->getPose();
+    const float z = p_camera[2];
+    if (z <= 0) continue;
+    auto pixel = frame_curr->camera_->camera2pixel(p_camera);
+    const float pu = pixel[0], pv = pixel[1];
+    if (pu > xMax || pu < xMin) continue;
+    if (pv > yMax || pv < yMin) continue;
+    auto line = mp->getPose() - Ow;
+    const float distance = line.norm();
+    const float maxDistance = mp->getMaxDistanceThreshold();
+    const float minDistance = mp->getMinDistanceThreshold();
+    if (distance < minDistance || distance > maxDistance) continue;
+    valid[i] = 1;
+    u[i] = pu; v[i] = pv;
+    octave[i] = mp->predictScale(distance, frame_curr);
+    angle[i] = keyframe->unKeypoints_[i].angle;
+    std::memcpy(&desc[(size_t)i * 32], mp->getDescriptor().data, 32);
+  }
+  detail::FrameArrays<FrameT> cur(frame_curr);
+  cur.view.scale_factors = keyframe->scaleFactors_.data();                                     // :203
+  cur.view.nlevels = (int)keyframe->scaleFactors_.size();
+  for (int i = 0; i < cur.view.n; ++i) cur.occupied[i] = frame_curr->mappoints_[i] != nullptr;  // :218
+  orbx_sbp_frame_points pts = {M, valid.data(), u.data(), v.data(), zerosf.data(), octave.data(), angle.data(), desc.data(),
+                               zeros8.data()};
+  std::vector<int32_t> assign(cur.view.n > 0 ? cur.view.n : 1, -1);
+  int match_cnt = 0;
+  detail::check(orbx_search_by_projection_reloc(&cur.view, &pts, radius, distThreshold, checkRot, assign.data(), &match_cnt,
+                                                device));
+  for (int i = 0; i < cur.view.n; ++i) {
+    if (assign[i] >= 0) frame_curr->mappoints_[i] = mappoints[assign[i]];
+    else if (assign[i] == -2) frame_curr->mappoints_[i] = nullptr;
+  }
+  return match_cnt;
+}
+
+// Matcher::searchByBoW(KeyFrame* keyframe, Frame* frame, mappointMatches, checkRot)              matcher.cpp:449-559
+template <class KeyFrameT, class FrameT, class MapPointT>
+int searchByBoW(KeyFrameT* keyframe, FrameT* frame, std::vector<MapPointT*>& mappointMatches, bool checkRot, float ratio,
+                int device = 0) {
+  const int TH_LOW = 50;                                                                       // matcher.cpp:12
+  mappointMatches = std::vector<MapPointT*>(frame->N_, static_cast<MapPointT*>(nullptr));
+  const std::vector<MapPointT*> mappoints = keyframe->getMapPoints();
+  typedef typename std::remove_reference<decltype(keyframe->featVec_)>::type FVa;
+  typedef typename std::remove_reference<decltype(frame->featVec_)>::type FVb;
+  detail::FeatCsr<FVa> ca(keyframe->featVec_);
+  detail::FeatCsr<FVb> cb(frame->featVec_);
+  detail::BowSide<KeyFrameT> a(keyframe, ca);
+  detail::BowSide<FrameT> bside(frame, cb);
+  for (int i = 0; i < a.side.n; ++i) a.valid[i] = mappoints[i] && !mappoints[i]->isBad();      // :476-478
+  std::vector<int32_t> match(bside.side.n > 0 ? bside.side.n : 1, -1);
+  int match_cnt = 0;
+  detail::check(orbx_search_by_bow(&a.side, &bside.side, 0, ratio, TH_LOW, checkRot, match.data(), &match_cnt, device));
+  for (int i = 0; i < bside.side.n; ++i)
+    if (match[i] >= 0) mappointMatches[i] = mappoints[match[i]];                               // :508 (cleared ones stay null, :552)
+  return match_cnt;
+}
+
+// Matcher::searchByBoW(KeyFrame* keyframe1, KeyFrame* keyframe2, mappointMatches, checkRot)      matcher.cpp:561-677
+template <class KeyFrameT, class MapPointT>
+int searchByBoWKeyFrames(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector<MapPointT*>& mappointMatches, bool checkRot,
+                         float ratio, int device = 0) {
+  const int TH_LOW = 50;
+  mappointMatches = std::vector<MapPointT*>(keyframe1->N_, static_cast<MapPointT*>(nullptr));
+  const std::vector<MapPointT*> mappoints1 = keyframe1->getMapPoints();
+  const std::vector<MapPointT*> mappoints2 = keyframe2->getMapPoints();
+  typedef typename std::remove_reference<decltype(keyframe1->featVec_)>::type FV;
+  detail::FeatCsr<FV> c1(keyframe1->featVec_), c2(keyframe2->featVec_);
+  detail::BowSide<KeyFrameT> a(keyframe1, c1), bside(keyframe2, c2);
+  for (int i = 0; i < a.side.n; ++i) a.valid[i] = mappoints1[i] && !mappoints1[i]->isBad();            // :590-592
+  for (int i = 0; i < bside.side.n; ++i) bside.valid[i] = mappoints2[i] && !mappoints2[i]->isBad();    // :603-608
+  std::vector<int32_t> match(a.side.n > 0 ? a.side.n : 1, -1);
+  int match_cnt = 0;
+  detail::check(orbx_search_by_bow(&a.side, &bside.side, 1, ratio, TH_LOW, checkRot, match.data(), &match_cnt, device));
+  for (int i = 0; i < a.side.n; ++i)
+    if (match[i] >= 0) mappointMatches[i] = mappoints2[match[i]];                                      // :629
+  return match_cnt;
+}
+
+// Matcher::computeDistance(const Mat&, const Mat&)                                               matcher.cpp:1240-1256
+template <class MatT>
+int computeDistance(const MatT& desp1, const MatT& desp2, int device = 0) {
+  int32_t idx, d1, d2; uint8_t ok;
+  detail::check(hamm_knn2(desp1.data, 1, desp2.data, 1, 256, 1.0f, &idx, &d1, &d2, &ok, device));
+  return d1;
+}
+
+// The class itself, for callers that prefer to swap the type: `typedef myslam_b200::MatcherT<Frame, KeyFrame, MapPoint>
+// Matcher;` gives the call sites of visualOdometry.cpp:238,263,354 / localMapping.cpp:134 the same constructor and the
+// same overload set for the searches above.
+template <class FrameT, class KeyFrameT, class MapPointT>
+class MatcherT {
+ public:
+  MatcherT() : ratio_(0.f), device_(0) {}
+  explicit MatcherT(float ratio, int device = 0) : ratio_(ratio), device_(device) {}
+  int searchByProjection(FrameT* frame_curr, FrameT* frame_last, const float radius, bool checkRot = true) {
+    return myslam_b200::searchByProjection(frame_curr, frame_last, radius, checkRot, device_);
+  }
+  int searchByProjection(FrameT* frame, const std::vector<MapPointT*>& mappoints, const float thRadius) {
+    return myslam_b200::searchByProjection(frame, mappoints, thRadius, ratio_, device_);
+  }
+  template <class FoundSetT>
+  int searchByProjection(FrameT* frame_curr, KeyFrameT* keyframe, const float radius, const float distThreshold,
+                         const FoundSetT& found, bool checkRot = true) {
+    return myslam_b200::searchByProjection(frame_curr, keyframe, radius, distThreshold, found, checkRot, device_);
+  }
+  int searchByBoW(KeyFrameT* keyframe, FrameT* frame, std::vector<MapPointT*>& mappointMatches, bool checkRot = true) {
+    return myslam_b200::searchByBoW(keyframe, frame, mappointMatches, checkRot, ratio_, device_);
+  }
+  int searchByBoW(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector<MapPointT*>& mappointMatches, bool checkRot) {
+    return myslam_b200::searchByBoWKeyFrames(keyframe1, keyframe2, mappointMatches, checkRot, ratio_, device_);
+  }
+  template <class MatT>
+  static int computeDistance(const MatT& desp1, const MatT& desp2) { return myslam_b200::computeDistance(desp1, desp2); }
+
+ private:
+  float ratio_;
+  int device_;
+};
+
+}  // namespace myslam_b200

@@ -1,0 +1,63 @@
+"""include/orb_b200_matcher.hpp -- the reference's Matcher search signatures (include/myslam/matcher.h:16-37) over the C ABI.
+
+The header is a template over the reference's Frame / KeyFrame / MapPoint types; here it is instantiated with stand-ins
+that carry exactly the members matcher.cpp touches (tests/tools/myslam_stub.hpp).  tests/tools/matcher_adapter_check.cpp
+builds two identical object graphs, runs a loop-for-loop CPU statement of the reference functions on one and the adapter on
+the other, and compares the `mappoints_` / `mappointMatches` vectors pointer by pointer plus the returned counts.
+
+* not gpu: the C-ABI calls are served by the CPU oracle port (tests/tools/cabi_on_port.cpp) -> checks the adapter's host logic
+  (gates, projection, flattening, replay of the writes) and, independently, the port against the object-walking statement.
+* gpu: the same program linked with libvoslam_b200.so -> the CUDA kernels behind the reference's signatures.
+"""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOOLS = os.path.join(ROOT, "tests", "tools")
+INC = ["-I" + os.path.join(ROOT, "oracle", "compat"), "-I" + os.path.join(ROOT, "include"), "-I" + TOOLS]
+
+
+def _build():
+    import __graft_entry__ as g
+    if not (os.path.exists(os.path.join(ROOT, "vo_slam_test_b200", "lib", "libvoslam_b200.so"))
+            and os.path.exists(os.path.join(ROOT, "oracle", "liborbport.so"))):
+        g.build()
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def test_matcher_adapter_host_logic_on_port(tmp_path):
+    _build()
+    exe = str(tmp_path / "mcheck_port")
+    odir = os.path.join(ROOT, "oracle")
+    _run(["g++", "-std=c++11", "-O1"] + INC + [os.path.join(TOOLS, "matcher_adapter_check.cpp"),
+                                               os.path.join(TOOLS, "cabi_on_port.cpp"), "-L" + odir, "-lorbport",
+                                               "-Wl,-rpath," + odir, "-o", exe])
+    out = _run([exe])
+    assert "all comparisons identical" in out and out.count(" same") == 24 and "DIFFERENT" not in out, out
+
+
+def _link_product(tmp_path):
+    _build()
+    exe = str(tmp_path / "mcheck")
+    ldir = os.path.join(ROOT, "vo_slam_test_b200", "lib")
+    _run(["g++", "-std=c++11", "-O1"] + INC + [os.path.join(TOOLS, "matcher_adapter_check.cpp"), "-L" + ldir, "-lvoslam_b200",
+                                               "-Wl,-rpath," + ldir, "-o", exe])
+    return exe
+
+
+def test_matcher_adapter_links_against_the_library(tmp_path):
+    out = _run([_link_product(tmp_path)])
+    assert "matcher adapter" in out
+
+
+@pytest.mark.gpu
+def test_matcher_adapter_on_gpu(tmp_path):
+    out = _run([_link_product(tmp_path)])
+    assert "all comparisons identical" in out and out.count(" same") == 24 and "DIFFERENT" not in out, out

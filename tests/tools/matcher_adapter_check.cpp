@@ -1,0 +1,214 @@
+// tests/tools/matcher_adapter_check.cpp -- compile/link check of include/orb_b200_matcher.hpp against stand-in Frame /
+// KeyFrame / MapPoint types, and (with a GPU) a run-time comparison with a CPU statement of the reference's own loops
+// (tests/tools/myslam_stub.hpp, RefMatcher) on identical object graphs: the mappoints_ / mappointMatches vectors written by
+// the two must be the same pointers, and the returned match counts equal.
+//   g++ -std=c++11 -Ioracle/compat -Iinclude tests/tools/matcher_adapter_check.cpp -Lvo_slam_test_b200/lib -lvoslam_b200 -o /tmp/mcheck
+#include <cstdio>
+#include <cstring>
+#include <set>
+
+#include "myslam_stub.hpp"
+#include "orb_b200_matcher.hpp"
+
+using namespace myslam;
+
+static unsigned g_seed = 1;
+static unsigned rnd() { g_seed = g_seed * 1664525u + 1013904223u; return g_seed >> 8; }
+static float urand() { return (float)(rnd() & 0xFFFFFF) / 16777216.0f; }
+
+static void flipBits(uchar* d, int nflip) {
+  for (int k = 0; k < nflip; ++k) { const unsigned b = rnd() % 256; d[b >> 3] ^= (uchar)(1u << (b & 7)); }
+}
+
+struct Scene {
+  Camera cam;
+  std::vector<MapPoint> points;         // storage; pointers into it are shared by every copy of the frames
+  Frame cur, last;
+  KeyFrame kf1, kf2;
+  std::vector<MapPoint*> local;
+};
+
+static void fillFeatures(std::vector<cv::KeyPoint>& kps, cv::Mat& desc, std::vector<float>* uright, int n, int W, int H) {
+  kps.resize(n);
+  desc = cv::Mat(n, 32, CV_8UC1);
+  if (uright) uright->resize(n);
+  for (int i = 0; i < n; ++i) {
+    kps[i] = cv::KeyPoint(urand() * W, urand() * H, 31.f, urand() * 360.f, 20.f + (float)(rnd() % 60), (int)(rnd() % 8), -1);
+    for (int b = 0; b < 32; ++b) desc.data[(size_t)i * 32 + b] = (uchar)rnd();
+    if (uright) (*uright)[i] = (rnd() % 3 == 0) ? -1.f : kps[i].pt.x - 30.f * urand();
+  }
+}
+
+static void buildScene(Scene& s, unsigned seed, bool moveForward) {
+  g_seed = seed;
+  const int W = 640, H = 480, N = 1000, M = 900;
+  s.cam.fx_ = 517.3f; s.cam.fy_ = 516.5f; s.cam.cx_ = 318.6f; s.cam.cy_ = 255.3f; s.cam.bf_ = 40.f; s.cam.b_ = 40.f / 517.3f;
+  Frame& c = s.cur;
+  c.camera_ = &s.cam;
+  c.N_ = N;
+  fillFeatures(c.unKeypoints_, c.descriptors_, &c.uRight_, N, W, H);
+  c.xMin_ = 0; c.yMin_ = 0; c.xMax_ = W; c.yMax_ = H;
+  c.gridPerPixelWidth_ = 64.f / (c.xMax_ - c.xMin_); c.gridPerPixelHeight_ = 48.f / (c.yMax_ - c.yMin_);
+  c.scaleFactors_.resize(8); c.scaleFactors_[0] = 1.f;
+  for (int l = 1; l < 8; ++l) c.scaleFactors_[l] = (float)(c.scaleFactors_[l - 1] * (double)1.2f);
+  c.assignFeaturesToGrid();
+  c.Tcw_ = SE3::rotY(0.02, 0.05, -0.01, 0.1);
+  c.mappoints_.assign(N, nullptr);
+
+  s.points.resize(M + 200);
+  Frame& l = s.last;
+  l.camera_ = &s.cam;
+  l.Tcw_ = moveForward ? SE3::rotY(0.02, 0.05, -0.01, 0.5) : SE3::rotY(0.021, 0.06, -0.012, 0.11);
+  l.N_ = M;
+  l.unKeypoints_.resize(M);
+  l.mappoints_.assign(M, nullptr);
+  l.outliers_.assign(M, false);
+  const SE3 Twc = c.Tcw_.inverse();
+  for (int i = 0; i < M; ++i) {
+    const int j = (int)(rnd() % N);                 // the current-frame feature this point should land near
+    MapPoint& mp = s.points[i];
+    const double z = (rnd() % 40 == 0) ? -1.0 : 1.0 + 6.0 * urand();
+    const double u = c.unKeypoints_[j].pt.x + 8.0 * (urand() - 0.5) + ((rnd() % 25 == 0) ? 700.0 : 0.0);
+    const double v = c.unKeypoints_[j].pt.y + 8.0 * (urand() - 0.5);
+    mp.pos_ = Twc * Vector3d((u - s.cam.cx_) / s.cam.fx_ * z, (v - s.cam.cy_) / s.cam.fy_ * z, z);
+    mp.descriptor_ = c.descriptors_.row(j).clone();
+    flipBits(mp.descriptor_.data, (int)(rnd() % 70));
+    mp.observe_cnt_ = (int)(rnd() % 3);             // 0: a temporal point that does not block later ones
+    l.unKeypoints_[i] = c.unKeypoints_[j];
+    l.unKeypoints_[i].octave = std::max(0, std::min(7, c.unKeypoints_[j].octave + (int)(rnd() % 3) - 1));
+    l.unKeypoints_[i].angle = std::fmod(c.unKeypoints_[j].angle + ((rnd() % 6 == 0) ? 360.f * urand() : 3.f * urand()), 360.f);
+    l.mappoints_[i] = (rnd() % 10 == 0) ? nullptr : &mp;
+    l.outliers_[i] = rnd() % 12 == 0;
+    // local-map view of the same point
+    mp.bad_ = rnd() % 15 == 0;
+    mp.trackInLocalMap_ = rnd() % 8 != 0;
+    mp.trackScaleLevel_ = l.unKeypoints_[i].octave;
+    mp.trackProj_u_ = (float)u; mp.trackProj_v_ = (float)v; mp.trackProj_uR_ = (float)u - 40.f / (float)std::fabs(z);
+    mp.viewCos_ = 0.99f + 0.01f * urand();
+    {                                                // scale-invariance range around the true distance (reloc search)
+      const float d3 = (float)(mp.pos_ - Twc.translation()).norm();
+      mp.maxDistance_ = d3 * (0.7f + 1.6f * urand());
+      mp.minDistance_ = mp.maxDistance_ / 3.5831808f;
+    }
+    s.local.push_back(&mp);
+  }
+  for (int i = 0; i < N; ++i)                        // some features of the current frame already hold points
+    if (rnd() % 9 == 0) { MapPoint& mp = s.points[M + (rnd() % 200)]; mp.observe_cnt_ = (int)(rnd() % 2); c.mappoints_[i] = &mp; }
+
+  // two key frames + feature vectors (node = a coarse hash of the feature so that corresponding features share a node)
+  KeyFrame* kfs[2] = {&s.kf1, &s.kf2};
+  for (int k = 0; k < 2; ++k) {
+    KeyFrame& kf = *kfs[k];
+    kf.N_ = N;
+    kf.unKeypoints_ = c.unKeypoints_;
+    kf.descriptors_ = c.descriptors_.clone();
+    kf.mappoints_.assign(N, nullptr);
+    kf.scaleFactors_ = c.scaleFactors_;
+    for (int i = 0; i < N; ++i) {
+      flipBits(kf.descriptors_.data + (size_t)i * 32, (int)(rnd() % 50));
+      kf.unKeypoints_[i].angle = std::fmod(c.unKeypoints_[i].angle + ((rnd() % 5 == 0) ? 360.f * urand() : 4.f * urand()), 360.f);
+      if (rnd() % 5 != 0) kf.mappoints_[i] = &s.points[rnd() % M];
+      if (rnd() % 7 != 0) kf.featVec_[(unsigned)((i * 2654435761u) >> 26) + (rnd() % 11 == 0 ? 100u : 0u)].push_back((unsigned)i);
+    }
+  }
+  for (int i = 0; i < N; ++i)
+    if (rnd() % 7 != 0) c.featVec_[(unsigned)((i * 2654435761u) >> 26) + (rnd() % 13 == 0 ? 200u : 0u)].push_back((unsigned)i);
+}
+
+static int fails = 0;
+static void expect(bool ok, const char* what) {
+  std::printf("  %-58s %s\n", what, ok ? "same" : "DIFFERENT");
+  if (!ok) ++fails;
+}
+
+int main() {
+  int ndev = 0;
+  orbx_device_count(&ndev);
+  if (ndev == 0) { std::printf("matcher adapter links; no CUDA device -> compute skipped\n"); return 0; }
+  typedef myslam_b200::MatcherT<Frame, KeyFrame, MapPoint> Matcher;
+  for (int round = 0; round < 4; ++round) {
+    const bool fwd = round == 1, checkRot = round != 2;
+    const float ratio = round == 3 ? 0.9f : 0.7f;
+    Scene a, b;                                   // identical object graphs: a for the reference loops, b for the adapter
+    buildScene(a, 77u + round, fwd);
+    buildScene(b, 77u + round, fwd);
+    RefMatcher ref(ratio);
+    Matcher gpu(ratio);
+    std::printf("round %d (forward %d, checkRot %d, ratio %.2f)\n", round, (int)fwd, (int)checkRot, ratio);
+
+    // 1. frame-to-frame projection search; compare by index into the scene's own point storage
+    Frame ca = a.cur, cb = b.cur;
+    int na = ref.searchByProjection(&ca, &a.last, 15.f, checkRot);
+    int nb = gpu.searchByProjection(&cb, &b.last, 15.f, checkRot);
+    bool same = na == nb;
+    for (size_t i = 0; i < ca.mappoints_.size() && same; ++i) {
+      const long ia = ca.mappoints_[i] ? (long)(ca.mappoints_[i] - &a.points[0]) : -1;
+      const long ib = cb.mappoints_[i] ? (long)(cb.mappoints_[i] - &b.points[0]) : -1;
+      same = ia == ib;
+    }
+    std::printf("  searchByProjection(Frame*,Frame*): %d matches\n", na);
+    expect(same && na > 50, "searchByProjection(Frame*, Frame*, radius, checkRot)");
+
+    // 2. local-map projection search
+    ca = a.cur; cb = b.cur;
+    na = ref.searchByProjection(&ca, a.local, 1.0f + round);
+    nb = gpu.searchByProjection(&cb, b.local, 1.0f + round);
+    same = na == nb;
+    for (size_t i = 0; i < ca.mappoints_.size() && same; ++i) {
+      const long ia = ca.mappoints_[i] ? (long)(ca.mappoints_[i] - &a.points[0]) : -1;
+      const long ib = cb.mappoints_[i] ? (long)(cb.mappoints_[i] - &b.points[0]) : -1;
+      same = ia == ib;
+    }
+    std::printf("  searchByProjection(Frame*,vector<MapPoint*>): %d matches\n", na);
+    expect(same && na > 50, "searchByProjection(Frame*, vector<MapPoint*>&, thRadius)");
+
+    // 2b. relocalisation projection search against a key frame (some of its points already "found")
+    {
+      KeyFrame ka = a.kf1, kb = b.kf1;
+      for (size_t i = 0; i < ka.mappoints_.size(); ++i) {          // give the key frame the points that project near feature i
+        ka.mappoints_[i] = i < a.last.mappoints_.size() ? a.last.mappoints_[i] : nullptr;
+        kb.mappoints_[i] = i < b.last.mappoints_.size() ? b.last.mappoints_[i] : nullptr;
+        if (i < a.last.unKeypoints_.size()) { ka.unKeypoints_[i].angle = a.last.unKeypoints_[i].angle; kb.unKeypoints_[i].angle = b.last.unKeypoints_[i].angle; }
+      }
+      std::set<MapPoint*> fa, fb;
+      for (size_t i = 0; i < 900; i += 17) { fa.insert(&a.points[i]); fb.insert(&b.points[i]); }
+      ca = a.cur; cb = b.cur;
+      na = ref.searchByProjection(&ca, &ka, 10.f + 5.f * round, round == 1 ? 64.f : 100.f, fa, checkRot);
+      nb = gpu.searchByProjection(&cb, &kb, 10.f + 5.f * round, round == 1 ? 64.f : 100.f, fb, checkRot);
+      same = na == nb;
+      for (size_t i = 0; i < ca.mappoints_.size() && same; ++i) {
+        const long ia = ca.mappoints_[i] ? (long)(ca.mappoints_[i] - &a.points[0]) : -1;
+        const long ib = cb.mappoints_[i] ? (long)(cb.mappoints_[i] - &b.points[0]) : -1;
+        same = ia == ib;
+      }
+      std::printf("  searchByProjection(Frame*,KeyFrame*): %d matches\n", na);
+      expect(same && na > 50, "searchByProjection(Frame*, KeyFrame*, radius, distTh, found, rot)");
+    }
+
+    // 3. BoW search key frame -> frame
+    std::vector<MapPoint*> ma, mb;
+    na = ref.searchByBoW(&a.kf1, &a.cur, nullptr, ma, checkRot);
+    nb = gpu.searchByBoW(&b.kf1, &b.cur, mb, checkRot);
+    same = na == nb && ma.size() == mb.size();
+    for (size_t i = 0; i < ma.size() && same; ++i)
+      same = (ma[i] ? (long)(ma[i] - &a.points[0]) : -1) == (mb[i] ? (long)(mb[i] - &b.points[0]) : -1);
+    std::printf("  searchByBoW(KeyFrame*,Frame*): %d matches\n", na);
+    expect(same && na > 50, "searchByBoW(KeyFrame*, Frame*, matches, checkRot)");
+
+    // 4. BoW search key frame -> key frame
+    na = ref.searchByBoW(&a.kf1, nullptr, &a.kf2, ma, checkRot);
+    nb = gpu.searchByBoW(&b.kf1, &b.kf2, mb, checkRot);
+    same = na == nb && ma.size() == mb.size();
+    for (size_t i = 0; i < ma.size() && same; ++i)
+      same = (ma[i] ? (long)(ma[i] - &a.points[0]) : -1) == (mb[i] ? (long)(mb[i] - &b.points[0]) : -1);
+    std::printf("  searchByBoW(KeyFrame*,KeyFrame*): %d matches\n", na);
+    expect(same && na > 20, "searchByBoW(KeyFrame*, KeyFrame*, matches, checkRot)");
+
+    // 5. computeDistance
+    const int d0 = RefMatcher::computeDistance(a.cur.descriptors_.row(3), a.kf1.descriptors_.row(3));
+    const int d1 = Matcher::computeDistance(b.cur.descriptors_.row(3), b.kf1.descriptors_.row(3));
+    expect(d0 == d1, "computeDistance(Mat, Mat)");
+  }
+  std::printf(fails ? "matcher adapter: %d comparisons DIFFER\n" : "matcher adapter: all comparisons identical\n", fails);
+  return fails ? 1 : 0;
+}

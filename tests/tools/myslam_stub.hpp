@@ -1,0 +1,356 @@
+// tests/tools/myslam_stub.hpp -- TEST INFRASTRUCTURE.  Stand-ins for the reference's Frame / KeyFrame / MapPoint / Camera /
+// SE3 types with exactly the members Matcher's loops touch (include/myslam/frame.h:16-71, keyframe.h, mappoint.h:20-90,
+// camera.h:13-45), so that include/orb_b200_matcher.hpp can be compiled and run without Sophus / Eigen / DBoW3, plus a
+// loop-for-loop CPU statement of the reference's search functions over these objects (`RefMatcher`), which is what the
+// adapter's results are compared with.
+#pragma once
+#include <cmath>
+#include <map>
+#include <set>
+#include <vector>
+
+#include "opencv/cv.h"
+
+namespace myslam {
+
+struct Vector3d {
+  double d[3];
+  Vector3d() { d[0] = d[1] = d[2] = 0; }
+  Vector3d(double x, double y, double z) { d[0] = x; d[1] = y; d[2] = z; }
+  double operator[](int i) const { return d[i]; }
+  Vector3d operator-(const Vector3d& o) const { return Vector3d(d[0] - o.d[0], d[1] - o.d[1], d[2] - o.d[2]); }
+  double norm() const { return std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]); }
+};
+struct Vector2d {
+  double d[2];
+  Vector2d(double x, double y) { d[0] = x; d[1] = y; }
+  double operator[](int i) const { return d[i]; }
+};
+
+// rigid transform x -> R x + t (what Sophus::SE3 provides to the matcher: operator*, inverse, translation)
+struct SE3 {
+  double R[9], t[3];
+  SE3() { for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0); t[0] = t[1] = t[2] = 0; }
+  static SE3 rotY(double a, double tx, double ty, double tz) {
+    SE3 s; s.R[0] = std::cos(a); s.R[2] = std::sin(a); s.R[6] = -std::sin(a); s.R[8] = std::cos(a);
+    s.t[0] = tx; s.t[1] = ty; s.t[2] = tz; return s;
+  }
+  Vector3d operator*(const Vector3d& p) const {
+    return Vector3d(R[0] * p[0] + R[1] * p[1] + R[2] * p[2] + t[0], R[3] * p[0] + R[4] * p[1] + R[5] * p[2] + t[1],
+                    R[6] * p[0] + R[7] * p[1] + R[8] * p[2] + t[2]);
+  }
+  SE3 operator*(const SE3& o) const {
+    SE3 s;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) s.R[i * 3 + j] = R[i * 3] * o.R[j] + R[i * 3 + 1] * o.R[3 + j] + R[i * 3 + 2] * o.R[6 + j];
+      s.t[i] = R[i * 3] * o.t[0] + R[i * 3 + 1] * o.t[1] + R[i * 3 + 2] * o.t[2] + t[i];
+    }
+    return s;
+  }
+  SE3 inverse() const {
+    SE3 s;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) s.R[i * 3 + j] = R[j * 3 + i];
+    for (int i = 0; i < 3; ++i) s.t[i] = -(s.R[i * 3] * t[0] + s.R[i * 3 + 1] * t[1] + s.R[i * 3 + 2] * t[2]);
+    return s;
+  }
+  Vector3d translation() const { return Vector3d(t[0], t[1], t[2]); }
+};
+
+struct Camera {
+  float fx_, fy_, cx_, cy_, bf_, b_;
+  Vector2d camera2pixel(const Vector3d& p) { return Vector2d(fx_ * p[0] / p[2] + cx_, fy_ * p[1] / p[2] + cy_); }   // camera.cpp:72-75
+};
+
+struct Frame;
+struct MapPoint {
+  Vector3d pos_;
+  float minDistance_ = 0, maxDistance_ = 0;
+  float getMinDistanceThreshold() { return 0.8f * minDistance_; }      // mappoint.cpp:391-401
+  float getMaxDistanceThreshold() { return 1.2f * maxDistance_; }
+  inline int predictScale(const float& currDist, Frame* frame);        // mappoint.cpp:182-196
+  cv::Mat descriptor_;
+  int observe_cnt_ = 0;
+  bool bad_ = false;
+  bool trackInLocalMap_ = false;
+  int trackScaleLevel_ = 0;
+  float trackProj_u_ = 0, trackProj_uR_ = 0, trackProj_v_ = 0, viewCos_ = 0;
+  Vector3d getPose() { return pos_; }
+  cv::Mat getDescriptor() { return descriptor_.clone(); }
+  int getObsCnt() { return observe_cnt_; }
+  bool isBad() { return bad_; }
+};
+
+typedef std::map<unsigned, std::vector<unsigned> > FeatureVector;   // DBoW3::FeatureVector
+
+struct Frame {
+  Camera* camera_ = nullptr;
+  SE3 Tcw_;
+  std::vector<cv::KeyPoint> unKeypoints_;
+  std::vector<float> uRight_;
+  cv::Mat descriptors_;
+  std::vector<MapPoint*> mappoints_;
+  std::vector<float> scaleFactors_;
+  size_t N_ = 0;
+  float xMin_ = 0, xMax_ = 0, yMin_ = 0, yMax_ = 0, gridPerPixelWidth_ = 0, gridPerPixelHeight_ = 0;
+  std::vector<int> gridKeypoints_[64][48];
+  std::vector<bool> outliers_;
+  FeatureVector featVec_;
+
+  void assignFeaturesToGrid() {                                       // frame.cpp:72-97
+    for (int i = 0; i < (int)N_; ++i) {
+      const int gx = (int)round((unKeypoints_[i].pt.x - xMin_) * gridPerPixelWidth_);
+      const int gy = (int)round((unKeypoints_[i].pt.y - yMin_) * gridPerPixelHeight_);
+      if (gx >= 0 && gx < 64 && gy >= 0 && gy < 48) gridKeypoints_[gx][gy].push_back(i);
+    }
+  }
+  std::vector<int> getFeaturesInArea(const float& u, const float& v, const float& radius, int min_level, int max_level) {   // frame.cpp:199-247
+    std::vector<int> out;
+    const int x0 = std::max(0, (int)floor((u - xMin_ - radius) * gridPerPixelWidth_));
+    if (x0 >= 64) return out;
+    const int x1 = std::min(63, (int)floor((u - xMin_ + radius) * gridPerPixelWidth_));
+    if (x1 < 0) return out;
+    const int y0 = std::max(0, (int)floor((v - yMin_ - radius) * gridPerPixelHeight_));
+    if (y0 >= 48) return out;
+    const int y1 = std::min(47, (int)floor((v - yMin_ + radius) * gridPerPixelHeight_));
+    if (y1 < 0) return out;
+    for (int ix = x0; ix <= x1; ++ix)
+      for (int iy = y0; iy <= y1; ++iy)
+        for (size_t k = 0; k < gridKeypoints_[ix][iy].size(); ++k) {
+          const int id = gridKeypoints_[ix][iy][k];
+          const cv::KeyPoint& kp = unKeypoints_[id];
+          if (kp.octave < min_level || kp.octave > max_level) continue;
+          if (fabs(kp.pt.x - u) < radius && fabs(kp.pt.y - v) < radius) out.push_back(id);
+        }
+    return out;
+  }
+};
+
+inline int MapPoint::predictScale(const float& currDist, Frame* frame) {
+  const float ratio = maxDistance_ / currDist;
+  int scale = (int)ceil(log(ratio) / log(frame->scaleFactors_[1]));
+  if (scale < 0) scale = 0;
+  else if (scale >= (int)frame->scaleFactors_.size()) scale = (int)frame->scaleFactors_.size() - 1;
+  return scale;
+}
+
+struct KeyFrame {
+  std::vector<float> scaleFactors_;
+  std::vector<cv::KeyPoint> unKeypoints_;
+  cv::Mat descriptors_;
+  size_t N_ = 0;
+  FeatureVector featVec_;
+  std::vector<MapPoint*> mappoints_;
+  std::vector<MapPoint*> getMapPoints() { return mappoints_; }
+};
+
+// ---- CPU statement of the reference's loops over the objects above (checker only) ------------------------------------
+struct RefMatcher {
+  float ratio_;
+  explicit RefMatcher(float r) : ratio_(r) {}
+
+  static int computeDistance(const cv::Mat& a, const cv::Mat& b) {   // matcher.cpp:1240-1256 (value: 256-bit Hamming distance)
+    int d = 0;
+    for (int i = 0; i < 32; ++i) d += __builtin_popcount((unsigned)(a.data[i] ^ b.data[i]));
+    return d;
+  }
+  static void threeMax(std::vector<int>* h, int L, int& i1, int& i2, int& i3) {   // matcher.cpp:1258-1304
+    int m1 = 0, m2 = 0, m3 = 0;
+    for (int i = 0; i < L; ++i) {
+      const int s = (int)h[i].size();
+      if (s > m1) { m3 = m2; i3 = i2; m2 = m1; i2 = i1; m1 = s; i1 = i; }
+      else if (s > m2) { m3 = m2; i3 = i2; m2 = s; i2 = i; }
+      else if (s > m3) { m3 = s; i3 = i; }
+    }
+    if (m2 < 0.1f * (float)m1) { i2 = -1; i3 = -1; }
+    else if (m3 < 0.1f * (float)m1) i3 = -1;
+  }
+  static int histBin(float rot, bool half_even) {
+    if (rot < 0) rot += 360.0f;
+    const float x = rot * (30 / 360.0f);
+    int bin = half_even ? cvRound(x) : (int)round(x);     // :118 uses cvRound, :637 uses round
+    return bin == 30 ? 0 : bin;
+  }
+
+  int searchByProjection(Frame* cur, Frame* last, const float radius, bool checkRot) {   // matcher.cpp:18-148
+    int cnt = 0;
+    std::vector<int> hist[30];
+    Camera* cam = cur->camera_;
+    const int xMax = cur->xMax_, xMin = cur->xMin_, yMax = cur->yMax_, yMin = cur->yMin_;
+    const int levels = (int)cur->scaleFactors_.size();
+    SE3 Tcw = cur->Tcw_;
+    SE3 Tlc = last->Tcw_ * Tcw.inverse();
+    const bool forward = (float)Tlc.translation()[2] > cam->b_;
+    const bool backward = -(float)Tlc.translation()[2] > cam->b_;
+    for (int i = 0; i < (int)last->mappoints_.size(); ++i) {
+      MapPoint* mp = last->mappoints_[i];
+      if (!mp || last->outliers_[i]) continue;
+      Vector3d pc = Tcw * mp->getPose();
+      const float z = (float)pc[2];
+      if (z < 0.0f) continue;
+      const float invz = 1.0f / z;
+      Vector2d px = cam->camera2pixel(pc);
+      const float u = px[0], v = px[1];
+      if (u < xMin || u > xMax || v < yMin || v > yMax) continue;
+      const int oct = last->unKeypoints_[i].octave;
+      const float rs = radius * cur->scaleFactors_[oct];
+      std::vector<int> ids = forward ? cur->getFeaturesInArea(u, v, rs, oct, levels)
+                           : backward ? cur->getFeaturesInArea(u, v, rs, 0, oct)
+                                      : cur->getFeaturesInArea(u, v, rs, oct - 1, oct + 1);
+      if (ids.empty()) continue;
+      int best = 256, bestIdx = -1;
+      const cv::Mat dl = mp->getDescriptor();
+      for (size_t j = 0; j < ids.size(); ++j) {
+        const int idx = ids[j];
+        if (cur->mappoints_[idx] && cur->mappoints_[idx]->observe_cnt_ > 0) continue;
+        if (cur->uRight_[idx] > 0) {
+          const float ur = u - cam->bf_ * invz;
+          if (fabs(ur - cur->uRight_[idx]) > rs) continue;
+        }
+        const int d = computeDistance(dl, cur->descriptors_.row(idx));
+        if (d < best) { best = d; bestIdx = idx; }
+      }
+      if (best <= 100) {
+        cur->mappoints_[bestIdx] = mp;
+        ++cnt;
+        if (checkRot) hist[histBin(last->unKeypoints_[i].angle - cur->unKeypoints_[bestIdx].angle, true)].push_back(bestIdx);
+      }
+    }
+    if (checkRot) {
+      int i1 = -1, i2 = -1, i3 = -1;
+      threeMax(hist, 30, i1, i2, i3);
+      for (int i = 0; i < 30; ++i)
+        if (i != i1 && i != i2 && i != i3)
+          for (size_t j = 0; j < hist[i].size(); ++j) { cur->mappoints_[hist[i][j]] = nullptr; --cnt; }
+    }
+    return cnt;
+  }
+
+  int searchByProjection(Frame* cur, KeyFrame* kf, const float radius, const float distThreshold,
+                         const std::set<MapPoint*>& found, bool checkRot) {                     // matcher.cpp:150-272
+    int cnt = 0;
+    std::vector<int> hist[30];
+    const int xMax = cur->xMax_, xMin = cur->xMin_, yMax = cur->yMax_, yMin = cur->yMin_;
+    const SE3 Tcw = cur->Tcw_;
+    Vector3d Ow = Tcw.inverse().translation();
+    const std::vector<MapPoint*> mps = kf->getMapPoints();
+    for (int i = 0; i < (int)mps.size(); ++i) {
+      MapPoint* mp = mps[i];
+      if (!mp || mp->isBad() || found.count(mp)) continue;
+      Vector3d pc = Tcw * mp->getPose();
+      const float z = pc[2];
+      if (z <= 0) continue;
+      Vector2d px = cur->camera_->camera2pixel(pc);
+      const float u = px[0], v = px[1];
+      if (u > xMax || u < xMin || v > yMax || v < yMin) continue;
+      const float dist3 = (mp->getPose() - Ow).norm();
+      if (dist3 < mp->getMinDistanceThreshold() || dist3 > mp->getMaxDistanceThreshold()) continue;
+      const int lp = mp->predictScale(dist3, cur);
+      const float rs = radius * kf->scaleFactors_[lp];
+      std::vector<int> ids = cur->getFeaturesInArea(u, v, rs, lp - 1, lp + 1);
+      if (ids.empty()) continue;
+      int best = 256, bestIdx = -1;
+      const cv::Mat dl = mp->getDescriptor();
+      for (size_t j = 0; j < ids.size(); ++j) {
+        const int idx = ids[j];
+        if (cur->mappoints_[idx]) continue;
+        const int d = computeDistance(dl, cur->descriptors_.row(idx));
+        if (d < best) { best = d; bestIdx = idx; }
+      }
+      if (best <= distThreshold) {
+        cur->mappoints_[bestIdx] = mp;
+        ++cnt;
+        if (checkRot) hist[histBin(kf->unKeypoints_[i].angle - cur->unKeypoints_[bestIdx].angle, true)].push_back(bestIdx);
+      }
+    }
+    if (checkRot) {
+      int i1 = -1, i2 = -1, i3 = -1;
+      threeMax(hist, 30, i1, i2, i3);
+      for (int i = 0; i < 30; ++i)
+        if (i != i1 && i != i2 && i != i3)
+          for (size_t j = 0; j < hist[i].size(); ++j) { cur->mappoints_[hist[i][j]] = nullptr; --cnt; }
+    }
+    return cnt;
+  }
+
+  int searchByProjection(Frame* f, const std::vector<MapPoint*>& mps, const float thRadius) {   // matcher.cpp:274-353
+    int cnt = 0;
+    for (size_t im = 0; im < mps.size(); ++im) {
+      MapPoint* mp = mps[im];
+      if (mp->isBad() || !mp->trackInLocalMap_) continue;
+      float radius = mp->viewCos_ > 0.998 ? 2.5 : 4.0;
+      radius *= thRadius;
+      const int lp = mp->trackScaleLevel_;
+      const float rs = radius * f->scaleFactors_[lp];
+      const std::vector<int> ids = f->getFeaturesInArea(mp->trackProj_u_, mp->trackProj_v_, rs, lp - 1, lp);
+      if (ids.empty()) continue;
+      int best = 256, bestLevel = -1, best2 = 256, bestLevel2 = -1, bestIdx = -1;
+      const cv::Mat dl = mp->getDescriptor();
+      for (size_t j = 0; j < ids.size(); ++j) {
+        const int idx = ids[j];
+        if (f->mappoints_[idx] && f->mappoints_[idx]->getObsCnt() > 0) continue;
+        if (f->uRight_[idx] > 0 && fabs(mp->trackProj_uR_ - f->uRight_[idx]) > rs) continue;
+        const int d = computeDistance(dl, f->descriptors_.row(idx));
+        if (d < best) { best2 = best; best = d; bestLevel2 = bestLevel; bestLevel = f->unKeypoints_[idx].octave; bestIdx = idx; }
+        else if (d < best2) { bestLevel2 = f->unKeypoints_[idx].octave; best2 = d; }
+      }
+      if (best <= 100) {
+        if (bestLevel == bestLevel2 && float(best) > ratio_ * float(best2)) continue;
+        f->mappoints_[bestIdx] = mp;
+        ++cnt;
+      }
+    }
+    return cnt;
+  }
+
+  // matcher.cpp:449-559 (kf2 == nullptr) and :561-677 (frame == nullptr): the two BoW searches share the merge walk over the
+  // two node-sorted feature vectors; they differ in the exclusion rule, the output indexing and the rounding of the bin.
+  int searchByBoW(KeyFrame* kf, Frame* frame, KeyFrame* kf2, std::vector<MapPoint*>& out, bool checkRot) {
+    int cnt = 0;
+    const bool kk = kf2 != nullptr;
+    out.assign(kk ? kf->N_ : frame->N_, nullptr);
+    std::vector<bool> matched2(kk ? kf2->N_ : 0, false);
+    std::vector<MapPoint*> mps = kf->getMapPoints(), mps2;
+    if (kk) mps2 = kf2->getMapPoints();
+    const FeatureVector& fb = kk ? kf2->featVec_ : frame->featVec_;
+    const cv::Mat& descB = kk ? kf2->descriptors_ : frame->descriptors_;
+    const std::vector<cv::KeyPoint>& kpsB = kk ? kf2->unKeypoints_ : frame->unKeypoints_;
+    std::vector<int> hist[30];
+    FeatureVector::const_iterator a = kf->featVec_.begin(), ae = kf->featVec_.end(), b = fb.begin(), be = fb.end();
+    while (a != ae && b != be) {
+      if (a->first == b->first) {
+        for (size_t ik = 0; ik < a->second.size(); ++ik) {
+          const unsigned ia = a->second[ik];
+          MapPoint* mpk = mps[ia];
+          if (!mpk || mpk->isBad()) continue;
+          int best = 256, bestIdx = -1, best2 = 256;
+          for (size_t ir = 0; ir < b->second.size(); ++ir) {
+            const unsigned ib = b->second[ir];
+            if (kk) { if (matched2[ib] || !mps2[ib] || mps2[ib]->isBad()) continue; }
+            else if (out[ib]) continue;
+            const int d = computeDistance(kf->descriptors_.row(ia), descB.row(ib));
+            if (d < best) { best2 = best; best = d; bestIdx = (int)ib; }
+            else if (d < best2) best2 = d;
+          }
+          if (best <= 50 && (float)best < ratio_ * (float)best2) {
+            if (kk) { out[ia] = mps2[bestIdx]; matched2[bestIdx] = true; }
+            else out[bestIdx] = mpk;
+            if (checkRot) hist[histBin(kf->unKeypoints_[ia].angle - kpsB[bestIdx].angle, !kk)].push_back(kk ? (int)ia : bestIdx);
+            ++cnt;
+          }
+        }
+        ++a; ++b;
+      } else if (a->first < b->first) a = kf->featVec_.lower_bound(b->first);
+      else b = fb.lower_bound(a->first);
+    }
+    if (checkRot) {
+      int i1 = -1, i2 = -1, i3 = -1;
+      threeMax(hist, 30, i1, i2, i3);
+      for (int i = 0; i < 30; ++i)
+        if (i != i1 && i != i2 && i != i3)
+          for (size_t j = 0; j < hist[i].size(); ++j) { out[hist[i][j]] = nullptr; --cnt; }
+    }
+    return cnt;
+  }
+};
+
+}  // namespace myslam
