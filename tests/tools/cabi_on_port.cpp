@@ -36,7 +36,7 @@ int port_sbp_reloc(const port_sbp_frame_in* in, float dist_threshold, int32_t* a
 int port_search_by_bow(const port_bow_side* a, const port_bow_side* b, int mode, float ratio, int th_low, int check_rot,
                        int32_t* match);
 void port_knn2(const uint8_t* q, int Q, const uint8_t* t, long long M, int th, float ratio, int32_t* idx, int32_t* d1,
-               int32_t* d2, uint8_t* ok);
+               int32_t* d2, uint8_t* ok, int nthreads);
 
 int orbx_device_count(int* n) { *n = 1; return ORBX_OK; }
 const char* orbx_last_error(void) { return "cabi_on_port"; }
@@ -73,7 +73,7 @@ int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b, int mode,
 }
 int hamm_knn2(const uint8_t* q, int nq, const uint8_t* t, long long nt, int th, float ratio, int32_t* idx, int32_t* d1,
               int32_t* d2, uint8_t* ok, int) {
-  port_knn2(q, nq, t, nt, th, ratio, idx, d1, d2, ok);
+  port_knn2(q, nq, t, nt, th, ratio, idx, d1, d2, ok, 1);
   return ORBX_OK;
 }
 }
