@@ -251,6 +251,139 @@ int searchByProjection(FrameT* frame_curr, KeyFrameT* keyframe, const float radi
   return match_cnt;
 }
 
+// Matcher::searchByProjection(KeyFrame* keyframe, Sim3& Scw, loopMapPoints, matchMapPoints, th)       matcher.cpp:356-447
+// Host: Sim3 decomposition (:365-368), null / bad / already-found gates (:370-377), projection, isInImg, distance range,
+// viewing angle (:379-404), predictScale; device: KeyFrame::getFeaturesInArea window (no level filter), levels
+// [level_predict-1, level_predict], TH_LOW, and the reference's `matchMapPoints[j]` test by WINDOW POSITION (:422).
+template <class KeyFrameT, class Sim3T, class MapPointT>
+int searchByProjection(KeyFrameT* keyframe, Sim3T& Scw, std::vector<MapPointT*>& loopMapPoints,
+                       std::vector<MapPointT*>& matchMapPoints, int th, int device = 0) {
+  const float fx = keyframe->camera_->fx_, fy = keyframe->camera_->fy_;
+  const float cx = keyframe->camera_->cx_, cy = keyframe->camera_->cy_;
+  const double scale = Scw.scale();
+  auto Rcw = Scw.rotation_matrix() / scale;
+  auto tcw = Scw.translation() / scale;
+  auto Ow = -Rcw.transpose() * tcw;
+  const int M = (int)loopMapPoints.size();
+  const int M1 = M > 0 ? M : 1;
+  std::vector<uint8_t> valid(M1, 0), zeros8(M1, 0), desc((size_t)M1 * 32, 0);
+  std::vector<float> u(M1, 0.f), v(M1, 0.f), zerosf(M1, 0.f);
+  std::vector<int32_t> octave(M1, 0);
+  for (int i = 0; i < M; ++i) {
+    MapPointT* mp = loopMapPoints[i];
+    if (!mp || mp->isBad()) continue;
+    bool alreadyFound = false;                                        // set<MapPoint*>(matchMapPoints) minus nullptr (:370-371)
+    for (size_t k = 0; k < matchMapPoints.size() && !alreadyFound; ++k) alreadyFound = matchMapPoints[k] == mp;
+    if (alreadyFound) continue;
+    auto p_cam = Rcw * mp->getPose() + tcw;
+    const float z = static_cast<float>(p_cam[2]);
+    if (z < 0) continue;
+    const float invz = 1.0f / z;
+    const float x = static_cast<float>(p_cam[0]) * invz;
+    const float y = static_cast<float>(p_cam[1]) * invz;
+    const float pu = fx * x + cx, pv = fy * y + cy;
+    if (!keyframe->isInImg(pu, pv)) continue;
+    const float max_distance = mp->getMaxDistanceThreshold();
+    const float min_distance = mp->getMinDistanceThreshold();
+    auto pline = mp->getPose() - Ow;
+    const float distance = pline.norm();
+    if (distance < min_distance || distance > max_distance) continue;
+    auto pNormal = mp->getNormalVector();
+    if (pline.dot(pNormal) < 0.5 * distance) continue;
+    valid[i] = 1;
+    u[i] = pu; v[i] = pv;
+    octave[i] = mp->predictScale(distance, keyframe);
+    std::memcpy(&desc[(size_t)i * 32], mp->getDescriptor().data, 32);
+  }
+  detail::FrameArrays<KeyFrameT> kf(keyframe);
+  for (int i = 0; i < kf.view.n; ++i) kf.occupied[i] = matchMapPoints[i] != nullptr;
+  orbx_sbp_frame_points pts = {M, valid.data(), u.data(), v.data(), zerosf.data(), octave.data(), zerosf.data(), desc.data(),
+                               zeros8.data()};
+  std::vector<int32_t> assign(kf.view.n > 0 ? kf.view.n : 1, -1);
+  int inlier_cnt = 0;
+  detail::check(orbx_search_by_projection_sim3(&kf.view, &pts, th, assign.data(), &inlier_cnt, device));
+  for (int i = 0; i < kf.view.n; ++i)
+    if (assign[i] >= 0) matchMapPoints[i] = loopMapPoints[assign[i]];                         // :439
+  return inlier_cnt;
+}
+
+// Matcher::searchBySim3(KeyFrame* keyframe1, KeyFrame* keyframe2, matches12, Sim3& S12, th)             matcher.cpp:679-865
+// Host: the "already matched" marks (:697-709), both projections with their gates (:715-743, :781-804; note z < 0 vs
+// z <= 0 and the isBad() test only in the first direction, as in the reference); device: both windowed TH_HIGH searches
+// and the mutual-consistency check (:838-852).
+namespace detail {
+template <class KeyFrameT, class MapPointT, class TransformT, class PoseT>
+void sim3Project(const std::vector<MapPointT*>& mappoints, const std::vector<bool>& matched, bool testBad, bool zStrict,
+                 const PoseT& Tcw, TransformT& S, KeyFrameT* target, float fx, float fy, float cx, float cy,
+                 std::vector<uint8_t>& valid, std::vector<float>& u, std::vector<float>& v, std::vector<int32_t>& octave,
+                 std::vector<uint8_t>& desc) {
+  const int N = (int)mappoints.size();
+  const int N1 = N > 0 ? N : 1;
+  valid.assign(N1, 0); u.assign(N1, 0.f); v.assign(N1, 0.f); octave.assign(N1, 0); desc.assign((size_t)N1 * 32, 0);
+  for (int i = 0; i < N; ++i) {
+    MapPointT* mp = mappoints[i];
+    if (!mp || matched[i]) continue;
+    if (testBad && mp->isBad()) continue;
+    auto p_world = mp->pos_;
+    auto p_own = Tcw * p_world;
+    auto p_other = S * p_own;
+    const float z = static_cast<float>(p_other[2]);
+    if (zStrict ? (z < 0) : (z <= 0)) continue;
+    const float invz = 1.0f / z;
+    const float x = static_cast<float>(p_other[0]) * invz;
+    const float y = static_cast<float>(p_other[1]) * invz;
+    const float pu = fx * x + cx, pv = fy * y + cy;
+    if (!target->isInImg(pu, pv)) continue;
+    const float maxDistance = mp->getMaxDistanceThreshold();
+    const float minDistance = mp->getMinDistanceThreshold();
+    const float distance = p_other.norm();
+    if (distance < minDistance || distance > maxDistance) continue;
+    valid[i] = 1;
+    u[i] = pu; v[i] = pv;
+    octave[i] = mp->predictScale(distance, target);
+    std::memcpy(&desc[(size_t)i * 32], mp->getDescriptor().data, 32);
+  }
+}
+}  // namespace detail
+
+template <class KeyFrameT, class MapPointT, class Sim3T>
+int searchBySim3(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector<MapPointT*>& matches12, Sim3T& S12, const float th,
+                 int device = 0) {
+  const float fx = keyframe1->camera_->fx_, fy = keyframe1->camera_->fy_;
+  const float cx = keyframe1->camera_->cx_, cy = keyframe1->camera_->cy_;
+  std::vector<MapPointT*> mappoints1 = keyframe1->getMapPoints();
+  std::vector<MapPointT*> mappoints2 = keyframe2->getMapPoints();
+  const int N1 = (int)mappoints1.size(), N2 = (int)mappoints2.size();
+  std::vector<bool> matched1(N1, false), matched2(N2, false);
+  auto Tcw1 = keyframe1->getPose();
+  auto Tcw2 = keyframe2->getPose();
+  auto S21 = S12.inverse();
+  for (int i = 0; i < N1; ++i) {
+    MapPointT* mp = matches12[i];
+    if (mp) {
+      matched1[i] = true;
+      const int idx2 = mp->getIndexInKeyFrame(keyframe2);
+      if (idx2 >= 0 && idx2 < N2) matched2[idx2] = true;
+    }
+  }
+  std::vector<uint8_t> valid1, valid2, desc1, desc2;
+  std::vector<float> u1, v1, u2, v2;
+  std::vector<int32_t> oct1, oct2;
+  detail::sim3Project(mappoints1, matched1, true, true, Tcw1, S21, keyframe2, fx, fy, cx, cy, valid1, u1, v1, oct1, desc1);
+  detail::sim3Project(mappoints2, matched2, false, false, Tcw2, S12, keyframe1, fx, fy, cx, cy, valid2, u2, v2, oct2, desc2);
+  std::vector<float> zf((size_t)(N1 > N2 ? N1 : N2) + 1, 0.f);
+  std::vector<uint8_t> z8((size_t)(N1 > N2 ? N1 : N2) + 1, 0);
+  detail::FrameArrays<KeyFrameT> a1(keyframe1), a2(keyframe2);
+  orbx_sbp_frame_points p12 = {N1, valid1.data(), u1.data(), v1.data(), zf.data(), oct1.data(), zf.data(), desc1.data(), z8.data()};
+  orbx_sbp_frame_points p21 = {N2, valid2.data(), u2.data(), v2.data(), zf.data(), oct2.data(), zf.data(), desc2.data(), z8.data()};
+  std::vector<int32_t> match12(N1 > 0 ? N1 : 1, -1);
+  int found = 0;
+  detail::check(orbx_search_by_sim3(&a1.view, &p12, &a2.view, &p21, th, match12.data(), &found, device));
+  for (int i = 0; i < N1; ++i)
+    if (match12[i] >= 0) matches12[i] = mappoints2[match12[i]];                                 // :848
+  return found;
+}
+
 // Matcher::searchByBoW(KeyFrame* keyframe, Frame* frame, mappointMatches, checkRot)              matcher.cpp:449-559
 template <class KeyFrameT, class FrameT, class MapPointT>
 int searchByBoW(KeyFrameT* keyframe, FrameT* frame, std::vector<MapPointT*>& mappointMatches, bool checkRot, float ratio,
@@ -321,11 +454,20 @@ class MatcherT {
                          const FoundSetT& found, bool checkRot = true) {
     return myslam_b200::searchByProjection(frame_curr, keyframe, radius, distThreshold, found, checkRot, device_);
   }
+  template <class Sim3T>
+  int searchByProjection(KeyFrameT* keyframe, Sim3T& Scw, std::vector<MapPointT*>& loopMapPoints,
+                         std::vector<MapPointT*>& matchMapPoints, int th) {
+    return myslam_b200::searchByProjection(keyframe, Scw, loopMapPoints, matchMapPoints, th, device_);
+  }
   int searchByBoW(KeyFrameT* keyframe, FrameT* frame, std::vector<MapPointT*>& mappointMatches, bool checkRot = true) {
     return myslam_b200::searchByBoW(keyframe, frame, mappointMatches, checkRot, ratio_, device_);
   }
   int searchByBoW(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector<MapPointT*>& mappointMatches, bool checkRot) {
     return myslam_b200::searchByBoWKeyFrames(keyframe1, keyframe2, mappointMatches, checkRot, ratio_, device_);
+  }
+  template <class Sim3T>
+  int searchBySim3(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector<MapPointT*>& matches12, Sim3T& S12, const float th) {
+    return myslam_b200::searchBySim3(keyframe1, keyframe2, matches12, S12, th, device_);
   }
   template <class MatT>
   static int computeDistance(const MatT& desp1, const MatT& desp2) { return myslam_b200::computeDistance(desp1, desp2); }

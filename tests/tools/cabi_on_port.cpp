@@ -33,6 +33,8 @@ extern "C" {
 int port_sbp_frame(const port_sbp_frame_in* in, int32_t* assign);
 int port_sbp_local(const port_sbp_local_in* in, int32_t* assign);
 int port_sbp_reloc(const port_sbp_frame_in* in, float dist_threshold, int32_t* assign);
+int port_sbp_sim3(const port_sbp_frame_in* in, int th, int32_t* assign);
+int port_search_by_sim3(const port_sbp_frame_in* in12, const port_sbp_frame_in* in21, float th, int32_t* match12);
 int port_search_by_bow(const port_bow_side* a, const port_bow_side* b, int mode, float ratio, int th_low, int check_rot,
                        int32_t* match);
 void port_knn2(const uint8_t* q, int Q, const uint8_t* t, long long M, int th, float ratio, int32_t* idx, int32_t* d1,
@@ -55,6 +57,26 @@ int orbx_search_by_projection_reloc(const orbx_frame_view* f, const orbx_sbp_fra
                           f->occupied0, p->m, p->valid, p->u, p->v, p->invz, p->octave, p->angle, p->desc, p->has_obs,
                           radius, 0.f, 0, 0, check_rot};
   *match_cnt = port_sbp_reloc(&in, dist_threshold, assign);
+  return ORBX_OK;
+}
+int orbx_search_by_projection_sim3(const orbx_frame_view* f, const orbx_sbp_frame_points* p, int th, int32_t* assign,
+                                   int* match_cnt, int) {
+  port_sbp_frame_in in = {f->kps, f->desc, f->uright, f->n, f->xmin, f->xmax, f->ymin, f->ymax, f->scale_factors, f->nlevels,
+                          f->occupied0, p->m, p->valid, p->u, p->v, p->invz, p->octave, p->angle, p->desc, p->has_obs,
+                          0.f, 0.f, 0, 0, 0};
+  *match_cnt = port_sbp_sim3(&in, th, assign);
+  return ORBX_OK;
+}
+int orbx_search_by_sim3(const orbx_frame_view* kf1, const orbx_sbp_frame_points* p12, const orbx_frame_view* kf2,
+                        const orbx_sbp_frame_points* p21, float th, int32_t* match12, int* found, int) {
+  // the port pairs "searched frame" with "projected points": kf1's points are searched in kf2 and vice versa
+  port_sbp_frame_in in12 = {kf2->kps, kf2->desc, kf2->uright, kf2->n, kf2->xmin, kf2->xmax, kf2->ymin, kf2->ymax, kf2->scale_factors,
+                            kf2->nlevels, kf2->occupied0, p12->m, p12->valid, p12->u, p12->v, p12->invz, p12->octave, p12->angle,
+                            p12->desc, p12->has_obs, 0.f, 0.f, 0, 0, 0};
+  port_sbp_frame_in in21 = {kf1->kps, kf1->desc, kf1->uright, kf1->n, kf1->xmin, kf1->xmax, kf1->ymin, kf1->ymax, kf1->scale_factors,
+                            kf1->nlevels, kf1->occupied0, p21->m, p21->valid, p21->u, p21->v, p21->invz, p21->octave, p21->angle,
+                            p21->desc, p21->has_obs, 0.f, 0.f, 0, 0, 0};
+  *found = port_search_by_sim3(&in12, &in21, th, match12);
   return ORBX_OK;
 }
 int orbx_search_by_projection_local(const orbx_frame_view* f, const orbx_sbp_local_points* p, float th_radius, float ratio,

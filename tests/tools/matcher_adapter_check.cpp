@@ -89,6 +89,9 @@ static void buildScene(Scene& s, unsigned seed, bool moveForward) {
       const float d3 = (float)(mp.pos_ - Twc.translation()).norm();
       mp.maxDistance_ = d3 * (0.7f + 1.6f * urand());
       mp.minDistance_ = mp.maxDistance_ / 3.5831808f;
+      const Vector3d ray = mp.pos_ - Twc.translation();      // mean viewing direction: mostly towards the camera, sometimes not
+      const double nr = ray.norm() > 0 ? ray.norm() : 1.0;
+      mp.normalVector_ = (rnd() % 9 == 0) ? Vector3d(1, 0, 0) : Vector3d(ray[0] / nr + 0.3 * (urand() - 0.5), ray[1] / nr, ray[2] / nr);
     }
     s.local.push_back(&mp);
   }
@@ -104,6 +107,11 @@ static void buildScene(Scene& s, unsigned seed, bool moveForward) {
     kf.descriptors_ = c.descriptors_.clone();
     kf.mappoints_.assign(N, nullptr);
     kf.scaleFactors_ = c.scaleFactors_;
+    kf.camera_ = &s.cam;
+    kf.uRight_ = c.uRight_;
+    kf.xMin_ = c.xMin_; kf.xMax_ = c.xMax_; kf.yMin_ = c.yMin_; kf.yMax_ = c.yMax_;
+    kf.gridPerPixelWidth_ = c.gridPerPixelWidth_; kf.gridPerPixelHeight_ = c.gridPerPixelHeight_;
+    kf.assignFeaturesToGrid();
     for (int i = 0; i < N; ++i) {
       flipBits(kf.descriptors_.data + (size_t)i * 32, (int)(rnd() % 50));
       kf.unKeypoints_[i].angle = std::fmod(c.unKeypoints_[i].angle + ((rnd() % 5 == 0) ? 360.f * urand() : 4.f * urand()), 360.f);
@@ -183,6 +191,67 @@ int main() {
       }
       std::printf("  searchByProjection(Frame*,KeyFrame*): %d matches\n", na);
       expect(same && na > 50, "searchByProjection(Frame*, KeyFrame*, radius, distTh, found, rot)");
+    }
+
+    // 2c. loop-closure projection search through a Sim3 (key frame pose = the current frame's pose, scale != 1)
+    {
+      const double sc = 1.0 + 0.1 * round;
+      SE3 T = a.cur.Tcw_;
+      for (int k = 0; k < 3; ++k) T.t[k] *= sc;             // Sim3(s, R, s*t): x -> s (R x + t) projects like the SE3
+      Sim3 Sa(T, sc), Sb(T, sc);
+      std::vector<MapPoint*> la = a.local, lb = b.local, ma2(a.kf1.N_, nullptr), mb2(b.kf1.N_, nullptr);
+      for (size_t i = 0; i < la.size(); i += 13) { la[i] = nullptr; lb[i] = nullptr; }
+      for (size_t i = 0; i < ma2.size(); i += 7) { ma2[i] = &a.points[(i * 31) % 900]; mb2[i] = &b.points[(i * 31) % 900]; }
+      na = ref.searchByProjection(&a.kf1, Sa, la, ma2, 10);
+      nb = gpu.searchByProjection(&b.kf1, Sb, lb, mb2, 10);
+      same = na == nb;
+      for (size_t i = 0; i < ma2.size() && same; ++i)
+        same = (ma2[i] ? (long)(ma2[i] - &a.points[0]) : -1) == (mb2[i] ? (long)(mb2[i] - &b.points[0]) : -1);
+      std::printf("  searchByProjection(KeyFrame*,Sim3&): %d matches\n", na);
+      expect(same && na > 30, "searchByProjection(KeyFrame*, Sim3&, loopPts, matchPts, th)");
+    }
+
+    // 2d. searchBySim3 between two key frames at the same pose (S12 close to identity, scale != 1 folded into the points)
+    {
+      KeyFrame ka1 = a.kf1, ka2 = a.kf2, kb1 = b.kf1, kb2 = b.kf2;
+      KeyFrame* ks[4] = {&ka1, &ka2, &kb1, &kb2};
+      Scene* sc[4] = {&a, &a, &b, &b};
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int k = k4 & 1;                                      // key frame 1 / 2 of either scene
+        ks[k4]->Tcw_ = sc[k4]->cur.Tcw_;
+        ks[k4]->descriptors_ = ks[k4]->descriptors_.clone();       // cv::Mat copies are shallow
+        for (size_t i = 0; i < ks[k4]->mappoints_.size(); ++i)     // points that really project near feature i of both key frames
+          ks[k4]->mappoints_[i] = (i < 900 && (i * 7 + k) % 11 != 0) ? &sc[k4]->points[i] : nullptr;
+        for (size_t i = 0; i < 900; ++i) {                         // ... which means feature i must sit where point i projects
+          const MapPoint& mp = sc[k4]->points[i];
+          ks[k4]->unKeypoints_[i].pt.x = mp.trackProj_u_ + (float)((i * 13 + k) % 5) - 2.f;
+          ks[k4]->unKeypoints_[i].pt.y = mp.trackProj_v_ + (float)((i * 17 + k) % 5) - 2.f;
+          ks[k4]->unKeypoints_[i].octave = mp.trackScaleLevel_;
+          std::memcpy(ks[k4]->descriptors_.data + i * 32, mp.descriptor_.data, 32);
+          ks[k4]->descriptors_.data[i * 32 + (i % 32)] ^= (uchar)(1u << k);
+        }
+        ks[k4]->assignFeaturesToGrid();
+      }
+      for (int i = 0; i < 900; ++i) {                              // predictScale must land on the feature's level
+        for (int k = 0; k < 2; ++k) {
+          MapPoint& mp = (k ? b : a).points[i];
+          const float d3 = (float)(( (k ? b : a).cur.Tcw_ * mp.pos_)).norm();
+          mp.maxDistance_ = d3 * std::pow(1.2f, (float)mp.trackScaleLevel_ - 0.5f);
+          mp.minDistance_ = mp.maxDistance_ / 3.5831808f;
+          if (i % 50 == 0) mp.indexInKF_[k ? &kb2 : &ka2] = (i * 3) % 1000;
+        }
+      }
+      SE3 I; I.t[0] = 0.002; I.t[2] = -0.001;
+      Sim3 Sa(I, 1.0 + 0.002 * round), Sb(I, 1.0 + 0.002 * round);
+      std::vector<MapPoint*> m12a(ka1.N_, nullptr), m12b(kb1.N_, nullptr);
+      for (size_t i = 0; i < 900; i += 50) { m12a[i] = &a.points[i]; m12b[i] = &b.points[i]; }
+      na = ref.searchBySim3(&ka1, &ka2, m12a, Sa, 7.5f);
+      nb = gpu.searchBySim3(&kb1, &kb2, m12b, Sb, 7.5f);
+      same = na == nb;
+      for (size_t i = 0; i < m12a.size() && same; ++i)
+        same = (m12a[i] ? (long)(m12a[i] - &a.points[0]) : -1) == (m12b[i] ? (long)(m12b[i] - &b.points[0]) : -1);
+      std::printf("  searchBySim3(KeyFrame*,KeyFrame*): %d matches\n", na);
+      expect(same && na > 50, "searchBySim3(KeyFrame*, KeyFrame*, matches12, S12, th)");
     }
 
     // 3. BoW search key frame -> frame

@@ -19,7 +19,19 @@ struct Vector3d {
   Vector3d(double x, double y, double z) { d[0] = x; d[1] = y; d[2] = z; }
   double operator[](int i) const { return d[i]; }
   Vector3d operator-(const Vector3d& o) const { return Vector3d(d[0] - o.d[0], d[1] - o.d[1], d[2] - o.d[2]); }
+  Vector3d operator+(const Vector3d& o) const { return Vector3d(d[0] + o.d[0], d[1] + o.d[1], d[2] + o.d[2]); }
+  Vector3d operator/(double s) const { return Vector3d(d[0] / s, d[1] / s, d[2] / s); }
+  double dot(const Vector3d& o) const { return d[0] * o.d[0] + d[1] * o.d[1] + d[2] * o.d[2]; }
   double norm() const { return std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]); }
+};
+struct Matrix3d {                                     // the slice of Eigen::Matrix3d the Sim3 searches use
+  double m[9];
+  Matrix3d operator/(double s) const { Matrix3d r; for (int i = 0; i < 9; ++i) r.m[i] = m[i] / s; return r; }
+  Matrix3d operator-() const { Matrix3d r; for (int i = 0; i < 9; ++i) r.m[i] = -m[i]; return r; }
+  Matrix3d transpose() const { Matrix3d r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i * 3 + j] = m[j * 3 + i]; return r; }
+  Vector3d operator*(const Vector3d& p) const {
+    return Vector3d(m[0] * p[0] + m[1] * p[1] + m[2] * p[2], m[3] * p[0] + m[4] * p[1] + m[5] * p[2], m[6] * p[0] + m[7] * p[1] + m[8] * p[2]);
+  }
 };
 struct Vector2d {
   double d[2];
@@ -56,6 +68,24 @@ struct SE3 {
   Vector3d translation() const { return Vector3d(t[0], t[1], t[2]); }
 };
 
+// similarity x -> s R x + t (Sophus::Sim3: rotation_matrix() returns s*R, like the non-templated Sophus the reference uses)
+struct Sim3 {
+  SE3 rt; double s;
+  Sim3(const SE3& T, double scale) : rt(T), s(scale) {}
+  double scale() const { return s; }
+  Matrix3d rotation_matrix() const { Matrix3d r; for (int i = 0; i < 9; ++i) r.m[i] = s * rt.R[i]; return r; }
+  Vector3d translation() const { return rt.translation(); }
+  Vector3d operator*(const Vector3d& p) const {
+    const Vector3d r = rt * p;                          // R p + t ...
+    return Vector3d(s * (r[0] - rt.t[0]) + rt.t[0], s * (r[1] - rt.t[1]) + rt.t[1], s * (r[2] - rt.t[2]) + rt.t[2]);   // ... as s R p + t
+  }
+  Sim3 inverse() const {                                // x = (1/s) R^T (y - t)
+    SE3 inv = rt.inverse();
+    for (int k = 0; k < 3; ++k) inv.t[k] /= s;
+    return Sim3(inv, 1.0 / s);
+  }
+};
+
 struct Camera {
   float fx_, fy_, cx_, cy_, bf_, b_;
   Vector2d camera2pixel(const Vector3d& p) { return Vector2d(fx_ * p[0] / p[2] + cx_, fy_ * p[1] / p[2] + cy_); }   // camera.cpp:72-75
@@ -65,6 +95,11 @@ struct Frame;
 struct MapPoint {
   Vector3d pos_;
   float minDistance_ = 0, maxDistance_ = 0;
+  Vector3d normalVector_;
+  Vector3d getNormalVector() { return normalVector_; }
+  std::map<struct KeyFrame*, int> indexInKF_;
+  int getIndexInKeyFrame(struct KeyFrame* kf) { return indexInKF_.count(kf) ? indexInKF_[kf] : -1; }
+  inline int predictScale(const float& currDist, struct KeyFrame* kf);  // mappoint.cpp:198-212
   float getMinDistanceThreshold() { return 0.8f * minDistance_; }      // mappoint.cpp:391-401
   float getMaxDistanceThreshold() { return 1.2f * maxDistance_; }
   inline int predictScale(const float& currDist, Frame* frame);        // mappoint.cpp:182-196
@@ -134,6 +169,39 @@ inline int MapPoint::predictScale(const float& currDist, Frame* frame) {
 }
 
 struct KeyFrame {
+  Camera* camera_ = nullptr;
+  SE3 Tcw_;
+  SE3 getPose() { return Tcw_; }
+  std::vector<float> uRight_;
+  float xMin_ = 0, xMax_ = 0, yMin_ = 0, yMax_ = 0, gridPerPixelWidth_ = 0, gridPerPixelHeight_ = 0;
+  std::vector<std::vector<std::vector<int> > > gridKeypoints_;
+  bool isInImg(const float& u, const float& v) { return u >= xMin_ && v >= yMin_ && u < xMax_ && v < yMax_; }   // keyframe.cpp:64-67
+  void assignFeaturesToGrid() {                                        // same rule as Frame (keyframe.cpp copies the frame's grid)
+    gridKeypoints_.assign(64, std::vector<std::vector<int> >(48));
+    for (int i = 0; i < (int)N_; ++i) {
+      const int gx = (int)round((unKeypoints_[i].pt.x - xMin_) * gridPerPixelWidth_);
+      const int gy = (int)round((unKeypoints_[i].pt.y - yMin_) * gridPerPixelHeight_);
+      if (gx >= 0 && gx < 64 && gy >= 0 && gy < 48) gridKeypoints_[gx][gy].push_back(i);
+    }
+  }
+  std::vector<int> getFeaturesInArea(const float& u, const float& v, const float& radius) {   // keyframe.cpp:268-312
+    std::vector<int> out;
+    const int x0 = std::max(0, (int)floor((u - xMin_ - radius) * gridPerPixelWidth_));
+    if (x0 >= 64) return out;
+    const int x1 = std::min(63, (int)floor((u - xMin_ + radius) * gridPerPixelWidth_));
+    if (x1 < 0) return out;
+    const int y0 = std::max(0, (int)floor((v - yMin_ - radius) * gridPerPixelHeight_));
+    if (y0 >= 48) return out;
+    const int y1 = std::min(47, (int)floor((v - yMin_ + radius) * gridPerPixelHeight_));
+    if (y1 < 0) return out;
+    for (int ix = x0; ix <= x1; ++ix)
+      for (int iy = y0; iy <= y1; ++iy)
+        for (size_t k = 0; k < gridKeypoints_[ix][iy].size(); ++k) {
+          const int id = gridKeypoints_[ix][iy][k];
+          if (fabs(unKeypoints_[id].pt.x - u) < radius && fabs(unKeypoints_[id].pt.y - v) < radius) out.push_back(id);
+        }
+    return out;
+  }
   std::vector<float> scaleFactors_;
   std::vector<cv::KeyPoint> unKeypoints_;
   cv::Mat descriptors_;
@@ -142,6 +210,14 @@ struct KeyFrame {
   std::vector<MapPoint*> mappoints_;
   std::vector<MapPoint*> getMapPoints() { return mappoints_; }
 };
+
+inline int MapPoint::predictScale(const float& currDist, KeyFrame* kf) {
+  const float ratio = maxDistance_ / currDist;
+  int scale = (int)ceil(log(ratio) / log(kf->scaleFactors_[1]));
+  if (scale < 0) scale = 0;
+  else if (scale >= (int)kf->scaleFactors_.size()) scale = (int)kf->scaleFactors_.size() - 1;
+  return scale;
+}
 
 // ---- CPU statement of the reference's loops over the objects above (checker only) ------------------------------------
 struct RefMatcher {
@@ -270,6 +346,99 @@ struct RefMatcher {
           for (size_t j = 0; j < hist[i].size(); ++j) { cur->mappoints_[hist[i][j]] = nullptr; --cnt; }
     }
     return cnt;
+  }
+
+  int searchByProjection(KeyFrame* kf, Sim3& Scw, std::vector<MapPoint*>& loopPts, std::vector<MapPoint*>& matchPts, int th) {
+    Camera* cam = kf->camera_;                                                                  // matcher.cpp:356-447
+    const double sc = Scw.scale();
+    Matrix3d Rcw = Scw.rotation_matrix() / sc;
+    Vector3d tcw = Scw.translation() / sc;
+    Vector3d Ow = -Rcw.transpose() * tcw;
+    std::set<MapPoint*> already(matchPts.begin(), matchPts.end());
+    already.erase(nullptr);
+    int cnt = 0;
+    for (size_t i = 0; i < loopPts.size(); ++i) {
+      MapPoint* mp = loopPts[i];
+      if (!mp || mp->isBad() || already.count(mp)) continue;
+      Vector3d pc = Rcw * mp->getPose() + tcw;
+      const float z = (float)pc[2];
+      if (z < 0) continue;
+      const float invz = 1.0f / z;
+      const float x = (float)pc[0] * invz, y = (float)pc[1] * invz;
+      const float u = cam->fx_ * x + cam->cx_, v = cam->fy_ * y + cam->cy_;
+      if (!kf->isInImg(u, v)) continue;
+      Vector3d pl = mp->getPose() - Ow;
+      const float dist3 = pl.norm();
+      if (dist3 < mp->getMinDistanceThreshold() || dist3 > mp->getMaxDistanceThreshold()) continue;
+      if (pl.dot(mp->getNormalVector()) < 0.5 * dist3) continue;
+      const int lp = mp->predictScale(dist3, kf);
+      const float radius = th * kf->scaleFactors_[lp];
+      const std::vector<int> ids = kf->getFeaturesInArea(u, v, radius);
+      if (ids.empty()) continue;
+      cv::Mat dm = mp->getDescriptor();
+      int best = 256, bestIdx = -1;
+      for (int j = 0; j < (int)ids.size(); ++j) {
+        const int idx = ids[j];
+        if (matchPts[j]) continue;                          // the reference indexes by the loop counter here (:422)
+        const int level = kf->unKeypoints_[idx].octave;
+        if (level < lp - 1 || level > lp) continue;
+        const int d = computeDistance(dm, kf->descriptors_.row(idx));
+        if (d < best) { best = d; bestIdx = idx; }
+      }
+      if (best <= 50) { matchPts[bestIdx] = mp; ++cnt; }
+    }
+    return cnt;
+  }
+
+  // one direction of searchBySim3 (matcher.cpp:711-780 with badTest/strict = true, :782-846 with false)
+  static void sim3Direction(const std::vector<MapPoint*>& mps, const std::vector<bool>& matched, bool badTest, bool strict,
+                            const SE3& Tcw, Sim3& S, KeyFrame* target, Camera* cam, float th, std::vector<int>& match) {
+    for (int i = 0; i < (int)mps.size(); ++i) {
+      MapPoint* mp = mps[i];
+      if (!mp || matched[i]) continue;
+      if (badTest && mp->isBad()) continue;
+      Vector3d po = S * (Tcw * mp->pos_);
+      const float z = (float)po[2];
+      if (strict ? z < 0 : z <= 0) continue;
+      const float invz = 1.0f / z;
+      const float x = (float)po[0] * invz, y = (float)po[1] * invz;
+      const float u = cam->fx_ * x + cam->cx_, v = cam->fy_ * y + cam->cy_;
+      if (!target->isInImg(u, v)) continue;
+      const float dist3 = po.norm();
+      if (dist3 < mp->getMinDistanceThreshold() || dist3 > mp->getMaxDistanceThreshold()) continue;
+      const int lp = mp->predictScale(dist3, target);
+      const float radius = th * target->scaleFactors_[lp];
+      const std::vector<int> ids = target->getFeaturesInArea(u, v, radius);
+      if (ids.empty()) continue;
+      const cv::Mat dm = mp->getDescriptor();
+      int best = 256, bestIdx = -1;
+      for (size_t k = 0; k < ids.size(); ++k) {
+        const cv::KeyPoint& kp = target->unKeypoints_[ids[k]];
+        if (kp.octave < lp - 1 || kp.octave > lp) continue;
+        const int d = computeDistance(dm, target->descriptors_.row(ids[k]));
+        if (d < best) { best = d; bestIdx = ids[k]; }
+      }
+      if (best <= 100) match[i] = bestIdx;
+    }
+  }
+  int searchBySim3(KeyFrame* kf1, KeyFrame* kf2, std::vector<MapPoint*>& matches12, Sim3& S12, const float th) {   // matcher.cpp:679-865
+    std::vector<MapPoint*> mps1 = kf1->getMapPoints(), mps2 = kf2->getMapPoints();
+    const int N1 = (int)mps1.size(), N2 = (int)mps2.size();
+    std::vector<bool> matched1(N1, false), matched2(N2, false);
+    Sim3 S21 = S12.inverse();
+    for (int i = 0; i < N1; ++i)
+      if (matches12[i]) {
+        matched1[i] = true;
+        const int idx2 = matches12[i]->getIndexInKeyFrame(kf2);
+        if (idx2 >= 0 && idx2 < N2) matched2[idx2] = true;
+      }
+    std::vector<int> match1(N1, -1), match2(N2, -1);
+    sim3Direction(mps1, matched1, true, true, kf1->getPose(), S21, kf2, kf1->camera_, th, match1);
+    sim3Direction(mps2, matched2, false, false, kf2->getPose(), S12, kf1, kf1->camera_, th, match2);
+    int found = 0;
+    for (int i = 0; i < N1; ++i)
+      if (match1[i] >= 0 && match2[match1[i]] == i) { matches12[i] = mps2[match1[i]]; ++found; }
+    return found;
   }
 
   int searchByProjection(Frame* f, const std::vector<MapPoint*>& mps, const float thRadius) {   // matcher.cpp:274-353
