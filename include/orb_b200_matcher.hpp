@@ -27,9 +27,11 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "orb_b200.h"
@@ -269,12 +271,11 @@ int searchByProjection(KeyFrameT* keyframe, Sim3T& Scw, std::vector<MapPointT*>&
   std::vector<uint8_t> valid(M1, 0), zeros8(M1, 0), desc((size_t)M1 * 32, 0);
   std::vector<float> u(M1, 0.f), v(M1, 0.f), zerosf(M1, 0.f);
   std::vector<int32_t> octave(M1, 0);
+  std::set<MapPointT*> alreadyFound(matchMapPoints.begin(), matchMapPoints.end());          // :370-371
+  alreadyFound.erase(static_cast<MapPointT*>(nullptr));
   for (int i = 0; i < M; ++i) {
     MapPointT* mp = loopMapPoints[i];
-    if (!mp || mp->isBad()) continue;
-    bool alreadyFound = false;                                        // set<MapPoint*>(matchMapPoints) minus nullptr (:370-371)
-    for (size_t k = 0; k < matchMapPoints.size() && !alreadyFound; ++k) alreadyFound = matchMapPoints[k] == mp;
-    if (alreadyFound) continue;
+    if (!mp || mp->isBad() || alreadyFound.count(mp)) continue;
     auto p_cam = Rcw * mp->getPose() + tcw;
     const float z = static_cast<float>(p_cam[2]);
     if (z < 0) continue;
@@ -384,6 +385,176 @@ int searchBySim3(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector<MapPoin
   return found;
 }
 
+// Matcher::fuseMapPoints(KeyFrame* keyframe, vector<MapPoint*>& mappoints, threshold)                  matcher.cpp:1012-1133
+// The windowed search of point i (:1057-1100, with the chi-square reprojection gate :1073-1095) depends only on the point's
+// own geometry and descriptor, so all searches run in one device call.  The gates that the fusing itself can change
+// (isBad(), beObserved(keyframe): :1029) are evaluated in the sequential replay, exactly where the reference evaluates them:
+// a point whose state an earlier fusion changed is, afterwards, either bad or observed by `keyframe`, i.e. skipped either
+// way -- so searching it up front with stale data cannot leak into the result.  replaceMapPoint / addObservation /
+// addMapPoint (:1104-1121) stay the reference's own methods, called in point order.
+template <class KeyFrameT, class MapPointT>
+int fuseMapPoints(KeyFrameT* keyframe, std::vector<MapPointT*>& mappoints, const float& threshold, int device = 0) {
+  const int TH_LOW = 50;
+  const float fx = keyframe->camera_->fx_, fy = keyframe->camera_->fy_;
+  const float cx = keyframe->camera_->cx_, cy = keyframe->camera_->cy_, bf = keyframe->camera_->bf_;
+  auto Tcw = keyframe->getPose();
+  auto Ow = keyframe->getCamCenter();
+  const int M = (int)mappoints.size();
+  const int M1 = M > 0 ? M : 1;
+  std::vector<uint8_t> valid(M1, 0), zeros8(M1, 0), desc((size_t)M1 * 32, 0);
+  std::vector<float> u(M1, 0.f), v(M1, 0.f), ur(M1, 0.f), zerosf(M1, 0.f);
+  std::vector<int32_t> octave(M1, 0);
+  for (int i = 0; i < M; ++i) {
+    MapPointT* mp = mappoints[i];
+    if (!mp) continue;
+    auto p_world = mp->getPose();
+    auto pcam = Tcw * p_world;
+    const float z = static_cast<float>(pcam[2]);
+    if (z < 0.0f) continue;
+    const float invz = 1.0f / z;
+    const float x = static_cast<float>(pcam[0]) * invz;
+    const float y = static_cast<float>(pcam[1]) * invz;
+    const float pu = fx * x + cx, pv = fy * y + cy;
+    if (!keyframe->isInImg(pu, pv)) continue;
+    auto line = p_world - Ow;
+    const float dist = line.norm();
+    const float minDistance = mp->getMinDistanceThreshold();
+    const float maxDistance = mp->getMaxDistanceThreshold();
+    if (dist < minDistance || dist > maxDistance) continue;
+    auto pn = mp->getNormalVector();
+    if (line.dot(pn) < 0.5 * dist) continue;
+    valid[i] = 1;
+    u[i] = pu; v[i] = pv; ur[i] = pu - bf * invz;
+    octave[i] = mp->predictScale(dist, keyframe);
+    std::memcpy(&desc[(size_t)i * 32], mp->getDescriptor().data, 32);
+  }
+  detail::FrameArrays<KeyFrameT> kf(keyframe);
+  orbx_sbp_frame_points pts = {M, valid.data(), u.data(), v.data(), ur.data(), octave.data(), zerosf.data(), desc.data(),
+                               zeros8.data()};
+  std::vector<int32_t> best(M1, -1);
+  detail::check(orbx_window_argmin(&kf.view, &pts, threshold, (float)TH_LOW, 1, best.data(), device));
+  int cnt = 0;
+  for (int i = 0; i < M; ++i) {
+    MapPointT* mp = mappoints[i];
+    if (!mp || mp->isBad() || mp->beObserved(keyframe)) continue;                              // :1029, at replay time
+    if (best[i] < 0) continue;
+    const int bestIdx = best[i];
+    MapPointT* mpOrg = keyframe->mappoints_[bestIdx];
+    if (mpOrg) {
+      if (!mpOrg->isBad()) {
+        if (mpOrg->getObsCnt() > mp->getObsCnt()) mp->replaceMapPoint(mpOrg);
+        else mpOrg->replaceMapPoint(mp);
+      }
+    } else {
+      mp->addObservation(keyframe, bestIdx);
+      keyframe->addMapPoint(mp, bestIdx);
+    }
+    ++cnt;
+  }
+  return cnt;
+}
+
+// Matcher::fuseByPose(KeyFrame* keyframe, Sim3& Scw, loopMapPoints, replaceMapPoints, th)              matcher.cpp:1135-1238
+// Every gate is fixed before the loop (alreadyFound is built once, :1147-1154); only keyframe->mappoints_[bestIdx] is read
+// live in the replay (:1217-1228), because addMapPoint of an earlier point can fill it.
+template <class KeyFrameT, class Sim3T, class MapPointT>
+int fuseByPose(KeyFrameT* keyframe, Sim3T& Scw, std::vector<MapPointT*>& loopMapPoints,
+               std::vector<MapPointT*>& replaceMapPoints, const float th, int device = 0) {
+  const int TH_LOW = 50;
+  const float fx = keyframe->camera_->fx_, fy = keyframe->camera_->fy_;
+  const float cx = keyframe->camera_->cx_, cy = keyframe->camera_->cy_;
+  typedef decltype(keyframe->getPose()) SE3T;
+  SE3T Tcw(Scw.rotation_matrix(), Scw.translation());
+  auto Ow = -Tcw.rotation_matrix().transpose() * Tcw.translation();
+  const int M = (int)loopMapPoints.size();
+  const int M1 = M > 0 ? M : 1;
+  std::vector<uint8_t> valid(M1, 0), zeros8(M1, 0), desc((size_t)M1 * 32, 0);
+  std::vector<float> u(M1, 0.f), v(M1, 0.f), zerosf(M1, 0.f);
+  std::vector<int32_t> octave(M1, 0);
+  std::set<MapPointT*> alreadyFound;                                 // the key frame's own good points (:1147-1154)
+  for (size_t k = 0; k < keyframe->mappoints_.size(); ++k) {
+    MapPointT* mp = keyframe->mappoints_[k];
+    if (mp && !mp->isBad()) alreadyFound.insert(mp);
+  }
+  for (int i = 0; i < M; ++i) {
+    MapPointT* mp = loopMapPoints[i];
+    if (!mp || mp->isBad() || alreadyFound.count(mp)) continue;
+    auto p_cam = Tcw * mp->getPose();
+    const float z = static_cast<float>(p_cam[2]);
+    if (z < 0) continue;
+    const float invz = 1.0f / z;
+    const float x = static_cast<float>(p_cam[0]) * invz;
+    const float y = static_cast<float>(p_cam[1]) * invz;
+    const float pu = fx * x + cx, pv = fy * y + cy;
+    if (!keyframe->isInImg(pu, pv)) continue;
+    const float max_distance = mp->getMaxDistanceThreshold();
+    const float min_distance = mp->getMinDistanceThreshold();
+    auto pline = mp->getPose() - Ow;
+    const float distance = pline.norm();
+    if (distance < min_distance || distance > max_distance) continue;
+    auto pNormal = mp->getNormalVector();
+    if (pline.dot(pNormal) < 0.5 * distance) continue;
+    valid[i] = 1;
+    u[i] = pu; v[i] = pv;
+    octave[i] = mp->predictScale(distance, keyframe);
+    std::memcpy(&desc[(size_t)i * 32], mp->getDescriptor().data, 32);
+  }
+  detail::FrameArrays<KeyFrameT> kf(keyframe);
+  orbx_sbp_frame_points pts = {M, valid.data(), u.data(), v.data(), zerosf.data(), octave.data(), zerosf.data(), desc.data(),
+                               zeros8.data()};
+  std::vector<int32_t> best(M1, -1);
+  detail::check(orbx_window_argmin(&kf.view, &pts, th, (float)TH_LOW, 0, best.data(), device));
+  int fused = 0;
+  for (int i = 0; i < M; ++i) {
+    if (!valid[i] || best[i] < 0) continue;
+    MapPointT* mp = loopMapPoints[i];
+    MapPointT* mpKF = keyframe->mappoints_[best[i]];
+    if (mpKF) {
+      if (!mpKF->isBad()) replaceMapPoints[i] = mpKF;
+    } else {
+      mp->addObservation(keyframe, best[i]);
+      keyframe->addMapPoint(mp, best[i]);
+    }
+    ++fused;
+  }
+  return fused;
+}
+
+// Matcher::searchForTriangulation(KeyFrame* keyframe1, KeyFrame* keyframe2, matchIdxs, Matrix3d& F12, checkRot)
+//                                                                                     matcher.cpp:867-1010, 1306-1324
+// Host: the epipole of camera 1 in image 2 (:886-890) and the flattening; device: the BoW-guided greedy search between
+// features WITHOUT map points, the epipole distance test, the epipolar constraint in double and the rotation histogram.
+template <class KeyFrameT, class Matrix3T>
+int searchForTriangulation(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector<std::pair<int, int> >& matchIdxs,
+                           Matrix3T& F12, bool checkRot = true, int device = 0) {
+  const int TH_LOW = 50;
+  const auto mappoints1 = keyframe1->getMapPoints();
+  const auto mappoints2 = keyframe2->getMapPoints();
+  const auto Cw = keyframe1->getCamCenter();
+  const auto C2 = keyframe2->getPose() * Cw;
+  const auto C2_pixel = keyframe2->camera_->camera2pixel(C2);
+  const float ex = C2_pixel[0], ey = C2_pixel[1];
+  typedef typename std::remove_reference<decltype(keyframe1->featVec_)>::type FV;
+  detail::FeatCsr<FV> c1(keyframe1->featVec_), c2(keyframe2->featVec_);
+  detail::BowSide<KeyFrameT> a(keyframe1, c1), b(keyframe2, c2);
+  for (int i = 0; i < a.side.n; ++i) a.valid[i] = mappoints1[i] == nullptr;                    // :902 looks for features without points
+  for (int i = 0; i < b.side.n; ++i) b.valid[i] = mappoints2[i] == nullptr;                    // :921
+  orbx_tri_side ta = {a.side, reinterpret_cast<const orbx_keypoint*>(keyframe1->unKeypoints_.data()), keyframe1->uRight_.data()};
+  orbx_tri_side tb = {b.side, reinterpret_cast<const orbx_keypoint*>(keyframe2->unKeypoints_.data()), keyframe2->uRight_.data()};
+  double F[9];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F[r * 3 + c] = F12(r, c);
+  std::vector<int32_t> match(a.side.n > 0 ? a.side.n : 1, -1);
+  int match_cnt = 0;
+  detail::check(orbx_search_for_triangulation(&ta, &tb, F, ex, ey, keyframe2->scaleFactors_.data(),
+                                              (int)keyframe2->scaleFactors_.size(), TH_LOW, checkRot, match.data(), &match_cnt,
+                                              device));
+  matchIdxs.clear();
+  matchIdxs.reserve(match_cnt > 0 ? match_cnt : 0);
+  for (int i = 0; i < a.side.n; ++i)
+    if (match[i] >= 0) matchIdxs.push_back(std::make_pair(i, (int)match[i]));                  // :1001-1007
+  return match_cnt;
+}
+
 // Matcher::searchByBoW(KeyFrame* keyframe, Frame* frame, mappointMatches, checkRot)              matcher.cpp:449-559
 template <class KeyFrameT, class FrameT, class MapPointT>
 int searchByBoW(KeyFrameT* keyframe, FrameT* frame, std::vector<MapPointT*>& mappointMatches, bool checkRot, float ratio,
@@ -468,6 +639,19 @@ class MatcherT {
   template <class Sim3T>
   int searchBySim3(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector<MapPointT*>& matches12, Sim3T& S12, const float th) {
     return myslam_b200::searchBySim3(keyframe1, keyframe2, matches12, S12, th, device_);
+  }
+  int fuseMapPoints(KeyFrameT* keyframe, std::vector<MapPointT*>& mappoints, const float& threshold) {
+    return myslam_b200::fuseMapPoints(keyframe, mappoints, threshold, device_);
+  }
+  template <class Sim3T>
+  int fuseByPose(KeyFrameT* keyframe, Sim3T& Scw, std::vector<MapPointT*>& loopMapPoints,
+                 std::vector<MapPointT*>& replaceMapPoints, const float th) {
+    return myslam_b200::fuseByPose(keyframe, Scw, loopMapPoints, replaceMapPoints, th, device_);
+  }
+  template <class Matrix3T>
+  int searchForTriangulation(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector<std::pair<int, int> >& matchIdxs,
+                             Matrix3T& F12, bool checkRot = true) {
+    return myslam_b200::searchForTriangulation(keyframe1, keyframe2, matchIdxs, F12, checkRot, device_);
   }
   template <class MatT>
   static int computeDistance(const MatT& desp1, const MatT& desp2) { return myslam_b200::computeDistance(desp1, desp2); }

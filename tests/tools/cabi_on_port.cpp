@@ -29,11 +29,15 @@ struct port_bow_side {
   int n; const uint8_t* desc; const float* angle; const uint8_t* valid;
   int ngroups; const uint32_t* node_ids; const int32_t* group_start; const int32_t* feat_idx;
 };
+struct port_tri_side { port_bow_side side; const void* kps; const float* uright; };
 extern "C" {
+int port_search_for_triangulation(const port_tri_side* a, const port_tri_side* b, const double* F12, float ex, float ey,
+                                  const float* scale2, int th_low, int check_rot, int32_t* match);
 int port_sbp_frame(const port_sbp_frame_in* in, int32_t* assign);
 int port_sbp_local(const port_sbp_local_in* in, int32_t* assign);
 int port_sbp_reloc(const port_sbp_frame_in* in, float dist_threshold, int32_t* assign);
 int port_sbp_sim3(const port_sbp_frame_in* in, int th, int32_t* assign);
+void port_window_argmin(const port_sbp_frame_in* in, float th_radius, float dist_threshold, int chi2, int32_t* best);
 int port_search_by_sim3(const port_sbp_frame_in* in12, const port_sbp_frame_in* in21, float th, int32_t* match12);
 int port_search_by_bow(const port_bow_side* a, const port_bow_side* b, int mode, float ratio, int th_low, int check_rot,
                        int32_t* match);
@@ -77,6 +81,21 @@ int orbx_search_by_sim3(const orbx_frame_view* kf1, const orbx_sbp_frame_points*
                             kf1->nlevels, kf1->occupied0, p21->m, p21->valid, p21->u, p21->v, p21->invz, p21->octave, p21->angle,
                             p21->desc, p21->has_obs, 0.f, 0.f, 0, 0, 0};
   *found = port_search_by_sim3(&in12, &in21, th, match12);
+  return ORBX_OK;
+}
+int orbx_window_argmin(const orbx_frame_view* f, const orbx_sbp_frame_points* p, float th_radius, float dist_threshold, int chi2,
+                       int32_t* best, int) {
+  port_sbp_frame_in in = {f->kps, f->desc, f->uright, f->n, f->xmin, f->xmax, f->ymin, f->ymax, f->scale_factors, f->nlevels,
+                          f->occupied0, p->m, p->valid, p->u, p->v, p->invz, p->octave, p->angle, p->desc, p->has_obs,
+                          0.f, 0.f, 0, 0, 0};
+  port_window_argmin(&in, th_radius, dist_threshold, chi2, best);
+  return ORBX_OK;
+}
+int orbx_search_for_triangulation(const orbx_tri_side* a, const orbx_tri_side* b, const double* F12, float ex, float ey,
+                                  const float* scale_factors2, int, int th_low, int check_rot, int32_t* match, int* match_cnt, int) {
+  static_assert(sizeof(port_tri_side) == sizeof(orbx_tri_side), "same layout");
+  *match_cnt = port_search_for_triangulation((const port_tri_side*)a, (const port_tri_side*)b, F12, ex, ey, scale_factors2, th_low,
+                                             check_rot, match);
   return ORBX_OK;
 }
 int orbx_search_by_projection_local(const orbx_frame_view* f, const orbx_sbp_local_points* p, float th_radius, float ratio,

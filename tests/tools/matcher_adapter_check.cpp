@@ -252,6 +252,7 @@ int main() {
         same = (m12a[i] ? (long)(m12a[i] - &a.points[0]) : -1) == (m12b[i] ? (long)(m12b[i] - &b.points[0]) : -1);
       std::printf("  searchBySim3(KeyFrame*,KeyFrame*): %d matches\n", na);
       expect(same && na > 50, "searchBySim3(KeyFrame*, KeyFrame*, matches12, S12, th)");
+      for (int i = 0; i < 900; ++i) { a.points[i].indexInKF_.clear(); b.points[i].indexInKF_.clear(); }   // ka2 / kb2 die here
     }
 
     // 3. BoW search key frame -> frame
@@ -272,6 +273,93 @@ int main() {
       same = (ma[i] ? (long)(ma[i] - &a.points[0]) : -1) == (mb[i] ? (long)(mb[i] - &b.points[0]) : -1);
     std::printf("  searchByBoW(KeyFrame*,KeyFrame*): %d matches\n", na);
     expect(same && na > 20, "searchByBoW(KeyFrame*, KeyFrame*, matches, checkRot)");
+
+    // 4b. searchForTriangulation: key frame 2 a little to the right of key frame 1, F12 of that stereo-like pair
+    {
+      KeyFrame ka1 = a.kf1, ka2 = a.kf2, kb1 = b.kf1, kb2 = b.kf2;
+      KeyFrame* ks[4] = {&ka1, &ka2, &kb1, &kb2};
+      for (int k4 = 0; k4 < 4; ++k4) {
+        KeyFrame& kf = *ks[k4];
+        kf.Tcw_ = SE3();
+        if (k4 & 1) {
+          kf.Tcw_.t[0] = -0.3;                              // camera 2 sits at x = +0.3
+          for (int i = 0; i < 1000; ++i) kf.unKeypoints_[i].pt.x -= 25.f + (float)(i % 7);   // disparity; same row => on the epipolar line
+        }
+        for (int i = 0; i < 1000; ++i) {
+          if (i % 9 == 0) kf.unKeypoints_[i].pt.y += 9.f;  // off the epipolar line
+          if ((i + (k4 & 1)) % 4 != 0) kf.mappoints_[i] = nullptr;   // most features have no map point yet
+          if (i % 2 == (k4 & 1)) kf.uRight_[i] = -1.f;
+        }
+      }
+      // F12 with p1^T F12 p2 = 0 for pure x-translation and equal intrinsics: rows of image 1 map to rows of image 2
+      Matrix3d F; for (int i = 0; i < 9; ++i) F.m[i] = 0;
+      F.m[1 * 3 + 2] = 1.0; F.m[2 * 3 + 1] = -1.0;
+      std::vector<std::pair<int, int> > pa, pb;
+      na = ref.searchForTriangulation(&ka1, &ka2, pa, F, checkRot);
+      nb = gpu.searchForTriangulation(&kb1, &kb2, pb, F, checkRot);
+      same = na == nb && pa == pb;
+      std::printf("  searchForTriangulation: %d matches\n", na);
+      expect(same && na > 60, "searchForTriangulation(KeyFrame*, KeyFrame*, idxs, F12, checkRot)");
+    }
+
+    // 6. the two fuse functions (last: they rewire the object graph).  Key-frame features sit where the points project.
+    for (int pass = 0; pass < 2; ++pass) {
+      KeyFrame ka = a.kf1, kb = b.kf1;
+      KeyFrame* ks[2] = {&ka, &kb};
+      Scene* sc[2] = {&a, &b};
+      for (int k = 0; k < 2; ++k) {
+        KeyFrame& kf = *ks[k];
+        Scene& s = *sc[k];
+        kf.Tcw_ = s.cur.Tcw_;
+        kf.descriptors_ = kf.descriptors_.clone();
+        for (int i = 0; i < 1000; ++i) {
+          kf.mappoints_[i] = nullptr;
+          if (i >= 900) continue;
+          MapPoint& mp = s.points[i];
+          mp.bad_ = i % 15 == 3; mp.indexInKF_.clear(); mp.observe_cnt_ = i % 4;
+          kf.unKeypoints_[i].pt.x = mp.trackProj_u_ + (float)((i * 13) % 5) * 0.5f - 1.f;
+          kf.unKeypoints_[i].pt.y = mp.trackProj_v_ + (float)((i * 17) % 5) * 0.5f - 1.f;
+          kf.unKeypoints_[i].octave = mp.trackScaleLevel_;
+          kf.uRight_[i] = (i % 3 == 0) ? -1.f : mp.trackProj_uR_ + 0.3f;
+          std::memcpy(kf.descriptors_.data + i * 32, mp.descriptor_.data, 32);
+          kf.descriptors_.data[i * 32 + (i % 32)] ^= 1;
+          const float d3 = (float)((s.cur.Tcw_ * mp.pos_)).norm();
+          mp.maxDistance_ = d3 * std::pow(1.2f, (float)mp.trackScaleLevel_ - 0.5f);
+          mp.minDistance_ = mp.maxDistance_ / 3.5831808f;
+          if (i % 5 == 1) {                                  // the feature already holds another (spare) point
+            MapPoint& org = s.points[900 + (i % 200)];
+            if (!org.beObserved(&kf)) { org.bad_ = i % 35 == 1; org.observe_cnt_ = i % 3; org.addObservation(&kf, i); kf.mappoints_[i] = &org; }
+          }
+          if (i % 19 == 2) mp.addObservation(&kf, (i + 500) % 1000);   // already observed by the key frame elsewhere
+        }
+        kf.assignFeaturesToGrid();
+      }
+      std::vector<MapPoint*> la = a.local, lb = b.local, ra(la.size(), nullptr), rb(lb.size(), nullptr);
+      for (size_t i = 0; i < la.size(); i += 23) { la[i] = nullptr; lb[i] = nullptr; }
+      for (size_t i = 5; i < la.size(); i += 40) { la[i] = la[i - 1]; lb[i] = lb[i - 1]; }   // duplicates in the list
+      if (pass == 0) {
+        na = ref.fuseMapPoints(&ka, la, 3.0f);
+        nb = gpu.fuseMapPoints(&kb, lb, 3.0f);
+      } else {
+        Sim3 Sa(a.cur.Tcw_, 1.0), Sb(b.cur.Tcw_, 1.0);
+        na = ref.fuseByPose(&ka, Sa, la, ra, 4.0f);
+        nb = gpu.fuseByPose(&kb, Sb, lb, rb, 4.0f);
+      }
+      same = na == nb;
+      for (size_t i = 0; i < ka.mappoints_.size() && same; ++i)
+        same = (ka.mappoints_[i] ? (long)(ka.mappoints_[i] - &a.points[0]) : -1) == (kb.mappoints_[i] ? (long)(kb.mappoints_[i] - &b.points[0]) : -1);
+      for (size_t i = 0; i < ra.size() && same; ++i)
+        same = (ra[i] ? (long)(ra[i] - &a.points[0]) : -1) == (rb[i] ? (long)(rb[i] - &b.points[0]) : -1);
+      int nbad = 0;
+      for (size_t i = 0; i < a.points.size() && same; ++i) {
+        same = a.points[i].bad_ == b.points[i].bad_ && a.points[i].observe_cnt_ == b.points[i].observe_cnt_ &&
+               a.points[i].indexInKF_.size() == b.points[i].indexInKF_.size();
+        nbad += a.points[i].bad_;
+      }
+      std::printf("  %s: %d fused (%d bad points afterwards)\n", pass ? "fuseByPose" : "fuseMapPoints", na, nbad);
+      expect(same && na > 50, pass ? "fuseByPose(KeyFrame*, Sim3&, loopPts, replacePts, th)" : "fuseMapPoints(KeyFrame*, mappoints, threshold)");
+      for (size_t i = 0; i < a.points.size(); ++i) { a.points[i].indexInKF_.clear(); b.points[i].indexInKF_.clear(); }
+    }
 
     // 5. computeDistance
     const int d0 = RefMatcher::computeDistance(a.cur.descriptors_.row(3), a.kf1.descriptors_.row(3));

@@ -26,6 +26,7 @@ struct Vector3d {
 };
 struct Matrix3d {                                     // the slice of Eigen::Matrix3d the Sim3 searches use
   double m[9];
+  double operator()(int r, int c) const { return m[r * 3 + c]; }
   Matrix3d operator/(double s) const { Matrix3d r; for (int i = 0; i < 9; ++i) r.m[i] = m[i] / s; return r; }
   Matrix3d operator-() const { Matrix3d r; for (int i = 0; i < 9; ++i) r.m[i] = -m[i]; return r; }
   Matrix3d transpose() const { Matrix3d r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i * 3 + j] = m[j * 3 + i]; return r; }
@@ -43,6 +44,8 @@ struct Vector2d {
 struct SE3 {
   double R[9], t[3];
   SE3() { for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0); t[0] = t[1] = t[2] = 0; }
+  SE3(const Matrix3d& Rm, const Vector3d& tv) { for (int i = 0; i < 9; ++i) R[i] = Rm.m[i]; for (int i = 0; i < 3; ++i) t[i] = tv[i]; }
+  Matrix3d rotation_matrix() const { Matrix3d r; for (int i = 0; i < 9; ++i) r.m[i] = R[i]; return r; }
   static SE3 rotY(double a, double tx, double ty, double tz) {
     SE3 s; s.R[0] = std::cos(a); s.R[2] = std::sin(a); s.R[6] = -std::sin(a); s.R[8] = std::cos(a);
     s.t[0] = tx; s.t[1] = ty; s.t[2] = tz; return s;
@@ -99,6 +102,9 @@ struct MapPoint {
   Vector3d getNormalVector() { return normalVector_; }
   std::map<struct KeyFrame*, int> indexInKF_;
   int getIndexInKeyFrame(struct KeyFrame* kf) { return indexInKF_.count(kf) ? indexInKF_[kf] : -1; }
+  bool beObserved(struct KeyFrame* kf) { return indexInKF_.count(kf) != 0; }
+  void addObservation(struct KeyFrame* kf, int idx) { if (!indexInKF_.count(kf)) { indexInKF_[kf] = idx; ++observe_cnt_; } }
+  inline void replaceMapPoint(MapPoint* mp);            // stand-in for mappoint.cpp:214-262: hand the observations over, go bad
   inline int predictScale(const float& currDist, struct KeyFrame* kf);  // mappoint.cpp:198-212
   float getMinDistanceThreshold() { return 0.8f * minDistance_; }      // mappoint.cpp:391-401
   float getMaxDistanceThreshold() { return 1.2f * maxDistance_; }
@@ -172,6 +178,8 @@ struct KeyFrame {
   Camera* camera_ = nullptr;
   SE3 Tcw_;
   SE3 getPose() { return Tcw_; }
+  Vector3d getCamCenter() { return Tcw_.inverse().translation(); }
+  void addMapPoint(MapPoint* mp, int idx) { mappoints_[idx] = mp; }
   std::vector<float> uRight_;
   float xMin_ = 0, xMax_ = 0, yMin_ = 0, yMax_ = 0, gridPerPixelWidth_ = 0, gridPerPixelHeight_ = 0;
   std::vector<std::vector<std::vector<int> > > gridKeypoints_;
@@ -217,6 +225,17 @@ inline int MapPoint::predictScale(const float& currDist, KeyFrame* kf) {
   if (scale < 0) scale = 0;
   else if (scale >= (int)kf->scaleFactors_.size()) scale = (int)kf->scaleFactors_.size() - 1;
   return scale;
+}
+
+inline void MapPoint::replaceMapPoint(MapPoint* mp) {
+  if (mp == this) return;
+  std::map<KeyFrame*, int> obs = indexInKF_;
+  indexInKF_.clear();
+  bad_ = true;
+  for (std::map<KeyFrame*, int>::iterator it = obs.begin(); it != obs.end(); ++it) {
+    if (!mp->beObserved(it->first)) { it->first->mappoints_[it->second] = mp; mp->addObservation(it->first, it->second); }
+    else it->first->mappoints_[it->second] = nullptr;
+  }
 }
 
 // ---- CPU statement of the reference's loops over the objects above (checker only) ------------------------------------
@@ -387,6 +406,160 @@ struct RefMatcher {
       }
       if (best <= 50) { matchPts[bestIdx] = mp; ++cnt; }
     }
+    return cnt;
+  }
+
+  // windowed argmin shared by the two fuse functions (matcher.cpp:1064-1100 with chi2, :1197-1214 without)
+  static int fuseArgmin(KeyFrame* kf, MapPoint* mp, float u, float v, float ur, float radius, int lp, bool chi2) {
+    const std::vector<int> ids = kf->getFeaturesInArea(u, v, radius);
+    int best = 256, bestIdx = -1;
+    const cv::Mat dm = mp->getDescriptor();
+    for (size_t k = 0; k < ids.size(); ++k) {
+      const int idx = ids[k];
+      const cv::KeyPoint kp = kf->unKeypoints_[idx];
+      if (kp.octave < lp - 1 || kp.octave > lp) continue;
+      if (chi2) {
+        const float ex = u - kp.pt.x, ey = v - kp.pt.y;
+        const float invSigma = 1.0f / kf->scaleFactors_[kp.octave];
+        if (kf->uRight_[idx] >= 0) {
+          const float er = ur - kf->uRight_[idx];
+          const float e2 = ex * ex + ey * ey + er * er;
+          if (e2 * invSigma * invSigma > 7.815f) continue;
+        } else {
+          const float e2 = ex * ex + ey * ey;
+          if (e2 * invSigma * invSigma > 5.991f) continue;
+        }
+      }
+      const int d = computeDistance(dm, kf->descriptors_.row(idx));
+      if (d < best) { best = d; bestIdx = idx; }
+    }
+    return best <= 50 ? bestIdx : -1;
+  }
+  int fuseMapPoints(KeyFrame* kf, std::vector<MapPoint*>& mps, const float& threshold) {   // matcher.cpp:1012-1133
+    int cnt = 0;
+    Camera* cam = kf->camera_;
+    SE3 Tcw = kf->getPose();
+    Vector3d Ow = kf->getCamCenter();
+    for (size_t i = 0; i < mps.size(); ++i) {
+      MapPoint* mp = mps[i];
+      if (!mp || mp->isBad() || mp->beObserved(kf)) continue;
+      Vector3d pw = mp->getPose();
+      Vector3d pc = Tcw * pw;
+      const float z = (float)pc[2];
+      if (z < 0.0f) continue;
+      const float invz = 1.0f / z;
+      const float x = (float)pc[0] * invz, y = (float)pc[1] * invz;
+      const float u = cam->fx_ * x + cam->cx_, v = cam->fy_ * y + cam->cy_;
+      if (!kf->isInImg(u, v)) continue;
+      const float ur = u - cam->bf_ * invz;
+      Vector3d line = pw - Ow;
+      const float dist = line.norm();
+      if (dist < mp->getMinDistanceThreshold() || dist > mp->getMaxDistanceThreshold()) continue;
+      if (line.dot(mp->getNormalVector()) < 0.5 * dist) continue;
+      const int lp = mp->predictScale(dist, kf);
+      const int bestIdx = fuseArgmin(kf, mp, u, v, ur, threshold * kf->scaleFactors_[lp], lp, true);
+      if (bestIdx < 0) continue;
+      MapPoint* org = kf->mappoints_[bestIdx];
+      if (org) {
+        if (!org->isBad()) { if (org->getObsCnt() > mp->getObsCnt()) mp->replaceMapPoint(org); else org->replaceMapPoint(mp); }
+      } else { mp->addObservation(kf, bestIdx); kf->addMapPoint(mp, bestIdx); }
+      ++cnt;
+    }
+    return cnt;
+  }
+  int fuseByPose(KeyFrame* kf, Sim3& Scw, std::vector<MapPoint*>& loopPts, std::vector<MapPoint*>& replacePts, const float th) {
+    Camera* cam = kf->camera_;                                                              // matcher.cpp:1135-1238
+    SE3 Tcw(Scw.rotation_matrix(), Scw.translation());
+    Vector3d Ow = -Tcw.rotation_matrix().transpose() * Tcw.translation();
+    std::set<MapPoint*> already;
+    for (size_t i = 0; i < kf->mappoints_.size(); ++i)
+      if (kf->mappoints_[i] && !kf->mappoints_[i]->isBad()) already.insert(kf->mappoints_[i]);
+    int fused = 0;
+    for (size_t i = 0; i < loopPts.size(); ++i) {
+      MapPoint* mp = loopPts[i];
+      if (!mp || mp->isBad() || already.count(mp)) continue;
+      Vector3d pc = Tcw * mp->getPose();
+      const float z = (float)pc[2];
+      if (z < 0) continue;
+      const float invz = 1.0f / z;
+      const float x = (float)pc[0] * invz, y = (float)pc[1] * invz;
+      const float u = cam->fx_ * x + cam->cx_, v = cam->fy_ * y + cam->cy_;
+      if (!kf->isInImg(u, v)) continue;
+      Vector3d pl = mp->getPose() - Ow;
+      const float dist = pl.norm();
+      if (dist < mp->getMinDistanceThreshold() || dist > mp->getMaxDistanceThreshold()) continue;
+      if (pl.dot(mp->getNormalVector()) < 0.5 * dist) continue;
+      const int lp = mp->predictScale(dist, kf);
+      const int bestIdx = fuseArgmin(kf, mp, u, v, 0.f, th * kf->scaleFactors_[lp], lp, false);
+      if (bestIdx < 0) continue;
+      MapPoint* mk = kf->mappoints_[bestIdx];
+      if (mk) { if (!mk->isBad()) replacePts[i] = mk; }
+      else { mp->addObservation(kf, bestIdx); kf->addMapPoint(mp, bestIdx); }
+      ++fused;
+    }
+    return fused;
+  }
+
+  static bool epipolarOk(const cv::KeyPoint& k1, const cv::KeyPoint& k2, const Matrix3d& F, KeyFrame* kf2) {   // matcher.cpp:1306-1324
+    const double p1[3] = {k1.pt.x, k1.pt.y, 1}, p2[3] = {k2.pt.x, k2.pt.y, 1};
+    double l2[3];
+    for (int j = 0; j < 3; ++j) l2[j] = p1[0] * F(0, j) + p1[1] * F(1, j) + p1[2] * F(2, j);
+    const float num = l2[0] * p2[0] + l2[1] * p2[1] + l2[2] * p2[2];
+    const float den = l2[0] * l2[0] + l2[1] * l2[1];
+    if (den == 0) return false;
+    const float sigma = kf2->scaleFactors_[k2.octave];
+    return num * num / den < 3.84f * sigma * sigma;
+  }
+  int searchForTriangulation(KeyFrame* kf1, KeyFrame* kf2, std::vector<std::pair<int, int> >& out, Matrix3d& F12, bool checkRot) {
+    int cnt = 0;                                                                             // matcher.cpp:867-1010
+    std::vector<int> m12(kf1->N_, -1);
+    std::vector<bool> matched2(kf2->N_, false);
+    std::vector<int> hist[30];
+    const std::vector<MapPoint*> mps1 = kf1->getMapPoints(), mps2 = kf2->getMapPoints();
+    const Vector3d C2 = kf2->getPose() * kf1->getCamCenter();
+    const Vector2d e = kf2->camera_->camera2pixel(C2);
+    const float ex = e[0], ey = e[1];
+    FeatureVector::const_iterator a = kf1->featVec_.begin(), ae = kf1->featVec_.end(), b = kf2->featVec_.begin(), be = kf2->featVec_.end();
+    while (a != ae && b != be) {
+      if (a->first == b->first) {
+        for (size_t ik = 0; ik < a->second.size(); ++ik) {
+          const unsigned i1 = a->second[ik];
+          if (mps1[i1]) continue;
+          const bool stereo1 = kf1->uRight_[i1] >= 0;
+          int best = 50, bestIdx2 = -1;
+          for (size_t ir = 0; ir < b->second.size(); ++ir) {
+            const unsigned i2 = b->second[ir];
+            if (matched2[i2] || mps2[i2]) continue;
+            const bool stereo2 = kf2->uRight_[i2] >= 0;
+            const int d = computeDistance(kf1->descriptors_.row(i1), kf2->descriptors_.row(i2));
+            if (d > 50 || d > best) continue;
+            const cv::KeyPoint k2 = kf2->unKeypoints_[i2];
+            if (!stereo1 && !stereo2) {
+              const float dx = ex - k2.pt.x, dy = ey - k2.pt.y;
+              if (dx * dx + dy * dy < 100 * kf2->scaleFactors_[k2.octave]) continue;
+            }
+            if (epipolarOk(kf1->unKeypoints_[i1], k2, F12, kf2)) { best = d; bestIdx2 = (int)i2; }
+          }
+          if (bestIdx2 >= 0) {
+            m12[i1] = bestIdx2;
+            matched2[bestIdx2] = true;
+            if (checkRot) hist[histBin(kf1->unKeypoints_[i1].angle - kf2->unKeypoints_[bestIdx2].angle, false)].push_back((int)i1);
+            ++cnt;
+          }
+        }
+        ++a; ++b;
+      } else if (a->first < b->first) a = kf1->featVec_.lower_bound(b->first);
+      else b = kf2->featVec_.lower_bound(a->first);
+    }
+    if (checkRot) {
+      int i1 = -1, i2 = -1, i3 = -1;
+      threeMax(hist, 30, i1, i2, i3);
+      for (int i = 0; i < 30; ++i)
+        if (i != i1 && i != i2 && i != i3)
+          for (size_t j = 0; j < hist[i].size(); ++j) { m12[hist[i][j]] = -1; --cnt; }
+    }
+    out.clear();
+    for (int i = 0; i < (int)m12.size(); ++i) if (m12[i] >= 0) out.push_back(std::make_pair(i, m12[i]));
     return cnt;
   }
 
