@@ -599,6 +599,8 @@ int searchByBoWKeyFrames(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector
 }
 
 // Matcher::computeDistance(const Mat&, const Mat&)                                               matcher.cpp:1240-1256
+// For parity and completeness: a single 32-byte pair costs a host<->device round trip here, so scalar call sites
+// (mappoint.cpp:154) should keep the reference's inline version or be batched (orbx_medoid_descriptors, hamm_knn2).
 template <class MatT>
 int computeDistance(const MatT& desp1, const MatT& desp2, int device = 0) {
   int32_t idx, d1, d2; uint8_t ok;
