@@ -119,3 +119,42 @@ def test_properties_at_baseline_scale(vo):
     first = np.array([np.flatnonzero((d0[5, :c0[5]] == row).all(1))[0] for row in d0[5, :c0[5]]])
     assert np.array_equal(idx, first)
     ex.close()
+
+
+def test_two_lane_resident_batch_equals_oracle(vo):
+    """orbx_extract_batch_device splits a batch of >= 2 chunks over two lanes (this handle on the caller's stream, a sibling
+    handle with its own workspace on a second stream, joined by an event).  Both lane counts must give the oracle's bits,
+    for an odd number of chunks and a ragged last chunk, and later work on the caller's stream must see every frame."""
+    import os
+    torch = pytest.importorskip("torch")
+    B, H, W = 19, 240, 320
+    imgs = np.stack([synth.make_frame(100 + f, H, W) for f in range(B)])
+    P = oracle.Port(300)
+    ref = [P.extract(imgs[f]) for f in range(B)]
+    d_imgs = torch.from_numpy(imgs).cuda()
+    try:
+        os.environ["ORBX_CHUNK"] = "4"       # 5 chunks: 3 on the first lane, 2 (the last one ragged) on the second
+        for lanes in ("2", "1", "2"):
+            os.environ["ORBX_LANES"] = lanes
+            ex = vo.ORBextractor(300, 1.2, 8, 20, 7)
+            cap = ex.max_keypoints
+            for rep in range(2):             # second pass reuses both workspaces and the level-0 tensor maps
+                d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda")
+                d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+                d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+                st = torch.cuda.current_stream()
+                ex.extract_batch_device(d_imgs.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                        d_cnt.data_ptr(), st.cuda_stream)
+                total = d_cnt.sum()          # ordered after the join on the caller's stream, no explicit synchronisation
+                cnt = d_cnt.cpu().numpy()
+                assert int(total.item()) == sum(len(r[0]) for r in ref)
+                kps = d_kps.cpu().numpy().view(vo.KP_DTYPE).reshape(B, cap)
+                desc = d_desc.cpu().numpy()
+                for f in range(B):
+                    assert cnt[f] == len(ref[f][0]), (lanes, f)
+                    assert np.array_equal(kps[f, :cnt[f]], ref[f][0]) and np.array_equal(desc[f, :cnt[f]], ref[f][1]), (lanes, f)
+            assert ex.launch_count() == 2 * 5 * 11          # 7 resize + FAST + quadtree + blur + orient/desc per chunk, both lanes counted
+            ex.close()
+    finally:
+        os.environ.pop("ORBX_CHUNK", None)
+        os.environ.pop("ORBX_LANES", None)

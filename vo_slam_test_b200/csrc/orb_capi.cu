@@ -87,6 +87,11 @@ struct orbx_extractor {
   size_t m_frames = 0; int m_cap = 0;
   long long launches = 0;
   const uint8_t* map0_base = nullptr; size_t map0_row = 0, map0_frame = 0; int map0_n = 0, map0_want = 0;
+  // second lane of the device-resident batch path: a sibling extractor (own workspace, own stream) that takes the second
+  // half of a large batch concurrently, so that kernel tails and the latency-bound stages of one lane fill under the
+  // throughput-bound stages of the other (measured: +2.4 % on 4096 VGA frames, tools/lanes_probe.py)
+  orbx_extractor* lane2 = nullptr;
+  cudaEvent_t laneFork = nullptr, laneJoin = nullptr;
   // last chunk info for the debug taps
   const uint8_t* last_img0 = nullptr; size_t last_rowStride = 0, last_frameStride = 0; int last_frames = 0;
 };
@@ -535,6 +540,9 @@ int orbx_destroy(orbx_handle h) {
   if (!h) return ORBX_OK;
   cudaSetDevice(h->p.device);
   cudaDeviceSynchronize();
+  if (h->lane2) orbx_destroy(h->lane2);
+  if (h->laneFork) cudaEventDestroy(h->laneFork);
+  if (h->laneJoin) cudaEventDestroy(h->laneJoin);
   free_workspace(h);
   cudaFree(h->d_maps);
   cudaFree(h->d_pattern); cudaFree(h->d_umax); cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc);
@@ -575,7 +583,7 @@ int orbx_max_keypoints(orbx_handle h, int* cap) {
 }
 int orbx_launch_count(orbx_handle h, long long* n) {
   if (check_handle(h) || !n) return ORBX_ERR_ARG;
-  *n = h->launches;
+  *n = h->launches + (h->lane2 ? h->lane2->launches : 0);
   return ORBX_OK;
 }
 
@@ -594,6 +602,41 @@ int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes,
   int rc = configure(h, w, height, chunk);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const int want_lanes = env_int("ORBX_LANES", 2);
+  const int nchunks = (nframes + chunk - 1) / chunk;
+  if (want_lanes >= 2 && nchunks >= 2) {
+    // two lanes: chunks [0, ca) on the caller's stream with this handle's workspace, chunks [ca, nchunks) on the sibling's
+    if (!h->lane2) {
+      orbx_handle sib = nullptr;
+      rc = orbx_create(&h->p, &sib);
+      if (rc) return rc;
+      h->lane2 = sib;
+      ORBX_CUDA(cudaEventCreateWithFlags(&h->laneFork, cudaEventDisableTiming));
+      ORBX_CUDA(cudaEventCreateWithFlags(&h->laneJoin, cudaEventDisableTiming));
+    }
+    orbx_extractor* g = h->lane2;
+    rc = configure(g, w, height, chunk);
+    if (rc) return rc;
+    const int ca = (nchunks + 1) / 2, half = ca * chunk;
+    const uint8_t* imgs2 = d_imgs + (size_t)half * frame_stride;
+    h->map0_want = half;
+    g->map0_want = nframes - half;
+    ORBX_CUDA(cudaEventRecord(h->laneFork, st));
+    ORBX_CUDA(cudaStreamWaitEvent(g->stream, h->laneFork, 0));
+    for (int c = 0; c < ca; ++c) {              // submissions alternate so that both streams have work from the start
+      rc = run_chunk(h, d_imgs, row_stride, frame_stride, c * chunk, std::min(chunk, half - c * chunk), d_kps, d_desc, cap, d_counts, st);
+      if (rc) return rc;
+      const int f2 = c * chunk;
+      if (half + f2 < nframes) {
+        rc = run_chunk(g, imgs2, row_stride, frame_stride, f2, std::min(chunk, nframes - half - f2), d_kps + (size_t)half * cap,
+                       d_desc + (size_t)half * cap * 32, cap, d_counts + half, g->stream);
+        if (rc) return rc;
+      }
+    }
+    ORBX_CUDA(cudaEventRecord(h->laneJoin, g->stream));
+    ORBX_CUDA(cudaStreamWaitEvent(st, h->laneJoin, 0));
+    return ORBX_OK;
+  }
   h->map0_want = nframes;
   for (int f0 = 0; f0 < nframes; f0 += chunk) {
     const int n = std::min(chunk, nframes - f0);
