@@ -424,7 +424,7 @@ def run_b200(args, rank, world, local_rank):
                                        "levels, 1.2, FAST 20/7) + frame-to-frame Hamming kNN (k=2, TH_LOW 50, ratio 0.7); frames sharded, "
                                        "no collective" % F,
                            "frames_per_gpu": F, "l2": "inputs (%.2f GB per GPU) larger than L2" % (F * W_IMG * H_IMG / 1e9),
-                           "chunk_frames": int(os.environ.get("ORBX_CHUNK", "512")), "chunk_frames_host_pipeline": int(os.environ.get("ORBX_CHUNK_HOST", os.environ.get("ORBX_CHUNK", "256"))), "mean_keypoints": float(counts.mean()), "accepted_matches_per_pair": accepted / max(npairs, 1)},
+                           "chunk_frames": int(os.environ.get("ORBX_CHUNK", "512")), "resident_lanes": int(os.environ.get("ORBX_LANES", "2")), "chunk_frames_host_pipeline": int(os.environ.get("ORBX_CHUNK_HOST", os.environ.get("ORBX_CHUNK", "256"))), "mean_keypoints": float(counts.mean()), "accepted_matches_per_pair": accepted / max(npairs, 1)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "orbx_extract_match_batch (host C ABI, pinned host buffers, copies inside the timed region)"},
