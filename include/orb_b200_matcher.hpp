@@ -126,7 +126,8 @@ int searchByProjection(FrameT* frame_curr, FrameT* frame_last, const float radiu
   const bool backward = -static_cast<float>(tlc[2]) > b;
 
   const int M = (int)frame_last->mappoints_.size();
-  const int M1 = M > 0 ? M : 1;
+  if (M == 0 || frame_curr->unKeypoints_.empty()) return 0;           // nothing to project / nothing to match: the loops are no-ops
+  const int M1 = M;
   std::vector<uint8_t> valid(M1, 0), has_obs(M1, 0), desc((size_t)M1 * 32, 0);
   std::vector<float> u(M1, 0.f), v(M1, 0.f), invz(M1, 0.f), angle(M1, 0.f);
   std::vector<int32_t> octave(M1, 0);
@@ -170,7 +171,8 @@ template <class FrameT, class MapPointT>
 int searchByProjection(FrameT* frame, const std::vector<MapPointT*>& mappoints, const float thRadius, float ratio,
                        int device = 0) {
   const int M = (int)mappoints.size();
-  const int M1 = M > 0 ? M : 1;
+  if (M == 0 || frame->unKeypoints_.empty()) return 0;
+  const int M1 = M;
   std::vector<uint8_t> valid(M1, 0), has_obs(M1, 0), desc((size_t)M1 * 32, 0);
   std::vector<float> u(M1, 0.f), v(M1, 0.f), ur(M1, 0.f), view_cos(M1, 0.f);
   std::vector<int32_t> level(M1, 0);
@@ -210,7 +212,8 @@ int searchByProjection(FrameT* frame_curr, KeyFrameT* keyframe, const float radi
   auto Ow = Tcw.inverse().translation();
   const auto mappoints = keyframe->getMapPoints();
   const int M = (int)mappoints.size();
-  const int M1 = M > 0 ? M : 1;
+  if (M == 0 || frame_curr->unKeypoints_.empty()) return 0;
+  const int M1 = M;
   std::vector<uint8_t> valid(M1, 0), zeros8(M1, 0), desc((size_t)M1 * 32, 0);
   std::vector<float> u(M1, 0.f), v(M1, 0.f), zerosf(M1, 0.f), angle(M1, 0.f);
   std::vector<int32_t> octave(M1, 0);
@@ -267,7 +270,8 @@ int searchByProjection(KeyFrameT* keyframe, Sim3T& Scw, std::vector<MapPointT*>&
   auto tcw = Scw.translation() / scale;
   auto Ow = -Rcw.transpose() * tcw;
   const int M = (int)loopMapPoints.size();
-  const int M1 = M > 0 ? M : 1;
+  if (M == 0 || keyframe->unKeypoints_.empty()) return 0;
+  const int M1 = M;
   std::vector<uint8_t> valid(M1, 0), zeros8(M1, 0), desc((size_t)M1 * 32, 0);
   std::vector<float> u(M1, 0.f), v(M1, 0.f), zerosf(M1, 0.f);
   std::vector<int32_t> octave(M1, 0);
@@ -355,6 +359,7 @@ int searchBySim3(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector<MapPoin
   std::vector<MapPointT*> mappoints1 = keyframe1->getMapPoints();
   std::vector<MapPointT*> mappoints2 = keyframe2->getMapPoints();
   const int N1 = (int)mappoints1.size(), N2 = (int)mappoints2.size();
+  if (N1 == 0 || N2 == 0) return 0;
   std::vector<bool> matched1(N1, false), matched2(N2, false);
   auto Tcw1 = keyframe1->getPose();
   auto Tcw2 = keyframe2->getPose();
@@ -400,7 +405,8 @@ int fuseMapPoints(KeyFrameT* keyframe, std::vector<MapPointT*>& mappoints, const
   auto Tcw = keyframe->getPose();
   auto Ow = keyframe->getCamCenter();
   const int M = (int)mappoints.size();
-  const int M1 = M > 0 ? M : 1;
+  if (M == 0 || keyframe->unKeypoints_.empty()) return 0;
+  const int M1 = M;
   std::vector<uint8_t> valid(M1, 0), zeros8(M1, 0), desc((size_t)M1 * 32, 0);
   std::vector<float> u(M1, 0.f), v(M1, 0.f), ur(M1, 0.f), zerosf(M1, 0.f);
   std::vector<int32_t> octave(M1, 0);
@@ -467,7 +473,8 @@ int fuseByPose(KeyFrameT* keyframe, Sim3T& Scw, std::vector<MapPointT*>& loopMap
   SE3T Tcw(Scw.rotation_matrix(), Scw.translation());
   auto Ow = -Tcw.rotation_matrix().transpose() * Tcw.translation();
   const int M = (int)loopMapPoints.size();
-  const int M1 = M > 0 ? M : 1;
+  if (M == 0 || keyframe->unKeypoints_.empty()) return 0;
+  const int M1 = M;
   std::vector<uint8_t> valid(M1, 0), zeros8(M1, 0), desc((size_t)M1 * 32, 0);
   std::vector<float> u(M1, 0.f), v(M1, 0.f), zerosf(M1, 0.f);
   std::vector<int32_t> octave(M1, 0);
@@ -528,6 +535,8 @@ template <class KeyFrameT, class Matrix3T>
 int searchForTriangulation(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector<std::pair<int, int> >& matchIdxs,
                            Matrix3T& F12, bool checkRot = true, int device = 0) {
   const int TH_LOW = 50;
+  matchIdxs.clear();
+  if (keyframe1->unKeypoints_.empty() || keyframe2->unKeypoints_.empty() || keyframe1->featVec_.empty() || keyframe2->featVec_.empty()) return 0;
   const auto mappoints1 = keyframe1->getMapPoints();
   const auto mappoints2 = keyframe2->getMapPoints();
   const auto Cw = keyframe1->getCamCenter();
@@ -561,6 +570,7 @@ int searchByBoW(KeyFrameT* keyframe, FrameT* frame, std::vector<MapPointT*>& map
                 int device = 0) {
   const int TH_LOW = 50;                                                                       // matcher.cpp:12
   mappointMatches = std::vector<MapPointT*>(frame->N_, static_cast<MapPointT*>(nullptr));
+  if (frame->unKeypoints_.empty() || keyframe->unKeypoints_.empty() || frame->featVec_.empty() || keyframe->featVec_.empty()) return 0;
   const std::vector<MapPointT*> mappoints = keyframe->getMapPoints();
   typedef typename std::remove_reference<decltype(keyframe->featVec_)>::type FVa;
   typedef typename std::remove_reference<decltype(frame->featVec_)>::type FVb;
@@ -583,6 +593,7 @@ int searchByBoWKeyFrames(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector
                          float ratio, int device = 0) {
   const int TH_LOW = 50;
   mappointMatches = std::vector<MapPointT*>(keyframe1->N_, static_cast<MapPointT*>(nullptr));
+  if (keyframe1->unKeypoints_.empty() || keyframe2->unKeypoints_.empty() || keyframe1->featVec_.empty() || keyframe2->featVec_.empty()) return 0;
   const std::vector<MapPointT*> mappoints1 = keyframe1->getMapPoints();
   const std::vector<MapPointT*> mappoints2 = keyframe2->getMapPoints();
   typedef typename std::remove_reference<decltype(keyframe1->featVec_)>::type FV;

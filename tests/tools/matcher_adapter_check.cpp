@@ -366,6 +366,38 @@ int main() {
     const int d1 = Matcher::computeDistance(b.cur.descriptors_.row(3), b.kf1.descriptors_.row(3));
     expect(d0 == d1, "computeDistance(Mat, Mat)");
   }
+  // Empty inputs: the reference's loops are no-ops; the adapter must return 0 without touching the device or the objects.
+  {
+    Scene a;
+    buildScene(a, 5u, false);
+    typedef myslam_b200::MatcherT<Frame, KeyFrame, MapPoint> M;
+    M gpu(0.7f);
+    RefMatcher ref(0.7f);
+    Frame none; none.camera_ = &a.cam; none.scaleFactors_ = a.cur.scaleFactors_; none.xMax_ = 640; none.yMax_ = 480;
+    none.gridPerPixelWidth_ = 0.1f; none.gridPerPixelHeight_ = 0.1f;
+    KeyFrame knone; knone.camera_ = &a.cam; knone.scaleFactors_ = a.cur.scaleFactors_; knone.assignFeaturesToGrid();
+    std::vector<MapPoint*> empty, out1, out2;
+    std::set<MapPoint*> found;
+    Sim3 S(a.cur.Tcw_, 1.0);
+    Matrix3d F; for (int i = 0; i < 9; ++i) F.m[i] = 0;
+    std::vector<std::pair<int, int> > idxs(3, std::make_pair(1, 2));
+    Frame c1 = a.cur, c2 = a.cur;
+    bool ok = gpu.searchByProjection(&c1, &none, 15.f, true) == 0 && ref.searchByProjection(&c2, &none, 15.f, true) == 0;   // no map points
+    ok = ok && gpu.searchByProjection(&none, &a.last, 15.f, true) == 0;                                                       // no features
+    ok = ok && gpu.searchByProjection(&c1, empty, 1.f) == 0 && gpu.searchByProjection(&none, a.local, 1.f) == 0;
+    ok = ok && gpu.searchByProjection(&c1, &knone, 10.f, 100.f, found, true) == 0 && gpu.searchByProjection(&none, &a.kf1, 10.f, 100.f, found, true) == 0;
+    ok = ok && gpu.searchByProjection(&knone, S, a.local, empty, 10) == 0 && gpu.searchByProjection(&a.kf1, S, empty, out1, 10) == 0;
+    ok = ok && gpu.searchByBoW(&knone, &c1, out1, true) == 0 && out1.size() == c1.N_;
+    ok = ok && gpu.searchByBoW(&a.kf1, &none, out1, true) == 0 && out1.empty();
+    ok = ok && gpu.searchByBoW(&a.kf1, &knone, out2, true) == 0 && out2.size() == a.kf1.N_;
+    ok = ok && gpu.searchBySim3(&knone, &a.kf1, empty, S, 7.5f) == 0;
+    ok = ok && gpu.searchForTriangulation(&knone, &a.kf1, idxs, F, true) == 0 && idxs.empty();
+    ok = ok && gpu.fuseMapPoints(&a.kf1, empty, 3.f) == 0 && gpu.fuseMapPoints(&knone, a.local, 3.f) == 0;
+    ok = ok && gpu.fuseByPose(&a.kf1, S, empty, out1, 4.f) == 0 && gpu.fuseByPose(&knone, S, a.local, out2, 4.f) == 0;
+    for (size_t i = 0; i < c1.mappoints_.size() && ok; ++i) ok = c1.mappoints_[i] == a.cur.mappoints_[i];
+    std::printf("empty inputs\n");
+    expect(ok, "every entry point with empty point lists / featureless frames");
+  }
   std::printf(fails ? "matcher adapter: %d comparisons DIFFER\n" : "matcher adapter: all comparisons identical\n", fails);
   return fails ? 1 : 0;
 }
