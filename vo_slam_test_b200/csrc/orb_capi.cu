@@ -611,9 +611,9 @@ int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes,
       rc = orbx_create(&h->p, &sib);
       if (rc) return rc;
       h->lane2 = sib;
-      ORBX_CUDA(cudaEventCreateWithFlags(&h->laneFork, cudaEventDisableTiming));
-      ORBX_CUDA(cudaEventCreateWithFlags(&h->laneJoin, cudaEventDisableTiming));
     }
+    if (!h->laneFork) ORBX_CUDA(cudaEventCreateWithFlags(&h->laneFork, cudaEventDisableTiming));
+    if (!h->laneJoin) ORBX_CUDA(cudaEventCreateWithFlags(&h->laneJoin, cudaEventDisableTiming));
     orbx_extractor* g = h->lane2;
     rc = configure(g, w, height, chunk);
     if (rc) return rc;
