@@ -30,7 +30,10 @@ struct port_bow_side {
   int ngroups; const uint32_t* node_ids; const int32_t* group_start; const int32_t* feat_idx;
 };
 struct port_tri_side { port_bow_side side; const void* kps; const float* uright; };
+struct port_camera { float fx, fy, cx, cy; float dist[8]; int ndist; float bf; float xmin, xmax, ymin, ymax; };
 extern "C" {
+int port_frame_finish(const port_camera* cam, const void* kps_in, int n, const float* depth, int W, int H, size_t depth_step,
+                      void* unkps_out, float* uright, float* depth_out, int* cell_start, int* ids);
 int port_search_for_triangulation(const port_tri_side* a, const port_tri_side* b, const double* F12, float ex, float ey,
                                   const float* scale2, int th_low, int check_rot, int32_t* match);
 int port_sbp_frame(const port_sbp_frame_in* in, int32_t* assign);
@@ -96,6 +99,17 @@ int orbx_search_for_triangulation(const orbx_tri_side* a, const orbx_tri_side* b
   static_assert(sizeof(port_tri_side) == sizeof(orbx_tri_side), "same layout");
   *match_cnt = port_search_for_triangulation((const port_tri_side*)a, (const port_tri_side*)b, F12, ex, ey, scale_factors2, th_low,
                                              check_rot, match);
+  return ORBX_OK;
+}
+int orbx_frame_finish(const orbx_camera* cam, const orbx_keypoint* kps, const int32_t* counts, int nframes, int cap, const float* depth,
+                      int w, int height, size_t depth_row_stride, size_t depth_frame_stride, orbx_keypoint* unkps, float* uright,
+                      float* depth_out, int32_t* cell_start, int32_t* ids, int) {
+  static_assert(sizeof(port_camera) == sizeof(orbx_camera), "same layout");
+  for (int f = 0; f < nframes; ++f)
+    port_frame_finish((const port_camera*)cam, kps + (size_t)f * cap, counts[f],
+                      depth ? (const float*)((const char*)depth + f * depth_frame_stride) : nullptr, w, height, depth_row_stride,
+                      unkps + (size_t)f * cap, uright + (size_t)f * cap, depth_out + (size_t)f * cap,
+                      cell_start + (size_t)f * (ORBX_GRID_COLS * ORBX_GRID_ROWS + 1), ids + (size_t)f * cap);
   return ORBX_OK;
 }
 int orbx_search_by_projection_local(const orbx_frame_view* f, const orbx_sbp_local_points* p, float th_radius, float ratio,

@@ -8,6 +8,7 @@
 #include <set>
 
 #include "myslam_stub.hpp"
+#include "orb_b200_frame.hpp"
 #include "orb_b200_matcher.hpp"
 
 using namespace myslam;
@@ -366,6 +367,41 @@ int main() {
     const int d1 = Matcher::computeDistance(b.cur.descriptors_.row(3), b.kf1.descriptors_.row(3));
     expect(d0 == d1, "computeDistance(Mat, Mat)");
   }
+  // Frame::Frame after the extractor call (frame.cpp:29-31): undistortKeyPoints + findDepth + assignFeaturesToGrid
+  for (int variant = 0; variant < 3; ++variant) {
+    Scene a, b;
+    buildScene(a, 900u + variant, false);
+    buildScene(b, 900u + variant, false);
+    const float dist[5] = {variant == 2 ? 0.f : 0.2624f, -0.9531f, -0.0054f, 0.0026f, 1.1633f};   // TUM fr1-like; variant 2: k1 == 0 copies
+    a.cam.setIntrinsics(dist, variant == 1 ? 5 : 4);
+    b.cam.setIntrinsics(dist, variant == 1 ? 5 : 4);
+    std::vector<float> depthStore(480 * 640);
+    cv::Mat depth(480, 640, CV_32F, depthStore.data(), 640 * sizeof(float));   // CV_32F 480 x 640 over external memory
+    g_seed = 31u + variant;
+    for (int y = 0; y < 480; ++y)
+      for (int x = 0; x < 640; ++x) depth.at<float>(y, x) = (rnd() % 6 == 0) ? 0.f : 0.5f + 7.f * urand();
+    Frame* fr[2] = {&a.cur, &b.cur};
+    for (int k = 0; k < 2; ++k) {
+      fr[k]->keypoints_ = fr[k]->unKeypoints_;
+      for (size_t i = 0; i < fr[k]->keypoints_.size(); ++i) {             // keep the depth lookup inside the image
+        fr[k]->keypoints_[i].pt.x = std::min(fr[k]->keypoints_[i].pt.x, 639.f);
+        fr[k]->keypoints_[i].pt.y = std::min(fr[k]->keypoints_[i].pt.y, 479.f);
+      }
+      fr[k]->unKeypoints_.clear(); fr[k]->uRight_.clear(); fr[k]->depth_.clear();
+    }
+    a.cur.undistortKeyPoints(); a.cur.findDepth(depth); a.cur.assignFeaturesToGrid();
+    myslam_b200::finishFrame(&b.cur, depth);
+    bool same = a.cur.unKeypoints_.size() == b.cur.unKeypoints_.size() &&
+                std::memcmp(a.cur.unKeypoints_.data(), b.cur.unKeypoints_.data(), a.cur.unKeypoints_.size() * sizeof(cv::KeyPoint)) == 0 &&
+                a.cur.uRight_ == b.cur.uRight_ && a.cur.depth_ == b.cur.depth_;
+    int moved = 0;
+    for (size_t i = 0; i < a.cur.keypoints_.size(); ++i) moved += a.cur.keypoints_[i].pt.x != a.cur.unKeypoints_[i].pt.x;
+    for (int ix = 0; ix < 64 && same; ++ix)
+      for (int iy = 0; iy < 48 && same; ++iy) same = a.cur.gridKeypoints_[ix][iy] == b.cur.gridKeypoints_[ix][iy];
+    std::printf("finishFrame variant %d: %d of %zu keypoints moved by the undistortion\n", variant, moved, a.cur.keypoints_.size());
+    expect(same && (variant == 2 ? moved == 0 : moved > 900), "Frame::Frame post-processing (undistort, depth, grid)");
+  }
+
   // Empty inputs: the reference's loops are no-ops; the adapter must return 0 without touching the device or the objects.
   {
     Scene a;

@@ -91,6 +91,13 @@ struct Sim3 {
 
 struct Camera {
   float fx_, fy_, cx_, cy_, bf_, b_;
+  cv::Mat K_, distCoef_;                                  // CV_32F 3x3 and 4x1 / 5x1, stored in byte matrices of 4x the width
+  void setIntrinsics(const float* dist, int ndist) {      // camera.cpp:19-38
+    K_ = cv::Mat(3, 3 * 4, CV_8UC1); distCoef_ = cv::Mat(ndist, 4, CV_8UC1);
+    const float k[9] = {fx_, 0, cx_, 0, fy_, cy_, 0, 0, 1};
+    for (int i = 0; i < 9; ++i) K_.at<float>(i / 3, i % 3) = k[i];
+    for (int i = 0; i < ndist; ++i) distCoef_.at<float>(i, 0) = dist[i];
+  }
   Vector2d camera2pixel(const Vector3d& p) { return Vector2d(fx_ * p[0] / p[2] + cx_, fy_ * p[1] / p[2] + cy_); }   // camera.cpp:72-75
 };
 
@@ -126,7 +133,9 @@ typedef std::map<unsigned, std::vector<unsigned> > FeatureVector;   // DBoW3::Fe
 struct Frame {
   Camera* camera_ = nullptr;
   SE3 Tcw_;
+  std::vector<cv::KeyPoint> keypoints_;
   std::vector<cv::KeyPoint> unKeypoints_;
+  std::vector<float> depth_;
   std::vector<float> uRight_;
   cv::Mat descriptors_;
   std::vector<MapPoint*> mappoints_;
@@ -137,7 +146,30 @@ struct Frame {
   std::vector<bool> outliers_;
   FeatureVector featVec_;
 
+  // frame.cpp:36-70 with cv::undistortPoints(mat, mat, K, distCoef, Mat(), K) stated by oracle/cvprims.h (pinned to cv2 4.13)
+  void undistortKeyPoints() {
+    const cv::Mat& D = camera_->distCoef_;
+    unKeypoints_ = keypoints_;
+    if (D.at<float>(0, 0) == 0.0f) return;
+    double k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < D.rows && i < 8; ++i) k[i] = (double)D.at<float>(i, 0);
+    const cv::Mat& K = camera_->K_;
+    for (int i = 0; i < (int)N_; ++i)
+      cvp::undistort_point_k(keypoints_[i].pt.x, keypoints_[i].pt.y, K.at<float>(0, 0), K.at<float>(1, 1), K.at<float>(0, 2),
+                             K.at<float>(1, 2), k, &unKeypoints_[i].pt.x, &unKeypoints_[i].pt.y);
+  }
+  void findDepth(cv::Mat& depthImg) {                                  // frame.cpp:108-133
+    if (keypoints_.empty()) return;
+    uRight_ = std::vector<float>(N_, -1);
+    depth_ = std::vector<float>(N_, -1);
+    for (int i = 0; i < (int)N_; ++i) {
+      const float u = keypoints_[i].pt.x, v = keypoints_[i].pt.y;
+      const float d = depthImg.at<float>(v, u);
+      if (d > 0) { depth_[i] = d; uRight_[i] = unKeypoints_[i].pt.x - camera_->bf_ / d; }
+    }
+  }
   void assignFeaturesToGrid() {                                       // frame.cpp:72-97
+    for (int ix = 0; ix < 64; ++ix) for (int iy = 0; iy < 48; ++iy) gridKeypoints_[ix][iy].clear();
     for (int i = 0; i < (int)N_; ++i) {
       const int gx = (int)round((unKeypoints_[i].pt.x - xMin_) * gridPerPixelWidth_);
       const int gy = (int)round((unKeypoints_[i].pt.y - yMin_) * gridPerPixelHeight_);
