@@ -27,6 +27,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -607,6 +608,46 @@ int searchByBoWKeyFrames(KeyFrameT* keyframe1, KeyFrameT* keyframe2, std::vector
   for (int i = 0; i < a.side.n; ++i)
     if (match[i] >= 0) mappointMatches[i] = mappoints2[match[i]];                                      // :629
   return match_cnt;
+}
+
+// MapPoint::computeDescriptor()                                                                   mappoint.cpp:118-179
+// for MANY map points in one device call (the reference calls it point by point: localMapping.cpp / tracking after new
+// observations).  Per point: the descriptors of its good observing key frames in std::map order
+// (:131-137), all-pairs Hamming distances, the row with the smallest median (first wins) becomes descriptor_ (:173-176).
+// Bad points, points without observations or without a good key frame keep their descriptor, like the early returns.
+template <class MapPointT>
+void computeDescriptors(const std::vector<MapPointT*>& points, int device = 0) {
+  const int P = (int)points.size();
+  if (P == 0) return;
+  typedef typename std::remove_reference<decltype(points[0]->observedKFs_)>::type ObsMap;
+  typedef typename std::remove_reference<decltype(points[0]->descriptor_)>::type MatT;
+  std::vector<uint8_t> desc;
+  std::vector<int32_t> start(1, 0);
+  std::vector<MatT> rows;                                   // the Mat rows behind `desc`, to clone the winner from
+  for (int p = 0; p < P; ++p) {
+    ObsMap observedKFs;
+    bool bad = true;
+    if (points[p]) {
+      std::unique_lock<decltype(points[p]->mutexFeature_)> lock(points[p]->mutexFeature_);
+      bad = points[p]->badFlag_;
+      if (!bad) observedKFs = points[p]->observedKFs_;
+    }
+    if (!bad)
+      for (typename ObsMap::iterator it = observedKFs.begin(); it != observedKFs.end(); ++it)
+        if (!it->first->isBad()) {
+          rows.push_back(it->first->descriptors_.row((int)it->second));
+          desc.insert(desc.end(), rows.back().data, rows.back().data + 32);
+        }
+    start.push_back((int32_t)rows.size());
+  }
+  if (rows.empty()) return;
+  std::vector<int32_t> best(P, -1);
+  detail::check(orbx_medoid_descriptors(desc.data(), start.data(), P, best.data(), device));
+  for (int p = 0; p < P; ++p)
+    if (best[p] >= 0) {
+      std::unique_lock<decltype(points[p]->mutexFeature_)> lock(points[p]->mutexFeature_);
+      points[p]->descriptor_ = rows[start[p] + best[p]].clone();
+    }
 }
 
 // Matcher::computeDistance(const Mat&, const Mat&)                                               matcher.cpp:1240-1256

@@ -40,7 +40,7 @@ def test_matcher_adapter_host_logic_on_port(tmp_path):
                                                os.path.join(TOOLS, "cabi_on_port.cpp"), "-L" + odir, "-lorbport",
                                                "-Wl,-rpath," + odir, "-o", exe])
     out = _run([exe])
-    assert "all comparisons identical" in out and out.count(" same") == 48 and "DIFFERENT" not in out, out
+    assert "all comparisons identical" in out and out.count(" same") == 49 and "DIFFERENT" not in out, out
 
 
 def _link_product(tmp_path):
@@ -60,4 +60,4 @@ def test_matcher_adapter_links_against_the_library(tmp_path):
 @pytest.mark.gpu
 def test_matcher_adapter_on_gpu(tmp_path):
     out = _run([_link_product(tmp_path)])
-    assert "all comparisons identical" in out and out.count(" same") == 48 and "DIFFERENT" not in out, out
+    assert "all comparisons identical" in out and out.count(" same") == 49 and "DIFFERENT" not in out, out

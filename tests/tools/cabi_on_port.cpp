@@ -40,6 +40,7 @@ int port_sbp_frame(const port_sbp_frame_in* in, int32_t* assign);
 int port_sbp_local(const port_sbp_local_in* in, int32_t* assign);
 int port_sbp_reloc(const port_sbp_frame_in* in, float dist_threshold, int32_t* assign);
 int port_sbp_sim3(const port_sbp_frame_in* in, int th, int32_t* assign);
+void port_medoid(const uint8_t* desc, const int32_t* start, int npoints, int32_t* best);
 void port_window_argmin(const port_sbp_frame_in* in, float th_radius, float dist_threshold, int chi2, int32_t* best);
 int port_search_by_sim3(const port_sbp_frame_in* in12, const port_sbp_frame_in* in21, float th, int32_t* match12);
 int port_search_by_bow(const port_bow_side* a, const port_bow_side* b, int mode, float ratio, int th_low, int check_rot,
@@ -110,6 +111,10 @@ int orbx_frame_finish(const orbx_camera* cam, const orbx_keypoint* kps, const in
                       depth ? (const float*)((const char*)depth + f * depth_frame_stride) : nullptr, w, height, depth_row_stride,
                       unkps + (size_t)f * cap, uright + (size_t)f * cap, depth_out + (size_t)f * cap,
                       cell_start + (size_t)f * (ORBX_GRID_COLS * ORBX_GRID_ROWS + 1), ids + (size_t)f * cap);
+  return ORBX_OK;
+}
+int orbx_medoid_descriptors(const uint8_t* desc, const int32_t* start, int npoints, int32_t* best, int) {
+  port_medoid(desc, start, npoints, best);
   return ORBX_OK;
 }
 int orbx_search_by_projection_local(const orbx_frame_view* f, const orbx_sbp_local_points* p, float th_radius, float ratio,

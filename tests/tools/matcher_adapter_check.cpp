@@ -81,7 +81,7 @@ static void buildScene(Scene& s, unsigned seed, bool moveForward) {
     l.mappoints_[i] = (rnd() % 10 == 0) ? nullptr : &mp;
     l.outliers_[i] = rnd() % 12 == 0;
     // local-map view of the same point
-    mp.bad_ = rnd() % 15 == 0;
+    mp.badFlag_ = rnd() % 15 == 0;
     mp.trackInLocalMap_ = rnd() % 8 != 0;
     mp.trackScaleLevel_ = l.unKeypoints_[i].octave;
     mp.trackProj_u_ = (float)u; mp.trackProj_v_ = (float)v; mp.trackProj_uR_ = (float)u - 40.f / (float)std::fabs(z);
@@ -239,7 +239,7 @@ int main() {
           const float d3 = (float)(( (k ? b : a).cur.Tcw_ * mp.pos_)).norm();
           mp.maxDistance_ = d3 * std::pow(1.2f, (float)mp.trackScaleLevel_ - 0.5f);
           mp.minDistance_ = mp.maxDistance_ / 3.5831808f;
-          if (i % 50 == 0) mp.indexInKF_[k ? &kb2 : &ka2] = (i * 3) % 1000;
+          if (i % 50 == 0) mp.observedKFs_[k ? &kb2 : &ka2] = (i * 3) % 1000;
         }
       }
       SE3 I; I.t[0] = 0.002; I.t[2] = -0.001;
@@ -253,7 +253,7 @@ int main() {
         same = (m12a[i] ? (long)(m12a[i] - &a.points[0]) : -1) == (m12b[i] ? (long)(m12b[i] - &b.points[0]) : -1);
       std::printf("  searchBySim3(KeyFrame*,KeyFrame*): %d matches\n", na);
       expect(same && na > 50, "searchBySim3(KeyFrame*, KeyFrame*, matches12, S12, th)");
-      for (int i = 0; i < 900; ++i) { a.points[i].indexInKF_.clear(); b.points[i].indexInKF_.clear(); }   // ka2 / kb2 die here
+      for (int i = 0; i < 900; ++i) { a.points[i].observedKFs_.clear(); b.points[i].observedKFs_.clear(); }   // ka2 / kb2 die here
     }
 
     // 3. BoW search key frame -> frame
@@ -317,7 +317,7 @@ int main() {
           kf.mappoints_[i] = nullptr;
           if (i >= 900) continue;
           MapPoint& mp = s.points[i];
-          mp.bad_ = i % 15 == 3; mp.indexInKF_.clear(); mp.observe_cnt_ = i % 4;
+          mp.badFlag_ = i % 15 == 3; mp.observedKFs_.clear(); mp.observe_cnt_ = i % 4;
           kf.unKeypoints_[i].pt.x = mp.trackProj_u_ + (float)((i * 13) % 5) * 0.5f - 1.f;
           kf.unKeypoints_[i].pt.y = mp.trackProj_v_ + (float)((i * 17) % 5) * 0.5f - 1.f;
           kf.unKeypoints_[i].octave = mp.trackScaleLevel_;
@@ -329,7 +329,7 @@ int main() {
           mp.minDistance_ = mp.maxDistance_ / 3.5831808f;
           if (i % 5 == 1) {                                  // the feature already holds another (spare) point
             MapPoint& org = s.points[900 + (i % 200)];
-            if (!org.beObserved(&kf)) { org.bad_ = i % 35 == 1; org.observe_cnt_ = i % 3; org.addObservation(&kf, i); kf.mappoints_[i] = &org; }
+            if (!org.beObserved(&kf)) { org.badFlag_ = i % 35 == 1; org.observe_cnt_ = i % 3; org.addObservation(&kf, i); kf.mappoints_[i] = &org; }
           }
           if (i % 19 == 2) mp.addObservation(&kf, (i + 500) % 1000);   // already observed by the key frame elsewhere
         }
@@ -353,13 +353,13 @@ int main() {
         same = (ra[i] ? (long)(ra[i] - &a.points[0]) : -1) == (rb[i] ? (long)(rb[i] - &b.points[0]) : -1);
       int nbad = 0;
       for (size_t i = 0; i < a.points.size() && same; ++i) {
-        same = a.points[i].bad_ == b.points[i].bad_ && a.points[i].observe_cnt_ == b.points[i].observe_cnt_ &&
-               a.points[i].indexInKF_.size() == b.points[i].indexInKF_.size();
-        nbad += a.points[i].bad_;
+        same = a.points[i].badFlag_ == b.points[i].badFlag_ && a.points[i].observe_cnt_ == b.points[i].observe_cnt_ &&
+               a.points[i].observedKFs_.size() == b.points[i].observedKFs_.size();
+        nbad += a.points[i].badFlag_;
       }
       std::printf("  %s: %d fused (%d bad points afterwards)\n", pass ? "fuseByPose" : "fuseMapPoints", na, nbad);
       expect(same && na > 50, pass ? "fuseByPose(KeyFrame*, Sim3&, loopPts, replacePts, th)" : "fuseMapPoints(KeyFrame*, mappoints, threshold)");
-      for (size_t i = 0; i < a.points.size(); ++i) { a.points[i].indexInKF_.clear(); b.points[i].indexInKF_.clear(); }
+      for (size_t i = 0; i < a.points.size(); ++i) { a.points[i].observedKFs_.clear(); b.points[i].observedKFs_.clear(); }
     }
 
     // 5. computeDistance
@@ -400,6 +400,47 @@ int main() {
       for (int iy = 0; iy < 48 && same; ++iy) same = a.cur.gridKeypoints_[ix][iy] == b.cur.gridKeypoints_[ix][iy];
     std::printf("finishFrame variant %d: %d of %zu keypoints moved by the undistortion\n", variant, moved, a.cur.keypoints_.size());
     expect(same && (variant == 2 ? moved == 0 : moved > 900), "Frame::Frame post-processing (undistort, depth, grid)");
+  }
+
+  // MapPoint::computeDescriptor for many points at once
+  {
+    Scene a, b;
+    buildScene(a, 1234u, false);
+    buildScene(b, 1234u, false);
+    std::vector<KeyFrame> kfa(12), kfb(12);
+    g_seed = 99u;
+    for (int k = 0; k < 12; ++k) {
+      kfa[k] = a.kf1; kfa[k].descriptors_ = a.kf1.descriptors_.clone();
+      for (int i = 0; i < 1000; ++i) flipBits(kfa[k].descriptors_.data + (size_t)i * 32, (int)(rnd() % 40));
+      kfa[k].bad_kf_ = k == 5;
+      kfb[k] = b.kf1; kfb[k].descriptors_ = kfa[k].descriptors_.clone(); kfb[k].bad_kf_ = kfa[k].bad_kf_;
+    }
+    std::vector<MapPoint*> pa, pb;
+    for (int i = 0; i < 900; ++i) {
+      MapPoint& ma = a.points[i]; MapPoint& mb = b.points[i];
+      ma.observedKFs_.clear(); mb.observedKFs_.clear();
+      const int nobs = (i % 17 == 0) ? 0 : 1 + (int)(rnd() % 12);          // some points without observations
+      for (int o = 0; o < nobs; ++o) {
+        const int k = (int)(rnd() % 12);
+        const size_t idx = (i % 3 == 0) ? (size_t)i : (size_t)(rnd() % 1000);
+        ma.observedKFs_[&kfa[k]] = idx; mb.observedKFs_[&kfb[k]] = idx;
+      }
+      if (i % 29 == 0) { ma.observedKFs_.clear(); mb.observedKFs_.clear(); ma.observedKFs_[&kfa[5]] = 7; mb.observedKFs_[&kfb[5]] = 7; }   // only a bad key frame
+      pa.push_back(&ma); pb.push_back(&mb);
+    }
+    pa.push_back(nullptr); pb.push_back(nullptr);
+    for (size_t i = 0; i + 1 < pa.size(); ++i) refComputeDescriptor(pa[i]);
+    myslam_b200::computeDescriptors(pb);
+    bool same = true;
+    int changed = 0;
+    Scene c; buildScene(c, 1234u, false);                                  // untouched copy: how many descriptors moved at all
+    for (int i = 0; i < 900 && same; ++i) {
+      same = std::memcmp(a.points[i].descriptor_.data, b.points[i].descriptor_.data, 32) == 0;
+      changed += std::memcmp(a.points[i].descriptor_.data, c.points[i].descriptor_.data, 32) != 0;
+    }
+    std::printf("computeDescriptors: %d of 900 map points got a new representative descriptor\n", changed);
+    expect(same && changed > 500, "MapPoint::computeDescriptor, batched (medoid by median Hamming distance)");
+    for (int i = 0; i < 900; ++i) { a.points[i].observedKFs_.clear(); b.points[i].observedKFs_.clear(); }
   }
 
   // Empty inputs: the reference's loops are no-ops; the adapter must return 0 without touching the device or the objects.

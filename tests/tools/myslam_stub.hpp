@@ -4,6 +4,7 @@
 // loop-for-loop CPU statement of the reference's search functions over these objects (`RefMatcher`), which is what the
 // adapter's results are compared with.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <set>
@@ -107,10 +108,11 @@ struct MapPoint {
   float minDistance_ = 0, maxDistance_ = 0;
   Vector3d normalVector_;
   Vector3d getNormalVector() { return normalVector_; }
-  std::map<struct KeyFrame*, int> indexInKF_;
-  int getIndexInKeyFrame(struct KeyFrame* kf) { return indexInKF_.count(kf) ? indexInKF_[kf] : -1; }
-  bool beObserved(struct KeyFrame* kf) { return indexInKF_.count(kf) != 0; }
-  void addObservation(struct KeyFrame* kf, int idx) { if (!indexInKF_.count(kf)) { indexInKF_[kf] = idx; ++observe_cnt_; } }
+  std::map<struct KeyFrame*, size_t> observedKFs_;   // mappoint.h:49
+  struct NoMutex { void lock() {} void unlock() {} } mutexFeature_;   // single-threaded stand-in for std::mutex
+  int getIndexInKeyFrame(struct KeyFrame* kf) { return observedKFs_.count(kf) ? (int)observedKFs_[kf] : -1; }
+  bool beObserved(struct KeyFrame* kf) { return observedKFs_.count(kf) != 0; }
+  void addObservation(struct KeyFrame* kf, int idx) { if (!observedKFs_.count(kf)) { observedKFs_[kf] = idx; ++observe_cnt_; } }
   inline void replaceMapPoint(MapPoint* mp);            // stand-in for mappoint.cpp:214-262: hand the observations over, go bad
   inline int predictScale(const float& currDist, struct KeyFrame* kf);  // mappoint.cpp:198-212
   float getMinDistanceThreshold() { return 0.8f * minDistance_; }      // mappoint.cpp:391-401
@@ -118,14 +120,14 @@ struct MapPoint {
   inline int predictScale(const float& currDist, Frame* frame);        // mappoint.cpp:182-196
   cv::Mat descriptor_;
   int observe_cnt_ = 0;
-  bool bad_ = false;
+  bool badFlag_ = false;
   bool trackInLocalMap_ = false;
   int trackScaleLevel_ = 0;
   float trackProj_u_ = 0, trackProj_uR_ = 0, trackProj_v_ = 0, viewCos_ = 0;
   Vector3d getPose() { return pos_; }
   cv::Mat getDescriptor() { return descriptor_.clone(); }
   int getObsCnt() { return observe_cnt_; }
-  bool isBad() { return bad_; }
+  bool isBad() { return badFlag_; }
 };
 
 typedef std::map<unsigned, std::vector<unsigned> > FeatureVector;   // DBoW3::FeatureVector
@@ -207,6 +209,8 @@ inline int MapPoint::predictScale(const float& currDist, Frame* frame) {
 }
 
 struct KeyFrame {
+  bool bad_kf_ = false;
+  bool isBad() { return bad_kf_; }
   Camera* camera_ = nullptr;
   SE3 Tcw_;
   SE3 getPose() { return Tcw_; }
@@ -261,13 +265,38 @@ inline int MapPoint::predictScale(const float& currDist, KeyFrame* kf) {
 
 inline void MapPoint::replaceMapPoint(MapPoint* mp) {
   if (mp == this) return;
-  std::map<KeyFrame*, int> obs = indexInKF_;
-  indexInKF_.clear();
-  bad_ = true;
-  for (std::map<KeyFrame*, int>::iterator it = obs.begin(); it != obs.end(); ++it) {
+  std::map<KeyFrame*, size_t> obs = observedKFs_;
+  observedKFs_.clear();
+  badFlag_ = true;
+  for (std::map<KeyFrame*, size_t>::iterator it = obs.begin(); it != obs.end(); ++it) {
     if (!mp->beObserved(it->first)) { it->first->mappoints_[it->second] = mp; mp->addObservation(it->first, it->second); }
     else it->first->mappoints_[it->second] = nullptr;
   }
+}
+
+// MapPoint::computeDescriptor (mappoint.cpp:118-179) over the stand-in objects
+inline void refComputeDescriptor(MapPoint* mp) {
+  if (mp->badFlag_ || mp->observedKFs_.empty()) return;
+  std::vector<cv::Mat> desp;
+  for (std::map<KeyFrame*, size_t>::iterator it = mp->observedKFs_.begin(); it != mp->observedKFs_.end(); ++it)
+    if (!it->first->isBad()) desp.push_back(it->first->descriptors_.row((int)it->second));
+  if (desp.empty()) return;
+  const size_t N = desp.size();
+  std::vector<std::vector<float> > dm(N, std::vector<float>(N, 0));
+  for (size_t i = 0; i < N; ++i)
+    for (size_t j = i + 1; j < N; ++j) {
+      int d = 0;
+      for (int b = 0; b < 32; ++b) d += __builtin_popcount((unsigned)(desp[i].data[b] ^ desp[j].data[b]));
+      dm[i][j] = d; dm[j][i] = d;
+    }
+  int bestMid = 256, bestIdx = 0;
+  for (size_t i = 0; i < N; ++i) {
+    std::vector<int> row(dm[i].begin(), dm[i].end());
+    std::sort(row.begin(), row.end());
+    const int mid = row[int(0.5 * (N - 1))];
+    if (mid < bestMid) { bestMid = mid; bestIdx = (int)i; }
+  }
+  mp->descriptor_ = desp[bestIdx].clone();
 }
 
 // ---- CPU statement of the reference's loops over the objects above (checker only) ------------------------------------
