@@ -30,6 +30,17 @@ def test_library_exports_every_declared_symbol(vo):
     assert not missing, missing
 
 
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/orb_b200.h must compile as C99 (no C++-isms, no torch / CUDA types)."""
+    src = tmp_path / "c_hdr.c"
+    src.write_text('#include "orb_b200.h"\nint main(void) { orbx_params p; orbx_frame_view v; (void)p; (void)v; return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "orb_b200.h")).read(), flags=re.S)
+    assert "torch" not in hdr and "cuda_runtime" not in hdr and "at::" not in hdr and "#include <cuda" not in hdr
+
+
 def test_no_cpu_fallback(vo):
     import numpy as np
     if vo.device_count() > 0:
