@@ -60,4 +60,8 @@ def test_matcher_adapter_links_against_the_library(tmp_path):
 @pytest.mark.gpu
 def test_matcher_adapter_on_gpu(tmp_path):
     out = _run([_link_product(tmp_path)])
+    log_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(log_dir):                      # keep the program's report (incl. its timing lines) next to the other GPU logs
+        with open(os.path.join(log_dir, "matcher_adapter_gpu.log"), "w") as f:
+            f.write(out)
     assert "all comparisons identical" in out and out.count(" same") == 49 and "DIFFERENT" not in out, out

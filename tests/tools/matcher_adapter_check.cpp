@@ -3,6 +3,7 @@
 // (tests/tools/myslam_stub.hpp, RefMatcher) on identical object graphs: the mappoints_ / mappointMatches vectors written by
 // the two must be the same pointers, and the returned match counts equal.
 //   g++ -std=c++11 -Ioracle/compat -Iinclude tests/tools/matcher_adapter_check.cpp -Lvo_slam_test_b200/lib -lvoslam_b200 -o /tmp/mcheck
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <set>
@@ -474,6 +475,34 @@ int main() {
     for (size_t i = 0; i < c1.mappoints_.size() && ok; ++i) ok = c1.mappoints_[i] == a.cur.mappoints_[i];
     std::printf("empty inputs\n");
     expect(ok, "every entry point with empty point lists / featureless frames");
+  }
+  // Timing of the tracking-thread calls through the adapter (host objects in, host objects out, synchronous), next to the
+  // object-walking CPU statement on this machine's host (one core).  Informative only: nothing is asserted on it.
+  {
+    Scene a;
+    buildScene(a, 4242u, false);
+    typedef myslam_b200::MatcherT<Frame, KeyFrame, MapPoint> M;
+    M gpu(0.7f);
+    RefMatcher ref(0.7f);
+    const int reps = 20;
+    double tr[3] = {0, 0, 0}, tg[3] = {0, 0, 0};
+    std::vector<MapPoint*> out;
+    for (int r = -2; r < reps; ++r) {                      // two warm-up rounds
+      for (int which = 0; which < 2; ++which) {
+        for (int k = 0; k < 3; ++k) {
+          Frame c = a.cur;                                 // fresh copy: the searches write mappoints_
+          const auto t0 = std::chrono::steady_clock::now();
+          if (k == 0) { if (which) gpu.searchByProjection(&c, &a.last, 15.f, true); else ref.searchByProjection(&c, &a.last, 15.f, true); }
+          if (k == 1) { if (which) gpu.searchByProjection(&c, a.local, 3.f); else ref.searchByProjection(&c, a.local, 3.f); }
+          if (k == 2) { if (which) gpu.searchByBoW(&a.kf1, &c, out, true); else ref.searchByBoW(&a.kf1, &c, nullptr, out, true); }
+          const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+          if (r >= 0) (which ? tg : tr)[k] += ms / reps;
+        }
+      }
+    }
+    const char* names[3] = {"searchByProjection(Frame*,Frame*)", "searchByProjection(Frame*,local map)", "searchByBoW(KeyFrame*,Frame*)"};
+    for (int k = 0; k < 3; ++k)
+      std::printf("timing  %-40s CPU statement %.3f ms   adapter %.3f ms   (1000 features, 900 points)\n", names[k], tr[k], tg[k]);
   }
   std::printf(fails ? "matcher adapter: %d comparisons DIFFER\n" : "matcher adapter: all comparisons identical\n", fails);
   return fails ? 1 : 0;
