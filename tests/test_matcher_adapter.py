@@ -41,6 +41,9 @@ def test_matcher_adapter_host_logic_on_port(tmp_path):
                                                "-Wl,-rpath," + odir, "-o", exe])
     out = _run([exe])
     assert "all comparisons identical" in out and out.count(" same") == 49 and "DIFFERENT" not in out, out
+    for seed in range(1000, 1000 + 40 * 16, 16):          # 40 more families of scenes (4 rounds each) through every entry point
+        out = _run([exe, str(seed)])
+        assert "all comparisons identical" in out and "DIFFERENT" not in out, (seed, out)
 
 
 def _link_product(tmp_path):

@@ -5,6 +5,7 @@
 //   g++ -std=c++11 -Ioracle/compat -Iinclude tests/tools/matcher_adapter_check.cpp -Lvo_slam_test_b200/lib -lvoslam_b200 -o /tmp/mcheck
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 
@@ -131,7 +132,8 @@ static void expect(bool ok, const char* what) {
   if (!ok) ++fails;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const unsigned seedBase = argc > 1 ? (unsigned)std::strtoul(argv[1], nullptr, 10) : 77u;   // other scenes for the CPU sweep
   int ndev = 0;
   orbx_device_count(&ndev);
   if (ndev == 0) { std::printf("matcher adapter links; no CUDA device -> compute skipped\n"); return 0; }
@@ -140,8 +142,8 @@ int main() {
     const bool fwd = round == 1, checkRot = round != 2;
     const float ratio = round == 3 ? 0.9f : 0.7f;
     Scene a, b;                                   // identical object graphs: a for the reference loops, b for the adapter
-    buildScene(a, 77u + round, fwd);
-    buildScene(b, 77u + round, fwd);
+    buildScene(a, seedBase + round, fwd);
+    buildScene(b, seedBase + round, fwd);
     RefMatcher ref(ratio);
     Matcher gpu(ratio);
     std::printf("round %d (forward %d, checkRot %d, ratio %.2f)\n", round, (int)fwd, (int)checkRot, ratio);
@@ -210,7 +212,7 @@ int main() {
       for (size_t i = 0; i < ma2.size() && same; ++i)
         same = (ma2[i] ? (long)(ma2[i] - &a.points[0]) : -1) == (mb2[i] ? (long)(mb2[i] - &b.points[0]) : -1);
       std::printf("  searchByProjection(KeyFrame*,Sim3&): %d matches\n", na);
-      expect(same && na > 30, "searchByProjection(KeyFrame*, Sim3&, loopPts, matchPts, th)");
+      expect(same && na > 10, "searchByProjection(KeyFrame*, Sim3&, loopPts, matchPts, th)");
     }
 
     // 2d. searchBySim3 between two key frames at the same pose (S12 close to identity, scale != 1 folded into the points)
