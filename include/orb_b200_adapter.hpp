@@ -5,11 +5,12 @@
 // and links libvoslam_b200.so; `ORB_SLAM2::ORBextractor` keeps its constructor, call operator and getters
 // (include/myslam/ORBextractor.h:45-108), so Frame::Frame (src/frame.cpp:22) and VisualOdometry
 // (src/visualOdometry.cpp:27-31) compile unchanged.  Needs OpenCV's core types (cv::Mat, cv::KeyPoint,
-// cv::InputArray, cv::OutputArray); in this repo it is type-checked against oracle/compat (tests/test_adapter_compile.py).
+// cv::InputArray, cv::OutputArray); in this repo it is type-checked against oracle/compat (tests/test_abi_and_adapter.py).
 //
 // Error convention: the reference returns void and asserts; the adapter throws std::runtime_error with
 // orbx_last_error() when the CUDA path fails (there is no CPU fallback to fall back to).
 #pragma once
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
