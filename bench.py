@@ -367,6 +367,23 @@ def run_b200(args, rank, world, local_rank):
     h2d = F * W_IMG * H_IMG
     d2h = F * 4 + F * cap * 28 + F * cap * 32 + npairs * cap * 13
     assert np.array_equal(h_counts.numpy(), counts), "e2e and resident paths disagree"
+    # What bounds e2e: the plain pinned host->device copy rate of the same input on this box (copies only, nothing else running).
+    # Reported beside e2e; a failure here must not cost the bench line.
+    link = None
+    try:
+        c0 = torch.cuda.Event(enable_timing=True); c1 = torch.cuda.Event(enable_timing=True)
+        d_imgs.copy_(h_imgs, non_blocking=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(3):
+            d_imgs.copy_(h_imgs, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        gbs = 3 * h2d / (c0.elapsed_time(c1) * 1e6)
+        link = {"h2d_copy_gbs": gbs, "e2e_input_gbs": (e2e_value / world) * W_IMG * H_IMG / 1e9,
+                "e2e_frac_of_copy_rate": (e2e_value / world) * W_IMG * H_IMG / 1e9 / gbs}
+    except Exception as exc:                          # noqa: BLE001
+        link = {"error": str(exc)[:120]}
 
     # ---- single-frame latency through orbx_extract (the reference's actual call pattern: one frame per call) ------
     single = None
@@ -427,7 +444,7 @@ def run_b200(args, rank, world, local_rank):
                            "chunk_frames": int(os.environ.get("ORBX_CHUNK", "512")), "resident_lanes": int(os.environ.get("ORBX_LANES", "2")), "chunk_frames_host_pipeline": int(os.environ.get("ORBX_CHUNK_HOST", os.environ.get("ORBX_CHUNK", "256"))), "mean_keypoints": float(counts.mean()), "accepted_matches_per_pair": accepted / max(npairs, 1)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "orbx_extract_match_batch (host C ABI, pinned host buffers, copies inside the timed region)"},
+                        "api": "orbx_extract_match_batch (host C ABI, pinned host buffers, copies inside the timed region)", "link": link},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "stages": stages, "hamming_gmatch_per_s": stages["hamming_pairs"]["gmatch_per_s"],
                 "hamming_roofline": hamming_roofline, "hamming_map": hamming_map, "single_frame": single, "cpu_baseline": cpu_baseline}
