@@ -345,6 +345,12 @@ __device__ __forceinline__ uint32_t far4(uint32_t s, uint32_t c, uint32_t kc, bo
 __device__ __forceinline__ uint32_t gather_flags(uint32_t m) { return (((m >> 7) & 0x01010101u) * 0x00204081u) >> 21 & 0xFu; }
 __device__ __forceinline__ uint32_t scatter_flags(uint32_t bits) { return (bits * 0x10204080u) & 0x80808080u; }
 
+// Build switch ORBX_FAST_A2 (default 0, A/B only, tools/build_variants.sh): stage a tests only the two axis pairs
+// (0|8, 4|12) and the two pairs next to the vertical axis move to stage b -- half the stage-a work on every pixel against
+// more survivors in stage b.  Both stages are filters in front of the exact arc score, so the result cannot change.
+#ifndef ORBX_FAST_A2
+#define ORBX_FAST_A2 0
+#endif
 // Necessary condition of a FAST-9 corner (same shape as OpenCV's quick test, sign-agnostic): every opposite ring pair
 // has a member that differs from the centre by more than t.  Per-byte flags (bit 7) for the 4 centres, in two stages so
 // that the second one can run densely over the items that survived the first.
@@ -357,8 +363,10 @@ __device__ __forceinline__ uint32_t reject4_a(const uint8_t* rowm3, int sp, uint
   const uint32_t c = pick4<SH, 0>(W0);
   uint32_t m = far4(pick4<SH, 0>(Wp3), c, kc, hiT) | far4(pick4<SH, 0>(Wm3), c, kc, hiT);     // ring 0 | 8
   m &= far4(pick4<SH, 3>(W0), c, kc, hiT) | far4(pick4<SH, -3>(W0), c, kc, hiT);               // ring 4 | 12
+#if !ORBX_FAST_A2
   m &= far4(pick4<SH, 1>(Wp3), c, kc, hiT) | far4(pick4<SH, -1>(Wm3), c, kc, hiT);             // ring 1 | 9
   m &= far4(pick4<SH, 1>(Wm3), c, kc, hiT) | far4(pick4<SH, -1>(Wp3), c, kc, hiT);             // ring 7 | 15
+#endif
   return m;
 }
 template <int SH>
@@ -374,6 +382,12 @@ __device__ __forceinline__ uint32_t reject4_b(const uint8_t* rowm3, int sp, uint
   load_window(Wb, rowm3 + 2 * sp);   // row -1
   m &= far4(pick4<SH, 3>(Wa), c, kc, hiT) | far4(pick4<SH, -3>(Wb), c, kc, hiT);               // ring 3 | 11
   m &= far4(pick4<SH, 3>(Wb), c, kc, hiT) | far4(pick4<SH, -3>(Wa), c, kc, hiT);               // ring 5 | 13
+#if ORBX_FAST_A2
+  load_window(Wa, rowm3 + 6 * sp);   // row +3
+  load_window(Wb, rowm3);            // row -3
+  m &= far4(pick4<SH, 1>(Wa), c, kc, hiT) | far4(pick4<SH, -1>(Wb), c, kc, hiT);               // ring 1 | 9
+  m &= far4(pick4<SH, 1>(Wb), c, kc, hiT) | far4(pick4<SH, -1>(Wa), c, kc, hiT);               // ring 7 | 15
+#endif
   return m;
 }
 
