@@ -185,3 +185,34 @@ def test_error_convention(vo):
     p = vo.api._Params(1000, 1.2, 8, 20, 7, 99)
     assert L.orbx_create(C.byref(p), C.byref(h)) == -2     # no such device
     ex.close()
+
+
+@pytest.mark.skipif(os.environ.get("ORBX_EXTRA_GPU_TESTS") != "1",
+                    reason="written in a session that had no GPU minutes left to confirm it: opt in with ORBX_EXTRA_GPU_TESTS=1")
+def test_random_configurations(vo):
+    """The generator of tests/test_oracle_vs_reference.py::test_port_equals_compiled_reference_random_configurations on the
+    GPU: random frame sizes, feature budgets, scale factors, level counts and thresholds.  Shapes the library declines
+     must come back as an error, never as different bits."""
+    rng = np.random.default_rng(20261017)
+    done = declined = 0
+    while done < 24:
+        H = int(rng.integers(140, 700)); W = int(rng.integers(H, 1000))
+        nf = int(rng.choice([50, 200, 500, 1000, 2000])); sc = float(rng.choice([1.2, 1.1, 1.5, 2.0])); nl = int(rng.integers(1, 9))
+        ini = int(rng.choice([20, 12, 40, 7])); mn = min(int(rng.choice([7, 3, ini])), ini)
+        if min(W, H) / (sc ** (nl - 1)) < 80:
+            continue
+        img = synth.make_frame(int(rng.integers(0, 10 ** 6)), H, W)
+        if done % 5 == 0:
+            img = (img.astype(np.int32) // 6 + 90).astype(np.uint8)
+        done += 1
+        rk, rd = oracle.Port(nf, sc, nl, ini, mn).extract(img)
+        ex = vo.ORBextractor(nf, sc, nl, ini, mn)
+        try:
+            k, d = ex(img)
+        except vo.OrbError:
+            declined += 1
+            continue
+        finally:
+            ex.close()
+        assert np.array_equal(k, rk) and np.array_equal(d, rd), (H, W, nf, sc, nl, ini, mn)
+    assert declined <= 4
