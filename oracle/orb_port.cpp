@@ -9,6 +9,11 @@
 // cv2 4.13.0; this port is asserted bit-equal to the reference's own ORBextractor.cpp compiled in
 // place (oracle/_ref/liborbref_parity.so) in tests/test_oracle_vs_reference.py, and both are
 // asserted against the committed fixtures in tests/golden/.
+// PARITY UNPINNED for the matcher.cpp / frame.cpp / mappoint.cpp functions below: the reference ships no tests or golden
+// vectors for them and their translation units need Eigen / Sophus / DBoW3, which are not installed, so no output of the
+// reference itself exists to compare with.  They are cross-checked instead against two independent restatements written
+// from the same source lines: a pure-Python one (tests/test_gpu_bow.py) and an object-walking C++ one over
+// reference-shaped Frame / KeyFrame / MapPoint types (tests/tools/myslam_stub.hpp, tests/test_matcher_adapter.py).
 //
 // Reference lines followed:
 //   ctor tables            ORBextractor.cpp:414-476          -> port_tables()
