@@ -19,7 +19,7 @@
 // or uses `myslam_b200::MatcherT<Frame, KeyFrame, MapPoint>` as the class itself.  Everything is a template over the
 // reference's own types and touches only members the reference's loops touch (named at each use), so the header needs
 // neither Sophus, Eigen nor DBoW3 itself.  In this repo it is compiled and run against stand-in types
-// (tests/tools/myslam_stub.hpp, tests/tools/matcher_adapter_check.cpp), next to a loop-for-loop CPU statement of the
+// (oracle/compat_myslam/myslam_stub.hpp, tests/tools/matcher_adapter_check.cpp), next to a loop-for-loop CPU statement of the
 // reference functions over the same objects.
 //
 // Error convention: the reference returns match counts and cannot fail; the adapter throws std::runtime_error with

@@ -1,8 +1,10 @@
-// tests/tools/myslam_stub.hpp -- TEST INFRASTRUCTURE.  Stand-ins for the reference's Frame / KeyFrame / MapPoint / Camera /
+// oracle/compat_myslam/myslam_stub.hpp -- TEST INFRASTRUCTURE.  Stand-ins for the reference's Frame / KeyFrame / MapPoint / Camera /
 // SE3 types with exactly the members Matcher's loops touch (include/myslam/frame.h:16-71, keyframe.h, mappoint.h:20-90,
 // camera.h:13-45), so that include/orb_b200_matcher.hpp can be compiled and run without Sophus / Eigen / DBoW3, plus a
 // loop-for-loop CPU statement of the reference's search functions over these objects (`RefMatcher`), which is what the
-// adapter's results are compared with.
+// adapter's results are compared with.  The same types stand in for the real ones when the reference's OWN src/matcher.cpp is
+// compiled in place (oracle/Makefile, _ref/libmatcherref.so; myslam/keyframe.h and myslam/mappoint.h in this directory
+// shadow the reference's headers), which is the stronger checker of the two.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -24,7 +26,15 @@ struct Vector3d {
   Vector3d operator/(double s) const { return Vector3d(d[0] / s, d[1] / s, d[2] / s); }
   double dot(const Vector3d& o) const { return d[0] * o.d[0] + d[1] * o.d[1] + d[2] * o.d[2]; }
   double norm() const { return std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]); }
+  inline struct RowVector3d transpose() const;
 };
+struct Matrix3d;
+struct RowVector3d {                                  // p.transpose(): only what (p1.transpose() * F12).transpose() needs
+  double d[3];
+  inline RowVector3d operator*(const Matrix3d& M) const;
+  Vector3d transpose() const { return Vector3d(d[0], d[1], d[2]); }
+};
+inline RowVector3d transposeOf(const Vector3d& v) { RowVector3d r; r.d[0] = v[0]; r.d[1] = v[1]; r.d[2] = v[2]; return r; }
 struct Matrix3d {                                     // the slice of Eigen::Matrix3d the Sim3 searches use
   double m[9];
   double operator()(int r, int c) const { return m[r * 3 + c]; }
@@ -40,6 +50,13 @@ struct Vector2d {
   Vector2d(double x, double y) { d[0] = x; d[1] = y; }
   double operator[](int i) const { return d[i]; }
 };
+
+inline RowVector3d RowVector3d::operator*(const Matrix3d& M) const {      // Eigen evaluates the 3-term sums left to right
+  RowVector3d r;
+  for (int j = 0; j < 3; ++j) r.d[j] = d[0] * M(0, j) + d[1] * M(1, j) + d[2] * M(2, j);
+  return r;
+}
+inline RowVector3d Vector3d::transpose() const { return transposeOf(*this); }
 
 // rigid transform x -> R x + t (what Sophus::SE3 provides to the matcher: operator*, inverse, translation)
 struct SE3 {

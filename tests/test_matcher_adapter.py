@@ -1,7 +1,7 @@
 """include/orb_b200_matcher.hpp -- the reference's Matcher search signatures (include/myslam/matcher.h:16-37) over the C ABI.
 
 The header is a template over the reference's Frame / KeyFrame / MapPoint types; here it is instantiated with stand-ins
-that carry exactly the members matcher.cpp touches (tests/tools/myslam_stub.hpp).  tests/tools/matcher_adapter_check.cpp
+that carry exactly the members matcher.cpp touches (oracle/compat_myslam/myslam_stub.hpp).  tests/tools/matcher_adapter_check.cpp
 builds two identical object graphs, runs a loop-for-loop CPU statement of the reference functions on one and the adapter on
 the other, and compares the `mappoints_` / `mappointMatches` vectors pointer by pointer plus the returned counts.
 
@@ -16,7 +16,11 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOOLS = os.path.join(ROOT, "tests", "tools")
-INC = ["-I" + os.path.join(ROOT, "oracle", "compat"), "-I" + os.path.join(ROOT, "include"), "-I" + TOOLS]
+INC = ["-I" + os.path.join(ROOT, "oracle", "compat_myslam"), "-I" + os.path.join(ROOT, "oracle", "compat"),
+       "-I" + os.path.join(ROOT, "include"), "-I" + TOOLS]
+REF_LIB_DIR = os.path.join(ROOT, "oracle", "_ref")
+HAVE_REF_MATCHER = os.path.exists(os.path.join(REF_LIB_DIR, "libmatcherref.so")) or os.path.exists("/root/reference/src/matcher.cpp")
+REF_LINK = ["-DREF_MATCHER", "-L" + REF_LIB_DIR, "-lmatcherref", "-Wl,-rpath," + REF_LIB_DIR]
 
 
 def _build():
@@ -46,12 +50,31 @@ def test_matcher_adapter_host_logic_on_port(tmp_path):
         assert "all comparisons identical" in out and "DIFFERENT" not in out, (seed, out)
 
 
-def _link_product(tmp_path):
+@pytest.mark.skipif(not HAVE_REF_MATCHER, reason="oracle/_ref/libmatcherref.so not built and /root/reference absent")
+def test_port_behind_adapter_equals_reference_matcher_cpp(tmp_path):
+    """The checker is the reference's OWN src/matcher.cpp, compiled in place against the stand-in object types
+    (oracle/Makefile -> oracle/_ref/libmatcherref.so): all eleven Matcher entry points, 41 scene families x 4 rounds.
+    This is what pins the matcher part of the oracle port to the reference itself."""
     _build()
-    exe = str(tmp_path / "mcheck")
+    exe = str(tmp_path / "mcheck_real")
+    odir = os.path.join(ROOT, "oracle")
+    _run(["g++", "-std=c++11", "-O1"] + INC + [os.path.join(TOOLS, "matcher_adapter_check.cpp"),
+                                               os.path.join(TOOLS, "cabi_on_port.cpp"), "-L" + odir, "-lorbport",
+                                               "-Wl,-rpath," + odir] + REF_LINK + ["-o", exe])
+    out = _run([exe])
+    assert "checker: the reference's own src/matcher.cpp" in out
+    assert "all comparisons identical" in out and out.count(" same") == 49 and "DIFFERENT" not in out, out
+    for seed in range(1000, 1000 + 40 * 16, 16):
+        out = _run([exe, str(seed)])
+        assert "all comparisons identical" in out and "DIFFERENT" not in out, (seed, out)
+
+
+def _link_product(tmp_path, real_reference=False):
+    _build()
+    exe = str(tmp_path / ("mcheck_real" if real_reference else "mcheck"))
     ldir = os.path.join(ROOT, "vo_slam_test_b200", "lib")
     _run(["g++", "-std=c++11", "-O1"] + INC + [os.path.join(TOOLS, "matcher_adapter_check.cpp"), "-L" + ldir, "-lvoslam_b200",
-                                               "-Wl,-rpath," + ldir, "-o", exe])
+                                               "-Wl,-rpath," + ldir] + (REF_LINK if real_reference else []) + ["-o", exe])
     return exe
 
 
@@ -67,4 +90,18 @@ def test_matcher_adapter_on_gpu(tmp_path):
     if os.path.isdir(log_dir):                      # keep the program's report (incl. its timing lines) next to the other GPU logs
         with open(os.path.join(log_dir, "matcher_adapter_gpu.log"), "w") as f:
             f.write(out)
+    assert "all comparisons identical" in out and out.count(" same") == 49 and "DIFFERENT" not in out, out
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not HAVE_REF_MATCHER, reason="oracle/_ref/libmatcherref.so not built and /root/reference absent")
+def test_matcher_adapter_on_gpu_against_reference_matcher_cpp(tmp_path):
+    """The CUDA library behind the adapters against the reference's own src/matcher.cpp (prebuilt oracle/_ref/libmatcherref.so
+    travels to the GPU box; the program itself needs none of the reference's headers)."""
+    try:
+        exe = _link_product(tmp_path, real_reference=True)
+    except AssertionError as e:                      # a box that cannot link the prebuilt checker is not a parity failure
+        pytest.skip("could not link against libmatcherref.so: %s" % str(e)[-200:])
+    out = _run([exe])
+    assert "checker: the reference's own src/matcher.cpp" in out
     assert "all comparisons identical" in out and out.count(" same") == 49 and "DIFFERENT" not in out, out

@@ -1,8 +1,8 @@
 // tests/tools/matcher_adapter_check.cpp -- compile/link check of include/orb_b200_matcher.hpp against stand-in Frame /
 // KeyFrame / MapPoint types, and (with a GPU) a run-time comparison with a CPU statement of the reference's own loops
-// (tests/tools/myslam_stub.hpp, RefMatcher) on identical object graphs: the mappoints_ / mappointMatches vectors written by
+// (oracle/compat_myslam/myslam_stub.hpp, RefMatcher) on identical object graphs: the mappoints_ / mappointMatches vectors written by
 // the two must be the same pointers, and the returned match counts equal.
-//   g++ -std=c++11 -Ioracle/compat -Iinclude tests/tools/matcher_adapter_check.cpp -Lvo_slam_test_b200/lib -lvoslam_b200 -o /tmp/mcheck
+//   g++ -std=c++11 -Ioracle/compat_myslam -Ioracle/compat -Iinclude tests/tools/matcher_adapter_check.cpp -Lvo_slam_test_b200/lib -lvoslam_b200 -o /tmp/mcheck
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -14,6 +14,42 @@
 #include "orb_b200_matcher.hpp"
 
 using namespace myslam;
+
+#ifdef REF_MATCHER
+// The reference's OWN src/matcher.cpp, compiled in place against these stand-in types (oracle/Makefile ->
+// oracle/_ref/libmatcherref.so, entry points in oracle/ref_matcher_wrap.cpp), plays the checker instead of RefMatcher.
+int refm_searchByProjection_FF(float ratio, Frame* c, Frame* l, float radius, bool checkRot);
+int refm_searchByProjection_FK(float ratio, Frame* c, KeyFrame* kf, float radius, float distTh, const std::set<MapPoint*>& found, bool checkRot);
+int refm_searchByProjection_local(float ratio, Frame* f, const std::vector<MapPoint*>& mps, float th);
+int refm_searchByProjection_sim3(float ratio, KeyFrame* kf, Sim3& Scw, std::vector<MapPoint*>& loopPts, std::vector<MapPoint*>& matchPts, int th);
+int refm_searchByBoW_KF(float ratio, KeyFrame* kf, Frame* f, std::vector<MapPoint*>& out, bool checkRot);
+int refm_searchByBoW_KK(float ratio, KeyFrame* k1, KeyFrame* k2, std::vector<MapPoint*>& out, bool checkRot);
+int refm_searchBySim3(float ratio, KeyFrame* k1, KeyFrame* k2, std::vector<MapPoint*>& m12, Sim3& S12, float th);
+int refm_searchForTriangulation(float ratio, KeyFrame* k1, KeyFrame* k2, std::vector<std::pair<int, int> >& idxs, Matrix3d& F12, bool checkRot);
+int refm_fuseMapPoints(float ratio, KeyFrame* kf, std::vector<MapPoint*>& mps, const float& th);
+int refm_fuseByPose(float ratio, KeyFrame* kf, Sim3& Scw, std::vector<MapPoint*>& loopPts, std::vector<MapPoint*>& replacePts, float th);
+int refm_computeDistance(const cv::Mat& a, const cv::Mat& b);
+struct Checker {
+  float r;
+  explicit Checker(float ratio) : r(ratio) {}
+  static const char* name() { return "the reference's own src/matcher.cpp (compiled in place)"; }
+  int searchByProjection(Frame* c, Frame* l, float radius, bool rot) { return refm_searchByProjection_FF(r, c, l, radius, rot); }
+  int searchByProjection(Frame* c, KeyFrame* kf, float radius, float dt, const std::set<MapPoint*>& f, bool rot) { return refm_searchByProjection_FK(r, c, kf, radius, dt, f, rot); }
+  int searchByProjection(Frame* f, const std::vector<MapPoint*>& mps, float th) { return refm_searchByProjection_local(r, f, mps, th); }
+  int searchByProjection(KeyFrame* kf, Sim3& S, std::vector<MapPoint*>& lp, std::vector<MapPoint*>& mp, int th) { return refm_searchByProjection_sim3(r, kf, S, lp, mp, th); }
+  int searchByBoW(KeyFrame* kf, Frame* f, KeyFrame* kf2, std::vector<MapPoint*>& out, bool rot) { return kf2 ? refm_searchByBoW_KK(r, kf, kf2, out, rot) : refm_searchByBoW_KF(r, kf, f, out, rot); }
+  int searchBySim3(KeyFrame* k1, KeyFrame* k2, std::vector<MapPoint*>& m12, Sim3& S, float th) { return refm_searchBySim3(r, k1, k2, m12, S, th); }
+  int searchForTriangulation(KeyFrame* k1, KeyFrame* k2, std::vector<std::pair<int, int> >& idxs, Matrix3d& F, bool rot) { return refm_searchForTriangulation(r, k1, k2, idxs, F, rot); }
+  int fuseMapPoints(KeyFrame* kf, std::vector<MapPoint*>& mps, const float& th) { return refm_fuseMapPoints(r, kf, mps, th); }
+  int fuseByPose(KeyFrame* kf, Sim3& S, std::vector<MapPoint*>& lp, std::vector<MapPoint*>& rp, float th) { return refm_fuseByPose(r, kf, S, lp, rp, th); }
+  static int computeDistance(const cv::Mat& a, const cv::Mat& b) { return refm_computeDistance(a, b); }
+};
+#else
+struct Checker : RefMatcher {
+  explicit Checker(float ratio) : RefMatcher(ratio) {}
+  static const char* name() { return "the object-walking restatement (RefMatcher)"; }
+};
+#endif
 
 static unsigned g_seed = 1;
 static unsigned rnd() { g_seed = g_seed * 1664525u + 1013904223u; return g_seed >> 8; }
@@ -138,13 +174,14 @@ int main(int argc, char** argv) {
   orbx_device_count(&ndev);
   if (ndev == 0) { std::printf("matcher adapter links; no CUDA device -> compute skipped\n"); return 0; }
   typedef myslam_b200::MatcherT<Frame, KeyFrame, MapPoint> Matcher;
+  std::printf("checker: %s\n", Checker::name());
   for (int round = 0; round < 4; ++round) {
     const bool fwd = round == 1, checkRot = round != 2;
     const float ratio = round == 3 ? 0.9f : 0.7f;
     Scene a, b;                                   // identical object graphs: a for the reference loops, b for the adapter
     buildScene(a, seedBase + round, fwd);
     buildScene(b, seedBase + round, fwd);
-    RefMatcher ref(ratio);
+    Checker ref(ratio);
     Matcher gpu(ratio);
     std::printf("round %d (forward %d, checkRot %d, ratio %.2f)\n", round, (int)fwd, (int)checkRot, ratio);
 
@@ -366,7 +403,7 @@ int main(int argc, char** argv) {
     }
 
     // 5. computeDistance
-    const int d0 = RefMatcher::computeDistance(a.cur.descriptors_.row(3), a.kf1.descriptors_.row(3));
+    const int d0 = Checker::computeDistance(a.cur.descriptors_.row(3), a.kf1.descriptors_.row(3));
     const int d1 = Matcher::computeDistance(b.cur.descriptors_.row(3), b.kf1.descriptors_.row(3));
     expect(d0 == d1, "computeDistance(Mat, Mat)");
   }
@@ -452,7 +489,7 @@ int main(int argc, char** argv) {
     buildScene(a, 5u, false);
     typedef myslam_b200::MatcherT<Frame, KeyFrame, MapPoint> M;
     M gpu(0.7f);
-    RefMatcher ref(0.7f);
+    Checker ref(0.7f);
     Frame none; none.camera_ = &a.cam; none.scaleFactors_ = a.cur.scaleFactors_; none.xMax_ = 640; none.yMax_ = 480;
     none.gridPerPixelWidth_ = 0.1f; none.gridPerPixelHeight_ = 0.1f;
     KeyFrame knone; knone.camera_ = &a.cam; knone.scaleFactors_ = a.cur.scaleFactors_; knone.assignFeaturesToGrid();
@@ -485,7 +522,7 @@ int main(int argc, char** argv) {
     buildScene(a, 4242u, false);
     typedef myslam_b200::MatcherT<Frame, KeyFrame, MapPoint> M;
     M gpu(0.7f);
-    RefMatcher ref(0.7f);
+    Checker ref(0.7f);
     const int reps = 20;
     double tr[3] = {0, 0, 0}, tg[3] = {0, 0, 0};
     std::vector<MapPoint*> out;
