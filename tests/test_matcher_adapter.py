@@ -28,6 +28,9 @@ def _build():
     if not (os.path.exists(os.path.join(ROOT, "vo_slam_test_b200", "lib", "libvoslam_b200.so"))
             and os.path.exists(os.path.join(ROOT, "oracle", "liborbport.so"))):
         g.build()
+    if os.path.exists("/root/reference/src/matcher.cpp") and not os.path.exists(os.path.join(REF_LIB_DIR, "libmatcherref.so")):
+        import oracle
+        oracle.build()
 
 
 def _run(cmd):
