@@ -6,6 +6,9 @@ CPU oracles for the ORB front-end hot path of guisongchen/vo_slam_test:
 * ``Ref``   -- the reference's OWN ``src/ORBextractor.cpp`` compiled in place against oracle/compat
               (oracle/_ref/liborbref*.so; built only where /root/reference exists, prebuilt files
               travel to the GPU box).
+* oracle/_ref/libmatcherref.so -- the reference's OWN ``src/matcher.cpp`` compiled in place against its own
+              matcher.h and the stand-in object types of oracle/compat_myslam; linked by the C++ check program
+              of tests/test_matcher_adapter.py (not loaded from Python).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
 legs may import this package.  The product (``vo_slam_test_b200``) never does.
