@@ -13,10 +13,12 @@
 // include/myslam/matcher.h, with Frame / KeyFrame / MapPoint / SE3 / Sim3 / FeatureVector replaced by the stand-in types of
 // oracle/compat_myslam because Eigen, Sophus and DBoW3 are not installed); tests/test_matcher_adapter.py asserts that all
 // eleven Matcher entry points, run on identical object graphs, leave the same pointers and counts as this port behind the
-// C++ adapters (164 scenes in the CPU suite).  What stays PARITY UNPINNED by reference output: the small helpers the
-// stand-in types restate from frame.cpp / keyframe.cpp / mappoint.cpp / camera.cpp (getFeaturesInArea, isInImg,
-// predictScale, camera2pixel), MapPoint::computeDescriptor and the Frame post-processing -- their translation units need
-// the missing libraries and the reference ships no tests or golden vectors; cv::undistortPoints is pinned against cv2.
+// C++ adapters (164 scenes in the CPU suite).  The small helpers underneath -- Frame::assignFeaturesToGrid / getFeaturesInArea /
+// findDepth, KeyFrame::getFeaturesInArea / isInImg, MapPoint::predictScale / computeDescriptor, Camera::camera2pixel -- are
+// pinned the same way: their line ranges are compiled in place (oracle/ref_helpers_wrap.cpp -> _ref/librefhelpers.so) and
+// held against this port and against the stand-in types (tests/test_oracle_helpers_vs_reference.py).  Only
+// Frame::undistortKeyPoints is not run as reference code: it is a loop around cv::undistortPoints, whose arithmetic is pinned
+// against cv2 4.13.0 (tests/golden/cv2_undistort.npz).
 //
 // Reference lines followed:
 //   ctor tables            ORBextractor.cpp:414-476          -> port_tables()
