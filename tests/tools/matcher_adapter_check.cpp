@@ -162,6 +162,13 @@ static void buildScene(Scene& s, unsigned seed, bool moveForward) {
     if (rnd() % 7 != 0) c.featVec_[(unsigned)((i * 2654435761u) >> 26) + (rnd() % 13 == 0 ? 200u : 0u)].push_back((unsigned)i);
 }
 
+// Fingerprint of what the CHECKER wrote (indices into the scene's point storage): goes into the printed report so that
+// tests/golden/matcher_reference_counts.txt carries the reference's assignments, not only its counts.
+static unsigned long long fingerprint(const std::vector<MapPoint*>& v, const std::vector<MapPoint>& store) {
+  unsigned long long h = 1469598103934665603ull;
+  for (size_t i = 0; i < v.size(); ++i) { h ^= (unsigned long long)(v[i] ? (v[i] - &store[0]) + 1 : 0); h *= 1099511628211ull; }
+  return h;
+}
 static int fails = 0;
 static void expect(bool ok, const char* what) {
   std::printf("  %-58s %s\n", what, ok ? "same" : "DIFFERENT");
@@ -175,6 +182,14 @@ int main(int argc, char** argv) {
   if (ndev == 0) { std::printf("matcher adapter links; no CUDA device -> compute skipped\n"); return 0; }
   typedef myslam_b200::MatcherT<Frame, KeyFrame, MapPoint> Matcher;
   std::printf("checker: %s\n", Checker::name());
+  {  // the scenes are built with libm calls: a machine whose libm rounds these differently builds (slightly) different scenes
+    volatile double x = 0.02, y = 0.021, z = 1.7;
+    volatile float w = 2.5f;
+    const double sig[4] = {std::cos(x), std::sin(y), std::log(z), (double)std::pow(1.2f, (float)w)};
+    unsigned long long h = 1469598103934665603ull;
+    for (int i = 0; i < 4; ++i) { unsigned long long b; std::memcpy(&b, &sig[i], 8); h ^= b; h *= 1099511628211ull; }
+    std::printf("libm signature %016llx\n", h);
+  }
   for (int round = 0; round < 4; ++round) {
     const bool fwd = round == 1, checkRot = round != 2;
     const float ratio = round == 3 ? 0.9f : 0.7f;
@@ -195,7 +210,7 @@ int main(int argc, char** argv) {
       const long ib = cb.mappoints_[i] ? (long)(cb.mappoints_[i] - &b.points[0]) : -1;
       same = ia == ib;
     }
-    std::printf("  searchByProjection(Frame*,Frame*): %d matches\n", na);
+    std::printf("  searchByProjection(Frame*,Frame*): %d matches [%016llx]\n", na, fingerprint(ca.mappoints_, a.points));
     expect(same && na > 50, "searchByProjection(Frame*, Frame*, radius, checkRot)");
 
     // 2. local-map projection search
@@ -208,7 +223,7 @@ int main(int argc, char** argv) {
       const long ib = cb.mappoints_[i] ? (long)(cb.mappoints_[i] - &b.points[0]) : -1;
       same = ia == ib;
     }
-    std::printf("  searchByProjection(Frame*,vector<MapPoint*>): %d matches\n", na);
+    std::printf("  searchByProjection(Frame*,vector<MapPoint*>): %d matches [%016llx]\n", na, fingerprint(ca.mappoints_, a.points));
     expect(same && na > 50, "searchByProjection(Frame*, vector<MapPoint*>&, thRadius)");
 
     // 2b. relocalisation projection search against a key frame (some of its points already "found")
@@ -230,7 +245,7 @@ int main(int argc, char** argv) {
         const long ib = cb.mappoints_[i] ? (long)(cb.mappoints_[i] - &b.points[0]) : -1;
         same = ia == ib;
       }
-      std::printf("  searchByProjection(Frame*,KeyFrame*): %d matches\n", na);
+      std::printf("  searchByProjection(Frame*,KeyFrame*): %d matches [%016llx]\n", na, fingerprint(ca.mappoints_, a.points));
       expect(same && na > 50, "searchByProjection(Frame*, KeyFrame*, radius, distTh, found, rot)");
     }
 
@@ -248,7 +263,7 @@ int main(int argc, char** argv) {
       same = na == nb;
       for (size_t i = 0; i < ma2.size() && same; ++i)
         same = (ma2[i] ? (long)(ma2[i] - &a.points[0]) : -1) == (mb2[i] ? (long)(mb2[i] - &b.points[0]) : -1);
-      std::printf("  searchByProjection(KeyFrame*,Sim3&): %d matches\n", na);
+      std::printf("  searchByProjection(KeyFrame*,Sim3&): %d matches [%016llx]\n", na, fingerprint(ma2, a.points));
       expect(same && na > 10, "searchByProjection(KeyFrame*, Sim3&, loopPts, matchPts, th)");
     }
 
@@ -291,7 +306,7 @@ int main(int argc, char** argv) {
       same = na == nb;
       for (size_t i = 0; i < m12a.size() && same; ++i)
         same = (m12a[i] ? (long)(m12a[i] - &a.points[0]) : -1) == (m12b[i] ? (long)(m12b[i] - &b.points[0]) : -1);
-      std::printf("  searchBySim3(KeyFrame*,KeyFrame*): %d matches\n", na);
+      std::printf("  searchBySim3(KeyFrame*,KeyFrame*): %d matches [%016llx]\n", na, fingerprint(m12a, a.points));
       expect(same && na > 50, "searchBySim3(KeyFrame*, KeyFrame*, matches12, S12, th)");
       for (int i = 0; i < 900; ++i) { a.points[i].observedKFs_.clear(); b.points[i].observedKFs_.clear(); }   // ka2 / kb2 die here
     }
@@ -303,7 +318,7 @@ int main(int argc, char** argv) {
     same = na == nb && ma.size() == mb.size();
     for (size_t i = 0; i < ma.size() && same; ++i)
       same = (ma[i] ? (long)(ma[i] - &a.points[0]) : -1) == (mb[i] ? (long)(mb[i] - &b.points[0]) : -1);
-    std::printf("  searchByBoW(KeyFrame*,Frame*): %d matches\n", na);
+    std::printf("  searchByBoW(KeyFrame*,Frame*): %d matches [%016llx]\n", na, fingerprint(ma, a.points));
     expect(same && na > 50, "searchByBoW(KeyFrame*, Frame*, matches, checkRot)");
 
     // 4. BoW search key frame -> key frame
@@ -312,7 +327,7 @@ int main(int argc, char** argv) {
     same = na == nb && ma.size() == mb.size();
     for (size_t i = 0; i < ma.size() && same; ++i)
       same = (ma[i] ? (long)(ma[i] - &a.points[0]) : -1) == (mb[i] ? (long)(mb[i] - &b.points[0]) : -1);
-    std::printf("  searchByBoW(KeyFrame*,KeyFrame*): %d matches\n", na);
+    std::printf("  searchByBoW(KeyFrame*,KeyFrame*): %d matches [%016llx]\n", na, fingerprint(ma, a.points));
     expect(same && na > 20, "searchByBoW(KeyFrame*, KeyFrame*, matches, checkRot)");
 
     // 4b. searchForTriangulation: key frame 2 a little to the right of key frame 1, F12 of that stereo-like pair
@@ -339,7 +354,9 @@ int main(int argc, char** argv) {
       na = ref.searchForTriangulation(&ka1, &ka2, pa, F, checkRot);
       nb = gpu.searchForTriangulation(&kb1, &kb2, pb, F, checkRot);
       same = na == nb && pa == pb;
-      std::printf("  searchForTriangulation: %d matches\n", na);
+      unsigned long long ht = 1469598103934665603ull;
+      for (size_t i = 0; i < pa.size(); ++i) { ht ^= (unsigned long long)pa[i].first * 4096u + (unsigned long long)pa[i].second; ht *= 1099511628211ull; }
+      std::printf("  searchForTriangulation: %d matches [%016llx]\n", na, ht);
       expect(same && na > 60, "searchForTriangulation(KeyFrame*, KeyFrame*, idxs, F12, checkRot)");
     }
 
@@ -397,7 +414,7 @@ int main(int argc, char** argv) {
                a.points[i].observedKFs_.size() == b.points[i].observedKFs_.size();
         nbad += a.points[i].badFlag_;
       }
-      std::printf("  %s: %d fused (%d bad points afterwards)\n", pass ? "fuseByPose" : "fuseMapPoints", na, nbad);
+      std::printf("  %s: %d fused (%d bad points afterwards) [%016llx %016llx]\n", pass ? "fuseByPose" : "fuseMapPoints", na, nbad, fingerprint(ka.mappoints_, a.points), fingerprint(ra, a.points));
       expect(same && na > 50, pass ? "fuseByPose(KeyFrame*, Sim3&, loopPts, replacePts, th)" : "fuseMapPoints(KeyFrame*, mappoints, threshold)");
       for (size_t i = 0; i < a.points.size(); ++i) { a.points[i].observedKFs_.clear(); b.points[i].observedKFs_.clear(); }
     }
