@@ -113,13 +113,30 @@ def bind_to_gpu_numa_node(index):
         pass
 
 
+_CPU_MATCHER = None
+
+
+def cpu_matcher(port):
+    """The matcher leg of the CPU arm: the reference's own computeDistance (matcher.cpp compiled in place, oracle/_ref) inside its
+    matching loop; the CPU port of the same loop where that library is absent."""
+    global _CPU_MATCHER
+    if _CPU_MATCHER is None:
+        import oracle
+        try:
+            _CPU_MATCHER = oracle.RefMatcher()
+        except Exception:
+            _CPU_MATCHER = port
+    return _CPU_MATCHER
+
+
 def cpu_reference_step(imgs, cores, Ref, port):
     """The reference's own extractor (oracle/_ref, one instance per core over disjoint frames, ORBextractor.h:85 is
-    stateful) + the reference's matcher loop (CPU port, threaded over queries) on `imgs`.  Returns seconds."""
+    stateful) + the reference's matcher loop (threaded over queries) on `imgs`.  Returns seconds."""
+    m = cpu_matcher(port)
     t0 = time.perf_counter()
     kps, desc, cnt = Ref.extract_batch(imgs, cores, keep_outputs=True)
     for f in range(len(imgs) - 1):
-        port.knn2(desc[f, :cnt[f]], desc[f + 1, :cnt[f + 1]], TH_LOW, RATIO, nthreads=cores)
+        m.knn2(desc[f, :cnt[f]], desc[f + 1, :cnt[f + 1]], TH_LOW, RATIO, nthreads=cores)
     return time.perf_counter() - t0
 
 

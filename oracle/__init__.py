@@ -488,3 +488,24 @@ def camera_struct(cam):
     cs.ndist = len(d)
     cs.xmin, cs.xmax, cs.ymin, cs.ymax = cam["bounds"]
     return cs
+
+
+class RefMatcher:
+    """The reference's OWN distance function (src/matcher.cpp:1240-1256, compiled in place: oracle/_ref/libmatcherref.so) inside
+    the reference's matching loop shape (matcher.cpp:481-507), threaded over queries: the matcher leg of bench.py's CPU arm."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libmatcherref.so")
+        if not os.path.exists(path):
+            build()
+        self.lib = C.CDLL(path)          # raises OSError where the reference was never compiled (callers fall back to the port)
+        self.lib.refm_knn2.restype = None
+        self.lib.refm_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int]
+
+    def knn2(self, q, t, th=50, ratio=0.7, nthreads=1):
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        Q = len(q)
+        idx = np.empty(Q, np.int32); d1 = np.empty(Q, np.int32); d2 = np.empty(Q, np.int32); ok = np.empty(Q, np.uint8)
+        self.lib.refm_knn2(_ptr(q), Q, _ptr(t), len(t), th, ratio, _ptr(idx), _ptr(d1), _ptr(d2), _ptr(ok), nthreads)
+        return idx, d1, d2, ok

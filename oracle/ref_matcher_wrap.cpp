@@ -39,3 +39,30 @@ int refm_fuseByPose(float ratio, KeyFrame* kf, Sim3& Scw, std::vector<MapPoint*>
   Matcher m(ratio); return m.fuseByPose(kf, Scw, loopPts, replacePts, th);
 }
 int refm_computeDistance(const cv::Mat& a, const cv::Mat& b) { return Matcher::computeDistance(a, b); }
+
+// Frame-to-frame top-2 + ratio test the way the reference's matching loops do it (matcher.cpp:481-507: a Mat row header per
+// descriptor, Matcher::computeDistance per pair, strict '<' so the first index wins), threaded over queries for the CPU
+// timing baseline of bench.py.  The distance function is the reference's own (matcher.cpp:1240-1256).
+#include <thread>
+extern "C" void refm_knn2(const uint8_t* q, int Q, const uint8_t* t, int M, int th, float ratio, int32_t* idx, int32_t* d1, int32_t* d2,
+                          uint8_t* ok, int nthreads) {
+  const cv::Mat qm(Q, 32, CV_8UC1, (void*)q, 32), tm(M, 32, CV_8UC1, (void*)t, 32);
+  auto work = [&](int q0, int q1) {
+    for (int i = q0; i < q1; ++i) {
+      const cv::Mat qd = qm.row(i);
+      int best1 = 256, best2 = 256, bi = -1;
+      for (int j = 0; j < M; ++j) {
+        const cv::Mat td = tm.row(j);
+        const int dist = Matcher::computeDistance(qd, td);
+        if (dist < best1) { best2 = best1; best1 = dist; bi = j; }
+        else if (dist < best2) best2 = dist;
+      }
+      idx[i] = bi; d1[i] = best1; d2[i] = best2;
+      ok[i] = (best1 <= th && static_cast<float>(best1) < ratio * static_cast<float>(best2)) ? 1 : 0;
+    }
+  };
+  if (nthreads <= 1) { work(0, Q); return; }
+  std::vector<std::thread> pool;
+  for (int k = 0; k < nthreads; ++k) pool.emplace_back(work, (int)((long long)Q * k / nthreads), (int)((long long)Q * (k + 1) / nthreads));
+  for (auto& x : pool) x.join();
+}
