@@ -16,9 +16,9 @@
 // C++ adapters (164 scenes in the CPU suite).  The small helpers underneath -- Frame::assignFeaturesToGrid / getFeaturesInArea /
 // findDepth, KeyFrame::getFeaturesInArea / isInImg, MapPoint::predictScale / computeDescriptor, Camera::camera2pixel -- are
 // pinned the same way: their line ranges are compiled in place (oracle/ref_helpers_wrap.cpp -> _ref/librefhelpers.so) and
-// held against this port and against the stand-in types (tests/test_oracle_helpers_vs_reference.py).  Only
-// Frame::undistortKeyPoints is not run as reference code: it is a loop around cv::undistortPoints, whose arithmetic is pinned
-// against cv2 4.13.0 (tests/golden/cv2_undistort.npz).
+// held against this port and against the stand-in types (tests/test_oracle_helpers_vs_reference.py), Frame::undistortKeyPoints
+// included (its loop is the reference's; the cv::undistortPoints underneath is the restatement pinned against cv2 4.13.0,
+// tests/golden/cv2_undistort.npz).
 //
 // Reference lines followed:
 //   ctor tables            ORBextractor.cpp:414-476          -> port_tables()

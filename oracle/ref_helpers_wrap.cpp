@@ -4,6 +4,7 @@
 // but the helpers the matcher path depends on are self-contained member functions.  The Makefile pulls exactly these line
 // ranges out of the read-only reference tree at build time into a temporary file (REFSRC_GENERATED, never stored in the
 // repo) and compiles them here, unmodified, as members of the minimal classes below (the reference's member names):
+//   frame.cpp:36-70     Frame::undistortKeyPoints (separately, REFSRC_GENERATED_U: it needs a float Mat, see below)
 //   frame.cpp:72-97     Frame::assignFeaturesToGrid, Frame::postionInGrad
 //   frame.cpp:108-133   Frame::findDepth
 //   frame.cpp:199-247   Frame::getFeaturesInArea
@@ -87,6 +88,65 @@ struct MapPoint {
 // only the static member's symbol is used, which is why a one-line declaration of the class is enough here)
 namespace myslam { class Matcher { public: static int computeDistance(const cv::Mat& desp1, const cv::Mat& desp2); }; }
 int refsrc::Matcher::computeDistance(const Mat& a, const Mat& b) { return myslam::Matcher::computeDistance(a, b); }
+
+// ---- Frame::undistortKeyPoints (frame.cpp:36-70), the reference's own loop around cv::undistortPoints -------------------------
+// It needs a CV_32F matrix with reshape(), which the byte-only cv::Mat of oracle/compat does not have, so this block brings its
+// own minimal float Mat and a cv::undistortPoints built on cvprims.h (the arithmetic pinned against cv2 4.13.0).
+#include <memory>
+namespace refsrc_u {
+using namespace std;
+struct Mat {
+  int rows, cols, cn;
+  std::shared_ptr<std::vector<float> > buf;
+  Mat() : rows(0), cols(0), cn(1) {}
+  Mat(int r, int c, int /*CV_32F*/) : rows(r), cols(c), cn(1), buf(new std::vector<float>((size_t)r * c, 0.f)) {}
+  template <typename T> T& at(int i) { return (*buf)[i]; }
+  template <typename T> const T& at(int i) const { return (*buf)[i]; }
+  template <typename T> T& at(int i, int j) { return (*buf)[((size_t)i * cols + j) * cn]; }
+  Mat reshape(int newCn) const {                       // same data, rows kept: N x 2 x 1 <-> N x 1 x 2 (frame.cpp:55-59)
+    Mat m = *this;
+    m.cols = cols * cn / newCn; m.cn = newCn;
+    return m;
+  }
+};
+namespace cv {
+using ::cv::KeyPoint;
+inline void undistortPoints(const Mat& src, Mat dst, const Mat& K, const Mat& D, const Mat& /*R*/, const Mat& P) {
+  double k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int nd = D.rows * D.cols;
+  for (int i = 0; i < nd && i < 8; ++i) k[i] = (double)D.at<float>(i);
+  for (int i = 0; i < src.rows; ++i) {
+    float u, v;
+    cvp::undistort_point_k((*src.buf)[2 * i], (*src.buf)[2 * i + 1], K.at<float>(0), K.at<float>(4), K.at<float>(2), K.at<float>(5), k, &u, &v);
+    (void)P;                                           // the call site passes P = K (frame.cpp:58), which undistort_point_k applies
+    (*dst.buf)[2 * i] = u; (*dst.buf)[2 * i + 1] = v;
+  }
+}
+}  // namespace cv
+struct Camera { Mat distCoef_, K_; };
+struct Frame {
+  Camera* camera_;
+  vector<cv::KeyPoint> keypoints_, unKeypoints_;
+  size_t N_;
+  void undistortKeyPoints();
+};
+#include REFSRC_GENERATED_U
+}  // namespace refsrc_u
+
+extern "C" void refh_undistort(const void* kps, int n, float fx, float fy, float cx, float cy, const float* dist, int ndist, void* unkps) {
+  refsrc_u::Camera cam;
+  cam.K_ = refsrc_u::Mat(3, 3, CV_32F);
+  const float K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) cam.K_.at<float>(i) = K[i];
+  cam.distCoef_ = refsrc_u::Mat(ndist, 1, CV_32F);
+  for (int i = 0; i < ndist; ++i) cam.distCoef_.at<float>(i) = dist[i];
+  refsrc_u::Frame f;
+  f.camera_ = &cam;
+  f.keypoints_.assign((const cv::KeyPoint*)kps, (const cv::KeyPoint*)kps + n);
+  f.N_ = n;
+  f.undistortKeyPoints();
+  std::memcpy(unkps, f.unKeypoints_.data(), sizeof(cv::KeyPoint) * (size_t)n);
+}
 
 using namespace refsrc;
 

@@ -4,7 +4,7 @@ frame.cpp, keyframe.cpp, mappoint.cpp and camera.cpp do not compile as a whole h
 the matcher path depends on are self-contained member functions.  oracle/Makefile pulls those line ranges out of the read-only
 reference tree at build time and compiles them, unmodified, inside oracle/ref_helpers_wrap.cpp
 (oracle/_ref/librefhelpers.so).  Here the oracle port's restatements are held against that code on random inputs:
-assignFeaturesToGrid + getFeaturesInArea (Frame and KeyFrame), findDepth, MapPoint::computeDescriptor."""
+assignFeaturesToGrid + getFeaturesInArea (Frame and KeyFrame), findDepth, undistortKeyPoints, MapPoint::computeDescriptor."""
 import ctypes as C
 import os
 
@@ -29,6 +29,7 @@ def ref():
     L.refh_features_in_area.argtypes = [vp, i32, f32, f32, f32, f32, vp, vp, vp, vp, vp, i32, vp, vp, i32]
     L.refh_find_depth.argtypes = [vp, vp, i32, vp, i32, i32, f32, vp, vp]
     L.refh_medoid.argtypes = [vp, vp, i32, vp]
+    L.refh_undistort.argtypes = [vp, i32, f32, f32, f32, f32, vp, i32, vp]
     return L
 
 
@@ -85,6 +86,23 @@ def test_find_depth_vs_reference(port, ref):
     ref.refh_find_depth(kps.ctypes.data, unx.ctypes.data, n, depth.ctypes.data, W, H, 40.0, d_ref.ctypes.data, ur_ref.ctypes.data)
     assert np.array_equal(dp, d_ref) and np.array_equal(ur, ur_ref)
     assert (d_ref > 0).sum() > n // 2 and (d_ref == -1).sum() > n // 10
+
+
+@pytest.mark.parametrize("dist", [[0.2624, -0.9531, -0.0054, 0.0026, 1.1633], [0.2312, -0.7849, -0.0033, -0.0001], [-0.28, 0.07, 0.0002, 0.00002],
+                                  [0.0, 0.3, 0.001, 0.001]])
+def test_undistort_keypoints_vs_reference(port, ref, dist):
+    """Frame::undistortKeyPoints (frame.cpp:36-70) itself -- the k1 == 0 shortcut, the N x 2 <-> N x 1 x 2 reshapes, the
+    float round trip -- around the cv2-pinned cv::undistortPoints arithmetic, against the port's frame_finish."""
+    rng = np.random.default_rng(3)
+    kps = _keypoints(rng, 2000, 640, 480, 0.0)
+    cam = dict(fx=517.3, fy=516.5, cx=318.6, cy=255.3, dist=dist, bf=40.0, bounds=(0.0, 640.0, 0.0, 480.0))
+    un, _, _, _, _ = port.frame_finish(kps, cam, None)
+    out = np.empty_like(kps)
+    d = np.asarray(dist, np.float32)
+    ref.refh_undistort(kps.ctypes.data, len(kps), 517.3, 516.5, 318.6, 255.3, d.ctypes.data, len(d), out.ctypes.data)
+    assert np.array_equal(un, out)
+    moved = int((out["x"] != kps["x"]).sum())
+    assert moved == 0 if dist[0] == 0.0 else moved > 1500
 
 
 def test_compute_descriptor_vs_reference(port, ref):
