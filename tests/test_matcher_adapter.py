@@ -8,6 +8,10 @@ the other, and compares the `mappoints_` / `mappointMatches` vectors pointer by 
 * not gpu: the C-ABI calls are served by the CPU oracle port (tests/tools/cabi_on_port.cpp) -> checks the adapter's host logic
   (gates, projection, flattening, replay of the writes) and, independently, the port against the object-walking statement.
 * gpu: the same program linked with libvoslam_b200.so -> the CUDA kernels behind the reference's signatures.
+
+Two checkers play the "reference" side: this repo's object-walking restatement (RefMatcher, always available) and the
+reference's OWN src/matcher.cpp compiled in place against the same stand-in types (-DREF_MATCHER, oracle/_ref/libmatcherref.so);
+what the latter returned on the fixed scenes is also committed as tests/golden/matcher_reference_results.txt.
 """
 import os
 import subprocess
