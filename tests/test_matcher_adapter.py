@@ -138,3 +138,23 @@ def test_report_equals_results_of_the_reference_matcher(tmp_path):
     if got[1] != want[1]:
         pytest.skip("this machine's libm rounds the scene set-up differently (%s vs %s): the fixed scenes are not reproduced" % (got[1], want[1]))
     assert got == want
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/include/myslam/matcher.h"), reason="needs the reference's own matcher.h")
+def test_integration_bodies_define_the_reference_matcher_abi(tmp_path):
+    """INTEGRATION.md section 2 in compiled form (tests/tools/matcher_oneliners.cpp): the replacement bodies, built against the
+    reference's OWN include/myslam/matcher.h, must define exactly the public member symbols that the reference's matcher.cpp
+    defines (same mangled names = a link-level drop-in for Tracking / LocalMapping / LoopClosing)."""
+    _build()
+    obj = str(tmp_path / "oneliners.o")
+    _run(["g++", "-std=c++11", "-Wall", "-Werror", "-c"] + INC + ["-I/root/reference/include", os.path.join(TOOLS, "matcher_oneliners.cpp"),
+                                                                 "-o", obj])
+
+    def members(path, dynamic):
+        out = _run(["nm", "-D" if dynamic else "-g", "--defined-only", path])
+        return {l.split()[-1] for l in out.splitlines() if "N6myslam7Matcher" in l and " T " in l}
+    ours = members(obj, False)
+    theirs = members(os.path.join(REF_LIB_DIR, "libmatcherref.so"), True)
+    internal = {s for s in theirs if "computeThreeMax" in s or "checkEpipolarConstrain" in s}     # protected helpers (matcher.h:39-42)
+    assert len(theirs - internal) >= 12
+    assert ours == theirs - internal, (sorted(ours ^ (theirs - internal)))
