@@ -44,6 +44,9 @@ class ORBextractor {
                   cv::OutputArray _descriptors) {
     if (_image.empty()) return;
     cv::Mat image = _image.getMat();
+    // the reference asserts image.type() == CV_8UC1 (ORBextractor.cpp:1058); a multi-channel or non-8-bit Mat must not be
+    // read as raw bytes
+    if (image.type() != CV_8UC1) throw std::runtime_error("libvoslam_b200: ORBextractor needs a CV_8UC1 image");
     int n = 0;
     check(orbx_extract(h_, image.data, image.cols, image.rows, (size_t)image.step, kps_.data(), desc_.data(), cap_, &n));
     if (n == 0) {

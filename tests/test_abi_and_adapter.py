@@ -59,21 +59,35 @@ def test_product_does_not_import_oracle():
                 assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace("# oracle/", ""), f
 
 
-def test_adapter_header_compiles_and_links(vo, tmp_path):
+def _build_adapter_check(tmp_path):
     exe = str(tmp_path / "adapter_check")
     cmd = ["g++", "-std=c++11", "-I" + os.path.join(ROOT, "oracle", "compat"), "-I" + os.path.join(ROOT, "include"),
            os.path.join(ROOT, "tests", "tools", "adapter_check.cpp"), "-L" + os.path.join(ROOT, "vo_slam_test_b200", "lib"),
-           "-lvoslam_b200", "-Wl,-rpath," + os.path.join(ROOT, "vo_slam_test_b200", "lib"), "-o", exe]
+           "-lvoslam_b200", "-ldl", "-Wl,-rpath," + os.path.join(ROOT, "vo_slam_test_b200", "lib"), "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_adapter_header_compiles_and_links(vo, tmp_path):
+    exe = _build_adapter_check(tmp_path)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "adapter" in r.stdout
 
 
 @pytest.mark.gpu
-def test_adapter_runs_on_gpu(vo, tmp_path):
-    test_adapter_header_compiles_and_links(vo, tmp_path)
-    exe = str(tmp_path / "adapter_check")
-    r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 0 and "keypoints" in r.stdout, r.stdout + r.stderr
+def test_adapter_equals_oracle_on_gpu(vo, tmp_path):
+    """The C++ ORBextractor adapter (cv::Mat with step != cols in, std::vector<cv::KeyPoint> + descriptor Mat out) against
+    the oracle port and, where oracle/_ref is built, the reference's own class: every keypoint and descriptor byte."""
+    import oracle
+    oracle.build()
+    exe = _build_adapter_check(tmp_path)
+    port = os.path.join(ROOT, "oracle", "liborbport.so")
+    ref = os.path.join(ROOT, "oracle", "_ref", "liborbref_parity.so")
+    args = [exe, port] + ([ref] if os.path.exists(ref) else [])
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "adapter_check: all equal (4 cases" in r.stdout and r.stdout.count("adapter parity ok vs oracle port") == 4, r.stdout
+    if os.path.exists(ref):
+        assert r.stdout.count("the reference's own ORBextractor class") == 4, r.stdout

@@ -187,8 +187,6 @@ def test_error_convention(vo):
     ex.close()
 
 
-@pytest.mark.skipif(os.environ.get("ORBX_EXTRA_GPU_TESTS") != "1",
-                    reason="written in a session that had no GPU minutes left to confirm it: opt in with ORBX_EXTRA_GPU_TESTS=1")
 def test_random_configurations(vo):
     """The generator of tests/test_oracle_vs_reference.py::test_port_equals_compiled_reference_random_configurations on the
     GPU: random frame sizes, feature budgets, scale factors, level counts and thresholds.  Shapes the library declines

@@ -27,6 +27,10 @@ def test_frame_and_pair_blocks_cover_everything():
                 if halo is not None:
                     assert halo == blocks[r][1] and halo < n       # the replicated boundary frame
             assert pairs == list(range(n - 1))                       # every consecutive pair exactly once
+            for r in range(world):                                   # the strong-scaling view of the same partition
+                lo, hi, hi_ext, p_hi = sharded.strong_block(n, r, world)
+                assert (lo, hi) == blocks[r] and hi_ext in (hi, hi + 1) and hi_ext <= n
+                assert all(p + 1 < hi_ext for p in range(lo, p_hi))  # every owned pair has both frames on the rank
 
 
 def test_train_shards():
@@ -51,6 +55,26 @@ def test_merge_rule_equals_sequential_scan():
             idx.append(np.where(i >= 0, i + lo, i)); d1.append(a); d2.append(b)
         mi, m1, m2 = sharded.merge_top2_numpy(np.stack(idx), np.stack(d1), np.stack(d2))
         assert np.array_equal(mi, want[0]) and np.array_equal(m1, want[1]) and np.array_equal(m2, want[2])
+
+
+def test_merge_rule_with_empty_shards():
+    """M = 9 rows over 8 ranks: train_shard gives trailing ranks an EMPTY shard; its record is the sentinel (-1, 256, 256)
+    and the merge must ignore it."""
+    rng = np.random.default_rng(4)
+    P = oracle.Port()
+    t = synth.make_descriptors(9, seed=6)
+    q = synth.flip_bits(t[rng.integers(0, 9, 40)], rng.integers(0, 40, 40), rng)
+    want = P.knn2(q, t, 50, 0.7)
+    idx, d1, d2 = [], [], []
+    empties = 0
+    for r in range(8):
+        lo, hi = sharded.train_shard(9, r, 8)
+        empties += hi == lo
+        i, a, b, _ = P.knn2(q, t[lo:hi], 50, 0.7)
+        idx.append(np.where(i >= 0, i + lo, i)); d1.append(a); d2.append(b)
+    assert empties >= 3
+    mi, m1, m2 = sharded.merge_top2_numpy(np.stack(idx), np.stack(d1), np.stack(d2))
+    assert np.array_equal(mi, want[0]) and np.array_equal(m1, want[1]) and np.array_equal(m2, want[2])
 
 
 def _free_port():

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <algorithm>
 #include <string>
 
 #include "../../include/orb_b200.h"
@@ -48,6 +49,43 @@ static inline cudaError_t launch_chain(bool pdl, void (*kernel)(KArgs...), dim3 
 
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 static inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- host-side scratch shared by the host entry points (sbp.cu, hamming.cu, frame.cu, bow.cu) ---------------------
+struct DevArena {      // grow-only per-thread device scratch so repeated searches do not pay cudaMalloc
+  uint8_t* base = nullptr; size_t cap = 0, used = 0; int device = -1;
+  int reserve(size_t bytes, int dev) {
+    if (dev != device || bytes > cap) {
+      if (base) { cudaSetDevice(device < 0 ? dev : device); cudaFree(base); base = nullptr; cap = 0; }
+      if (cudaSetDevice(dev) != cudaSuccess) return ORBX_ERR_CUDA;
+      size_t want = std::max(bytes + bytes / 2, (size_t)8 << 20);
+      if (cudaMalloc(&base, want) != cudaSuccess) { base = nullptr; return ORBX_ERR_CUDA; }
+      cap = want; device = dev;
+    } else if (cudaSetDevice(dev) != cudaSuccess) {
+      return ORBX_ERR_CUDA;
+    }
+    used = 0;
+    return ORBX_OK;
+  }
+  template <typename T> T* take(size_t count) {
+    used = align_up_sz(used, 256);
+    T* p = reinterpret_cast<T*>(base + used);
+    used += sizeof(T) * count;
+    return p;
+  }
+};
+struct HostArena {     // pinned staging so that all inputs of one search go up in a single copy
+  uint8_t* base = nullptr; size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes > cap) {
+      if (base) cudaFreeHost(base);
+      base = nullptr; cap = 0;
+      size_t want = std::max(bytes + bytes / 2, (size_t)4 << 20);
+      if (cudaMallocHost(&base, want) != cudaSuccess) { base = nullptr; return ORBX_ERR_CUDA; }
+      cap = want;
+    }
+    return ORBX_OK;
+  }
+};
 
 // Candidate / keypoint packing used between the stages: x:12 | y:12 | score:8 (region coordinates).
 __host__ __device__ static inline uint32_t pack_key(int x, int y, int s) {

@@ -180,9 +180,9 @@ extern "C" int orbx_frame_finish(const orbx_camera* cam, const orbx_keypoint* kp
                o_dp = align_up_sz(o_ur + nk * 4, 256), o_ids = align_up_sz(o_dp + nk * 4, 256), o_cs = align_up_sz(o_ids + nk * 4, 256),
                o_cnt = align_up_sz(o_cs + (size_t)nframes * (FNCELL + 1) * 4, 256), o_depth = align_up_sz(o_cnt + (size_t)nframes * 4, 256),
                totalBytes = o_depth + depthBytes + 256;
-  char* db = nullptr;
-  cudaError_t e = cudaMalloc(&db, totalBytes);
-  if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return ORBX_ERR_CUDA; }
+  static thread_local DevArena arena;      // grow-only: the tracking thread calls this once per frame
+  if (arena.reserve(totalBytes, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
+  char* db = (char*)arena.take<uint8_t>(totalBytes);
   int rc = ORBX_OK;
   auto run = [&]() -> int {
     ORBX_CUDA(cudaMemcpy(db + o_kps, kps, nk * sizeof(orbx_keypoint), cudaMemcpyHostToDevice));
@@ -201,6 +201,5 @@ extern "C" int orbx_frame_finish(const orbx_camera* cam, const orbx_keypoint* kp
     return ORBX_OK;
   };
   rc = run();
-  cudaFree(db);
   return rc;
 }

@@ -256,18 +256,26 @@ __global__ void knn2_merge_scatter_kernel(const int32_t* __restrict__ pidx, cons
 }
 
 __global__ void knn2_gather_merge_kernel(const int32_t* __restrict__ own, int world, int nq, int maxq, int parity, int epoch, int th,
-                                         float ratio, int32_t* idx, int32_t* d1, int32_t* d2, uint8_t* ok, int32_t* status) {
-  if ((int)threadIdx.x < world) {                            // one thread per source rank; ~1 s bound instead of a hang
+                                         float ratio, int32_t* idx, int32_t* d1, int32_t* d2, uint8_t* ok, int32_t* status, long long spin_ticks) {
+  // one thread per source rank; a bounded spin (spin_ticks of clock64, set by the host: ORBX_PEER_TIMEOUT_MS, default 20 s --
+  // long enough for a peer's first-call module load) instead of a hang.  On a timeout NOTHING stale is merged: every query of
+  // this CTA gets the sentinel record (idx -1, d1 = d2 = 256, ok 0) and *status = 1; the exchange must then be torn down
+  // (sharded.py raises on every rank together).
+  __shared__ int timedOut;
+  if (threadIdx.x == 0) timedOut = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
     const int32_t* flag = own + parity * kMaxPeers + threadIdx.x;
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) != epoch) {
-      if (clock64() - t0 > 2000000000LL) { atomicExch(status, 1); break; }
+      if (clock64() - t0 > spin_ticks) { atomicExch(status, 1); timedOut = 1; break; }
       __nanosleep(200);
     }
   }
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
+  if (timedOut) { idx[i] = -1; d1[i] = 256; d2[i] = 256; ok[i] = 0; return; }
   int b1 = 256, b2 = 256, bi = -1;
   for (int s = 0; s < world; ++s) {                           // sources in ascending train-index order
     const int32_t* r = own + xchg_rec_off(parity, s, world, maxq) + (size_t)3 * i;
@@ -315,7 +323,8 @@ size_t hamm_knn2_workspace_bytes(int nq, long long nt) {
 
 int hamm_knn2_device(const uint8_t* d_q, int nq, const uint8_t* d_t, long long nt, int th, float ratio, int32_t* d_idx,
                      int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok, void* d_workspace, size_t workspace_bytes, void* stream) {
-  if (!d_q || !d_t || !d_idx || !d_d1 || !d_d2 || !d_ok || nq < 0 || nt < 0) { set_error("bad argument"); return ORBX_ERR_ARG; }
+  // an empty train set (nt == 0: a trailing rank of a small sharded map) is legal and may come with a null pointer
+  if (!d_q || (!d_t && nt > 0) || !d_idx || !d_d1 || !d_d2 || !d_ok || nq < 0 || nt < 0) { set_error("bad argument"); return ORBX_ERR_ARG; }
   if (nq == 0) return ORBX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   long long per;
@@ -340,28 +349,31 @@ int hamm_knn2(const uint8_t* q, int nq, const uint8_t* t, long long nt, int th, 
               int32_t* d2, uint8_t* ok, int device) {
   if (!q || (!t && nt > 0) || !idx || !d1 || !d2 || !ok || nq < 0 || nt < 0) { set_error("bad argument"); return ORBX_ERR_ARG; }
   if (nq == 0) return ORBX_OK;
-  ORBX_CUDA(cudaSetDevice(device));
-  uint8_t *dq = nullptr, *dt = nullptr, *dok = nullptr; int32_t *di = nullptr, *dd1 = nullptr, *dd2 = nullptr; void* ws = nullptr;
+  // grow-only per-thread arenas (one packed upload, one packed download) instead of 7 cudaMalloc/cudaFree + 6 copies per call:
+  // this entry point is what Matcher::computeDistance / matchTop2 of the adapter call per descriptor set
+  static thread_local DevArena arena;
+  static thread_local HostArena host;
   const size_t wsb = hamm_knn2_workspace_bytes(nq, nt);
-  int rc = ORBX_OK;
-  auto cleanup = [&]() { cudaFree(dq); cudaFree(dt); cudaFree(dok); cudaFree(di); cudaFree(dd1); cudaFree(dd2); cudaFree(ws); };
-#define HK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error(cudaGetErrorString(e_)); cleanup(); return ORBX_ERR_CUDA; } } while (0)
-  HK(cudaMalloc(&dq, (size_t)nq * 32)); HK(cudaMalloc(&dt, std::max<size_t>((size_t)nt * 32, 32)));
-  HK(cudaMalloc(&di, sizeof(int32_t) * nq)); HK(cudaMalloc(&dd1, sizeof(int32_t) * nq)); HK(cudaMalloc(&dd2, sizeof(int32_t) * nq));
-  HK(cudaMalloc(&dok, nq));
-  if (wsb) HK(cudaMalloc(&ws, wsb));
-  HK(cudaMemcpy(dq, q, (size_t)nq * 32, cudaMemcpyHostToDevice));
-  if (nt) HK(cudaMemcpy(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice));
-  rc = hamm_knn2_device(dq, nq, dt, nt, th, ratio, di, dd1, dd2, dok, ws, wsb, nullptr);
-  if (rc == ORBX_OK) {
-    HK(cudaMemcpy(idx, di, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost));
-    HK(cudaMemcpy(d1, dd1, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost));
-    HK(cudaMemcpy(d2, dd2, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost));
-    HK(cudaMemcpy(ok, dok, nq, cudaMemcpyDeviceToHost));
-  }
-#undef HK
-  cleanup();
-  return rc;
+  const size_t qB = align_up_sz((size_t)nq * 32, 256), tB = align_up_sz((size_t)nt * 32, 256);
+  const size_t outB = align_up_sz((size_t)nq * 13, 256);                 // idx, d1, d2 (int32) + ok (u8), one block
+  if (arena.reserve(qB + tB + outB + wsb + 1024, device) || host.reserve(qB + tB + outB)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
+  uint8_t* db = arena.take<uint8_t>(qB + tB);
+  uint8_t* dout = arena.take<uint8_t>(outB);
+  void* ws = wsb ? (void*)arena.take<uint8_t>(wsb) : nullptr;
+  memcpy(host.base, q, (size_t)nq * 32);
+  if (nt) memcpy(host.base + qB, t, (size_t)nt * 32);
+  cudaStream_t st = nullptr;
+  ORBX_CUDA(cudaMemcpyAsync(db, host.base, qB + (nt ? (size_t)nt * 32 : 0), cudaMemcpyHostToDevice, st));
+  int32_t *di = (int32_t*)dout, *dd1 = di + nq, *dd2 = dd1 + nq;
+  uint8_t* dok = (uint8_t*)(dd2 + nq);
+  const int rc = hamm_knn2_device(db, nq, db + qB, nt, th, ratio, di, dd1, dd2, dok, ws, wsb, st);
+  if (rc != ORBX_OK) return rc;
+  uint8_t* hout = host.base + qB + tB;
+  ORBX_CUDA(cudaMemcpyAsync(hout, dout, (size_t)nq * 13, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaStreamSynchronize(st));
+  memcpy(idx, hout, sizeof(int32_t) * nq); memcpy(d1, hout + 4 * (size_t)nq, sizeof(int32_t) * nq);
+  memcpy(d2, hout + 8 * (size_t)nq, sizeof(int32_t) * nq); memcpy(ok, hout + 12 * (size_t)nq, nq);
+  return ORBX_OK;
 }
 
 int hamm_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_counts, int cap, const int32_t* d_qf, const int32_t* d_tf,
@@ -479,8 +491,13 @@ int hamm_knn2_sharded_phases_device(const uint8_t* d_q, int nq, const uint8_t* d
     g_hamm_launches += 2;
   }
   if (phases & 2) {
+    static const long long spinTicks = []() {
+      const char* e = getenv("ORBX_PEER_TIMEOUT_MS");
+      const long long ms = e && atoll(e) > 0 ? atoll(e) : 20000;
+      return ms * 2000000LL;                                 // clock64 ticks at <= 2 GHz: a lower bound of the wait
+    }();
     knn2_gather_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(peers.p[rank], world, nq, max_queries, parity, epoch, th, ratio, d_idx,
-                                                              d_d1, d_d2, d_ok, d_status);
+                                                              d_d1, d_d2, d_ok, d_status, spinTicks);
     g_hamm_launches += 1;
   }
   ORBX_CUDA(cudaGetLastError());

@@ -336,41 +336,6 @@ __global__ void __launch_bounds__(kResolveThreads) sbp_resolve_kernel(FrameDev F
 }
 
 // ---- host orchestration -----------------------------------------------------------------------------------
-struct DevArena {      // grow-only per-thread device scratch so repeated searches do not pay cudaMalloc
-  uint8_t* base = nullptr; size_t cap = 0, used = 0; int device = -1;
-  int reserve(size_t bytes, int dev) {
-    if (dev != device || bytes > cap) {
-      if (base) { cudaSetDevice(device < 0 ? dev : device); cudaFree(base); base = nullptr; cap = 0; }
-      if (cudaSetDevice(dev) != cudaSuccess) return ORBX_ERR_CUDA;
-      size_t want = std::max(bytes + bytes / 2, (size_t)8 << 20);
-      if (cudaMalloc(&base, want) != cudaSuccess) { base = nullptr; return ORBX_ERR_CUDA; }
-      cap = want; device = dev;
-    } else if (cudaSetDevice(dev) != cudaSuccess) {
-      return ORBX_ERR_CUDA;
-    }
-    used = 0;
-    return ORBX_OK;
-  }
-  template <typename T> T* take(size_t count) {
-    used = align_up_sz(used, 256);
-    T* p = reinterpret_cast<T*>(base + used);
-    used += sizeof(T) * count;
-    return p;
-  }
-};
-struct HostArena {     // pinned staging so that all inputs of one search go up in a single copy
-  uint8_t* base = nullptr; size_t cap = 0;
-  int reserve(size_t bytes) {
-    if (bytes > cap) {
-      if (base) cudaFreeHost(base);
-      base = nullptr; cap = 0;
-      size_t want = std::max(bytes + bytes / 2, (size_t)4 << 20);
-      if (cudaMallocHost(&base, want) != cudaSuccess) { base = nullptr; return ORBX_ERR_CUDA; }
-      cap = want;
-    }
-    return ORBX_OK;
-  }
-};
 static thread_local DevArena g_arena, g_cand_arena;
 static thread_local HostArena g_host;
 
@@ -449,11 +414,8 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
   // candidate buffer: start with 48 per point; on overflow the search is re-run with the exact size (known afterwards)
   size_t capCand = std::max<size_t>((size_t)m * 48, 4096);
   const int smemN = 8192;
-  static thread_local bool attrSet = false;
-  if (!attrSet) {
-    ORBX_CUDA(cudaFuncSetAttribute(sbp_resolve_kernel<LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * 2 * smemN)));
-    attrSet = true;
-  }
+  // the attribute is per device and every entry point takes a device argument: set it on every call (cheap, as frame.cu does)
+  ORBX_CUDA(cudaFuncSetAttribute(sbp_resolve_kernel<LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * 2 * smemN)));
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (g_cand_arena.reserve(sizeof(uint32_t) * capCand + 256, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
     uint32_t* d_cand = g_cand_arena.take<uint32_t>(capCand);

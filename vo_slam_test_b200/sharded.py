@@ -49,17 +49,42 @@ def merge_top2_numpy(idx, d1, d2):
 
 
 def allgather_records(rec, dist):
-    """All-gather a [Q,3] int32 tensor (idx, d1, d2) from every rank -> [world, Q, 3] (works for nccl and gloo)."""
+    """All-gather a [Q,3] int32 tensor (idx, d1, d2) from every rank -> [world, Q, 3].  NCCL gathers device tensors in
+    place; gloo (CPU tests, or several ranks sharing one GPU) has no device all-gather, so device records take the host
+    route there."""
     import torch
     world = dist.get_world_size()
-    out = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
-    dist.all_gather_into_tensor(out, rec.contiguous()) if rec.is_cuda else dist.all_gather(list(out.unbind(0)), rec.contiguous())
-    return out
+    rec = rec.contiguous()
+    if rec.is_cuda and dist.get_backend() != "gloo":
+        out = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
+        dist.all_gather_into_tensor(out, rec)
+        return out
+    host = rec.cpu()
+    out = torch.empty((world,) + tuple(host.shape), dtype=host.dtype)
+    dist.all_gather(list(out.unbind(0)), host)
+    return out.to(rec.device)
 
 
-def sharded_knn2_cuda(d_q, d_t_local, shard_lo, th, ratio, dist, stream=None):
+def strong_block(nframes, rank, world):
+    """BASELINE config 2 as SURVEY section 8(d,e) states it: ONE batch of `nframes` frames block-partitioned over `world`
+    ranks.  Rank r extracts frames [lo, hi_ext) = its block plus the replicated boundary frame (the halo: first frame of the
+    next rank's block) and matches the pairs (p, p+1) for p in [lo, p_hi); with local frame numbering (frame lo -> 0) that
+    is pairs 0 .. p_hi-lo-1.  Returns (lo, hi, hi_ext, p_hi).  No data-path collective: every pair is owned by exactly one
+    rank (matcher.cpp:481-507 is a loop over independent query/train sets)."""
+    lo, hi = frame_block(nframes, rank, world)
+    plo, p_hi, halo = pair_block(nframes, rank, world)
+    hi_ext = hi + 1 if halo is not None else hi
+    return lo, hi, hi_ext, p_hi
+
+
+def sharded_knn2_cuda(d_q, d_t_local, shard_lo, th, ratio, dist, stream=None, check=False):
     """Local shard top-2 on this rank's GPU, NCCL all-gather of the records, merge kernel.  torch CUDA tensors in,
-    (idx, d1, d2, ok) torch CUDA tensors out.  d_t_local holds train rows [shard_lo, shard_lo + len)."""
+    (idx, d1, d2, ok) torch CUDA tensors out.  d_t_local holds train rows [shard_lo, shard_lo + len); an EMPTY shard (a
+    trailing rank when the map is small relative to the world, train_shard(9, 7, 8)) is legal.
+
+    A rank whose local kernel call fails must not leave its peers waiting in the collective: it contributes records with
+    the error marker idx = -2 and raises only AFTER the all-gather; with check=True every rank looks for the marker (one
+    sync) and all ranks raise together."""
     import torch
     from . import api
     Q, Ml = d_q.shape[0], d_t_local.shape[0]
@@ -69,14 +94,26 @@ def sharded_knn2_cuda(d_q, d_t_local, shard_lo, th, ratio, dist, stream=None):
     wsb = api.knn2_workspace_bytes(Q, Ml)
     ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
-    api.knn2_device(d_q.data_ptr(), Q, d_t_local.data_ptr(), Ml, th, ratio, idx.data_ptr(), d1.data_ptr(), d2.data_ptr(),
-                    ok.data_ptr(), ws.data_ptr(), wsb, st)
-    idx = torch.where(idx >= 0, idx + shard_lo, idx)          # local -> global row index
-    rec = torch.stack([idx, d1, d2], dim=1).contiguous()
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    err = None
+    try:
+        api.knn2_device(d_q.data_ptr(), Q, d_t_local.data_ptr() if Ml > 0 else 0, Ml, th, ratio, idx.data_ptr(), d1.data_ptr(),
+                        d2.data_ptr(), ok.data_ptr(), ws.data_ptr(), wsb, st)
+    except Exception as e:      # noqa: BLE001
+        if world == 1:
+            raise
+        err = e
+        idx.fill_(-2); d1.fill_(256); d2.fill_(256)
+    else:
+        idx = torch.where(idx >= 0, idx + shard_lo, idx)      # local -> global row index
+    rec = torch.stack([idx, d1, d2], dim=1).contiguous()
     if world == 1:
         return idx, d1, d2, ok
     allrec = allgather_records(rec, dist)                      # [world, Q, 3]
+    if err is not None:
+        raise err
+    if check and Q > 0 and bool((allrec[:, :, 0] == -2).any().item()):
+        raise RuntimeError("sharded top-2: the local kernel of a peer rank failed")
     parts = allrec.permute(2, 0, 1).contiguous()               # [3, world, Q]
     api.knn2_merge_device(parts[0].data_ptr(), parts[1].data_ptr(), parts[2].data_ptr(), world, Q, th, ratio,
                           idx.data_ptr(), d1.data_ptr(), d2.data_ptr(), ok.data_ptr(), st)
@@ -93,7 +130,16 @@ class PeerExchange:
         from . import api
         self.dist, self.device, self.max_queries = dist, int(device), int(max_queries)
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.bufs, self.own, self.epoch = None, None, 0
+        self.bufs, self.own, self.epoch, self.broken = None, None, 0, False
+        # The flag protocol orders call n's gather before call n+1's scatter only inside ONE stream: the stream that is
+        # current at construction is remembered and every call must be issued on it (sharded_knn2_peer checks).
+        self.stream = None
+        try:
+            import torch
+            if torch.cuda.is_available():
+                self.stream = torch.cuda.current_stream(self.device).cuda_stream
+        except Exception:       # noqa: BLE001
+            pass
         # Every rank runs the SAME sequence of collectives whatever fails locally (a rank that raised early would leave
         # its peers waiting in a collective): local failures are recorded and agreed on afterwards.
         handle, err = None, None
@@ -138,10 +184,19 @@ class PeerExchange:
 
 
 def sharded_knn2_peer(d_q, d_t_local, shard_lo, th, ratio, xchg, check=True):
-    """Same contract as sharded_knn2_cuda, but the exchange is fused into the kernels (xchg = PeerExchange).  `check`
-    reads the status word back (one sync) and raises if a peer's records did not arrive."""
+    """Same contract as sharded_knn2_cuda, but the exchange is fused into the kernels (xchg = PeerExchange).
+
+    check=True reads the status word back (one sync), agrees on it across ranks (one small all-reduce) and raises on EVERY
+    rank if any rank's gather timed out; the exchange is then marked broken and must be closed (epochs of the ranks may no
+    longer be in step).  check=False is the pure data path: a timed-out gather writes sentinel records (idx -1, ok 0), never
+    stale ones, and leaves the device status word in xchg.last_status for the caller to look at."""
     import torch
     from . import api
+    if xchg.broken:
+        raise RuntimeError("peer exchange is broken after a timeout: close it and build a new one")
+    cur = torch.cuda.current_stream().cuda_stream
+    if xchg.stream is not None and cur != xchg.stream:
+        raise RuntimeError("every call on a PeerExchange must be issued on the stream it was created on")
     Q, Ml = d_q.shape[0], d_t_local.shape[0]
     dev = d_q.device
     idx = torch.empty(Q, dtype=torch.int32, device=dev); d1 = torch.empty_like(idx); d2 = torch.empty_like(idx)
@@ -150,9 +205,14 @@ def sharded_knn2_peer(d_q, d_t_local, shard_lo, th, ratio, xchg, check=True):
     wsb = api.knn2_workspace_bytes(Q, Ml)
     ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
     xchg.epoch += 1
-    api.knn2_sharded_device(d_q.data_ptr(), Q, d_t_local.data_ptr(), Ml, int(shard_lo), th, ratio, xchg.rank, xchg.world, xchg.bufs,
-                            xchg.max_queries, xchg.epoch, idx.data_ptr(), d1.data_ptr(), d2.data_ptr(), ok.data_ptr(),
-                            status.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
-    if check and int(status.item()) != 0:
-        raise RuntimeError("sharded top-2: a peer's records did not arrive (exchange timed out)")
+    api.knn2_sharded_device(d_q.data_ptr(), Q, d_t_local.data_ptr() if Ml > 0 else 0, Ml, int(shard_lo), th, ratio, xchg.rank,
+                            xchg.world, xchg.bufs, xchg.max_queries, xchg.epoch, idx.data_ptr(), d1.data_ptr(), d2.data_ptr(),
+                            ok.data_ptr(), status.data_ptr(), ws.data_ptr(), wsb, cur)
+    if check:
+        if xchg.world > 1:
+            xchg.dist.all_reduce(status, op=xchg.dist.ReduceOp.MAX)
+        if int(status.item()) != 0:
+            xchg.broken = True
+            raise RuntimeError("sharded top-2: a peer's records did not arrive (exchange timed out)")
+    xchg.last_status = status
     return idx, d1, d2, ok
