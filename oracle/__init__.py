@@ -392,6 +392,21 @@ class Port:
         return assign[:s.n].copy(), cnt
 
 
+def best_march():
+    """Highest x86-64 micro-architecture level of THIS host among the prebuilt "-march=native" stand-ins (oracle/Makefile):
+    "v4" (AVX-512), "v3" (AVX2) or None."""
+    try:
+        flags = set(next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split(":")[1].split())
+    except Exception:       # noqa: BLE001
+        return None
+    v3 = {"avx", "avx2", "bmi1", "bmi2", "fma", "movbe", "popcnt", "f16c", "abm"} <= flags | ({"abm"} if "lzcnt" in flags else set())
+    v4 = v3 and {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags
+    for lvl, okay in (("v4", v4), ("v3", v3)):
+        if okay and os.path.exists(os.path.join(HERE, "_ref", "liborbref_%s.so" % lvl)):
+            return lvl
+    return None
+
+
 class Ref:
     """ctypes view of the reference's own extractor, compiled in place (oracle/_ref).
 
@@ -399,8 +414,8 @@ class Ref:
     parity=False -> liborbref.so        (normal allocator, reference flags: the CPU timing baseline)
     """
 
-    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, parity=True):
-        name = "liborbref_parity.so" if parity else "liborbref.so"
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, parity=True, march=None):
+        name = "liborbref_parity.so" if parity else ("liborbref_%s.so" % march if march else "liborbref.so")
         path = os.path.join(HERE, "_ref", name)
         if not os.path.exists(path):
             build()
@@ -494,8 +509,8 @@ class RefMatcher:
     """The reference's OWN distance function (src/matcher.cpp:1240-1256, compiled in place: oracle/_ref/libmatcherref.so) inside
     the reference's matching loop shape (matcher.cpp:481-507), threaded over queries: the matcher leg of bench.py's CPU arm."""
 
-    def __init__(self):
-        path = os.path.join(HERE, "_ref", "libmatcherref.so")
+    def __init__(self, march=None):
+        path = os.path.join(HERE, "_ref", "libmatcherref_%s.so" % march if march else "libmatcherref.so")
         if not os.path.exists(path):
             build()
         self.lib = C.CDLL(path)          # raises OSError where the reference was never compiled (callers fall back to the port)

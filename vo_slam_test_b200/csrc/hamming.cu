@@ -11,6 +11,8 @@
 #include <atomic>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace orbx {
@@ -385,7 +387,9 @@ int hamm_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_counts, int c
   }
   if (npairs == 0) return ORBX_OK;
   dim3 grid((cap + kQT - 1) / kQT, npairs);
+  nvtxRangePushA("orbx:hamming_pairs");
   knn2_pairs_kernel<<<grid, kQT, 0, (cudaStream_t)stream>>>(d_desc, d_counts, cap, d_qf, d_tf, th, ratio, d_idx, d_d1, d_d2, d_ok);
+  nvtxRangePop();
   g_hamm_launches++;
   ORBX_CUDA(cudaGetLastError());
   return ORBX_OK;

@@ -8,6 +8,8 @@
 #include <mutex>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "orb_extract.cuh"
 #include "orb_pattern.h"
 
@@ -118,6 +120,7 @@ int capped_chunk(int dflt, int w, int hgt) {
   if (c >= 64) c &= ~31;
   return std::max(1, c);
 }
+constexpr int kLaneMinFrames = 32;     // below 2 x this many frames a second lane is not worth its fork/join
 int resident_chunk(int w, int hgt) {
   const int e = env_int("ORBX_CHUNK", 0);
   return e > 0 ? e : capped_chunk(kDefaultChunk, w, hgt);
@@ -416,6 +419,7 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
   const uint8_t* img0 = d_imgs + (size_t)frame0 * frameStride;
   Bufs B = make_bufs(h, img0, rowStride, frameStride);
   if (ev) cudaEventRecord(ev[0], st);
+  nvtxRangePushA("orbx:pyramid");          // NVTX ranges per stage (host side of the launches): nsys timelines of the lanes
   for (int l = 1; l < G.nlevels; ++l) {        // ComputePyramid: level l from level l-1 (ORBextractor.cpp:1129)
     const LevelGeom& S = G.L[l - 1];
     const LevelGeom& D = G.L[l];
@@ -425,15 +429,24 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
     launch_resize(src, S.w, S.h, spitch, sframe, h->d_pyr + D.pyrOff, D.w, D.h, D.pitch, (size_t)D.h * D.pitch,
                   h->taps[l].t, h->taps[l].rt, h->d_maps ? h->d_maps + 3 * kMaxLevels + l : nullptr, l == 1 ? frame0 : 0, n, st);
   }
+  nvtxRangePop();
   if (ev) cudaEventRecord(ev[1], st);
   h->tma.frame0 = frame0;
+  nvtxRangePushA("orbx:fast");
   launch_fast(G, B, h->tma, n, st);
+  nvtxRangePop();
   if (ev) cudaEventRecord(ev[2], st);
+  nvtxRangePushA("orbx:quadtree");
   launch_octree(G, B, n, st);
+  nvtxRangePop();
   if (ev) cudaEventRecord(ev[3], st);
+  nvtxRangePushA("orbx:blur");
   launch_blur(G, B, h->tma, n, st);
+  nvtxRangePop();
   if (ev) cudaEventRecord(ev[4], st);
+  nvtxRangePushA("orbx:orient_desc");
   launch_orient_desc(G, B, h->tma, d_kps, d_desc, cap, d_counts, frame0, n, st);
+  nvtxRangePop();
   if (ev) cudaEventRecord(ev[5], st);
   h->launches += (G.nlevels - 1) + 4;
   h->last_img0 = img0; h->last_rowStride = rowStride; h->last_frameStride = frameStride; h->last_frames = n;
@@ -598,11 +611,18 @@ int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes,
   }
   if (nframes == 0) return ORBX_OK;
   ORBX_CUDA(cudaSetDevice(h->p.device));
-  const int chunk = std::min(nframes, resident_chunk(w, height));
+  const int want_lanes = env_int("ORBX_LANES", 2);
+  // Equal chunks, an even number of them when two lanes run: a batch that is a little larger than a multiple of the chunk
+  // size (a rank's block + its replicated boundary frame in the strong-scaling split: 513, 1025, 2049 frames) must not leave
+  // one lane with a one-frame chunk, and a batch of at most one chunk (512 frames per GPU at N = 8) still gets both lanes.
+  int chunk = std::min(nframes, resident_chunk(w, height));
+  if (want_lanes >= 2 && nframes >= 2 * kLaneMinFrames) {
+    const int pairs = (nframes + 2 * chunk - 1) / (2 * chunk);          // chunk pairs needed at the configured chunk size
+    chunk = (nframes + 2 * pairs - 1) / (2 * pairs);
+  }
   int rc = configure(h, w, height, chunk);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const int want_lanes = env_int("ORBX_LANES", 2);
   const int nchunks = (nframes + chunk - 1) / chunk;
   if (want_lanes >= 2 && nchunks >= 2) {
     // two lanes: chunks [0, ca) on the caller's stream with this handle's workspace, chunks [ca, nchunks) on the sibling's

@@ -39,10 +39,13 @@ def make_frame(seed, H=480, W=640, flat_band=True):
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
-def make_sequence(nframes, seed=0, H=480, W=640, step=2, out=None):
+def make_sequence(nframes, seed=0, H=480, W=640, step=2, out=None, start=0):
     """A panning 'video': frame i is a window sliding `step` px per frame over one wide canvas, plus
     per-frame sensor noise.  Consecutive frames overlap, so frame-to-frame matching finds real
-    correspondences.  Returns uint8 (nframes, H, W) (written into `out` if given)."""
+    correspondences.  Returns uint8 (nframes, H, W) (written into `out` if given) = frames [start, start + nframes)
+    of the sequence (a rank of a sharded run generates only its own block).  The pan wraps after period / step = 1024
+    frames and the noise pattern after 128, so frames i and i + 1024 are identical: a 4096-frame batch holds 1024 distinct
+    frames (no kernel caches by content, so timing is unaffected; bench.py states it in `config`)."""
     rng = np.random.default_rng(seed)
     period = 2048  # canvas columns; the pan wraps around
     canvas = _canvas(rng, H, period + W)
@@ -52,12 +55,13 @@ def make_sequence(nframes, seed=0, H=480, W=640, step=2, out=None):
     noise = rng.integers(-4, 5, (H, period + W + 64)).astype(np.float32)
     if out is None:
         out = np.empty((nframes, H, W), np.uint8)
-    for i in range(nframes):
+    for k in range(nframes):
+        i = start + k
         x = (i * step) % period
         nx = (i * 37) % 64
         f = canvas[:, x:x + W] + noise[:, nx:nx + W] * (1 if (i // 64) % 2 == 0 else -1)
         np.clip(f, 0, 255, out=f)
-        out[i] = f.astype(np.uint8)
+        out[k] = f.astype(np.uint8)
     return out
 
 
