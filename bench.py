@@ -283,8 +283,16 @@ class Block:
         self.owned = hi - lo
         self.npairs = npairs = p_hi - lo
         self.cap = cap = ex.max_keypoints
-        self.h_imgs = torch.empty((F, H_IMG, W_IMG), dtype=torch.uint8, pin_memory=True)
-        synth.make_sequence(F, seed=seed, out=self.h_imgs.numpy(), start=lo)
+        self.wc = None
+        if os.environ.get("ORBX_BENCH_WC", "0") == "1":       # experiment: write-combined pinned input (orbx_host_alloc)
+            from vo_slam_test_b200 import api
+            self.wc = api.HostBuffer((F, H_IMG, W_IMG), write_combined=True)
+            tmp = synth.make_sequence(F, seed=seed, start=lo)
+            self.wc.array[...] = tmp
+            self.h_imgs = torch.from_numpy(self.wc.array)
+        else:
+            self.h_imgs = torch.empty((F, H_IMG, W_IMG), dtype=torch.uint8, pin_memory=True)
+            synth.make_sequence(F, seed=seed, out=self.h_imgs.numpy(), start=lo)
         self.d_imgs = self.h_imgs.to(dev)
         self.d_kps = torch.empty((F, cap, 7), dtype=torch.float32, device=dev)
         self.d_desc = torch.empty((F, cap, 32), dtype=torch.uint8, device=dev)
@@ -544,6 +552,30 @@ def run_b200(args, rank, world, local_rank):
         e2e_in = e2e_value * W_IMG * H_IMG / 1e9
         link = {"h2d_copy_gbs_this_rank": gbs, "aggregate_h2d_gbs": agg, "e2e_input_gbs": e2e_in, "e2e_frac_of_aggregate": e2e_in / agg,
                 "simultaneous_ranks": world, "numa_node": numa}
+        # the copies of one step and nothing else: the input up on one stream while the step's results (counts, keypoints,
+        # descriptors, matches) come down on another, on ALL ranks at once -- no e2e step can be shorter than this
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        H = blk.host
+        pairs_rows = max(F - 1, 1)
+
+        def copies_only():
+            with torch.cuda.stream(s_up):
+                blk.d_imgs.copy_(blk.h_imgs, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                H["counts"].copy_(blk.d_counts, non_blocking=True); H["kps"].copy_(blk.d_kps, non_blocking=True)
+                H["desc"].copy_(blk.d_desc, non_blocking=True)
+                for hk, dt in (("midx", blk.d_midx), ("md1", blk.d_md1), ("md2", blk.d_md2), ("mok", blk.d_mok)):
+                    H[hk][:dt.shape[0]].copy_(dt[:pairs_rows], non_blocking=True)
+        copies_only()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            copies_only()
+        torch.cuda.synchronize()
+        tc = max_over_ranks(time.perf_counter() - t0) / 3
+        link["copies_only_ms_per_step"] = tc * 1e3
+        link["copies_only_frames_per_s"] = job_frames / tc
+        link["e2e_frac_of_copies_only"] = e2e_value / (job_frames / tc)
     except Exception as exc:                          # noqa: BLE001
         link = {"error": str(exc)[:120]}
 
@@ -739,6 +771,117 @@ def bench_hamming_map(args, torch, dist, sharded, dev, rank, world, local_rank, 
     return res
 
 
+def bench_tracking_frame(vo, synth):
+    """The reference's real per-frame call pattern (frame.cpp:22-32, then visualOdometry.cpp:240,265,354): ONE frame through
+    Frame::Frame (extract + undistort + depth + grid) and three searches against it, timed on the host around the C-ABI calls
+    (arguments marshalled once, outside the timed loop).  `handle`: orbx_frame_create + the *_h searches (frame resident);
+    `host_arrays`: orbx_extract + orbx_frame_finish + the host-array searches (every call re-uploads the frame)."""
+    import ctypes as C
+    from vo_slam_test_b200 import api
+    L = vo.lib()
+    ex = vo.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    cam = vo.camera(517.3, 516.5, 318.6, 255.3, [0.2624, -0.9531, -0.0054, 0.0026, 1.1633], 40.0, (0.0, 640.0, 0.0, 480.0))
+    img = synth.make_frame(42)
+    rng = np.random.default_rng(5)
+    depth = rng.uniform(0.5, 8.0, (H_IMG, W_IMG)).astype(np.float32)
+    fr = vo.Frame(ex, cam, img, depth)
+    sf = np.asarray(ex.GetScaleFactors(), np.float32)
+    n = fr.n
+    frame, pts = synth.make_projection_case(fr.unkps, fr.desc, sf, 1000, seed=1)
+    frame["uright"] = fr.uright
+    frameL, ptsL = synth.make_projection_case(fr.unkps, fr.desc, sf, 2000, seed=2, local=True)
+    src = rng.integers(0, n, 900)
+    kd = synth.flip_bits(fr.desc[src], rng.integers(0, 40, 900), rng)
+    A = synth.make_bow_side(kd, ((fr.unkps["angle"][src] + rng.normal(0, 8, 900)) % 360).astype(np.float32), None, 9, 1)
+    B = synth.make_bow_side(fr.desc, fr.unkps["angle"], None, 9, 2)
+    keep = []
+    M = vo.Matcher(0.9)
+    sF = M._frame_points(pts, keep)
+
+    def a(x, dt):
+        y = np.ascontiguousarray(x, dt); keep.append(y); return y.ctypes.data
+    sL = api._SbpLocalPoints()
+    sL.m = len(ptsL["u"]); sL.valid = a(ptsL["valid"], np.uint8); sL.u = a(ptsL["u"], np.float32); sL.v = a(ptsL["v"], np.float32)
+    sL.ur = a(ptsL["ur"], np.float32); sL.level = a(ptsL["level"], np.int32); sL.view_cos = a(ptsL["view_cos"], np.float32)
+    sL.desc = a(ptsL["desc"], np.uint8); sL.has_obs = a(ptsL["has_obs"], np.uint8)
+
+    def side(d, with_desc=True):
+        b = api._BowSide()
+        b.n = len(d["desc"]); b.desc = a(d["desc"], np.uint8) if with_desc else None; b.angle = a(d["angle"], np.float32) if with_desc else None
+        b.valid = a(d["valid"], np.uint8); b.ngroups = len(d["node_ids"]); b.node_ids = a(d["node_ids"], np.uint32)
+        b.group_start = a(d["group_start"], np.int32); b.feat_idx = a(d["feat_idx"], np.int32)
+        return b
+    bA, bB, bBh = side(A), side(B), side(B, False)
+    fv = M._frame_view(frame, keep)
+    occ = a(frame["occupied0"], np.uint8)
+    cap = ex.max_keypoints
+    assign = np.zeros(cap, np.int32); cnt = C.c_int(0); nn = C.c_int(0)
+    vp = C.c_void_p
+    kps = np.zeros(cap, api.KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); un = np.zeros(cap, api.KP_DTYPE)
+    ur = np.zeros(cap, np.float32); dp = np.zeros(cap, np.float32); cs = np.zeros(64 * 48 + 1, np.int32); ids = np.zeros(cap, np.int32)
+    cnt1 = np.zeros(1, np.int32)
+    pimg, pdepth = vp(img.ctypes.data), vp(depth.ctypes.data)
+    pa = vp(assign.ctypes.data)
+    fr.close()
+    h = vp()
+
+    def one_handle():
+        assert L.orbx_frame_create(ex._h, C.byref(cam), pimg, W_IMG, H_IMG, W_IMG, pdepth, 4 * W_IMG, C.byref(h), C.byref(nn)) == 0
+        L.orbx_frame_get(h, vp(kps.ctypes.data), vp(desc.ctypes.data), vp(un.ctypes.data), vp(ur.ctypes.data), vp(dp.ctypes.data), cap)
+        r1 = L.orbx_search_by_projection_frame_h(h, vp(occ), C.byref(sF), 15.0, 40.0, 0, 0, 1, pa, C.byref(cnt))
+        r2 = L.orbx_search_by_bow_h(C.byref(bA), h, C.byref(bBh), 0.7, TH_LOW, 1, pa, C.byref(cnt))
+        r3 = L.orbx_search_by_projection_local_h(h, vp(occ), C.byref(sL), 3.0, 0.8, pa, C.byref(cnt))
+        L.orbx_frame_destroy(h)
+        assert r1 == 0 and r2 == 0 and r3 == 0
+
+    def one_host():
+        assert L.orbx_extract(ex._h, pimg, W_IMG, H_IMG, W_IMG, vp(kps.ctypes.data), vp(desc.ctypes.data), cap, C.byref(nn)) == 0
+        cnt1[0] = nn.value
+        assert L.orbx_frame_finish(C.byref(cam), vp(kps.ctypes.data), vp(cnt1.ctypes.data), 1, cap, pdepth, W_IMG, H_IMG, 4 * W_IMG, 0,
+                                   vp(un.ctypes.data), vp(ur.ctypes.data), vp(dp.ctypes.data), vp(cs.ctypes.data), vp(ids.ctypes.data), 0) == 0
+        r1 = L.orbx_search_by_projection_frame(C.byref(fv), C.byref(sF), 15.0, 40.0, 0, 0, 1, pa, C.byref(cnt), 0)
+        r2 = L.orbx_search_by_bow(C.byref(bA), C.byref(bB), 0, 0.7, TH_LOW, 1, pa, C.byref(cnt), 0)
+        r3 = L.orbx_search_by_projection_local(C.byref(fv), C.byref(sL), 3.0, 0.8, pa, C.byref(cnt), 0)
+        assert r1 == 0 and r2 == 0 and r3 == 0
+
+    out = {}
+    for name, fn in (("handle", one_handle), ("host_arrays", one_host)):
+        for _ in range(10):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(100):
+            fn()
+        out[name] = (time.perf_counter() - t0) / 100 * 1e3
+    # the parts of the handle path
+    parts = {}
+
+    def timeit(fn, reps=100):
+        for _ in range(5):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e3
+    assert L.orbx_frame_create(ex._h, C.byref(cam), pimg, W_IMG, H_IMG, W_IMG, pdepth, 4 * W_IMG, C.byref(h), C.byref(nn)) == 0
+    parts["search_by_projection_frame_h"] = timeit(lambda: L.orbx_search_by_projection_frame_h(h, vp(occ), C.byref(sF), 15.0, 40.0, 0, 0, 1, pa, C.byref(cnt)))
+    parts["search_by_bow_h"] = timeit(lambda: L.orbx_search_by_bow_h(C.byref(bA), h, C.byref(bBh), 0.7, TH_LOW, 1, pa, C.byref(cnt)))
+    parts["search_by_projection_local_h"] = timeit(lambda: L.orbx_search_by_projection_local_h(h, vp(occ), C.byref(sL), 3.0, 0.8, pa, C.byref(cnt)))
+    L.orbx_frame_destroy(h)
+
+    def create_only():
+        L.orbx_frame_create(ex._h, C.byref(cam), pimg, W_IMG, H_IMG, W_IMG, pdepth, 4 * W_IMG, C.byref(h), C.byref(nn)); L.orbx_frame_destroy(h)
+    parts["frame_create_with_depth"] = timeit(create_only)
+
+    def create_nodepth():
+        L.orbx_frame_create(ex._h, C.byref(cam), pimg, W_IMG, H_IMG, W_IMG, None, 0, C.byref(h), C.byref(nn)); L.orbx_frame_destroy(h)
+    parts["frame_create_no_depth"] = timeit(create_nodepth)
+    ex.close()
+    return {"tracking_frame_ms": out["handle"], "tracking_frame_ms_host_arrays": out["host_arrays"], "parts_ms": parts,
+            "what": "one 640x480 frame: Frame::Frame (extract 1000 kp + undistort + findDepth from a pageable 640x480 float depth image + grid) "
+                    "+ searchByProjection(Frame,Frame) 1000 pts + searchByBoW(KeyFrame,Frame) 900 feats + searchByProjection(local map) 2000 pts; "
+                    "host wall clock around the C-ABI calls, 100 reps"}
+
+
 def bench_other_configs(torch, vo, synth, hbm_peak):
     """BASELINE configs 3 (1920x1080 / 2000 features, 3840x2160 / 5000 features) and 4 (10k map points projected into one VGA
     frame, radius 15) as extra keys of the bench line; a few seconds in total."""
@@ -800,6 +943,11 @@ def bench_other_configs(torch, vo, synth, hbm_peak):
         res[name] = {"ms_per_search": dt * 1e3, "points_per_s": 10000 / dt, "matches": int(r[1]) if isinstance(r, tuple) else None}
     res["api"] = "host C ABI (orbx_search_by_projection_frame / _local): host arrays in, assignment out, synchronous"
     out["config4_sbp"] = res
+    try:
+        out["tracking_frame"] = bench_tracking_frame(vo, synth)
+        out["tracking_frame_ms"] = out["tracking_frame"]["tracking_frame_ms"]
+    except Exception as exc:                          # noqa: BLE001
+        out["tracking_frame"] = {"error": str(exc)[:200]}
     return out
 
 

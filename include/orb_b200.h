@@ -55,6 +55,12 @@ typedef struct orbx_extractor* orbx_handle;
 
 const char* orbx_last_error(void);        /* thread-local message of the last failing call */
 int orbx_device_count(int* n);
+/* Pinned (page-locked) host staging memory for the batch entry points, visible to every CUDA context of the process
+ * (cudaHostAllocPortable); write_combined != 0 adds cudaHostAllocWriteCombined: the host writes frames once and never reads
+ * them back, the GPU's copy engine reads them without snooping the CPU caches.  The reference has no equivalent (its frames
+ * are cv::Mat buffers read by the CPU, src/frame.cpp:22); a maintainer allocates the grabber's ring with this. */
+int orbx_host_alloc(size_t bytes, int write_combined, void** out);
+int orbx_host_free(void* p);
 
 /* ---------------------------------------------------------------------------------------------------
  * Extractor  (replaces ORBextractor::ORBextractor / operator() / Get*ScaleFactors)
@@ -318,6 +324,39 @@ int orbx_frame_finish_device(const orbx_camera* cam, const orbx_keypoint* d_kps,
                              int cap, const float* d_depth, int w, int height, size_t depth_row_stride,
                              size_t depth_frame_stride, orbx_keypoint* d_unkps, float* d_uright, float* d_depth_out,
                              int32_t* d_cell_start, int32_t* d_ids, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Device-resident frame: the reference's per-frame call chain without host round trips.
+ *   Frame::Frame (frame.cpp:22-32) = extractor call + undistortKeyPoints + findDepth + assignFeaturesToGrid, then the tracking
+ *   thread runs 1-4 searches against that frame (visualOdometry.cpp:240 searchByProjection(Frame*,Frame*), :265 / :329
+ *   searchByBoW(KeyFrame*,Frame*), :329 searchByProjection(Frame*,KeyFrame*), :354 searchByProjection(Frame*,local map)).
+ * orbx_frame_create does the whole constructor on the device in one call (image up, kernels, ONE packed copy of keypoints /
+ * descriptors / undistorted keypoints / uRight / depth down) and keeps everything the searches read -- undistorted keypoints,
+ * descriptors, uRight, the 64x48 CSR grid -- in HBM; the *_h searches take the handle, so per search only the projected map
+ * points and the frame's `occupied0` flags go up and the assignment comes down.  Results are bit-identical to
+ * orbx_extract + orbx_frame_finish + the host-array searches.
+ *   depth: float32 image (height x w, row stride in BYTES) or NULL; pinned memory (orbx_host_alloc) makes its upload
+ *   asynchronous under the extraction kernels.  A frame belongs to the extractor handle that created it (its stream, its
+ *   block pool): destroy frames before their extractor; orbx_destroy frees whatever is left.  One thread per extractor.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct orbx_frame* orbx_frame_t;
+int orbx_frame_create(orbx_handle h, const orbx_camera* cam, const uint8_t* img, int w, int height, size_t stride,
+                      const float* depth, size_t depth_row_stride, orbx_frame_t* out, int* n);
+int orbx_frame_size(orbx_frame_t f, int* n);
+/* host copies of keypoints_ / descriptors_ / unKeypoints_ / uRight_ / depth_ (any pointer may be NULL; cap >= n) */
+int orbx_frame_get(orbx_frame_t f, orbx_keypoint* kps, uint8_t* desc, orbx_keypoint* unkps, float* uright, float* depth, int cap);
+int orbx_frame_destroy(orbx_frame_t f);
+/* occupied0[i] (i < n): as orbx_frame_view.occupied0 of the corresponding host-array search */
+int orbx_search_by_projection_frame_h(orbx_frame_t frame, const uint8_t* occupied0, const orbx_sbp_frame_points* pts, float radius,
+                                      float bf, int forward, int backward, int check_rot, int32_t* assign, int* match_cnt);
+int orbx_search_by_projection_local_h(orbx_frame_t frame, const uint8_t* occupied0, const orbx_sbp_local_points* pts,
+                                      float th_radius, float ratio, int32_t* assign, int* match_cnt);
+int orbx_search_by_projection_reloc_h(orbx_frame_t frame, const uint8_t* occupied0, const orbx_sbp_frame_points* pts, float radius,
+                                      float dist_threshold, int check_rot, int32_t* assign, int* match_cnt);
+/* searchByBoW(KeyFrame*, Frame*) (mode 0 of orbx_search_by_bow): frame_groups carries the frame's n, valid flags and
+ * FeatureVector CSR; its desc / angle may be NULL (read from the handle). */
+int orbx_search_by_bow_h(const orbx_bow_side* keyframe, orbx_frame_t frame, const orbx_bow_side* frame_groups, float ratio,
+                         int th_low, int check_rot, int32_t* match, int* match_cnt);
 
 #ifdef __cplusplus
 }

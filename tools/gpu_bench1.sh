@@ -2,7 +2,7 @@
 # One-GPU bench line (default flags) -> gpurun_out/bench_$1.json, plus a short summary on stdout.
 TAG=${1:-x}; shift
 mkdir -p gpurun_out
-env "$@" python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+env "$@" python bench.py $BENCH_ARGS > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
 tail -3 gpurun_out/bench_$TAG.err
 python - <<PY
 import json
@@ -13,6 +13,6 @@ print("roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"], 4), "lin
 print("hamming_map", d["hamming_map"])
 print("cpu", d["cpu_baseline"])
 print("parity", d["config"]["parity_spot_check"], d["config"]["checksum"])
-for k in ("config3_1080p", "config3_4k", "config4_sbp", "configs_error", "single_frame", "other_scaling"):
+for k in ("config3_1080p", "config3_4k", "config4_sbp", "tracking_frame", "configs_error", "single_frame", "other_scaling"):
     if k in d: print(k, d[k])
 PY

@@ -74,7 +74,17 @@ def load_library():
     vp, i32, f32, sz, ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
     L.orbx_last_error.restype = C.c_char_p
     L.orbx_device_count.argtypes = [vp]
+    L.orbx_host_alloc.argtypes = [sz, i32, vp]
+    L.orbx_host_free.argtypes = [vp]
     L.orbx_create.argtypes = [vp, vp]
+    L.orbx_frame_create.argtypes = [vp, vp, vp, i32, i32, sz, vp, sz, vp, vp]
+    L.orbx_frame_size.argtypes = [vp, vp]
+    L.orbx_frame_get.argtypes = [vp, vp, vp, vp, vp, vp, i32]
+    L.orbx_frame_destroy.argtypes = [vp]
+    L.orbx_search_by_projection_frame_h.argtypes = [vp, vp, vp, f32, f32, i32, i32, i32, vp, vp]
+    L.orbx_search_by_projection_local_h.argtypes = [vp, vp, vp, f32, f32, vp, vp]
+    L.orbx_search_by_projection_reloc_h.argtypes = [vp, vp, vp, f32, f32, i32, vp, vp]
+    L.orbx_search_by_bow_h.argtypes = [vp, vp, vp, f32, i32, i32, vp, vp]
     L.orbx_destroy.argtypes = [vp]
     L.orbx_get_levels.argtypes = [vp, vp]
     L.orbx_scale_factors.argtypes = [vp, vp, i32]
@@ -134,6 +144,22 @@ def device_count():
     n = C.c_int(0)
     load_library().orbx_device_count(C.byref(n))
     return n.value
+
+
+class HostBuffer:
+    """Pinned host staging memory from orbx_host_alloc (optionally write-combined) as a numpy uint8 array `.array`."""
+
+    def __init__(self, shape, write_combined=False):
+        n = int(np.prod(shape))
+        self.ptr = C.c_void_p()
+        _check(load_library().orbx_host_alloc(n, 1 if write_combined else 0, C.byref(self.ptr)))
+        self.array = np.ctypeslib.as_array((C.c_uint8 * n).from_address(self.ptr.value)).reshape(shape)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            load_library().orbx_host_free(self.ptr)
+            self.ptr = None
 
 
 def _p(a):
@@ -377,6 +403,46 @@ def frame_finish(kps, counts, cam, depth=None, device=0):
     return un, ur, dp, start, ids
 
 
+class Frame:
+    """Device-resident frame (orbx_frame_t): Frame::Frame (frame.cpp:22-32) = extraction + undistortKeyPoints + findDepth +
+    assignFeaturesToGrid in one call; keypoints / descriptors / grid stay in HBM for the searches (`*_h` entry points).
+    Host copies of the members: kps, desc, unkps, uright, depth."""
+
+    def __init__(self, extractor, cam, image, depth=None):
+        img = np.ascontiguousarray(image, np.uint8)
+        H, W = img.shape
+        self._lib = load_library()
+        self._ex = extractor             # the frame lives in its extractor's pool: keep the extractor alive
+        self._h = C.c_void_p()
+        n = C.c_int(0)
+        dptr, ds = None, 0
+        if depth is not None:
+            depth = np.ascontiguousarray(depth, np.float32)
+            assert depth.shape == (H, W)
+            dptr, ds = _p(depth), depth.strides[0]
+        _check(self._lib.orbx_frame_create(extractor._h, C.byref(cam), _p(img), W, H, img.strides[0], dptr, ds, C.byref(self._h),
+                                           C.byref(n)))
+        self.n = n.value
+        self.bounds = (cam.xmin, cam.xmax, cam.ymin, cam.ymax)
+        m = max(self.n, 1)
+        self.kps = np.zeros(m, KP_DTYPE); self.desc = np.zeros((m, 32), np.uint8); self.unkps = np.zeros(m, KP_DTYPE)
+        self.uright = np.zeros(m, np.float32); self.depth = np.zeros(m, np.float32)
+        _check(self._lib.orbx_frame_get(self._h, _p(self.kps), _p(self.desc), _p(self.unkps), _p(self.uright), _p(self.depth), m))
+        self.kps, self.desc, self.unkps = self.kps[:self.n], self.desc[:self.n], self.unkps[:self.n]
+        self.uright, self.depth = self.uright[:self.n], self.depth[:self.n]
+
+    def close(self):
+        if self._h:
+            self._lib.orbx_frame_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Matcher:
     """Mirror of myslam::Matcher (matcher.h:9-45) for the hot-path overloads; map points arrive already projected."""
 
@@ -517,6 +583,56 @@ class Matcher:
         _check(self._lib.orbx_search_by_bow(C.byref(sa), C.byref(sb), mode, self.ratio_, th_low, int(checkRot), _p(match),
                                             C.byref(cnt), self.device))
         return match[:n_out].copy(), cnt.value
+
+    # ---- the tracking-thread searches against a device-resident Frame (only the points and occupied0 go up) -----------------
+    def searchByProjectionH(self, frame, occupied0, frame_last_points, radius, checkRot=True, bf=40.0, forward=False, backward=False):
+        keep = []
+        s = self._frame_points(frame_last_points, keep)
+        occ = np.ascontiguousarray(occupied0, np.uint8)
+        assign = np.zeros(max(frame.n, 1), np.int32); cnt = C.c_int(0)
+        _check(self._lib.orbx_search_by_projection_frame_h(frame._h, _p(occ), C.byref(s), radius, bf, int(forward), int(backward),
+                                                           int(checkRot), _p(assign), C.byref(cnt)))
+        return assign[:frame.n].copy(), cnt.value
+
+    def searchByProjectionKeyFrameH(self, frame, occupied0, keyframe_points, radius, distThreshold, checkRot=True):
+        keep = []
+        s = self._frame_points(keyframe_points, keep)
+        occ = np.ascontiguousarray(occupied0, np.uint8)
+        assign = np.zeros(max(frame.n, 1), np.int32); cnt = C.c_int(0)
+        _check(self._lib.orbx_search_by_projection_reloc_h(frame._h, _p(occ), C.byref(s), radius, distThreshold, int(checkRot),
+                                                           _p(assign), C.byref(cnt)))
+        return assign[:frame.n].copy(), cnt.value
+
+    def searchByProjectionLocalH(self, frame, occupied0, mappoints, thRadius):
+        keep = []
+        def a(x, dt):
+            y = np.ascontiguousarray(x, dt); keep.append(y); return y.ctypes.data
+        p = mappoints
+        s = _SbpLocalPoints()
+        s.m = len(p["u"]); s.valid = a(p["valid"], np.uint8); s.u = a(p["u"], np.float32); s.v = a(p["v"], np.float32)
+        s.ur = a(p["ur"], np.float32); s.level = a(p["level"], np.int32); s.view_cos = a(p["view_cos"], np.float32)
+        s.desc = a(p["desc"], np.uint8); s.has_obs = a(p["has_obs"], np.uint8)
+        occ = np.ascontiguousarray(occupied0, np.uint8)
+        assign = np.zeros(max(frame.n, 1), np.int32); cnt = C.c_int(0)
+        _check(self._lib.orbx_search_by_projection_local_h(frame._h, _p(occ), C.byref(s), thRadius, self.ratio_, _p(assign), C.byref(cnt)))
+        return assign[:frame.n].copy(), cnt.value
+
+    def searchByBoWH(self, side_a, frame, frame_groups, checkRot=True, th_low=TH_LOW):
+        """searchByBoW(KeyFrame*, Frame*) with the frame resident: frame_groups = dict(valid, node_ids, group_start, feat_idx)."""
+        keep = []
+        def a(x, dt):
+            y = np.ascontiguousarray(x, dt); keep.append(y); return y.ctypes.data
+        sa = _BowSide()
+        sa.n = len(side_a["desc"]); sa.desc = a(side_a["desc"], np.uint8); sa.angle = a(side_a["angle"], np.float32)
+        sa.valid = a(side_a["valid"], np.uint8); sa.ngroups = len(side_a["node_ids"]); sa.node_ids = a(side_a["node_ids"], np.uint32)
+        sa.group_start = a(side_a["group_start"], np.int32); sa.feat_idx = a(side_a["feat_idx"], np.int32)
+        sb = _BowSide()
+        sb.n = frame.n; sb.desc = None; sb.angle = None; sb.valid = a(frame_groups["valid"], np.uint8)
+        sb.ngroups = len(frame_groups["node_ids"]); sb.node_ids = a(frame_groups["node_ids"], np.uint32)
+        sb.group_start = a(frame_groups["group_start"], np.int32); sb.feat_idx = a(frame_groups["feat_idx"], np.int32)
+        match = np.zeros(max(frame.n, 1), np.int32); cnt = C.c_int(0)
+        _check(self._lib.orbx_search_by_bow_h(C.byref(sa), frame._h, C.byref(sb), self.ratio_, th_low, int(checkRot), _p(match), C.byref(cnt)))
+        return match[:frame.n].copy(), cnt.value
 
     def searchByProjectionLocal(self, frame, mappoints, thRadius):
         """Matcher::searchByProjection(Frame*, const vector<MapPoint*>&, thRadius) (matcher.cpp:274-353)."""

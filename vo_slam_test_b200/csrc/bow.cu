@@ -12,7 +12,7 @@
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "frame_handle.cuh"
 
 namespace orbx {
 
@@ -244,8 +244,19 @@ static int check_side(const orbx_bow_side* s) {
 
 using namespace orbx;
 
-extern "C" int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b, int mode, float ratio, int th_low, int check_rot,
-                                  int32_t* match, int* match_cnt, int device) {
+// rfB != nullptr: side b is a device-resident frame (orbx_frame_t): its descriptors and angles are read in place from the
+// handle, b->desc / b->angle are ignored and only b's validity flags and FeatureVector CSR are uploaded.
+static int bow_run(const orbx_bow_side* a, const orbx_bow_side* b, int mode, float ratio, int th_low, int check_rot,
+                   int32_t* match, int* match_cnt, int device, const orbx_frame* rfB) {
+  orbx_bow_side bfix;
+  static const uint8_t kDummy = 0;
+  if (rfB && b) {          // let the side checks pass without host descriptor / angle arrays
+    bfix = *b;
+    if (bfix.n != rfB->n) { set_error("side b: n differs from the frame handle"); return ORBX_ERR_ARG; }
+    if (!bfix.desc) bfix.desc = &kDummy;
+    if (!bfix.angle) bfix.angle = (const float*)&kDummy;
+    b = &bfix;
+  }
   if (check_side(a) || check_side(b)) return ORBX_ERR_ARG;
   if (!match || !match_cnt || (mode != 0 && mode != 1)) { set_error("bad argument"); return ORBX_ERR_ARG; }
   const int nOut = mode == 0 ? b->n : a->n;
@@ -262,7 +273,8 @@ extern "C" int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b
   for (int s = 0; s < 2; ++s) {
     const orbx_bow_side* S = sides[s];
     const int nfi = S->group_start[S->ngroups];
-    offs[s][0] = add((size_t)S->n * 32); offs[s][1] = add(sizeof(float) * S->n); offs[s][2] = add(S->n);
+    const bool res = s == 1 && rfB;
+    offs[s][0] = add(res ? 0 : (size_t)S->n * 32); offs[s][1] = add(res ? 0 : sizeof(float) * S->n); offs[s][2] = add(S->n);
     offs[s][3] = add(sizeof(uint32_t) * S->ngroups); offs[s][4] = add(sizeof(int32_t) * (S->ngroups + 1)); offs[s][5] = add(sizeof(int32_t) * nfi);
   }
   const size_t inBytes = align_up_sz(used, 256);
@@ -272,7 +284,7 @@ extern "C" int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b
   for (int s = 0; s < 2; ++s) {
     const orbx_bow_side* S = sides[s];
     const int nfi = S->group_start[S->ngroups];
-    memcpy(g_bow.h + offs[s][0], S->desc, (size_t)S->n * 32); memcpy(g_bow.h + offs[s][1], S->angle, sizeof(float) * S->n);
+    if (!(s == 1 && rfB)) { memcpy(g_bow.h + offs[s][0], S->desc, (size_t)S->n * 32); memcpy(g_bow.h + offs[s][1], S->angle, sizeof(float) * S->n); }
     memcpy(g_bow.h + offs[s][2], S->valid, S->n); memcpy(g_bow.h + offs[s][3], S->node_ids, sizeof(uint32_t) * S->ngroups);
     memcpy(g_bow.h + offs[s][4], S->group_start, sizeof(int32_t) * (S->ngroups + 1)); memcpy(g_bow.h + offs[s][5], S->feat_idx, sizeof(int32_t) * nfi);
   }
@@ -288,6 +300,7 @@ extern "C" int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b
     D[s].ngroups = sides[s]->ngroups; D[s].node_ids = (const uint32_t*)(db + offs[s][3]);
     D[s].group_start = (const int32_t*)(db + offs[s][4]); D[s].feat_idx = (const int32_t*)(db + offs[s][5]);
   }
+  if (rfB) { D[1].desc = rfB->d_desc; D[1].angle = rfB->d_angle; }
   bow_match_kernel<<<(a->ngroups + 7) / 8, 256, 0, st>>>(D[0], D[1], mode, ratio, th_low, check_rot, (int*)(db + o_taken),
                                                          (int32_t*)(db + o_match), (int8_t*)(db + o_bin), (int*)(db + o_hist));
   bow_finish_kernel<<<1, 1024, 0, st>>>(nOut, check_rot, (int32_t*)(db + o_match), (const int8_t*)(db + o_bin), (const int*)(db + o_hist),
@@ -299,6 +312,18 @@ extern "C" int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b
   ORBX_CUDA(cudaGetLastError());
   *match_cnt = res;
   return ORBX_OK;
+}
+
+extern "C" int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b, int mode, float ratio, int th_low, int check_rot,
+                                  int32_t* match, int* match_cnt, int device) {
+  return bow_run(a, b, mode, ratio, th_low, check_rot, match, match_cnt, device, nullptr);
+}
+
+// Matcher::searchByBoW(KeyFrame*, Frame*, ...) (matcher.cpp:449-559, mode 0) with the frame resident on the device.
+extern "C" int orbx_search_by_bow_h(const orbx_bow_side* keyframe, orbx_frame_t frame, const orbx_bow_side* frame_groups, float ratio,
+                                    int th_low, int check_rot, int32_t* match, int* match_cnt) {
+  if (!frame || !frame_groups) { set_error("null frame handle"); return ORBX_ERR_ARG; }
+  return bow_run(keyframe, frame_groups, 0, ratio, th_low, check_rot, match, match_cnt, frame->device, frame);
 }
 
 // Matcher::searchForTriangulation(KeyFrame*, KeyFrame*, matchIdxs, F12, checkRot)  (matcher.cpp:867-1010).

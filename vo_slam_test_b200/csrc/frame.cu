@@ -12,7 +12,7 @@
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "frame_handle.cuh"
 
 namespace orbx {
 
@@ -60,7 +60,8 @@ __device__ __forceinline__ void undistort_point(const CamDev& C, float uin, floa
 __global__ void __launch_bounds__(kFrameThreads) frame_finish_kernel(
     const CamDev C, const orbx_keypoint* __restrict__ kps, const int32_t* __restrict__ counts, int cap,
     const float* __restrict__ depth, int W, int H, size_t depthRow, size_t depthFrame, orbx_keypoint* __restrict__ unkps,
-    float* __restrict__ uright, float* __restrict__ depthOut, int32_t* __restrict__ cellStart, int32_t* __restrict__ ids) {
+    float* __restrict__ uright, float* __restrict__ depthOut, int32_t* __restrict__ cellStart, int32_t* __restrict__ ids,
+    float4* __restrict__ feat, float* __restrict__ angle) {
   extern __shared__ int16_t cellOf[];     // [cap]
   __shared__ int cnt[FNCELL];
   __shared__ int ws[40];
@@ -68,6 +69,8 @@ __global__ void __launch_bounds__(kFrameThreads) frame_finish_kernel(
   const int n = min(max(counts[f], 0), cap);
   kps += (size_t)f * cap; unkps += (size_t)f * cap; uright += (size_t)f * cap; depthOut += (size_t)f * cap;
   ids += (size_t)f * cap; cellStart += (size_t)f * (FNCELL + 1);
+  if (feat) feat += (size_t)f * cap;
+  if (angle) angle += (size_t)f * cap;
   const char* dimg = depth ? (const char*)depth + (size_t)f * depthFrame : nullptr;
   for (int c = tid; c < FNCELL; c += kFrameThreads) cnt[c] = 0;
   __syncthreads();
@@ -83,6 +86,8 @@ __global__ void __launch_bounds__(kFrameThreads) frame_finish_kernel(
       if (dv > 0) { d = dv; ur = __fsub_rn(k.x, __fdiv_rn(C.bf, dv)); }                 // :126-130
     }
     uright[i] = ur; depthOut[i] = d;
+    if (feat) feat[i] = make_float4(k.x, k.y, __int_as_float(k.octave), ur);    // the searches' per-feature record (sbp.cu FrameDev::feat)
+    if (angle) angle[i] = k.angle;
     const int gx = (int)roundf(__fmul_rn(__fsub_rn(k.x, C.xmin), C.gw));                // frame.cpp:83-84
     const int gy = (int)roundf(__fmul_rn(__fsub_rn(k.y, C.ymin), C.gh));
     int c = -1;
@@ -126,15 +131,25 @@ static int make_cam(const orbx_camera* cam, CamDev& C) {
 
 static int launch_frame_finish(const CamDev& C, const orbx_keypoint* d_kps, const int32_t* d_counts, int nframes, int cap,
                                const float* d_depth, int w, int h, size_t depthRow, size_t depthFrame, orbx_keypoint* d_unkps,
-                               float* d_uright, float* d_depthOut, int32_t* d_cellStart, int32_t* d_ids, cudaStream_t st) {
+                               float* d_uright, float* d_depthOut, int32_t* d_cellStart, int32_t* d_ids, cudaStream_t st,
+                               float4* d_feat = nullptr, float* d_angle = nullptr) {
   const size_t smem = sizeof(int16_t) * (size_t)cap;
   if (smem > 160 * 1024) { set_error("cap too large for the frame kernel (max 81920 keypoints per frame)"); return ORBX_ERR_ARG; }
   if (smem > 32 * 1024)
     ORBX_CUDA(cudaFuncSetAttribute(frame_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   frame_finish_kernel<<<nframes, kFrameThreads, smem, st>>>(C, d_kps, d_counts, cap, d_depth, w, h, depthRow, depthFrame, d_unkps,
-                                                           d_uright, d_depthOut, d_cellStart, d_ids);
+                                                           d_uright, d_depthOut, d_cellStart, d_ids, d_feat, d_angle);
   ORBX_CUDA(cudaGetLastError());
   return ORBX_OK;
+}
+
+int frame_finish_launch(const orbx_camera* cam, const orbx_keypoint* d_kps, const int32_t* d_counts, int nframes, int cap,
+                        const float* d_depth, int w, int h, size_t depthRow, size_t depthFrame, orbx_keypoint* d_unkps, float* d_uright,
+                        float* d_depthOut, int32_t* d_cellStart, int32_t* d_ids, float4* d_feat, float* d_angle, cudaStream_t st) {
+  CamDev C;
+  if (int rc = make_cam(cam, C)) return rc;
+  return launch_frame_finish(C, d_kps, d_counts, nframes, cap, d_depth, w, h, depthRow, depthFrame, d_unkps, d_uright, d_depthOut,
+                             d_cellStart, d_ids, st, d_feat, d_angle);
 }
 
 }  // namespace orbx

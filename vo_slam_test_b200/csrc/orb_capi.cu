@@ -10,6 +10,7 @@
 
 #include <nvtx3/nvToolsExt.h>
 
+#include "frame_handle.cuh"
 #include "orb_extract.cuh"
 #include "orb_pattern.h"
 
@@ -94,11 +95,16 @@ struct orbx_extractor {
   // throughput-bound stages of the other (measured: +2.4 % on 4096 VGA frames, tools/lanes_probe.py)
   orbx_extractor* lane2 = nullptr;
   cudaEvent_t laneFork = nullptr, laneJoin = nullptr;
+  // device-resident frames (orbx_frame_t): blocks handed back by orbx_frame_destroy are reused by the next orbx_frame_create
+  std::vector<orbx_frame*> framePool, framesAll;      // framesAll: every block not yet freed (live ones included)
+  int framesLive = 0;
   // last chunk info for the debug taps
   const uint8_t* last_img0 = nullptr; size_t last_rowStride = 0, last_frameStride = 0; int last_frames = 0;
 };
 
 namespace {
+
+void free_frame_block(orbx_frame* f);
 
 // Frames per chunk.  Device-resident batches: 512 (fewer, larger launches: +3 % over 256, no gain beyond).  Host-pipelined
 // batches: 256, because the upload of chunk c+1 overlaps the kernels of chunk c and the pipeline fill/drain grows with the
@@ -454,6 +460,44 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
   return ORBX_OK;
 }
 
+void free_frame_block(orbx_frame* f) {
+  if (!f) return;
+  cudaFree(f->d_block); cudaFree(f->d_depthImg);
+  if (f->h_mirror) cudaFreeHost(f->h_mirror);
+  delete f;
+}
+
+// carve one device block: [packed region | angle | scale | cellStart | ids | feat]
+int alloc_frame_block(orbx_extractor* h, orbx_frame** out) {
+  const int cap = h->maxKp, nl = h->p.nlevels;
+  orbx_frame* f = new orbx_frame();
+  f->owner = h; f->device = h->p.device; f->cap = cap; f->nlevels = nl;
+  size_t used = 0;
+  auto add = [&](size_t bytes) { used = align_up_sz(used, 256); size_t o = used; used += bytes; return o; };
+  const size_t o_cnt = add(64), o_kps = add(sizeof(orbx_keypoint) * cap), o_desc = add((size_t)32 * cap), o_un = add(sizeof(orbx_keypoint) * cap),
+               o_ur = add(sizeof(float) * cap), o_dp = add(sizeof(float) * cap);
+  f->packed_bytes = align_up_sz(used, 256);
+  const size_t o_ang = add(sizeof(float) * cap), o_sc = add(sizeof(float) * nl), o_cs = add(sizeof(int32_t) * (ORBX_GRID_COLS * ORBX_GRID_ROWS + 1)),
+               o_ids = add(sizeof(int32_t) * cap), o_feat = add(sizeof(float4) * cap);
+  if (cudaMalloc(&f->d_block, used + 256) != cudaSuccess || cudaHostAlloc(&f->h_mirror, f->packed_bytes, cudaHostAllocDefault) != cudaSuccess) {
+    set_error("frame block allocation failed");
+    free_frame_block(f);
+    return ORBX_ERR_CUDA;
+  }
+  uint8_t* b = f->d_block;
+  f->d_count = (int32_t*)(b + o_cnt); f->d_kps = (orbx_keypoint*)(b + o_kps); f->d_desc = b + o_desc; f->d_unkps = (orbx_keypoint*)(b + o_un);
+  f->d_uright = (float*)(b + o_ur); f->d_depth = (float*)(b + o_dp); f->d_angle = (float*)(b + o_ang); f->d_scale = (float*)(b + o_sc);
+  f->d_cellStart = (int32_t*)(b + o_cs); f->d_ids = (int32_t*)(b + o_ids); f->d_feat = (float4*)(b + o_feat);
+  if (cudaMemcpy(f->d_scale, h->scale.data(), sizeof(float) * nl, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("frame block initialisation failed");
+    free_frame_block(f);
+    return ORBX_ERR_CUDA;
+  }
+  h->framesAll.push_back(f);
+  *out = f;
+  return ORBX_OK;
+}
+
 int check_handle(orbx_handle h) {
   if (!h) { set_error("null handle"); return ORBX_ERR_ARG; }
   return ORBX_OK;
@@ -471,6 +515,17 @@ int orbx_device_count(int* n) {
   cudaError_t e = cudaGetDeviceCount(&c);
   if (e != cudaSuccess) { *n = 0; set_error(cudaGetErrorString(e)); return ORBX_ERR_CUDA; }
   *n = c;
+  return ORBX_OK;
+}
+
+int orbx_host_alloc(size_t bytes, int write_combined, void** out) {
+  if (!out || bytes == 0) { set_error("bad argument"); return ORBX_ERR_ARG; }
+  *out = nullptr;
+  ORBX_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+  return ORBX_OK;
+}
+int orbx_host_free(void* p) {
+  if (p) ORBX_CUDA(cudaFreeHost(p));
   return ORBX_OK;
 }
 
@@ -553,6 +608,8 @@ int orbx_destroy(orbx_handle h) {
   if (!h) return ORBX_OK;
   cudaSetDevice(h->p.device);
   cudaDeviceSynchronize();
+  for (orbx_frame* f : h->framesAll) free_frame_block(f);      // frames die with their extractor (documented in orb_b200.h)
+  h->framesAll.clear(); h->framePool.clear();
   if (h->lane2) orbx_destroy(h->lane2);
   if (h->laneFork) cudaEventDestroy(h->laneFork);
   if (h->laneJoin) cudaEventDestroy(h->laneJoin);
@@ -892,6 +949,109 @@ int orbx_extract_match_batch(orbx_handle h, const uint8_t* imgs, int nframes, in
     return ORBX_ERR_CUDA;
   }
   ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+// ---- device-resident frame: Frame::Frame (frame.cpp:22-32) in one call -----------------------------------------------------
+// image up -> the extractor's kernel chain -> frame_finish_kernel (undistortKeyPoints, findDepth, assignFeaturesToGrid, the
+// searches' per-feature records) -> ONE packed copy down.  Everything is enqueued on the handle's stream before the single
+// synchronisation; the depth image (when given) goes up on the copy stream under the extraction kernels.
+int orbx_frame_create(orbx_handle h, const orbx_camera* cam, const uint8_t* img, int w, int height, size_t stride, const float* depth,
+                      size_t depth_row_stride, orbx_frame_t* out, int* n) {
+  if (check_handle(h)) return ORBX_ERR_ARG;
+  if (!cam || !img || !out || w <= 0 || height <= 0 || stride < (size_t)w ||
+      (depth && (depth_row_stride < sizeof(float) * (size_t)w || depth_row_stride % sizeof(float)))) {
+    set_error("bad argument");
+    return ORBX_ERR_ARG;
+  }
+  *out = nullptr;
+  ORBX_CUDA(cudaSetDevice(h->p.device));
+  orbx_frame* f = nullptr;
+  if (!h->framePool.empty()) { f = h->framePool.back(); h->framePool.pop_back(); }
+  else if (int rc = alloc_frame_block(h, &f)) return rc;
+  auto fail = [&](int rc) { h->framePool.push_back(f); return rc; };
+  const size_t pitch = align_up_sz((size_t)w, 64), fbytes = pitch * height;
+  if (h->d_in_bytes < fbytes) {
+    cudaFree(h->d_in); h->d_in = nullptr; h->d_in_bytes = 0;
+    if (cudaMalloc(&h->d_in, fbytes) != cudaSuccess) { set_error("input staging allocation failed"); return fail(ORBX_ERR_CUDA); }
+    h->d_in_bytes = fbytes;
+  }
+  cudaStream_t st = h->stream;
+  cudaError_t e = pitch == stride ? cudaMemcpyAsync(h->d_in, img, fbytes, cudaMemcpyHostToDevice, st)
+                                  : cudaMemcpy2DAsync(h->d_in, pitch, img, stride, w, height, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return fail(ORBX_ERR_CUDA); }
+  cudaEvent_t depthUp = nullptr;
+  if (depth) {
+    const size_t dbytes = sizeof(float) * (size_t)w * height;
+    if (f->depthImgBytes < dbytes) {
+      cudaFree(f->d_depthImg); f->d_depthImg = nullptr; f->depthImgBytes = 0;
+      if (cudaMalloc(&f->d_depthImg, dbytes) != cudaSuccess) { set_error("depth staging allocation failed"); return fail(ORBX_ERR_CUDA); }
+      f->depthImgBytes = dbytes;
+    }
+    if (!h->copyStream) {
+      if (cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaStreamCreateWithFlags(&h->backStream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(ORBX_ERR_CUDA); }
+    }
+    e = cudaMemcpy2DAsync(f->d_depthImg, sizeof(float) * (size_t)w, depth, depth_row_stride, sizeof(float) * (size_t)w, height,
+                          cudaMemcpyHostToDevice, h->copyStream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&depthUp, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(depthUp, h->copyStream);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); if (depthUp) cudaEventDestroy(depthUp); return fail(ORBX_ERR_CUDA); }
+  }
+  int rc = orbx_extract_batch_device(h, h->d_in, 1, w, height, pitch, fbytes, f->d_kps, f->d_desc, f->cap, f->d_count, st);
+  if (rc == ORBX_OK && depthUp && cudaStreamWaitEvent(st, depthUp, 0) != cudaSuccess) { set_error("event wait failed"); rc = ORBX_ERR_CUDA; }
+  if (rc == ORBX_OK)
+    rc = frame_finish_launch(cam, f->d_kps, f->d_count, 1, f->cap, depth ? f->d_depthImg : nullptr, w, height, sizeof(float) * (size_t)w, 0,
+                             f->d_unkps, f->d_uright, f->d_depth, f->d_cellStart, f->d_ids, f->d_feat, f->d_angle, st);
+  if (rc == ORBX_OK) {
+    h->launches += 1;
+    e = cudaMemcpyAsync(f->h_mirror, f->d_block, f->packed_bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = ORBX_ERR_CUDA; }
+  } else {
+    cudaStreamSynchronize(st);
+  }
+  if (depthUp) cudaEventDestroy(depthUp);
+  if (rc) return fail(rc);
+  const int32_t c = *(const int32_t*)f->h_mirror;
+  f->n = std::max(0, std::min((int)c, f->cap));
+  f->xmin = cam->xmin; f->xmax = cam->xmax; f->ymin = cam->ymin; f->ymax = cam->ymax;
+  h->framesLive++;
+  if (n) *n = f->n;
+  *out = f;
+  return ORBX_OK;
+}
+
+int orbx_frame_size(orbx_frame_t f, int* n) {
+  if (!f || !n) { set_error("null argument"); return ORBX_ERR_ARG; }
+  *n = f->n;
+  return ORBX_OK;
+}
+
+// Host copies of the frame's members out of the pinned mirror (no device traffic).  Any pointer may be NULL.
+int orbx_frame_get(orbx_frame_t f, orbx_keypoint* kps, uint8_t* desc, orbx_keypoint* unkps, float* uright, float* depth, int cap) {
+  if (!f || cap < 0) { set_error("bad argument"); return ORBX_ERR_ARG; }
+  if (cap < f->n) { set_error("keypoint buffer too small"); return ORBX_ERR_CAPACITY; }
+  const uint8_t* m = f->h_mirror;
+  const size_t n = (size_t)f->n;
+  if (kps) memcpy(kps, m + ((uint8_t*)f->d_kps - f->d_block), sizeof(orbx_keypoint) * n);
+  if (desc) memcpy(desc, m + (f->d_desc - f->d_block), 32 * n);
+  if (unkps) memcpy(unkps, m + ((uint8_t*)f->d_unkps - f->d_block), sizeof(orbx_keypoint) * n);
+  if (uright) memcpy(uright, m + ((uint8_t*)f->d_uright - f->d_block), sizeof(float) * n);
+  if (depth) memcpy(depth, m + ((uint8_t*)f->d_depth - f->d_block), sizeof(float) * n);
+  return ORBX_OK;
+}
+
+int orbx_frame_destroy(orbx_frame_t f) {
+  if (!f) return ORBX_OK;
+  orbx_extractor* h = f->owner;
+  h->framesLive--;
+  if (h->framePool.size() < 8) h->framePool.push_back(f);      // the tracking thread keeps 2-3 frames alive; key frames persist
+  else {
+    cudaSetDevice(f->device);
+    h->framesAll.erase(std::remove(h->framesAll.begin(), h->framesAll.end(), f), h->framesAll.end());
+    free_frame_block(f);
+  }
   return ORBX_OK;
 }
 

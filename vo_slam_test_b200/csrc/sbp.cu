@@ -24,7 +24,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
+#include "frame_handle.cuh"
 
 namespace orbx {
 
@@ -354,11 +354,16 @@ static int check_frame(const orbx_frame_view* f) {
   return ORBX_OK;
 }
 
+// `rf` != nullptr: the frame side is a device-resident orbx_frame (keypoints, descriptors, uRight, grid and per-feature records
+// already in HBM, built by orbx_frame_create); `frame` then only carries n / bounds / occupied0 and nothing of it but
+// occupied0 is uploaded, and no grid is built.
 template <bool LOCAL>
 static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid, const float* u, const float* v, const float* aux,
                       const int32_t* level, const float* angle_or_cos, const uint8_t* desc, const uint8_t* has_obs,
-                      const SearchParams& S, int32_t* assign, int* match_cnt, int device, int32_t* choice_out = nullptr) {
-  if (check_frame(frame)) return ORBX_ERR_ARG;
+                      const SearchParams& S, int32_t* assign, int* match_cnt, int device, int32_t* choice_out = nullptr,
+                      const orbx_frame* rf = nullptr) {
+  if (!rf && check_frame(frame)) return ORBX_ERR_ARG;
+  if (rf && (!frame || frame->n != rf->n || (frame->n > 0 && !frame->occupied0))) { set_error("bad resident frame view"); return ORBX_ERR_ARG; }
   if (!assign || !match_cnt || m < 0 || (m > 0 && (!valid || !u || !v || !aux || !level || !angle_or_cos || !desc || !has_obs))) {
     set_error("bad argument");
     return ORBX_ERR_ARG;
@@ -372,21 +377,31 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
   }
   // ---- pack every input into one pinned staging block ------------------------------------------------------
   Packer pk;
-  const size_t o_kps = pk.add(sizeof(orbx_keypoint) * n), o_desc = pk.add((size_t)n * 32), o_ur = pk.add(sizeof(float) * n);
-  const size_t o_sc = pk.add(sizeof(float) * frame->nlevels), o_occ = pk.add(n);
+  const size_t o_kps = pk.add(rf ? 0 : sizeof(orbx_keypoint) * n), o_desc = pk.add(rf ? 0 : (size_t)n * 32), o_ur = pk.add(rf ? 0 : sizeof(float) * n);
+  const size_t o_sc = pk.add(rf ? 0 : sizeof(float) * frame->nlevels), o_occ = pk.add(n);
   const size_t o_valid = pk.add(m), o_obs = pk.add(m), o_u = pk.add(sizeof(float) * m), o_v = pk.add(sizeof(float) * m);
   const size_t o_aux = pk.add(sizeof(float) * m), o_ac = pk.add(sizeof(float) * m), o_lvl = pk.add(sizeof(int32_t) * m);
   const size_t o_pd = pk.add((size_t)m * 32);
-  const size_t inBytes = align_up_sz(pk.used, 256);
+  // counters = the LAST 32 bytes of the upload (zeroed by it, no separate memset); the results follow directly, so that
+  // [counters | assign (n) | choice (m)] come back in ONE copy into the pinned staging block
+  const size_t inBytes = align_up_sz(pk.used + sizeof(int) * 8, 256);
+  const size_t o_misc = inBytes - sizeof(int) * 8;
+  pk.used = inBytes;
+  const size_t o_assign = pk.used; pk.used += sizeof(int32_t) * n;
+  const size_t o_choice = pk.used; pk.used += sizeof(int) * m;
+  const size_t outBytes = pk.used - o_misc;
   // device-only scratch behind the inputs
-  const size_t o_cellOf = pk.add(sizeof(int) * n), o_cellStart = pk.add(sizeof(int) * (NCELL + 1)), o_ids = pk.add(sizeof(int) * n);
-  const size_t o_feat = pk.add(sizeof(float4) * n), o_offs = pk.add(sizeof(int) * m), o_cnts = pk.add(sizeof(int) * m);
-  const size_t o_choice = pk.add(sizeof(int) * m), o_bF = pk.add(sizeof(int) * n), o_bT = pk.add(sizeof(int) * n);
-  const size_t o_assign = pk.add(sizeof(int32_t) * n), o_misc = pk.add(sizeof(int) * 8);
-  if (g_host.reserve(inBytes) || g_arena.reserve(pk.used + 256, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
+  const size_t o_cellOf = pk.add(rf ? 0 : sizeof(int) * n), o_cellStart = pk.add(rf ? 0 : sizeof(int) * (NCELL + 1)), o_ids = pk.add(rf ? 0 : sizeof(int) * n);
+  const size_t o_feat = pk.add(rf ? 0 : sizeof(float4) * n), o_offs = pk.add(sizeof(int) * m), o_cnts = pk.add(sizeof(int) * m);
+  const size_t o_bF = pk.add(sizeof(int) * n), o_bT = pk.add(sizeof(int) * n);
+  if (g_host.reserve(inBytes + outBytes + 256) || g_arena.reserve(pk.used + 256, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
   uint8_t* hb = g_host.base;
-  memcpy(hb + o_kps, frame->kps, sizeof(orbx_keypoint) * n); memcpy(hb + o_desc, frame->desc, (size_t)n * 32);
-  memcpy(hb + o_ur, frame->uright, sizeof(float) * n); memcpy(hb + o_sc, frame->scale_factors, sizeof(float) * frame->nlevels);
+  uint8_t* hout = hb + inBytes;
+  memset(hb + o_misc, 0, sizeof(int) * 8);
+  if (!rf) {
+    memcpy(hb + o_kps, frame->kps, sizeof(orbx_keypoint) * n); memcpy(hb + o_desc, frame->desc, (size_t)n * 32);
+    memcpy(hb + o_ur, frame->uright, sizeof(float) * n); memcpy(hb + o_sc, frame->scale_factors, sizeof(float) * frame->nlevels);
+  }
   memcpy(hb + o_occ, frame->occupied0, n);
   memcpy(hb + o_valid, valid, m); memcpy(hb + o_obs, has_obs, m); memcpy(hb + o_u, u, sizeof(float) * m);
   memcpy(hb + o_v, v, sizeof(float) * m); memcpy(hb + o_aux, aux, sizeof(float) * m); memcpy(hb + o_ac, angle_or_cos, sizeof(float) * m);
@@ -395,22 +410,23 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
   uint8_t* db = g_arena.take<uint8_t>(pk.used);
   ORBX_CUDA(cudaMemcpyAsync(db, hb, inBytes, cudaMemcpyHostToDevice, st));
   int* d_misc = (int*)(db + o_misc);
-  ORBX_CUDA(cudaMemsetAsync(d_misc, 0, sizeof(int) * 8, st));
 
   FrameDev F;
-  F.kps = (const orbx_keypoint*)(db + o_kps); F.desc = db + o_desc; F.n = n;
+  F.kps = rf ? rf->d_unkps : (const orbx_keypoint*)(db + o_kps); F.desc = rf ? rf->d_desc : db + o_desc; F.n = n;
   F.xmin = frame->xmin; F.xmax = frame->xmax; F.ymin = frame->ymin; F.ymax = frame->ymax;
   F.gw = (float)GC / (frame->xmax - frame->xmin);           // camera.cpp:47-48
   F.gh = (float)GR / (frame->ymax - frame->ymin);
-  F.scale = (const float*)(db + o_sc); F.nlevels = frame->nlevels; F.occupied0 = db + o_occ;
-  F.cellStart = (const int*)(db + o_cellStart); F.ids = (const int*)(db + o_ids); F.feat = (const float4*)(db + o_feat);
+  F.scale = rf ? rf->d_scale : (const float*)(db + o_sc); F.nlevels = frame->nlevels; F.occupied0 = db + o_occ;
+  F.cellStart = rf ? rf->d_cellStart : (const int*)(db + o_cellStart); F.ids = rf ? rf->d_ids : (const int*)(db + o_ids);
+  F.feat = rf ? rf->d_feat : (const float4*)(db + o_feat);
   PointsDev P;
   P.m = m; P.valid = db + o_valid; P.has_obs = db + o_obs; P.u = (const float*)(db + o_u); P.v = (const float*)(db + o_v);
   P.aux = (const float*)(db + o_aux); P.angle_or_cos = (const float*)(db + o_ac); P.level = (const int32_t*)(db + o_lvl);
   P.desc = db + o_pd;
 
-  grid_build_kernel<<<1, 1024, 0, st>>>(F.kps, (const float*)(db + o_ur), n, F.xmin, F.ymin, F.gw, F.gh, (int*)(db + o_cellOf),
-                                        (int*)(db + o_cellStart), (int*)(db + o_ids), (float4*)(db + o_feat));
+  if (!rf)
+    grid_build_kernel<<<1, 1024, 0, st>>>(F.kps, (const float*)(db + o_ur), n, F.xmin, F.ymin, F.gw, F.gh, (int*)(db + o_cellOf),
+                                          (int*)(db + o_cellStart), (int*)(db + o_ids), (float4*)(db + o_feat));
   // candidate buffer: start with 48 per point; on overflow the search is re-run with the exact size (known afterwards)
   size_t capCand = std::max<size_t>((size_t)m * 48, 4096);
   const int smemN = 8192;
@@ -424,13 +440,16 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
     sbp_resolve_kernel<LOCAL><<<1, kResolveThreads, sizeof(int) * 2 * smemN, st>>>(F, P, S, (const int*)(db + o_offs), (const int*)(db + o_cnts), d_cand,
                                                                               (int*)(db + o_choice), (int*)(db + o_bF), (int*)(db + o_bT), smemN,
                                                                               (int32_t*)(db + o_assign), d_misc);
-    int res[4] = {0, 0, 0, 0};
-    ORBX_CUDA(cudaMemcpyAsync(res, d_misc, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-    ORBX_CUDA(cudaMemcpyAsync(assign, db + o_assign, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-    if (choice_out) ORBX_CUDA(cudaMemcpyAsync(choice_out, db + o_choice, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(hout, db + o_misc, choice_out ? outBytes : outBytes - sizeof(int) * m, cudaMemcpyDeviceToHost, st));
     ORBX_CUDA(cudaStreamSynchronize(st));
     ORBX_CUDA(cudaGetLastError());
-    if (!res[3]) { *match_cnt = res[1]; return ORBX_OK; }
+    const int* res = (const int*)hout;
+    if (!res[3]) {
+      memcpy(assign, hout + sizeof(int) * 8, sizeof(int32_t) * n);
+      if (choice_out) memcpy(choice_out, hout + sizeof(int) * 8 + sizeof(int32_t) * n, sizeof(int32_t) * m);
+      *match_cnt = res[1];
+      return ORBX_OK;
+    }
     capCand = (size_t)res[0] + 1024;      // exact need (the allocation counter keeps counting past the capacity)
   }
   set_error("candidate buffer overflow");
@@ -481,6 +500,48 @@ int orbx_search_by_projection_local(const orbx_frame_view* frame, const orbx_sbp
                           assign, match_cnt, device);
 }
 
+
+// ---- the same three tracking-thread searches against a device-resident frame (orbx_frame_t) ---------------------------------
+static int resident_view(const orbx_frame* f, const uint8_t* occupied0, orbx_frame_view* v) {
+  if (!f || (f->n > 0 && !occupied0)) { set_error("null frame handle / occupied0"); return ORBX_ERR_ARG; }
+  memset(v, 0, sizeof(*v));
+  v->n = f->n; v->xmin = f->xmin; v->xmax = f->xmax; v->ymin = f->ymin; v->ymax = f->ymax; v->nlevels = f->nlevels; v->occupied0 = occupied0;
+  return ORBX_OK;
+}
+
+int orbx_search_by_projection_frame_h(orbx_frame_t frame, const uint8_t* occupied0, const orbx_sbp_frame_points* pts, float radius, float bf,
+                                      int forward, int backward, int check_rot, int32_t* assign, int* match_cnt) {
+  orbx_frame_view v;
+  if (!pts) { set_error("null points"); return ORBX_ERR_ARG; }
+  if (resident_view(frame, occupied0, &v)) return ORBX_ERR_ARG;
+  SearchParams S{};
+  S.radius = radius; S.bf = bf; S.forward = forward; S.backward = backward; S.check_rot = check_rot; S.ratio = 0.f;
+  S.th = (float)TH_HIGH; S.level_span_lo = -1; S.level_span_hi = 1;
+  return run_search<false>(&v, pts->m, pts->valid, pts->u, pts->v, pts->invz, pts->octave, pts->angle, pts->desc, pts->has_obs, S,
+                           assign, match_cnt, frame->device, nullptr, frame);
+}
+
+int orbx_search_by_projection_local_h(orbx_frame_t frame, const uint8_t* occupied0, const orbx_sbp_local_points* pts, float th_radius,
+                                      float ratio, int32_t* assign, int* match_cnt) {
+  orbx_frame_view v;
+  if (!pts) { set_error("null points"); return ORBX_ERR_ARG; }
+  if (resident_view(frame, occupied0, &v)) return ORBX_ERR_ARG;
+  SearchParams S{};
+  S.radius = th_radius; S.ratio = ratio; S.th = (float)TH_HIGH;
+  return run_search<true>(&v, pts->m, pts->valid, pts->u, pts->v, pts->ur, pts->level, pts->view_cos, pts->desc, pts->has_obs, S,
+                          assign, match_cnt, frame->device, nullptr, frame);
+}
+
+int orbx_search_by_projection_reloc_h(orbx_frame_t frame, const uint8_t* occupied0, const orbx_sbp_frame_points* pts, float radius,
+                                      float dist_threshold, int check_rot, int32_t* assign, int* match_cnt) {
+  orbx_frame_view v;
+  if (!pts) { set_error("null points"); return ORBX_ERR_ARG; }
+  if (resident_view(frame, occupied0, &v)) return ORBX_ERR_ARG;
+  SearchParams S{};
+  S.radius = radius; S.check_rot = check_rot; S.th = dist_threshold; S.block_all = 1; S.host_gates = 1; S.level_span_lo = -1; S.level_span_hi = 1;
+  return run_search<false>(&v, pts->m, pts->valid, pts->u, pts->v, pts->invz, pts->octave, pts->angle, pts->desc, pts->has_obs, S,
+                           assign, match_cnt, frame->device, nullptr, frame);
+}
 
 // Matcher::searchByProjection(Frame*, KeyFrame*, radius, distThreshold, found, checkRot)  (matcher.cpp:150-272).
 // pts->valid folds the host-side gates (:173-200: null/bad/found, z <= 0, image bounds, distance range); pts->octave is
