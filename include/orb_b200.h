@@ -335,8 +335,9 @@ int orbx_frame_finish_device(const orbx_camera* cam, const orbx_keypoint* d_kps,
  * descriptors, uRight, the 64x48 CSR grid -- in HBM; the *_h searches take the handle, so per search only the projected map
  * points and the frame's `occupied0` flags go up and the assignment comes down.  Results are bit-identical to
  * orbx_extract + orbx_frame_finish + the host-array searches.
- *   depth: float32 image (height x w, row stride in BYTES) or NULL; pinned memory (orbx_host_alloc) makes its upload
- *   asynchronous under the extraction kernels.  A frame belongs to the extractor handle that created it (its stream, its
+ *   depth: float32 image (height x w, row stride in BYTES, host memory) or NULL.  findDepth needs it only at the ~1000 keypoint
+ *   positions, so the image is never uploaded: the host samples it after the packed copy down and sends uRight_ (4 KB) back.
+ *   A frame belongs to the extractor handle that created it (its stream, its
  *   block pool): destroy frames before their extractor; orbx_destroy frees whatever is left.  One thread per extractor.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct orbx_frame* orbx_frame_t;

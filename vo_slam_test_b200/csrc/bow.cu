@@ -277,10 +277,15 @@ static int bow_run(const orbx_bow_side* a, const orbx_bow_side* b, int mode, flo
     offs[s][0] = add(res ? 0 : (size_t)S->n * 32); offs[s][1] = add(res ? 0 : sizeof(float) * S->n); offs[s][2] = add(S->n);
     offs[s][3] = add(sizeof(uint32_t) * S->ngroups); offs[s][4] = add(sizeof(int32_t) * (S->ngroups + 1)); offs[s][5] = add(sizeof(int32_t) * nfi);
   }
+  // the zero / -1 initialised work arrays ride in the same upload (no memsets); [match | res] come back in one copy
+  const size_t o_taken = add(sizeof(int) * b->n), o_hist = add(sizeof(int) * 32 + 256);
+  const size_t o_match = add(sizeof(int32_t) * nOut + sizeof(int) * 4), o_res = o_match + sizeof(int32_t) * nOut;
   const size_t inBytes = align_up_sz(used, 256);
-  const size_t o_taken = add(sizeof(int) * b->n), o_match = add(sizeof(int32_t) * nOut), o_bin = add(nOut), o_hist = add(sizeof(int) * 32),
-               o_res = add(sizeof(int) * 4);
-  if (g_bow.reserve(used + 256, inBytes, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
+  const size_t outBytes = sizeof(int32_t) * nOut + sizeof(int) * 4;
+  const size_t o_bin = add(nOut);
+  if (g_bow.reserve(used + 256, inBytes + outBytes + 256, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
+  memset(g_bow.h + o_taken, 0, sizeof(int) * b->n); memset(g_bow.h + o_hist, 0, sizeof(int) * 32 + 256);
+  memset(g_bow.h + o_match, 0xFF, sizeof(int32_t) * nOut); memset(g_bow.h + o_res, 0, sizeof(int) * 4);
   for (int s = 0; s < 2; ++s) {
     const orbx_bow_side* S = sides[s];
     const int nfi = S->group_start[S->ngroups];
@@ -291,9 +296,6 @@ static int bow_run(const orbx_bow_side* a, const orbx_bow_side* b, int mode, flo
   cudaStream_t st = nullptr;
   uint8_t* db = g_bow.d;
   ORBX_CUDA(cudaMemcpyAsync(db, g_bow.h, inBytes, cudaMemcpyHostToDevice, st));
-  ORBX_CUDA(cudaMemsetAsync(db + o_taken, 0, sizeof(int) * b->n, st));
-  ORBX_CUDA(cudaMemsetAsync(db + o_match, 0xFF, sizeof(int32_t) * nOut, st));      // -1
-  ORBX_CUDA(cudaMemsetAsync(db + o_hist, 0, sizeof(int) * 32 + 256, st));
   BowSideDev D[2];
   for (int s = 0; s < 2; ++s) {
     D[s].n = sides[s]->n; D[s].desc = db + offs[s][0]; D[s].angle = (const float*)(db + offs[s][1]); D[s].valid = db + offs[s][2];
@@ -305,12 +307,12 @@ static int bow_run(const orbx_bow_side* a, const orbx_bow_side* b, int mode, flo
                                                          (int32_t*)(db + o_match), (int8_t*)(db + o_bin), (int*)(db + o_hist));
   bow_finish_kernel<<<1, 1024, 0, st>>>(nOut, check_rot, (int32_t*)(db + o_match), (const int8_t*)(db + o_bin), (const int*)(db + o_hist),
                                         (int*)(db + o_res));
-  int res = 0;
-  ORBX_CUDA(cudaMemcpyAsync(match, db + o_match, sizeof(int32_t) * nOut, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(&res, db + o_res, sizeof(int), cudaMemcpyDeviceToHost, st));
+  uint8_t* hout = g_bow.h + inBytes;
+  ORBX_CUDA(cudaMemcpyAsync(hout, db + o_match, outBytes, cudaMemcpyDeviceToHost, st));
   ORBX_CUDA(cudaStreamSynchronize(st));
   ORBX_CUDA(cudaGetLastError());
-  *match_cnt = res;
+  memcpy(match, hout, sizeof(int32_t) * nOut);
+  *match_cnt = *(const int*)(hout + sizeof(int32_t) * nOut);
   return ORBX_OK;
 }
 

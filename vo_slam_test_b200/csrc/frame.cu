@@ -17,7 +17,7 @@
 namespace orbx {
 
 constexpr int FGC = ORBX_GRID_COLS, FGR = ORBX_GRID_ROWS, FNCELL = FGC * FGR;
-constexpr int kFrameThreads = 256;
+constexpr int kFrameThreads = 1024;    // one CTA per frame: 1000 keypoints = one undistortion per thread (latency of the tracked frame)
 
 struct CamDev {
   double fx, fy, cx, cy, ifx, ify;
@@ -150,6 +150,17 @@ int frame_finish_launch(const orbx_camera* cam, const orbx_keypoint* d_kps, cons
   if (int rc = make_cam(cam, C)) return rc;
   return launch_frame_finish(C, d_kps, d_counts, nframes, cap, d_depth, w, h, depthRow, depthFrame, d_unkps, d_uright, d_depthOut,
                              d_cellStart, d_ids, st, d_feat, d_angle);
+}
+
+// feat[i].w = uright[i] after the host filled uRight_ from a host-side depth image (orbx_frame_create)
+__global__ void patch_uright_kernel(const float* __restrict__ uright, float4* __restrict__ feat, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) feat[i].w = uright[i];
+}
+int frame_patch_uright(const float* d_uright, float4* d_feat, int n, cudaStream_t st) {
+  if (n > 0) patch_uright_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_uright, d_feat, n);
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
 }
 
 }  // namespace orbx

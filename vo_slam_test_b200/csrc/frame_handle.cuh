@@ -18,7 +18,6 @@ struct orbx_frame {
   float* d_uright = nullptr; float* d_depth = nullptr;
   // device-only: what the searches read
   float* d_angle = nullptr; float* d_scale = nullptr; int32_t* d_cellStart = nullptr; int32_t* d_ids = nullptr; float4* d_feat = nullptr;
-  float* d_depthImg = nullptr; size_t depthImgBytes = 0;
 };
 
 namespace orbx {
@@ -28,5 +27,7 @@ namespace orbx {
 int frame_finish_launch(const orbx_camera* cam, const orbx_keypoint* d_kps, const int32_t* d_counts, int nframes, int cap,
                         const float* d_depth, int w, int h, size_t depthRow, size_t depthFrame, orbx_keypoint* d_unkps, float* d_uright,
                         float* d_depthOut, int32_t* d_cellStart, int32_t* d_ids, float4* d_feat, float* d_angle, cudaStream_t st);
+
+int frame_patch_uright(const float* d_uright, float4* d_feat, int n, cudaStream_t st);
 
 }  // namespace orbx

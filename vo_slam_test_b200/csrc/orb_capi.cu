@@ -462,7 +462,7 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
 
 void free_frame_block(orbx_frame* f) {
   if (!f) return;
-  cudaFree(f->d_block); cudaFree(f->d_depthImg);
+  cudaFree(f->d_block);
   if (f->h_mirror) cudaFreeHost(f->h_mirror);
   delete f;
 }
@@ -980,28 +980,14 @@ int orbx_frame_create(orbx_handle h, const orbx_camera* cam, const uint8_t* img,
   cudaError_t e = pitch == stride ? cudaMemcpyAsync(h->d_in, img, fbytes, cudaMemcpyHostToDevice, st)
                                   : cudaMemcpy2DAsync(h->d_in, pitch, img, stride, w, height, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return fail(ORBX_ERR_CUDA); }
-  cudaEvent_t depthUp = nullptr;
-  if (depth) {
-    const size_t dbytes = sizeof(float) * (size_t)w * height;
-    if (f->depthImgBytes < dbytes) {
-      cudaFree(f->d_depthImg); f->d_depthImg = nullptr; f->depthImgBytes = 0;
-      if (cudaMalloc(&f->d_depthImg, dbytes) != cudaSuccess) { set_error("depth staging allocation failed"); return fail(ORBX_ERR_CUDA); }
-      f->depthImgBytes = dbytes;
-    }
-    if (!h->copyStream) {
-      if (cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
-          cudaStreamCreateWithFlags(&h->backStream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(ORBX_ERR_CUDA); }
-    }
-    e = cudaMemcpy2DAsync(f->d_depthImg, sizeof(float) * (size_t)w, depth, depth_row_stride, sizeof(float) * (size_t)w, height,
-                          cudaMemcpyHostToDevice, h->copyStream);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&depthUp, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventRecord(depthUp, h->copyStream);
-    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); if (depthUp) cudaEventDestroy(depthUp); return fail(ORBX_ERR_CUDA); }
-  }
+  // findDepth (frame.cpp:108-133) needs the depth image only at the ~1000 keypoint positions, which exist after the extraction:
+  // uploading the whole image (1.2 MB, pageable in the reference: 55 us) would cost more than the rest of the constructor's
+  // copies together.  The kernel therefore leaves depth_/uRight_ at -1; after the one packed copy down the host samples the
+  // image at the ORIGINAL keypoints with the reference's float->int truncation, computes uRight_ = unKp.x - bf/d in IEEE float
+  // (one division, one subtraction: no contraction possible) and sends the 4 KB of uRight_ back for the searches.
   int rc = orbx_extract_batch_device(h, h->d_in, 1, w, height, pitch, fbytes, f->d_kps, f->d_desc, f->cap, f->d_count, st);
-  if (rc == ORBX_OK && depthUp && cudaStreamWaitEvent(st, depthUp, 0) != cudaSuccess) { set_error("event wait failed"); rc = ORBX_ERR_CUDA; }
   if (rc == ORBX_OK)
-    rc = frame_finish_launch(cam, f->d_kps, f->d_count, 1, f->cap, depth ? f->d_depthImg : nullptr, w, height, sizeof(float) * (size_t)w, 0,
+    rc = frame_finish_launch(cam, f->d_kps, f->d_count, 1, f->cap, nullptr, w, height, sizeof(float) * (size_t)w, 0,
                              f->d_unkps, f->d_uright, f->d_depth, f->d_cellStart, f->d_ids, f->d_feat, f->d_angle, st);
   if (rc == ORBX_OK) {
     h->launches += 1;
@@ -1011,10 +997,30 @@ int orbx_frame_create(orbx_handle h, const orbx_camera* cam, const uint8_t* img,
   } else {
     cudaStreamSynchronize(st);
   }
-  if (depthUp) cudaEventDestroy(depthUp);
   if (rc) return fail(rc);
   const int32_t c = *(const int32_t*)f->h_mirror;
   f->n = std::max(0, std::min((int)c, f->cap));
+  if (depth && f->n > 0) {
+    uint8_t* m = f->h_mirror;
+    const orbx_keypoint* hk = (const orbx_keypoint*)(m + ((uint8_t*)f->d_kps - f->d_block));
+    const orbx_keypoint* hu = (const orbx_keypoint*)(m + ((uint8_t*)f->d_unkps - f->d_block));
+    float* hur = (float*)(m + ((uint8_t*)f->d_uright - f->d_block));
+    float* hdp = (float*)(m + ((uint8_t*)f->d_depth - f->d_block));
+    const float bf = cam->bf;
+    for (int i = 0; i < f->n; ++i) {
+      const int col = std::min(std::max((int)hk[i].x, 0), w - 1), row = std::min(std::max((int)hk[i].y, 0), height - 1);   // at<float>(v,u)
+      const volatile float dv = *(const float*)((const char*)depth + (size_t)row * depth_row_stride + (size_t)col * sizeof(float));
+      if (dv > 0) {                                                     // frame.cpp:126-130
+        volatile float q = bf / dv;
+        hdp[i] = dv; hur[i] = hu[i].x - q;
+      }
+    }
+    // the searches run on the legacy default stream: the 4 KB and the patch kernel are ordered in front of them there
+    e = cudaMemcpyAsync(f->d_uright, hur, sizeof(float) * (size_t)f->n, cudaMemcpyHostToDevice, nullptr);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return fail(ORBX_ERR_CUDA); }
+    if (int r2 = frame_patch_uright(f->d_uright, f->d_feat, f->n, nullptr)) return fail(r2);
+    h->launches += 1;
+  }
   f->xmin = cam->xmin; f->xmax = cam->xmax; f->ymin = cam->ymin; f->ymax = cam->ymax;
   h->framesLive++;
   if (n) *n = f->n;
