@@ -343,9 +343,15 @@ int orbx_frame_finish_device(const orbx_camera* cam, const orbx_keypoint* d_kps,
 typedef struct orbx_frame* orbx_frame_t;
 int orbx_frame_create(orbx_handle h, const orbx_camera* cam, const uint8_t* img, int w, int height, size_t stride,
                       const float* depth, size_t depth_row_stride, orbx_frame_t* out, int* n);
+/* Make an existing host-side Frame / KeyFrame resident (e.g. a key frame that relocalisation or loop closing searches into
+ * repeatedly): unKeypoints_ / descriptors_ / uRight_ / scaleFactors_ of `view` go up once, the grid is built on the device;
+ * view->occupied0 is ignored.  The handle works with every *_h search; orbx_frame_get is not available for it. */
+int orbx_frame_upload(const orbx_frame_view* view, int device, orbx_frame_t* out);
 int orbx_frame_size(orbx_frame_t f, int* n);
 /* host copies of keypoints_ / descriptors_ / unKeypoints_ / uRight_ / depth_ (any pointer may be NULL; cap >= n) */
 int orbx_frame_get(orbx_frame_t f, orbx_keypoint* kps, uint8_t* desc, orbx_keypoint* unkps, float* uright, float* depth, int cap);
+/* the frame's 64x48 grid as the CSR of orbx_grid_build (Frame::gridKeypoints_, frame.cpp:72-89); cap >= number of gridded ids */
+int orbx_frame_grid(orbx_frame_t f, int32_t* cell_start, int32_t* ids, int cap);
 int orbx_frame_destroy(orbx_frame_t f);
 /* occupied0[i] (i < n): as orbx_frame_view.occupied0 of the corresponding host-array search */
 int orbx_search_by_projection_frame_h(orbx_frame_t frame, const uint8_t* occupied0, const orbx_sbp_frame_points* pts, float radius,

@@ -65,6 +65,7 @@ class ORBextractor {
     }
   }
 
+  orbx_handle handle() const { return h_; }      // for myslam_b200::constructFrame (orb_b200_frame.hpp)
   int GetLevels() { return nlevels_; }
   float GetScaleFactor() { return scaleFactor_; }
   std::vector<float> GetScaleFactors() { return mvScaleFactor; }

@@ -32,6 +32,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -68,6 +69,20 @@ struct FrameArrays {
     view.occupied0 = occupied.data();
   }
 };
+
+// Device-resident frames (orbx_frame_t, include/orb_b200.h): one handle per Frame* / KeyFrame*, looked up by the searches below.
+// A frame registered here is searched in place in HBM (only the projected points and the "already holds a point" flags go up
+// per call) instead of being flattened and re-uploaded.  The handle must describe the frame's CURRENT unKeypoints_ /
+// descriptors_ / uRight_ (a Frame's features never change after its constructor; drop the handle in the destructor).
+inline std::unordered_map<const void*, orbx_frame_t>& residentMap() { static std::unordered_map<const void*, orbx_frame_t> m; return m; }
+inline std::mutex& residentMutex() { static std::mutex m; return m; }
+inline orbx_frame_t resident(const void* frame, int n) {
+  std::lock_guard<std::mutex> lock(residentMutex());
+  std::unordered_map<const void*, orbx_frame_t>::const_iterator it = residentMap().find(frame);
+  if (it == residentMap().end()) return nullptr;
+  int hn = -1;
+  return (orbx_frame_size(it->second, &hn) == ORBX_OK && hn == n) ? it->second : nullptr;
+}
 
 // A DBoW3::FeatureVector (std::map<NodeId, std::vector<unsigned>>, iterated in node-id order) as the CSR of orbx_bow_side.
 template <class FeatVecT>
@@ -110,6 +125,32 @@ struct BowSide {
 
 }  // namespace detail
 
+// Register `handle` (from orbx_frame_create, see orb_b200_frame.hpp constructFrame) as the resident copy of `frame`; an older
+// handle of the same object is destroyed.
+inline void adoptResident(const void* frame, orbx_frame_t handle) {
+  std::lock_guard<std::mutex> lock(detail::residentMutex());
+  orbx_frame_t& slot = detail::residentMap()[frame];
+  if (slot && slot != handle) orbx_frame_destroy(slot);
+  slot = handle;
+}
+// Upload a host-side Frame / KeyFrame once (key frames that relocalisation / local-map tracking search repeatedly).
+template <class FrameT>
+orbx_frame_t makeResident(FrameT* frame, int device = 0) {
+  detail::FrameArrays<FrameT> a(frame);
+  orbx_frame_t h = nullptr;
+  detail::check(orbx_frame_upload(&a.view, device, &h));
+  adoptResident(frame, h);
+  return h;
+}
+// Call from the frame's destructor (or when its features are rebuilt).
+inline void dropResident(const void* frame) {
+  std::lock_guard<std::mutex> lock(detail::residentMutex());
+  std::unordered_map<const void*, orbx_frame_t>::iterator it = detail::residentMap().find(frame);
+  if (it == detail::residentMap().end()) return;
+  orbx_frame_destroy(it->second);
+  detail::residentMap().erase(it);
+}
+
 // Matcher::searchByProjection(Frame* frame_curr, Frame* frame_last, radius, checkRot)          matcher.cpp:18-148
 // Host: the per-point gates and the projection of :33-66 (same types, same float casts); device: the window search, the
 // "already holds an observed point" exclusion (:90), the stereo gate (:93-99), the strict-< argmin (:104-108), TH_HIGH
@@ -150,16 +191,24 @@ int searchByProjection(FrameT* frame_curr, FrameT* frame_last, const float radiu
     std::memcpy(&desc[(size_t)i * 32], mp->getDescriptor().data, 32);
   }
 
-  detail::FrameArrays<FrameT> cur(frame_curr);
-  for (int i = 0; i < cur.view.n; ++i)
-    cur.occupied[i] = frame_curr->mappoints_[i] && frame_curr->mappoints_[i]->observe_cnt_ > 0;
+  const int n = (int)frame_curr->unKeypoints_.size();
+  std::vector<uint8_t> occupied(n, 0);
+  for (int i = 0; i < n; ++i)
+    occupied[i] = frame_curr->mappoints_[i] && frame_curr->mappoints_[i]->observe_cnt_ > 0;
   orbx_sbp_frame_points pts = {M, valid.data(), u.data(), v.data(), invz.data(), octave.data(), angle.data(), desc.data(),
                                has_obs.data()};
-  std::vector<int32_t> assign(cur.view.n > 0 ? cur.view.n : 1, -1);
+  std::vector<int32_t> assign(n, -1);
   int match_cnt = 0;
-  detail::check(orbx_search_by_projection_frame(&cur.view, &pts, radius, bf, forward, backward, checkRot, assign.data(),
-                                                &match_cnt, device));
-  for (int i = 0; i < cur.view.n; ++i) {
+  if (orbx_frame_t rh = detail::resident(frame_curr, n)) {              // the frame is resident in HBM: search it in place
+    detail::check(orbx_search_by_projection_frame_h(rh, occupied.data(), &pts, radius, bf, forward, backward, checkRot, assign.data(),
+                                                    &match_cnt));
+  } else {
+    detail::FrameArrays<FrameT> cur(frame_curr);
+    cur.view.occupied0 = occupied.data();
+    detail::check(orbx_search_by_projection_frame(&cur.view, &pts, radius, bf, forward, backward, checkRot, assign.data(),
+                                                  &match_cnt, device));
+  }
+  for (int i = 0; i < n; ++i) {
     if (assign[i] >= 0) frame_curr->mappoints_[i] = frame_last->mappoints_[assign[i]];
     else if (assign[i] == -2) frame_curr->mappoints_[i] = nullptr;
   }
@@ -187,14 +236,21 @@ int searchByProjection(FrameT* frame, const std::vector<MapPointT*>& mappoints, 
     has_obs[i] = mp->getObsCnt() > 0;
     std::memcpy(&desc[(size_t)i * 32], mp->getDescriptor().data, 32);
   }
-  detail::FrameArrays<FrameT> cur(frame);
-  for (int i = 0; i < cur.view.n; ++i) cur.occupied[i] = frame->mappoints_[i] && frame->mappoints_[i]->getObsCnt() > 0;
+  const int n = (int)frame->unKeypoints_.size();
+  std::vector<uint8_t> occupied(n, 0);
+  for (int i = 0; i < n; ++i) occupied[i] = frame->mappoints_[i] && frame->mappoints_[i]->getObsCnt() > 0;
   orbx_sbp_local_points pts = {M, valid.data(), u.data(), v.data(), ur.data(), level.data(), view_cos.data(), desc.data(),
                                has_obs.data()};
-  std::vector<int32_t> assign(cur.view.n > 0 ? cur.view.n : 1, -1);
+  std::vector<int32_t> assign(n, -1);
   int match_cnt = 0;
-  detail::check(orbx_search_by_projection_local(&cur.view, &pts, thRadius, ratio, assign.data(), &match_cnt, device));
-  for (int i = 0; i < cur.view.n; ++i)
+  if (orbx_frame_t rh = detail::resident(frame, n)) {
+    detail::check(orbx_search_by_projection_local_h(rh, occupied.data(), &pts, thRadius, ratio, assign.data(), &match_cnt));
+  } else {
+    detail::FrameArrays<FrameT> cur(frame);
+    cur.view.occupied0 = occupied.data();
+    detail::check(orbx_search_by_projection_local(&cur.view, &pts, thRadius, ratio, assign.data(), &match_cnt, device));
+  }
+  for (int i = 0; i < n; ++i)
     if (assign[i] >= 0) frame->mappoints_[i] = mappoints[assign[i]];
   return match_cnt;
 }
@@ -240,17 +296,27 @@ int searchByProjection(FrameT* frame_curr, KeyFrameT* keyframe, const float radi
     angle[i] = keyframe->unKeypoints_[i].angle;
     std::memcpy(&desc[(size_t)i * 32], mp->getDescriptor().data, 32);
   }
-  detail::FrameArrays<FrameT> cur(frame_curr);
-  cur.view.scale_factors = keyframe->scaleFactors_.data();                                     // :203
-  cur.view.nlevels = (int)keyframe->scaleFactors_.size();
-  for (int i = 0; i < cur.view.n; ++i) cur.occupied[i] = frame_curr->mappoints_[i] != nullptr;  // :218
+  const int n = (int)frame_curr->unKeypoints_.size();
+  std::vector<uint8_t> occupied(n, 0);
+  for (int i = 0; i < n; ++i) occupied[i] = frame_curr->mappoints_[i] != nullptr;               // :218
   orbx_sbp_frame_points pts = {M, valid.data(), u.data(), v.data(), zerosf.data(), octave.data(), angle.data(), desc.data(),
                                zeros8.data()};
-  std::vector<int32_t> assign(cur.view.n > 0 ? cur.view.n : 1, -1);
+  std::vector<int32_t> assign(n, -1);
   int match_cnt = 0;
-  detail::check(orbx_search_by_projection_reloc(&cur.view, &pts, radius, distThreshold, checkRot, assign.data(), &match_cnt,
-                                                device));
-  for (int i = 0; i < cur.view.n; ++i) {
+  // the window radius uses the KEY FRAME's scale factors (:203); the resident frame carries its own, so the handle is used
+  // only when they are the same table (one extractor: always, in the reference)
+  orbx_frame_t rh = keyframe->scaleFactors_ == frame_curr->scaleFactors_ ? detail::resident(frame_curr, n) : nullptr;
+  if (rh) {
+    detail::check(orbx_search_by_projection_reloc_h(rh, occupied.data(), &pts, radius, distThreshold, checkRot, assign.data(), &match_cnt));
+  } else {
+    detail::FrameArrays<FrameT> cur(frame_curr);
+    cur.view.scale_factors = keyframe->scaleFactors_.data();                                   // :203
+    cur.view.nlevels = (int)keyframe->scaleFactors_.size();
+    cur.view.occupied0 = occupied.data();
+    detail::check(orbx_search_by_projection_reloc(&cur.view, &pts, radius, distThreshold, checkRot, assign.data(), &match_cnt,
+                                                  device));
+  }
+  for (int i = 0; i < n; ++i) {
     if (assign[i] >= 0) frame_curr->mappoints_[i] = mappoints[assign[i]];
     else if (assign[i] == -2) frame_curr->mappoints_[i] = nullptr;
   }
@@ -582,7 +648,10 @@ int searchByBoW(KeyFrameT* keyframe, FrameT* frame, std::vector<MapPointT*>& map
   for (int i = 0; i < a.side.n; ++i) a.valid[i] = mappoints[i] && !mappoints[i]->isBad();      // :476-478
   std::vector<int32_t> match(bside.side.n > 0 ? bside.side.n : 1, -1);
   int match_cnt = 0;
-  detail::check(orbx_search_by_bow(&a.side, &bside.side, 0, ratio, TH_LOW, checkRot, match.data(), &match_cnt, device));
+  if (orbx_frame_t rh = detail::resident(frame, bside.side.n))      // descriptors / angles of the frame are read in place
+    detail::check(orbx_search_by_bow_h(&a.side, rh, &bside.side, ratio, TH_LOW, checkRot, match.data(), &match_cnt));
+  else
+    detail::check(orbx_search_by_bow(&a.side, &bside.side, 0, ratio, TH_LOW, checkRot, match.data(), &match_cnt, device));
   for (int i = 0; i < bside.side.n; ++i)
     if (match[i] >= 0) mappointMatches[i] = mappoints[match[i]];                               // :508 (cleared ones stay null, :552)
   return match_cnt;

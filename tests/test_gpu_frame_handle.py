@@ -48,6 +48,8 @@ def test_frame_create_equals_oracle(vo, with_depth, cam):
         wun, wur, wdp, wstart, wids = P.frame_finish(rk, cam, depth)
         assert fr.unkps.tobytes() == wun.tobytes()
         assert fr.uright.tobytes() == wur.tobytes() and fr.depth.tobytes() == wdp.tobytes()
+        start, ids = fr.grid()
+        assert np.array_equal(start, wstart) and np.array_equal(ids, wids[:wstart[-1]])
         fr.close()
     ex.close()
 
@@ -111,6 +113,35 @@ def test_searches_on_the_handle_equal_oracle(vo, stereo):
         assert gc == wc and np.array_equal(got, want)
     assert wc > 100
     fr.close(); ex.close()
+
+
+def test_uploaded_frame_searches_equal_oracle(vo):
+    """orbx_frame_upload: a host-side frame (BASELINE config 4 shape: 10 k points, stereo on) made resident once, searched
+    repeatedly."""
+    P = oracle.Port()
+    kps, desc = P.extract(synth.make_frame(42))
+    sf = P.tables()[0]
+    frame, pts = synth.make_projection_case(kps, desc, sf, 10000, seed=1, stereo=True)
+    up = vo.UploadedFrame(frame)
+    M = vo.Matcher(0.9)
+    for rep in range(2):
+        want, wc = P.sbp_frame(frame, pts, 15.0)
+        got, gc = M.searchByProjectionH(up, frame["occupied0"], pts, 15.0)
+        assert gc == wc and np.array_equal(got, want) and wc > 500
+    frameL, ptsL = synth.make_projection_case(kps, desc, sf, 10000, seed=2, stereo=True, local=True)
+    frameL["uright"] = frame["uright"]
+    want, wc = P.sbp_local(frameL, ptsL, 3.0, 0.8)
+    got, gc = vo.Matcher(0.8).searchByProjectionLocalH(up, frameL["occupied0"], ptsL, 3.0)
+    assert gc == wc and np.array_equal(got, want)
+    B = synth.make_bow_side(desc, kps["angle"], None, 9, 2)
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, len(kps), 700)
+    kd = synth.flip_bits(desc[src], rng.integers(0, 40, 700), rng)
+    A = synth.make_bow_side(kd, kps["angle"][src], None, 9, 1)
+    want, wc = P.search_by_bow(A, B, 0, 0.7, 50, True)
+    got, gc = vo.Matcher(0.7).searchByBoWH(A, up, B)
+    assert gc == wc and np.array_equal(got, want)
+    up.close()
 
 
 def test_two_live_frames_and_batch_use_of_the_same_extractor(vo):

@@ -51,7 +51,7 @@ def test_matcher_adapter_host_logic_on_port(tmp_path):
                                                os.path.join(TOOLS, "cabi_on_port.cpp"), "-L" + odir, "-lorbport",
                                                "-Wl,-rpath," + odir, "-o", exe])
     out = _run([exe])
-    assert "all comparisons identical" in out and out.count(" same") == 49 and "DIFFERENT" not in out, out
+    assert "all comparisons identical" in out and out.count(" same") == 53 and "DIFFERENT" not in out, out
     for seed in range(1000, 1000 + 40 * 16, 16):          # 40 more families of scenes (4 rounds each) through every entry point
         out = _run([exe, str(seed)])
         assert "all comparisons identical" in out and "DIFFERENT" not in out, (seed, out)
@@ -70,7 +70,7 @@ def test_port_behind_adapter_equals_reference_matcher_cpp(tmp_path):
                                                "-Wl,-rpath," + odir] + REF_LINK + ["-o", exe])
     out = _run([exe])
     assert "checker: the reference's own src/matcher.cpp" in out
-    assert "all comparisons identical" in out and out.count(" same") == 49 and "DIFFERENT" not in out, out
+    assert "all comparisons identical" in out and out.count(" same") == 53 and "DIFFERENT" not in out, out
     for seed in range(1000, 1000 + 40 * 16, 16):
         out = _run([exe, str(seed)])
         assert "all comparisons identical" in out and "DIFFERENT" not in out, (seed, out)
@@ -97,7 +97,7 @@ def test_matcher_adapter_on_gpu(tmp_path):
     if os.path.isdir(log_dir):                      # keep the program's report (incl. its timing lines) next to the other GPU logs
         with open(os.path.join(log_dir, "matcher_adapter_gpu.log"), "w") as f:
             f.write(out)
-    assert "all comparisons identical" in out and out.count(" same") == 49 and "DIFFERENT" not in out, out
+    assert "all comparisons identical" in out and out.count(" same") == 56 and "DIFFERENT" not in out, out
 
 
 @pytest.mark.gpu
@@ -115,7 +115,7 @@ def test_matcher_adapter_on_gpu_against_reference_matcher_cpp(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     out = r.stdout
     assert "checker: the reference's own src/matcher.cpp" in out
-    assert "all comparisons identical" in out and out.count(" same") == 49 and "DIFFERENT" not in out, out
+    assert "all comparisons identical" in out and out.count(" same") == 56 and "DIFFERENT" not in out, out
 
 
 def test_report_equals_results_of_the_reference_matcher(tmp_path):

@@ -131,6 +131,67 @@ int orbx_search_by_bow(const orbx_bow_side* a, const orbx_bow_side* b, int mode,
   *match_cnt = port_search_by_bow((const port_bow_side*)a, (const port_bow_side*)b, mode, ratio, th_low, check_rot, match);
   return ORBX_OK;
 }
+// ---- device-resident frames, port flavour: the "resident" copy is a host copy of the arrays; the *_h searches rebuild the
+// view from it, so the adapter's handle path (registry look-up, occupied0 only) runs on a machine without a GPU too
+}  // extern "C"
+#include <vector>
+struct orbx_frame {
+  std::vector<orbx_keypoint> kps; std::vector<uint8_t> desc; std::vector<float> uright, scale;
+  float xmin, xmax, ymin, ymax;
+  orbx_frame_view view(const uint8_t* occupied0) const {
+    orbx_frame_view v;
+    v.kps = kps.data(); v.desc = desc.data(); v.uright = uright.data(); v.n = (int)kps.size();
+    v.xmin = xmin; v.xmax = xmax; v.ymin = ymin; v.ymax = ymax; v.scale_factors = scale.data(); v.nlevels = (int)scale.size();
+    v.occupied0 = occupied0;
+    return v;
+  }
+};
+extern "C" {
+int orbx_frame_upload(const orbx_frame_view* v, int, orbx_frame_t* out) {
+  orbx_frame* f = new orbx_frame();
+  f->kps.assign(v->kps, v->kps + v->n); f->desc.assign(v->desc, v->desc + (size_t)v->n * 32);
+  f->uright.assign(v->uright, v->uright + v->n); f->scale.assign(v->scale_factors, v->scale_factors + v->nlevels);
+  f->xmin = v->xmin; f->xmax = v->xmax; f->ymin = v->ymin; f->ymax = v->ymax;
+  *out = f;
+  return ORBX_OK;
+}
+int orbx_frame_size(orbx_frame_t f, int* n) { *n = (int)f->kps.size(); return ORBX_OK; }
+int orbx_frame_destroy(orbx_frame_t f) { delete f; return ORBX_OK; }
+int orbx_search_by_projection_frame_h(orbx_frame_t f, const uint8_t* occ, const orbx_sbp_frame_points* p, float radius, float bf,
+                                      int forward, int backward, int check_rot, int32_t* assign, int* match_cnt) {
+  const orbx_frame_view v = f->view(occ);
+  return orbx_search_by_projection_frame(&v, p, radius, bf, forward, backward, check_rot, assign, match_cnt, 0);
+}
+int orbx_search_by_projection_local_h(orbx_frame_t f, const uint8_t* occ, const orbx_sbp_local_points* p, float th_radius, float ratio,
+                                      int32_t* assign, int* match_cnt) {
+  const orbx_frame_view v = f->view(occ);
+  return orbx_search_by_projection_local(&v, p, th_radius, ratio, assign, match_cnt, 0);
+}
+int orbx_search_by_projection_reloc_h(orbx_frame_t f, const uint8_t* occ, const orbx_sbp_frame_points* p, float radius,
+                                      float dist_threshold, int check_rot, int32_t* assign, int* match_cnt) {
+  const orbx_frame_view v = f->view(occ);
+  return orbx_search_by_projection_reloc(&v, p, radius, dist_threshold, check_rot, assign, match_cnt, 0);
+}
+int orbx_search_by_bow_h(const orbx_bow_side* a, orbx_frame_t f, const orbx_bow_side* groups, float ratio, int th_low, int check_rot,
+                         int32_t* match, int* match_cnt) {
+  orbx_bow_side b = *groups;
+  std::vector<float> angle(f->kps.size() ? f->kps.size() : 1);
+  for (size_t i = 0; i < f->kps.size(); ++i) angle[i] = f->kps[i].angle;
+  b.desc = f->desc.data(); b.angle = angle.data();            // read from the "resident" copy, like the library does
+  return orbx_search_by_bow(a, &b, 0, ratio, th_low, check_rot, match, match_cnt, 0);
+}
+// The extractor itself is not served by the port here (tests/tools/adapter_check.cpp and the Python tests cover it on the GPU):
+// orbx_create fails, and matcher_adapter_check.cpp skips its constructFrame block.
+int orbx_create(const orbx_params*, orbx_handle* out) { *out = nullptr; return ORBX_ERR_CUDA; }
+int orbx_destroy(orbx_handle) { return ORBX_OK; }
+int orbx_max_keypoints(orbx_handle, int* cap) { *cap = 0; return ORBX_ERR_CUDA; }
+int orbx_extract(orbx_handle, const uint8_t*, int, int, size_t, orbx_keypoint*, uint8_t*, int, int*) { return ORBX_ERR_CUDA; }
+int orbx_frame_create(orbx_handle, const orbx_camera*, const uint8_t*, int, int, size_t, const float*, size_t, orbx_frame_t* out, int*) {
+  *out = nullptr;
+  return ORBX_ERR_CUDA;
+}
+int orbx_frame_get(orbx_frame_t, orbx_keypoint*, uint8_t*, orbx_keypoint*, float*, float*, int) { return ORBX_ERR_CUDA; }
+int orbx_frame_grid(orbx_frame_t, int32_t*, int32_t*, int) { return ORBX_ERR_CUDA; }
 int hamm_knn2(const uint8_t* q, int nq, const uint8_t* t, long long nt, int th, float ratio, int32_t* idx, int32_t* d1,
               int32_t* d2, uint8_t* ok, int) {
   port_knn2(q, nq, t, nt, th, ratio, idx, d1, d2, ok, 1);

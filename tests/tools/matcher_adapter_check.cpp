@@ -424,6 +424,50 @@ int main(int argc, char** argv) {
     const int d1 = Matcher::computeDistance(b.cur.descriptors_.row(3), b.kf1.descriptors_.row(3));
     expect(d0 == d1, "computeDistance(Mat, Mat)");
   }
+  // The same tracking-thread searches with the current frame RESIDENT on the device (myslam_b200::makeResident registers an
+  // orbx_frame_t for the Frame*; the adapter then sends only the projected points and the occupancy flags per search).
+  {
+    Scene a, b;
+    buildScene(a, seedBase + 40, false);
+    buildScene(b, seedBase + 40, false);
+    Checker ref(0.7f);
+    Matcher gpu(0.7f);
+    std::printf("resident frame (orbx_frame_t)\n");
+    auto samePtrs = [&](const Frame& x, const Frame& y) {
+      for (size_t i = 0; i < x.mappoints_.size(); ++i)
+        if ((x.mappoints_[i] ? (long)(x.mappoints_[i] - &a.points[0]) : -1) != (y.mappoints_[i] ? (long)(y.mappoints_[i] - &b.points[0]) : -1)) return false;
+      return true;
+    };
+    Frame ca = a.cur, cb = b.cur;
+    myslam_b200::makeResident(&cb);
+    int na = ref.searchByProjection(&ca, &a.last, 15.f, true), nb = gpu.searchByProjection(&cb, &b.last, 15.f, true);
+    expect(na == nb && na > 50 && samePtrs(ca, cb), "resident: searchByProjection(Frame*, Frame*)");
+    ca = a.cur; cb = b.cur;                                        // same object, same features: the handle stays valid
+    na = ref.searchByProjection(&ca, a.local, 2.0f); nb = gpu.searchByProjection(&cb, b.local, 2.0f);
+    expect(na == nb && na > 50 && samePtrs(ca, cb), "resident: searchByProjection(Frame*, local map)");
+    {
+      KeyFrame ka = a.kf1, kb = b.kf1;
+      for (size_t i = 0; i < ka.mappoints_.size(); ++i) {
+        ka.mappoints_[i] = i < a.last.mappoints_.size() ? a.last.mappoints_[i] : nullptr;
+        kb.mappoints_[i] = i < b.last.mappoints_.size() ? b.last.mappoints_[i] : nullptr;
+        if (i < a.last.unKeypoints_.size()) { ka.unKeypoints_[i].angle = a.last.unKeypoints_[i].angle; kb.unKeypoints_[i].angle = b.last.unKeypoints_[i].angle; }
+      }
+      std::set<MapPoint*> fa, fb;
+      for (size_t i = 0; i < 900; i += 17) { fa.insert(&a.points[i]); fb.insert(&b.points[i]); }
+      ca = a.cur; cb = b.cur;
+      na = ref.searchByProjection(&ca, &ka, 15.f, 100.f, fa, true); nb = gpu.searchByProjection(&cb, &kb, 15.f, 100.f, fb, true);
+      expect(na == nb && na > 50 && samePtrs(ca, cb), "resident: searchByProjection(Frame*, KeyFrame*)");
+    }
+    std::vector<MapPoint*> ma, mb;
+    cb = b.cur;
+    na = ref.searchByBoW(&a.kf1, &a.cur, nullptr, ma, true); nb = gpu.searchByBoW(&b.kf1, &cb, mb, true);
+    bool same = na == nb && ma.size() == mb.size();
+    for (size_t i = 0; i < ma.size() && same; ++i)
+      same = (ma[i] ? (long)(ma[i] - &a.points[0]) : -1) == (mb[i] ? (long)(mb[i] - &b.points[0]) : -1);
+    expect(same && na > 50, "resident: searchByBoW(KeyFrame*, Frame*)");
+    myslam_b200::dropResident(&cb);
+  }
+
   // Frame::Frame after the extractor call (frame.cpp:29-31): undistortKeyPoints + findDepth + assignFeaturesToGrid
   for (int variant = 0; variant < 3; ++variant) {
     Scene a, b;
@@ -457,6 +501,93 @@ int main(int argc, char** argv) {
       for (int iy = 0; iy < 48 && same; ++iy) same = a.cur.gridKeypoints_[ix][iy] == b.cur.gridKeypoints_[ix][iy];
     std::printf("finishFrame variant %d: %d of %zu keypoints moved by the undistortion\n", variant, moved, a.cur.keypoints_.size());
     expect(same && (variant == 2 ? moved == 0 : moved > 900), "Frame::Frame post-processing (undistort, depth, grid)");
+  }
+
+  // Frame::Frame as ONE call (myslam_b200::constructFrame: extractor + undistort + depth + grid on the device, frame left
+  // resident) against the step-by-step path: orbx_extract, then the reference's own three member functions on the host.
+  {
+    orbx_params prm = {1000, 1.2f, 8, 20, 7, 0};
+    orbx_handle ex = nullptr;
+    if (orbx_create(&prm, &ex) == ORBX_OK) {
+      Scene a, b;
+      buildScene(a, 4711u, false);
+      buildScene(b, 4711u, false);
+      const float dist[5] = {0.2624f, -0.9531f, -0.0054f, 0.0026f, 1.1633f};
+      a.cam.setIntrinsics(dist, 5); b.cam.setIntrinsics(dist, 5);
+      std::vector<uchar> pix(480 * 640);
+      g_seed = 99u;
+      for (int y = 0; y < 480; ++y)
+        for (int x = 0; x < 640; ++x) pix[(size_t)y * 640 + x] = (uchar)((((x / 24) + (y / 24)) & 1) * 120 + 60 + (rnd() % 8) + ((x * 7 + y * 3) % 23));
+      cv::Mat gray(480, 640, CV_8UC1, pix.data(), 640);
+      std::vector<float> depthStore(480 * 640);
+      cv::Mat depth(480, 640, CV_32F, depthStore.data(), 640 * sizeof(float));
+      for (int y = 0; y < 480; ++y)
+        for (int x = 0; x < 640; ++x) depth.at<float>(y, x) = (rnd() % 6 == 0) ? 0.f : 0.5f + 7.f * urand();
+      // step by step (reference members on the host)
+      int cap = 0, n = 0;
+      orbx_max_keypoints(ex, &cap);
+      Frame& fa = a.cur;
+      fa.keypoints_.resize(cap);
+      std::vector<uchar> dsc((size_t)cap * 32);
+      const int rc = orbx_extract(ex, pix.data(), 640, 480, 640, reinterpret_cast<orbx_keypoint*>(fa.keypoints_.data()), dsc.data(), cap, &n);
+      fa.keypoints_.resize(n); fa.N_ = n;
+      fa.descriptors_ = cv::Mat(n, 32, CV_8UC1);
+      std::memcpy(fa.descriptors_.data, dsc.data(), (size_t)n * 32);
+      fa.unKeypoints_.clear(); fa.uRight_.clear(); fa.depth_.clear();
+      fa.undistortKeyPoints(); fa.findDepth(depth); fa.assignFeaturesToGrid();
+      // one call
+      Frame& fb = b.cur;
+      myslam_b200::constructFrame(&fb, ex, gray, depth);
+      bool same = rc == ORBX_OK && n > 900 && fb.N_ == fa.N_ && fa.keypoints_.size() == fb.keypoints_.size() &&
+                  std::memcmp(fa.keypoints_.data(), fb.keypoints_.data(), (size_t)n * sizeof(cv::KeyPoint)) == 0 &&
+                  std::memcmp(fa.unKeypoints_.data(), fb.unKeypoints_.data(), (size_t)n * sizeof(cv::KeyPoint)) == 0 &&
+                  std::memcmp(fa.descriptors_.data, fb.descriptors_.data, (size_t)n * 32) == 0 && fa.uRight_ == fb.uRight_ && fa.depth_ == fb.depth_;
+      for (int ix = 0; ix < 64 && same; ++ix)
+        for (int iy = 0; iy < 48 && same; ++iy) same = fa.gridKeypoints_[ix][iy] == fb.gridKeypoints_[ix][iy];
+      int withDepth = 0;
+      for (int i = 0; i < n; ++i) withDepth += fb.uRight_[i] > 0;
+      std::printf("constructFrame: %d keypoints, %d with depth\n", n, withDepth);
+      expect(same && withDepth > 500, "Frame::Frame in one call (constructFrame) == extractor + reference members");
+      // the frame is resident: searches against it take the handle path and must equal the reference loops on the host copy
+      fa.mappoints_.assign(n, nullptr); fb.mappoints_.assign(n, nullptr);
+      Scene* sc[2] = {&a, &b};
+      for (int k = 0; k < 2; ++k) {                                // re-aim the scene's map points at the extracted features
+        Scene& s = *sc[k];
+        Frame& f = k ? fb : fa;
+        g_seed = 515u;
+        const SE3 Twc = f.Tcw_.inverse();
+        for (size_t i = 0; i < s.last.mappoints_.size(); ++i) {
+          const int j = (int)(rnd() % n);
+          MapPoint& mp = s.points[i];
+          const double z = 1.0 + 6.0 * urand();
+          const double u = f.unKeypoints_[j].pt.x + 6.0 * (urand() - 0.5), v = f.unKeypoints_[j].pt.y + 6.0 * (urand() - 0.5);
+          mp.pos_ = Twc * Vector3d((u - s.cam.cx_) / s.cam.fx_ * z, (v - s.cam.cy_) / s.cam.fy_ * z, z);
+          mp.descriptor_ = f.descriptors_.row(j).clone();
+          flipBits(mp.descriptor_.data, (int)(rnd() % 60));
+          s.last.unKeypoints_[i] = f.unKeypoints_[j];
+          mp.trackProj_u_ = (float)u; mp.trackProj_v_ = (float)v; mp.trackProj_uR_ = (float)u - 40.f / (float)z;
+          mp.trackScaleLevel_ = f.unKeypoints_[j].octave;
+        }
+      }
+      Checker ref(0.7f);
+      Matcher gpu(0.7f);
+      int na = ref.searchByProjection(&fa, &a.last, 15.f, true), nb = gpu.searchByProjection(&fb, &b.last, 15.f, true);
+      same = na == nb;
+      for (int i = 0; i < n && same; ++i)
+        same = (fa.mappoints_[i] ? (long)(fa.mappoints_[i] - &a.points[0]) : -1) == (fb.mappoints_[i] ? (long)(fb.mappoints_[i] - &b.points[0]) : -1);
+      std::printf("constructFrame + searchByProjection(Frame*,Frame*) on the resident frame: %d accepted\n", na);
+      expect(same && na > 100, "resident frame from constructFrame: searchByProjection(Frame*, Frame*)");
+      fa.mappoints_.assign(n, nullptr); fb.mappoints_.assign(n, nullptr);
+      na = ref.searchByProjection(&fa, a.local, 2.0f); nb = gpu.searchByProjection(&fb, b.local, 2.0f);
+      same = na == nb;
+      for (int i = 0; i < n && same; ++i)
+        same = (fa.mappoints_[i] ? (long)(fa.mappoints_[i] - &a.points[0]) : -1) == (fb.mappoints_[i] ? (long)(fb.mappoints_[i] - &b.points[0]) : -1);
+      expect(same && na > 100, "resident frame from constructFrame: searchByProjection(Frame*, local map)");
+      myslam_b200::dropResident(&fb);
+      orbx_destroy(ex);
+    } else {
+      std::printf("constructFrame: no extractor behind this C ABI (CPU port build) -> skipped\n");
+    }
   }
 
   // MapPoint::computeDescriptor for many points at once

@@ -12,7 +12,7 @@ Everything computes in hand-written CUDA behind the C ABI of ``include/orb_b200.
 (``vo_slam_test_b200/lib/libvoslam_b200.so``).  There is no CPU fallback: importing works anywhere, but
 any compute call without the built library or without a CUDA device raises.
 """
-from .api import (KP_DTYPE, Frame, HostBuffer, Matcher, ORBextractor, OrbError, camera, device_count, frame_finish, grid_build, knn2_device, knn2_merge_device,
+from .api import (KP_DTYPE, Frame, HostBuffer, UploadedFrame, Matcher, ORBextractor, OrbError, camera, device_count, frame_finish, grid_build, knn2_device, knn2_merge_device,
                   knn2_pairs_device, knn2_workspace_bytes, lib, lib_path, load_library, medoid_descriptors)
 
 __all__ = ["ORBextractor", "Matcher", "grid_build", "knn2_device", "KP_DTYPE", "OrbError", "device_count", "lib",

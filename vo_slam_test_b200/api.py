@@ -81,6 +81,8 @@ def load_library():
     L.orbx_frame_size.argtypes = [vp, vp]
     L.orbx_frame_get.argtypes = [vp, vp, vp, vp, vp, vp, i32]
     L.orbx_frame_destroy.argtypes = [vp]
+    L.orbx_frame_grid.argtypes = [vp, vp, vp, i32]
+    L.orbx_frame_upload.argtypes = [vp, i32, vp]
     L.orbx_search_by_projection_frame_h.argtypes = [vp, vp, vp, f32, f32, i32, i32, i32, vp, vp]
     L.orbx_search_by_projection_local_h.argtypes = [vp, vp, vp, f32, f32, vp, vp]
     L.orbx_search_by_projection_reloc_h.argtypes = [vp, vp, vp, f32, f32, i32, vp, vp]
@@ -430,6 +432,36 @@ class Frame:
         _check(self._lib.orbx_frame_get(self._h, _p(self.kps), _p(self.desc), _p(self.unkps), _p(self.uright), _p(self.depth), m))
         self.kps, self.desc, self.unkps = self.kps[:self.n], self.desc[:self.n], self.unkps[:self.n]
         self.uright, self.depth = self.uright[:self.n], self.depth[:self.n]
+
+    def grid(self):
+        """(cell_start[64*48+1], ids) like grid_build()."""
+        start = np.zeros(64 * 48 + 1, np.int32); ids = np.zeros(max(self.n, 1), np.int32)
+        _check(self._lib.orbx_frame_grid(self._h, _p(start), _p(ids), max(self.n, 1)))
+        return start, ids[:start[-1]].copy()
+
+    def close(self):
+        if self._h:
+            self._lib.orbx_frame_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class UploadedFrame:
+    """orbx_frame_upload: an existing host-side frame dict (kps = unKeypoints_, desc, uright, bounds, scale_factors) made
+    resident once; usable wherever a Frame handle is (the *_h searches)."""
+
+    def __init__(self, frame, device=0):
+        keep = []
+        v = Matcher._frame_view(dict(frame, occupied0=np.zeros(max(len(frame["kps"]), 1), np.uint8)), keep)
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        _check(self._lib.orbx_frame_upload(C.byref(v), device, C.byref(self._h)))
+        self.n = v.n
 
     def close(self):
         if self._h:

@@ -475,10 +475,10 @@ int alloc_frame_block(orbx_extractor* h, orbx_frame** out) {
   size_t used = 0;
   auto add = [&](size_t bytes) { used = align_up_sz(used, 256); size_t o = used; used += bytes; return o; };
   const size_t o_cnt = add(64), o_kps = add(sizeof(orbx_keypoint) * cap), o_desc = add((size_t)32 * cap), o_un = add(sizeof(orbx_keypoint) * cap),
-               o_ur = add(sizeof(float) * cap), o_dp = add(sizeof(float) * cap);
+               o_ur = add(sizeof(float) * cap), o_dp = add(sizeof(float) * cap),
+               o_cs = add(sizeof(int32_t) * (ORBX_GRID_COLS * ORBX_GRID_ROWS + 1)), o_ids = add(sizeof(int32_t) * cap);
   f->packed_bytes = align_up_sz(used, 256);
-  const size_t o_ang = add(sizeof(float) * cap), o_sc = add(sizeof(float) * nl), o_cs = add(sizeof(int32_t) * (ORBX_GRID_COLS * ORBX_GRID_ROWS + 1)),
-               o_ids = add(sizeof(int32_t) * cap), o_feat = add(sizeof(float4) * cap);
+  const size_t o_ang = add(sizeof(float) * cap), o_sc = add(sizeof(float) * nl), o_feat = add(sizeof(float4) * cap);
   if (cudaMalloc(&f->d_block, used + 256) != cudaSuccess || cudaHostAlloc(&f->h_mirror, f->packed_bytes, cudaHostAllocDefault) != cudaSuccess) {
     set_error("frame block allocation failed");
     free_frame_block(f);
@@ -1037,6 +1037,7 @@ int orbx_frame_size(orbx_frame_t f, int* n) {
 // Host copies of the frame's members out of the pinned mirror (no device traffic).  Any pointer may be NULL.
 int orbx_frame_get(orbx_frame_t f, orbx_keypoint* kps, uint8_t* desc, orbx_keypoint* unkps, float* uright, float* depth, int cap) {
   if (!f || cap < 0) { set_error("bad argument"); return ORBX_ERR_ARG; }
+  if (!f->h_mirror) { set_error("an uploaded frame has no host mirror (the caller holds the originals)"); return ORBX_ERR_ARG; }
   if (cap < f->n) { set_error("keypoint buffer too small"); return ORBX_ERR_CAPACITY; }
   const uint8_t* m = f->h_mirror;
   const size_t n = (size_t)f->n;
@@ -1048,9 +1049,27 @@ int orbx_frame_get(orbx_frame_t f, orbx_keypoint* kps, uint8_t* desc, orbx_keypo
   return ORBX_OK;
 }
 
+// The 64x48 grid as the CSR of orbx_grid_build (cell_start[64*48+1], ids[n]) -- Frame::gridKeypoints_ for host code that still
+// reads it.
+int orbx_frame_grid(orbx_frame_t f, int32_t* cell_start, int32_t* ids, int cap) {
+  if (!f || !cell_start || !ids) { set_error("bad argument"); return ORBX_ERR_ARG; }
+  if (!f->h_mirror) { set_error("an uploaded frame has no host mirror"); return ORBX_ERR_ARG; }
+  const int32_t* cs = (const int32_t*)(f->h_mirror + ((uint8_t*)f->d_cellStart - f->d_block));
+  const int total = cs[ORBX_GRID_COLS * ORBX_GRID_ROWS];
+  if (cap < total) { set_error("id buffer too small"); return ORBX_ERR_CAPACITY; }
+  memcpy(cell_start, cs, sizeof(int32_t) * (ORBX_GRID_COLS * ORBX_GRID_ROWS + 1));
+  memcpy(ids, f->h_mirror + ((uint8_t*)f->d_ids - f->d_block), sizeof(int32_t) * (size_t)total);
+  return ORBX_OK;
+}
+
 int orbx_frame_destroy(orbx_frame_t f) {
   if (!f) return ORBX_OK;
   orbx_extractor* h = f->owner;
+  if (!h) {                      // orbx_frame_upload: no extractor, no pool
+    cudaSetDevice(f->device);
+    free_frame_block(f);
+    return ORBX_OK;
+  }
   h->framesLive--;
   if (h->framePool.size() < 8) h->framePool.push_back(f);      // the tracking thread keeps 2-3 frames alive; key frames persist
   else {

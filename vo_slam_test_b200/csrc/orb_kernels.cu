@@ -728,7 +728,7 @@ __device__ __forceinline__ int fw_stage_b(const uint8_t* img, int sp, int aox, i
 // variants in the kernel (with all eight inlined, instruction-fetch stalls ate the whole gain of the dispatch).
 #define FW_DISPATCH(RES, FN, ...)                                                                   \
   do {                                                                                              \
-    if (hiT) RES = FN<0, false>(__VA_ARGS__);                                                       \
+    if (hiT || FW_NOFILTER_##FN) RES = FN<0, false>(__VA_ARGS__);                                   \
     else switch (sh) {                                                                              \
         case 0: RES = FN<0, true>(__VA_ARGS__); break;                                              \
         case 1: RES = FN<1, true>(__VA_ARGS__); break;                                              \
@@ -737,6 +737,12 @@ __device__ __forceinline__ int fw_stage_b(const uint8_t* img, int sp, int aox, i
       }                                                                                             \
   } while (0)
 
+// A/B switch: ORBX_FAST_NOB=1 runs stage b without its tests (stage-a survivors go straight to the arc score)
+#ifndef ORBX_FAST_NOB
+#define ORBX_FAST_NOB 0
+#endif
+#define FW_NOFILTER_fw_stage_a 0
+#define FW_NOFILTER_fw_stage_b ORBX_FAST_NOB
 #ifndef ORBX_FAST_MINB
 #define ORBX_FAST_MINB 16
 #endif

@@ -143,7 +143,7 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
 // ---- grid build (one CTA) ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) grid_build_kernel(const orbx_keypoint* __restrict__ kps, const float* __restrict__ uright,
                                                           int n, float xmin, float ymin, float gw, float gh, int* cellOf,
-                                                          int* cellStart, int* ids, float4* feat) {
+                                                          int* cellStart, int* ids, float4* feat, float* angle = nullptr) {
   __shared__ int cnt[NCELL];
   __shared__ int ws[40];
   const int tid = threadIdx.x, T = blockDim.x;
@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const orbx_keypoint* _
     if (gx >= 0 && gx < GC && gy >= 0 && gy < GR) { c = gx * GR + gy; atomicAdd(&cnt[c], 1); }   // :91-97
     cellOf[i] = c;
     if (feat) feat[i] = make_float4(k.x, k.y, __int_as_float(k.octave), uright ? uright[i] : -1.f);
+    if (angle) angle[i] = k.angle;
   }
   __syncthreads();
   const int total = block_exclusive_scan(cnt, NCELL, ws);
@@ -500,6 +501,50 @@ int orbx_search_by_projection_local(const orbx_frame_view* frame, const orbx_sbp
                           assign, match_cnt, device);
 }
 
+
+// Make an existing host-side Frame / KeyFrame resident: unKeypoints_, descriptors_, uRight_, scaleFactors_ go up once, the grid
+// and the per-feature records are built on the device.  The handle has no extractor (owner == nullptr) and no host mirror.
+int orbx_frame_upload(const orbx_frame_view* view, int device, orbx_frame_t* out) {
+  if (!out) { set_error("null argument"); return ORBX_ERR_ARG; }
+  *out = nullptr;
+  orbx_frame_view v;
+  if (view) { v = *view; static const uint8_t kZero = 0; if (!v.occupied0) v.occupied0 = &kZero; }
+  if (check_frame(view ? &v : nullptr)) return ORBX_ERR_ARG;
+  ORBX_CUDA(cudaSetDevice(device));
+  const int n = v.n, cap = std::max(n, 1), nl = v.nlevels;
+  Packer pk;
+  const size_t o_kps = pk.add(sizeof(orbx_keypoint) * cap), o_desc = pk.add((size_t)32 * cap), o_ur = pk.add(sizeof(float) * cap);
+  const size_t o_sc = pk.add(sizeof(float) * nl);
+  const size_t inBytes = align_up_sz(pk.used, 256);
+  const size_t o_ang = pk.add(sizeof(float) * cap), o_cs = pk.add(sizeof(int) * (NCELL + 1)), o_ids = pk.add(sizeof(int) * cap);
+  const size_t o_feat = pk.add(sizeof(float4) * cap), o_cellOf = pk.add(sizeof(int) * cap);
+  if (g_host.reserve(inBytes)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
+  orbx_frame* f = new orbx_frame();
+  if (cudaMalloc(&f->d_block, pk.used + 256) != cudaSuccess) { delete f; set_error("frame block allocation failed"); return ORBX_ERR_CUDA; }
+  uint8_t* hb = g_host.base;
+  if (n) {
+    memcpy(hb + o_kps, v.kps, sizeof(orbx_keypoint) * n); memcpy(hb + o_desc, v.desc, (size_t)32 * n);
+    memcpy(hb + o_ur, v.uright, sizeof(float) * n);
+  }
+  memcpy(hb + o_sc, v.scale_factors, sizeof(float) * nl);
+  uint8_t* b = f->d_block;
+  f->device = device; f->cap = cap; f->n = n; f->nlevels = nl;
+  f->xmin = v.xmin; f->xmax = v.xmax; f->ymin = v.ymin; f->ymax = v.ymax;
+  f->d_unkps = (orbx_keypoint*)(b + o_kps); f->d_kps = f->d_unkps; f->d_desc = b + o_desc; f->d_uright = (float*)(b + o_ur);
+  f->d_scale = (float*)(b + o_sc); f->d_angle = (float*)(b + o_ang); f->d_cellStart = (int32_t*)(b + o_cs); f->d_ids = (int32_t*)(b + o_ids);
+  f->d_feat = (float4*)(b + o_feat);
+  cudaStream_t st = nullptr;
+  cudaError_t e = cudaMemcpyAsync(b, hb, inBytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    grid_build_kernel<<<1, 1024, 0, st>>>(f->d_unkps, f->d_uright, n, f->xmin, f->ymin, (float)GC / (f->xmax - f->xmin),
+                                          (float)GR / (f->ymax - f->ymin), (int*)(b + o_cellOf), f->d_cellStart, f->d_ids, f->d_feat, f->d_angle);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // the staging block is reused by the next call
+  if (e != cudaSuccess) { cudaFree(f->d_block); delete f; set_error(cudaGetErrorString(e)); return ORBX_ERR_CUDA; }
+  *out = f;
+  return ORBX_OK;
+}
 
 // ---- the same three tracking-thread searches against a device-resident frame (orbx_frame_t) ---------------------------------
 static int resident_view(const orbx_frame* f, const uint8_t* occupied0, orbx_frame_view* v) {
