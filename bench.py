@@ -579,6 +579,42 @@ def run_b200(args, rank, world, local_rank):
     except Exception as exc:                          # noqa: BLE001
         link = {"error": str(exc)[:120]}
 
+    # ---- A/B of the opt-in Hamming variant (integer tensor pipe, identical results): the same resident step with it switched on --------
+    variants = None
+    if not args.skip_variants and npairs > 0:
+        try:
+            prev = api.set_hamming_variant(1)
+            for _ in range(3):
+                blk.step_resident(stream)
+            v0 = torch.cuda.Event(enable_timing=True); v1 = torch.cuda.Event(enable_timing=True)
+            barrier()
+            v0.record()
+            for _ in range(steps):
+                blk.step_resident(stream)
+            v1.record()
+            barrier()
+            vms = max_over_ranks(v0.elapsed_time(v1))
+            vchk = blk.checksum()
+            if world > 1:
+                dist.all_reduce(vchk)
+            h0 = torch.cuda.Event(enable_timing=True); h1 = torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(3):
+                api.knn2_pairs_device(blk.d_desc.data_ptr(), blk.d_counts.data_ptr(), cap, blk.d_qf.data_ptr(), blk.d_tf.data_ptr(), npairs, TH_LOW, RATIO,
+                                      blk.d_midx.data_ptr(), blk.d_md1.data_ptr(), blk.d_md2.data_ptr(), blk.d_mok.data_ptr(), stream)
+            h1.record()
+            torch.cuda.synchronize()
+            hms = h0.elapsed_time(h1) / 3
+            api.set_hamming_variant(prev)
+            variants = {"hamming_mma": {"value": job_frames * steps / (vms / 1000.0), "ms_per_step": vms / steps, "hamming_pairs_ms": hms,
+                                        "gmatch_per_s": stages["hamming_pairs"]["gmatch_per_s"] * stages["hamming_pairs"]["ms_per_step"] / hms,
+                                        "same_results": [int(x) for x in vchk.cpu().tolist()] == chk,
+                                        "what": "hamm_set_variant(1): descriptor bits as +-1 bytes on the integer tensor pipe (mma.sync IMMA.16832), "
+                                                "opt-in, bit-identical; the headline `value` uses the default POPC kernels"}}
+        except Exception as exc:                      # noqa: BLE001
+            variants = {"error": str(exc)[:160]}
+            api.set_hamming_variant(0)
+
     # ---- the other scaling mode beside it (N > 1): 4096 frames per GPU, every rank its own sequence ------------------------
     other = None
     if world > 1 and not args.skip_other:
@@ -665,6 +701,8 @@ def run_b200(args, rank, world, local_rank):
                 "hamming_roofline": hamming_roofline, "hamming_map": hamming_map, "single_frame": single, "cpu_baseline": cpu_baseline}
         if other is not None:
             line["other_scaling"] = other
+        if variants is not None:
+            line["variants"] = variants
         line.update(extra_cfg)
         emit(line)
     ex.close()
@@ -763,6 +801,16 @@ def bench_hamming_map(args, torch, dist, sharded, dev, rank, world, local_rank, 
     mms, out = time_map(xchg is not None)
     res = {"gmatch_per_s": world * Q * Ml / (mms * 1e6), "ms": mms, "queries": Q, "rows_per_gpu": Ml, "merge": merge_kind,
            "accepted": int(out[3].sum().item()), "equals_oracle": equals_oracle}
+    if not args.skip_variants:
+        try:
+            from vo_slam_test_b200 import api
+            prev = api.set_hamming_variant(1)
+            vms, vout = time_map(xchg is not None)
+            api.set_hamming_variant(prev)
+            res["variant_hamming_mma"] = {"ms": vms, "gmatch_per_s": world * Q * Ml / (vms * 1e6),
+                                          "same_results": all(bool(torch.equal(a, b)) for a, b in zip(out, vout))}
+        except Exception as exc:                      # noqa: BLE001
+            res["variant_hamming_mma"] = {"error": str(exc)[:160]}
     if xchg is not None:
         nms, ref = time_map(False)
         res["nccl_all_gather_ms"] = nms
@@ -980,6 +1028,7 @@ def main():
                          "replicated; weak: a batch per GPU")
     ap.add_argument("--skip-other", action="store_true", help="N > 1: do not also measure the other scaling mode")
     ap.add_argument("--skip-configs", action="store_true", help="do not add BASELINE configs 3/4 as extra keys")
+    ap.add_argument("--skip-variants", action="store_true", help="do not A/B the opt-in Hamming variant")
     ap.add_argument("--map-rows", type=int, default=2097152, help="map descriptors per GPU for the sharded kNN side metric")
     ap.add_argument("--skip-map", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

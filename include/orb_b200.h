@@ -169,6 +169,13 @@ int hamm_knn2_sharded_phases_device(const uint8_t* d_q, int nq, const uint8_t* d
 
 long long hamm_launch_count(void);
 
+/* Which kernels serve the hamm_* entry points and the frame-to-frame matching of orbx_extract_match_batch:
+ *   0 (default)  XOR + POPC on the integer pipe (carry-save tree, 5 POPC per pair) -- the design BASELINE's north_star states;
+ *   1            descriptor bits as +-1 bytes through the legacy integer tensor pipe (mma.sync m16n8k32 s8 -> IMMA.16832),
+ *                dot = 256 - 2 * hamming, exact integers: an A/B variant with bit-identical results (tests/test_gpu_hamming_mma.py).
+ * Returns the previous value; any other argument only queries.  Initial value: environment ORBX_HAMM_MMA. */
+int hamm_set_variant(int variant);
+
 /* ---------------------------------------------------------------------------------------------------
  * Grid index + projection searches
  *   grid:  Frame::assignFeaturesToGrid / getFeaturesInArea   (frame.cpp:72-97,199-247; camera.h:8-9)

@@ -13,6 +13,6 @@ print("roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"], 4), "lin
 print("hamming_map", d["hamming_map"])
 print("cpu", d["cpu_baseline"])
 print("parity", d["config"]["parity_spot_check"], d["config"]["checksum"])
-for k in ("config3_1080p", "config3_4k", "config4_sbp", "tracking_frame", "configs_error", "single_frame", "other_scaling"):
+for k in ("config3_1080p", "config3_4k", "config4_sbp", "tracking_frame", "configs_error", "single_frame", "other_scaling", "variants"):
     if k in d: print(k, d[k])
 PY

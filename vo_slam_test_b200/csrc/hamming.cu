@@ -203,6 +203,196 @@ __global__ void __launch_bounds__(kQT) knn2_pairs_kernel(const uint8_t* __restri
   ok[o] = accept(bd1, bd2, th, ratio);
 }
 
+// ---- opt-in variant: the distance matrix on the integer tensor pipe (ORBX_HAMM_MMA=1; default stays the POPC kernel) ----------
+// BASELINE's north_star keeps the Hamming stage off the tensor cores; the round-1 review asked for an A/B of exactly that
+// alternative, so it is built as a switchable variant with identical results.  Descriptor bits become +-1 bytes (bit 1 -> +1,
+// bit 0 -> -1), so dot(a, b) = 256 - 2 * hamming(a, b) is an exact integer and the packed key is ONE multiply-add of the
+// accumulator:  key = hamming << 23 | col = dot * (-2^22) + (2^30 + col).  On sm_100a ptxas lowers the one-bit mma.sync
+// (xor.popc / and.popc) to this same u8/s8 IMMA.16832 plus per-instruction LOP3 bit-plane masks, so expanding once per
+// tile in shared memory is the cheaper route to the same pipe (measured IMMA peak: tools/probes/imma_peak.cu).
+//   CTA = 128 queries (8 warps x 16 rows), A fragments for all 256 bits live in 32 registers per thread; train tiles of 64
+//   descriptors are expanded through a 256-entry byte -> 8-byte table into a double-buffered shared-memory tile (row pitch
+//   272 B: ldmatrix rows land in distinct banks); per 16 x 8 output tile 4 ldmatrix.x4 + 8 IMMA + the top-2 update of the four
+//   accumulators each thread owns; the 4 lanes that share a query row merge their candidates at the very end.
+#ifndef ORBX_MMA_UNROLL
+#define ORBX_MMA_UNROLL 2
+#endif
+constexpr int kMmaUnroll = ORBX_MMA_UNROLL;
+constexpr int kMQ = 256, kMT = 64, kMRow = 272;
+// the query tile (kMQ rows) is dead once the A fragments are in registers: the two train buffers live in the same bytes
+constexpr size_t kMmaSmem = 2048 + (size_t)kMQ * kMRow;
+static_assert(2 * kMT <= kMQ, "train double buffer aliases the query tile");
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void imma_s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 8 descriptor bytes (two words) -> 64 expanded bytes at dst (8-byte aligned)
+__device__ __forceinline__ void expand8(const uint2* lut, uint32_t lo, uint32_t hi, uint8_t* dst) {
+  uint2* d = reinterpret_cast<uint2*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d[i] = lut[(lo >> (8 * i)) & 0xFFu];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d[4 + i] = lut[(hi >> (8 * i)) & 0xFFu];
+}
+
+// Every warp owns 32 query rows (two m16 tiles): a B fragment fetched from shared memory feeds two IMMAs, which halves the
+// ldmatrix traffic per MMA -- with 16 rows per warp the shared-memory data pipe (85 % busy) bound the kernel, not the tensor
+// pipe (50 %) (profiles/r2_hamming_mma.md).
+// mma_scan: top-2 of the CTA's kMQ query rows (rows q0.. of qsrc, valid below nq) over train rows [0, nt) of tsrc (nt < 2^23);
+// a1/a2[i] = packed keys (distance << 23 | local train index) of row  q0 + warp*32 + (i>>1)*16 + lane/4 + 8*(i&1),  merged over
+// the 4 lanes of the row (valid in every lane).
+__device__ __forceinline__ void mma_scan(const uint8_t* __restrict__ qsrc, int nq, int q0, const uint8_t* __restrict__ tsrc, int nt,
+                                         uint8_t* msm, uint32_t (&a1)[4], uint32_t (&a2)[4]) {
+  uint2* lut = reinterpret_cast<uint2*>(msm);
+  uint8_t* qa = msm + 2048;
+  uint8_t* tb = qa;                                         // reused after the A fragments are loaded
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {  // byte -> 8 bytes: bit j set -> 0x01, clear -> 0xFF
+    uint32_t w[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j >> 2] |= (((uint32_t)tid >> j) & 1u ? 0x01u : 0xFFu) << (8 * (j & 3));
+    lut[tid] = make_uint2(w[0], w[1]);
+  }
+  __syncthreads();
+  {  // queries: 256 rows x 32 B, one descriptor per thread
+    uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+    if (q0 + tid < nq) {
+      const uint4* src = reinterpret_cast<const uint4*>(qsrc + (size_t)(q0 + tid) * 32);
+      v0 = __ldg(src); v1 = __ldg(src + 1);
+    }
+    uint8_t* dst = qa + (size_t)tid * kMRow;
+    expand8(lut, v0.x, v0.y, dst); expand8(lut, v0.z, v0.w, dst + 64);
+    expand8(lut, v1.x, v1.y, dst + 128); expand8(lut, v1.z, v1.w, dst + 192);
+  }
+  __syncthreads();
+  uint32_t A[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const uint8_t* base = qa + (size_t)(warp * 32 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kMRow + (lane >> 4) * 16;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) ldsm_x4(A[mt][ks], base + ks * 32);
+  }
+  __syncthreads();                                          // every warp holds its fragments: the tile becomes the train double buffer
+  const int ntiles = (nt + kMT - 1) / kMT;
+  // train tile: 64 rows x 32 B = 256 threads x 8 B; thread = (row, quarter)
+  const int tr = tid >> 2, tq = tid & 3;
+  auto fetch = [&](int t) {
+    const int row = t * kMT + tr;
+    return row < nt ? __ldg(reinterpret_cast<const uint2*>(tsrc + (size_t)row * 32) + tq) : make_uint2(0u, 0u);
+  };
+  if (ntiles > 0) { const uint2 v = fetch(0); expand8(lut, v.x, v.y, tb + (size_t)tr * kMRow + tq * 64); }
+  __syncthreads();
+  uint32_t k1[2][2], k2[2][2];                              // [m tile][row lane/4 | lane/4 + 8]
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { k1[i >> 1][i & 1] = kKeyInit; k2[i >> 1][i & 1] = kKeyInit; }
+  const uint32_t colLane = 0x40000000u + (uint32_t)((lane & 3) * 2);
+  for (int t = 0; t < ntiles; ++t) {
+    const bool more = t + 1 < ntiles;
+    uint2 nxt = make_uint2(0u, 0u);
+    if (more) nxt = fetch(t + 1);                           // in flight under this tile's MMAs
+    const uint8_t* tile = tb + (size_t)(t & 1) * kMT * kMRow;
+    const bool tail = (t + 1) * kMT > nt;                   // only the last tile can hold columns >= nt
+#pragma unroll kMmaUnroll
+    for (int n8 = 0; n8 < kMT / 8; ++n8) {
+      const uint8_t* brow = tile + (size_t)(n8 * 8 + (lane & 7)) * kMRow + (lane >> 3) * 16;
+      uint32_t Bf[4][4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) ldsm_x4(Bf[x], brow + x * 64);
+      int c[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        imma_s8(c[0], A[0][ks], Bf[ks >> 1][(ks & 1) * 2], Bf[ks >> 1][(ks & 1) * 2 + 1]);
+        imma_s8(c[1], A[1][ks], Bf[ks >> 1][(ks & 1) * 2], Bf[ks >> 1][(ks & 1) * 2 + 1]);
+      }
+      const uint32_t col = (uint32_t)(t * kMT + n8 * 8) + colLane;      // 2^30 + column of c[.][0] / c[.][2]
+      uint32_t kill0 = 0u, kill1 = 0u;
+      if (tail) {
+        const int cc = t * kMT + n8 * 8 + (lane & 3) * 2;
+        kill0 = cc >= nt ? 0xFFFFFFFFu : 0u; kill1 = cc + 1 >= nt ? 0xFFFFFFFFu : 0u;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t key0 = ((uint32_t)c[mt][0] * 0xFFC00000u + col) | kill0, key1 = ((uint32_t)c[mt][1] * 0xFFC00000u + col + 1u) | kill1;
+        const uint32_t key2 = ((uint32_t)c[mt][2] * 0xFFC00000u + col) | kill0, key3 = ((uint32_t)c[mt][3] * 0xFFC00000u + col + 1u) | kill1;
+        top2_update(k1[mt][0], k2[mt][0], key0); top2_update(k1[mt][0], k2[mt][0], key1);
+        top2_update(k1[mt][1], k2[mt][1], key2); top2_update(k1[mt][1], k2[mt][1], key3);
+      }
+    }
+    if (more) expand8(lut, nxt.x, nxt.y, tb + (size_t)((t + 1) & 1) * kMT * kMRow + (size_t)tr * kMRow + tq * 64);
+    __syncthreads();
+  }
+  // the 4 lanes of a row hold disjoint column subsets: two smallest keys of the union
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t x1 = k1[i >> 1][i & 1], x2 = k2[i >> 1][i & 1];
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      const uint32_t b1 = __shfl_xor_sync(0xffffffffu, x1, o), b2 = __shfl_xor_sync(0xffffffffu, x2, o);
+      x2 = min(max(x1, b1), min(x2, b2)); x1 = min(x1, b1);
+    }
+    a1[i] = x1; a2[i] = x2;
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) knn2_pairs_mma_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ counts, int cap,
+                                                                const int32_t* __restrict__ qf, const int32_t* __restrict__ tf, int th,
+                                                                float ratio, int32_t* idx, int32_t* d1, int32_t* d2, uint8_t* ok) {
+  extern __shared__ __align__(128) uint8_t msm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = blockIdx.y;
+  const int fq = qf[p], ft = tf[p];
+  const int nq = min(counts[fq], cap), nt = min(counts[ft], cap);
+  const int q0 = blockIdx.x * kMQ;
+  if (q0 >= nq) return;
+  uint32_t a1[4], a2[4];
+  mma_scan(desc + (size_t)fq * cap * 32, nq, q0, desc + (size_t)ft * cap * 32, nt, msm, a1, a2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = q0 + warp * 32 + (i >> 1) * 16 + (lane >> 2) + 8 * (i & 1);
+    if ((lane & 3) == 0 && r < nq) {
+      const int bd1 = (int)min(a1[i] >> 23, 256u), bd2 = (int)min(a2[i] >> 23, 256u);
+      const size_t o = (size_t)p * cap + r;
+      idx[o] = bd1 < 256 ? (int)(a1[i] & 0x7FFFFFu) : -1;
+      d1[o] = bd1; d2[o] = bd2;
+      ok[o] = accept(bd1, bd2, th, ratio);
+    }
+  }
+}
+
+// Same scan for one query set against a long train set (map-scale search): grid (ceil(nq/kMQ), nsplit) like knn2_kernel, same
+// outputs (final when there is one split, per-split partials (local idx + split offset, d1, d2) otherwise).
+__global__ void __launch_bounds__(256, 2) knn2_mma_kernel(const uint8_t* __restrict__ qs, int nq, const uint8_t* __restrict__ train, long long nt,
+                                                          long long per, int th, float ratio, int32_t* idx, int32_t* d1, int32_t* d2, uint8_t* ok,
+                                                          int32_t* part) {
+  extern __shared__ __align__(128) uint8_t msm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.y;
+  const long long t0 = (long long)s * per;
+  const int cnt = (int)min(per, nt - t0);
+  const int q0 = blockIdx.x * kMQ;
+  uint32_t a1[4], a2[4];
+  mma_scan(qs, nq, q0, train + (size_t)t0 * 32, cnt, msm, a1, a2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = q0 + warp * 32 + (i >> 1) * 16 + (lane >> 2) + 8 * (i & 1);
+    if ((lane & 3) == 0 && r < nq) {
+      const int bd1 = (int)min(a1[i] >> 23, 256u), bd2 = (int)min(a2[i] >> 23, 256u);
+      const int bi = bd1 < 256 ? (int)(t0 + (long long)(a1[i] & 0x7FFFFFu)) : -1;
+      if (gridDim.y == 1) {
+        idx[r] = bi; d1[r] = bd1; d2[r] = bd2;
+        ok[r] = accept(bd1, bd2, th, ratio);
+      } else {
+        int32_t* pp = part + ((size_t)s * nq + r) * 3;
+        pp[0] = bi; pp[1] = bd1; pp[2] = bd2;
+      }
+    }
+  }
+}
+
 // ---- sharded top-2 with the exchange fused into the kernels (no NCCL on the data path) -------------------------------
 // Every rank owns an exchange buffer in its HBM that all peers have mapped (CUDA IPC over NVLink / NVSwitch):
 //   int32 [0, 2*kMaxPeers)   flags[parity][source rank] = epoch of the last completed scatter of that source
@@ -309,6 +499,40 @@ static int pick_splits(int nq, long long nt, long long* per_out) {
   return (int)ns;
 }
 
+// which kernels serve the Hamming entry points: 0 = POPC (default, BASELINE's stated design), 1 = the integer-tensor-pipe
+// variant above (same results).  Initial value from ORBX_HAMM_MMA, changed at run time by hamm_set_variant().
+static std::atomic<int> g_variant{-1};
+static bool use_mma() {
+  int v = g_variant.load(std::memory_order_relaxed);
+  if (v < 0) {
+    v = (getenv("ORBX_HAMM_MMA") && atoi(getenv("ORBX_HAMM_MMA")) != 0) ? 1 : 0;
+    g_variant.store(v, std::memory_order_relaxed);
+  }
+  return v == 1;
+}
+static int mma_prepare() {
+  static thread_local int attrDev = -1;
+  int dev = 0;
+  ORBX_CUDA(cudaGetDevice(&dev));
+  if (attrDev != dev) {
+    ORBX_CUDA(cudaFuncSetAttribute(knn2_pairs_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    ORBX_CUDA(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    attrDev = dev;
+  }
+  return ORBX_OK;
+}
+// the local-shard scan of hamm_knn2_device / hamm_knn2_sharded*: grid (query tiles, splits)
+static int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_t, long long nt, long long per, int ns, int th, float ratio,
+                       int32_t* d_idx, int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok, int32_t* part, cudaStream_t st) {
+  if (use_mma()) {
+    if (int rc = mma_prepare()) return rc;
+    knn2_mma_kernel<<<dim3((nq + kMQ - 1) / kMQ, ns), 256, kMmaSmem, st>>>(d_q, nq, d_t, nt, per, th, ratio, d_idx, d_d1, d_d2, d_ok, part);
+  } else {
+    knn2_kernel<<<dim3((nq + kQT - 1) / kQT, ns), kQT, 0, st>>>(d_q, nq, d_t, nt, per, th, ratio, d_idx, d_d1, d_d2, d_ok, part);
+  }
+  return ORBX_OK;
+}
+
 }  // namespace orbx
 
 using namespace orbx;
@@ -316,6 +540,12 @@ using namespace orbx;
 extern "C" {
 
 long long hamm_launch_count(void) { return g_hamm_launches.load(); }
+
+int hamm_set_variant(int variant) {
+  const int prev = use_mma() ? 1 : 0;
+  if (variant == 0 || variant == 1) g_variant.store(variant, std::memory_order_relaxed);
+  return prev;
+}
 
 size_t hamm_knn2_workspace_bytes(int nq, long long nt) {
   long long per;
@@ -335,8 +565,7 @@ int hamm_knn2_device(const uint8_t* d_q, int nq, const uint8_t* d_t, long long n
     set_error("workspace too small (see hamm_knn2_workspace_bytes)");
     return ORBX_ERR_CAPACITY;
   }
-  dim3 grid((nq + kQT - 1) / kQT, ns);
-  knn2_kernel<<<grid, kQT, 0, st>>>(d_q, nq, d_t, nt, per, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace);
+  if (int rc = launch_knn2(d_q, nq, d_t, nt, per, ns, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace, st)) return rc;
   g_hamm_launches++;
   if (ns > 1) {
     const int32_t* part = (const int32_t*)d_workspace;
@@ -386,9 +615,15 @@ int hamm_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_counts, int c
     return ORBX_ERR_ARG;
   }
   if (npairs == 0) return ORBX_OK;
-  dim3 grid((cap + kQT - 1) / kQT, npairs);
   nvtxRangePushA("orbx:hamming_pairs");
-  knn2_pairs_kernel<<<grid, kQT, 0, (cudaStream_t)stream>>>(d_desc, d_counts, cap, d_qf, d_tf, th, ratio, d_idx, d_d1, d_d2, d_ok);
+  if (use_mma()) {
+    if (int rc = mma_prepare()) { nvtxRangePop(); return rc; }
+    dim3 grid((cap + kMQ - 1) / kMQ, npairs);
+    knn2_pairs_mma_kernel<<<grid, 256, kMmaSmem, (cudaStream_t)stream>>>(d_desc, d_counts, cap, d_qf, d_tf, th, ratio, d_idx, d_d1, d_d2, d_ok);
+  } else {
+    dim3 grid((cap + kQT - 1) / kQT, npairs);
+    knn2_pairs_kernel<<<grid, kQT, 0, (cudaStream_t)stream>>>(d_desc, d_counts, cap, d_qf, d_tf, th, ratio, d_idx, d_d1, d_d2, d_ok);
+  }
   nvtxRangePop();
   g_hamm_launches++;
   ORBX_CUDA(cudaGetLastError());
@@ -483,8 +718,7 @@ int hamm_knn2_sharded_phases_device(const uint8_t* d_q, int nq, const uint8_t* d
   const int parity = epoch & 1;
   if (phases & 1) {
     // local shard: per-split partials (ns > 1) or the shard result in the output arrays (ns == 1), local row indices
-    dim3 grid((nq + kQT - 1) / kQT, ns);
-    knn2_kernel<<<grid, kQT, 0, st>>>(d_q, nq, d_t, nt, per, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace);
+    if (int rc = launch_knn2(d_q, nq, d_t, nt, per, ns, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace, st)) return rc;
     const int32_t* part = (const int32_t*)d_workspace;
     if (ns > 1)
       knn2_merge_scatter_kernel<<<(nq + 127) / 128, 128, 0, st>>>(part, part + 1, part + 2, 3, ns, nq, shard_lo, peers, rank, world,
