@@ -949,6 +949,12 @@ struct OctSmem {
   int* slotPre;     // [maxSlots+1]
   int* ws;          // [40]
 };
+// (node labels in shared memory instead of global scratch were measured and dropped: 12 KB more per CTA costs a third of the
+// resident CTAs, 1.51 -> 1.73 ms per 4096 VGA frames)
+#ifndef ORBX_OCT_BATCH
+#define ORBX_OCT_BATCH 4
+#endif
+constexpr int kOctBatch = ORBX_OCT_BATCH;   // independent (label, key) fetches in flight per thread in the per-key loops
 
 __device__ __forceinline__ int quadrant_of(const short4 b, int x, int y) {
   const int mx = b.x + ((b.z - b.x + 1) >> 1);   // ceil(float(x1-x0)/2)   (ORBextractor.cpp:489-490)
@@ -1002,12 +1008,20 @@ __global__ void __launch_bounds__(kOctMaxThreads) octree_kernel(const __grid_con
     return;
   }
   {
+    // one THREAD per slot (a slot holds the few dozen corners of two cells): every thread's chain count -> base -> keys runs
+    // beside the others' instead of one slot at a time per warp (this gather was the top line of the kernel's profile:
+    // three dependent L2 round trips per slot, serialised)
     const uint32_t* slotKeys = B.slotKeys + (size_t)f * G.slotKeysPerFrame;
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int s = warp; s < L.nSlots; s += T / 32) {
-      const int c = slotCount[s], o = S.slotPre[s];
+    for (int s = tid; s < L.nSlots; s += T) {
+      const int o = S.slotPre[s], c = (s + 1 < L.nSlots ? S.slotPre[s + 1] : n) - o;
       const uint32_t* src = slotKeys + __ldg(B.slotKeyBase + L.slot0 + s);
-      for (int k = lane; k < c; k += 32) keys[o + k] = src[k];
+      for (int k = 0; k < c; k += 4) {                    // four loads in flight per thread
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = k + j < c ? src[k + j] : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (k + j < c) keys[o + k + j] = v[j];
+      }
     }
   }
   if (tid < kMaxRoots) rootCnt[tid] = 0;
@@ -1061,12 +1075,19 @@ __global__ void __launch_bounds__(kOctMaxThreads) octree_kernel(const __grid_con
     for (int i = tid; i < Sn * 4; i += T) S.cnt4[i] = 0;
     if (tid == 0) { sh_stop = 0x7fffffff; sh_nexp = 0; }
     __syncthreads();
-    for (int k = tid; k < n; k += T) {
-      const int p = nodeOf[k];
-      if (cnt[p] > 1) {
-        const uint32_t key = keys[k];
-        atomicAdd(&S.cnt4[p * 4 + quadrant_of(box[p], key_x(key), key_y(key))], 1);
+    // keys and node labels live in global memory (L2): four independent (label, key) pairs are fetched per thread before
+    // anything is done with them, instead of label -> test -> key -> atomic one key at a time (two dependent L2 latencies each)
+    for (int k0 = tid; k0 < n; k0 += kOctBatch * T) {
+      int pp[kOctBatch]; uint32_t kk[kOctBatch];
+#pragma unroll
+      for (int j = 0; j < kOctBatch; ++j) {
+        const int k = k0 + j * T;
+        pp[j] = k < n ? (int)nodeOf[k] : -1;
+        kk[j] = k < n ? keys[k] : 0u;
       }
+#pragma unroll
+      for (int j = 0; j < kOctBatch; ++j)
+        if (pp[j] >= 0 && cnt[pp[j]] > 1) atomicAdd(&S.cnt4[pp[j] * 4 + quadrant_of(box[pp[j]], key_x(kk[j]), key_y(kk[j]))], 1);
     }
     __syncthreads();
 
@@ -1154,14 +1175,19 @@ __global__ void __launch_bounds__(kOctMaxThreads) octree_kernel(const __grid_con
       }
     }
     __syncthreads();
-    for (int k = tid; k < n; k += T) {
-      const int p = nodeOf[k];
-      const int kp = S.keepPos[p];
-      if (kp >= 0) {
-        nodeOf[k] = (uint16_t)(totalChildren + kp);
-      } else {
-        const uint32_t key = keys[k];
-        nodeOf[k] = (uint16_t)S.childPos[p * 4 + quadrant_of(box[p], key_x(key), key_y(key))];
+    for (int k0 = tid; k0 < n; k0 += kOctBatch * T) {
+      int pp[kOctBatch]; uint32_t kk[kOctBatch];
+#pragma unroll
+      for (int j = 0; j < kOctBatch; ++j) {
+        const int k = k0 + j * T;
+        pp[j] = k < n ? (int)nodeOf[k] : -1;
+        kk[j] = k < n ? keys[k] : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < kOctBatch; ++j) {
+        if (pp[j] < 0) continue;
+        const int p = pp[j], kp = S.keepPos[p];
+        nodeOf[k0 + j * T] = (uint16_t)(kp >= 0 ? totalChildren + kp : S.childPos[p * 4 + quadrant_of(box[p], key_x(kk[j]), key_y(kk[j]))]);
       }
     }
     const int newS = totalChildren + nKept;
@@ -1177,9 +1203,20 @@ __global__ void __launch_bounds__(kOctMaxThreads) octree_kernel(const __grid_con
   // ---- strongest key per node, first wins ties (ORBextractor.cpp:747-766) ------------------------------
   for (int p = tid; p < Scount; p += T) S.best[p] = 0ull;
   __syncthreads();
-  for (int k = tid; k < n; k += T) {
-    const unsigned long long v = ((unsigned long long)(key_s(keys[k]) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)k);
-    atomicMax(&S.best[nodeOf[k]], v);
+  for (int k0 = tid; k0 < n; k0 += kOctBatch * T) {
+    int pp[kOctBatch]; uint32_t kk[kOctBatch];
+#pragma unroll
+    for (int j = 0; j < kOctBatch; ++j) {
+      const int k = k0 + j * T;
+      pp[j] = k < n ? (int)nodeOf[k] : -1;
+      kk[j] = k < n ? keys[k] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kOctBatch; ++j) {
+      if (pp[j] < 0) continue;
+      const unsigned long long v = ((unsigned long long)(key_s(kk[j]) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(k0 + j * T));
+      atomicMax(&S.best[pp[j]], v);
+    }
   }
   __syncthreads();
   for (int p = tid; p < Scount; p += T) {
