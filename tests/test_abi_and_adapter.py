@@ -51,6 +51,33 @@ def test_no_cpu_fallback(vo):
         vo.Matcher(0.7).knn2(np.zeros((4, 32), np.uint8), np.zeros((4, 32), np.uint8))
 
 
+def test_round2_entry_points_without_a_gpu(vo):
+    """The run-time switch of the Hamming variant is pure host state; the resident-frame entry points refuse null handles and,
+    without a GPU, fail loudly instead of computing anything on the CPU."""
+    import ctypes as C
+    import numpy as np
+    L = vo.lib()
+    prev = L.hamm_set_variant(1)
+    assert prev in (0, 1) and L.hamm_set_variant(-1) == 1          # any other argument only queries
+    assert L.hamm_set_variant(0) == 1 and L.hamm_set_variant(prev) == 0
+    h = C.c_void_p(); n = C.c_int(0)
+    img = np.zeros((480, 640), np.uint8)
+    cam = vo.camera(500.0, 500.0, 320.0, 240.0)
+    assert L.orbx_frame_create(None, C.byref(cam), C.c_void_p(img.ctypes.data), 640, 480, 640, None, 0, C.byref(h), C.byref(n)) == -1
+    assert L.orbx_frame_size(None, C.byref(n)) == -1 and L.orbx_frame_destroy(None) == 0
+    assert L.orbx_search_by_projection_frame_h(None, None, None, 15.0, 40.0, 0, 0, 1, None, None) == -1
+    assert L.orbx_frame_upload(None, 0, C.byref(h)) == -1
+    if vo.device_count() == 0:
+        kps = np.zeros(4, vo.KP_DTYPE); desc = np.zeros((4, 32), np.uint8); ur = np.full(4, -1.0, np.float32); sf = np.ones(8, np.float32)
+        v = vo.api._FrameView()
+        v.kps = kps.ctypes.data; v.desc = desc.ctypes.data; v.uright = ur.ctypes.data; v.n = 4
+        v.xmin, v.xmax, v.ymin, v.ymax = 0.0, 640.0, 0.0, 480.0
+        v.scale_factors = sf.ctypes.data; v.nlevels = 8; v.occupied0 = None
+        assert L.orbx_frame_upload(C.byref(v), 0, C.byref(h)) == -2 and not h.value          # ORBX_ERR_CUDA, no handle
+        p = C.c_void_p()
+        assert L.orbx_host_alloc(4096, 0, C.byref(p)) == -2 and not p.value
+
+
 def test_product_does_not_import_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "vo_slam_test_b200")):
         for f in files:
