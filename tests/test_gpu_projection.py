@@ -63,6 +63,28 @@ def test_search_by_projection_local(vo, frame_out, m, stereo, th):
         assert wcnt > 100
 
 
+@pytest.mark.parametrize("radius,thl", [(70.0, 12.0), (200.0, 40.0)])
+def test_crowded_windows_take_the_exact_allocation_path(vo, frame_out, radius, thl):
+    """Windows that hold more candidates than the one-pass walk's 64 slots per point: the search must re-run with the exact
+    two-pass allocation and still equal the oracle (frame, local-map and relocalisation overloads)."""
+    P, kps, desc, sf = frame_out
+    frame, pts = synth.make_projection_case(kps, desc, sf, 1500, seed=77)
+    want, wcnt = P.sbp_frame(frame, pts, radius)
+    got, gcnt = vo.Matcher(0.9).searchByProjection(frame, pts, radius)
+    assert gcnt == wcnt and np.array_equal(got, want)
+    # the oracle's own window query confirms that windows really are that crowded
+    big = max(len(P.features_in_area(kps, frame["bounds"], float(pts["u"][i]), float(pts["v"][i]), radius * float(sf[pts["octave"][i]]), 0, 8))
+              for i in range(0, 200))
+    assert big > 64
+    want, wcnt = P.sbp_reloc(frame, pts, radius, 100.0, True)
+    got, gcnt = vo.Matcher(0.9).searchByProjectionKeyFrame(frame, pts, radius, 100.0, checkRot=True)
+    assert gcnt == wcnt and np.array_equal(got, want)
+    frameL, ptsL = synth.make_projection_case(kps, desc, sf, 1500, seed=78, local=True)
+    want, wcnt = P.sbp_local(frameL, ptsL, thl, 0.8)
+    got, gcnt = vo.Matcher(0.8).searchByProjectionLocal(frameL, ptsL, thl)
+    assert gcnt == wcnt and np.array_equal(got, want)
+
+
 def test_projection_empty_inputs(vo, frame_out):
     P, kps, desc, sf = frame_out
     frame, pts = synth.make_projection_case(kps, desc, sf, 50, seed=1)

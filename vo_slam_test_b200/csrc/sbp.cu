@@ -175,35 +175,47 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const orbx_keypoint* _
 }
 
 // ---- candidate generation: one warp per map point ---------------------------------------------------------
-// misc[0] = running total of candidates (atomic allocation), misc[3] = overflow flag
+// Candidate word: feature index (20 bits) | distance << 20 (9 bits, 511 = "never selectable") | octave << 29 (3 bits, only read
+// when the frame has at most 8 levels).
+// slotCap > 0: ONE pass, point i owns cand[i * slotCap .. + slotCap) (the common case: a window holds a few dozen features);
+//              a point with more candidates raises misc[3] and the host re-runs with slotCap == 0.
+// slotCap == 0: two passes, exact allocation: misc[0] = running total of candidates, misc[3] = overflow of `cap`.
+constexpr int kSlotCap = 64;
+constexpr int kCandCache = 12;      // candidates a resolve thread keeps in registers across its fixed-point rounds
 template <bool LOCAL>
 __global__ void __launch_bounds__(256) sbp_walk_kernel(FrameDev F, PointsDev P, SearchParams S, int* offs, int* cnts, uint32_t* cand,
-                                                       int cap, int* misc) {
+                                                       int cap, int slotCap, int* misc) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= P.m) return;
   const Window w = make_window<LOCAL>(F, P, S, i);
   int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
   const bool any = w.ok && window_cells(F, w, x0, x1, y0, y1);
-  int cnt = 0;
-  if (any) {
-    for (int ix = x0; ix <= x1; ++ix) {
-      const int lo = __ldg(F.cellStart + ix * GR + y0), hi = __ldg(F.cellStart + ix * GR + y1 + 1);
-      for (int e = lo + lane; e < ((hi - lo + 31) & ~31) + lo; e += 32) {
-        bool pass = false;
-        if (e < hi) pass = gate<LOCAL>(F, S, w, __ldg(F.feat + __ldg(F.ids + e)));
-        cnt += __popc(__ballot_sync(0xffffffffu, pass));
+  int base = 0, limit = 0;
+  if (slotCap > 0) {
+    base = i * slotCap; limit = base + slotCap;
+    if (!any) { if (lane == 0) { offs[i] = base; cnts[i] = 0; } return; }
+  } else {
+    int cnt = 0;
+    if (any) {
+      for (int ix = x0; ix <= x1; ++ix) {
+        const int lo = __ldg(F.cellStart + ix * GR + y0), hi = __ldg(F.cellStart + ix * GR + y1 + 1);
+        for (int e = lo + lane; e < ((hi - lo + 31) & ~31) + lo; e += 32) {
+          bool pass = false;
+          if (e < hi) pass = gate<LOCAL>(F, S, w, __ldg(F.feat + __ldg(F.ids + e)));
+          cnt += __popc(__ballot_sync(0xffffffffu, pass));
+        }
       }
     }
+    if (lane == 0) {
+      if (cnt > 0) base = atomicAdd(&misc[0], cnt);
+      offs[i] = base; cnts[i] = cnt;
+      if (base + cnt > cap) { misc[3] = 1; cnts[i] = 0; }
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (cnt == 0 || base + cnt > cap) return;
+    limit = base + cnt;
   }
-  int base = 0;
-  if (lane == 0) {
-    if (cnt > 0) base = atomicAdd(&misc[0], cnt);
-    offs[i] = base; cnts[i] = cnt;
-    if (base + cnt > cap) { misc[3] = 1; cnts[i] = 0; }
-  }
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (cnt == 0 || base + cnt > cap) return;
   const uint4* dq = reinterpret_cast<const uint4*>(P.desc + (size_t)i * 32);
   const uint4 d0 = __ldg(dq), d1 = __ldg(dq + 1);
   int run = base;
@@ -212,38 +224,50 @@ __global__ void __launch_bounds__(256) sbp_walk_kernel(FrameDev F, PointsDev P, 
     for (int e = lo + lane; e < ((hi - lo + 31) & ~31) + lo; e += 32) {
       bool pass = false;
       int idx = 0;
-      if (e < hi) { idx = __ldg(F.ids + e); pass = gate<LOCAL>(F, S, w, __ldg(F.feat + idx)); }
+      float4 ft = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < hi) { idx = __ldg(F.ids + e); ft = __ldg(F.feat + idx); pass = gate<LOCAL>(F, S, w, ft); }
       const unsigned b = __ballot_sync(0xffffffffu, pass);
-      if (pass) {
+      const int pos = run + __popc(b & ((1u << lane) - 1));
+      if (pass && pos < limit) {
         int dist = hamming256(d0, d1, F.desc + (size_t)idx * 32);
-        if (S.level_at_select) {               // keeps its position in the list but can never be selected
-          const int oct = __float_as_int(__ldg(F.feat + idx).z);
-          if (oct < w.minL || oct > w.maxL) dist = 511;
-        }
-        cand[run + __popc(b & ((1u << lane) - 1))] = (uint32_t)idx | ((uint32_t)dist << 20);
+        const int oct = __float_as_int(ft.z);
+        if (S.level_at_select && (oct < w.minL || oct > w.maxL)) dist = 511;   // keeps its position in the list but can never be selected
+        cand[pos] = (uint32_t)idx | ((uint32_t)dist << 20) | ((uint32_t)(oct & 7) << 29);
       }
       run += __popc(b);
     }
   }
+  if (slotCap > 0 && lane == 0) {
+    offs[i] = base; cnts[i] = min(run - base, slotCap);
+    if (run > limit) misc[3] = 1;
+    atomicAdd(&misc[0], run - base);
+  }
 }
 
 // ---- ordered resolution (one CTA) -------------------------------------------------------------------------
+// One candidate of point i against the running best / second best (matcher.cpp:87-105 / :314-339 / :218 / :422-427).
 template <bool LOCAL>
-__device__ __forceinline__ int select_choice(const FrameDev& F, const SearchParams& S, const uint32_t* cand, int b, int e, int i,
-                                             const int* blockTime) {
-  int bestD = 256, bestI = -1, bestD2 = 256, bestL = -1, bestL2 = -1;
-  for (int k = b; k < e; ++k) {
-    const uint32_t c = cand[k];
-    const int idx = (int)(c & 0xFFFFFu), d = (int)(c >> 20);
-    if (blockTime[S.pos_block ? (k - b) : idx] < i) continue;          // matcher.cpp:87 / :314 / :218 / :422
-    if (d == 511) continue;                                            // level gate applied at selection (:425-427)
-    if (LOCAL) {
-      if (d < bestD) { bestD2 = bestD; bestD = d; bestL2 = bestL; bestL = F.kps[idx].octave; bestI = idx; }   // :327-339
-      else if (d < bestD2) { bestL2 = F.kps[idx].octave; bestD2 = d; }
-    } else {
-      if (d < bestD) { bestD = d; bestI = idx; }                       // :101-105
-    }
+__device__ __forceinline__ void consider(const FrameDev& F, const SearchParams& S, uint32_t c, int pos, int i, const int* blockTime,
+                                         bool octInCand, int& bestD, int& bestI, int& bestD2, int& bestL, int& bestL2) {
+  const int idx = (int)(c & 0xFFFFFu), d = (int)((c >> 20) & 0x1FFu);
+  if (blockTime[S.pos_block ? pos : idx] < i) return;                  // matcher.cpp:87 / :314 / :218 / :422
+  if (d == 511) return;                                                // level gate applied at selection (:425-427)
+  if (LOCAL) {
+    if (d < bestD) { bestD2 = bestD; bestD = d; bestL2 = bestL; bestL = octInCand ? (int)(c >> 29) : F.kps[idx].octave; bestI = idx; }   // :327-339
+    else if (d < bestD2) { bestL2 = octInCand ? (int)(c >> 29) : F.kps[idx].octave; bestD2 = d; }
+  } else {
+    if (d < bestD) { bestD = d; bestI = idx; }                         // :101-105
   }
+}
+// cache[j] = cand[b + j] for j < min(e - b, kCandCache): fetched once per point, reused by every round of the fixed point
+template <bool LOCAL>
+__device__ __forceinline__ int select_choice(const FrameDev& F, const SearchParams& S, const uint32_t* cand, const uint32_t (&cache)[kCandCache],
+                                             int b, int e, int i, const int* blockTime, bool octInCand) {
+  int bestD = 256, bestI = -1, bestD2 = 256, bestL = -1, bestL2 = -1;
+#pragma unroll
+  for (int j = 0; j < kCandCache; ++j)
+    if (b + j < e) consider<LOCAL>(F, S, cache[j], j, i, blockTime, octInCand, bestD, bestI, bestD2, bestL, bestL2);
+  for (int k = b + kCandCache; k < e; ++k) consider<LOCAL>(F, S, cand[k], k - b, i, blockTime, octInCand, bestD, bestI, bestD2, bestL, bestL2);
   if (!((float)bestD <= S.th)) return -1;                              // :108 / :342 / :233 / :439
   if (LOCAL && bestL == bestL2 && (float)bestD > __fmul_rn(S.ratio, (float)bestD2)) return -1;   // :344
   return bestI;
@@ -258,6 +282,7 @@ __global__ void __launch_bounds__(kResolveThreads) sbp_resolve_kernel(FrameDev F
   extern __shared__ int sblock[];
   __shared__ int cnt, hist[HISTO], keepBin[3];
   const int tid = threadIdx.x, T = blockDim.x, m = P.m, n = F.n;
+  const bool octInCand = F.nlevels <= 8;                   // the 3-bit octave field of the candidate word is complete
   int* blockF = (n <= smemN) ? sblock : gBlockF;
   int* blockT = (n <= smemN) ? sblock + smemN : gBlockT;
   for (int c = tid; c < n; c += T) blockF[c] = (!S.no_block && F.occupied0[c]) ? -1 : INT_MAX;
@@ -268,13 +293,16 @@ __global__ void __launch_bounds__(kResolveThreads) sbp_resolve_kernel(FrameDev F
     const bool valid = i < m;
     const int b = valid ? offs[i] : 0, e = valid ? b + cnts[i] : 0;
     const bool obs = valid && !S.no_block && (S.block_all || P.has_obs[i]);
+    uint32_t cache[kCandCache];
+#pragma unroll
+    for (int j = 0; j < kCandCache; ++j) cache[j] = b + j < e ? cand[b + j] : 0u;     // independent loads: one L2 latency per point
     int ch = -1;
     while (true) {
       for (int c = tid; c < n; c += T) blockT[c] = blockF[c];
       __syncthreads();
       if (obs && ch >= 0) atomicMin(&blockT[ch], i);
       __syncthreads();
-      const int nc = (e > b) ? select_choice<LOCAL>(F, S, cand, b, e, i, blockT) : -1;
+      const int nc = (e > b) ? select_choice<LOCAL>(F, S, cand, cache, b, e, i, blockT, octInCand) : -1;
       const int changed = nc != ch;
       ch = nc;
       ++rounds;
@@ -428,16 +456,18 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
   if (!rf)
     grid_build_kernel<<<1, 1024, 0, st>>>(F.kps, (const float*)(db + o_ur), n, F.xmin, F.ymin, F.gw, F.gh, (int*)(db + o_cellOf),
                                           (int*)(db + o_cellStart), (int*)(db + o_ids), (float4*)(db + o_feat));
-  // candidate buffer: start with 48 per point; on overflow the search is re-run with the exact size (known afterwards)
-  size_t capCand = std::max<size_t>((size_t)m * 48, 4096);
+  // candidate buffer: first attempt = one-pass walk with kSlotCap slots per point; a point that needs more makes the search
+  // re-run with the two-pass exact allocation (size known from the first attempt's counter)
+  size_t capCand = std::max<size_t>((size_t)m * kSlotCap, 4096);
+  int slotCap = kSlotCap;
   const int smemN = 8192;
   // the attribute is per device and every entry point takes a device argument: set it on every call (cheap, as frame.cu does)
   ORBX_CUDA(cudaFuncSetAttribute(sbp_resolve_kernel<LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * 2 * smemN)));
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int attempt = 0; attempt < 3; ++attempt) {
     if (g_cand_arena.reserve(sizeof(uint32_t) * capCand + 256, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
     uint32_t* d_cand = g_cand_arena.take<uint32_t>(capCand);
     if (attempt) ORBX_CUDA(cudaMemsetAsync(d_misc, 0, sizeof(int) * 8, st));
-    sbp_walk_kernel<LOCAL><<<(m + 7) / 8, 256, 0, st>>>(F, P, S, (int*)(db + o_offs), (int*)(db + o_cnts), d_cand, (int)std::min<size_t>(capCand, INT_MAX), d_misc);
+    sbp_walk_kernel<LOCAL><<<(m + 7) / 8, 256, 0, st>>>(F, P, S, (int*)(db + o_offs), (int*)(db + o_cnts), d_cand, (int)std::min<size_t>(capCand, INT_MAX), slotCap, d_misc);
     sbp_resolve_kernel<LOCAL><<<1, kResolveThreads, sizeof(int) * 2 * smemN, st>>>(F, P, S, (const int*)(db + o_offs), (const int*)(db + o_cnts), d_cand,
                                                                               (int*)(db + o_choice), (int*)(db + o_bF), (int*)(db + o_bT), smemN,
                                                                               (int32_t*)(db + o_assign), d_misc);
@@ -452,6 +482,7 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
       return ORBX_OK;
     }
     capCand = (size_t)res[0] + 1024;      // exact need (the allocation counter keeps counting past the capacity)
+    slotCap = 0;
   }
   set_error("candidate buffer overflow");
   return ORBX_ERR_CAPACITY;
