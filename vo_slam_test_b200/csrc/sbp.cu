@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "frame_handle.cuh"
@@ -437,7 +438,11 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
   memcpy(hb + o_lvl, level, sizeof(int32_t) * m); memcpy(hb + o_pd, desc, (size_t)m * 32);
   cudaStream_t st = nullptr;
   uint8_t* db = g_arena.take<uint8_t>(pk.used);
+  static const bool phaseTiming = getenv("ORBX_SEARCH_TIMING") != nullptr;      // debugging aid: host clock with a sync after every phase
+  auto tnow = []() { return std::chrono::steady_clock::now(); };
+  auto t0 = tnow();
   ORBX_CUDA(cudaMemcpyAsync(db, hb, inBytes, cudaMemcpyHostToDevice, st));
+  if (phaseTiming) { cudaStreamSynchronize(st); fprintf(stderr, "[sbp] m=%d n=%d upload %zu B: %.1f us\n", m, n, inBytes, std::chrono::duration<double, std::micro>(tnow() - t0).count()); t0 = tnow(); }
   int* d_misc = (int*)(db + o_misc);
 
   FrameDev F;
@@ -468,12 +473,15 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
     uint32_t* d_cand = g_cand_arena.take<uint32_t>(capCand);
     if (attempt) ORBX_CUDA(cudaMemsetAsync(d_misc, 0, sizeof(int) * 8, st));
     sbp_walk_kernel<LOCAL><<<(m + 7) / 8, 256, 0, st>>>(F, P, S, (int*)(db + o_offs), (int*)(db + o_cnts), d_cand, (int)std::min<size_t>(capCand, INT_MAX), slotCap, d_misc);
+    if (phaseTiming) { cudaStreamSynchronize(st); fprintf(stderr, "[sbp] walk: %.1f us\n", std::chrono::duration<double, std::micro>(tnow() - t0).count()); t0 = tnow(); }
     sbp_resolve_kernel<LOCAL><<<1, kResolveThreads, sizeof(int) * 2 * smemN, st>>>(F, P, S, (const int*)(db + o_offs), (const int*)(db + o_cnts), d_cand,
                                                                               (int*)(db + o_choice), (int*)(db + o_bF), (int*)(db + o_bT), smemN,
                                                                               (int32_t*)(db + o_assign), d_misc);
+    if (phaseTiming) { cudaStreamSynchronize(st); fprintf(stderr, "[sbp] resolve: %.1f us\n", std::chrono::duration<double, std::micro>(tnow() - t0).count()); t0 = tnow(); }
     ORBX_CUDA(cudaMemcpyAsync(hout, db + o_misc, choice_out ? outBytes : outBytes - sizeof(int) * m, cudaMemcpyDeviceToHost, st));
     ORBX_CUDA(cudaStreamSynchronize(st));
     ORBX_CUDA(cudaGetLastError());
+    if (phaseTiming) fprintf(stderr, "[sbp] download %zu B: %.1f us (rounds %d)\n", outBytes, std::chrono::duration<double, std::micro>(tnow() - t0).count(), ((const int*)hout)[2]);
     const int* res = (const int*)hout;
     if (!res[3]) {
       memcpy(assign, hout + sizeof(int) * 8, sizeof(int32_t) * n);
