@@ -1201,7 +1201,12 @@ __global__ void __launch_bounds__(kOctMaxThreads) octree_kernel(const __grid_con
   }
 
   // ---- strongest key per node, first wins ties (ORBextractor.cpp:747-766) ------------------------------
-  for (int p = tid; p < Scount; p += T) S.best[p] = 0ull;
+  // max (response, then FIRST index): response + 1 (9 bits) above the complemented key index.  Below 2^23 candidates the pair fits
+  // 32 bits and the shared-memory atomicMax is one native instruction; the 64-bit form is a compare-and-swap loop (it was 12 %
+  // of the kernel's stall samples) and remains only for levels with more candidates than that
+  const bool narrow = n < (1 << 23);
+  uint32_t* best32 = reinterpret_cast<uint32_t*>(S.best);
+  for (int p = tid; p < Scount; p += T) { if (narrow) best32[p] = 0u; else S.best[p] = 0ull; }
   __syncthreads();
   for (int k0 = tid; k0 < n; k0 += kOctBatch * T) {
     int pp[kOctBatch]; uint32_t kk[kOctBatch];
@@ -1214,13 +1219,14 @@ __global__ void __launch_bounds__(kOctMaxThreads) octree_kernel(const __grid_con
 #pragma unroll
     for (int j = 0; j < kOctBatch; ++j) {
       if (pp[j] < 0) continue;
-      const unsigned long long v = ((unsigned long long)(key_s(kk[j]) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(k0 + j * T));
-      atomicMax(&S.best[pp[j]], v);
+      const int k = k0 + j * T;
+      if (narrow) atomicMax(&best32[pp[j]], ((uint32_t)(key_s(kk[j]) + 1) << 23) | (0x7FFFFFu - (uint32_t)k));   // native 32-bit shared atomic
+      else atomicMax(&S.best[pp[j]], ((unsigned long long)(key_s(kk[j]) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)k));
     }
   }
   __syncthreads();
   for (int p = tid; p < Scount; p += T) {
-    const uint32_t k = 0xFFFFFFFFu - (uint32_t)(S.best[p] & 0xFFFFFFFFull);
+    const uint32_t k = narrow ? 0x7FFFFFu - (best32[p] & 0x7FFFFFu) : 0xFFFFFFFFu - (uint32_t)(S.best[p] & 0xFFFFFFFFull);
     sel[p] = keys[k];
   }
   if (tid == 0) *selCount = Scount;
