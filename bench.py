@@ -757,7 +757,7 @@ def bench_hamming_map(args, torch, dist, sharded, dev, rank, world, local_rank, 
     # -- oracle-checked sub-problem: 1k x 64k rows over all ranks ---------------------------------------------
     sub = 65536 // world
     d_ts = make_shard(sub, 4321)
-    equals_oracle = None
+    equals_oracle, oracle_detail = None, None
     try:
         outs = {}
         if xchg is not None:
@@ -775,10 +775,11 @@ def bench_hamming_map(args, torch, dist, sharded, dev, rank, world, local_rank, 
         flag = torch.tensor([1 if good else 0], dtype=torch.int32, device=dev)
         if world > 1:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        equals_oracle = {"equal": bool(flag.item()), "paths": sorted(outs), "queries": Q, "rows": sub * world,
-                         "accepted": int(want[3].sum()), "cross_shard_ties": int(((want[1] == want[2]) & (want[1] == 0)).sum())}
+        equals_oracle = bool(flag.item())
+        oracle_detail = {"paths": sorted(outs), "queries": Q, "rows": sub * world, "accepted": int(want[3].sum()),
+                         "cross_shard_ties": int(((want[1] == want[2]) & (want[1] == 0)).sum())}
     except Exception as e:      # noqa: BLE001
-        equals_oracle = {"error": str(e)[:160]}
+        equals_oracle, oracle_detail = None, {"error": str(e)[:160]}
     del d_ts
 
     # -- the timed map ---------------------------------------------------------------------------------------------
@@ -800,7 +801,7 @@ def bench_hamming_map(args, torch, dist, sharded, dev, rank, world, local_rank, 
 
     mms, out = time_map(xchg is not None)
     res = {"gmatch_per_s": world * Q * Ml / (mms * 1e6), "ms": mms, "queries": Q, "rows_per_gpu": Ml, "merge": merge_kind,
-           "accepted": int(out[3].sum().item()), "equals_oracle": equals_oracle}
+           "accepted": int(out[3].sum().item()), "equals_oracle": equals_oracle, "equals_oracle_detail": oracle_detail}
     if not args.skip_variants:
         try:
             from vo_slam_test_b200 import api
