@@ -688,7 +688,7 @@ def run_b200(args, rank, world, local_rank):
                            "distinct_frames": min(Ftot, 1024),
                            "input_note": "the synthetic pan wraps every 1024 frames: frames i and i+1024 are identical (no kernel caches by content)",
                            "chunk_frames": chunk, "resident_lanes": int(os.environ.get("ORBX_LANES", "2")),
-                           "chunk_frames_host_pipeline": int(os.environ.get("ORBX_CHUNK_HOST", os.environ.get("ORBX_CHUNK", "256"))),
+                           "chunk_frames_host_pipeline": int(os.environ.get("ORBX_CHUNK_HOST", os.environ.get("ORBX_CHUNK", "128"))),
                            "mean_keypoints": checksum["keypoints"] / max(job_frames, 1),
                            "accepted_matches_per_pair": accepted / max(owned_pairs, 1), "checksum": checksum,
                            "parity_spot_check": parity},

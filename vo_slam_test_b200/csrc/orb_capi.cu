@@ -109,7 +109,7 @@ void free_frame_block(orbx_frame* f);
 // Frames per chunk.  Device-resident batches: 512 (fewer, larger launches: +3 % over 256, no gain beyond).  Host-pipelined
 // batches: 256, because the upload of chunk c+1 overlaps the kernels of chunk c and the pipeline fill/drain grows with the
 // chunk (measured end to end: 157 k frames/s at 256, 148 k at 512).  ORBX_CHUNK overrides both, ORBX_CHUNK_HOST the latter.
-constexpr int kDefaultChunk = 512, kDefaultHostChunk = 256;
+constexpr int kDefaultChunk = 512, kDefaultHostChunk = 128;   // host pipeline: 128-frame chunks on two lanes (tools/e2e_probe.py)
 
 int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
@@ -896,17 +896,39 @@ int orbx_extract_match_batch(orbx_handle h, const uint8_t* imgs, int nframes, in
     ORBX_CUDA(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
     ORBX_CUDA(cudaStreamCreateWithFlags(&h->backStream, cudaStreamNonBlocking));
   }
-  cudaStream_t sc = h->copyStream, sk = h->stream, sb = h->backStream;
+  cudaStream_t sc = h->copyStream, sb = h->backStream;
   h->map0_want = nframes;
   const int nchunks = (int)sched.size();
-  std::vector<cudaEvent_t> up(nchunks), done(nchunks);
+  // Two compute lanes (this handle and its sibling, each with its own workspace and stream) take the chunks alternately: one
+  // lane alone processes 256-frame chunks a little slower than the link delivers them, so the copies would wait for the kernels;
+  // with two lanes the kernel tails of one chunk fill under the next chunk's kernels and the step is bound by the upload.
+  // The pairs of chunk c need the last frame of chunk c-1, extracted on the other lane: its `ext` event orders them.
+  const bool two = env_int("ORBX_HOST_LANES", 2) >= 2 && nchunks >= 2;
+  orbx_extractor* g = h;
+  if (two) {
+    if (!h->lane2) {
+      orbx_handle sib = nullptr;
+      rc = orbx_create(&h->p, &sib);
+      if (rc) return rc;
+      h->lane2 = sib;
+    }
+    g = h->lane2;
+    rc = configure(g, w, height, std::min(nframes, host_chunk(w, height)));
+    if (rc) return rc;
+    g->map0_want = nframes;
+  }
+  std::vector<cudaEvent_t> up(nchunks), ext(nchunks), done(nchunks);
   for (int c = 0; c < nchunks; ++c) {
     ORBX_CUDA(cudaEventCreateWithFlags(&up[c], cudaEventDisableTiming));
+    ORBX_CUDA(cudaEventCreateWithFlags(&ext[c], cudaEventDisableTiming));
     ORBX_CUDA(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
   }
   const bool dense = frame_stride == row_stride * (size_t)height;
+  const int dbg = env_int("ORBX_E2E_DEBUG", 0);      // diagnosis only: 1 = no kernels, 2 = no downloads, 3 = neither
   for (int c = 0; c < nchunks && rc == ORBX_OK; ++c) {
     const int f0 = sched[c].first, n = sched[c].second;
+    orbx_extractor* x = (two && (c & 1)) ? g : h;
+    cudaStream_t sk = x->stream;
     if (dense && pitch == row_stride) {          // one contiguous block: a plain 1-D copy (no per-row DMA descriptors)
       cudaMemcpyAsync(h->d_in + f0 * fbytes, imgs + f0 * frame_stride, fbytes * n, cudaMemcpyHostToDevice, sc);
     } else if (dense) {
@@ -918,11 +940,13 @@ int orbx_extract_match_batch(orbx_handle h, const uint8_t* imgs, int nframes, in
     }
     cudaEventRecord(up[c], sc);
     cudaStreamWaitEvent(sk, up[c], 0);
-    rc = run_chunk(h, h->d_in, pitch, fbytes, f0, n, h->d_kps, h->d_desc, cap, h->d_counts, sk);
+    if (!(dbg & 1)) rc = run_chunk(x, h->d_in, pitch, fbytes, f0, n, h->d_kps, h->d_desc, cap, h->d_counts, sk);
     if (rc) break;
+    cudaEventRecord(ext[c], sk);
     // pairs whose second frame is now available: p in [max(f0-1,0), f0+n-1)
     const int p0 = std::max(f0 - 1, 0), p1 = f0 + n - 1;
-    if (p1 > p0) {
+    if (p1 > p0 && !(dbg & 1)) {
+      if (two && c > 0) cudaStreamWaitEvent(sk, ext[c - 1], 0);
       rc = hamm_knn2_pairs_device(h->d_desc, h->d_counts, cap, h->d_qf + p0, h->d_qf + p0 + 1, p1 - p0, th, ratio,
                                   h->d_midx + (size_t)p0 * cap, h->d_md1 + (size_t)p0 * cap, h->d_md2 + (size_t)p0 * cap,
                                   h->d_mok + (size_t)p0 * cap, sk);
@@ -930,6 +954,7 @@ int orbx_extract_match_batch(orbx_handle h, const uint8_t* imgs, int nframes, in
     }
     cudaEventRecord(done[c], sk);
     cudaStreamWaitEvent(sb, done[c], 0);
+    if (dbg & 2) continue;
     cudaMemcpyAsync(counts + f0, h->d_counts + f0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, sb);
     cudaMemcpyAsync(kps + (size_t)f0 * cap, h->d_kps + (size_t)f0 * cap, sizeof(orbx_keypoint) * (size_t)n * cap, cudaMemcpyDeviceToHost, sb);
     cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, h->d_desc + (size_t)f0 * cap * 32, (size_t)32 * n * cap, cudaMemcpyDeviceToHost, sb);
@@ -941,8 +966,9 @@ int orbx_extract_match_batch(orbx_handle h, const uint8_t* imgs, int nframes, in
       cudaMemcpyAsync(m_ok + o, h->d_mok + o, cnt, cudaMemcpyDeviceToHost, sb);
     }
   }
-  cudaError_t e1 = cudaStreamSynchronize(sk), e2 = cudaStreamSynchronize(sb), e3 = cudaStreamSynchronize(sc);
-  for (int c = 0; c < nchunks; ++c) { cudaEventDestroy(up[c]); cudaEventDestroy(done[c]); }
+  cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(sb), e3 = cudaStreamSynchronize(sc);
+  if (two) { const cudaError_t e4 = cudaStreamSynchronize(g->stream); if (e1 == cudaSuccess) e1 = e4; }
+  for (int c = 0; c < nchunks; ++c) { cudaEventDestroy(up[c]); cudaEventDestroy(ext[c]); cudaEventDestroy(done[c]); }
   if (rc) return rc;
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     set_error(cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
