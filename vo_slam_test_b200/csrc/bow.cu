@@ -176,8 +176,10 @@ __global__ void __launch_bounds__(256) tri_match_kernel(TriSideDev A, TriSideDev
   }
 }
 
+// hostOut != nullptr: [match (nOut) | count] also go straight into the caller's pinned (mapped) block -- the search then ends
+// with one stream synchronisation instead of a device->host copy.
 __global__ void __launch_bounds__(1024) bow_finish_kernel(int nOut, int check_rot, int32_t* match, const int8_t* binOf, const int* hist,
-                                                          int* result) {
+                                                          int* result, int32_t* hostOut = nullptr) {
   __shared__ int keep[3], cnt;
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -196,16 +198,19 @@ __global__ void __launch_bounds__(1024) bow_finish_kernel(int nOut, int check_ro
   __syncthreads();
   int mine = 0;
   for (int i = tid; i < nOut; i += blockDim.x) {
-    if (match[i] < 0) continue;
-    if (check_rot) {
-      const int b = binOf[i];
-      if (b != keep[0] && b != keep[1] && b != keep[2]) { match[i] = -2; continue; }   // cleared by the rotation check
+    int mi = match[i];
+    if (mi >= 0) {
+      if (check_rot) {
+        const int b = binOf[i];
+        if (b != keep[0] && b != keep[1] && b != keep[2]) { mi = -2; match[i] = -2; }   // cleared by the rotation check
+      }
+      if (mi >= 0) ++mine;
     }
-    ++mine;
+    if (hostOut) hostOut[i] = mi;
   }
   if (mine) atomicAdd(&cnt, mine);
   __syncthreads();
-  if (tid == 0) *result = cnt;
+  if (tid == 0) { *result = cnt; if (hostOut) hostOut[nOut] = cnt; }
 }
 
 struct Arena {
@@ -305,10 +310,13 @@ static int bow_run(const orbx_bow_side* a, const orbx_bow_side* b, int mode, flo
   if (rfB) { D[1].desc = rfB->d_desc; D[1].angle = rfB->d_angle; }
   bow_match_kernel<<<(a->ngroups + 7) / 8, 256, 0, st>>>(D[0], D[1], mode, ratio, th_low, check_rot, (int*)(db + o_taken),
                                                          (int32_t*)(db + o_match), (int8_t*)(db + o_bin), (int*)(db + o_hist));
-  bow_finish_kernel<<<1, 1024, 0, st>>>(nOut, check_rot, (int32_t*)(db + o_match), (const int8_t*)(db + o_bin), (const int*)(db + o_hist),
-                                        (int*)(db + o_res));
   uint8_t* hout = g_bow.h + inBytes;
-  ORBX_CUDA(cudaMemcpyAsync(hout, db + o_match, outBytes, cudaMemcpyDeviceToHost, st));
+  static const bool zcOn = [] { const char* e = getenv("ORBX_ZEROCOPY"); return e ? atoi(e) != 0 : true; }();
+  uint8_t* hdev = nullptr;
+  const bool zc = zcOn && nOut <= (1 << 16) && cudaHostGetDevicePointer((void**)&hdev, hout, 0) == cudaSuccess && hdev;
+  bow_finish_kernel<<<1, 1024, 0, st>>>(nOut, check_rot, (int32_t*)(db + o_match), (const int8_t*)(db + o_bin), (const int*)(db + o_hist),
+                                        (int*)(db + o_res), zc ? (int32_t*)hdev : nullptr);
+  if (!zc) ORBX_CUDA(cudaMemcpyAsync(hout, db + o_match, outBytes, cudaMemcpyDeviceToHost, st));
   ORBX_CUDA(cudaStreamSynchronize(st));
   ORBX_CUDA(cudaGetLastError());
   memcpy(match, hout, sizeof(int32_t) * nOut);

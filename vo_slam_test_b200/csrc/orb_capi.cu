@@ -26,8 +26,8 @@ void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe
 cudaError_t configure_kernels(const Geom& G);
 size_t fast_smem_bytes(const Geom& G);
 size_t octree_smem_bytes(const Geom& G);
-void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st);
-void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st);
+void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st, int level0 = 0, int nlev = -1);
+void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st, int level0 = 0, int nlev = -1);
 void launch_blur(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st);
 void launch_orient_desc(const Geom& G, const Bufs& B, const TmaSet& TM, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts,
                         int frame0, int nframes, cudaStream_t st);
@@ -86,6 +86,8 @@ struct orbx_extractor {
   uint8_t* d_one = nullptr; uint8_t* h_one = nullptr; int one_cap = 0;   // single-frame path: packed [count | kps | desc], pinned mirror
   size_t d_out_frames = 0; int d_out_cap = 0;
   cudaStream_t stream = nullptr, copyStream = nullptr, backStream = nullptr;
+  cudaStream_t auxStream = nullptr;           // latency mode: level 0's FAST + quadtree and the blur run here beside the pyramid
+  cudaEvent_t evIn = nullptr, evPyr = nullptr, evAux = nullptr;
   int32_t *d_midx = nullptr, *d_md1 = nullptr, *d_md2 = nullptr, *d_qf = nullptr; uint8_t* d_mok = nullptr;
   size_t m_frames = 0; int m_cap = 0;
   long long launches = 0;
@@ -93,7 +95,9 @@ struct orbx_extractor {
   // second lane of the device-resident batch path: a sibling extractor (own workspace, own stream) that takes the second
   // half of a large batch concurrently, so that kernel tails and the latency-bound stages of one lane fill under the
   // throughput-bound stages of the other (measured: +2.4 % on 4096 VGA frames, tools/lanes_probe.py)
-  orbx_extractor* lane2 = nullptr;
+  orbx_extractor* lane2 = nullptr;             // first sibling (also the second lane of the host pipeline)
+  orbx_extractor* laneX[2] = {nullptr, nullptr};   // third / fourth lane (ORBX_LANES=3|4, A/B only)
+  cudaEvent_t laneJoinX[2] = {nullptr, nullptr};
   cudaEvent_t laneFork = nullptr, laneJoin = nullptr;
   // device-resident frames (orbx_frame_t): blocks handed back by orbx_frame_destroy are reused by the next orbx_frame_create
   std::vector<orbx_frame*> framePool, framesAll;      // framesAll: every block not yet freed (live ones included)
@@ -126,6 +130,7 @@ int capped_chunk(int dflt, int w, int hgt) {
   if (c >= 64) c &= ~31;
   return std::max(1, c);
 }
+constexpr int kSplitFrames = 8;       // latency mode of run_chunk (two streams) up to this many frames per call
 constexpr int kLaneMinFrames = 32;     // below 2 x this many frames a second lane is not worth its fork/join
 int resident_chunk(int w, int hgt) {
   const int e = env_int("ORBX_CHUNK", 0);
@@ -424,6 +429,25 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
   }
   const uint8_t* img0 = d_imgs + (size_t)frame0 * frameStride;
   Bufs B = make_bufs(h, img0, rowStride, frameStride);
+  // Latency mode (a handful of frames per call: orbx_extract, orbx_frame_create): the chain is bound by the dependent launches,
+  // not by throughput, and level 0 needs nothing from the pyramid.  Level 0's FAST + quadtree (the longest single CTA of the
+  // chain) and then the blur of all levels run on a second stream beside the 7 resize launches and levels >= 1.
+  static const bool splitOn = env_int("ORBX_SPLIT", 1) != 0;
+  const bool split = splitOn && !ev && n <= kSplitFrames && G.nlevels > 1;
+  if (split && !h->auxStream) {
+    ORBX_CUDA(cudaStreamCreateWithFlags(&h->auxStream, cudaStreamNonBlocking));
+    ORBX_CUDA(cudaEventCreateWithFlags(&h->evIn, cudaEventDisableTiming));
+    ORBX_CUDA(cudaEventCreateWithFlags(&h->evPyr, cudaEventDisableTiming));
+    ORBX_CUDA(cudaEventCreateWithFlags(&h->evAux, cudaEventDisableTiming));
+  }
+  h->tma.frame0 = frame0;
+  if (split) {
+    cudaStream_t sa = h->auxStream;
+    ORBX_CUDA(cudaEventRecord(h->evIn, st));
+    ORBX_CUDA(cudaStreamWaitEvent(sa, h->evIn, 0));
+    launch_fast(G, B, h->tma, n, sa, 0, 1);
+    launch_octree(G, B, n, sa, 0, 1);
+  }
   if (ev) cudaEventRecord(ev[0], st);
   nvtxRangePushA("orbx:pyramid");          // NVTX ranges per stage (host side of the launches): nsys timelines of the lanes
   for (int l = 1; l < G.nlevels; ++l) {        // ComputePyramid: level l from level l-1 (ORBextractor.cpp:1129)
@@ -436,8 +460,18 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
                   h->taps[l].t, h->taps[l].rt, h->d_maps ? h->d_maps + 3 * kMaxLevels + l : nullptr, l == 1 ? frame0 : 0, n, st);
   }
   nvtxRangePop();
+  if (split) {
+    ORBX_CUDA(cudaEventRecord(h->evPyr, st));
+    ORBX_CUDA(cudaStreamWaitEvent(h->auxStream, h->evPyr, 0));
+    launch_blur(G, B, h->tma, n, h->auxStream);
+    ORBX_CUDA(cudaEventRecord(h->evAux, h->auxStream));
+    launch_fast(G, B, h->tma, n, st, 1, -1);
+    launch_octree(G, B, n, st, 1, -1);
+    ORBX_CUDA(cudaStreamWaitEvent(st, h->evAux, 0));
+    launch_orient_desc(G, B, h->tma, d_kps, d_desc, cap, d_counts, frame0, n, st);
+    h->launches += 2;
+  } else {
   if (ev) cudaEventRecord(ev[1], st);
-  h->tma.frame0 = frame0;
   nvtxRangePushA("orbx:fast");
   launch_fast(G, B, h->tma, n, st);
   nvtxRangePop();
@@ -454,6 +488,7 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
   launch_orient_desc(G, B, h->tma, d_kps, d_desc, cap, d_counts, frame0, n, st);
   nvtxRangePop();
   if (ev) cudaEventRecord(ev[5], st);
+  }
   h->launches += (G.nlevels - 1) + 4;
   h->last_img0 = img0; h->last_rowStride = rowStride; h->last_frameStride = frameStride; h->last_frames = n;
   ORBX_CUDA(cudaGetLastError());
@@ -611,6 +646,7 @@ int orbx_destroy(orbx_handle h) {
   for (orbx_frame* f : h->framesAll) free_frame_block(f);      // frames die with their extractor (documented in orb_b200.h)
   h->framesAll.clear(); h->framePool.clear();
   if (h->lane2) orbx_destroy(h->lane2);
+  for (int k = 0; k < 2; ++k) { if (h->laneX[k]) orbx_destroy(h->laneX[k]); if (h->laneJoinX[k]) cudaEventDestroy(h->laneJoinX[k]); }
   if (h->laneFork) cudaEventDestroy(h->laneFork);
   if (h->laneJoin) cudaEventDestroy(h->laneJoin);
   free_workspace(h);
@@ -619,6 +655,10 @@ int orbx_destroy(orbx_handle h) {
   cudaFree(h->d_counts);
   cudaFree(h->d_one); if (h->h_one) cudaFreeHost(h->h_one);
   cudaFree(h->d_midx); cudaFree(h->d_md1); cudaFree(h->d_md2); cudaFree(h->d_mok); cudaFree(h->d_qf);
+  if (h->auxStream) cudaStreamDestroy(h->auxStream);
+  if (h->evIn) cudaEventDestroy(h->evIn);
+  if (h->evPyr) cudaEventDestroy(h->evPyr);
+  if (h->evAux) cudaEventDestroy(h->evAux);
   if (h->copyStream) cudaStreamDestroy(h->copyStream);
   if (h->backStream) cudaStreamDestroy(h->backStream);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -653,7 +693,7 @@ int orbx_max_keypoints(orbx_handle h, int* cap) {
 }
 int orbx_launch_count(orbx_handle h, long long* n) {
   if (check_handle(h) || !n) return ORBX_ERR_ARG;
-  *n = h->launches + (h->lane2 ? h->lane2->launches : 0);
+  *n = h->launches + (h->lane2 ? h->lane2->launches : 0) + (h->laneX[0] ? h->laneX[0]->launches : 0) + (h->laneX[1] ? h->laneX[1]->launches : 0);
   return ORBX_OK;
 }
 
@@ -673,45 +713,56 @@ int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes,
   // size (a rank's block + its replicated boundary frame in the strong-scaling split: 513, 1025, 2049 frames) must not leave
   // one lane with a one-frame chunk, and a batch of at most one chunk (512 frames per GPU at N = 8) still gets both lanes.
   int chunk = std::min(nframes, resident_chunk(w, height));
-  if (want_lanes >= 2 && nframes >= 2 * kLaneMinFrames) {
-    const int pairs = (nframes + 2 * chunk - 1) / (2 * chunk);          // chunk pairs needed at the configured chunk size
-    chunk = (nframes + 2 * pairs - 1) / (2 * pairs);
+  const int NL = std::max(1, std::min(want_lanes, 4));
+  if (NL >= 2 && nframes >= NL * kLaneMinFrames) {
+    const int groups = (nframes + NL * chunk - 1) / (NL * chunk);          // chunk groups needed at the configured chunk size
+    chunk = (nframes + NL * groups - 1) / (NL * groups);
   }
   int rc = configure(h, w, height, chunk);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int nchunks = (nframes + chunk - 1) / chunk;
-  if (want_lanes >= 2 && nchunks >= 2) {
-    // two lanes: chunks [0, ca) on the caller's stream with this handle's workspace, chunks [ca, nchunks) on the sibling's
-    if (!h->lane2) {
-      orbx_handle sib = nullptr;
-      rc = orbx_create(&h->p, &sib);
+  if (NL >= 2 && nchunks >= 2) {
+    // lanes: lane 0 = this handle on the caller's stream, lanes 1.. = siblings (own workspace, own stream); lane k takes the
+    // chunks [k * cpl, (k + 1) * cpl)
+    const int nl = std::min(NL, nchunks), cpl = (nchunks + nl - 1) / nl;
+    orbx_extractor* lane[4] = {h, nullptr, nullptr, nullptr};
+    for (int k = 1; k < nl; ++k) {
+      orbx_extractor*& slot = k == 1 ? h->lane2 : h->laneX[k - 2];
+      if (!slot) {
+        orbx_handle sib = nullptr;
+        rc = orbx_create(&h->p, &sib);
+        if (rc) return rc;
+        slot = sib;
+      }
+      lane[k] = slot;
+      rc = configure(slot, w, height, chunk);
       if (rc) return rc;
-      h->lane2 = sib;
     }
     if (!h->laneFork) ORBX_CUDA(cudaEventCreateWithFlags(&h->laneFork, cudaEventDisableTiming));
     if (!h->laneJoin) ORBX_CUDA(cudaEventCreateWithFlags(&h->laneJoin, cudaEventDisableTiming));
-    orbx_extractor* g = h->lane2;
-    rc = configure(g, w, height, chunk);
-    if (rc) return rc;
-    const int ca = (nchunks + 1) / 2, half = ca * chunk;
-    const uint8_t* imgs2 = d_imgs + (size_t)half * frame_stride;
-    h->map0_want = half;
-    g->map0_want = nframes - half;
+    for (int k = 0; k < 2; ++k) if (!h->laneJoinX[k]) ORBX_CUDA(cudaEventCreateWithFlags(&h->laneJoinX[k], cudaEventDisableTiming));
     ORBX_CUDA(cudaEventRecord(h->laneFork, st));
-    ORBX_CUDA(cudaStreamWaitEvent(g->stream, h->laneFork, 0));
-    for (int c = 0; c < ca; ++c) {              // submissions alternate so that both streams have work from the start
-      rc = run_chunk(h, d_imgs, row_stride, frame_stride, c * chunk, std::min(chunk, half - c * chunk), d_kps, d_desc, cap, d_counts, st);
-      if (rc) return rc;
-      const int f2 = c * chunk;
-      if (half + f2 < nframes) {
-        rc = run_chunk(g, imgs2, row_stride, frame_stride, f2, std::min(chunk, nframes - half - f2), d_kps + (size_t)half * cap,
-                       d_desc + (size_t)half * cap * 32, cap, d_counts + half, g->stream);
+    int first[4], count[4];
+    for (int k = 0; k < nl; ++k) {
+      first[k] = std::min(k * cpl * chunk, nframes);
+      count[k] = std::min((k + 1) * cpl * chunk, nframes) - first[k];
+      lane[k]->map0_want = count[k];
+      if (k) ORBX_CUDA(cudaStreamWaitEvent(lane[k]->stream, h->laneFork, 0));
+    }
+    for (int c = 0; c < cpl; ++c)                 // submissions alternate so that every stream has work from the start
+      for (int k = 0; k < nl; ++k) {
+        const int f0 = c * chunk;
+        if (f0 >= count[k]) continue;
+        rc = run_chunk(lane[k], d_imgs + (size_t)first[k] * frame_stride, row_stride, frame_stride, f0, std::min(chunk, count[k] - f0),
+                       d_kps + (size_t)first[k] * cap, d_desc + (size_t)first[k] * cap * 32, cap, d_counts + first[k], k ? lane[k]->stream : st);
         if (rc) return rc;
       }
+    for (int k = 1; k < nl; ++k) {
+      cudaEvent_t ev = k == 1 ? h->laneJoin : h->laneJoinX[k - 2];
+      ORBX_CUDA(cudaEventRecord(ev, lane[k]->stream));
+      ORBX_CUDA(cudaStreamWaitEvent(st, ev, 0));
     }
-    ORBX_CUDA(cudaEventRecord(h->laneJoin, g->stream));
-    ORBX_CUDA(cudaStreamWaitEvent(st, h->laneJoin, 0));
     return ORBX_OK;
   }
   h->map0_want = nframes;

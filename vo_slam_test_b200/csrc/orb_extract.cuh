@@ -79,6 +79,8 @@ struct Bufs {
   int* selCount;           // [chunk][nlevels]
   const float2* pattern;   // 512 rBRIEF points
   const int* umax;         // 16
+  int slotOff;             // first FAST slot / quadtree level of this launch (latency mode launches level 0 and levels >= 1
+  int levelOff;            // separately, on two streams); 0 for whole-pyramid launches
 };
 
 // TMA descriptors (cuTensorMapEncodeTiled, rank 3: x bytes, y rows, frame) of every pyramid level, used by the FAST

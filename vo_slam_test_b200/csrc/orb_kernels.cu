@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_kernel(const __grid_constan
   __shared__ int qn, sn, in, cn, retryMask;
   __shared__ __align__(8) uint64_t tmaBar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slot = blockIdx.x, f = blockIdx.y;
+  const int slot = blockIdx.x + B.slotOff, f = blockIdx.y;
   int l = 0;
   while (l + 1 < G.nlevels && slot >= G.L[l + 1].slot0) ++l;
   const LevelGeom& L = G.L[l];
@@ -760,9 +760,9 @@ __global__ void __launch_bounds__(32 * kWarpCells, ORBX_FAST_MINB) fast_warp_ker
   __shared__ __align__(8) uint64_t tmaBar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #if ORBX_FAST_FF
-  const int slot = blockIdx.y, f = blockIdx.x;
+  const int slot = blockIdx.y + B.slotOff, f = blockIdx.x;
 #else
-  const int slot = blockIdx.x, f = blockIdx.y;
+  const int slot = blockIdx.x + B.slotOff, f = blockIdx.y;
 #endif
   const int keyBase = __ldg(B.slotKeyBase + slot);        // needed only by the emission: fetched now, off the critical path
   int l = 0;
@@ -967,9 +967,9 @@ __global__ void __launch_bounds__(kOctMaxThreads) octree_kernel(const __grid_con
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, T = blockDim.x;            // 128 ... 1024 threads, chosen by the host from the frame size
 #if ORBX_OCT_FF
-  const int l = blockIdx.y, f = blockIdx.x;
+  const int l = blockIdx.y + B.levelOff, f = blockIdx.x;
 #else
-  const int l = blockIdx.x, f = blockIdx.y;
+  const int l = blockIdx.x + B.levelOff, f = blockIdx.y;
 #endif
   const LevelGeom& L = G.L[l];
   const int cap = G.nodeCap;
@@ -2093,14 +2093,22 @@ static bool use_fast_warp() {
   return v;
 }
 
-void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st) {
+// level0 / nlev: the pyramid levels of this launch (the whole pyramid by default; latency mode splits it over two streams)
+void launch_fast(const Geom& G, const Bufs& B0, const TmaSet& TM, int nframes, cudaStream_t st, int level0, int nlev) {
+  if (nlev < 0) nlev = G.nlevels - level0;
+  Bufs B = B0;
+  B.slotOff = G.L[level0].slot0;
+  const int nslots = (level0 + nlev < G.nlevels ? G.L[level0 + nlev].slot0 : G.totalSlots) - B.slotOff;
   if (use_fast_warp()) {
-    launch_chain(pdl_long(G, nframes), fast_warp_kernel, ORBX_FAST_FF ? dim3(nframes, G.totalSlots) : dim3(G.totalSlots, nframes), dim3(32 * kWarpCells), fast_warp_smem_bytes(G), st, G, B, TM);
+    launch_chain(pdl_long(G, nframes), fast_warp_kernel, ORBX_FAST_FF ? dim3(nframes, nslots) : dim3(nslots, nframes), dim3(32 * kWarpCells), fast_warp_smem_bytes(G), st, G, B, TM);
     return;
   }
-  launch_chain(pdl_long(G, nframes), fast_kernel, dim3(G.totalSlots, nframes), dim3(kFastThreads), fast_smem_bytes(G), st, G, B, TM);
+  launch_chain(pdl_long(G, nframes), fast_kernel, dim3(nslots, nframes), dim3(kFastThreads), fast_smem_bytes(G), st, G, B, TM);
 }
-void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
+void launch_octree(const Geom& G, const Bufs& B0, int nframes, cudaStream_t st, int level0, int nlev) {
+  if (nlev < 0) nlev = G.nlevels - level0;
+  Bufs B = B0;
+  B.levelOff = level0;
   // CTA size: barriers dominate small levels (128 threads: 1.74 ms vs 1.96 at 256 for 640x480), the quadratic ranking pass
   // and the key loops dominate large ones (4K level 0: ~150 k candidates, ~1100 nodes); ORBX_OCT_THREADS overrides
   static const int forced = getenv("ORBX_OCT_THREADS") ? atoi(getenv("ORBX_OCT_THREADS")) : 0;
@@ -2108,7 +2116,7 @@ void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st) {
   int threads = area < 600000 ? 128 : area < 3000000 ? 512 : 1024;
   if (nframes <= kLatencyFrames) threads = std::max(threads, 512);   // a handful of CTAs: the level-0 CTA is the critical path    // measured: 1080p 0.67 / 0.42 / 0.35 ms per 128 frames at 128 / 256 / 512
   if (forced == 128 || forced == 256 || forced == 512 || forced == 1024) threads = forced;
-  launch_chain(pdl_long(G, nframes), octree_kernel, ORBX_OCT_FF ? dim3(nframes, G.nlevels) : dim3(G.nlevels, nframes), dim3(threads), octree_smem_bytes(G), st, G, B);
+  launch_chain(pdl_long(G, nframes), octree_kernel, ORBX_OCT_FF ? dim3(nframes, nlev) : dim3(nlev, nframes), dim3(threads), octree_smem_bytes(G), st, G, B);
 }
 void launch_blur(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st) {
   // default: TMA-staged tiles; ORBX_BLUR_TMA=0 selects the global-load walk for A/B runs

@@ -279,7 +279,7 @@ template <bool LOCAL>
 __global__ void __launch_bounds__(kResolveThreads) sbp_resolve_kernel(FrameDev F, PointsDev P, SearchParams S, const int* offs,
                                                                      const int* cnts, const uint32_t* cand, int* choice,
                                                                      int* gBlockF, int* gBlockT, int smemN, int32_t* assign,
-                                                                     int* misc) {
+                                                                     int* misc, int* hostOut, int wantChoice) {
   extern __shared__ int sblock[];
   __shared__ int cnt, hist[HISTO], keepBin[3];
   const int tid = threadIdx.x, T = blockDim.x, m = P.m, n = F.n;
@@ -363,11 +363,36 @@ __global__ void __launch_bounds__(kResolveThreads) sbp_resolve_kernel(FrameDev F
     __syncthreads();
   }
   if (tid == 0) { misc[1] = cnt; misc[2] = rounds; }
+  if (hostOut) {
+    // zero-copy result: [counters (8) | assign (n) | choice (m)] written straight into the caller's pinned (mapped) block, so
+    // the search ends with one stream synchronisation instead of a device->host copy; the counters are then cleared for the
+    // next search (they live in a persistent device block in this mode: no upload zeroes them)
+    __syncthreads();
+    if (tid < 8) hostOut[tid] = misc[tid];
+    for (int c = tid; c < n; c += T) hostOut[8 + c] = assign[c];
+    if (wantChoice) for (int i = tid; i < m; i += T) hostOut[8 + n + i] = choice[i];
+    __syncthreads();
+    if (tid < 8) misc[tid] = 0;
+  }
 }
 
 // ---- host orchestration -----------------------------------------------------------------------------------
 static thread_local DevArena g_arena, g_cand_arena;
 static thread_local HostArena g_host;
+// zero-copy searches: 8 counters per device, zero between searches (cleared by the resolve kernel that read them)
+struct ZcMisc {
+  int* p[64] = {};
+  int* get(int dev) {
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!p[dev]) {
+      if (cudaSetDevice(dev) != cudaSuccess || cudaMalloc(&p[dev], sizeof(int) * 8) != cudaSuccess) { p[dev] = nullptr; return nullptr; }
+      if (cudaMemset(p[dev], 0, sizeof(int) * 8) != cudaSuccess) { cudaFree(p[dev]); p[dev] = nullptr; return nullptr; }
+    }
+    return p[dev];
+  }
+};
+static thread_local ZcMisc g_zcMisc;
+static bool env_flag(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) != 0 : dflt != 0; }
 
 // one packed upload: the same layout on the host staging buffer and on the device
 struct Packer {
@@ -441,22 +466,31 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
   static const bool phaseTiming = getenv("ORBX_SEARCH_TIMING") != nullptr;      // debugging aid: host clock with a sync after every phase
   auto tnow = []() { return std::chrono::steady_clock::now(); };
   auto t0 = tnow();
-  ORBX_CUDA(cudaMemcpyAsync(db, hb, inBytes, cudaMemcpyHostToDevice, st));
+  // Zero-copy mode (resident frame, small point sets -- the tracking thread's calls): the kernels read the points straight
+  // from the pinned staging block over PCIe (each field once, coalesced) and the resolve kernel writes the result into it, so
+  // the search is two launches + one synchronisation, no copies.  The counters then live in a persistent device block that the
+  // resolve kernel clears at its end.
+  static const bool zcOn = env_flag("ORBX_ZEROCOPY", 1);
+  uint8_t* hdev = nullptr;      // device-side address of the staging block
+  const bool zc = zcOn && rf && inBytes <= ((size_t)256 << 10) && cudaHostGetDevicePointer((void**)&hdev, hb, 0) == cudaSuccess && hdev &&
+                  g_zcMisc.get(device) != nullptr;
+  uint8_t* pb = zc ? hdev : db;   // where the kernels find the points
+  if (!zc) ORBX_CUDA(cudaMemcpyAsync(db, hb, inBytes, cudaMemcpyHostToDevice, st));
   if (phaseTiming) { cudaStreamSynchronize(st); fprintf(stderr, "[sbp] m=%d n=%d upload %zu B: %.1f us\n", m, n, inBytes, std::chrono::duration<double, std::micro>(tnow() - t0).count()); t0 = tnow(); }
-  int* d_misc = (int*)(db + o_misc);
+  int* d_misc = zc ? g_zcMisc.get(device) : (int*)(db + o_misc);
 
   FrameDev F;
   F.kps = rf ? rf->d_unkps : (const orbx_keypoint*)(db + o_kps); F.desc = rf ? rf->d_desc : db + o_desc; F.n = n;
   F.xmin = frame->xmin; F.xmax = frame->xmax; F.ymin = frame->ymin; F.ymax = frame->ymax;
   F.gw = (float)GC / (frame->xmax - frame->xmin);           // camera.cpp:47-48
   F.gh = (float)GR / (frame->ymax - frame->ymin);
-  F.scale = rf ? rf->d_scale : (const float*)(db + o_sc); F.nlevels = frame->nlevels; F.occupied0 = db + o_occ;
+  F.scale = rf ? rf->d_scale : (const float*)(db + o_sc); F.nlevels = frame->nlevels; F.occupied0 = pb + o_occ;
   F.cellStart = rf ? rf->d_cellStart : (const int*)(db + o_cellStart); F.ids = rf ? rf->d_ids : (const int*)(db + o_ids);
   F.feat = rf ? rf->d_feat : (const float4*)(db + o_feat);
   PointsDev P;
-  P.m = m; P.valid = db + o_valid; P.has_obs = db + o_obs; P.u = (const float*)(db + o_u); P.v = (const float*)(db + o_v);
-  P.aux = (const float*)(db + o_aux); P.angle_or_cos = (const float*)(db + o_ac); P.level = (const int32_t*)(db + o_lvl);
-  P.desc = db + o_pd;
+  P.m = m; P.valid = pb + o_valid; P.has_obs = pb + o_obs; P.u = (const float*)(pb + o_u); P.v = (const float*)(pb + o_v);
+  P.aux = (const float*)(pb + o_aux); P.angle_or_cos = (const float*)(pb + o_ac); P.level = (const int32_t*)(pb + o_lvl);
+  P.desc = pb + o_pd;
 
   if (!rf)
     grid_build_kernel<<<1, 1024, 0, st>>>(F.kps, (const float*)(db + o_ur), n, F.xmin, F.ymin, F.gw, F.gh, (int*)(db + o_cellOf),
@@ -471,14 +505,15 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
   for (int attempt = 0; attempt < 3; ++attempt) {
     if (g_cand_arena.reserve(sizeof(uint32_t) * capCand + 256, device)) { set_error("scratch allocation failed"); return ORBX_ERR_CUDA; }
     uint32_t* d_cand = g_cand_arena.take<uint32_t>(capCand);
-    if (attempt) ORBX_CUDA(cudaMemsetAsync(d_misc, 0, sizeof(int) * 8, st));
+    if (attempt && !zc) ORBX_CUDA(cudaMemsetAsync(d_misc, 0, sizeof(int) * 8, st));
     sbp_walk_kernel<LOCAL><<<(m + 7) / 8, 256, 0, st>>>(F, P, S, (int*)(db + o_offs), (int*)(db + o_cnts), d_cand, (int)std::min<size_t>(capCand, INT_MAX), slotCap, d_misc);
     if (phaseTiming) { cudaStreamSynchronize(st); fprintf(stderr, "[sbp] walk: %.1f us\n", std::chrono::duration<double, std::micro>(tnow() - t0).count()); t0 = tnow(); }
     sbp_resolve_kernel<LOCAL><<<1, kResolveThreads, sizeof(int) * 2 * smemN, st>>>(F, P, S, (const int*)(db + o_offs), (const int*)(db + o_cnts), d_cand,
                                                                               (int*)(db + o_choice), (int*)(db + o_bF), (int*)(db + o_bT), smemN,
-                                                                              (int32_t*)(db + o_assign), d_misc);
+                                                                              (int32_t*)(db + o_assign), d_misc, zc ? (int*)(hdev + inBytes) : nullptr,
+                                                                              choice_out ? 1 : 0);
     if (phaseTiming) { cudaStreamSynchronize(st); fprintf(stderr, "[sbp] resolve: %.1f us\n", std::chrono::duration<double, std::micro>(tnow() - t0).count()); t0 = tnow(); }
-    ORBX_CUDA(cudaMemcpyAsync(hout, db + o_misc, choice_out ? outBytes : outBytes - sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+    if (!zc) ORBX_CUDA(cudaMemcpyAsync(hout, db + o_misc, choice_out ? outBytes : outBytes - sizeof(int) * m, cudaMemcpyDeviceToHost, st));
     ORBX_CUDA(cudaStreamSynchronize(st));
     ORBX_CUDA(cudaGetLastError());
     if (phaseTiming) fprintf(stderr, "[sbp] download %zu B: %.1f us (rounds %d)\n", outBytes, std::chrono::duration<double, std::micro>(tnow() - t0).count(), ((const int*)hout)[2]);
