@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -354,7 +355,10 @@ int configure(orbx_extractor* h, int W, int H, int chunk) {
       const int ntx = (D.w + kRzTileW - 1) / kRzTileW;
       const long long ctasFull = (long long)ntx * ((D.h + kRzTileH - 1) / kRzTileH) * chunk;
       T.rt.rows = (ctasFull < 6000 && env_int("ORBX_RESIZE_SMALL_TILES", 1)) ? kRwRows / 2 : kRwRows;
-      if ((D.h + 4 * T.rt.rows - 1) / (4 * T.rt.rows) > kRzMaxTY) T.rt.rows = kRwRows;      // tall level: keep the origin table in range
+      // latency mode (a handful of frames per call): the 7 dependent launches are each one partial wave, so their duration is
+      // the per-thread walk; quarter-height tiles shorten it (ORBX_RESIZE_LAT_ROWS, A/B)
+      if (chunk <= kSplitFrames) T.rt.rows = std::max(1, std::min(kRwRows, env_int("ORBX_RESIZE_LAT_ROWS", kRwRows / 4)));
+      while (T.rt.rows < kRwRows && (D.h + 4 * T.rt.rows - 1) / (4 * T.rt.rows) > kRzMaxTY) T.rt.rows *= 2;   // tall level: keep the origin table in range
       const int tileH = 4 * T.rt.rows;
       const int nty = (D.h + tileH - 1) / tileH;
       bool fits = quadOk && ntx <= kRzMaxTX && nty <= kRzMaxTY;
@@ -1054,6 +1058,8 @@ int orbx_frame_create(orbx_handle h, const orbx_camera* cam, const uint8_t* img,
     h->d_in_bytes = fbytes;
   }
   cudaStream_t st = h->stream;
+  static const bool phaseTiming = getenv("ORBX_CREATE_TIMING") != nullptr;   // debugging aid: where the host time of one call goes
+  const auto tc0 = std::chrono::steady_clock::now();
   cudaError_t e = pitch == stride ? cudaMemcpyAsync(h->d_in, img, fbytes, cudaMemcpyHostToDevice, st)
                                   : cudaMemcpy2DAsync(h->d_in, pitch, img, stride, w, height, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return fail(ORBX_ERR_CUDA); }
@@ -1069,7 +1075,13 @@ int orbx_frame_create(orbx_handle h, const orbx_camera* cam, const uint8_t* img,
   if (rc == ORBX_OK) {
     h->launches += 1;
     e = cudaMemcpyAsync(f->h_mirror, f->d_block, f->packed_bytes, cudaMemcpyDeviceToHost, st);
+    const auto tc1 = std::chrono::steady_clock::now();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (phaseTiming) {
+      const auto tc2 = std::chrono::steady_clock::now();
+      fprintf(stderr, "[frame_create] enqueue %.1f us, wait %.1f us\n", std::chrono::duration<double, std::micro>(tc1 - tc0).count(),
+              std::chrono::duration<double, std::micro>(tc2 - tc1).count());
+    }
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = ORBX_ERR_CUDA; }
   } else {
     cudaStreamSynchronize(st);

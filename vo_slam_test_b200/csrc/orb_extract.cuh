@@ -81,6 +81,7 @@ struct Bufs {
   const int* umax;         // 16
   int slotOff;             // first FAST slot / quadtree level of this launch (latency mode launches level 0 and levels >= 1
   int levelOff;            // separately, on two streams); 0 for whole-pyramid launches
+  int octKeySmem;          // latency mode: the quadtree CTA keeps up to this many (key, node label) pairs in shared memory
 };
 
 // TMA descriptors (cuTensorMapEncodeTiled, rank 3: x bytes, y rows, frame) of every pyramid level, used by the FAST

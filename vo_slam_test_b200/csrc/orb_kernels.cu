@@ -962,7 +962,10 @@ __device__ __forceinline__ int quadrant_of(const short4 b, int x, int y) {
   return (x < mx ? 0 : 1) | (y < my ? 0 : 2);     // 0:n1 1:n2 2:n3 3:n4   (:521-531)
 }
 
-__global__ void __launch_bounds__(kOctMaxThreads) octree_kernel(const __grid_constant__ Geom G, const Bufs B) {
+// (warp-aggregated shared atomics -- __match_any_sync groups electing one leader per node -- were measured and dropped: the
+// quadtree went 1.47 -> 1.80 ms per 4096 frames and 36 -> 39 us for one frame; same-address shared atomics are not its bound)
+template <bool KS>   // KS: latency mode, keys and node labels in shared memory (Bufs::octKeySmem)
+__global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_constant__ Geom G, const Bufs B) {
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, T = blockDim.x;            // 128 ... 1024 threads, chosen by the host from the frame size
@@ -1007,6 +1010,15 @@ __global__ void __launch_bounds__(kOctMaxThreads) octree_kernel(const __grid_con
     if (tid == 0) *selCount = 0;
     return;
   }
+  // Latency mode (a handful of CTAs per launch, occupancy is irrelevant): keys and node labels of this level stay in shared
+  // memory, so the two key sweeps of every pass cost shared-memory instead of L2 latency (the sweeps were ~80 % of the
+  // single-frame kernel).  The flat key list still goes to global memory once (stage taps read it).
+  const bool inS = KS && n <= B.octKeySmem;
+  uint32_t* gkeys = keys;
+  if (KS && inS) {
+    keys = reinterpret_cast<uint32_t*>(S.ws + 40);                       // behind the scan scratch: [octKeySmem] keys, then labels
+    nodeOf = reinterpret_cast<uint16_t*>(keys + B.octKeySmem);
+  }
   {
     // one THREAD per slot (a slot holds the few dozen corners of two cells): every thread's chain count -> base -> keys runs
     // beside the others' instead of one slot at a time per warp (this gather was the top line of the kernel's profile:
@@ -1020,7 +1032,7 @@ __global__ void __launch_bounds__(kOctMaxThreads) octree_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = k + j < c ? src[k + j] : 0u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (k + j < c) keys[o + k + j] = v[j];
+        for (int j = 0; j < 4; ++j) if (k + j < c) { gkeys[o + k + j] = v[j]; if (KS && inS) keys[o + k + j] = v[j]; }
       }
     }
   }
@@ -2073,13 +2085,23 @@ size_t octree_smem_bytes(const Geom& G) {
   return 8 * cap + 8 * cap * 2 + 4 * cap * 2 + 16 * cap + 4 * cap + 4 * (cap + 1) + 4 * cap + 16 * cap +
          4 * (size_t)(G.maxSlotsPerLevel + 1) + 4 * 40 + 64;
 }
+// latency mode: (key, label) pairs kept in shared memory behind the node arrays -- as many as a 200 KB CTA allows, at most the
+// largest level's candidate capacity
+int octree_key_smem(const Geom& G) {
+  int want = 0;
+  for (int l = 0; l < G.nlevels; ++l) want = std::max(want, G.L[l].keyCap);
+  const size_t base = octree_smem_bytes(G), room = base < ((size_t)200 << 10) ? (((size_t)200 << 10) - base) / 6 : 0;
+  return (int)std::min<size_t>((size_t)want, room) & ~7;
+}
 
 cudaError_t configure_kernels(const Geom& G) {
   cudaError_t e = cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(G));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(fast_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_warp_smem_bytes(G));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_smem_bytes(G));
+  e = cudaFuncSetAttribute(octree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(octree_smem_bytes(G) + 6 * (size_t)octree_key_smem(G)));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(octree_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_smem_bytes(G));
 }
 
 size_t fast_warp_smem_bytes(const Geom& G) {
@@ -2116,7 +2138,14 @@ void launch_octree(const Geom& G, const Bufs& B0, int nframes, cudaStream_t st, 
   int threads = area < 600000 ? 128 : area < 3000000 ? 512 : 1024;
   if (nframes <= kLatencyFrames) threads = std::max(threads, 512);   // a handful of CTAs: the level-0 CTA is the critical path    // measured: 1080p 0.67 / 0.42 / 0.35 ms per 128 frames at 128 / 256 / 512
   if (forced == 128 || forced == 256 || forced == 512 || forced == 1024) threads = forced;
-  launch_chain(pdl_long(G, nframes), octree_kernel, ORBX_OCT_FF ? dim3(nframes, nlev) : dim3(nlev, nframes), dim3(threads), octree_smem_bytes(G), st, G, B);
+  static const bool keySmem = !(getenv("ORBX_OCT_KEYSMEM") && atoi(getenv("ORBX_OCT_KEYSMEM")) == 0);
+  B.octKeySmem = (keySmem && nframes <= kLatencyFrames) ? octree_key_smem(G) : 0;
+  if (B.octKeySmem > 0)
+    launch_chain(pdl_long(G, nframes), octree_kernel<true>, ORBX_OCT_FF ? dim3(nframes, nlev) : dim3(nlev, nframes), dim3(threads),
+                 octree_smem_bytes(G) + 6 * (size_t)B.octKeySmem, st, G, B);
+  else
+    launch_chain(pdl_long(G, nframes), octree_kernel<false>, ORBX_OCT_FF ? dim3(nframes, nlev) : dim3(nlev, nframes), dim3(threads),
+                 octree_smem_bytes(G), st, G, B);
 }
 void launch_blur(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st) {
   // default: TMA-staged tiles; ORBX_BLUR_TMA=0 selects the global-load walk for A/B runs

@@ -220,22 +220,50 @@ __global__ void __launch_bounds__(256) sbp_walk_kernel(FrameDev F, PointsDev P, 
   const uint4* dq = reinterpret_cast<const uint4*>(P.desc + (size_t)i * 32);
   const uint4 d0 = __ldg(dq), d1 = __ldg(dq + 1);
   int run = base;
-  for (int ix = x0; ix <= x1; ++ix) {
-    const int lo = __ldg(F.cellStart + ix * GR + y0), hi = __ldg(F.cellStart + ix * GR + y1 + 1);
-    for (int e = lo + lane; e < ((hi - lo + 31) & ~31) + lo; e += 32) {
-      bool pass = false;
-      int idx = 0;
-      float4 ft = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e < hi) { idx = __ldg(F.ids + e); ft = __ldg(F.feat + idx); pass = gate<LOCAL>(F, S, w, ft); }
-      const unsigned b = __ballot_sync(0xffffffffu, pass);
-      const int pos = run + __popc(b & ((1u << lane) - 1));
-      if (pass && pos < limit) {
-        int dist = hamming256(d0, d1, F.desc + (size_t)idx * 32);
-        const int oct = __float_as_int(ft.z);
-        if (S.level_at_select && (oct < w.minL || oct > w.maxL)) dist = 511;   // keeps its position in the list but can never be selected
-        cand[pos] = (uint32_t)idx | ((uint32_t)dist << 20) | ((uint32_t)(oct & 7) << 29);
-      }
-      run += __popc(b);
+  auto emit = [&](bool live, int e) {        // one CSR entry per lane, survivors appended in lane order
+    bool pass = false;
+    int idx = 0;
+    float4 ft = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) { idx = __ldg(F.ids + e); ft = __ldg(F.feat + idx); pass = gate<LOCAL>(F, S, w, ft); }
+    const unsigned b = __ballot_sync(0xffffffffu, pass);
+    const int pos = run + __popc(b & ((1u << lane) - 1));
+    if (pass && pos < limit) {
+      int dist = hamming256(d0, d1, F.desc + (size_t)idx * 32);
+      const int oct = __float_as_int(ft.z);
+      if (S.level_at_select && (oct < w.minL || oct > w.maxL)) dist = 511;   // keeps its position in the list but can never be selected
+      cand[pos] = (uint32_t)idx | ((uint32_t)dist << 20) | ((uint32_t)(oct & 7) << 29);
+    }
+    run += __popc(b);
+  };
+  const int ncol = x1 - x0 + 1;
+  if (ncol <= 32) {
+    // The window's columns are walked as ONE flat list: lane c fetches the CSR range of column x0 + c (all columns at once), a warp
+    // scan gives every column its offset, and entry t of the list belongs to the column whose range covers it.  Same order as
+    // the column loop below (ix outer, CSR position inner), but the dependent chain cellStart -> ids -> feat -> descriptor is
+    // paid once per 32 entries instead of once per column (a tracking window holds a handful of features in 4..7 columns).
+    int lo = 0, len = 0;
+    if (lane < ncol) {
+      lo = __ldg(F.cellStart + (x0 + lane) * GR + y0);
+      len = __ldg(F.cellStart + (x0 + lane) * GR + y1 + 1) - lo;
+    }
+    int inc = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    const int E = __shfl_sync(0xffffffffu, inc, 31), pre = inc - len;
+    for (int t0 = 0; t0 < E; t0 += 32) {
+      const int t = t0 + lane;
+      int c = 0;
+      for (int j = 0; j < ncol - 1; ++j) c += (__shfl_sync(0xffffffffu, inc, j) <= t) ? 1 : 0;
+      const int lo_c = __shfl_sync(0xffffffffu, lo, c), pre_c = __shfl_sync(0xffffffffu, pre, c);
+      emit(t < E, lo_c + (t - pre_c));
+    }
+  } else {
+    for (int ix = x0; ix <= x1; ++ix) {
+      const int lo = __ldg(F.cellStart + ix * GR + y0), hi = __ldg(F.cellStart + ix * GR + y1 + 1);
+      for (int e = lo + lane; e < ((hi - lo + 31) & ~31) + lo; e += 32) emit(e < hi, e);
     }
   }
   if (slotCap > 0 && lane == 0) {
