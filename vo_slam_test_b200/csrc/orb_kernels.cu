@@ -964,6 +964,39 @@ __device__ __forceinline__ int quadrant_of(const short4 b, int x, int y) {
 
 // (warp-aggregated shared atomics -- __match_any_sync groups electing one leader per node -- were measured and dropped: the
 // quadtree went 1.47 -> 1.80 ms per 4096 frames and 36 -> 39 us for one frame; same-address shared atomics are not its bound)
+// Exclusive scan of `n` ints in shared memory, in place, by ONE warp (all 32 lanes call it; the data must be visible to the
+// warp: __syncwarp before).  Returns the total.
+__device__ __forceinline__ int warp_exclusive_scan(int* data, int n) {
+  const int lane = threadIdx.x & 31;
+  const int per = (n + 31) >> 5;
+  const int lo = min(lane * per, n), hi = min(lo + per, n);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += data[i];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  int run = incl - sum;
+  for (int i = lo; i < hi; ++i) {
+    const int v = data[i];
+    data[i] = run;
+    run += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  __syncwarp();
+  return total;
+}
+
+#ifndef ORBX_OCT_TRACE
+#define ORBX_OCT_TRACE 0            // debugging aid: level-0 CTA of frame 0 prints its phase timeline (cycles)
+#endif
+#if ORBX_OCT_TRACE
+#define OCT_STAMP(name) do { if (tid == 0 && l == 0 && f == 0 && nst < 48) { st_t[nst] = clock64(); st_n[nst++] = name; } } while (0)
+#else
+#define OCT_STAMP(name) do { } while (0)
+#endif
 template <bool KS>   // KS: latency mode, keys and node labels in shared memory (Bufs::octKeySmem)
 __global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_constant__ Geom G, const Bufs B) {
   pdl_prologue();
@@ -976,6 +1009,10 @@ __global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_
 #endif
   const LevelGeom& L = G.L[l];
   const int cap = G.nodeCap;
+#if ORBX_OCT_TRACE
+  long long st_t[48]; const char* st_n[48]; int nst = 0;
+#endif
+  OCT_STAMP("start");
   OctSmem S;
   {
     uint8_t* p = smem_raw;
@@ -992,7 +1029,7 @@ __global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_
     S.slotPre = (int*)p; p += 4 * (G.maxSlotsPerLevel + 1);
     S.ws = (int*)p;
   }
-  __shared__ int sh_stop, sh_nexp;
+  __shared__ int sh_stop, sh_res[3];
   __shared__ int rootCnt[kMaxRoots], rootPos[kMaxRoots];
 
   uint32_t* keys = B.flatKeys + (size_t)f * G.keysPerFrame + L.keyBase;
@@ -1020,24 +1057,37 @@ __global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_
     nodeOf = reinterpret_cast<uint16_t*>(keys + B.octKeySmem);
   }
   {
-    // one THREAD per slot (a slot holds the few dozen corners of two cells): every thread's chain count -> base -> keys runs
-    // beside the others' instead of one slot at a time per warp (this gather was the top line of the kernel's profile:
-    // three dependent L2 round trips per slot, serialised)
+    // one THREAD per KEY: the slot of flat position k is found by a binary search in the scanned slot counts (shared memory),
+    // then its key is one independent load -- four keys in flight per thread.  (One thread per slot walked a slot's few dozen keys
+    // as dependent rounds of four: 8400 of the 45000 cycles of a single-frame level-0 CTA.)
     const uint32_t* slotKeys = B.slotKeys + (size_t)f * G.slotKeysPerFrame;
-    for (int s = tid; s < L.nSlots; s += T) {
-      const int o = S.slotPre[s], c = (s + 1 < L.nSlots ? S.slotPre[s + 1] : n) - o;
-      const uint32_t* src = slotKeys + __ldg(B.slotKeyBase + L.slot0 + s);
-      for (int k = 0; k < c; k += 4) {                    // four loads in flight per thread
-        uint32_t v[4];
+    const int* keyBase = B.slotKeyBase + L.slot0;
+    const int nS = L.nSlots;
+    for (int k0 = tid; k0 < n; k0 += 4 * T) {
+      uint32_t v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = k + j < c ? src[k + j] : 0u;
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + j * T;
+        v[j] = 0u;
+        if (k < n) {
+          int lo = 0, hi = nS - 1;                   // largest s with slotPre[s] <= k (skips empty slots)
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (S.slotPre[mid] <= k) lo = mid; else hi = mid - 1;
+          }
+          v[j] = slotKeys[__ldg(keyBase + lo) + (k - S.slotPre[lo])];
+        }
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (k + j < c) { gkeys[o + k + j] = v[j]; if (KS && inS) keys[o + k + j] = v[j]; }
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + j * T;
+        if (k < n) { gkeys[k] = v[j]; if (KS && inS) keys[k] = v[j]; }
       }
     }
   }
   if (tid < kMaxRoots) rootCnt[tid] = 0;
   __syncthreads();
+  OCT_STAMP("gather");
 
   // ---- roots (ORBextractor.cpp:549-590) ----------------------------------------------------------------
   int cur = 0;
@@ -1076,6 +1126,15 @@ __global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_
   const int N = L.nFeat;
   int phase = 1;
   bool finish = false;
+  const int lane = tid & 31, wid = tid >> 5;
+  // One pass = [count sweep, all threads] barrier [node list rebuild, WARP 0 ALONE with warp scans and __syncwarp] barrier
+  // [relabel sweep, all threads].  The rebuild works on at most N + 3 nodes: spread over the whole CTA it was ~20 CTA barriers
+  // per pass (barrier stalls were half of the kernel's samples); one warp does it in a few hundred instructions while the
+  // other warps of the SM's CTAs run.  Only the quadratic phase-2 ranking stays CTA-wide.  Every thread owns the keys
+  // k = tid (mod T) in all sweeps, so the node labels need no barrier between the relabel sweep and the next count sweep.
+  for (int i = tid; i < Scount * 4; i += T) S.cnt4[i] = 0;
+  __syncthreads();
+  OCT_STAMP("roots");
   while (!finish) {
     // selects instead of S.box[cur]: a runtime index would put the pointer struct into local memory
     const short4* box = cur ? S.box[1] : S.box[0];
@@ -1084,9 +1143,6 @@ __global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_
     int* ncnt = cur ? S.cnt[0] : S.cnt[1];
     const int Sn = Scount;
 
-    for (int i = tid; i < Sn * 4; i += T) S.cnt4[i] = 0;
-    if (tid == 0) { sh_stop = 0x7fffffff; sh_nexp = 0; }
-    __syncthreads();
     // keys and node labels live in global memory (L2): four independent (label, key) pairs are fetched per thread before
     // anything is done with them, instead of label -> test -> key -> atomic one key at a time (two dependent L2 latencies each)
     for (int k0 = tid; k0 < n; k0 += kOctBatch * T) {
@@ -1102,11 +1158,8 @@ __global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_
         if (pp[j] >= 0 && cnt[pp[j]] > 1) atomicAdd(&S.cnt4[pp[j] * 4 + quadrant_of(box[pp[j]], key_x(kk[j]), key_y(kk[j]))], 1);
     }
     __syncthreads();
+    OCT_STAMP("count");
 
-    // processing rank of every expandable node
-    for (int p = tid; p < Sn; p += T) S.rank[p] = cnt[p] > 1 ? 1 : 0;
-    __syncthreads();
-    const int E = block_exclusive_scan(S.rank, Sn, S.ws);   // phase 1: list order
     if (phase == 2) {
       // stable descending-size order of the list (reference: sort of (size, node*) walked from the back)
       for (int p = tid; p < Sn; p += T) {
@@ -1122,71 +1175,141 @@ __global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_
       }
       __syncthreads();
     }
-    // children per processing rank
-    for (int p = tid; p < Sn; p += T) {
-      if (cnt[p] > 1) {
-        const int* c4 = S.cnt4 + p * 4;
-        S.childR[S.rank[p]] = (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0);
-      }
-    }
-    __syncthreads();
-    // keep a copy of per-rank child counts in keepPos (borrowed) before the scan overwrites them
-    for (int t = tid; t < E; t += T) S.keepPos[t] = S.childR[t];
-    __syncthreads();
-    const int allChildren = block_exclusive_scan(S.childR, E, S.ws);
-    if (tid == 0) S.childR[E] = allChildren;
-    int Pn = E;
-    if (phase == 2) {
-      // first rank t whose split makes the list reach N:  Sn + (children up to and incl. t) - (t+1) >= N
-      for (int t = tid; t < E; t += T) {
-        const int incl = S.childR[t] + S.keepPos[t];
-        if (Sn + incl - (t + 1) >= N) atomicMin(&sh_stop, t);
-      }
-    }
-    __syncthreads();
-    if (phase == 2 && sh_stop != 0x7fffffff) Pn = sh_stop + 1;
-    const int totalChildren = S.childR[Pn];
-    __syncthreads();   // everyone has read childR[Pn] / keepPos before keepPos is rewritten below
 
-    // positions of the children blocks and of the surviving old nodes
-    for (int p = tid; p < Sn; p += T) {
-      const bool split = cnt[p] > 1 && S.rank[p] < Pn;
-      int* cp = S.childPos + p * 4;
-      if (split) {
-        const int t = S.rank[p];
-        const int* c4 = S.cnt4 + p * 4;
-        const int nch = (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0);
-        int o = totalChildren - S.childR[t] - nch;      // blocks of later-processed parents come first
-        const short4 b = box[p];
-        const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);
+    if (wid == 0 && phase == 1) {
+      // Phase 1 splits EVERY expandable node in list order, so the new position of a node's children is the number of
+      // children of the expandable nodes behind it, and a kept node follows all children in list order: one packed warp scan
+      // (children << 16 | kept) over contiguous chunks of the list replaces the rank / per-rank child count / kept scans.
+      const int per = (Sn + 31) >> 5, p0 = min(lane * per, Sn), p1 = min(p0 + per, Sn);
+      int mine = 0;
+      for (int p = p0; p < p1; ++p) {
+        if (cnt[p] > 1) {
+          const int* c4 = S.cnt4 + p * 4;
+          mine += ((c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0)) << 16;
+        } else ++mine;
+      }
+      int incl = mine;
 #pragma unroll
-        for (int q = 3; q >= 0; --q) {
-          if (c4[q] > 0) {
-            cp[q] = o;
-            nbox[o] = make_short4((q & 1) ? mx : b.x, (q & 2) ? my : b.y, (q & 1) ? b.z : mx, (q & 2) ? b.w : my);
-            ncnt[o] = c4[q];
-            if (c4[q] > 1) atomicAdd(&sh_nexp, 1);
-            ++o;
-          } else cp[q] = -1;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int tot = __shfl_sync(0xffffffffu, incl, 31);
+      const int totalChildren = tot >> 16, nKept = tot & 0xFFFF;
+      int chBefore = (incl - mine) >> 16, keptBefore = (incl - mine) & 0xFFFF, nexp = 0;
+      for (int p = p0; p < p1; ++p) {
+        int* cp = S.childPos + p * 4;
+        if (cnt[p] > 1) {
+          const int* c4 = S.cnt4 + p * 4;
+          const int nch = (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0);
+          int o = totalChildren - chBefore - nch;         // blocks of later-processed parents come first
+          chBefore += nch;
+          const short4 b = box[p];
+          const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);
+#pragma unroll
+          for (int q = 3; q >= 0; --q) {
+            if (c4[q] > 0) {
+              cp[q] = o;
+              nbox[o] = make_short4((q & 1) ? mx : b.x, (q & 2) ? my : b.y, (q & 1) ? b.z : mx, (q & 2) ? b.w : my);
+              ncnt[o] = c4[q];
+              nexp += c4[q] > 1 ? 1 : 0;
+              ++o;
+            } else cp[q] = -1;
+          }
+          S.keepPos[p] = -1;
+        } else {
+          const int o = totalChildren + keptBefore;
+          nbox[o] = box[p];
+          ncnt[o] = cnt[p];
+          S.keepPos[p] = keptBefore++;
         }
       }
-    }
-    __syncthreads();
-    // surviving nodes keep their relative order behind the children
-    for (int p = tid; p < Sn; p += T) S.keepPos[p] = (cnt[p] > 1 && S.rank[p] < Pn) ? 0 : 1;
-    __syncthreads();
-    const int nKept = block_exclusive_scan(S.keepPos, Sn, S.ws);
-    for (int p = tid; p < Sn; p += T) {
-      const bool split = cnt[p] > 1 && S.rank[p] < Pn;
-      if (!split) {
-        const int o = totalChildren + S.keepPos[p];
-        nbox[o] = box[p];
-        ncnt[o] = cnt[p];
-      } else {
-        S.keepPos[p] = -1;
+      nexp = __reduce_add_sync(0xffffffffu, nexp);     // also orders the cnt4 reads above before the zeroing below
+      const int newS = totalChildren + nKept;
+      for (int i = lane; i < newS * 4; i += 32) S.cnt4[i] = 0;      // quadrant counters of the next pass
+      if (lane == 0) { sh_res[0] = totalChildren; sh_res[1] = newS; sh_res[2] = nexp; }
+    } else if (wid == 0) {
+      // phase 2: processing rank = stable descending-size order (S.rank, above); E expandable nodes
+      int E;
+      {
+        int c = 0;
+        for (int p = lane; p < Sn; p += 32) c += cnt[p] > 1 ? 1 : 0;
+        E = __reduce_add_sync(0xffffffffu, c);
       }
+      // children per processing rank
+      for (int p = lane; p < Sn; p += 32) {
+        if (cnt[p] > 1) {
+          const int* c4 = S.cnt4 + p * 4;
+          S.childR[S.rank[p]] = (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0);
+        }
+      }
+      __syncwarp();
+      // keep a copy of per-rank child counts in keepPos (borrowed) before the scan overwrites them
+      for (int t = lane; t < E; t += 32) S.keepPos[t] = S.childR[t];
+      __syncwarp();
+      const int allChildren = warp_exclusive_scan(S.childR, E);
+      if (lane == 0) S.childR[E] = allChildren;
+      __syncwarp();
+      int Pn = E;
+      if (phase == 2) {
+        // first rank t whose split makes the list reach N:  Sn + (children up to and incl. t) - (t+1) >= N
+        int stop = 0x7fffffff;
+        for (int t = lane; t < E; t += 32) {
+          const int incl = S.childR[t] + S.keepPos[t];
+          if (Sn + incl - (t + 1) >= N) stop = min(stop, t);
+        }
+        stop = __reduce_min_sync(0xffffffffu, stop);
+        if (stop != 0x7fffffff) Pn = stop + 1;
+      }
+      const int totalChildren = S.childR[Pn];
+      __syncwarp();   // every lane has read childR[Pn] / keepPos before keepPos is rewritten below
+
+      // positions of the children blocks and of the surviving old nodes
+      int nexp = 0;
+      for (int p = lane; p < Sn; p += 32) {
+        const bool split = cnt[p] > 1 && S.rank[p] < Pn;
+        int* cp = S.childPos + p * 4;
+        if (split) {
+          const int t = S.rank[p];
+          const int* c4 = S.cnt4 + p * 4;
+          const int nch = (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0);
+          int o = totalChildren - S.childR[t] - nch;      // blocks of later-processed parents come first
+          const short4 b = box[p];
+          const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);
+#pragma unroll
+          for (int q = 3; q >= 0; --q) {
+            if (c4[q] > 0) {
+              cp[q] = o;
+              nbox[o] = make_short4((q & 1) ? mx : b.x, (q & 2) ? my : b.y, (q & 1) ? b.z : mx, (q & 2) ? b.w : my);
+              ncnt[o] = c4[q];
+              nexp += c4[q] > 1 ? 1 : 0;
+              ++o;
+            } else cp[q] = -1;
+          }
+        }
+      }
+      nexp = __reduce_add_sync(0xffffffffu, nexp);
+      // surviving nodes keep their relative order behind the children
+      for (int p = lane; p < Sn; p += 32) S.keepPos[p] = (cnt[p] > 1 && S.rank[p] < Pn) ? 0 : 1;
+      __syncwarp();
+      const int nKept = warp_exclusive_scan(S.keepPos, Sn);
+      for (int p = lane; p < Sn; p += 32) {
+        const bool split = cnt[p] > 1 && S.rank[p] < Pn;
+        if (!split) {
+          const int o = totalChildren + S.keepPos[p];
+          nbox[o] = box[p];
+          ncnt[o] = cnt[p];
+        } else {
+          S.keepPos[p] = -1;
+        }
+      }
+      const int newS = totalChildren + nKept;
+      for (int i = lane; i < newS * 4; i += 32) S.cnt4[i] = 0;      // quadrant counters of the next pass
+      if (lane == 0) { sh_res[0] = totalChildren; sh_res[1] = newS; sh_res[2] = nexp; }
     }
     __syncthreads();
+    OCT_STAMP("nodes");
+    const int totalChildren = sh_res[0], newS = sh_res[1], nToExpand = sh_res[2];
     for (int k0 = tid; k0 < n; k0 += kOctBatch * T) {
       int pp[kOctBatch]; uint32_t kk[kOctBatch];
 #pragma unroll
@@ -1202,15 +1325,15 @@ __global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_
         nodeOf[k0 + j * T] = (uint16_t)(kp >= 0 ? totalChildren + kp : S.childPos[p * 4 + quadrant_of(box[p], key_x(kk[j]), key_y(kk[j]))]);
       }
     }
-    const int newS = totalChildren + nKept;
-    const int nToExpand = sh_nexp;
-    __syncthreads();
+    OCT_STAMP("relabel");
     cur ^= 1;
     Scount = newS;
     // termination (ORBextractor.cpp:672-744)
     if (newS >= N || newS == Sn) finish = true;
     else if (phase == 1 && newS + 3 * nToExpand > N) phase = 2;
   }
+  __syncthreads();      // the last relabel sweep read keepPos / childPos / box; the strongest-key pass below reuses nothing of them,
+                        // but Scount-sized arrays are initialised by all threads
 
   // ---- strongest key per node, first wins ties (ORBextractor.cpp:747-766) ------------------------------
   // max (response, then FIRST index): response + 1 (9 bits) above the complemented key index.  Below 2^23 candidates the pair fits
@@ -1242,6 +1365,14 @@ __global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_
     sel[p] = keys[k];
   }
   if (tid == 0) *selCount = Scount;
+#if ORBX_OCT_TRACE
+  OCT_STAMP("best");
+  if (tid == 0 && l == 0 && f == 0) {
+    printf("[octree] n=%d nodes=%d T=%d:", n, Scount, T);
+    for (int i = 1; i < nst; ++i) printf(" %s %lld", st_n[i], st_t[i] - st_t[i - 1]);
+    printf(" | total %lld cycles\n", st_t[nst - 1] - st_t[0]);
+  }
+#endif
 }
 
 // ======================================================================================================
