@@ -34,6 +34,7 @@ __device__ __forceinline__ int hamm(const uint4 a0, const uint4 a1, const uint8_
 // mode 1: KeyFrame -> KeyFrame: match[a_idx] = b_idx   (mappointMatches is indexed by the kf1 feature, :629)
 __global__ void __launch_bounds__(256) bow_match_kernel(BowSideDev A, BowSideDev B, int mode, float ratio, int th_low, int check_rot,
                                                         int* takenB, int32_t* match, int8_t* binOf, int* hist) {
+  pdl_prologue();      // lets bow_finish_kernel (a programmatic dependent launch) become resident while this grid drains
   const int lane = threadIdx.x & 31;
   const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (g >= A.ngroups) return;
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(256) tri_match_kernel(TriSideDev A, TriSideDev
 // with one stream synchronisation instead of a device->host copy.
 __global__ void __launch_bounds__(1024) bow_finish_kernel(int nOut, int check_rot, int32_t* match, const int8_t* binOf, const int* hist,
                                                           int* result, int32_t* hostOut = nullptr) {
+  pdl_prologue();      // blocks until the match kernel's results are complete and visible
   __shared__ int keep[3], cnt;
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -314,8 +316,8 @@ static int bow_run(const orbx_bow_side* a, const orbx_bow_side* b, int mode, flo
   static const bool zcOn = [] { const char* e = getenv("ORBX_ZEROCOPY"); return e ? atoi(e) != 0 : true; }();
   uint8_t* hdev = nullptr;
   const bool zc = zcOn && nOut <= (1 << 16) && cudaHostGetDevicePointer((void**)&hdev, hout, 0) == cudaSuccess && hdev;
-  bow_finish_kernel<<<1, 1024, 0, st>>>(nOut, check_rot, (int32_t*)(db + o_match), (const int8_t*)(db + o_bin), (const int*)(db + o_hist),
-                                        (int*)(db + o_res), zc ? (int32_t*)hdev : nullptr);
+  launch_chain(true, bow_finish_kernel, dim3(1), dim3(1024), 0, st, nOut, check_rot, (int32_t*)(db + o_match), (const int8_t*)(db + o_bin),
+               (const int*)(db + o_hist), (int*)(db + o_res), zc ? (int32_t*)hdev : (int32_t*)nullptr);
   if (!zc) ORBX_CUDA(cudaMemcpyAsync(hout, db + o_match, outBytes, cudaMemcpyDeviceToHost, st));
   ORBX_CUDA(cudaStreamSynchronize(st));
   ORBX_CUDA(cudaGetLastError());

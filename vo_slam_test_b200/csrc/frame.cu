@@ -153,12 +153,18 @@ int frame_finish_launch(const orbx_camera* cam, const orbx_keypoint* d_kps, cons
 }
 
 // feat[i].w = uright[i] after the host filled uRight_ from a host-side depth image (orbx_frame_create)
-__global__ void patch_uright_kernel(const float* __restrict__ uright, float4* __restrict__ feat, int n) {
+// `src` may be the frame's pinned host mirror (read over PCIe, 4 KB): the values then also land in the device copy `d_uright`,
+// and the separate host->device copy of uRight_ is saved.
+__global__ void patch_uright_kernel(const float* __restrict__ src, float* __restrict__ d_uright, float4* __restrict__ feat, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) feat[i].w = uright[i];
+  if (i < n) {
+    const float v = src[i];
+    if (d_uright != src) d_uright[i] = v;
+    feat[i].w = v;
+  }
 }
-int frame_patch_uright(const float* d_uright, float4* d_feat, int n, cudaStream_t st) {
-  if (n > 0) patch_uright_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_uright, d_feat, n);
+int frame_patch_uright(const float* src, float* d_uright, float4* d_feat, int n, cudaStream_t st) {
+  if (n > 0) patch_uright_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, d_uright, d_feat, n);
   ORBX_CUDA(cudaGetLastError());
   return ORBX_OK;
 }

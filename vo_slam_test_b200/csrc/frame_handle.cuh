@@ -18,6 +18,9 @@ struct orbx_frame {
   float* d_uright = nullptr; float* d_depth = nullptr;
   // device-only: what the searches read
   float* d_angle = nullptr; float* d_scale = nullptr; int32_t* d_cellStart = nullptr; int32_t* d_ids = nullptr; float4* d_feat = nullptr;
+  // the uRight_ patch of orbx_frame_create runs on the legacy default stream (where the searches run) and reads the mirror in
+  // place: the next frame built in this block (on the extractor's own stream) waits for it
+  cudaEvent_t patched = nullptr; bool patchPending = false;
 };
 
 namespace orbx {
@@ -28,6 +31,6 @@ int frame_finish_launch(const orbx_camera* cam, const orbx_keypoint* d_kps, cons
                         const float* d_depth, int w, int h, size_t depthRow, size_t depthFrame, orbx_keypoint* d_unkps, float* d_uright,
                         float* d_depthOut, int32_t* d_cellStart, int32_t* d_ids, float4* d_feat, float* d_angle, cudaStream_t st);
 
-int frame_patch_uright(const float* d_uright, float4* d_feat, int n, cudaStream_t st);
+int frame_patch_uright(const float* src, float* d_uright, float4* d_feat, int n, cudaStream_t st);
 
 }  // namespace orbx

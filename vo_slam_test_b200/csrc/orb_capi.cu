@@ -501,6 +501,7 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
 
 void free_frame_block(orbx_frame* f) {
   if (!f) return;
+  if (f->patched) cudaEventDestroy(f->patched);
   cudaFree(f->d_block);
   if (f->h_mirror) cudaFreeHost(f->h_mirror);
   delete f;
@@ -1058,6 +1059,7 @@ int orbx_frame_create(orbx_handle h, const orbx_camera* cam, const uint8_t* img,
     h->d_in_bytes = fbytes;
   }
   cudaStream_t st = h->stream;
+  if (f->patchPending) { cudaStreamWaitEvent(st, f->patched, 0); f->patchPending = false; }
   static const bool phaseTiming = getenv("ORBX_CREATE_TIMING") != nullptr;   // debugging aid: where the host time of one call goes
   const auto tc0 = std::chrono::steady_clock::now();
   cudaError_t e = pitch == stride ? cudaMemcpyAsync(h->d_in, img, fbytes, cudaMemcpyHostToDevice, st)
@@ -1105,9 +1107,16 @@ int orbx_frame_create(orbx_handle h, const orbx_camera* cam, const uint8_t* img,
       }
     }
     // the searches run on the legacy default stream: the 4 KB and the patch kernel are ordered in front of them there
-    e = cudaMemcpyAsync(f->d_uright, hur, sizeof(float) * (size_t)f->n, cudaMemcpyHostToDevice, nullptr);
-    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return fail(ORBX_ERR_CUDA); }
-    if (int r2 = frame_patch_uright(f->d_uright, f->d_feat, f->n, nullptr)) return fail(r2);
+    float* hurDev = nullptr;       // the pinned mirror as the device sees it: the patch kernel reads the 4 KB in place
+    if (cudaHostGetDevicePointer((void**)&hurDev, hur, 0) == cudaSuccess && hurDev) {
+      if (int r2 = frame_patch_uright(hurDev, f->d_uright, f->d_feat, f->n, nullptr)) return fail(r2);
+      if (!f->patched) cudaEventCreateWithFlags(&f->patched, cudaEventDisableTiming);
+      if (f->patched && cudaEventRecord(f->patched, nullptr) == cudaSuccess) f->patchPending = true;
+    } else {
+      e = cudaMemcpyAsync(f->d_uright, hur, sizeof(float) * (size_t)f->n, cudaMemcpyHostToDevice, nullptr);
+      if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return fail(ORBX_ERR_CUDA); }
+      if (int r2 = frame_patch_uright(f->d_uright, f->d_uright, f->d_feat, f->n, nullptr)) return fail(r2);
+    }
     h->launches += 1;
   }
   f->xmin = cam->xmin; f->xmax = cam->xmax; f->ymin = cam->ymin; f->ymax = cam->ymax;

@@ -186,6 +186,7 @@ constexpr int kCandCache = 12;      // candidates a resolve thread keeps in regi
 template <bool LOCAL>
 __global__ void __launch_bounds__(256) sbp_walk_kernel(FrameDev F, PointsDev P, SearchParams S, int* offs, int* cnts, uint32_t* cand,
                                                        int cap, int slotCap, int* misc) {
+  pdl_prologue();      // lets the resolve kernel (a programmatic dependent launch) become resident while this grid drains
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= P.m) return;
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__(kResolveThreads) sbp_resolve_kernel(FrameDev F
                                                                      const int* cnts, const uint32_t* cand, int* choice,
                                                                      int* gBlockF, int* gBlockT, int smemN, int32_t* assign,
                                                                      int* misc, int* hostOut, int wantChoice) {
+  pdl_prologue();      // blocks until the walk kernel's candidates are complete and visible
   extern __shared__ int sblock[];
   __shared__ int cnt, hist[HISTO], keepBin[3];
   const int tid = threadIdx.x, T = blockDim.x, m = P.m, n = F.n;
@@ -536,10 +538,9 @@ static int run_search(const orbx_frame_view* frame, int m, const uint8_t* valid,
     if (attempt && !zc) ORBX_CUDA(cudaMemsetAsync(d_misc, 0, sizeof(int) * 8, st));
     sbp_walk_kernel<LOCAL><<<(m + 7) / 8, 256, 0, st>>>(F, P, S, (int*)(db + o_offs), (int*)(db + o_cnts), d_cand, (int)std::min<size_t>(capCand, INT_MAX), slotCap, d_misc);
     if (phaseTiming) { cudaStreamSynchronize(st); fprintf(stderr, "[sbp] walk: %.1f us\n", std::chrono::duration<double, std::micro>(tnow() - t0).count()); t0 = tnow(); }
-    sbp_resolve_kernel<LOCAL><<<1, kResolveThreads, sizeof(int) * 2 * smemN, st>>>(F, P, S, (const int*)(db + o_offs), (const int*)(db + o_cnts), d_cand,
-                                                                              (int*)(db + o_choice), (int*)(db + o_bF), (int*)(db + o_bT), smemN,
-                                                                              (int32_t*)(db + o_assign), d_misc, zc ? (int*)(hdev + inBytes) : nullptr,
-                                                                              choice_out ? 1 : 0);
+    launch_chain(!phaseTiming, sbp_resolve_kernel<LOCAL>, dim3(1), dim3(kResolveThreads), sizeof(int) * 2 * smemN, st, F, P, S,
+                 (const int*)(db + o_offs), (const int*)(db + o_cnts), (const uint32_t*)d_cand, (int*)(db + o_choice), (int*)(db + o_bF),
+                 (int*)(db + o_bT), smemN, (int32_t*)(db + o_assign), d_misc, zc ? (int*)(hdev + inBytes) : (int*)nullptr, choice_out ? 1 : 0);
     if (phaseTiming) { cudaStreamSynchronize(st); fprintf(stderr, "[sbp] resolve: %.1f us\n", std::chrono::duration<double, std::micro>(tnow() - t0).count()); t0 = tnow(); }
     if (!zc) ORBX_CUDA(cudaMemcpyAsync(hout, db + o_misc, choice_out ? outBytes : outBytes - sizeof(int) * m, cudaMemcpyDeviceToHost, st));
     ORBX_CUDA(cudaStreamSynchronize(st));
