@@ -1224,7 +1224,8 @@ __global__ void __launch_bounds__(kOctMaxThreads, 1) octree_kernel(const __grid_
           S.keepPos[p] = keptBefore++;
         }
       }
-      nexp = __reduce_add_sync(0xffffffffu, nexp);     // also orders the cnt4 reads above before the zeroing below
+      nexp = __reduce_add_sync(0xffffffffu, nexp);
+      __syncwarp();                                    // every lane has read its nodes' cnt4 before the zeroing below
       const int newS = totalChildren + nKept;
       for (int i = lane; i < newS * 4; i += 32) S.cnt4[i] = 0;      // quadrant counters of the next pass
       if (lane == 0) { sh_res[0] = totalChildren; sh_res[1] = newS; sh_res[2] = nexp; }
