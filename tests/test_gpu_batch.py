@@ -160,3 +160,29 @@ def test_two_lane_resident_batch_equals_oracle(vo):
     finally:
         os.environ.pop("ORBX_CHUNK", None)
         os.environ.pop("ORBX_LANES", None)
+
+
+def test_batch_mode_equals_latency_mode_and_oracle(vo):
+    """One chunk of 12 frames (throughput mode: one stream, quadtree keys in global memory) against the same frames one call
+    at a time (latency mode: <= 8 frames per call run level 0 and the blur on a second stream and keep the quadtree's keys in
+    shared memory) and against the oracle."""
+    import os
+    B = 12
+    imgs = synth.make_sequence(B, seed=23)
+    P = oracle.Port()
+    os.environ["ORBX_CHUNK"] = "12"
+    try:
+        ex = vo.ORBextractor()
+        kk, dd, cc = ex.extract_batch(imgs)
+        launches_batch = ex.launch_count()
+        for f in range(B):
+            k1, d1 = ex(imgs[f])
+            rk, rd = P.extract(imgs[f])
+            assert cc[f] == len(rk) == len(k1)
+            assert np.array_equal(kk[f, :cc[f]], rk) and np.array_equal(dd[f, :cc[f]], rd)
+            assert np.array_equal(k1, rk) and np.array_equal(d1, rd)
+        assert launches_batch == 11                      # 7 resize + FAST + quadtree + blur + orient/desc: one chunk, one stream
+        assert ex.launch_count() == 11 + B * 13          # latency mode: level 0 has its own FAST and quadtree launches
+        ex.close()
+    finally:
+        del os.environ["ORBX_CHUNK"]

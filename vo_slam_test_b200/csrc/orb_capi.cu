@@ -27,6 +27,8 @@ void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe
 cudaError_t configure_kernels(const Geom& G);
 size_t fast_smem_bytes(const Geom& G);
 size_t octree_smem_bytes(const Geom& G);
+void launch_pyramid_fused(const PyrLevel* d_plan, const PyrLaunch& P, int* d_sync, size_t smem, bool pdl, cudaStream_t st);
+bool pyramid_pdl();
 void launch_fast(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st, int level0 = 0, int nlev = -1);
 void launch_octree(const Geom& G, const Bufs& B, int nframes, cudaStream_t st, int level0 = 0, int nlev = -1);
 void launch_blur(const Geom& G, const Bufs& B, const TmaSet& TM, int nframes, cudaStream_t st);
@@ -87,6 +89,7 @@ struct orbx_extractor {
   uint8_t* d_one = nullptr; uint8_t* h_one = nullptr; int one_cap = 0;   // single-frame path: packed [count | kps | desc], pinned mirror
   size_t d_out_frames = 0; int d_out_cap = 0;
   cudaStream_t stream = nullptr, copyStream = nullptr, backStream = nullptr;
+  PyrLevel* d_plan = nullptr; int* d_pyrSync = nullptr; size_t pyrSyncInts = 0, pyrSmem = 0; bool planDirty = true, planOk = false;   // fused pyramid
   cudaStream_t auxStream = nullptr;           // latency mode: level 0's FAST + quadtree and the blur run here beside the pyramid
   cudaEvent_t evIn = nullptr, evPyr = nullptr, evAux = nullptr;
   int32_t *d_midx = nullptr, *d_md1 = nullptr, *d_md2 = nullptr, *d_qf = nullptr; uint8_t* d_mok = nullptr;
@@ -167,6 +170,7 @@ void free_workspace(orbx_extractor* h) {
   h->d_flatKeys = nullptr; h->d_nodeOf = nullptr; h->d_candCount = nullptr; h->d_sel = nullptr; h->d_selCount = nullptr;
   for (auto& t : h->taps) cudaFree(t.block);
   h->taps.clear();
+  cudaFree(h->d_plan); cudaFree(h->d_pyrSync); h->d_plan = nullptr; h->d_pyrSync = nullptr; h->pyrSyncInts = 0; h->planDirty = true; h->planOk = false;
   h->haveGeom = false; h->chunk = 0;
   h->map0_base = nullptr; h->map0_n = 0;
   for (int l = 0; l < kMaxLevels; ++l) { h->tma.use[l] = 0; h->patchU[l] = h->patchB[l] = h->blurSrc[l] = false; }
@@ -224,6 +228,7 @@ bool encode_level_map(orbx_extractor* h, int l, const uint8_t* base, size_t pitc
   if (l + 1 < h->G.nlevels && l + 1 < (int)h->taps.size()) {       // this level is the resize source of level l + 1
     DevTaps& T = h->taps[l + 1];
     T.rt.use = T.rtFits && encode_map(h, 3 * kMaxLevels + l + 1, base, L.w, L.h, pitch, frameStride, nframes, T.rt.boxW, T.rt.boxH) ? 1 : 0;
+    h->planDirty = true;
   }
   refresh_use_patch(h);
   return h->tma.use[l] != 0;
@@ -418,6 +423,46 @@ Bufs make_bufs(orbx_extractor* h, const uint8_t* img0, size_t rowStride, size_t 
   return B;
 }
 
+// (Re)build the device plan of the fused pyramid kernel: one record per destination level.  planOk: every level can be staged
+// by TMA (descriptor encodable, tile origins in range); otherwise the per-level launches are used.
+int refresh_plan(orbx_extractor* h) {
+  const Geom& G = h->G;
+  const int nlev = G.nlevels - 1;
+  h->planDirty = false;
+  h->planOk = false;
+  if (nlev < 1 || !h->d_maps) return ORBX_OK;
+  std::vector<PyrLevel> plan(nlev);
+  size_t smem = 0;
+  for (int l = 1; l < G.nlevels; ++l) {
+    const DevTaps& T = h->taps[l];
+    if (!T.t.quadOk || !T.rt.use) return ORBX_OK;
+    const LevelGeom& D = G.L[l];
+    PyrLevel& P = plan[l - 1];
+    memset(&P, 0, sizeof(P));
+    P.map = h->d_maps + 3 * kMaxLevels + l;
+    P.dst = h->d_pyr + D.pyrOff; P.dframe = (size_t)D.h * D.pitch;
+    P.dw = D.w; P.dh = D.h; P.dpitch = D.pitch; P.sh = G.L[l - 1].h;
+    P.ntx = (D.w + kRzTileW - 1) / kRzTileW; P.nty = (D.h + 4 * T.rt.rows - 1) / (4 * T.rt.rows);
+    if (P.nty > kPyrSyncStride) return ORBX_OK;
+    if (l > 1) { P.srcTileH = 4 * h->taps[l - 1].rt.rows; P.srcNtx = plan[l - 2].ntx; } else { P.srcTileH = 1; P.srcNtx = 0; }
+    P.T = T.t; P.R = T.rt;
+    smem = std::max(smem, (size_t)T.rt.boxW * T.rt.boxH);
+  }
+  if (!h->d_plan) ORBX_CUDA(cudaMalloc(&h->d_plan, sizeof(PyrLevel) * kMaxLevels));
+  const size_t ints = 1 + (size_t)h->chunk * nlev * kPyrSyncStride;
+  if (h->pyrSyncInts < ints) {
+    cudaFree(h->d_pyrSync); h->d_pyrSync = nullptr; h->pyrSyncInts = 0;
+    ORBX_CUDA(cudaMalloc(&h->d_pyrSync, sizeof(int) * ints));
+    h->pyrSyncInts = ints;
+  }
+  // earlier launches of this handle may still read the old plan: drain them (only when the geometry or the input buffer changes)
+  ORBX_CUDA(cudaDeviceSynchronize());
+  ORBX_CUDA(cudaMemcpy(h->d_plan, plan.data(), sizeof(PyrLevel) * nlev, cudaMemcpyHostToDevice));
+  h->pyrSmem = smem;
+  h->planOk = true;
+  return ORBX_OK;
+}
+
 // The whole extractor for frames [frame0, frame0+n) of a device-resident batch (n <= h->chunk).
 int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t frameStride, int frame0, int n,
               orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t st,
@@ -454,7 +499,26 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
   }
   if (ev) cudaEventRecord(ev[0], st);
   nvtxRangePushA("orbx:pyramid");          // NVTX ranges per stage (host side of the launches): nsys timelines of the lanes
-  for (int l = 1; l < G.nlevels; ++l) {        // ComputePyramid: level l from level l-1 (ORBextractor.cpp:1129)
+  static const int fusedMode = env_int("ORBX_PYR_FUSED", 0);   // 0: per-level launches, 1: one launch, 2: one launch in latency mode only
+  bool fused = false;
+  if (fusedMode == 1 || (fusedMode == 2 && n <= kSplitFrames)) {
+    if (h->planDirty) { if (int rc = refresh_plan(h)) return rc; }
+    fused = h->planOk;
+  }
+  if (fused) {                                 // ComputePyramid (ORBextractor.cpp:1114-1135) as ONE kernel
+    PyrLaunch P{};
+    P.nlev = G.nlevels - 1; P.nframes = n; P.z0 = frame0;
+    int t = 0;
+    for (int l = 1; l < G.nlevels; ++l) {
+      P.start[l - 1] = t;
+      const int rows = h->taps[l].rt.rows;
+      t += n * ((G.L[l].w + kRzTileW - 1) / kRzTileW) * ((G.L[l].h + 4 * rows - 1) / (4 * rows));
+    }
+    P.start[P.nlev] = t;
+    ORBX_CUDA(cudaMemsetAsync(h->d_pyrSync, 0, sizeof(int) * (1 + (size_t)n * P.nlev * kPyrSyncStride), st));
+    launch_pyramid_fused(h->d_plan, P, h->d_pyrSync, h->pyrSmem, pyramid_pdl(), st);
+  }
+  for (int l = 1; l < G.nlevels && !fused; ++l) {        // ComputePyramid: level l from level l-1 (ORBextractor.cpp:1129)
     const LevelGeom& S = G.L[l - 1];
     const LevelGeom& D = G.L[l];
     const uint8_t* src = (l == 1) ? img0 : h->d_pyr + S.pyrOff;
@@ -493,7 +557,7 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
   nvtxRangePop();
   if (ev) cudaEventRecord(ev[5], st);
   }
-  h->launches += (G.nlevels - 1) + 4;
+  h->launches += (fused ? 1 : G.nlevels - 1) + 4;
   h->last_img0 = img0; h->last_rowStride = rowStride; h->last_frameStride = frameStride; h->last_frames = n;
   ORBX_CUDA(cudaGetLastError());
   return ORBX_OK;

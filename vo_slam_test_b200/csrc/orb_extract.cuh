@@ -125,4 +125,22 @@ struct ResizeTma {
   short y0[kRzMaxTY];      // first source row of tile row ty
 };
 
+// Fused pyramid (pyramid_fused_kernel): ONE launch builds levels 1..n-1 of every frame of the chunk.  A CTA takes a ticket
+// (level-major order), and a tile of level l waits on per-(frame, level, tile row) completion counters of level l-1 instead of
+// on a kernel boundary.  PyrLevel: one destination level (device array, uploaded when the geometry or the input map changes).
+struct PyrLevel {
+  const CUtensorMap* map;  // source box descriptor (a box over level l-1; level 1: over the caller's frames)
+  uint8_t* dst; size_t dframe;
+  int dw, dh, dpitch;
+  int sh;                  // rows of the source level
+  int ntx, nty;            // destination tiles of this level (128 columns x 4 * R.rows rows)
+  int srcTileH, srcNtx;    // tile height / tiles per tile row of the source level's own destination tiling (level 1: unused)
+  ResizeTaps T; ResizeTma R;
+};
+struct PyrLaunch {
+  int nlev, nframes, z0;   // destination levels, frames of this launch, z of the chunk's first frame in the level-0 map
+  int start[kMaxLevels + 1];   // first ticket of destination level index i (level i + 1); start[nlev] = all tickets
+};
+constexpr int kPyrSyncStride = kRzMaxTY;   // completion counters per (frame, level)
+
 }  // namespace orbx

@@ -190,15 +190,14 @@ __global__ void __launch_bounds__(128) resize_walk_kernel(const uint8_t* __restr
 // global-load latency that bounded resize_walk_kernel (long-scoreboard stalls 9 per issue) is paid once per CTA and
 // overlapped by the other resident CTAs.  Row taps of the 16 rows of a warp live in lanes 0..15 and are broadcast by
 // shuffles.  Same integer arithmetic as resize_walk_kernel.
-__global__ void __launch_bounds__(128) resize_tma_kernel(const CUtensorMap* __restrict__ map, int z0, int sh, uint8_t* __restrict__ dst,
-                                                         int dw, int dh, int dpitch, size_t dframe, ResizeTaps T,
-                                                         const __grid_constant__ ResizeTma R) {
-  pdl_prologue();
-  extern __shared__ __align__(128) uint8_t rz_tile[];
-  __shared__ __align__(8) uint64_t bar;
-  const int lane = threadIdx.x, wy = threadIdx.y, f = blockIdx.z;
-  const int tx0 = R.x0[blockIdx.x], ty0 = R.y0[blockIdx.y];
-  const uint32_t barA = (uint32_t)__cvta_generic_to_shared(&bar);
+// One destination tile (tx, ty) of frame f: shared by the per-level kernel and the fused pyramid kernel.  `bar` is a fresh
+// (uninitialised) mbarrier of this CTA.  No early exit: every thread returns from here (the fused kernel signals afterwards).
+__device__ __forceinline__ void resize_tma_tile(const CUtensorMap* __restrict__ map, int z, int sh, uint8_t* __restrict__ dst, int dw, int dh,
+                                                int dpitch, size_t dframe, const ResizeTaps& T, const ResizeTma& R, int tx, int ty, int f,
+                                                uint8_t* rz_tile, uint64_t* bar) {
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  const int tx0 = R.x0[tx], ty0 = R.y0[ty];
+  const uint32_t barA = (uint32_t)__cvta_generic_to_shared(bar);
   if (lane == 0 && wy == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -206,11 +205,11 @@ __global__ void __launch_bounds__(128) resize_tma_kernel(const CUtensorMap* __re
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
             (uint32_t)__cvta_generic_to_shared(rz_tile)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(tx0), "r"(ty0), "r"(z0 + f), "r"(barA)
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(tx0), "r"(ty0), "r"(z), "r"(barA)
         : "memory");
   }
-  const int q = blockIdx.x * (kRzTileW / 4) + lane;
-  const int dy0 = (blockIdx.y * 4 + wy) * R.rows;
+  const int q = tx * (kRzTileW / 4) + lane;
+  const int dy0 = (ty * 4 + wy) * R.rows;
   const int dx0 = q * 4;
   const bool live = dx0 < dw && dy0 < dh;
   int4 Q = make_int4(0, 0, 0, 0);
@@ -282,6 +281,63 @@ __global__ void __launch_bounds__(128) resize_tma_kernel(const CUtensorMap* __re
     }
     d += dpitch;
   }
+}
+
+__global__ void __launch_bounds__(128) resize_tma_kernel(const CUtensorMap* __restrict__ map, int z0, int sh, uint8_t* __restrict__ dst,
+                                                         int dw, int dh, int dpitch, size_t dframe, ResizeTaps T,
+                                                         const __grid_constant__ ResizeTma R) {
+  pdl_prologue();
+  extern __shared__ __align__(128) uint8_t rz_tile[];
+  __shared__ __align__(8) uint64_t bar;
+  resize_tma_tile(map, z0 + (int)blockIdx.z, sh, dst, dw, dh, dpitch, dframe, T, R, blockIdx.x, blockIdx.y, blockIdx.z, rz_tile, &bar);
+}
+
+// ONE launch for the whole pyramid (north_star: "one kernel builds the scale pyramid").  Tickets are handed out in level-major
+// order, so a CTA only ever waits for CTAs that hold earlier tickets and are therefore already running: no deadlock whatever the
+// number of resident CTAs.  A tile of level l needs source rows [y0, y0 + boxH) of level l-1 = a few destination tile rows of
+// that level: it spins (one thread, ld.acquire.gpu) until their completion counters reach the tiles-per-row of level l-1, orders
+// the generic-proxy acquire in front of its async-proxy (TMA) read with fence.proxy.async, and after its own stores signals
+// its tile row (stores -> __syncthreads -> __threadfence -> atomicAdd).  sync[0] = ticket counter, sync[1 + ((f * nlev + i) *
+// kPyrSyncStride) + ty] = finished tiles of tile row ty of level i + 1 of frame f; zeroed by the host before every launch.
+__global__ void __launch_bounds__(128) pyramid_fused_kernel(const PyrLevel* __restrict__ plan, const __grid_constant__ PyrLaunch P,
+                                                            int* __restrict__ sync) {
+  pdl_prologue();
+  extern __shared__ __align__(128) uint8_t rz_tile[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_ticket;
+  __shared__ PyrLevel sL;
+  const bool t0 = threadIdx.x == 0 && threadIdx.y == 0;
+  if (t0) s_ticket = atomicAdd(&sync[0], 1);
+  __syncthreads();
+  const int t = s_ticket;
+  int li = 0;
+  while (li + 1 < P.nlev && t >= P.start[li + 1]) ++li;
+  {   // this level's record -> shared memory (the taps / tile origins are indexed at run time)
+    const int* src = reinterpret_cast<const int*>(plan + li);
+    int* dstw = reinterpret_cast<int*>(&sL);
+    for (int i = threadIdx.y * 32 + threadIdx.x; i < (int)(sizeof(PyrLevel) / sizeof(int)); i += 128) dstw[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const PyrLevel& L = sL;
+  const int r = t - P.start[li], per = L.ntx * L.nty;
+  const int f = r / per, tt = r - f * per, ty = tt / L.ntx, tx = tt - ty * L.ntx;
+  int* mine = sync + 1 + ((size_t)f * P.nlev + li) * kPyrSyncStride;
+  if (li > 0 && t0) {
+    const int y0 = L.R.y0[ty], y1 = min(y0 + L.R.boxH, L.sh) - 1;
+    const int* cnt = mine - kPyrSyncStride;
+    for (int sy = y0 / L.srcTileH; sy <= y1 / L.srcTileH; ++sy) {
+      int v;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt + sy) : "memory");
+      } while (v < L.srcNtx);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  __syncthreads();
+  resize_tma_tile(L.map, (li == 0 ? P.z0 : 0) + f, L.sh, L.dst, L.dw, L.dh, L.dpitch, L.dframe, L.T, L.R, tx, ty, f, rz_tile, &bar);
+  __threadfence();                               // every thread's stores are visible GPU-wide before the tile row is signalled
+  __syncthreads();
+  if (t0 && li + 1 < P.nlev) atomicAdd(mine + ty, 1);
 }
 
 // ======================================================================================================
@@ -2204,6 +2260,12 @@ void launch_resize(const uint8_t* src, int sw, int sh, int spitch, size_t sframe
   else
     launch_chain(pdl_enabled() >= 1, resize_kernel, grid, block, 0, st, src, sw, sh, spitch, sframe, dst, dw, dh, dpitch, dframe, T);
 }
+
+void launch_pyramid_fused(const PyrLevel* d_plan, const PyrLaunch& P, int* d_sync, size_t smem, bool pdl, cudaStream_t st) {
+  const dim3 tblock(32, 4), tgrid(P.start[P.nlev]);
+  launch_chain(pdl, pyramid_fused_kernel, tgrid, tblock, smem, st, d_plan, P, d_sync);
+}
+bool pyramid_pdl() { return pdl_enabled() >= 1; }
 
 size_t fast_warp_smem_bytes(const Geom& G);
 
