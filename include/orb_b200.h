@@ -169,6 +169,14 @@ int hamm_knn2_sharded_phases_device(const uint8_t* d_q, int nq, const uint8_t* d
 
 long long hamm_launch_count(void);
 
+/* The same job with everything resident in device memory (frames in, keypoints / descriptors / matches out), asynchronous on
+ * `stream`: the frame-to-frame top-2 of a chunk is launched on the chunk's lane right behind its extraction, so the POPC-bound
+ * matching of one lane runs under the extraction kernels of the other instead of alone at the end of the batch.
+ * d_m_* are [(nframes-1) * cap].  Results are identical to orbx_extract_batch_device + hamm_knn2_pairs_device. */
+int orbx_extract_match_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes, int w, int height, size_t row_stride,
+                                    size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, int th,
+                                    float ratio, int32_t* d_m_idx, int32_t* d_m_d1, int32_t* d_m_d2, uint8_t* d_m_ok, void* stream);
+
 /* Which kernels serve the hamm_* entry points and the frame-to-frame matching of orbx_extract_match_batch:
  *   0 (default)  XOR + POPC on the integer pipe (carry-save tree, 5 POPC per pair) -- the design BASELINE's north_star states;
  *   1            descriptor bits as +-1 bytes through the legacy integer tensor pipe (mma.sync m16n8k32 s8 -> IMMA.16832),

@@ -186,3 +186,61 @@ def test_batch_mode_equals_latency_mode_and_oracle(vo):
         ex.close()
     finally:
         del os.environ["ORBX_CHUNK"]
+
+
+def test_resident_extract_match_equals_two_step_path_and_oracle(vo):
+    """orbx_extract_match_batch_device (matching of every chunk launched on its lane right behind the extraction; the pairs that
+    straddle a lane boundary after the join) against orbx_extract_batch_device + hamm_knn2_pairs_device, and against the oracle
+    on a few pairs: several chunks per lane, a ragged last chunk, two and one lanes."""
+    import os
+    torch = pytest.importorskip("torch")
+    from vo_slam_test_b200 import api
+    B, H, W = 23, 240, 320
+    imgs = np.stack([synth.make_frame(300 + f // 2, H, W) if f % 5 else synth.make_frame(300 + f, H, W) for f in range(B)])
+    d_imgs = torch.from_numpy(imgs).cuda()
+    P = oracle.Port(300)
+    try:
+        os.environ["ORBX_CHUNK"] = "4"
+        for lanes in ("2", "1"):
+            os.environ["ORBX_LANES"] = lanes
+            ex = vo.ORBextractor(300, 1.2, 8, 20, 7)
+            cap = ex.max_keypoints
+            outs = []
+            for fused in (True, False):
+                d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda")
+                d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+                d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+                m = [torch.full((B - 1, cap), -9, dtype=torch.int32, device="cuda") for _ in range(3)]
+                ok = torch.full((B - 1, cap), 7, dtype=torch.uint8, device="cuda")
+                st = torch.cuda.current_stream().cuda_stream
+                if fused:
+                    ex.extract_match_batch_device(d_imgs.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                                  d_cnt.data_ptr(), 50, 0.7, m[0].data_ptr(), m[1].data_ptr(), m[2].data_ptr(),
+                                                  ok.data_ptr(), st)
+                else:
+                    ex.extract_batch_device(d_imgs.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                            d_cnt.data_ptr(), st)
+                    qf = torch.arange(0, B - 1, dtype=torch.int32, device="cuda"); tf = qf + 1
+                    api.knn2_pairs_device(d_desc.data_ptr(), d_cnt.data_ptr(), cap, qf.data_ptr(), tf.data_ptr(), B - 1, 50, 0.7,
+                                          m[0].data_ptr(), m[1].data_ptr(), m[2].data_ptr(), ok.data_ptr(), st)
+                torch.cuda.synchronize()
+                cnt = d_cnt.cpu().numpy()
+                outs.append((cnt, d_desc.cpu().numpy(), [x.cpu().numpy() for x in m], ok.cpu().numpy()))
+            (c0, de0, m0, ok0), (c1, de1, m1, ok1) = outs
+            assert np.array_equal(c0, c1) and np.array_equal(de0, de1)
+            for p in range(B - 1):
+                n = c0[p]
+                for a, b in zip(m0, m1):
+                    assert np.array_equal(a[p, :n], b[p, :n]), (lanes, p)
+                assert np.array_equal(ok0[p, :n], ok1[p, :n]), (lanes, p)
+            for p in (0, 3, 11, 12, 21):       # chunk boundaries (3|4, 11|12 = the lane boundary with two lanes) and interior pairs
+                want = oracle.Port().knn2(de0[p, :c0[p]], de0[p + 1, :c0[p + 1]], 50, 0.7)
+                n = c0[p]
+                assert np.array_equal(m0[0][p, :n], want[0]) and np.array_equal(m0[1][p, :n], want[1])
+                assert np.array_equal(m0[2][p, :n], want[2]) and np.array_equal(ok0[p, :n], want[3])
+            rk, rd = P.extract(imgs[12])
+            assert c0[12] == len(rk) and np.array_equal(de0[12, :c0[12]], rd)
+            ex.close()
+    finally:
+        os.environ.pop("ORBX_CHUNK", None)
+        os.environ.pop("ORBX_LANES", None)

@@ -98,6 +98,7 @@ def load_library():
     L.orbx_extract_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp, vp]
     L.orbx_launch_count.argtypes = [vp, vp]
     L.orbx_extract_match_batch.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp, i32, f32, vp, vp, vp, vp]
+    L.orbx_extract_match_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp, i32, f32, vp, vp, vp, vp, vp]
     L.orbx_profile_stages.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp, vp, vp]
     L.orbx_debug_level.argtypes = [vp, i32, i32, i32, vp, vp, vp]
     L.orbx_debug_candidates.argtypes = [vp, i32, i32, vp, i32, vp]
@@ -251,6 +252,14 @@ class ORBextractor:
         _check(self._lib.orbx_extract_batch_device(self._h, C.c_void_p(d_imgs), nframes, W, H, row_stride, frame_stride,
                                                    C.c_void_p(d_kps), C.c_void_p(d_desc), cap, C.c_void_p(d_counts),
                                                    C.c_void_p(stream)))
+
+    def extract_match_batch_device(self, d_imgs, nframes, W, H, row_stride, frame_stride, d_kps, d_desc, cap, d_counts, th, ratio,
+                                   d_midx, d_md1, d_md2, d_mok, stream=0):
+        """Raw device pointers (ints); asynchronous on `stream`: extraction + frame-to-frame top-2, matching pipelined per chunk."""
+        _check(self._lib.orbx_extract_match_batch_device(self._h, C.c_void_p(d_imgs), nframes, W, H, row_stride, frame_stride,
+                                                         C.c_void_p(d_kps), C.c_void_p(d_desc), cap, C.c_void_p(d_counts), th, ratio,
+                                                         C.c_void_p(d_midx), C.c_void_p(d_md1), C.c_void_p(d_md2), C.c_void_p(d_mok),
+                                                         C.c_void_p(stream)))
 
     def extract_match_batch(self, imgs_ptr, nframes, W, H, kps_ptr, desc_ptr, cap, counts_ptr, th, ratio, midx_ptr,
                             md1_ptr, md2_ptr, mok_ptr, row_stride=None, frame_stride=None):

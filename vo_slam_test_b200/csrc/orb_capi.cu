@@ -89,6 +89,7 @@ struct orbx_extractor {
   uint8_t* d_one = nullptr; uint8_t* h_one = nullptr; int one_cap = 0;   // single-frame path: packed [count | kps | desc], pinned mirror
   size_t d_out_frames = 0; int d_out_cap = 0;
   cudaStream_t stream = nullptr, copyStream = nullptr, backStream = nullptr;
+  int32_t* d_qf2 = nullptr; size_t qf_frames = 0;     // pair index 0, 1, 2, ... of the resident extract + match entry point
   PyrLevel* d_plan = nullptr; int* d_pyrSync = nullptr; size_t pyrSyncInts = 0, pyrSmem = 0; bool planDirty = true, planOk = false;   // fused pyramid
   cudaStream_t auxStream = nullptr;           // latency mode: level 0's FAST + quadtree and the blur run here beside the pyramid
   cudaEvent_t evIn = nullptr, evPyr = nullptr, evAux = nullptr;
@@ -724,6 +725,7 @@ int orbx_destroy(orbx_handle h) {
   cudaFree(h->d_counts);
   cudaFree(h->d_one); if (h->h_one) cudaFreeHost(h->h_one);
   cudaFree(h->d_midx); cudaFree(h->d_md1); cudaFree(h->d_md2); cudaFree(h->d_mok); cudaFree(h->d_qf);
+  cudaFree(h->d_qf2);
   if (h->auxStream) cudaStreamDestroy(h->auxStream);
   if (h->evIn) cudaEventDestroy(h->evIn);
   if (h->evPyr) cudaEventDestroy(h->evPyr);
@@ -766,9 +768,46 @@ int orbx_launch_count(orbx_handle h, long long* n) {
   return ORBX_OK;
 }
 
+struct MatchOut { int th; float ratio; int32_t* idx; int32_t* d1; int32_t* d2; uint8_t* ok; };
+static int ensure_pair_index(orbx_extractor* h, int nframes) {       // d_qf = 0, 1, 2, ... (frame index of pair p / of its train frame p + 1)
+  if (h->qf_frames >= (size_t)nframes + 1) return ORBX_OK;
+  cudaFree(h->d_qf2); h->d_qf2 = nullptr; h->qf_frames = 0;
+  ORBX_CUDA(cudaMalloc(&h->d_qf2, sizeof(int32_t) * ((size_t)nframes + 1)));
+  std::vector<int32_t> iota((size_t)nframes + 1);
+  for (int i = 0; i <= nframes; ++i) iota[i] = i;
+  ORBX_CUDA(cudaMemcpy(h->d_qf2, iota.data(), sizeof(int32_t) * ((size_t)nframes + 1), cudaMemcpyHostToDevice));
+  h->qf_frames = (size_t)nframes + 1;
+  return ORBX_OK;
+}
+// pairs [p0, p1) (pair p: queries = frame p, train = frame p + 1) on `st`
+static int launch_pairs(orbx_extractor* h, const uint8_t* d_desc, const int32_t* d_counts, int cap, int p0, int p1, const MatchOut& M,
+                        cudaStream_t st) {
+  if (p1 <= p0) return ORBX_OK;      // (counted by hamm_launch_count)
+  return hamm_knn2_pairs_device(d_desc, d_counts, cap, h->d_qf2 + p0, h->d_qf2 + p0 + 1, p1 - p0, M.th, M.ratio, M.idx + (size_t)p0 * cap,
+                                M.d1 + (size_t)p0 * cap, M.d2 + (size_t)p0 * cap, M.ok + (size_t)p0 * cap, st);
+}
+static int extract_batch_device_impl(orbx_handle h, const uint8_t* d_imgs, int nframes, int w, int height, size_t row_stride,
+                                     size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts,
+                                     void* stream, const MatchOut* M);
+
 int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes, int w, int height, size_t row_stride,
                               size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts,
                               void* stream) {
+  return extract_batch_device_impl(h, d_imgs, nframes, w, height, row_stride, frame_stride, d_kps, d_desc, cap, d_counts, stream, nullptr);
+}
+
+int orbx_extract_match_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes, int w, int height, size_t row_stride,
+                                    size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts, int th,
+                                    float ratio, int32_t* d_m_idx, int32_t* d_m_d1, int32_t* d_m_d2, uint8_t* d_m_ok, void* stream) {
+  if (check_handle(h)) return ORBX_ERR_ARG;
+  if (nframes > 1 && (!d_m_idx || !d_m_d1 || !d_m_d2 || !d_m_ok)) { set_error("bad argument"); return ORBX_ERR_ARG; }
+  const MatchOut M{th, ratio, d_m_idx, d_m_d1, d_m_d2, d_m_ok};
+  return extract_batch_device_impl(h, d_imgs, nframes, w, height, row_stride, frame_stride, d_kps, d_desc, cap, d_counts, stream, &M);
+}
+
+static int extract_batch_device_impl(orbx_handle h, const uint8_t* d_imgs, int nframes, int w, int height, size_t row_stride,
+                                     size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts,
+                                     void* stream, const MatchOut* M) {
   if (check_handle(h)) return ORBX_ERR_ARG;
   if (!d_imgs || !d_kps || !d_desc || !d_counts || nframes < 0 || w <= 0 || height <= 0 || cap <= 0 ||
       row_stride < (size_t)w || frame_stride < row_stride * (size_t)(height - 1) + w) {
@@ -777,6 +816,7 @@ int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes,
   }
   if (nframes == 0) return ORBX_OK;
   ORBX_CUDA(cudaSetDevice(h->p.device));
+  if (M) { if (int rcq = ensure_pair_index(h, nframes)) return rcq; }
   const int want_lanes = env_int("ORBX_LANES", 2);
   // Equal chunks, an even number of them when two lanes run: a batch that is a little larger than a multiple of the chunk
   // size (a rank's block + its replicated boundary frame in the strong-scaling split: 513, 1025, 2049 frames) must not leave
@@ -823,15 +863,28 @@ int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes,
       for (int k = 0; k < nl; ++k) {
         const int f0 = c * chunk;
         if (f0 >= count[k]) continue;
-        rc = run_chunk(lane[k], d_imgs + (size_t)first[k] * frame_stride, row_stride, frame_stride, f0, std::min(chunk, count[k] - f0),
+        const int nn = std::min(chunk, count[k] - f0);
+        rc = run_chunk(lane[k], d_imgs + (size_t)first[k] * frame_stride, row_stride, frame_stride, f0, nn,
                        d_kps + (size_t)first[k] * cap, d_desc + (size_t)first[k] * cap * 32, cap, d_counts + first[k], k ? lane[k]->stream : st);
         if (rc) return rc;
+        // the pairs whose train frame is in this chunk and whose query frame is in this lane: [first + f0 - 1, first + f0 + nn - 1),
+        // without the pair that straddles the lane boundary (its query frame belongs to the previous lane: after the join)
+        if (M) {
+          const int g0 = first[k] + f0;
+          rc = launch_pairs(h, d_desc, d_counts, cap, std::max(g0 - 1, first[k]), g0 + nn - 1, *M, k ? lane[k]->stream : st);
+          if (rc) return rc;
+        }
       }
     for (int k = 1; k < nl; ++k) {
       cudaEvent_t ev = k == 1 ? h->laneJoin : h->laneJoinX[k - 2];
       ORBX_CUDA(cudaEventRecord(ev, lane[k]->stream));
       ORBX_CUDA(cudaStreamWaitEvent(st, ev, 0));
     }
+    if (M)
+      for (int k = 1; k < nl; ++k) {                // the nl - 1 pairs across the lane boundaries
+        rc = launch_pairs(h, d_desc, d_counts, cap, first[k] - 1, first[k], *M, st);
+        if (rc) return rc;
+      }
     return ORBX_OK;
   }
   h->map0_want = nframes;
@@ -839,6 +892,7 @@ int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_imgs, int nframes,
     const int n = std::min(chunk, nframes - f0);
     rc = run_chunk(h, d_imgs, row_stride, frame_stride, f0, n, d_kps, d_desc, cap, d_counts, st);
     if (rc) return rc;
+    if (M) { rc = launch_pairs(h, d_desc, d_counts, cap, std::max(f0 - 1, 0), f0 + n - 1, *M, st); if (rc) return rc; }
   }
   return ORBX_OK;
 }
@@ -1070,7 +1124,6 @@ int orbx_extract_match_batch(orbx_handle h, const uint8_t* imgs, int nframes, in
       rc = hamm_knn2_pairs_device(h->d_desc, h->d_counts, cap, h->d_qf + p0, h->d_qf + p0 + 1, p1 - p0, th, ratio,
                                   h->d_midx + (size_t)p0 * cap, h->d_md1 + (size_t)p0 * cap, h->d_md2 + (size_t)p0 * cap,
                                   h->d_mok + (size_t)p0 * cap, sk);
-      h->launches += 1;
     }
     cudaEventRecord(done[c], sk);
     cudaStreamWaitEvent(sb, done[c], 0);
