@@ -116,8 +116,9 @@ namespace {
 void free_frame_block(orbx_frame* f);
 
 // Frames per chunk.  Device-resident batches: 512 (fewer, larger launches: +3 % over 256, no gain beyond).  Host-pipelined
-// batches: 256, because the upload of chunk c+1 overlaps the kernels of chunk c and the pipeline fill/drain grows with the
-// chunk (measured end to end: 157 k frames/s at 256, 148 k at 512).  ORBX_CHUNK overrides both, ORBX_CHUNK_HOST the latter.
+// batches: 128 on two compute lanes, because the upload of chunk c+1 overlaps the kernels of chunk c and the pipeline fill/drain
+// grows with the chunk (measured end to end, ms per 4096-frame step: 24.5 at 128, 25.0 at 256, 26.6 at 512; one lane alone cannot
+// keep up with the link below 256).  ORBX_CHUNK overrides both, ORBX_CHUNK_HOST the latter.
 constexpr int kDefaultChunk = 512, kDefaultHostChunk = 128;   // host pipeline: 128-frame chunks on two lanes (tools/e2e_probe.py)
 
 int env_int(const char* name, int dflt) {
