@@ -1000,6 +1000,28 @@ def bench_other_configs(torch, vo, synth, hbm_peak):
         dt = (time.perf_counter() - t0) / 20
         res[name] = {"ms_per_search": dt * 1e3, "points_per_s": 10000 / dt, "matches": int(r[1]) if isinstance(r, tuple) else None}
     res["api"] = "host C ABI (orbx_search_by_projection_frame / _local): host arrays in, assignment out, synchronous"
+    # the same searches against the frame kept resident by orbx_frame_create (zero distortion: unKeypoints_ == keypoints_)
+    try:
+        exh = vo.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+        cam0 = vo.camera(517.3, 516.5, 318.6, 255.3, [0.0, 0.0, 0.0, 0.0, 0.0], 40.0, (0.0, 640.0, 0.0, 480.0))
+        fr = vo.Frame(exh, cam0, synth.make_frame(42))
+        for name, ratio, kw, fn in (("frame_h", 0.9, {}, "f"), ("local_map_h", 0.8, {"local": True}, "l")):
+            frame, pts = synth.make_projection_case(kps, desc, sf, 10000, seed=1, **kw)
+            M = vo.Matcher(ratio)
+            call = ((lambda: M.searchByProjectionH(fr, frame["occupied0"], pts, 15.0)) if fn == "f"
+                    else (lambda: M.searchByProjectionLocalH(fr, frame["occupied0"], pts, 3.0)))
+            for _ in range(3):
+                r = call()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                r = call()
+            dt = (time.perf_counter() - t0) / 20
+            res[name] = {"ms_per_search": dt * 1e3, "points_per_s": 10000 / dt, "matches": int(r[1]),
+                         "same_matches_as_host_arrays": int(r[1]) == res[name[:-2]]["matches"]}
+        fr.close(); exh.close()
+        res["api_h"] = "orbx_search_by_projection_frame_h / _local_h on the resident frame (orbx_frame_t)"
+    except Exception as exc:                          # noqa: BLE001
+        res["handle_error"] = str(exc)[:200]
     out["config4_sbp"] = res
     try:
         out["tracking_frame"] = bench_tracking_frame(vo, synth)
