@@ -540,6 +540,23 @@ def run_b200(args, rank, world, local_rank):
                         % (ab[dom], frames_per_launch, ab["frame_total"] / 1e6, ab["frame_total"] * per_gpu_fps / 1e9,
                            ab["frame_total"] * per_gpu_fps / 1e9 / hbm_peak)}
 
+    # The binding resource of the image stages is the instruction issue rate, not HBM (ncu: DRAM 6-38 % of peak, issue slots 76-90 %
+    # busy).  For the dominant stage the executed warp instructions per frame come from the committed ncu capture
+    # (profiles/r2_fast_lines.md: 827,639,446 per 512 frames); achieved = that count over the live stage time, peak = 4 schedulers per
+    # SM x SMs x the SM clock sampled during the run.
+    if dom == "fast":
+        try:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+            wi_frame = 827639446 / 512.0
+            ach = wi_frame * F / (stages["fast"]["ms_per_step"] * 1e-3)     # F = frames of this rank (the stage times are this rank's)
+            peak_issue = 4.0 * sms * mhz * 1e6
+            roofline["issue_slots"] = {"bound": "warp-instruction issue", "warp_instructions_per_frame": wi_frame, "achieved": ach,
+                                       "peak": peak_issue, "unit": "warp-instr/s", "frac": ach / peak_issue,
+                                       "source": "profiles/r2_fast_lines.md (ncu smsp__inst_executed.sum) / live stage time"}
+        except Exception:       # noqa: BLE001
+            pass
+
     # ---- what bounds e2e: the pinned host->device copy rate of the same input, ALL ranks copying at the same time -------------
     link = None
     try:
