@@ -486,7 +486,8 @@ static int pick_splits(int nq, long long nt, long long* per_out) {
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // aim at ~8 resident CTAs per SM, each split at least 4 tiles and below 2^23 rows
-  long long want = ((long long)sms * 8 + qtiles - 1) / qtiles;
+  static const int perSm = [] { const char* e = getenv("ORBX_HAMM_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();   // A/B knob
+  long long want = ((long long)sms * perSm + qtiles - 1) / qtiles;
   long long maxSplits = (nt + 4LL * kTT - 1) / (4LL * kTT);
   long long ns = std::max(1LL, std::min(want, maxSplits));
   long long per = (nt + ns - 1) / ns;
