@@ -183,6 +183,10 @@ int orbx_extract_match_batch_device(orbx_handle h, const uint8_t* d_imgs, int nf
  *                dot = 256 - 2 * hamming, exact integers: an A/B variant with bit-identical results (tests/test_gpu_hamming_mma.py).
  * Returns the previous value; any other argument only queries.  Initial value: environment ORBX_HAMM_MMA. */
 int hamm_set_variant(int variant);
+/* Map-scale scans hand the train rows out in blocks from a counter per query tile (all CTAs finish together whatever the warp
+ * schedulers favour) instead of giving every CTA a fixed range: 0 = never, 1 = automatic (default: long scans only), 2 = whenever
+ * the scan is split at all (tests).  Same results.  Returns the previous mode. */
+int hamm_set_dynamic(int mode);
 
 /* ---------------------------------------------------------------------------------------------------
  * Grid index + projection searches

@@ -100,3 +100,32 @@ def test_fused_peer_exchange_two_virtual_ranks(vo):
     finally:
         for b in bufs:
             api.exchange_free(b)
+
+
+def test_dynamic_block_scan_equals_static_and_oracle(vo):
+    """Map-scale scans hand the rows out in blocks from one counter per query tile (knn2_dyn_kernel): a CTA's blocks are not
+    contiguous, so the merge breaks distance ties by row index.  Forced on a problem the oracle finishes in seconds, with exact
+    duplicates of the queries planted far apart (ties at distance 0 across blocks and CTAs: the lowest row must win and the
+    second-best must count the duplicate), all-equal rows, and a ragged last block."""
+    from vo_slam_test_b200 import api
+    rng = np.random.default_rng(77)
+    nq, nt = 300, 200003
+    t = synth.make_descriptors(nt, seed=5)
+    src = rng.integers(0, nt, nq)
+    q = synth.flip_bits(t[src], rng.integers(0, 40, nq), rng)
+    for k in range(0, nq, 3):                       # every third query: exact copies at three far-apart rows
+        rows = rng.choice(nt, 3, replace=False)
+        t[rows] = q[k]
+    t[150000:150600] = t[150000]                    # a run of identical rows spanning a block boundary
+    want = oracle.Port().knn2(q, t, 50, 0.7, nthreads=8)
+    prev = api.set_hamming_dynamic(2)
+    try:
+        got_dyn = vo.Matcher(0.7).knn2(q, t, th=50)
+        api.set_hamming_dynamic(0)
+        got_sta = vo.Matcher(0.7).knn2(q, t, th=50)
+    finally:
+        api.set_hamming_dynamic(prev)
+    for a, b, c, name in zip(got_dyn, got_sta, want, ["idx", "d1", "d2", "ok"]):
+        assert np.array_equal(a, c), "dynamic " + name
+        assert np.array_equal(b, c), "static " + name
+    assert (want[1][::3] == 0).all() and (want[2][::3] == 0).all()      # the planted ties are really there

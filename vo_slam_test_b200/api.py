@@ -111,6 +111,7 @@ def load_library():
     L.hamm_knn2_merge_device.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]
     L.hamm_launch_count.restype = ll
     L.hamm_set_variant.argtypes = [i32]
+    L.hamm_set_dynamic.argtypes = [i32]
     L.hamm_exchange_bytes.restype = sz
     L.hamm_exchange_bytes.argtypes = [i32, i32]
     L.hamm_exchange_alloc.argtypes = [i32, i32, i32, vp, vp]
@@ -348,6 +349,12 @@ def knn2_sharded_device(d_q, nq, d_t, nt, shard_lo, th, ratio, rank, world, bufs
                                                           arr, max_queries, epoch, C.c_void_p(d_idx), C.c_void_p(d_d1),
                                                           C.c_void_p(d_d2), C.c_void_p(d_ok), C.c_void_p(d_status), C.c_void_p(d_ws),
                                                           ws_bytes, C.c_void_p(stream), phases))
+
+
+def set_hamming_dynamic(mode):
+    """Map-scale scans: 0 = fixed row range per CTA, 1 = automatic (default), 2 = dynamic block hand-out whenever the scan is split
+    (same results); returns the previous mode."""
+    return int(load_library().hamm_set_dynamic(int(mode)))
 
 
 def set_hamming_variant(variant):

@@ -26,6 +26,9 @@ namespace orbx {
 #ifndef ORBX_HAMM_STAGES
 #define ORBX_HAMM_STAGES 3
 #endif
+#ifndef ORBX_HAMM_TRACE
+#define ORBX_HAMM_TRACE 0
+#endif
 constexpr int kQT = ORBX_HAMM_QT;          // queries per CTA (threads)
 constexpr int kTT = ORBX_HAMM_TT;          // train descriptors per shared-memory tile (8 KB at 256)
 constexpr int kStages = ORBX_HAMM_STAGES;  // tiles in flight (TMA bulk copies, mbarrier-tracked)
@@ -81,7 +84,7 @@ struct TileRing {
 // Scan train rows [0, nt) (nt < 2^23) for the CTA's queries.  Tiles of kTT rows are fetched by the TMA engine
 // (one elected thread issues cp.async.bulk, completion is tracked by an mbarrier per stage), kStages deep.
 __device__ __forceinline__ void scan_train(const uint32_t (&q)[8], const uint8_t* __restrict__ train, int nt, const TileRing& R,
-                                           uint32_t& k1, uint32_t& k2) {
+                                           uint32_t& k1, uint32_t& k2, int idx0 = 0) {
   const int tid = threadIdx.x;
   const int ntiles = (nt + kTT - 1) / kTT;
   if (tid == 0) {
@@ -102,7 +105,7 @@ __device__ __forceinline__ void scan_train(const uint32_t (&q)[8], const uint8_t
     mbar_wait(&R.full[s], (uint32_t)((t / kStages) & 1));
     const uint4* tile = R.tile + (size_t)s * kTT * 2;
     const int cnt = min(kTT, nt - t * kTT);
-    const int base = t * kTT;
+    const int base = idx0 + t * kTT;
 #pragma unroll 4
     for (int j = 0; j < cnt; ++j) {
       const uint4 a = tile[2 * j], b = tile[2 * j + 1];
@@ -144,10 +147,22 @@ __global__ void __launch_bounds__(kQT) knn2_kernel(const uint8_t* __restrict__ q
   const int s = blockIdx.y;
   const long long t0 = (long long)s * per;
   const int cnt = (int)min(per, nt - t0);
+#if ORBX_HAMM_TRACE
+  unsigned long long tr0 = 0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr0));
+#endif
   uint32_t q[8];
   load_query(q, qs, i, nq);
   uint32_t k1 = kKeyInit, k2 = kKeyInit;
   scan_train(q, train + (size_t)t0 * 32, cnt, ring, k1, k2);
+#if ORBX_HAMM_TRACE
+  if (threadIdx.x == 0 && gridDim.y > 64) {      // debugging aid: one line per CTA of a large map scan (SM, start, end in ns)
+    unsigned long long tr1; unsigned sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr1));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    printf("HT %d %d %u %llu %llu\n", (int)blockIdx.x, (int)blockIdx.y, sm, tr0, tr1);
+  }
+#endif
   if (i >= nq) return;
   const int bd1 = (int)(k1 >> 23), bd2 = (int)(k2 >> 23);
   const int bi = bd1 < 256 ? (int)(t0 + (long long)(k1 & 0x7FFFFFu)) : -1;
@@ -160,8 +175,44 @@ __global__ void __launch_bounds__(kQT) knn2_kernel(const uint8_t* __restrict__ q
   }
 }
 
-// Merge per-split / per-shard partial results (ascending train ranges): best = smallest d1, lowest range
-// wins ties (== lowest index); second = 2nd smallest of the multiset {d1_s, d2_s}.
+// Map-scale scans: the same work for every CTA does NOT mean the same finishing time.  The warp schedulers favour some warps
+// (cycle stamps of the static-split kernel on 1k x 2M rows: all 1176 CTAs start within 0.4 us, the first one is done after
+// 0.79 ms, the median after 1.80 ms, the last after 2.89 ms), so SMs run out of resident warps long before the kernel ends: 21
+// resident warps per SM on average against 32 for the frame-pair kernel, whose grid keeps refilling the SMs.  Here the rows
+// are handed out in blocks of kDynTiles tiles (2 measured best: 799.5 Gmatch/s against 793.5 at 4) from one counter per query tile: a CTA that gets ahead simply scans more
+// blocks, and all CTAs finish within one block of each other.  A CTA's blocks are not contiguous, so its keys carry the row
+// index relative to the whole set (nt < 2^23) and the merge breaks distance ties by index.
+#ifndef ORBX_HAMM_DYN_TILES
+#define ORBX_HAMM_DYN_TILES 2
+#endif
+constexpr int kDynTiles = ORBX_HAMM_DYN_TILES;
+__global__ void __launch_bounds__(kQT) knn2_dyn_kernel(const uint8_t* __restrict__ qs, int nq, const uint8_t* __restrict__ train, int nt,
+                                                       int nblocks, int* __restrict__ counters, int32_t* __restrict__ part) {
+  __shared__ __align__(128) uint4 tile[kStages * kTT * 2];
+  __shared__ __align__(8) uint64_t full[kStages];
+  __shared__ int s_blk;
+  const TileRing ring{tile, full};
+  const int i = blockIdx.x * kQT + threadIdx.x;
+  uint32_t q[8];
+  load_query(q, qs, i, nq);
+  uint32_t k1 = kKeyInit, k2 = kKeyInit;
+  constexpr int kRows = kDynTiles * kTT;
+  for (;;) {
+    if (threadIdx.x == 0) s_blk = atomicAdd(&counters[blockIdx.x], 1);
+    __syncthreads();
+    const int blk = s_blk;
+    if (blk >= nblocks) break;
+    const int r0 = blk * kRows;
+    scan_train(q, train + (size_t)r0 * 32, min(kRows, nt - r0), ring, k1, k2, r0);   // ends with a CTA barrier: s_blk is free again
+  }
+  if (i >= nq) return;
+  const int bd1 = (int)(k1 >> 23), bd2 = (int)(k2 >> 23);
+  int32_t* p = part + ((size_t)blockIdx.y * nq + i) * 3;
+  p[0] = bd1 < 256 ? (int)(k1 & 0x7FFFFFu) : -1; p[1] = bd1; p[2] = bd2;
+}
+
+// Merge per-split / per-shard partial results: best = smallest d1, the lowest row index wins ties (parts usually come in
+// ascending ranges, but the dynamic scan's do not); second = 2nd smallest of the multiset {d1_s, d2_s}.
 __global__ void knn2_merge_kernel(const int32_t* __restrict__ pidx, const int32_t* __restrict__ pd1,
                                   const int32_t* __restrict__ pd2, int stride, int nparts, int nq, int th, float ratio,
                                   int32_t* idx, int32_t* d1, int32_t* d2, uint8_t* ok) {
@@ -171,7 +222,7 @@ __global__ void knn2_merge_kernel(const int32_t* __restrict__ pidx, const int32_
   for (int s = 0; s < nparts; ++s) {
     const size_t o = ((size_t)s * nq + i) * stride;
     const int a1 = pd1[o], a2 = pd2[o], ai = pidx[o];
-    if (a1 < b1) { b2 = min(b1, a2); b1 = a1; bi = ai; }
+    if (a1 < b1 || (a1 == b1 && a1 < 256 && ai < bi)) { b2 = min(b1, a2); b1 = a1; bi = ai; }
     else { b2 = min(b2, a1); }
   }
   idx[i] = bi; d1[i] = b1; d2[i] = b2;
@@ -548,10 +599,30 @@ int hamm_set_variant(int variant) {
   return prev;
 }
 
+// dynamic block hand-out (knn2_dyn_kernel) when the scan is long enough to matter: >= 8 blocks per worker CTA, rows < 2^23
+static std::atomic<int> g_dynamic{-1};      // 0 = static splits only, 1 = automatic (default), 2 = whenever there is more than one split
+static bool use_dynamic(int nq, long long nt, int ns) {
+  int mode = g_dynamic.load(std::memory_order_relaxed);
+  if (mode < 0) {
+    mode = getenv("ORBX_HAMM_DYNAMIC") ? atoi(getenv("ORBX_HAMM_DYNAMIC")) : 1;
+    g_dynamic.store(mode, std::memory_order_relaxed);
+  }
+  if (mode <= 0 || use_mma() || ns <= 1 || nt >= (1LL << 23)) return false;
+  const long long nblocks = (nt + (long long)kDynTiles * kTT - 1) / ((long long)kDynTiles * kTT);
+  return mode >= 2 ? nblocks >= 1 : nblocks >= 8LL * ns;
+}
+int hamm_set_dynamic(int mode) {
+  const int prev = g_dynamic.load(std::memory_order_relaxed);
+  if (mode >= 0 && mode <= 2) g_dynamic.store(mode, std::memory_order_relaxed);
+  return prev < 0 ? 1 : prev;
+}
+
+constexpr size_t kDynCounterBytes = 256;          // one counter per query tile (<= 64 tiles = 8192 queries in dynamic mode)
+
 size_t hamm_knn2_workspace_bytes(int nq, long long nt) {
   long long per;
   const int ns = pick_splits(nq, nt, &per);
-  return ns > 1 ? (size_t)ns * nq * 3 * sizeof(int32_t) : 0;
+  return ns > 1 ? (size_t)ns * nq * 3 * sizeof(int32_t) + kDynCounterBytes : 0;
 }
 
 int hamm_knn2_device(const uint8_t* d_q, int nq, const uint8_t* d_t, long long nt, int th, float ratio, int32_t* d_idx,
@@ -562,11 +633,17 @@ int hamm_knn2_device(const uint8_t* d_q, int nq, const uint8_t* d_t, long long n
   cudaStream_t st = (cudaStream_t)stream;
   long long per;
   const int ns = pick_splits(nq, nt, &per);
-  if (ns > 1 && (!d_workspace || workspace_bytes < (size_t)ns * nq * 3 * sizeof(int32_t))) {
+  if (ns > 1 && (!d_workspace || workspace_bytes < (size_t)ns * nq * 3 * sizeof(int32_t) + kDynCounterBytes)) {
     set_error("workspace too small (see hamm_knn2_workspace_bytes)");
     return ORBX_ERR_CAPACITY;
   }
-  if (int rc = launch_knn2(d_q, nq, d_t, nt, per, ns, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace, st)) return rc;
+  const int qtiles = (nq + kQT - 1) / kQT;
+  if (use_dynamic(nq, nt, ns) && (size_t)qtiles * sizeof(int) <= kDynCounterBytes) {
+    int* counters = (int*)((uint8_t*)d_workspace + (size_t)ns * nq * 3 * sizeof(int32_t));
+    ORBX_CUDA(cudaMemsetAsync(counters, 0, kDynCounterBytes, st));
+    const int nblocks = (int)((nt + (long long)kDynTiles * kTT - 1) / ((long long)kDynTiles * kTT));
+    knn2_dyn_kernel<<<dim3(qtiles, ns), kQT, 0, st>>>(d_q, nq, d_t, (int)nt, nblocks, counters, (int32_t*)d_workspace);
+  } else if (int rc = launch_knn2(d_q, nq, d_t, nt, per, ns, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace, st)) return rc;
   g_hamm_launches++;
   if (ns > 1) {
     const int32_t* part = (const int32_t*)d_workspace;
