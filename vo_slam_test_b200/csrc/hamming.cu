@@ -476,7 +476,7 @@ __global__ void knn2_merge_scatter_kernel(const int32_t* __restrict__ pidx, cons
     for (int s = 0; s < nparts; ++s) {
       const size_t o = ((size_t)s * nq + i) * stride;
       const int a1 = pd1[o], a2 = pd2[o], ai = pidx[o];
-      if (a1 < b1) { b2 = min(b1, a2); b1 = a1; bi = ai; }
+      if (a1 < b1 || (a1 == b1 && a1 < 256 && ai < bi)) { b2 = min(b1, a2); b1 = a1; bi = ai; }   // ties: lowest row (dynamic scan parts are unordered)
       else { b2 = min(b2, a1); }
     }
     const int gi = bi >= 0 ? (int)(shard_lo + bi) : -1;       // local -> global row index
@@ -625,6 +625,21 @@ size_t hamm_knn2_workspace_bytes(int nq, long long nt) {
   return ns > 1 ? (size_t)ns * nq * 3 * sizeof(int32_t) + kDynCounterBytes : 0;
 }
 
+// The local scan of both entry points: per-split partials into the workspace (ns > 1; dynamic block hand-out for long scans) or
+// the final result into the output arrays (ns == 1).
+static int scan_local(const uint8_t* d_q, int nq, const uint8_t* d_t, long long nt, long long per, int ns, int th, float ratio,
+                      int32_t* d_idx, int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok, void* d_workspace, cudaStream_t st) {
+  const int qtiles = (nq + kQT - 1) / kQT;
+  if (use_dynamic(nq, nt, ns) && (size_t)qtiles * sizeof(int) <= kDynCounterBytes) {
+    int* counters = (int*)((uint8_t*)d_workspace + (size_t)ns * nq * 3 * sizeof(int32_t));
+    ORBX_CUDA(cudaMemsetAsync(counters, 0, kDynCounterBytes, st));
+    const int nblocks = (int)((nt + (long long)kDynTiles * kTT - 1) / ((long long)kDynTiles * kTT));
+    knn2_dyn_kernel<<<dim3(qtiles, ns), kQT, 0, st>>>(d_q, nq, d_t, (int)nt, nblocks, counters, (int32_t*)d_workspace);
+    return ORBX_OK;
+  }
+  return launch_knn2(d_q, nq, d_t, nt, per, ns, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace, st);
+}
+
 int hamm_knn2_device(const uint8_t* d_q, int nq, const uint8_t* d_t, long long nt, int th, float ratio, int32_t* d_idx,
                      int32_t* d_d1, int32_t* d_d2, uint8_t* d_ok, void* d_workspace, size_t workspace_bytes, void* stream) {
   // an empty train set (nt == 0: a trailing rank of a small sharded map) is legal and may come with a null pointer
@@ -637,13 +652,7 @@ int hamm_knn2_device(const uint8_t* d_q, int nq, const uint8_t* d_t, long long n
     set_error("workspace too small (see hamm_knn2_workspace_bytes)");
     return ORBX_ERR_CAPACITY;
   }
-  const int qtiles = (nq + kQT - 1) / kQT;
-  if (use_dynamic(nq, nt, ns) && (size_t)qtiles * sizeof(int) <= kDynCounterBytes) {
-    int* counters = (int*)((uint8_t*)d_workspace + (size_t)ns * nq * 3 * sizeof(int32_t));
-    ORBX_CUDA(cudaMemsetAsync(counters, 0, kDynCounterBytes, st));
-    const int nblocks = (int)((nt + (long long)kDynTiles * kTT - 1) / ((long long)kDynTiles * kTT));
-    knn2_dyn_kernel<<<dim3(qtiles, ns), kQT, 0, st>>>(d_q, nq, d_t, (int)nt, nblocks, counters, (int32_t*)d_workspace);
-  } else if (int rc = launch_knn2(d_q, nq, d_t, nt, per, ns, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace, st)) return rc;
+  if (int rc = scan_local(d_q, nq, d_t, nt, per, ns, th, ratio, d_idx, d_d1, d_d2, d_ok, d_workspace, st)) return rc;
   g_hamm_launches++;
   if (ns > 1) {
     const int32_t* part = (const int32_t*)d_workspace;
@@ -789,14 +798,14 @@ int hamm_knn2_sharded_phases_device(const uint8_t* d_q, int nq, const uint8_t* d
   }
   long long per;
   const int ns = pick_splits(nq, nt, &per);
-  if (ns > 1 && (!d_workspace || workspace_bytes < (size_t)ns * nq * 3 * sizeof(int32_t))) {
+  if (ns > 1 && (!d_workspace || workspace_bytes < (size_t)ns * nq * 3 * sizeof(int32_t) + kDynCounterBytes)) {
     set_error("workspace too small (see hamm_knn2_workspace_bytes)");
     return ORBX_ERR_CAPACITY;
   }
   const int parity = epoch & 1;
   if (phases & 1) {
     // local shard: per-split partials (ns > 1) or the shard result in the output arrays (ns == 1), local row indices
-    if (int rc = launch_knn2(d_q, nq, d_t, nt, per, ns, th, ratio, d_idx, d_d1, d_d2, d_ok, (int32_t*)d_workspace, st)) return rc;
+    if (int rc = scan_local(d_q, nq, d_t, nt, per, ns, th, ratio, d_idx, d_d1, d_d2, d_ok, d_workspace, st)) return rc;
     const int32_t* part = (const int32_t*)d_workspace;
     if (ns > 1)
       knn2_merge_scatter_kernel<<<(nq + 127) / 128, 128, 0, st>>>(part, part + 1, part + 2, 3, ns, nq, shard_lo, peers, rank, world,
