@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kQT) knn2_kernel(const uint8_t* __restrict__ q
 // (cycle stamps of the static-split kernel on 1k x 2M rows: all 1176 CTAs start within 0.4 us, the first one is done after
 // 0.79 ms, the median after 1.80 ms, the last after 2.89 ms), so SMs run out of resident warps long before the kernel ends: 21
 // resident warps per SM on average against 32 for the frame-pair kernel, whose grid keeps refilling the SMs.  Here the rows
-// are handed out in blocks of kDynTiles tiles (2 measured best: 799.5 Gmatch/s against 793.5 at 4) from one counter per query tile: a CTA that gets ahead simply scans more
+// are handed out in blocks of kDynTiles tiles (2 or 4: 793 ... 800 Gmatch/s, inside the run-to-run spread) from one counter per query tile: a CTA that gets ahead simply scans more
 // blocks, and all CTAs finish within one block of each other.  A CTA's blocks are not contiguous, so its keys carry the row
 // index relative to the whole set (nt < 2^23) and the merge breaks distance ties by index.
 #ifndef ORBX_HAMM_DYN_TILES
@@ -190,20 +190,58 @@ __global__ void __launch_bounds__(kQT) knn2_dyn_kernel(const uint8_t* __restrict
                                                        int nblocks, int* __restrict__ counters, int32_t* __restrict__ part) {
   __shared__ __align__(128) uint4 tile[kStages * kTT * 2];
   __shared__ __align__(8) uint64_t full[kStages];
-  __shared__ int s_blk;
-  const TileRing ring{tile, full};
-  const int i = blockIdx.x * kQT + threadIdx.x;
+  __shared__ int s_base[kStages], s_cnt[kStages];     // first row / rows of the tile in each ring slot (0 rows: no more work)
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * kQT + tid;
   uint32_t q[8];
   load_query(q, qs, i, nq);
   uint32_t k1 = kKeyInit, k2 = kKeyInit;
   constexpr int kRows = kDynTiles * kTT;
-  for (;;) {
-    if (threadIdx.x == 0) s_blk = atomicAdd(&counters[blockIdx.x], 1);
-    __syncthreads();
-    const int blk = s_blk;
-    if (blk >= nblocks) break;
-    const int r0 = blk * kRows;
-    scan_train(q, train + (size_t)r0 * 32, min(kRows, nt - r0), ring, k1, k2, r0);   // ends with a CTA barrier: s_blk is free again
+  // The tile ring never drains between blocks: the producer (thread 0) takes the next block from the counter as soon as the
+  // current one has no tile left to request, so the stream of tiles is continuous until the counter runs out.
+  int curBlk = -1, tileInBlk = kDynTiles;
+  bool done = false;
+  auto produce = [&](int slot) {                      // thread 0 only
+    for (;;) {
+      if (done) { s_cnt[slot] = 0; return; }
+      if (tileInBlk == kDynTiles) {
+        curBlk = atomicAdd(&counters[blockIdx.x], 1);
+        tileInBlk = 0;
+        if (curBlk >= nblocks) { done = true; continue; }
+      }
+      const int r0 = curBlk * kRows + tileInBlk * kTT, c = min(kTT, nt - r0);
+      if (c <= 0) { tileInBlk = kDynTiles; continue; }   // ragged last block
+      ++tileInBlk;
+      s_base[slot] = r0; s_cnt[slot] = c;
+      mbar_expect_tx(&full[slot], (uint32_t)c * 32u);
+      bulk_g2s(tile + (size_t)slot * kTT * 2, train + (size_t)r0 * 32, (uint32_t)c * 32u, &full[slot]);
+      return;
+    }
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < kStages; ++s) produce(s);
+  }
+  __syncthreads();
+  for (int t = 0;; ++t) {
+    const int s = t % kStages;
+    const int cnt = s_cnt[s];
+    if (cnt == 0) break;                               // uniform: the slots are consumed in the order they were filled
+    mbar_wait(&full[s], (uint32_t)((t / kStages) & 1));
+    const uint4* tl = tile + (size_t)s * kTT * 2;
+    const int base = s_base[s];
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const uint4 a = tl[2 * j], b = tl[2 * j + 1];
+      const uint32_t d = (uint32_t)hamming8(q, a, b);
+      top2_update(k1, k2, (d << 23) | (uint32_t)(base + j));
+    }
+    __syncthreads();                                   // everyone is done reading slot s (tile and its two words)
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before async-proxy writes
+      produce(s);
+    }
   }
   if (i >= nq) return;
   const int bd1 = (int)(k1 >> 23), bd2 = (int)(k2 >> 23);
