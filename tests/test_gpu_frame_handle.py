@@ -178,3 +178,29 @@ def test_frame_handle_errors(vo):
     assert L.orbx_search_by_projection_frame_h(h, None, None, 15.0, 40.0, 0, 0, 1, None, None) == -1
     assert L.orbx_frame_destroy(h) == 0 and L.orbx_frame_destroy(None) == 0
     ex.close()
+
+
+def test_frame_create_graph_replay_and_invalidation(vo):
+    """orbx_frame_create captures its device chain into a CUDA graph on the second frame built in a block and replays it from
+    the third on.  The replay must give the oracle's bits, and a different camera, a different image size (new workspace) and
+    the way back must each re-capture instead of replaying a stale graph."""
+    P = oracle.Port()
+    ex = vo.ORBextractor()
+    camB = dict(TUM1, dist=[-0.28, 0.07, 0.0002, 0.00002], bounds=(-8.0, 652.0, -5.0, 489.0))
+    small = dict(fx=258.6, fy=258.2, cx=159.3, cy=127.6, dist=TUM1["dist"], bf=20.0, bounds=(0.0, 320.0, 0.0, 240.0))
+    plan = [(TUM1, 601, 480, 640), (TUM1, 602, 480, 640), (TUM1, 603, 480, 640), (TUM1, 604, 480, 640),     # eager, capture, replay x2
+            (camB, 601, 480, 640), (camB, 605, 480, 640),                                                     # other camera: re-capture, replay
+            (small, 606, 240, 320), (small, 607, 240, 320), (small, 608, 240, 320),                          # other size: new workspace
+            (TUM1, 609, 480, 640), (TUM1, 610, 480, 640), (TUM1, 611, 480, 640)]                             # and back
+    for cam, seed, H, W in plan:
+        img = synth.make_frame(seed, H, W)
+        depth = _depth(seed, H, W)
+        fr = vo.Frame(ex, _cam(vo, cam), img, depth)
+        rk, rd = P.extract(img)
+        assert fr.n == len(rk) and fr.kps.tobytes() == rk.tobytes() and np.array_equal(fr.desc, rd), (seed, H)
+        wun, wur, wdp, wstart, wids = P.frame_finish(rk, cam, depth)
+        assert fr.unkps.tobytes() == wun.tobytes() and fr.uright.tobytes() == wur.tobytes() and fr.depth.tobytes() == wdp.tobytes(), seed
+        start, ids = fr.grid()
+        assert np.array_equal(start, wstart) and np.array_equal(ids, wids[:wstart[-1]])
+        fr.close()
+    ex.close()

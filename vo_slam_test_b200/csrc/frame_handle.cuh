@@ -21,6 +21,8 @@ struct orbx_frame {
   // the uRight_ patch of orbx_frame_create runs on the legacy default stream (where the searches run) and reads the mirror in
   // place: the next frame built in this block (on the extractor's own stream) waits for it
   cudaEvent_t patched = nullptr; bool patchPending = false;
+  // the captured device chain of orbx_frame_create for this block (same outputs every time) and what it was captured for
+  cudaGraphExec_t graph = nullptr; unsigned long long graphKey = 0; int graphLaunches = 0;
 };
 
 namespace orbx {

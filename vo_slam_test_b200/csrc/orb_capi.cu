@@ -96,6 +96,8 @@ struct orbx_extractor {
   int32_t *d_midx = nullptr, *d_md1 = nullptr, *d_md2 = nullptr, *d_qf = nullptr; uint8_t* d_mok = nullptr;
   size_t m_frames = 0; int m_cap = 0;
   long long launches = 0;
+  unsigned long long geomEpoch = 0;          // bumped whenever the workspace or the level-0 map is rebuilt: captured graphs of older epochs are stale
+  bool graphBroken = false;                  // stream capture of the single-frame chain failed once: stay eager
   const uint8_t* map0_base = nullptr; size_t map0_row = 0, map0_frame = 0; int map0_n = 0, map0_want = 0;
   // second lane of the device-resident batch path: a sibling extractor (own workspace, own stream) that takes the second
   // half of a large batch concurrently, so that kernel tails and the latency-bound stages of one lane fill under the
@@ -174,6 +176,7 @@ void free_workspace(orbx_extractor* h) {
   h->taps.clear();
   cudaFree(h->d_plan); cudaFree(h->d_pyrSync); h->d_plan = nullptr; h->d_pyrSync = nullptr; h->pyrSyncInts = 0; h->planDirty = true; h->planOk = false;
   h->haveGeom = false; h->chunk = 0;
+  h->geomEpoch++;
   h->map0_base = nullptr; h->map0_n = 0;
   for (int l = 0; l < kMaxLevels; ++l) { h->tma.use[l] = 0; h->patchU[l] = h->patchB[l] = h->blurSrc[l] = false; }
   h->tma.usePatch = 0; h->tma.useBlur = 0;
@@ -476,6 +479,7 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
     // the old ones are drained first; this only happens when the caller switches input buffers.
     if (h->map0_base) cudaDeviceSynchronize();
     encode_level_map(h, 0, d_imgs, rowStride, frameStride, std::max(frame0 + n, h->map0_want));
+    h->geomEpoch++;
     h->map0_base = d_imgs; h->map0_row = rowStride; h->map0_frame = frameStride; h->map0_n = std::max(frame0 + n, h->map0_want);
   }
   const uint8_t* img0 = d_imgs + (size_t)frame0 * frameStride;
@@ -568,6 +572,7 @@ int run_chunk(orbx_extractor* h, const uint8_t* d_imgs, size_t rowStride, size_t
 void free_frame_block(orbx_frame* f) {
   if (!f) return;
   if (f->patched) cudaEventDestroy(f->patched);
+  if (f->graph) cudaGraphExecDestroy(f->graph);
   cudaFree(f->d_block);
   if (f->h_mirror) cudaFreeHost(f->h_mirror);
   delete f;
@@ -1188,13 +1193,64 @@ int orbx_frame_create(orbx_handle h, const orbx_camera* cam, const uint8_t* img,
   // copies together.  The kernel therefore leaves depth_/uRight_ at -1; after the one packed copy down the host samples the
   // image at the ORIGINAL keypoints with the reference's float->int truncation, computes uRight_ = unKp.x - bf/d in IEEE float
   // (one division, one subtraction: no contraction possible) and sends the 4 KB of uRight_ back for the searches.
-  int rc = orbx_extract_batch_device(h, h->d_in, 1, w, height, pitch, fbytes, f->d_kps, f->d_desc, f->cap, f->d_count, st);
-  if (rc == ORBX_OK)
-    rc = frame_finish_launch(cam, f->d_kps, f->d_count, 1, f->cap, nullptr, w, height, sizeof(float) * (size_t)w, 0,
-                             f->d_unkps, f->d_uright, f->d_depth, f->d_cellStart, f->d_ids, f->d_feat, f->d_angle, st);
+  // The device chain of one frame (14 launches on two streams, their events, the finish kernel and the copy down) is the same
+  // work descriptor for every frame built in this block with this camera: it is captured ONCE into a CUDA graph and replayed,
+  // which takes the per-launch cost off the host and off the GPU front end.  Captured on the second frame of a block (the first
+  // call runs eagerly: it may still configure the workspace and describe the staging buffer, which a capture cannot contain).
+  static const bool graphsOn = env_int("ORBX_GRAPH", 1) != 0;
+  unsigned long long key = 1469598103934665603ull;
+  {
+    auto mix = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; for (size_t i = 0; i < n; ++i) { key ^= b[i]; key *= 1099511628211ull; } };
+    mix(cam, sizeof(*cam)); mix(&w, sizeof(w)); mix(&height, sizeof(height)); mix(&h->geomEpoch, sizeof(h->geomEpoch));
+  }
+  const bool steady = graphsOn && !h->graphBroken && h->haveGeom && h->G.W == w && h->G.H == height && h->map0_base == h->d_in &&
+                      h->map0_row == pitch && h->map0_frame == fbytes && h->auxStream != nullptr;
+  int rc = ORBX_OK;
+  bool replayed = false;
+  if (steady && f->graph && f->graphKey == key) {
+    e = cudaGraphLaunch(f->graph, st);
+    if (e == cudaSuccess) { replayed = true; h->launches += f->graphLaunches; }
+    else { cudaGetLastError(); cudaGraphExecDestroy(f->graph); f->graph = nullptr; h->graphBroken = true; }
+  }
+  if (!replayed) {
+    const bool capture = steady && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    const long long l0 = h->launches;
+    rc = orbx_extract_batch_device(h, h->d_in, 1, w, height, pitch, fbytes, f->d_kps, f->d_desc, f->cap, f->d_count, st);
+    if (rc == ORBX_OK)
+      rc = frame_finish_launch(cam, f->d_kps, f->d_count, 1, f->cap, nullptr, w, height, sizeof(float) * (size_t)w, 0,
+                               f->d_unkps, f->d_uright, f->d_depth, f->d_cellStart, f->d_ids, f->d_feat, f->d_angle, st);
+    if (rc == ORBX_OK) {
+      h->launches += 1;
+      if (cudaMemcpyAsync(f->h_mirror, f->d_block, f->packed_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = ORBX_ERR_CUDA;
+    }
+    if (capture) {
+      cudaGraph_t g = nullptr;
+      cudaGraphExec_t ge = nullptr;
+      e = cudaStreamEndCapture(st, &g);
+      if (e == cudaSuccess && rc == ORBX_OK && g) e = cudaGraphInstantiate(&ge, g, 0);
+      if (g) cudaGraphDestroy(g);
+      if (e == cudaSuccess && rc == ORBX_OK && ge) {
+        if (f->graph) cudaGraphExecDestroy(f->graph);
+        f->graph = ge; f->graphKey = key; f->graphLaunches = (int)(h->launches - l0);
+        e = cudaGraphLaunch(f->graph, st);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = ORBX_ERR_CUDA; }
+      } else {
+        // this driver cannot capture the chain (or a launch failed inside it): run eagerly from now on
+        cudaGetLastError();
+        if (ge) cudaGraphExecDestroy(ge);
+        h->graphBroken = true;
+        if (rc == ORBX_OK) {
+          rc = orbx_extract_batch_device(h, h->d_in, 1, w, height, pitch, fbytes, f->d_kps, f->d_desc, f->cap, f->d_count, st);
+          if (rc == ORBX_OK)
+            rc = frame_finish_launch(cam, f->d_kps, f->d_count, 1, f->cap, nullptr, w, height, sizeof(float) * (size_t)w, 0,
+                                     f->d_unkps, f->d_uright, f->d_depth, f->d_cellStart, f->d_ids, f->d_feat, f->d_angle, st);
+          if (rc == ORBX_OK && cudaMemcpyAsync(f->h_mirror, f->d_block, f->packed_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = ORBX_ERR_CUDA;
+        }
+      }
+    }
+  }
   if (rc == ORBX_OK) {
-    h->launches += 1;
-    e = cudaMemcpyAsync(f->h_mirror, f->d_block, f->packed_bytes, cudaMemcpyDeviceToHost, st);
+    e = cudaSuccess;
     const auto tc1 = std::chrono::steady_clock::now();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (phaseTiming) {
