@@ -283,7 +283,10 @@ __device__ __forceinline__ void resize_tma_tile(const CUtensorMap* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(128) resize_tma_kernel(const CUtensorMap* __restrict__ map, int z0, int sh, uint8_t* __restrict__ dst,
+#ifndef ORBX_RZ_MINB
+#define ORBX_RZ_MINB 1
+#endif
+__global__ void __launch_bounds__(128, ORBX_RZ_MINB) resize_tma_kernel(const CUtensorMap* __restrict__ map, int z0, int sh, uint8_t* __restrict__ dst,
                                                          int dw, int dh, int dpitch, size_t dframe, ResizeTaps T,
                                                          const __grid_constant__ ResizeTma R) {
   pdl_prologue();
@@ -1734,7 +1737,10 @@ __global__ void __launch_bounds__(128, 8) blur_walk_kernel(const __grid_constant
 // interior code path on LDS: one specialisation instead of five (instruction-cache misses were the top stall of
 // blur_walk_kernel) and no dependent global-load latency in the walk.
 static_assert(kBtBoxH == kBwTileH + 6 && kBtBoxW == 64 + 32, "blur box");
-__global__ void __launch_bounds__(128, 8) blur_tma_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM) {
+#ifndef ORBX_BLUR_MINB
+#define ORBX_BLUR_MINB 8
+#endif
+__global__ void __launch_bounds__(128, ORBX_BLUR_MINB) blur_tma_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM) {
   pdl_prologue();
   __shared__ __align__(128) uint8_t tile[kBtBoxH * kBtBoxW];
   __shared__ __align__(8) uint64_t bar;
@@ -2073,7 +2079,10 @@ __device__ __forceinline__ int od_round(float v) {                        // cvR
   return __float_as_int(__fadd_rn(v, 12582912.f));
 }
 
-__global__ void __launch_bounds__(32 * kOdWarps) orient_desc_tma_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM,
+#ifndef ORBX_OD_MINB
+#define ORBX_OD_MINB 7          // 72 registers, 7 CTAs per SM: 2.53 -> 2.47 ms per 4096 frames (6: 2.50, 8: 2.52)
+#endif
+__global__ void __launch_bounds__(32 * kOdWarps, ORBX_OD_MINB) orient_desc_tma_kernel(const __grid_constant__ Geom G, const Bufs B, const __grid_constant__ TmaSet TM,
                                                                         orbx_keypoint* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
                                                                         int cap, int32_t* __restrict__ counts_out, int frame0, int K) {
   pdl_prologue();
