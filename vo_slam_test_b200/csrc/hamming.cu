@@ -26,6 +26,9 @@ namespace orbx {
 #ifndef ORBX_HAMM_STAGES
 #define ORBX_HAMM_STAGES 3
 #endif
+#ifndef ORBX_HAMM_MINB
+#define ORBX_HAMM_MINB 1          // min CTAs per SM of the POPC kernels (A/B)
+#endif
 #ifndef ORBX_HAMM_TRACE
 #define ORBX_HAMM_TRACE 0
 #endif
@@ -137,7 +140,7 @@ __device__ __forceinline__ uint8_t accept(int d1, int d2, int th, float ratio) {
 
 // grid (ceil(nq/kQT), nsplit).  Split s scans train rows [s*per, min((s+1)*per, nt)).
 // nsplit == 1: final outputs are written directly; otherwise partial (idx, d1, d2) go to the workspace.
-__global__ void __launch_bounds__(kQT) knn2_kernel(const uint8_t* __restrict__ qs, int nq, const uint8_t* __restrict__ train,
+__global__ void __launch_bounds__(kQT, ORBX_HAMM_MINB) knn2_kernel(const uint8_t* __restrict__ qs, int nq, const uint8_t* __restrict__ train,
                                                    long long nt, long long per, int th, float ratio, int32_t* idx,
                                                    int32_t* d1, int32_t* d2, uint8_t* ok, int32_t* part) {
   __shared__ __align__(128) uint4 tile[kStages * kTT * 2];
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(kQT) knn2_kernel(const uint8_t* __restrict__ q
 #define ORBX_HAMM_DYN_TILES 2
 #endif
 constexpr int kDynTiles = ORBX_HAMM_DYN_TILES;
-__global__ void __launch_bounds__(kQT) knn2_dyn_kernel(const uint8_t* __restrict__ qs, int nq, const uint8_t* __restrict__ train, int nt,
+__global__ void __launch_bounds__(kQT, ORBX_HAMM_MINB) knn2_dyn_kernel(const uint8_t* __restrict__ qs, int nq, const uint8_t* __restrict__ train, int nt,
                                                        int nblocks, int* __restrict__ counters, int32_t* __restrict__ part) {
   __shared__ __align__(128) uint4 tile[kStages * kTT * 2];
   __shared__ __align__(8) uint64_t full[kStages];
@@ -268,7 +271,7 @@ __global__ void knn2_merge_kernel(const int32_t* __restrict__ pidx, const int32_
 }
 
 // Frame-to-frame matching over extractor output: pair p = (query frame qf[p], train frame tf[p]).
-__global__ void __launch_bounds__(kQT) knn2_pairs_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ counts,
+__global__ void __launch_bounds__(kQT, ORBX_HAMM_MINB) knn2_pairs_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ counts,
                                                          int cap, const int32_t* __restrict__ qf, const int32_t* __restrict__ tf,
                                                          int th, float ratio, int32_t* idx, int32_t* d1, int32_t* d2,
                                                          uint8_t* ok) {
